@@ -1,0 +1,190 @@
+"""Host-side mirror of the reference operator surface for the hot path.
+
+Same names, argument meaning and error behaviour as the reference:
+  * ``Aggregator``            <- ``bm::aggregator<BV>``            (reference src/bmaggregator.h:56-1060)
+        add / reset / set_optimization / combine_or / combine_and / combine_and_sub
+  * ``bit_and / bit_or / bit_xor / bit_sub`` <- 3-operand ``bvector::bit_*`` (src/bm.h:1745-1850)
+  * ``count_and / count_or / count_xor / count_sub`` <- ``bm::count_*`` (src/bmalgo.h:48-51)
+  * ``RSIndex / build_rs_index / count_to / select`` <- ``rs_index``, ``bvector::build_rs_index``,
+        ``count_to``, ``select`` (src/bmrs.h:40-155, src/bm.h:2531,3120,5350)
+
+Everything below the signatures is: pack the host block trees into the column-major arena, call the
+C ABI (libbmb200.so, CUDA), unpack the result.  No set algebra happens in Python.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import capi
+from .capi import (BLK_NULL, F_COUNT_ONLY, F_OPT_COMPRESS, F_OPT_NONE, OP_AND, OP_AND_SUB, OP_OR, OP_XOR)
+from .hostfmt import BVector, PackedSet, result_to_bvector
+
+OPT_NONE = 0       # bvector::opt_none
+OPT_COMPRESS = 3   # bvector::opt_compress (reference src/bm.h:132-138)
+
+
+def _run(ctx, vectors, op, g0, g1, opt_mode, count_only=False):
+    n_blocks = max(v.n_blocks for v in vectors)
+    dset = capi.DeviceSet.upload_vectors(ctx, vectors, n_blocks)
+    try:
+        flags = (F_OPT_COMPRESS if opt_mode else F_OPT_NONE) | (F_COUNT_ONLY if count_only else 0)
+        res = capi.aggregate(ctx, dset, op, g0, g1, flags)
+        try:
+            total, any_ = res.total()
+            if count_only:
+                return None, total, any_
+            kind, off, bits, gaps = res.fetch()
+            return result_to_bvector(kind, off, bits, gaps), total, any_
+        finally:
+            res.free()
+    finally:
+        dset.free()
+
+
+class Aggregator:
+    """``bm::aggregator<bvector>`` with the block algebra on the GPU.
+
+    Group 0 is the OR / AND group, group 1 the SUB group (reference src/bmaggregator.h:383-388).
+    The target is *replaced* (resize_target(init_clear=true), src/bmaggregator.h:2215-2219).
+    """
+
+    def __init__(self, ctx: capi.Context | None = None):
+        self.ctx = ctx or capi.default_context()
+        self._groups: list[list[BVector]] = [[], []]
+        self._opt = OPT_NONE
+
+    def set_optimization(self, opt: int = OPT_COMPRESS):
+        self._opt = opt
+
+    def add(self, bv: BVector, agr_group: int = 0) -> int:
+        if agr_group not in (0, 1):
+            raise ValueError("agr_group must be 0 or 1")
+        self._groups[agr_group].append(bv)
+        return len(self._groups[agr_group])
+
+    def reset(self):
+        self._groups = [[], []]
+
+    # --- C-style entry points (src/bmaggregator.h:503-540) ---
+    def combine_or(self, bv_src: list[BVector] | None = None) -> BVector:
+        src = self._groups[0] if bv_src is None else bv_src
+        if not src:
+            return BVector(0)                                  # n == 0 => clear(), :1105-1109
+        res, _, _ = _run(self.ctx, src, OP_OR, np.arange(len(src)), None, self._opt)
+        return res
+
+    def combine_and(self, bv_src: list[BVector] | None = None) -> BVector:
+        if bv_src is None:
+            # member form routes through combine_and_sub with an empty SUB group, :1030-1039
+            res, _ = self.combine_and_sub(self._groups[0], [], any_=False)
+            return res
+        if not bv_src:
+            return BVector(0)
+        res, _, _ = _run(self.ctx, bv_src, OP_AND, np.arange(len(bv_src)), None, self._opt)
+        return res
+
+    def combine_and_sub(self, bv_src_and: list[BVector] | None = None, bv_src_sub: list[BVector] | None = None,
+                        any_: bool = False) -> tuple[BVector, bool]:
+        a = self._groups[0] if bv_src_and is None else bv_src_and
+        s = self._groups[1] if bv_src_sub is None else bv_src_sub
+        if not a:
+            return BVector(0), False                           # empty AND group => clear + false, :1170-1174
+        vecs = list(a) + list(s)
+        # combine_and_sub always stores through opt_copy_bit_block(opt_compress), :1209
+        res, total, found = _run(self.ctx, vecs, OP_AND_SUB, np.arange(len(a)),
+                                 np.arange(len(a), len(vecs)), OPT_COMPRESS)
+        return res, found
+
+    def count_and_sub(self, bv_src_and, bv_src_sub) -> int:
+        """counts-only mode of the pipeline (src/bmaggregator.h:1397-1398)."""
+        if not bv_src_and:
+            return 0
+        vecs = list(bv_src_and) + list(bv_src_sub)
+        _, total, _ = _run(self.ctx, vecs, OP_AND_SUB, np.arange(len(bv_src_and)),
+                           np.arange(len(bv_src_and), len(vecs)), OPT_NONE, count_only=True)
+        return total
+
+
+def _binop(op, a: BVector, b: BVector, opt_mode: int, ctx=None):
+    ctx = ctx or capi.default_context()
+    if op == "sub":
+        res, _, _ = _run(ctx, [a, b], OP_AND_SUB, [0], [1], opt_mode)
+    else:
+        res, _, _ = _run(ctx, [a, b], {"and": OP_AND, "or": OP_OR, "xor": OP_XOR}[op], [0, 1], None, opt_mode)
+    return res
+
+
+def bit_and(a: BVector, b: BVector, opt_mode: int = OPT_NONE, ctx=None) -> BVector:
+    return _binop("and", a, b, opt_mode, ctx)
+
+
+def bit_or(a: BVector, b: BVector, opt_mode: int = OPT_NONE, ctx=None) -> BVector:
+    return _binop("or", a, b, opt_mode, ctx)
+
+
+def bit_xor(a: BVector, b: BVector, opt_mode: int = OPT_NONE, ctx=None) -> BVector:
+    return _binop("xor", a, b, opt_mode, ctx)
+
+
+def bit_sub(a: BVector, b: BVector, opt_mode: int = OPT_NONE, ctx=None) -> BVector:
+    return _binop("sub", a, b, opt_mode, ctx)
+
+
+def _count(op, a, b, ctx=None) -> int:
+    ctx = ctx or capi.default_context()
+    if op == "sub":
+        return _run(ctx, [a, b], OP_AND_SUB, [0], [1], OPT_NONE, count_only=True)[1]
+    return _run(ctx, [a, b], {"and": OP_AND, "or": OP_OR, "xor": OP_XOR}[op], [0, 1], None, OPT_NONE, count_only=True)[1]
+
+
+def count_and(a, b, ctx=None) -> int:
+    return _count("and", a, b, ctx)
+
+
+def count_or(a, b, ctx=None) -> int:
+    return _count("or", a, b, ctx)
+
+
+def count_xor(a, b, ctx=None) -> int:
+    return _count("xor", a, b, ctx)
+
+
+def count_sub(a, b, ctx=None) -> int:
+    return _count("sub", a, b, ctx)
+
+
+class RSIndex:
+    """``bvector::rs_index_type`` built on the GPU; answers batched count_to / select."""
+
+    def __init__(self, bv: BVector, ctx: capi.Context | None = None):
+        self.ctx = ctx or capi.default_context()
+        self._dset = capi.DeviceSet.upload_vectors(self.ctx, [bv], bv.n_blocks)
+        self._rs = capi.DeviceRS(self.ctx, self._dset, 0)
+        self.n_blocks = bv.n_blocks
+
+    def count(self) -> int:
+        return self._rs.total()
+
+    def fields(self):
+        """(bcount, sub_count, sblock_count) as register_super_block receives them."""
+        return self._rs.export()
+
+    def count_to(self, pos) -> np.ndarray:
+        """Inclusive rank: bits set in [0, pos] (bvector::count_to)."""
+        return self._rs.rank(np.atleast_1d(pos))
+
+    def rank_corrected(self, pos, bit_at_pos) -> np.ndarray:
+        """count_to minus the bit at pos (bvector::rank_corrected src/bm.h:3229)."""
+        return self.count_to(pos) - np.asarray(bit_at_pos, dtype=np.uint64)
+
+    def select(self, rank):
+        """1-based select; returns (pos, found) (bvector::select)."""
+        return self._rs.select(np.atleast_1d(rank))
+
+    def close(self):
+        self._rs.free()
+        self._dset.free()
+
+
+def build_rs_index(bv: BVector, ctx=None) -> RSIndex:
+    return RSIndex(bv, ctx)

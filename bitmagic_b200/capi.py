@@ -1,0 +1,385 @@
+"""ctypes binding of libbmb200.so (the C ABI declared in include/bmb200.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is no
+fallback: if the library is missing, or no B200 is present, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libbmb200.so"
+
+# ---- constants (mirror include/bmb200.h) ----
+OK = 0
+ERR_BADALLOC, ERR_BADARG, ERR_RANGE, ERR_RS_IDX_MISSING = 1, 2, 3, 7
+ERR_CUDA, ERR_NODEVICE = 200, 201
+BLOCK_WORDS, BLOCK_BYTES, BLOCK_BITS = 2048, 8192, 65536
+GAP_MAX_WORDS, GAP_THRESHOLD, GAP_UNIT_WORDS, SUPERBLOCK = 1280, 1276, 8, 256
+BLK_NULL, BLK_FULL, BLK_BIT, BLK_GAP = 0, 1, 2, 3
+OP_OR, OP_AND, OP_AND_SUB, OP_XOR = 0, 1, 2, 3
+F_COUNT_ONLY, F_OPT_NONE, F_OPT_COMPRESS = 1, 0, 2
+
+# every symbol include/bmb200.h declares (checked by tests/test_cabi_symbols.py)
+SYMBOLS = [
+    "bmb200_init", "bmb200_destroy", "bmb200_error_msg", "bmb200_last_error", "bmb200_ctx_set_stream",
+    "bmb200_ctx_get_stream", "bmb200_ctx_sync", "bmb200_ctx_launch_count", "bmb200_device_info",
+    "bmb200_set_upload", "bmb200_set_upload_vectors", "bmb200_set_adopt_device", "bmb200_set_info",
+    "bmb200_set_column_sizes", "bmb200_set_download", "bmb200_set_device_ptrs", "bmb200_set_free",
+    "bmb200_synth_set", "bmb200_aggregate", "bmb200_result_optimize", "bmb200_result_total",
+    "bmb200_result_fetch_meta", "bmb200_result_sizes", "bmb200_result_fetch", "bmb200_result_device_ptrs",
+    "bmb200_result_free", "bmb200_aggregate_host", "bmb200_rs_build", "bmb200_rs_export", "bmb200_rs_total",
+    "bmb200_rank_batch", "bmb200_select_batch", "bmb200_rank_batch_dev", "bmb200_select_batch_dev",
+    "bmb200_rs_free",
+]
+
+
+class PackedSetC(C.Structure):
+    _fields_ = [
+        ("n_vec", C.c_uint32), ("n_blocks", C.c_uint32),
+        ("desc", C.c_void_p), ("bit_base", C.c_void_p), ("gap_base", C.c_void_p),
+        ("bit_pool", C.c_void_p), ("gap_pool", C.c_void_p),
+    ]
+
+
+class VecBlocksC(C.Structure):
+    _fields_ = [("n_blocks", C.c_uint32), ("kind", C.c_void_p), ("ptr", C.c_void_p)]
+
+
+class AggArgsC(C.Structure):
+    _fields_ = [
+        ("op", C.c_int32), ("flags", C.c_uint32),
+        ("group0", C.c_void_p), ("n0", C.c_uint32),
+        ("group1", C.c_void_p), ("n1", C.c_uint32),
+        ("nb_from", C.c_uint32), ("nb_to", C.c_uint32),
+    ]
+
+
+class ResultMetaC(C.Structure):
+    _fields_ = [("kind", C.c_void_p), ("popcnt", C.c_void_p), ("digest", C.c_void_p), ("nruns", C.c_void_p)]
+
+
+class BMB200Error(RuntimeError):
+    def __init__(self, code: int, what: str, detail: str = ""):
+        self.code = code
+        super().__init__(f"{what}: error {code} ({_msg(code)})" + (f" [{detail}]" if detail else ""))
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libbmb200.so; fail loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "bitmagic_b200 has no CPU fallback.")
+        _lib = C.CDLL(str(LIB_PATH))
+        _lib.bmb200_error_msg.restype = C.c_char_p
+        _lib.bmb200_error_msg.argtypes = [C.c_int]
+        for name in SYMBOLS:
+            if name != "bmb200_error_msg":
+                getattr(_lib, name).restype = C.c_int
+    return _lib
+
+
+def _msg(code: int) -> str:
+    try:
+        return lib().bmb200_error_msg(code).decode()
+    except Exception:  # pragma: no cover
+        return "?"
+
+
+def ptr(a) -> C.c_void_p:
+    if a is None:
+        return C.c_void_p(0)
+    return C.c_void_p(a.ctypes.data)
+
+
+def packed_c(n_vec, n_blocks, desc, bit_base, gap_base, bit_pool, gap_pool) -> PackedSetC:
+    return PackedSetC(int(n_vec), int(n_blocks), ptr(desc), ptr(bit_base), ptr(gap_base),
+                      ptr(bit_pool) if bit_pool is not None and bit_pool.size else C.c_void_p(0),
+                      ptr(gap_pool) if gap_pool is not None and gap_pool.size else C.c_void_p(0))
+
+
+class Context:
+    """One per process per GPU (bmb200_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p(0)
+        rc = lib().bmb200_init(int(device), C.byref(self._h))
+        if rc != OK:
+            raise BMB200Error(rc, "bmb200_init")
+        self.device = device
+
+    def check(self, rc: int, what: str):
+        if rc != OK:
+            buf = C.create_string_buffer(512)
+            lib().bmb200_last_error(self._h, buf, C.c_size_t(512))
+            raise BMB200Error(rc, what, buf.value.decode(errors="replace"))
+
+    def close(self):
+        if self._h:
+            lib().bmb200_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self.check(lib().bmb200_ctx_sync(self._h), "ctx_sync")
+
+    def set_stream(self, cuda_stream: int):
+        self.check(lib().bmb200_ctx_set_stream(self._h, C.c_void_p(int(cuda_stream))), "ctx_set_stream")
+
+    def get_stream(self) -> int:
+        s = C.c_void_p(0)
+        self.check(lib().bmb200_ctx_get_stream(self._h, C.byref(s)), "ctx_get_stream")
+        return int(s.value or 0)
+
+    def launch_count(self) -> int:
+        n = C.c_uint64(0)
+        self.check(lib().bmb200_ctx_launch_count(self._h, C.byref(n)), "launch_count")
+        return int(n.value)
+
+    def device_info(self) -> dict:
+        sm, ma, mi, hbm = C.c_int(0), C.c_int(0), C.c_int(0), C.c_uint64(0)
+        self.check(lib().bmb200_device_info(self._h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(hbm)), "device_info")
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "hbm_bytes": hbm.value}
+
+
+_default_ctx: dict[int, Context] = {}
+
+
+def default_context(device: int | None = None) -> Context:
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class DeviceSet:
+    """Device-resident packed column-major set (bmb200_set)."""
+
+    def __init__(self, ctx: Context, handle: C.c_void_p):
+        self.ctx, self._h = ctx, handle
+        nv, nb, nbit, ngap = C.c_uint32(0), C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
+        ctx.check(lib().bmb200_set_info(handle, C.byref(nv), C.byref(nb), C.byref(nbit), C.byref(ngap)), "set_info")
+        self.n_vec, self.n_blocks = nv.value, nb.value
+        self.n_bit_blocks, self.n_gap_units = nbit.value, ngap.value
+
+    @classmethod
+    def upload(cls, ctx: Context, ps) -> "DeviceSet":
+        h = C.c_void_p(0)
+        c = packed_c(ps.n_vec, ps.n_blocks, ps.desc, ps.bit_base, ps.gap_base, ps.bit_pool, ps.gap_pool)
+        ctx.check(lib().bmb200_set_upload(ctx._h, C.byref(c), C.byref(h)), "set_upload")
+        ctx.sync()   # the host arrays may be released by the caller right after
+        return cls(ctx, h)
+
+    @classmethod
+    def upload_vectors(cls, ctx: Context, vectors, n_blocks: int | None = None) -> "DeviceSet":
+        """Gather per-vector block trees (hostfmt.BVector) through bmb200_set_upload_vectors."""
+        if n_blocks is None:
+            n_blocks = max(v.n_blocks for v in vectors)
+        arr = (VecBlocksC * len(vectors))()
+        keep = []
+        for i, v in enumerate(vectors):
+            kind = np.ascontiguousarray(v.kind, dtype=np.uint8)
+            ptrs = np.zeros(v.n_blocks, dtype=np.uint64)
+            for nb in range(v.n_blocks):
+                if kind[nb] == BLK_BIT or kind[nb] == BLK_GAP:
+                    blk = v.blocks[nb]
+                    keep.append(blk)
+                    ptrs[nb] = blk.ctypes.data
+            keep += [kind, ptrs]
+            arr[i] = VecBlocksC(v.n_blocks, ptr(kind), ptr(ptrs))
+        h = C.c_void_p(0)
+        ctx.check(lib().bmb200_set_upload_vectors(ctx._h, len(vectors), int(n_blocks), arr, C.byref(h)), "set_upload_vectors")
+        return cls(ctx, h)
+
+    @classmethod
+    def synth(cls, ctx: Context, n_vec: int, n_blocks: int, density, seed, optimize: bool) -> "DeviceSet":
+        d = np.ascontiguousarray(density, dtype=np.float64)
+        s = np.ascontiguousarray(seed, dtype=np.uint64)
+        assert d.size == n_vec and s.size == n_vec
+        h = C.c_void_p(0)
+        ctx.check(lib().bmb200_synth_set(ctx._h, int(n_vec), int(n_blocks), ptr(d), ptr(s), int(bool(optimize)), C.byref(h)), "synth_set")
+        return cls(ctx, h)
+
+    def column_sizes(self, nb_from: int, nb_to: int) -> tuple[int, int]:
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self.ctx.check(lib().bmb200_set_column_sizes(self._h, int(nb_from), int(nb_to), C.byref(a), C.byref(b)), "set_column_sizes")
+        return a.value, b.value
+
+    def download(self, nb_from: int = 0, nb_to: int | None = None):
+        """Columns [nb_from, nb_to) as a host PackedSet."""
+        from .hostfmt import PackedSet
+        nb_to = self.n_blocks if nb_to is None else nb_to
+        nbit, ngap = self.column_sizes(nb_from, nb_to)
+        nc = nb_to - nb_from
+        desc = np.empty(nc * self.n_vec, dtype=np.uint32)
+        bb = np.empty(nc + 1, dtype=np.uint64)
+        gb = np.empty(nc + 1, dtype=np.uint64)
+        bp = np.empty(nbit * BLOCK_WORDS, dtype=np.uint32)
+        gp = np.empty(ngap * GAP_UNIT_WORDS, dtype=np.uint16)
+        self.ctx.check(lib().bmb200_set_download(self._h, int(nb_from), int(nb_to), ptr(desc), ptr(bb), ptr(gb),
+                                                 ptr(bp) if nbit else C.c_void_p(0), ptr(gp) if ngap else C.c_void_p(0)),
+                       "set_download")
+        return PackedSet(self.n_vec, nc, desc, bb, gb, bp, gp)
+
+    def device_ptrs(self) -> PackedSetC:
+        c = PackedSetC()
+        self.ctx.check(lib().bmb200_set_device_ptrs(self._h, C.byref(c)), "set_device_ptrs")
+        return c
+
+    def stored_bytes(self) -> int:
+        """Algorithmic source bytes: 8192 per bit-block + the 16-byte units of the GAP blocks."""
+        return self.n_bit_blocks * BLOCK_BYTES + self.n_gap_units * GAP_UNIT_WORDS * 2
+
+    def free(self):
+        if self._h:
+            lib().bmb200_set_free(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceResult:
+    """Device-resident aggregation result (bmb200_result)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self._h = C.c_void_p(0)
+        self.n_cols = 0
+
+    def total(self) -> tuple[int, bool]:
+        t, a = C.c_uint64(0), C.c_int(0)
+        self.ctx.check(lib().bmb200_result_total(self._h, C.byref(t), C.byref(a)), "result_total")
+        return t.value, bool(a.value)
+
+    def meta(self):
+        n = self.n_cols
+        kind = np.empty(n, np.uint8); pop = np.empty(n, np.uint32)
+        dig = np.empty(n, np.uint64); nr = np.empty(n, np.uint32)
+        m = ResultMetaC(ptr(kind), ptr(pop), ptr(dig), ptr(nr))
+        self.ctx.check(lib().bmb200_result_fetch_meta(self._h, C.byref(m)), "result_fetch_meta")
+        return kind, pop, dig, nr
+
+    def fetch(self):
+        """(kind[n], off[n], bits[n_bit*2048], gaps[n_gap_words]) -- per-vector flat form."""
+        nb, ng = C.c_uint64(0), C.c_uint64(0)
+        self.ctx.check(lib().bmb200_result_sizes(self._h, C.byref(nb), C.byref(ng)), "result_sizes")
+        kind = np.empty(self.n_cols, np.uint8); off = np.empty(self.n_cols, np.uint64)
+        bits = np.empty(nb.value * BLOCK_WORDS, np.uint32); gaps = np.empty(ng.value, np.uint16)
+        self.ctx.check(lib().bmb200_result_fetch(self._h, ptr(kind), ptr(off),
+                                                 ptr(bits) if nb.value else C.c_void_p(0),
+                                                 ptr(gaps) if ng.value else C.c_void_p(0)), "result_fetch")
+        return kind, off, bits, gaps
+
+    def device_ptrs(self) -> dict:
+        b, p, d, f, n = C.c_void_p(0), C.c_void_p(0), C.c_void_p(0), C.c_void_p(0), C.c_uint32(0)
+        self.ctx.check(lib().bmb200_result_device_ptrs(self._h, C.byref(b), C.byref(p), C.byref(d), C.byref(f), C.byref(n)), "result_device_ptrs")
+        return {"blocks": b.value or 0, "popcnt": p.value or 0, "digest": d.value or 0, "kind": f.value or 0, "n_cols": n.value}
+
+    def free(self):
+        if self._h:
+            lib().bmb200_result_free(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def aggregate(ctx: Context, dset: DeviceSet, op: int, group0, group1=None, flags: int = 0,
+              nb_from: int = 0, nb_to: int = 0, result: DeviceResult | None = None) -> DeviceResult:
+    """bmb200_aggregate: asynchronous launch; the result stays in HBM."""
+    g0 = np.ascontiguousarray(group0, dtype=np.uint32)
+    g1 = np.ascontiguousarray(group1 if group1 is not None else [], dtype=np.uint32)
+    args = AggArgsC(int(op), int(flags), ptr(g0) if g0.size else C.c_void_p(0), g0.size,
+                    ptr(g1) if g1.size else C.c_void_p(0), g1.size, int(nb_from), int(nb_to))
+    res = result if result is not None else DeviceResult(ctx)
+    ctx.check(lib().bmb200_aggregate(ctx._h, dset._h, C.byref(args), C.byref(res._h)), "aggregate")
+    res.n_cols = (nb_to if nb_to else dset.n_blocks) - nb_from
+    return res
+
+
+def aggregate_host(ctx: Context, ps, op: int, group0, group1=None, flags: int = 0):
+    """bmb200_aggregate_host: host packed set in, host metadata out (H2D + kernel + D2H in one call)."""
+    g0 = np.ascontiguousarray(group0, dtype=np.uint32)
+    g1 = np.ascontiguousarray(group1 if group1 is not None else [], dtype=np.uint32)
+    args = AggArgsC(int(op), int(flags), ptr(g0) if g0.size else C.c_void_p(0), g0.size,
+                    ptr(g1) if g1.size else C.c_void_p(0), g1.size, 0, 0)
+    n = ps.n_blocks
+    kind = np.empty(n, np.uint8); pop = np.empty(n, np.uint32); dig = np.empty(n, np.uint64); nr = np.empty(n, np.uint32)
+    m = ResultMetaC(ptr(kind), ptr(pop), ptr(dig), ptr(nr))
+    tot = C.c_uint64(0)
+    c = packed_c(ps.n_vec, ps.n_blocks, ps.desc, ps.bit_base, ps.gap_base, ps.bit_pool, ps.gap_pool)
+    ctx.check(lib().bmb200_aggregate_host(ctx._h, C.byref(c), C.byref(args), C.byref(m), C.byref(tot)), "aggregate_host")
+    return kind, pop, dig, nr, tot.value
+
+
+class DeviceRS:
+    """Device-resident rank-select index (bmb200_rs) over one vector of a DeviceSet."""
+
+    def __init__(self, ctx: Context, dset: DeviceSet, vec: int):
+        self.ctx, self.dset, self.vec = ctx, dset, vec
+        self._h = C.c_void_p(0)
+        ctx.check(lib().bmb200_rs_build(ctx._h, dset._h, int(vec), C.byref(self._h)), "rs_build")
+
+    def export(self):
+        nb = self.dset.n_blocks
+        nsb = (nb + 255) // 256
+        bc = np.empty(nb, np.uint32); sc = np.empty(nb, np.uint64); sb = np.empty(nsb + 1, np.uint64)
+        self.ctx.check(lib().bmb200_rs_export(self._h, ptr(bc), ptr(sc), ptr(sb)), "rs_export")
+        return bc, sc, sb
+
+    def total(self) -> int:
+        t = C.c_uint64(0)
+        self.ctx.check(lib().bmb200_rs_total(self._h, C.byref(t)), "rs_total")
+        return t.value
+
+    def rank(self, pos) -> np.ndarray:
+        p = np.ascontiguousarray(pos, dtype=np.uint64)
+        out = np.empty(p.size, np.uint64)
+        self.ctx.check(lib().bmb200_rank_batch(self._h, ptr(p), C.c_uint64(p.size), ptr(out)), "rank_batch")
+        return out
+
+    def select(self, rank) -> tuple[np.ndarray, np.ndarray]:
+        r = np.ascontiguousarray(rank, dtype=np.uint64)
+        pos = np.empty(r.size, np.uint64); found = np.empty(r.size, np.uint8)
+        self.ctx.check(lib().bmb200_select_batch(self._h, ptr(r), C.c_uint64(r.size), ptr(pos), ptr(found)), "select_batch")
+        return pos, found.astype(bool)
+
+    def rank_dev(self, d_pos: int, n: int, d_out: int):
+        self.ctx.check(lib().bmb200_rank_batch_dev(self._h, C.c_void_p(d_pos), C.c_uint64(n), C.c_void_p(d_out)), "rank_batch_dev")
+
+    def select_dev(self, d_rank: int, n: int, d_pos: int, d_found: int):
+        self.ctx.check(lib().bmb200_select_batch_dev(self._h, C.c_void_p(d_rank), C.c_uint64(n), C.c_void_p(d_pos), C.c_void_p(d_found)), "select_batch_dev")
+
+    def free(self):
+        if self._h:
+            lib().bmb200_rs_free(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -1,0 +1,838 @@
+// capi.cu -- C ABI of libbmb200 (see include/bmb200.h).  Host-side orchestration only: arena
+// allocation, H2D/D2H, launches.  There is deliberately NO CPU compute path: without an sm_100
+// device bmb200_init fails with BMB200_ERR_NODEVICE.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "agg_kernel.cuh"
+#include "aux_kernels.cuh"
+
+using namespace bmb200;
+
+struct bmb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    std::string last_err;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t hbm_bytes = 0;
+    uint32_t* d_work = nullptr;             // work counter for the persistent kernel
+    uint32_t* d_group = nullptr;            // group member ids
+    size_t group_cap = 0;
+    uint32_t* h_group = nullptr;            // pinned staging for the group ids
+    int agg_ctas_per_sm = 2;
+};
+
+struct bmb200_set {
+    bmb200_ctx* ctx = nullptr;
+    SetView v{};
+    bool owns = false;
+    uint64_t n_bit_blocks = 0, n_gap_units = 0;
+};
+
+struct bmb200_result {
+    bmb200_ctx* ctx = nullptr;
+    uint32_t n_cols = 0;
+    bool has_blocks = false, compress = false, gaps_ready = false;
+    uint32_t* blocks = nullptr;
+    uint32_t* popcnt = nullptr;
+    uint64_t* digest = nullptr;
+    uint32_t* nruns = nullptr;
+    uint8_t*  kind = nullptr;
+    uint16_t* gaps = nullptr;
+    unsigned long long* total = nullptr;
+};
+
+struct bmb200_rs {
+    bmb200_ctx* ctx = nullptr;
+    const bmb200_set* set = nullptr;
+    uint32_t vec = 0, nsb = 0, n_blocks = 0;
+    uint32_t* bcount = nullptr;
+    uint64_t* sub_count = nullptr;
+    uint32_t* row_cum = nullptr;
+    uint64_t* sb_tot = nullptr;
+    uint64_t* sb_cum = nullptr;
+};
+
+namespace {
+
+constexpr size_t kSlack = 512;   // readable bytes past the end of each pool (GAP first-load over-read)
+
+#define CU(call)                                                                        \
+    do {                                                                                \
+        cudaError_t _e = (call);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            if (ctx) { ctx->last_err = std::string(#call) + ": " + cudaGetErrorString(_e); } \
+            return BMB200_ERR_CUDA;                                                     \
+        }                                                                               \
+    } while (0)
+
+int after_launch(bmb200_ctx* ctx)
+{
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ctx->last_err = std::string("kernel launch: ") + cudaGetErrorString(e); return BMB200_ERR_CUDA; }
+    return BMB200_OK;
+}
+
+template <typename T>
+int dev_alloc(bmb200_ctx* ctx, T** p, size_t n, size_t slack_bytes = 0)
+{
+    *p = nullptr;
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T) + slack_bytes + 16);
+    if (e != cudaSuccess) {
+        ctx->last_err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? BMB200_ERR_BADALLOC : BMB200_ERR_CUDA;
+    }
+    return BMB200_OK;
+}
+
+void free_set_arrays(bmb200_set* s)
+{
+    if (!s || !s->owns) return;
+    cudaFree((void*)s->v.desc); cudaFree((void*)s->v.bit_base); cudaFree((void*)s->v.gap_base);
+    cudaFree((void*)s->v.bit_pool); cudaFree((void*)s->v.gap_pool);
+}
+
+void free_result_arrays(bmb200_result* r)
+{
+    if (!r) return;
+    cudaFree(r->blocks); cudaFree(r->popcnt); cudaFree(r->digest); cudaFree(r->nruns);
+    cudaFree(r->kind); cudaFree(r->gaps); cudaFree(r->total);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bmb200_error_msg(int code)
+{
+    switch (code) {
+    case BMB200_OK: return "ok";
+    case BMB200_ERR_BADALLOC: return "allocation failed";
+    case BMB200_ERR_BADARG: return "bad argument";
+    case BMB200_ERR_RANGE: return "index out of range";
+    case BMB200_ERR_RS_IDX_MISSING: return "rank-select index missing";
+    case BMB200_ERR_CUDA: return "CUDA runtime error (see bmb200_last_error)";
+    case BMB200_ERR_NODEVICE: return "no sm_100 (B200) device available; libbmb200 has no CPU fallback";
+    default: return "unknown error";
+    }
+}
+
+int bmb200_init(int device, bmb200_ctx** out)
+{
+    if (!out) return BMB200_ERR_BADARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return BMB200_ERR_NODEVICE; }
+    if (device < 0 || device >= n) return BMB200_ERR_BADARG;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return BMB200_ERR_NODEVICE;
+    if (prop.major != 10) return BMB200_ERR_NODEVICE;     // kernels are built for sm_100a only
+    bmb200_ctx* ctx = new (std::nothrow) bmb200_ctx();
+    if (!ctx) return BMB200_ERR_BADALLOC;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major; ctx->cc_minor = prop.minor;
+    ctx->hbm_bytes = prop.totalGlobalMem;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_work, 64) != cudaSuccess) {
+        delete ctx; return BMB200_ERR_CUDA;
+    }
+    ctx->own_stream = true;
+    const char* e = getenv("BMB200_AGG_CTAS_PER_SM");
+    if (e && atoi(e) > 0) ctx->agg_ctas_per_sm = atoi(e);
+    *out = ctx;
+    return BMB200_OK;
+}
+
+int bmb200_destroy(bmb200_ctx* ctx)
+{
+    if (!ctx) return BMB200_ERR_BADARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    cudaFree(ctx->d_work); cudaFree(ctx->d_group);
+    if (ctx->h_group) cudaFreeHost(ctx->h_group);
+    delete ctx;
+    return BMB200_OK;
+}
+
+int bmb200_last_error(const bmb200_ctx* ctx, char* buf, size_t buflen)
+{
+    if (!ctx || !buf || !buflen) return BMB200_ERR_BADARG;
+    snprintf(buf, buflen, "%s", ctx->last_err.c_str());
+    return BMB200_OK;
+}
+
+int bmb200_ctx_set_stream(bmb200_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return BMB200_ERR_BADARG;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return BMB200_OK;
+}
+
+int bmb200_ctx_get_stream(const bmb200_ctx* ctx, void** cuda_stream)
+{
+    if (!ctx || !cuda_stream) return BMB200_ERR_BADARG;
+    *cuda_stream = (void*)ctx->stream;
+    return BMB200_OK;
+}
+
+int bmb200_ctx_sync(bmb200_ctx* ctx)
+{
+    if (!ctx) return BMB200_ERR_BADARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BMB200_OK;
+}
+
+int bmb200_ctx_launch_count(const bmb200_ctx* ctx, uint64_t* out)
+{
+    if (!ctx || !out) return BMB200_ERR_BADARG;
+    *out = ctx->launches;
+    return BMB200_OK;
+}
+
+int bmb200_device_info(const bmb200_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, uint64_t* hbm_bytes)
+{
+    if (!ctx) return BMB200_ERR_BADARG;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    if (hbm_bytes) *hbm_bytes = ctx->hbm_bytes;
+    return BMB200_OK;
+}
+
+/* ------------------------------------------------------------------ sets */
+
+static int set_alloc(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, uint64_t n_bit, uint64_t n_gap_units,
+                     bmb200_set** out)
+{
+    bmb200_set* s = new (std::nothrow) bmb200_set();
+    if (!s) return BMB200_ERR_BADALLOC;
+    s->ctx = ctx; s->owns = true;
+    s->v.n_vec = n_vec; s->v.n_blocks = n_blocks;
+    s->n_bit_blocks = n_bit; s->n_gap_units = n_gap_units;
+    int rc;
+    uint32_t* desc = nullptr; uint64_t *bb = nullptr, *gb = nullptr; uint32_t* bp = nullptr; uint16_t* gp = nullptr;
+    if ((rc = dev_alloc(ctx, &desc, (size_t)n_vec * n_blocks)) ||
+        (rc = dev_alloc(ctx, &bb, (size_t)n_blocks + 1)) ||
+        (rc = dev_alloc(ctx, &gb, (size_t)n_blocks + 1)) ||
+        (rc = dev_alloc(ctx, &bp, (size_t)n_bit * kBlockWords, kSlack)) ||
+        (rc = dev_alloc(ctx, &gp, (size_t)n_gap_units * kGapUnit, kSlack))) {
+        cudaFree(desc); cudaFree(bb); cudaFree(gb); cudaFree(bp); cudaFree(gp);
+        delete s; return rc;
+    }
+    s->v.desc = desc; s->v.bit_base = bb; s->v.gap_base = gb; s->v.bit_pool = bp; s->v.gap_pool = gp;
+    // the slack past the GAP pool is read (never interpreted) by the first pair-word load of a GAP block
+    cudaMemsetAsync((char*)gp + (size_t)n_gap_units * kGapUnit * 2, 0, kSlack, ctx->stream);
+    *out = s;
+    return BMB200_OK;
+}
+
+int bmb200_set_upload(bmb200_ctx* ctx, const bmb200_packed_set* h, bmb200_set** out)
+{
+    if (!ctx || !h || !out || !h->n_vec || !h->n_blocks || !h->desc || !h->bit_base || !h->gap_base)
+        return BMB200_ERR_BADARG;
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t n_bit = h->bit_base[h->n_blocks], n_gap = h->gap_base[h->n_blocks];
+    if ((n_bit && !h->bit_pool) || (n_gap && !h->gap_pool)) return BMB200_ERR_BADARG;
+    bmb200_set* s = nullptr;
+    int rc = set_alloc(ctx, h->n_vec, h->n_blocks, n_bit, n_gap, &s);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    cudaError_t e = cudaSuccess;
+    auto cp = [&](const void* dst, const void* src, size_t bytes) {
+        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync((void*)dst, src, bytes, cudaMemcpyHostToDevice, st);
+    };
+    cp(s->v.desc, h->desc, (size_t)h->n_vec * h->n_blocks * 4);
+    cp(s->v.bit_base, h->bit_base, ((size_t)h->n_blocks + 1) * 8);
+    cp(s->v.gap_base, h->gap_base, ((size_t)h->n_blocks + 1) * 8);
+    cp(s->v.bit_pool, h->bit_pool, (size_t)n_bit * BMB200_BLOCK_BYTES);
+    cp(s->v.gap_pool, h->gap_pool, (size_t)n_gap * kGapUnit * 2);
+    if (e != cudaSuccess) {
+        ctx->last_err = std::string("set_upload memcpy: ") + cudaGetErrorString(e);
+        free_set_arrays(s); delete s; return BMB200_ERR_CUDA;
+    }
+    *out = s;
+    return BMB200_OK;
+}
+
+int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks,
+                              const bmb200_vec_blocks* vecs, bmb200_set** out)
+{
+    if (!ctx || !vecs || !out || !n_vec || !n_blocks) return BMB200_ERR_BADARG;
+    for (uint32_t v = 0; v < n_vec; ++v)
+        if (vecs[v].n_blocks > n_blocks || (vecs[v].n_blocks && (!vecs[v].kind || !vecs[v].ptr))) return BMB200_ERR_BADARG;
+    // host-side gather of the block tree into the packed column-major layout (the block manager stays on the host)
+    std::vector<uint32_t> desc; std::vector<uint64_t> bb, gb;
+    try { desc.assign((size_t)n_vec * n_blocks, 0u); bb.assign((size_t)n_blocks + 1, 0); gb.assign((size_t)n_blocks + 1, 0); }
+    catch (...) { return BMB200_ERR_BADALLOC; }
+    for (uint32_t nb = 0; nb < n_blocks; ++nb) {
+        uint64_t nbit = 0, ngap = 0;
+        for (uint32_t v = 0; v < n_vec; ++v) {
+            uint32_t kd = (nb < vecs[v].n_blocks) ? vecs[v].kind[nb] : BMB200_BLK_NULL;
+            uint32_t rel = 0;
+            if (kd == BMB200_BLK_BIT) rel = (uint32_t)nbit++;
+            else if (kd == BMB200_BLK_GAP) {
+                const uint16_t* g = (const uint16_t*)vecs[v].ptr[nb];
+                if (!g) return BMB200_ERR_BADARG;
+                uint32_t words = (uint32_t)(g[0] >> 3) + 1u;
+                if (words > kGapMax) return BMB200_ERR_BADARG;
+                rel = (uint32_t)ngap; ngap += (words + kGapUnit - 1) / kGapUnit;
+            } else if (kd > 3u) return BMB200_ERR_BADARG;
+            desc[(size_t)nb * n_vec + v] = kd | (rel << 2);
+        }
+        bb[nb + 1] = bb[nb] + nbit; gb[nb + 1] = gb[nb] + ngap;
+    }
+    const uint64_t n_bit = bb[n_blocks], n_gap = gb[n_blocks];
+    CU(cudaSetDevice(ctx->device));
+    uint32_t* hb = nullptr; uint16_t* hg = nullptr;
+    if (n_bit) CU(cudaMallocHost((void**)&hb, (size_t)n_bit * BMB200_BLOCK_BYTES));
+    if (n_gap) { cudaError_t e = cudaMallocHost((void**)&hg, (size_t)n_gap * kGapUnit * 2);
+                 if (e != cudaSuccess) { if (hb) cudaFreeHost(hb); ctx->last_err = "cudaMallocHost"; return BMB200_ERR_BADALLOC; } }
+    if (hg) memset(hg, 0, (size_t)n_gap * kGapUnit * 2);
+    for (uint32_t nb = 0; nb < n_blocks; ++nb)
+        for (uint32_t v = 0; v < n_vec; ++v) {
+            const uint32_t d = desc[(size_t)nb * n_vec + v], kd = d & 3u, rel = d >> 2;
+            if (kd == BMB200_BLK_BIT)
+                memcpy(hb + (bb[nb] + rel) * (size_t)kBlockWords, vecs[v].ptr[nb], BMB200_BLOCK_BYTES);
+            else if (kd == BMB200_BLK_GAP) {
+                const uint16_t* g = (const uint16_t*)vecs[v].ptr[nb];
+                memcpy(hg + (gb[nb] + rel) * (size_t)kGapUnit, g, ((size_t)(g[0] >> 3) + 1) * 2);
+            }
+        }
+    bmb200_packed_set h{n_vec, n_blocks, desc.data(), bb.data(), gb.data(), hb, hg};
+    int rc = bmb200_set_upload(ctx, &h, out);
+    cudaStreamSynchronize(ctx->stream);
+    if (hb) cudaFreeHost(hb);
+    if (hg) cudaFreeHost(hg);
+    return rc;
+}
+
+int bmb200_set_adopt_device(bmb200_ctx* ctx, const bmb200_packed_set* d, bmb200_set** out)
+{
+    if (!ctx || !d || !out || !d->n_vec || !d->n_blocks || !d->desc || !d->bit_base || !d->gap_base) return BMB200_ERR_BADARG;
+    CU(cudaSetDevice(ctx->device));
+    bmb200_set* s = new (std::nothrow) bmb200_set();
+    if (!s) return BMB200_ERR_BADALLOC;
+    s->ctx = ctx; s->owns = false;
+    s->v.n_vec = d->n_vec; s->v.n_blocks = d->n_blocks;
+    s->v.desc = d->desc; s->v.bit_base = d->bit_base; s->v.gap_base = d->gap_base;
+    s->v.bit_pool = d->bit_pool; s->v.gap_pool = d->gap_pool;
+    uint64_t tails[2] = {0, 0};
+    cudaError_t e1 = cudaMemcpyAsync(&tails[0], d->bit_base + d->n_blocks, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaMemcpyAsync(&tails[1], d->gap_base + d->n_blocks, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e3 = cudaStreamSynchronize(ctx->stream);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { delete s; ctx->last_err = "adopt: cannot read bases"; return BMB200_ERR_CUDA; }
+    s->n_bit_blocks = tails[0]; s->n_gap_units = tails[1];
+    *out = s;
+    return BMB200_OK;
+}
+
+int bmb200_set_info(const bmb200_set* s, uint32_t* n_vec, uint32_t* n_blocks, uint64_t* n_bit_blocks, uint64_t* n_gap_units)
+{
+    if (!s) return BMB200_ERR_BADARG;
+    if (n_vec) *n_vec = s->v.n_vec;
+    if (n_blocks) *n_blocks = s->v.n_blocks;
+    if (n_bit_blocks) *n_bit_blocks = s->n_bit_blocks;
+    if (n_gap_units) *n_gap_units = s->n_gap_units;
+    return BMB200_OK;
+}
+
+static int set_col_bases(const bmb200_set* s, uint32_t nb_from, uint32_t nb_to, uint64_t b[2], uint64_t g[2])
+{
+    bmb200_ctx* ctx = s->ctx;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(&b[0], s->v.bit_base + nb_from, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&b[1], s->v.bit_base + nb_to, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&g[0], s->v.gap_base + nb_from, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&g[1], s->v.gap_base + nb_to, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BMB200_OK;
+}
+
+int bmb200_set_column_sizes(const bmb200_set* s, uint32_t nb_from, uint32_t nb_to, uint64_t* n_bit_blocks, uint64_t* n_gap_units)
+{
+    if (!s) return BMB200_ERR_BADARG;
+    if (nb_from > nb_to || nb_to > s->v.n_blocks) return BMB200_ERR_RANGE;
+    uint64_t b[2], g[2];
+    int rc = set_col_bases(s, nb_from, nb_to, b, g);
+    if (rc) return rc;
+    if (n_bit_blocks) *n_bit_blocks = b[1] - b[0];
+    if (n_gap_units) *n_gap_units = g[1] - g[0];
+    return BMB200_OK;
+}
+
+int bmb200_set_download(const bmb200_set* s, uint32_t nb_from, uint32_t nb_to,
+                        uint32_t* desc, uint64_t* bit_base, uint64_t* gap_base, uint32_t* bit_pool, uint16_t* gap_pool)
+{
+    if (!s || !desc || !bit_base || !gap_base) return BMB200_ERR_BADARG;
+    if (nb_from > nb_to || nb_to > s->v.n_blocks) return BMB200_ERR_RANGE;
+    bmb200_ctx* ctx = s->ctx;
+    uint64_t b[2], g[2];
+    int rc = set_col_bases(s, nb_from, nb_to, b, g);
+    if (rc) return rc;
+    const uint32_t nc = nb_to - nb_from;
+    if ((b[1] > b[0] && !bit_pool) || (g[1] > g[0] && !gap_pool)) return BMB200_ERR_BADARG;
+    CU(cudaMemcpyAsync(desc, s->v.desc + (size_t)nb_from * s->v.n_vec, (size_t)nc * s->v.n_vec * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(bit_base, s->v.bit_base + nb_from, ((size_t)nc + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(gap_base, s->v.gap_base + nb_from, ((size_t)nc + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (b[1] > b[0])
+        CU(cudaMemcpyAsync(bit_pool, s->v.bit_pool + b[0] * (size_t)kBlockWords, (size_t)(b[1] - b[0]) * BMB200_BLOCK_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    if (g[1] > g[0])
+        CU(cudaMemcpyAsync(gap_pool, s->v.gap_pool + g[0] * (size_t)kGapUnit, (size_t)(g[1] - g[0]) * kGapUnit * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i <= nc; ++i) { bit_base[i] -= b[0]; gap_base[i] -= g[0]; }
+    return BMB200_OK;
+}
+
+int bmb200_set_device_ptrs(const bmb200_set* s, bmb200_packed_set* out)
+{
+    if (!s || !out) return BMB200_ERR_BADARG;
+    out->n_vec = s->v.n_vec; out->n_blocks = s->v.n_blocks;
+    out->desc = s->v.desc; out->bit_base = s->v.bit_base; out->gap_base = s->v.gap_base;
+    out->bit_pool = s->v.bit_pool; out->gap_pool = s->v.gap_pool;
+    return BMB200_OK;
+}
+
+int bmb200_set_free(bmb200_set* s)
+{
+    if (!s) return BMB200_ERR_BADARG;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    free_set_arrays(s);
+    delete s;
+    return BMB200_OK;
+}
+
+int bmb200_synth_set(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks,
+                     const double* density, const uint64_t* seed, int optimize, bmb200_set** out)
+{
+    if (!ctx || !out || !density || !seed || !n_vec || !n_blocks) return BMB200_ERR_BADARG;
+    if ((uint64_t)n_vec * n_blocks > 0x7fffffffull) return BMB200_ERR_RANGE;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    std::vector<uint32_t> thr(n_vec);
+    for (uint32_t v = 0; v < n_vec; ++v) {
+        double t = density[v] * 65536.0 + 0.5;
+        thr[v] = t <= 0 ? 0u : t >= 65536.0 ? 65536u : (uint32_t)t;
+    }
+    const size_t items = (size_t)n_vec * n_blocks;
+    uint64_t* d_seed = nullptr; uint32_t* d_thr = nullptr; uint8_t* d_kind = nullptr; uint16_t* d_glen = nullptr;
+    uint64_t *d_cb = nullptr, *d_cg = nullptr;
+    uint32_t* desc = nullptr; uint64_t *bb = nullptr, *gb = nullptr;
+    int rc = BMB200_OK;
+    auto cleanup_tmp = [&]() { cudaFree(d_seed); cudaFree(d_thr); cudaFree(d_kind); cudaFree(d_glen); cudaFree(d_cb); cudaFree(d_cg); };
+    if ((rc = dev_alloc(ctx, &d_seed, n_vec)) || (rc = dev_alloc(ctx, &d_thr, n_vec)) ||
+        (rc = dev_alloc(ctx, &d_kind, items)) || (rc = dev_alloc(ctx, &d_glen, items)) ||
+        (rc = dev_alloc(ctx, &d_cb, n_blocks)) || (rc = dev_alloc(ctx, &d_cg, n_blocks)) ||
+        (rc = dev_alloc(ctx, &desc, items)) || (rc = dev_alloc(ctx, &bb, (size_t)n_blocks + 1)) ||
+        (rc = dev_alloc(ctx, &gb, (size_t)n_blocks + 1))) {
+        cleanup_tmp(); cudaFree(desc); cudaFree(bb); cudaFree(gb); return rc;
+    }
+    cudaMemcpyAsync(d_seed, seed, n_vec * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_thr, thr.data(), n_vec * 4, cudaMemcpyHostToDevice, st);
+    synth_classify_kernel<<<(unsigned)items, kPostThreads, 0, st>>>(n_vec, n_blocks, d_seed, d_thr, optimize, d_kind, d_glen);
+    if ((rc = after_launch(ctx))) { cleanup_tmp(); cudaFree(desc); cudaFree(bb); cudaFree(gb); return rc; }
+    synth_layout_kernel<<<n_blocks, 256, 0, st>>>(n_vec, d_kind, d_glen, desc, d_cb, d_cg);
+    after_launch(ctx);
+    scan_u64_kernel<<<1, 1024, 0, st>>>(d_cb, n_blocks, bb); after_launch(ctx);
+    scan_u64_kernel<<<1, 1024, 0, st>>>(d_cg, n_blocks, gb); after_launch(ctx);
+    uint64_t tails[2] = {0, 0};
+    cudaMemcpyAsync(&tails[0], bb + n_blocks, 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&tails[1], gb + n_blocks, 8, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { ctx->last_err = std::string("synth: ") + cudaGetErrorString(e); cleanup_tmp(); cudaFree(desc); cudaFree(bb); cudaFree(gb); return BMB200_ERR_CUDA; }
+    uint32_t* bp = nullptr; uint16_t* gp = nullptr;
+    if ((rc = dev_alloc(ctx, &bp, (size_t)tails[0] * kBlockWords, kSlack)) ||
+        (rc = dev_alloc(ctx, &gp, (size_t)tails[1] * kGapUnit, kSlack))) {
+        cleanup_tmp(); cudaFree(desc); cudaFree(bb); cudaFree(gb); cudaFree(bp); cudaFree(gp); return rc;
+    }
+    cudaMemsetAsync((char*)gp + (size_t)tails[1] * kGapUnit * 2, 0, kSlack, st);
+    synth_write_kernel<<<(unsigned)items, kPostThreads, 0, st>>>(n_vec, n_blocks, d_seed, d_thr, desc, bb, gb, bp, gp);
+    rc = after_launch(ctx);
+    e = cudaStreamSynchronize(st);
+    cleanup_tmp();
+    if (rc || e != cudaSuccess) {
+        if (e != cudaSuccess) ctx->last_err = std::string("synth write: ") + cudaGetErrorString(e);
+        cudaFree(desc); cudaFree(bb); cudaFree(gb); cudaFree(bp); cudaFree(gp); return BMB200_ERR_CUDA;
+    }
+    bmb200_set* s = new (std::nothrow) bmb200_set();
+    if (!s) { cudaFree(desc); cudaFree(bb); cudaFree(gb); cudaFree(bp); cudaFree(gp); return BMB200_ERR_BADALLOC; }
+    s->ctx = ctx; s->owns = true;
+    s->v.n_vec = n_vec; s->v.n_blocks = n_blocks;
+    s->v.desc = desc; s->v.bit_base = bb; s->v.gap_base = gb; s->v.bit_pool = bp; s->v.gap_pool = gp;
+    s->n_bit_blocks = tails[0]; s->n_gap_units = tails[1];
+    *out = s;
+    return BMB200_OK;
+}
+
+/* ------------------------------------------------------------------ aggregation */
+
+static int result_alloc(bmb200_ctx* ctx, uint32_t n_cols, bool blocks, bool gaps, bmb200_result** out)
+{
+    bmb200_result* r = new (std::nothrow) bmb200_result();
+    if (!r) return BMB200_ERR_BADALLOC;
+    r->ctx = ctx; r->n_cols = n_cols;
+    int rc;
+    if ((rc = dev_alloc(ctx, &r->popcnt, n_cols)) || (rc = dev_alloc(ctx, &r->digest, n_cols)) ||
+        (rc = dev_alloc(ctx, &r->nruns, n_cols)) || (rc = dev_alloc(ctx, &r->kind, n_cols)) ||
+        (rc = dev_alloc(ctx, &r->total, 1)) ||
+        (blocks && (rc = dev_alloc(ctx, &r->blocks, (size_t)n_cols * kBlockWords))) ||
+        (gaps && (rc = dev_alloc(ctx, &r->gaps, (size_t)n_cols * kGapMax)))) {
+        free_result_arrays(r); delete r; return rc;
+    }
+    r->has_blocks = blocks;
+    *out = r;
+    return BMB200_OK;
+}
+
+int bmb200_aggregate(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_agg_args* a, bmb200_result** inout)
+{
+    if (!ctx || !set || !a || !inout || set->ctx != ctx) return BMB200_ERR_BADARG;
+    if (a->op < BMB200_OP_OR || a->op > BMB200_OP_XOR) return BMB200_ERR_BADARG;
+    const uint32_t nb_to = a->nb_to ? a->nb_to : set->v.n_blocks;
+    if (a->nb_from >= nb_to || nb_to > set->v.n_blocks) return BMB200_ERR_RANGE;
+    const uint32_t n1 = (a->op == BMB200_OP_AND_SUB) ? a->n1 : 0u;
+    if ((a->n0 && !a->group0) || (n1 && !a->group1)) return BMB200_ERR_BADARG;
+    for (uint32_t k = 0; k < a->n0; ++k) if (a->group0[k] >= set->v.n_vec) return BMB200_ERR_RANGE;
+    for (uint32_t k = 0; k < n1; ++k) if (a->group1[k] >= set->v.n_vec) return BMB200_ERR_RANGE;
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t n_cols = nb_to - a->nb_from;
+    const bool store = !(a->flags & BMB200_F_COUNT_ONLY);
+    const bool compress = (a->flags & BMB200_F_OPT_COMPRESS) != 0;
+
+    bmb200_result* r = *inout;
+    if (r && (r->ctx != ctx || r->n_cols != n_cols || (store && !r->blocks) || (store && compress && !r->gaps))) {
+        bmb200_result_free(r); r = nullptr; *inout = nullptr;
+    }
+    if (!r) {
+        int rc = result_alloc(ctx, n_cols, store, store && compress, &r);
+        if (rc) return rc;
+    }
+    r->has_blocks = store; r->compress = compress; r->gaps_ready = false;
+
+    // group ids -> device (pinned staging keeps the copy asynchronous)
+    const size_t ng = (size_t)a->n0 + n1;
+    if (ng > ctx->group_cap) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(ctx->d_group); if (ctx->h_group) cudaFreeHost(ctx->h_group);
+        ctx->d_group = nullptr; ctx->h_group = nullptr; ctx->group_cap = 0;
+        size_t cap = ng < 1024 ? 1024 : ng;
+        if (cudaMalloc((void**)&ctx->d_group, cap * 4) != cudaSuccess || cudaMallocHost((void**)&ctx->h_group, cap * 4) != cudaSuccess) {
+            ctx->last_err = "group buffer allocation"; if (!*inout) bmb200_result_free(r); return BMB200_ERR_BADALLOC;
+        }
+        ctx->group_cap = cap;
+    }
+    if (ng) {
+        cudaStreamSynchronize(ctx->stream);    // the staging buffer may still feed a previous launch
+        memcpy(ctx->h_group, a->group0, (size_t)a->n0 * 4);
+        if (n1) memcpy(ctx->h_group + a->n0, a->group1, (size_t)n1 * 4);
+        CU(cudaMemcpyAsync(ctx->d_group, ctx->h_group, ng * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(cudaMemsetAsync(ctx->d_work, 0, 4, ctx->stream));
+    CU(cudaMemsetAsync(r->total, 0, 8, ctx->stream));
+
+    AggParams p{};
+    p.set = set->v; p.group = ctx->d_group; p.n0 = a->n0; p.n1 = n1;
+    p.nb_from = a->nb_from; p.n_cols = n_cols;
+    p.compress = compress ? 1u : 0u; p.store_blocks = store ? 1u : 0u;
+    p.blocks = r->blocks; p.popcnt = r->popcnt; p.digest = r->digest; p.nruns = r->nruns; p.kind = r->kind;
+    p.total = r->total; p.work_counter = ctx->d_work;
+    uint32_t grid = (uint32_t)(ctx->sm_count * ctx->agg_ctas_per_sm);
+    if (grid > n_cols) grid = n_cols;
+    switch (a->op) {
+    case BMB200_OP_OR:      agg_kernel<BMB200_OP_OR><<<grid, kAggThreads, 0, ctx->stream>>>(p); break;
+    case BMB200_OP_AND:     agg_kernel<BMB200_OP_AND><<<grid, kAggThreads, 0, ctx->stream>>>(p); break;
+    case BMB200_OP_AND_SUB: agg_kernel<BMB200_OP_AND_SUB><<<grid, kAggThreads, 0, ctx->stream>>>(p); break;
+    default:                agg_kernel<BMB200_OP_XOR><<<grid, kAggThreads, 0, ctx->stream>>>(p); break;
+    }
+    int rc = after_launch(ctx);
+    if (rc) { if (!*inout) bmb200_result_free(r); return rc; }
+    *inout = r;
+    if (store && compress) return bmb200_result_optimize(r);
+    return BMB200_OK;
+}
+
+int bmb200_result_optimize(bmb200_result* r)
+{
+    if (!r) return BMB200_ERR_BADARG;
+    bmb200_ctx* ctx = r->ctx;
+    if (!r->compress || !r->has_blocks) return BMB200_ERR_BADARG;
+    if (r->gaps_ready) return BMB200_OK;
+    CU(cudaSetDevice(ctx->device));
+    uint32_t grid = (uint32_t)ctx->sm_count * 8u; if (grid > r->n_cols) grid = r->n_cols;
+    result_to_gap_kernel<<<grid, kPostThreads, 0, ctx->stream>>>(r->blocks, r->kind, r->gaps, r->n_cols);
+    int rc = after_launch(ctx);
+    if (!rc) r->gaps_ready = true;
+    return rc;
+}
+
+int bmb200_result_total(bmb200_result* r, uint64_t* total, int* any)
+{
+    if (!r) return BMB200_ERR_BADARG;
+    bmb200_ctx* ctx = r->ctx;
+    CU(cudaSetDevice(ctx->device));
+    unsigned long long t = 0;
+    CU(cudaMemcpyAsync(&t, r->total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (total) *total = t;
+    if (any) *any = t ? 1 : 0;
+    return BMB200_OK;
+}
+
+int bmb200_result_fetch_meta(bmb200_result* r, const bmb200_result_meta* m)
+{
+    if (!r || !m) return BMB200_ERR_BADARG;
+    bmb200_ctx* ctx = r->ctx;
+    CU(cudaSetDevice(ctx->device));
+    if (m->kind)   CU(cudaMemcpyAsync(m->kind, r->kind, r->n_cols, cudaMemcpyDeviceToHost, ctx->stream));
+    if (m->popcnt) CU(cudaMemcpyAsync(m->popcnt, r->popcnt, (size_t)r->n_cols * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (m->digest) CU(cudaMemcpyAsync(m->digest, r->digest, (size_t)r->n_cols * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (m->nruns)  CU(cudaMemcpyAsync(m->nruns, r->nruns, (size_t)r->n_cols * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BMB200_OK;
+}
+
+// host-side layout of the compacted result: offsets per column from kinds and run counts
+static int result_layout(bmb200_result* r, std::vector<uint8_t>& kind, std::vector<uint64_t>& off, uint64_t* n_bit, uint64_t* n_gap_words)
+{
+    bmb200_ctx* ctx = r->ctx;
+    std::vector<uint32_t> nruns;
+    try { kind.resize(r->n_cols); off.assign(r->n_cols, 0); nruns.resize(r->n_cols); } catch (...) { return BMB200_ERR_BADALLOC; }
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(kind.data(), r->kind, r->n_cols, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(nruns.data(), r->nruns, (size_t)r->n_cols * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    uint64_t nb = 0, ng = 0;
+    for (uint32_t c = 0; c < r->n_cols; ++c) {
+        if (kind[c] == BMB200_BLK_BIT) off[c] = nb++;
+        else if (kind[c] == BMB200_BLK_GAP) { off[c] = ng; ng += ((uint64_t)nruns[c] + 1 + kGapUnit - 1) / kGapUnit * kGapUnit; }
+    }
+    *n_bit = nb; *n_gap_words = ng;
+    return BMB200_OK;
+}
+
+int bmb200_result_sizes(bmb200_result* r, uint64_t* n_bit_blocks, uint64_t* n_gap_words)
+{
+    if (!r || !r->has_blocks) return BMB200_ERR_BADARG;
+    std::vector<uint8_t> kind; std::vector<uint64_t> off; uint64_t nb, ng;
+    int rc = result_layout(r, kind, off, &nb, &ng);
+    if (rc) return rc;
+    if (n_bit_blocks) *n_bit_blocks = nb;
+    if (n_gap_words) *n_gap_words = ng;
+    return BMB200_OK;
+}
+
+int bmb200_result_fetch(bmb200_result* r, uint8_t* kind_out, uint64_t* off_out, uint32_t* bits, uint16_t* gaps)
+{
+    if (!r || !r->has_blocks || !kind_out || !off_out) return BMB200_ERR_BADARG;
+    bmb200_ctx* ctx = r->ctx;
+    if (r->compress && !r->gaps_ready) { int rc = bmb200_result_optimize(r); if (rc) return rc; }
+    std::vector<uint8_t> kind; std::vector<uint64_t> off; uint64_t nb, ng;
+    int rc = result_layout(r, kind, off, &nb, &ng);
+    if (rc) return rc;
+    if ((nb && !bits) || (ng && !gaps)) return BMB200_ERR_BADARG;
+    memcpy(kind_out, kind.data(), r->n_cols);
+    memcpy(off_out, off.data(), (size_t)r->n_cols * 8);
+    if (!nb && !ng) return BMB200_OK;
+    uint64_t* d_off = nullptr; uint32_t* d_bits = nullptr; uint16_t* d_gaps = nullptr;
+    if ((rc = dev_alloc(ctx, &d_off, r->n_cols)) || (rc = dev_alloc(ctx, &d_bits, (size_t)nb * kBlockWords)) ||
+        (rc = dev_alloc(ctx, &d_gaps, (size_t)ng))) { cudaFree(d_off); cudaFree(d_bits); cudaFree(d_gaps); return rc; }
+    cudaMemcpyAsync(d_off, off.data(), (size_t)r->n_cols * 8, cudaMemcpyHostToDevice, ctx->stream);
+    uint32_t grid = (uint32_t)ctx->sm_count * 8u; if (grid > r->n_cols) grid = r->n_cols;
+    result_compact_kernel<<<grid, 256, 0, ctx->stream>>>(r->blocks, r->gaps, r->kind, d_off, d_bits, d_gaps, r->n_cols);
+    rc = after_launch(ctx);
+    cudaError_t e = cudaSuccess;
+    if (!rc && nb) e = cudaMemcpyAsync(bits, d_bits, (size_t)nb * BMB200_BLOCK_BYTES, cudaMemcpyDeviceToHost, ctx->stream);
+    if (!rc && e == cudaSuccess && ng) e = cudaMemcpyAsync(gaps, d_gaps, (size_t)ng * 2, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_off); cudaFree(d_bits); cudaFree(d_gaps);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess) { ctx->last_err = std::string("result_fetch: ") + cudaGetErrorString(e != cudaSuccess ? e : e2); return BMB200_ERR_CUDA; }
+    return BMB200_OK;
+}
+
+int bmb200_result_device_ptrs(const bmb200_result* r, void** blocks, void** popcnt, void** digest, void** flag, uint32_t* n_cols)
+{
+    if (!r) return BMB200_ERR_BADARG;
+    if (blocks) *blocks = r->blocks;
+    if (popcnt) *popcnt = r->popcnt;
+    if (digest) *digest = r->digest;
+    if (flag) *flag = r->kind;
+    if (n_cols) *n_cols = r->n_cols;
+    return BMB200_OK;
+}
+
+int bmb200_result_free(bmb200_result* r)
+{
+    if (!r) return BMB200_ERR_BADARG;
+    cudaSetDevice(r->ctx->device);
+    cudaStreamSynchronize(r->ctx->stream);
+    free_result_arrays(r);
+    delete r;
+    return BMB200_OK;
+}
+
+int bmb200_aggregate_host(bmb200_ctx* ctx, const bmb200_packed_set* host, const bmb200_agg_args* args,
+                          const bmb200_result_meta* meta_out, uint64_t* total_out)
+{
+    if (!ctx || !host || !args) return BMB200_ERR_BADARG;
+    bmb200_set* s = nullptr; bmb200_result* r = nullptr;
+    int rc = bmb200_set_upload(ctx, host, &s);
+    if (rc) return rc;
+    rc = bmb200_aggregate(ctx, s, args, &r);
+    if (!rc && meta_out) rc = bmb200_result_fetch_meta(r, meta_out);
+    if (!rc && total_out) rc = bmb200_result_total(r, total_out, nullptr);
+    if (r) bmb200_result_free(r);
+    bmb200_set_free(s);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ rank / select */
+
+static RsView rs_view(const bmb200_rs* rs)
+{
+    RsView v{};
+    v.set = rs->set->v; v.vec = rs->vec; v.nsb = rs->nsb;
+    v.bcount = rs->bcount; v.sub_count = rs->sub_count; v.row_cum = rs->row_cum; v.sb_cum = rs->sb_cum;
+    return v;
+}
+
+int bmb200_rs_build(bmb200_ctx* ctx, const bmb200_set* set, uint32_t vec, bmb200_rs** out)
+{
+    if (!ctx || !set || !out || set->ctx != ctx) return BMB200_ERR_BADARG;
+    if (vec >= set->v.n_vec) return BMB200_ERR_RANGE;
+    CU(cudaSetDevice(ctx->device));
+    bmb200_rs* rs = new (std::nothrow) bmb200_rs();
+    if (!rs) return BMB200_ERR_BADALLOC;
+    rs->ctx = ctx; rs->set = set; rs->vec = vec; rs->n_blocks = set->v.n_blocks;
+    rs->nsb = (set->v.n_blocks + 255u) / 256u;
+    int rc;
+    if ((rc = dev_alloc(ctx, &rs->bcount, rs->n_blocks)) || (rc = dev_alloc(ctx, &rs->sub_count, rs->n_blocks)) ||
+        (rc = dev_alloc(ctx, &rs->row_cum, rs->n_blocks)) || (rc = dev_alloc(ctx, &rs->sb_tot, rs->nsb)) ||
+        (rc = dev_alloc(ctx, &rs->sb_cum, (size_t)rs->nsb + 1))) { bmb200_rs_free(rs); return rc; }
+    uint32_t grid = (rs->n_blocks + 7u) / 8u;
+    const uint32_t maxg = (uint32_t)ctx->sm_count * 16u; if (grid > maxg) grid = maxg;
+    rs_block_kernel<<<grid, 256, 0, ctx->stream>>>(set->v, vec, rs->bcount, rs->sub_count);
+    if ((rc = after_launch(ctx))) { bmb200_rs_free(rs); return rc; }
+    rs_scan_rows_kernel<<<rs->nsb, 256, 0, ctx->stream>>>(rs->bcount, rs->n_blocks, rs->row_cum, rs->sb_tot);
+    if ((rc = after_launch(ctx))) { bmb200_rs_free(rs); return rc; }
+    rs_scan_sb_kernel<<<1, 1024, 0, ctx->stream>>>(rs->sb_tot, rs->nsb, rs->sb_cum);
+    if ((rc = after_launch(ctx))) { bmb200_rs_free(rs); return rc; }
+    *out = rs;
+    return BMB200_OK;
+}
+
+int bmb200_rs_export(bmb200_rs* rs, uint32_t* bcount, uint64_t* sub_count, uint64_t* sb_count)
+{
+    if (!rs) return BMB200_ERR_RS_IDX_MISSING;
+    bmb200_ctx* ctx = rs->ctx;
+    CU(cudaSetDevice(ctx->device));
+    if (bcount)    CU(cudaMemcpyAsync(bcount, rs->bcount, (size_t)rs->n_blocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sub_count) CU(cudaMemcpyAsync(sub_count, rs->sub_count, (size_t)rs->n_blocks * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sb_count)  CU(cudaMemcpyAsync(sb_count, rs->sb_cum, ((size_t)rs->nsb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BMB200_OK;
+}
+
+int bmb200_rs_total(bmb200_rs* rs, uint64_t* total)
+{
+    if (!rs) return BMB200_ERR_RS_IDX_MISSING;
+    if (!total) return BMB200_ERR_BADARG;
+    bmb200_ctx* ctx = rs->ctx;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(total, rs->sb_cum + rs->nsb, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BMB200_OK;
+}
+
+int bmb200_rank_batch_dev(bmb200_rs* rs, const uint64_t* d_pos, uint64_t n, uint64_t* d_out)
+{
+    if (!rs) return BMB200_ERR_RS_IDX_MISSING;
+    if (!n) return BMB200_OK;
+    if (!d_pos || !d_out) return BMB200_ERR_BADARG;
+    bmb200_ctx* ctx = rs->ctx;
+    CU(cudaSetDevice(ctx->device));
+    uint64_t g = (n + 255) / 256; const uint64_t maxg = (uint64_t)ctx->sm_count * 32; if (g > maxg) g = maxg;
+    rs_rank_kernel<<<(unsigned)g, 256, 0, ctx->stream>>>(rs_view(rs), d_pos, n, d_out);
+    return after_launch(ctx);
+}
+
+int bmb200_select_batch_dev(bmb200_rs* rs, const uint64_t* d_rank, uint64_t n, uint64_t* d_pos, uint8_t* d_found)
+{
+    if (!rs) return BMB200_ERR_RS_IDX_MISSING;
+    if (!n) return BMB200_OK;
+    if (!d_rank || !d_pos || !d_found) return BMB200_ERR_BADARG;
+    bmb200_ctx* ctx = rs->ctx;
+    CU(cudaSetDevice(ctx->device));
+    uint64_t g = (n + 255) / 256; const uint64_t maxg = (uint64_t)ctx->sm_count * 32; if (g > maxg) g = maxg;
+    rs_select_kernel<<<(unsigned)g, 256, 0, ctx->stream>>>(rs_view(rs), d_rank, n, d_pos, d_found);
+    return after_launch(ctx);
+}
+
+int bmb200_rank_batch(bmb200_rs* rs, const uint64_t* pos, uint64_t n, uint64_t* out)
+{
+    if (!rs) return BMB200_ERR_RS_IDX_MISSING;
+    if (!n) return BMB200_OK;
+    if (!pos || !out) return BMB200_ERR_BADARG;
+    bmb200_ctx* ctx = rs->ctx;
+    CU(cudaSetDevice(ctx->device));
+    uint64_t *d_in = nullptr, *d_out = nullptr;
+    int rc;
+    if ((rc = dev_alloc(ctx, &d_in, n)) || (rc = dev_alloc(ctx, &d_out, n))) { cudaFree(d_in); cudaFree(d_out); return rc; }
+    cudaError_t e = cudaMemcpyAsync(d_in, pos, n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    rc = bmb200_rank_batch_dev(rs, d_in, n, d_out);
+    if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in); cudaFree(d_out);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess) { ctx->last_err = std::string("rank_batch: ") + cudaGetErrorString(e != cudaSuccess ? e : e2); return BMB200_ERR_CUDA; }
+    return BMB200_OK;
+}
+
+int bmb200_select_batch(bmb200_rs* rs, const uint64_t* rank, uint64_t n, uint64_t* pos, uint8_t* found)
+{
+    if (!rs) return BMB200_ERR_RS_IDX_MISSING;
+    if (!n) return BMB200_OK;
+    if (!rank || !pos || !found) return BMB200_ERR_BADARG;
+    bmb200_ctx* ctx = rs->ctx;
+    CU(cudaSetDevice(ctx->device));
+    uint64_t *d_in = nullptr, *d_pos = nullptr; uint8_t* d_f = nullptr;
+    int rc;
+    if ((rc = dev_alloc(ctx, &d_in, n)) || (rc = dev_alloc(ctx, &d_pos, n)) || (rc = dev_alloc(ctx, &d_f, n))) {
+        cudaFree(d_in); cudaFree(d_pos); cudaFree(d_f); return rc;
+    }
+    cudaError_t e = cudaMemcpyAsync(d_in, rank, n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    rc = bmb200_select_batch_dev(rs, d_in, n, d_pos, d_f);
+    if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(pos, d_pos, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(found, d_f, n, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in); cudaFree(d_pos); cudaFree(d_f);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess) { ctx->last_err = std::string("select_batch: ") + cudaGetErrorString(e != cudaSuccess ? e : e2); return BMB200_ERR_CUDA; }
+    return BMB200_OK;
+}
+
+int bmb200_rs_free(bmb200_rs* rs)
+{
+    if (!rs) return BMB200_ERR_BADARG;
+    cudaSetDevice(rs->ctx->device);
+    cudaStreamSynchronize(rs->ctx->stream);
+    cudaFree(rs->bcount); cudaFree(rs->sub_count); cudaFree(rs->row_cum); cudaFree(rs->sb_tot); cudaFree(rs->sb_cum);
+    delete rs;
+    return BMB200_OK;
+}
+
+}  // extern "C"

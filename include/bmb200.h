@@ -1,0 +1,218 @@
+/*
+ * bmb200.h -- C ABI of libbmb200: B200 (sm_100a) block-level set algebra for
+ * BitMagic-format bit-vectors.
+ *
+ * This is the drop-in boundary for ONE path of tlk00/BitMagic: the 64 Kbit
+ * block kernels behind bm::aggregator<>::combine_or / combine_and /
+ * combine_and_sub, bm::bvector<>::bit_and/bit_or/bit_xor/bit_sub, bm::count_*
+ * and the rank/select path (rs_index build, count_to, select).
+ *
+ * Conventions follow the reference's own C binding
+ * (lang-maps/libbm/include/libbm.h:28-35,123-140): every function returns an
+ * int error code (0 == OK), results come back through out-pointers, handles
+ * are opaque, no C++ type or exception crosses the boundary.
+ *
+ * Reference interfaces replaced (file:line under the reference tree):
+ *   bmb200_aggregate  OP_OR       <- aggregator::combine_or        src/bmaggregator.h:1101-1122,1626-1663
+ *   bmb200_aggregate  OP_AND      <- aggregator::combine_and       src/bmaggregator.h:1126-1157,1668-1716
+ *   bmb200_aggregate  OP_AND_SUB  <- aggregator::combine_and_sub   src/bmaggregator.h:1162-1220,1720-1803
+ *   bmb200_aggregate  OP_XOR      <- bvector::bit_xor              src/bm.h:6072 (bit_block_xor src/bmfunc.h:9191)
+ *   BMB200_F_COUNT_ONLY           <- bm::count_and/or/xor/sub      src/bmalgo.h:48-51, pipeline counts src/bmaggregator.h:1397
+ *   bmb200_result_optimize        <- blocks_manager::opt_copy_bit_block src/bmblocks.h:1355-1409
+ *   bmb200_rs_build               <- bvector::build_rs_index       src/bm.h:2531-2660, rs_index src/bmrs.h:688-715
+ *   bmb200_rank_batch             <- bvector::count_to             src/bm.h:3120-3167
+ *   bmb200_select_batch           <- bvector::select               src/bm.h:5350-5385
+ *
+ * Block geometry (src/bmconst.h:55-68,78-87): a bit-block is 2048 x u32 =
+ * 8192 B = 65536 bits; a GAP block is u16 buf[0..len], buf[0] = header
+ * (bit0 = value of first run, bits1-2 = capacity level, bits3.. = len),
+ * buf[1..len] = inclusive run-end positions, buf[len] == 65535.
+ */
+#ifndef BMB200_H_INCLUDED
+#define BMB200_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes; 0..7 numerically identical to libbm.h:28-35 ---- */
+#define BMB200_OK                  0
+#define BMB200_ERR_BADALLOC        1
+#define BMB200_ERR_BADARG          2
+#define BMB200_ERR_RANGE           3
+#define BMB200_ERR_RS_IDX_MISSING  7
+#define BMB200_ERR_CUDA            200  /* a CUDA runtime call failed; see bmb200_last_error */
+#define BMB200_ERR_NODEVICE        201  /* no sm_100 device: this library has NO CPU fallback */
+
+/* ---- geometry ---- */
+#define BMB200_BLOCK_WORDS     2048u
+#define BMB200_BLOCK_BYTES     8192u
+#define BMB200_BLOCK_BITS      65536u
+#define BMB200_GAP_MAX_WORDS   1280u     /* src/bmconst.h:80  gap_max_buff_len */
+#define BMB200_GAP_THRESHOLD   1276u     /* glen(max_level)-4, src/bmblocks.h:1391 */
+#define BMB200_GAP_UNIT_WORDS  8u        /* GAP blocks start on 16-byte units in the arena */
+#define BMB200_SUPERBLOCK      256u      /* blocks per top-level entry, src/bmconst.h:95 */
+
+/* block kinds (2 bits); mirror the four pointer states of src/bmdef.h:165-199 */
+#define BMB200_BLK_NULL  0u
+#define BMB200_BLK_FULL  1u
+#define BMB200_BLK_BIT   2u
+#define BMB200_BLK_GAP   3u
+
+/* ---- operations ---- */
+#define BMB200_OP_OR       0   /* group0 = sources                       */
+#define BMB200_OP_AND      1   /* group0 = sources                       */
+#define BMB200_OP_AND_SUB  2   /* group0 = AND sources, group1 = SUB set */
+#define BMB200_OP_XOR      3   /* group0 = sources (2-operand in the reference, N-way here) */
+
+/* ---- flags for bmb200_aggregate ---- */
+#define BMB200_F_COUNT_ONLY  1u  /* per-column popcount/digest only; no result blocks stored */
+#define BMB200_F_OPT_NONE    0u  /* result kinds as aggregator opt_mode_ == opt_none           */
+#define BMB200_F_OPT_COMPRESS 2u /* classify + bit->GAP like opt_copy_bit_block(opt_compress) */
+
+typedef struct bmb200_ctx    bmb200_ctx;     /* one per process per GPU                      */
+typedef struct bmb200_set    bmb200_set;     /* device-resident column-major set of vectors  */
+typedef struct bmb200_result bmb200_result;  /* device-resident aggregate result             */
+typedef struct bmb200_rs     bmb200_rs;      /* device-resident rank-select index            */
+
+/*
+ * Packed (column-major) set of n_vec vectors x n_blocks block columns.
+ *   desc[nb*n_vec + v] = kind | (rel << 2)
+ *      BIT: rel = index of the block inside column nb's bit segment
+ *      GAP: rel = offset inside column nb's GAP segment, in 16-byte units
+ *   bit segment of column nb = bit_pool blocks [bit_base[nb], bit_base[nb+1])
+ *   GAP segment of column nb = gap_pool units  [gap_base[nb], gap_base[nb+1])
+ * All blocks of one column are contiguous, so one CTA streams one column.
+ */
+typedef struct bmb200_packed_set {
+    uint32_t        n_vec;
+    uint32_t        n_blocks;
+    const uint32_t* desc;      /* [n_blocks * n_vec]            */
+    const uint64_t* bit_base;  /* [n_blocks + 1], in blocks     */
+    const uint64_t* gap_base;  /* [n_blocks + 1], in 16-B units */
+    const uint32_t* bit_pool;  /* bit_base[n_blocks] * 2048 u32 */
+    const uint16_t* gap_pool;  /* gap_base[n_blocks] * 8 u16    */
+} bmb200_packed_set;
+
+/* One vector as the host block tree sees it: kind + pointer per block slot
+ * (what blocks_manager::get_block_ptr(i,j) yields, src/bmblocks.h:556). */
+typedef struct bmb200_vec_blocks {
+    uint32_t           n_blocks;
+    const uint8_t*     kind;   /* [n_blocks] BMB200_BLK_*                        */
+    const void* const* ptr;    /* [n_blocks] 8 KB bit-block or GAP buf, else 0   */
+} bmb200_vec_blocks;
+
+typedef struct bmb200_agg_args {
+    int32_t         op;        /* BMB200_OP_*                                    */
+    uint32_t        flags;     /* BMB200_F_*                                     */
+    const uint32_t* group0;    /* vector indices inside the set                  */
+    uint32_t        n0;
+    const uint32_t* group1;    /* SUB group for OP_AND_SUB, else ignored         */
+    uint32_t        n1;
+    uint32_t        nb_from;   /* block-column range [nb_from, nb_to)            */
+    uint32_t        nb_to;     /* 0 == n_blocks                                  */
+} bmb200_agg_args;
+
+/* Per-column result metadata (host arrays of n_cols = nb_to - nb_from entries; any may be NULL) */
+typedef struct bmb200_result_meta {
+    uint8_t*  kind;     /* BMB200_BLK_* after the opt-mode classification         */
+    uint32_t* popcnt;   /* bits set in the column's result block                  */
+    uint64_t* digest;   /* 64-wave non-zero bitmap, calc_block_digest0 src/bmfunc.h:1239 */
+    uint32_t* nruns;    /* bit_block_calc_change of the result, src/bmfunc.h:6040  */
+} bmb200_result_meta;
+
+/* ---------------- context ---------------- */
+int bmb200_init(int device, bmb200_ctx** out);
+int bmb200_destroy(bmb200_ctx* ctx);
+const char* bmb200_error_msg(int code);
+/* text of the last CUDA failure seen by this context (empty string if none) */
+int bmb200_last_error(const bmb200_ctx* ctx, char* buf, size_t buflen);
+/* run all work of this context on an existing cudaStream_t (e.g. torch's current stream) */
+int bmb200_ctx_set_stream(bmb200_ctx* ctx, void* cuda_stream);
+int bmb200_ctx_get_stream(const bmb200_ctx* ctx, void** cuda_stream);
+int bmb200_ctx_sync(bmb200_ctx* ctx);
+/* number of kernels this context has launched so far */
+int bmb200_ctx_launch_count(const bmb200_ctx* ctx, uint64_t* out);
+int bmb200_device_info(const bmb200_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, uint64_t* hbm_bytes);
+
+/* ---------------- sets ---------------- */
+/* copy a packed set from HOST memory (pinned or pageable) into HBM */
+int bmb200_set_upload(bmb200_ctx* ctx, const bmb200_packed_set* host, bmb200_set** out);
+/* gather per-vector block pointers (the host block tree) into a packed device set */
+int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks,
+                              const bmb200_vec_blocks* vecs, bmb200_set** out);
+/* adopt pointers that already live in HBM (caller keeps ownership of the memory) */
+int bmb200_set_adopt_device(bmb200_ctx* ctx, const bmb200_packed_set* dev, bmb200_set** out);
+/* sizes: total bit blocks, total GAP 16-B units, stored bytes of all source blocks */
+int bmb200_set_info(const bmb200_set* set, uint32_t* n_vec, uint32_t* n_blocks,
+                    uint64_t* n_bit_blocks, uint64_t* n_gap_units);
+/* copy columns [nb_from, nb_to) back to caller-provided host buffers.
+ * desc: (nb_to-nb_from)*n_vec u32; bit_base/gap_base: (nb_to-nb_from+1) u64, rebased to 0;
+ * bit_pool / gap_pool sized from bmb200_set_column_sizes. */
+int bmb200_set_column_sizes(const bmb200_set* set, uint32_t nb_from, uint32_t nb_to,
+                            uint64_t* n_bit_blocks, uint64_t* n_gap_units);
+int bmb200_set_download(const bmb200_set* set, uint32_t nb_from, uint32_t nb_to,
+                        uint32_t* desc, uint64_t* bit_base, uint64_t* gap_base,
+                        uint32_t* bit_pool, uint16_t* gap_pool);
+/* device addresses of the packed arrays (for torch / NCCL interop) */
+int bmb200_set_device_ptrs(const bmb200_set* set, bmb200_packed_set* out);
+int bmb200_set_free(bmb200_set* set);
+
+/* synthetic input generator (bench / test support): vector v has iid bit density
+ * density[v], counter-based RNG keyed by seed[v]; with optimize != 0 every block is
+ * stored the way bvector::optimize(opt_compress) would store it (NULL/FULL/GAP/BIT). */
+int bmb200_synth_set(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks,
+                     const double* density, const uint64_t* seed, int optimize,
+                     bmb200_set** out);
+
+/* ---------------- aggregation ---------------- */
+/* asynchronous on the context stream; result stays in HBM until fetched or freed.
+ * *reuse (may be NULL): pass a previous result of the same shape to recycle its buffers. */
+int bmb200_aggregate(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_agg_args* args,
+                     bmb200_result** inout);
+/* classify every result column like opt_copy_bit_block and convert runs < 1276 to GAP on device */
+int bmb200_result_optimize(bmb200_result* res);
+/* total popcount over all columns and "any bit found" (combine_and_sub's return value) */
+int bmb200_result_total(bmb200_result* res, uint64_t* total, int* any);
+int bmb200_result_fetch_meta(bmb200_result* res, const bmb200_result_meta* out);
+/* sizes of the compacted result: BIT blocks and GAP u16 words (each GAP block padded to 8 words) */
+int bmb200_result_sizes(bmb200_result* res, uint64_t* n_bit_blocks, uint64_t* n_gap_words);
+/* compacted result in per-vector flat form: off[c] = index into bits (blocks) for BIT columns,
+ * offset into gaps (u16 words) for GAP columns */
+int bmb200_result_fetch(bmb200_result* res, uint8_t* kind, uint64_t* off,
+                        uint32_t* bits, uint16_t* gaps);
+/* device addresses: blocks [n_cols][2048] u32, popcnt [n_cols] u32, digest [n_cols] u64, flag [n_cols] u8 */
+int bmb200_result_device_ptrs(const bmb200_result* res, void** blocks, void** popcnt,
+                              void** digest, void** flag, uint32_t* n_cols);
+int bmb200_result_free(bmb200_result* res);
+
+/* end-to-end convenience: HOST packed set in, HOST metadata out, in one call
+ * (H2D of the set, kernel, D2H of kind/popcnt/digest [+ result blocks when bits != NULL]) */
+int bmb200_aggregate_host(bmb200_ctx* ctx, const bmb200_packed_set* host,
+                          const bmb200_agg_args* args, const bmb200_result_meta* meta_out,
+                          uint64_t* total_out);
+
+/* ---------------- rank / select ---------------- */
+/* build the rs_index of vector `vec` of `set`; the set must outlive the index */
+int bmb200_rs_build(bmb200_ctx* ctx, const bmb200_set* set, uint32_t vec, bmb200_rs** out);
+/* index fields exactly as rs_index::register_super_block receives them (src/bmrs.h:688):
+ * bcount[n_blocks] u32, sub_count[n_blocks] u64 (first | second<<16 | aux0<<32 | aux1<<48),
+ * sb_count[n_superblocks+1] u64 running totals (sblock_count_) */
+int bmb200_rs_export(bmb200_rs* rs, uint32_t* bcount, uint64_t* sub_count, uint64_t* sb_count);
+int bmb200_rs_total(bmb200_rs* rs, uint64_t* total_bits_set);
+/* inclusive rank: out[q] = number of set bits in [0, pos[q]]   (bvector::count_to) */
+int bmb200_rank_batch(bmb200_rs* rs, const uint64_t* pos, uint64_t n, uint64_t* out);
+/* 1-based select: found[q] = 0 for rank 0 or rank > count      (bvector::select)   */
+int bmb200_select_batch(bmb200_rs* rs, const uint64_t* rank, uint64_t n, uint64_t* pos, uint8_t* found);
+/* same, queries and answers already in HBM (asynchronous on the context stream) */
+int bmb200_rank_batch_dev(bmb200_rs* rs, const uint64_t* d_pos, uint64_t n, uint64_t* d_out);
+int bmb200_select_batch_dev(bmb200_rs* rs, const uint64_t* d_rank, uint64_t n, uint64_t* d_pos, uint8_t* d_found);
+int bmb200_rs_free(bmb200_rs* rs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BMB200_H_INCLUDED */

@@ -1,0 +1,83 @@
+"""Seeded input generators shared by the tests (host-side numpy only)."""
+from __future__ import annotations
+
+import numpy as np
+
+import bitmagic_b200 as bm
+from bitmagic_b200.hostfmt import bits_to_gap, bits_to_words, BLOCK_BITS
+
+
+def gap_from_runs(ends, first):
+    """GAP block from explicit inclusive run ends (last must be 65535) and first-run value."""
+    ends = np.asarray(ends, dtype=np.uint16)
+    n = ends.size
+    out = np.empty(n + 1, dtype=np.uint16)
+    out[1:] = ends
+    lvl = 0 if n <= 124 else 1 if n <= 252 else 2 if n <= 508 else 3
+    out[0] = (first & 1) | (lvl << 1) | (n << 3)
+    return out
+
+
+def block_with_runs(rng, n_runs):
+    """Bit-block (words) with exactly n_runs runs at random boundaries."""
+    cuts = np.sort(rng.choice(np.arange(1, BLOCK_BITS), size=n_runs - 1, replace=False)) if n_runs > 1 else np.zeros(0, int)
+    bits = np.zeros(BLOCK_BITS, np.uint8)
+    val = int(rng.integers(0, 2))
+    prev = 0
+    for c in list(cuts) + [BLOCK_BITS]:
+        bits[prev:c] = val
+        val ^= 1
+        prev = c
+    return bits_to_words(bits)
+
+
+def mixed_vectors(rng, n_vec, n_blocks, p_null=0.15, p_full=0.05, p_gap=0.4):
+    """Vectors whose blocks mix NULL / FULL / bit / GAP with varied densities and run structures."""
+    vecs = []
+    for _ in range(n_vec):
+        v = bm.BVector(n_blocks)
+        dens = float(10 ** rng.uniform(-3.3, -0.3))
+        for nb in range(n_blocks):
+            u = rng.random()
+            if u < p_null:
+                continue
+            if u < p_null + p_full:
+                v.set_full(nb)
+            elif u < p_null + p_full + p_gap:
+                style = rng.integers(0, 5)
+                if style == 0:      # sparse random bits
+                    w = bits_to_words(rng.random(BLOCK_BITS) < min(dens, 0.008))
+                elif style == 1:    # few long runs
+                    w = block_with_runs(rng, int(rng.integers(1, 40)))
+                elif style == 2:    # many runs, near the GAP limit
+                    w = block_with_runs(rng, int(rng.integers(900, 1276)))
+                elif style == 3:    # word-aligned runs
+                    bits = np.zeros(BLOCK_BITS, np.uint8)
+                    for s in rng.choice(2048, size=20, replace=False):
+                        bits[s * 32:(s + int(rng.integers(1, 6))) * 32] = 1
+                    w = bits_to_words(bits)
+                else:               # inverse of sparse (mostly ones)
+                    w = bits_to_words(rng.random(BLOCK_BITS) >= 0.003)
+                g = bits_to_gap(w)
+                if (int(g[0]) >> 3) < 1276:
+                    v.set_gap(nb, g)
+                else:
+                    v.set_bits(nb, w)
+            else:
+                v.set_bits(nb, bits_to_words(rng.random(BLOCK_BITS) < dens))
+        vecs.append(v)
+    return vecs
+
+
+def edge_vectors(n_blocks=4):
+    """Hand-made edge cases: all-zero / all-one GAP blocks, single-bit runs at word borders, FULL, NULL."""
+    vs = []
+    v = bm.BVector(n_blocks); v.set_gap(0, gap_from_runs([65535], 0)); v.set_gap(1, gap_from_runs([65535], 1)); vs.append(v)
+    v = bm.BVector(n_blocks); v.set_gap(0, gap_from_runs([0, 65535], 1)); v.set_gap(1, gap_from_runs([65534, 65535], 0))
+    v.set_gap(2, gap_from_runs([30, 31, 32, 63, 64, 65535], 0)); vs.append(v)
+    v = bm.BVector(n_blocks); v.set_full(0); v.set_full(2); v.set_bits(1, np.full(2048, 0xFFFFFFFF, np.uint32)); vs.append(v)
+    v = bm.BVector(n_blocks); v.set_bits(0, np.full(2048, 0xAAAAAAAA, np.uint32)); v.set_bits(3, np.full(2048, 0x55555555, np.uint32)); vs.append(v)
+    v = bm.BVector(n_blocks); w = np.zeros(2048, np.uint32); w[0] = 1; w[2047] = 0x80000000; v.set_bits(1, w)
+    v.set_gap(3, gap_from_runs([21823, 21824, 43647, 43648, 65535], 1)); vs.append(v)
+    v = bm.BVector(n_blocks); vs.append(v)   # all NULL
+    return vs

@@ -1,0 +1,178 @@
+"""ctypes access to the CHECKERS (test infrastructure): oracle/liboracle.so (plain-C restatement) and, when
+present, oracle/_ref/libbmref*.so (the unmodified reference compiled from /root/reference/src).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference may import this."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from bitmagic_b200.capi import (AggArgsC, BLOCK_WORDS, GAP_MAX_WORDS, PackedSetC, packed_c, ptr)
+
+ROOT = Path(__file__).resolve().parent.parent
+ORACLE_DIR = ROOT / "oracle"
+
+_oracle = None
+_ref = {}
+
+
+def oracle() -> C.CDLL:
+    global _oracle
+    if _oracle is None:
+        so = ORACLE_DIR / "liboracle.so"
+        src = ORACLE_DIR / "bm_oracle.c"
+        if not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
+            subprocess.run(["make", "-C", str(ORACLE_DIR), str(so)], check=True, capture_output=True)
+        _oracle = C.CDLL(str(so))
+        _oracle.orc_bit_block_count.restype = C.c_uint32
+        _oracle.orc_block_digest.restype = C.c_uint64
+        _oracle.orc_bit_block_calc_change.restype = C.c_uint32
+        _oracle.orc_bit_to_gap.restype = C.c_uint32
+        _oracle.orc_gap_bit_count.restype = C.c_uint32
+        _oracle.orc_gap_bfind.restype = C.c_uint32
+        _oracle.orc_gap_bit_count_range.restype = C.c_uint32
+        _oracle.orc_bit_block_count_range.restype = C.c_uint32
+    return _oracle
+
+
+def have_ref(addr64: bool = False) -> bool:
+    return (ORACLE_DIR / "_ref" / ("libbmref64.so" if addr64 else "libbmref.so")).exists()
+
+
+def ref(addr64: bool = False) -> C.CDLL:
+    key = bool(addr64)
+    if key not in _ref:
+        so = ORACLE_DIR / "_ref" / ("libbmref64.so" if addr64 else "libbmref.so")
+        lib = C.CDLL(str(so))
+        lib.ref_simd.restype = C.c_char_p
+        _ref[key] = lib
+    return _ref[key]
+
+
+def _args(op, g0, g1, flags, nb_from=0, nb_to=0):
+    g0 = np.ascontiguousarray(g0, dtype=np.uint32)
+    g1 = np.ascontiguousarray(g1 if g1 is not None else [], dtype=np.uint32)
+    a = AggArgsC(int(op), int(flags), ptr(g0) if g0.size else C.c_void_p(0), g0.size,
+                 ptr(g1) if g1.size else C.c_void_p(0), g1.size, int(nb_from), int(nb_to))
+    return a, (g0, g1)
+
+
+def _pc(ps) -> PackedSetC:
+    return packed_c(ps.n_vec, ps.n_blocks, ps.desc, ps.bit_base, ps.gap_base, ps.bit_pool, ps.gap_pool)
+
+
+def oracle_aggregate(ps, op, g0, g1=None, flags=0, nb_from=0, nb_to=0):
+    """-> kind, popcnt, digest, nruns, blocks[n_cols][2048], gaps[n_cols][1280]"""
+    n = (nb_to if nb_to else ps.n_blocks) - nb_from
+    a, keep = _args(op, g0, g1, flags, nb_from, nb_to)
+    kind = np.zeros(n, np.uint8); pop = np.zeros(n, np.uint32); dig = np.zeros(n, np.uint64); nr = np.zeros(n, np.uint32)
+    blocks = np.zeros((n, BLOCK_WORDS), np.uint32); gaps = np.zeros((n, GAP_MAX_WORDS), np.uint16)
+    c = _pc(ps)
+    rc = oracle().orc_aggregate(C.byref(c), C.byref(a), ptr(kind), ptr(pop), ptr(dig), ptr(nr), ptr(blocks), ptr(gaps))
+    assert rc == 0, f"orc_aggregate rc={rc}"
+    return kind, pop, dig, nr, blocks, gaps
+
+
+def ref_aggregate(ps, op, g0, g1=None, flags=0, horizontal=False, addr64=False):
+    """The real reference -> kind, popcnt, blocks, gaps, any"""
+    n = ps.n_blocks
+    a, keep = _args(op, g0, g1, flags)
+    kind = np.zeros(n, np.uint8); pop = np.zeros(n, np.uint32)
+    blocks = np.zeros((n, BLOCK_WORDS), np.uint32); gaps = np.zeros((n, GAP_MAX_WORDS), np.uint16)
+    any_ = C.c_int(0)
+    c = _pc(ps)
+    if horizontal:
+        rc = ref(addr64).ref_aggregate_horizontal(C.byref(c), C.byref(a), ptr(kind), ptr(pop), ptr(blocks))
+    else:
+        rc = ref(addr64).ref_aggregate(C.byref(c), C.byref(a), ptr(kind), ptr(pop), ptr(blocks), ptr(gaps), C.byref(any_))
+    assert rc == 0, f"ref_aggregate rc={rc}"
+    return kind, pop, blocks, gaps, bool(any_.value)
+
+
+def ref_binop(ps, op, va, vb, compress=False):
+    """op: 0 OR 1 AND 2 SUB 3 XOR (bvector::bit_* 3-operand) -> kind, popcnt, blocks, count"""
+    n = ps.n_blocks
+    kind = np.zeros(n, np.uint8); pop = np.zeros(n, np.uint32); blocks = np.zeros((n, BLOCK_WORDS), np.uint32)
+    cnt = C.c_uint64(0)
+    c = _pc(ps)
+    rc = ref().ref_binop(C.byref(c), int(op), int(va), int(vb), int(compress), ptr(kind), ptr(pop), ptr(blocks), C.byref(cnt))
+    assert rc == 0
+    return kind, pop, blocks, cnt.value
+
+
+def ref_count_op(ps, op, va, vb) -> int:
+    out = C.c_uint64(0)
+    c = _pc(ps)
+    rc = ref().ref_count_op(C.byref(c), int(op), int(va), int(vb), C.byref(out))
+    assert rc == 0
+    return out.value
+
+
+def ref_optimize(ps, v):
+    n = ps.n_blocks
+    kind = np.zeros(n, np.uint8); pop = np.zeros(n, np.uint32)
+    blocks = np.zeros((n, BLOCK_WORDS), np.uint32); gaps = np.zeros((n, GAP_MAX_WORDS), np.uint16)
+    c = _pc(ps)
+    rc = ref().ref_optimize(C.byref(c), int(v), ptr(kind), ptr(pop), ptr(blocks), ptr(gaps))
+    assert rc == 0
+    return kind, pop, blocks, gaps
+
+
+def oracle_rs_build(ps, v):
+    nb = ps.n_blocks; nsb = (nb + 255) // 256
+    bc = np.zeros(nb, np.uint32); sc = np.zeros(nb, np.uint64); sb = np.zeros(nsb + 1, np.uint64)
+    c = _pc(ps)
+    rc = oracle().orc_rs_build(C.byref(c), int(v), ptr(bc), ptr(sc), ptr(sb))
+    assert rc == 0
+    return bc, sc, sb
+
+
+def ref_rs_build(ps, v, addr64=False):
+    nb = ps.n_blocks; nsb = (nb + 255) // 256
+    bc = np.zeros(nb, np.uint32); sc = np.zeros(nb, np.uint64); sb = np.zeros(nsb + 1, np.uint64)
+    tot = C.c_uint64(0)
+    c = _pc(ps)
+    rc = ref(addr64).ref_rs_build(C.byref(c), int(v), ptr(bc), ptr(sc), ptr(sb), C.byref(tot))
+    assert rc == 0
+    return bc, sc, sb, tot.value
+
+
+def oracle_rank(ps, v, pos):
+    p = np.ascontiguousarray(pos, dtype=np.uint64); out = np.zeros(p.size, np.uint64)
+    c = _pc(ps)
+    rc = oracle().orc_rank_batch(C.byref(c), int(v), ptr(p), C.c_uint64(p.size), ptr(out))
+    assert rc == 0
+    return out
+
+
+def oracle_select(ps, v, rank):
+    r = np.ascontiguousarray(rank, dtype=np.uint64)
+    pos = np.zeros(r.size, np.uint64); found = np.zeros(r.size, np.uint8)
+    c = _pc(ps)
+    rc = oracle().orc_select_batch(C.byref(c), int(v), ptr(r), C.c_uint64(r.size), ptr(pos), ptr(found))
+    assert rc == 0
+    return pos, found.astype(bool)
+
+
+def ref_rank_select(ps, v, pos, rank, addr64=False):
+    """-> rank_out, pos_out, found, (sec_build, sec_rank, sec_select)"""
+    p = np.ascontiguousarray(pos, dtype=np.uint64); r = np.ascontiguousarray(rank, dtype=np.uint64)
+    ro = np.zeros(p.size, np.uint64); po = np.zeros(r.size, np.uint64); fo = np.zeros(r.size, np.uint8)
+    tb, tr, ts = C.c_double(0), C.c_double(0), C.c_double(0)
+    c = _pc(ps)
+    rc = ref(addr64).ref_rank_select(C.byref(c), int(v), ptr(p), C.c_uint64(p.size), ptr(ro),
+                                     ptr(r), C.c_uint64(r.size), ptr(po), ptr(fo),
+                                     C.byref(tb), C.byref(tr), C.byref(ts))
+    assert rc == 0
+    return ro, po, fo.astype(bool), (tb.value, tr.value, ts.value)
+
+
+def ref_time_aggregate(ps, op, g0, g1=None, flags=0, threads=1, repeats=3, nb_from=0, nb_to=0, addr64=False):
+    a, keep = _args(op, g0, g1, flags, nb_from, nb_to)
+    best = C.c_double(0); tot = C.c_uint64(0)
+    c = _pc(ps)
+    rc = ref(addr64).ref_time_aggregate(C.byref(c), C.byref(a), int(threads), int(repeats), C.byref(best), C.byref(tot))
+    assert rc == 0
+    return best.value, tot.value

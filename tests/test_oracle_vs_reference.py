@@ -1,0 +1,170 @@
+"""Pins oracle/bm_oracle.c (the plain-C restatement) against the UNMODIFIED reference compiled from
+/root/reference/src (oracle/_ref/libbmref.so).  Runs wherever the prebuilt reference library is present
+(this container; the GPU box when the built .so travelled with the repo); the committed fixtures in
+tests/golden/ cover the case where it is not (tests/test_golden.py)."""
+import numpy as np
+import pytest
+
+import bitmagic_b200 as bm
+import gen
+import orclib
+
+needs_ref = pytest.mark.skipif(not orclib.have_ref(), reason="oracle/_ref/libbmref.so not built")
+
+OPS = [(bm.OP_OR, "or"), (bm.OP_AND, "and"), (bm.OP_AND_SUB, "and_sub")]
+
+
+def _groups(rng, n_vec, op):
+    if op == bm.OP_AND_SUB:
+        na = int(rng.integers(1, 4))
+        perm = rng.permutation(n_vec)
+        return perm[:na], perm[na:]
+    if op == bm.OP_AND:
+        return rng.permutation(n_vec)[: int(rng.integers(2, 5))], None
+    return rng.permutation(n_vec)[: int(rng.integers(1, n_vec + 1))], None
+
+
+@needs_ref
+@pytest.mark.parametrize("op,name", OPS)
+@pytest.mark.parametrize("compress", [0, 1])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_aggregate_oracle_matches_reference(op, name, compress, seed):
+    rng = np.random.default_rng(1000 * op + 10 * seed + compress)
+    kw = dict(p_null=0.05, p_full=0.03) if op != bm.OP_OR else {}
+    vecs = gen.mixed_vectors(rng, 10, 5, **kw)
+    ps = bm.PackedSet.pack(vecs)
+    g0, g1 = _groups(rng, 10, op)
+    flags = bm.F_OPT_COMPRESS if (compress or op == bm.OP_AND_SUB) else 0   # combine_and_sub always compresses
+    okind, opop, odig, onr, oblk, ogap = orclib.oracle_aggregate(ps, op, g0, g1, flags)
+    rkind, rpop, rblk, rgap, rany = orclib.ref_aggregate(ps, op, g0, g1, flags)
+    assert np.array_equal(oblk, rblk)              # compare()==0
+    assert np.array_equal(opop, rpop)              # count()
+    assert np.array_equal(okind, rkind)            # calc_stat block kinds
+    is_gap = okind == bm.BLK_GAP
+    for c in np.flatnonzero(is_gap):
+        n = (int(ogap[c, 0]) >> 3) + 1
+        assert np.array_equal(ogap[c, :n], rgap[c, :n])
+    assert rany == bool(opop.sum())
+    # the reference's own independent check: the "horizontal" path (tests/stress/t.cpp:10887-10921)
+    hkind, hpop, hblk, _, _ = orclib.ref_aggregate(ps, op, g0, g1, flags, horizontal=True)
+    assert np.array_equal(oblk, hblk)
+
+
+@needs_ref
+def test_aggregate_edge_cases_match_reference():
+    vecs = gen.edge_vectors(4)
+    ps = bm.PackedSet.pack(vecs)
+    n = len(vecs)
+    cases = [(bm.OP_OR, list(range(n)), None), (bm.OP_OR, [0, 1], None), (bm.OP_OR, [5], None),
+             (bm.OP_OR, [3, 4], None), (bm.OP_AND, [2, 3], None), (bm.OP_AND, [0, 2], None),
+             (bm.OP_AND, [2, 2], None), (bm.OP_AND_SUB, [2], [0]), (bm.OP_AND_SUB, [2], [5]),
+             (bm.OP_AND_SUB, [2, 3], [1, 4]), (bm.OP_AND_SUB, [3], [2]), (bm.OP_AND_SUB, [1], [])]
+    for op, g0, g1 in cases:
+        for flags in (0, bm.F_OPT_COMPRESS):
+            if op == bm.OP_AND_SUB:
+                flags = bm.F_OPT_COMPRESS
+            okind, opop, odig, onr, oblk, ogap = orclib.oracle_aggregate(ps, op, g0, g1, flags)
+            rkind, rpop, rblk, rgap, rany = orclib.ref_aggregate(ps, op, g0, g1, flags)
+            assert np.array_equal(oblk, rblk), (op, g0, g1)
+            assert np.array_equal(opop, rpop), (op, g0, g1)
+            assert np.array_equal(okind, rkind), (op, g0, g1, flags, okind, rkind)
+
+
+@needs_ref
+def test_xor_matches_reference_bit_xor():
+    rng = np.random.default_rng(5)
+    vecs = gen.mixed_vectors(rng, 6, 4)
+    ps = bm.PackedSet.pack(vecs)
+    for a, b in [(0, 1), (2, 3), (4, 5), (1, 1)]:
+        okind, opop, odig, onr, oblk, _ = orclib.oracle_aggregate(ps, bm.OP_XOR, [a, b], None, bm.F_OPT_COMPRESS)
+        rkind, rpop, rblk, rcnt = orclib.ref_binop(ps, 3, a, b, compress=True)
+        assert np.array_equal(oblk, rblk)
+        assert int(opop.sum()) == rcnt == orclib.ref_count_op(ps, 3, a, b)
+    # 3-way chain
+    _, opop, _, _, oblk, _ = orclib.oracle_aggregate(ps, bm.OP_XOR, [0, 1, 2], None, 0)
+    _, _, rblk, _, _ = orclib.ref_aggregate(ps, bm.OP_XOR, [0, 1, 2], None, 0)
+    assert np.array_equal(oblk, rblk)
+
+
+@needs_ref
+def test_two_operand_ops_match_reference():
+    rng = np.random.default_rng(11)
+    vecs = gen.mixed_vectors(rng, 4, 6)
+    ps = bm.PackedSet.pack(vecs)
+    for a, b in [(0, 1), (2, 3), (1, 2)]:
+        for refop, op, g0, g1 in [(0, bm.OP_OR, [a, b], None), (1, bm.OP_AND, [a, b], None), (2, bm.OP_AND_SUB, [a], [b])]:
+            _, opop, _, _, oblk, _ = orclib.oracle_aggregate(ps, op, g0, g1, 0)
+            _, rpop, rblk, rcnt = orclib.ref_binop(ps, refop, a, b)
+            assert np.array_equal(oblk, rblk)
+            assert int(opop.sum()) == rcnt == orclib.ref_count_op(ps, refop, a, b)
+
+
+@needs_ref
+def test_optimize_classification_and_bit_to_gap():
+    """calc_change / bit_to_gap / the opt_compress classification vs bvector::optimize on the reference."""
+    rng = np.random.default_rng(3)
+    v = bm.BVector(8)
+    for nb, runs in enumerate([1, 2, 3, 1274, 1275, 1276, 1277, 4000]):
+        v.set_bits(nb, gen.block_with_runs(rng, runs))
+    ps = bm.PackedSet.pack([v])
+    rkind, rpop, rblk, rgap = orclib.ref_optimize(ps, 0)
+    import ctypes as C
+    for nb in range(8):
+        w = np.ascontiguousarray(v.blocks[nb])
+        runs = orclib.oracle().orc_bit_block_calc_change(orclib.ptr(w))
+        exp = bm.BLK_GAP if 1 < runs < 1276 else bm.BLK_BIT
+        if runs == 1:
+            exp = bm.BLK_FULL if w[0] else bm.BLK_NULL
+        assert rkind[nb] == exp, (nb, runs, rkind[nb])
+        if exp == bm.BLK_GAP:
+            out = np.zeros(70000, np.uint16)
+            ln = orclib.oracle().orc_bit_to_gap(orclib.ptr(out), orclib.ptr(w))
+            assert ln == runs
+            assert np.array_equal(out[:ln + 1], rgap[nb, :ln + 1])
+            # host mirror (product-side numpy helper) agrees too
+            assert np.array_equal(bm.hostfmt.bits_to_gap(w), out[:ln + 1])
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [1, 2])
+def test_rs_index_and_queries_match_reference(seed):
+    rng = np.random.default_rng(seed)
+    vecs = gen.mixed_vectors(rng, 3, 600, p_null=0.2, p_full=0.1, p_gap=0.4) + gen.edge_vectors(600)[:5]
+    ps = bm.PackedSet.pack(vecs)
+    for v in range(ps.n_vec):
+        obc, osc, osb = orclib.oracle_rs_build(ps, v)
+        rbc, rsc, rsb, rtot = orclib.ref_rs_build(ps, v)
+        if rtot == 0:
+            assert obc.sum() == 0
+            continue
+        assert np.array_equal(obc, rbc)
+        nz = rbc > 0          # the reference does not define sub_count for NULL blocks beyond 0
+        assert np.array_equal(osc[nz], rsc[nz])
+        assert np.array_equal(osb, rsb)
+        pos = rng.integers(0, 600 * 65536, 3000).astype(np.uint64)
+        rank = rng.integers(0, rtot + 3, 3000).astype(np.uint64)
+        rr, rp, rf, _ = orclib.ref_rank_select(ps, v, pos, rank)
+        assert np.array_equal(orclib.oracle_rank(ps, v, pos), rr)
+        op, of = orclib.oracle_select(ps, v, rank)
+        assert np.array_equal(of, rf)
+        assert np.array_equal(op[of], rp[rf])
+
+
+@needs_ref
+def test_reference_known_answers_sample16():
+    """samples/bvsample16/sample16.cpp:95-130 expected outputs:
+    OR -> 0..10,10000,20000 ; AND -> 10000,20000 ; AND-SUB -> 20000."""
+    nbk = 1
+    def mk(pos):
+        return bm.BVector.from_positions(pos, nbk)
+    bv1 = mk([1, 2, 3, 10000, 20000]); bv2 = mk([0, 4, 5, 6, 10000, 20000]); bv3 = mk([7, 8, 9, 10, 10000, 20000])
+    bv4 = mk([10000]);
+    ps = bm.PackedSet.pack([bv1, bv2, bv3, bv4])
+    for chk in ("oracle", "ref"):
+        f = (lambda *a: orclib.oracle_aggregate(*a)[4]) if chk == "oracle" else (lambda *a: orclib.ref_aggregate(*a)[2])
+        blk = f(ps, bm.OP_OR, [0, 1, 2], None, 0)
+        assert list(np.flatnonzero(bm.hostfmt.words_to_bits(blk[0]))) == list(range(11)) + [10000, 20000]
+        blk = f(ps, bm.OP_AND, [0, 1, 2], None, 0)
+        assert list(np.flatnonzero(bm.hostfmt.words_to_bits(blk[0]))) == [10000, 20000]
+        blk = f(ps, bm.OP_AND_SUB, [0, 1, 2], [3], bm.F_OPT_COMPRESS)
+        assert list(np.flatnonzero(bm.hostfmt.words_to_bits(blk[0]))) == [20000]
