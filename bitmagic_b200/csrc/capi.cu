@@ -25,6 +25,7 @@ struct bmb200_ctx {
     uint32_t* d_group = nullptr;            // group member ids
     size_t group_cap = 0;
     uint32_t* h_group = nullptr;            // pinned staging for the group ids
+    std::vector<uint32_t> last_group;       // ids currently resident in d_group (skip the re-upload when unchanged)
     int agg_ctas_per_sm = 2;
 };
 
@@ -528,18 +529,22 @@ int bmb200_aggregate(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_agg_ar
     if (ng > ctx->group_cap) {
         cudaStreamSynchronize(ctx->stream);
         cudaFree(ctx->d_group); if (ctx->h_group) cudaFreeHost(ctx->h_group);
-        ctx->d_group = nullptr; ctx->h_group = nullptr; ctx->group_cap = 0;
+        ctx->d_group = nullptr; ctx->h_group = nullptr; ctx->group_cap = 0; ctx->last_group.clear();
         size_t cap = ng < 1024 ? 1024 : ng;
         if (cudaMalloc((void**)&ctx->d_group, cap * 4) != cudaSuccess || cudaMallocHost((void**)&ctx->h_group, cap * 4) != cudaSuccess) {
             ctx->last_err = "group buffer allocation"; if (!*inout) bmb200_result_free(r); return BMB200_ERR_BADALLOC;
         }
         ctx->group_cap = cap;
     }
-    if (ng) {
+    bool same = (ctx->last_group.size() == ng) && ng &&
+                memcmp(ctx->last_group.data(), a->group0, (size_t)a->n0 * 4) == 0 &&
+                (!n1 || memcmp(ctx->last_group.data() + a->n0, a->group1, (size_t)n1 * 4) == 0);
+    if (ng && !same) {
         cudaStreamSynchronize(ctx->stream);    // the staging buffer may still feed a previous launch
         memcpy(ctx->h_group, a->group0, (size_t)a->n0 * 4);
         if (n1) memcpy(ctx->h_group + a->n0, a->group1, (size_t)n1 * 4);
         CU(cudaMemcpyAsync(ctx->d_group, ctx->h_group, ng * 4, cudaMemcpyHostToDevice, ctx->stream));
+        try { ctx->last_group.assign(ctx->h_group, ctx->h_group + ng); } catch (...) { ctx->last_group.clear(); }
     }
     CU(cudaMemsetAsync(ctx->d_work, 0, 4, ctx->stream));
     CU(cudaMemsetAsync(r->total, 0, 8, ctx->stream));

@@ -1,0 +1,41 @@
+"""The oracle against the committed golden vectors (outputs of the unmodified reference)."""
+import numpy as np
+import pytest
+
+import bitmagic_b200 as bm
+import golden_util as gu
+import orclib
+
+
+@pytest.mark.parametrize("name", ["agg_mixed", "agg_edge", "agg_zipf"])
+def test_oracle_aggregate_vs_golden(name):
+    ps, cases = gu.load_agg(name)
+    for case in cases:
+        kind, pop, dig, nr, blk, gaps = orclib.oracle_aggregate(ps, case["op"], case["g0"], case["g1"], case["flags"])
+        glen = np.where(kind == bm.BLK_GAP, (gaps[:, 0] >> 3) + 1, 0)
+        flat = np.concatenate([gaps[c, :glen[c]] for c in range(len(kind))]) if glen.sum() else np.zeros(0, np.uint16)
+        # XOR fixtures come from chained bit_xor, whose block kinds follow a different storage rule
+        gu.check_agg_case(case, kind, pop, blk, flat if case["op"] != bm.OP_XOR else None, check_kind=case["op"] != bm.OP_XOR)
+        assert case["any"] == bool(pop.sum())
+        # digest / run-count are consistent with the result bits
+        for c in range(ps.n_blocks):
+            w = np.ascontiguousarray(blk[c])
+            assert dig[c] == sum(1 << i for i in range(64) if w[32 * i:32 * i + 32].any())
+            assert nr[c] == bm.hostfmt.calc_change(w)
+
+
+def test_oracle_rs_vs_golden():
+    ps, vs = gu.load_rs("rs_mixed")
+    for v, g in enumerate(vs):
+        bc, sc, sb = orclib.oracle_rs_build(ps, v)
+        if int(g["total"]) == 0:
+            assert bc.sum() == 0
+            continue
+        assert np.array_equal(bc, g["bcount"])
+        nz = g["bcount"] > 0
+        assert np.array_equal(sc[nz], g["sub"][nz])
+        assert np.array_equal(sb, g["sb"])
+        assert np.array_equal(orclib.oracle_rank(ps, v, g["pos"]), g["rank_out"])
+        pos, found = orclib.oracle_select(ps, v, g["rank"])
+        assert np.array_equal(found, g["sel_found"])
+        assert np.array_equal(pos[found], g["sel_pos"][g["sel_found"]])

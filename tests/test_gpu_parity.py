@@ -1,0 +1,280 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the oracle, the committed golden vectors
+and -- when the prebuilt reference library travelled with the repo -- the unmodified reference itself.
+Bar: bit-exact (all arithmetic is u16/u32/u64 integer)."""
+import numpy as np
+import pytest
+
+import bitmagic_b200 as bm
+import gen
+import golden_util as gu
+import orclib
+
+pytestmark = pytest.mark.gpu
+
+C = bm.F_OPT_COMPRESS
+
+
+def gpu_aggregate(ctx, ps, op, g0, g1, flags, dset=None):
+    own = dset is None
+    if own:
+        dset = bm.DeviceSet.upload(ctx, ps)
+    res = bm.aggregate(ctx, dset, op, g0, g1, flags)
+    kind, pop, dig, nr = res.meta()
+    total, any_ = res.total()
+    fk, off, bits, gaps = res.fetch()
+    assert np.array_equal(fk, kind)
+    bv = bm.result_to_bvector(fk, off, bits, gaps)
+    blocks = np.stack([bv.block_words(c) for c in range(kind.size)])
+    gflat = np.concatenate([bv.blocks[c] for c in range(kind.size) if kind[c] == bm.BLK_GAP]) \
+        if (kind == bm.BLK_GAP).any() else np.zeros(0, np.uint16)
+    res.free()
+    if own:
+        dset.free()
+    return dict(kind=kind, pop=pop, dig=dig, nr=nr, total=total, any=any_, blocks=blocks, gflat=gflat)
+
+
+def check_vs_oracle(ctx, ps, op, g0, g1, flags, dset=None):
+    got = gpu_aggregate(ctx, ps, op, g0, g1, flags, dset)
+    okind, opop, odig, onr, oblk, ogap = orclib.oracle_aggregate(ps, op, g0, g1, flags)
+    assert np.array_equal(got["blocks"], oblk)
+    assert np.array_equal(got["pop"], opop)
+    assert np.array_equal(got["dig"], odig)
+    assert np.array_equal(got["nr"], onr)
+    assert np.array_equal(got["kind"], okind)
+    assert got["total"] == int(opop.sum()) and got["any"] == bool(opop.sum())
+    glen = np.where(okind == bm.BLK_GAP, (ogap[:, 0] >> 3) + 1, 0)
+    oflat = np.concatenate([ogap[c, :glen[c]] for c in range(len(okind))]) if glen.sum() else np.zeros(0, np.uint16)
+    assert np.array_equal(got["gflat"], oflat)
+    return got
+
+
+@pytest.mark.parametrize("name", ["agg_mixed", "agg_edge", "agg_zipf"])
+def test_aggregate_vs_golden(ctx, name):
+    ps, cases = gu.load_agg(name)
+    dset = bm.DeviceSet.upload(ctx, ps)
+    for case in cases:
+        got = gpu_aggregate(ctx, ps, case["op"], case["g0"], case["g1"], case["flags"], dset)
+        xor = case["op"] == bm.OP_XOR
+        gu.check_agg_case(case, got["kind"], got["pop"], got["blocks"], None if xor else got["gflat"], check_kind=not xor)
+        assert got["any"] == case["any"]
+    dset.free()
+
+
+@pytest.mark.parametrize("op", [bm.OP_OR, bm.OP_AND, bm.OP_AND_SUB, bm.OP_XOR])
+@pytest.mark.parametrize("seed", [1, 2])
+def test_aggregate_random_mixed_vs_oracle(ctx, op, seed):
+    rng = np.random.default_rng(100 * op + seed)
+    kw = dict(p_null=0.04, p_full=0.03) if op in (bm.OP_AND, bm.OP_AND_SUB) else {}
+    vecs = gen.mixed_vectors(rng, 24, 9, **kw)
+    ps = bm.PackedSet.pack(vecs)
+    dset = bm.DeviceSet.upload(ctx, ps)
+    for trial in range(4):
+        perm = rng.permutation(24)
+        if op == bm.OP_AND_SUB:
+            na = int(rng.integers(1, 4)); g0, g1 = perm[:na], perm[na:na + int(rng.integers(0, 20))]
+        elif op == bm.OP_AND:
+            g0, g1 = perm[: int(rng.integers(1, 5))], None
+        else:
+            g0, g1 = perm[: int(rng.integers(1, 25))], None
+        for flags in (0, C):
+            check_vs_oracle(ctx, ps, op, g0, g1, flags, dset)
+    dset.free()
+
+
+def test_edge_cases(ctx):
+    vecs = gen.edge_vectors(4)
+    ps = bm.PackedSet.pack(vecs)
+    dset = bm.DeviceSet.upload(ctx, ps)
+    n = len(vecs)
+    cases = [(bm.OP_OR, list(range(n)), None), (bm.OP_OR, [0, 1], None), (bm.OP_OR, [5], None), (bm.OP_OR, [3, 4], None),
+             (bm.OP_OR, [2, 2], None), (bm.OP_AND, [2, 3], None), (bm.OP_AND, [0, 2], None), (bm.OP_AND, [2, 2], None),
+             (bm.OP_AND, [5, 2], None), (bm.OP_AND_SUB, [2], [0]), (bm.OP_AND_SUB, [2], [5]), (bm.OP_AND_SUB, [2, 3], [1, 4]),
+             (bm.OP_AND_SUB, [3], [2]), (bm.OP_AND_SUB, [1], []), (bm.OP_AND_SUB, [2], [1]), (bm.OP_XOR, [2, 3], None),
+             (bm.OP_XOR, [0, 1, 4], None), (bm.OP_XOR, [2, 2], None), (bm.OP_XOR, [5], None)]
+    for op, g0, g1 in cases:
+        for flags in (0, C):
+            check_vs_oracle(ctx, ps, op, g0, g1, flags, dset)
+    # count-only mode returns the same totals and stores nothing
+    res = bm.aggregate(ctx, dset, bm.OP_AND_SUB, [2, 3], [1, 4], bm.F_COUNT_ONLY)
+    _, opop, *_ = orclib.oracle_aggregate(ps, bm.OP_AND_SUB, [2, 3], [1, 4], 0)
+    assert res.total()[0] == int(opop.sum())
+    assert np.array_equal(res.meta()[1], opop)
+    res.free()
+    # column sub-range
+    res = bm.aggregate(ctx, dset, bm.OP_OR, list(range(n)), None, 0, nb_from=1, nb_to=3)
+    _, opop, *_ = orclib.oracle_aggregate(ps, bm.OP_OR, list(range(n)), None, 0, 1, 3)
+    assert np.array_equal(res.meta()[1], opop)
+    res.free()
+    dset.free()
+
+
+def test_large_groups_chunked_classification(ctx):
+    """> 1024 group members exercises the multi-chunk classification path; duplicates are legal."""
+    rng = np.random.default_rng(42)
+    vecs = [bm.BVector.random(3, 0.02 / (1 + k % 7), rng) for k in range(40)]
+    for k in range(10, 40):
+        vecs[k].optimize()
+    ps = bm.PackedSet.pack(vecs)
+    dset = bm.DeviceSet.upload(ctx, ps)
+    g = rng.integers(0, 40, 2500)
+    check_vs_oracle(ctx, ps, bm.OP_OR, g, None, C, dset)
+    check_vs_oracle(ctx, ps, bm.OP_AND_SUB, [0, 1], g, C, dset)
+    check_vs_oracle(ctx, ps, bm.OP_XOR, g[:1500], None, 0, dset)
+    dset.free()
+
+
+def test_upload_vectors_and_host_mirror_api(ctx):
+    """bm::aggregator-style surface: add/combine_*; 2-operand bit_*; count_*."""
+    rng = np.random.default_rng(9)
+    vecs = gen.mixed_vectors(rng, 8, 4)
+    ps = bm.PackedSet.pack(vecs)
+    agg = bm.Aggregator(ctx)
+    for v in vecs[:5]:
+        agg.add(v)
+    for v in vecs[5:]:
+        agg.add(v, 1)
+    agg.set_optimization(bm.OPT_COMPRESS)
+    t = agg.combine_or()
+    _, _, _, _, oblk, _ = orclib.oracle_aggregate(ps, bm.OP_OR, range(5), None, C)
+    assert np.array_equal(np.stack([t.block_words(c) for c in range(4)]), oblk)
+    t, found = agg.combine_and_sub()
+    okind, opop, _, _, oblk, _ = orclib.oracle_aggregate(ps, bm.OP_AND_SUB, range(5), range(5, 8), C)
+    assert np.array_equal(np.stack([t.block_words(c) for c in range(4)]), oblk) and found == bool(opop.sum())
+    assert np.array_equal(t.kind, okind)
+    a, b = vecs[0], vecs[1]
+    for f, op, g0, g1 in [(bm.bit_and, bm.OP_AND, [0, 1], None), (bm.bit_or, bm.OP_OR, [0, 1], None),
+                          (bm.bit_xor, bm.OP_XOR, [0, 1], None), (bm.bit_sub, bm.OP_AND_SUB, [0], [1])]:
+        r = f(a, b, ctx=ctx)
+        _, opop, _, _, oblk, _ = orclib.oracle_aggregate(ps, op, g0, g1, 0)
+        assert np.array_equal(np.stack([r.block_words(c) for c in range(4)]), oblk)
+        assert r.count() == int(opop.sum())
+    assert bm.count_and(a, b, ctx=ctx) == int(orclib.oracle_aggregate(ps, bm.OP_AND, [0, 1], None, 0)[1].sum())
+    assert bm.count_sub(a, b, ctx=ctx) == int(orclib.oracle_aggregate(ps, bm.OP_AND_SUB, [0], [1], 0)[1].sum())
+    assert agg.combine_or([]).n_blocks == 0 and agg.combine_and_sub([], [])[1] is False
+
+
+def test_aggregate_host_end_to_end_call(ctx):
+    rng = np.random.default_rng(3)
+    ps = bm.PackedSet.pack(gen.mixed_vectors(rng, 10, 6))
+    kind, pop, dig, nr, total = bm.aggregate_host(ctx, ps, bm.OP_AND_SUB, [0, 1], list(range(2, 10)), C)
+    okind, opop, odig, onr, *_ = orclib.oracle_aggregate(ps, bm.OP_AND_SUB, [0, 1], list(range(2, 10)), C)
+    assert np.array_equal(kind, okind) and np.array_equal(pop, opop) and np.array_equal(dig, odig) and total == int(opop.sum())
+
+
+def test_rs_index_rank_select_vs_golden(ctx):
+    ps, vs = gu.load_rs("rs_mixed")
+    dset = bm.DeviceSet.upload(ctx, ps)
+    for v, g in enumerate(vs):
+        rs = bm.DeviceRS(ctx, dset, v)
+        bc, sc, sb = rs.export()
+        assert rs.total() == int(g["total"])
+        if int(g["total"]):
+            assert np.array_equal(bc, g["bcount"])
+            nz = g["bcount"] > 0
+            assert np.array_equal(sc[nz], g["sub"][nz])
+            assert np.array_equal(sb, g["sb"])
+        assert np.array_equal(rs.rank(g["pos"]), g["rank_out"]) or int(g["total"]) == 0
+        pos, found = rs.select(g["rank"])
+        assert np.array_equal(found, g["sel_found"])
+        assert np.array_equal(pos[found], g["sel_pos"][g["sel_found"]])
+        rs.free()
+    dset.free()
+
+
+def test_rs_index_vs_oracle_including_full_and_edges(ctx):
+    rng = np.random.default_rng(17)
+    vecs = gen.mixed_vectors(rng, 4, 300, p_null=0.3, p_full=0.15, p_gap=0.3)
+    full = bm.BVector(300)
+    for nb in range(300):
+        full.set_full(nb)                       # RankFindTest: rank(i) == i+1, select(rank) == i  (t.cpp:4975-5090)
+    vecs.append(full)
+    ps = bm.PackedSet.pack(vecs)
+    dset = bm.DeviceSet.upload(ctx, ps)
+    for v in range(ps.n_vec):
+        rs = bm.DeviceRS(ctx, dset, v)
+        obc, osc, osb = orclib.oracle_rs_build(ps, v)
+        bc, sc, sb = rs.export()
+        assert np.array_equal(bc, obc) and np.array_equal(sc, osc) and np.array_equal(sb, osb)
+        pos = np.concatenate([rng.integers(0, 300 * 65536, 5000), [0, 65535, 65536, 300 * 65536 - 1, 300 * 65536 + 5]]).astype(np.uint64)
+        assert np.array_equal(rs.rank(pos), orclib.oracle_rank(ps, v, pos))
+        tot = rs.total()
+        rank = np.concatenate([rng.integers(0, tot + 2, 5000), [0, 1, tot, tot + 1]]).astype(np.uint64)
+        p, f = rs.select(rank)
+        op, of = orclib.oracle_select(ps, v, rank)
+        assert np.array_equal(f, of) and np.array_equal(p[f], op[of])
+        rs.free()
+    i = rng.integers(0, 300 * 65536, 1000).astype(np.uint64)
+    rs = bm.DeviceRS(ctx, dset, ps.n_vec - 1)
+    assert np.array_equal(rs.rank(i), i + 1)
+    p, f = rs.select(i + 1)
+    assert f.all() and np.array_equal(p, i)
+    rs.free()
+    dset.free()
+
+
+def test_synth_set_matches_its_own_contract(ctx):
+    """The device generator: kinds follow optimize(), sizes add up, and aggregation over it matches the oracle."""
+    nv, nbk = 64, 5
+    dens = np.array([0.5 / (k + 1) for k in range(nv)])
+    seed = np.arange(1000, 1000 + nv, dtype=np.uint64)
+    dset = bm.DeviceSet.synth(ctx, nv, nbk, dens, seed, True)
+    ps = dset.download()
+    kinds = ps.kinds()
+    assert (kinds[:, 0] == bm.BLK_BIT).all() and (kinds[:, -1] == bm.BLK_GAP).all()
+    for v in range(nv):
+        bv = ps.vector(v)
+        d = bv.count() / (nbk * 65536)
+        assert abs(d - dens[v]) < 0.02 + 0.1 * dens[v]
+        for nb in range(nbk):
+            k, data = ps.block(v, nb)
+            if k == bm.BLK_GAP:
+                assert (int(data[0]) >> 3) < 1276 and data[-1] == 65535 and (np.diff(data[1:].astype(int)) > 0).all()
+            if k == bm.BLK_BIT:
+                assert bm.hostfmt.calc_change(data) >= 1276
+    check_vs_oracle(ctx, ps, bm.OP_AND_SUB, [0, 1], list(range(2, nv)), C, dset)
+    check_vs_oracle(ctx, ps, bm.OP_OR, list(range(nv)), None, 0, dset)
+    d2 = bm.DeviceSet.synth(ctx, nv, nbk, dens, seed, True).download()    # deterministic
+    assert np.array_equal(d2.bit_pool, ps.bit_pool) and np.array_equal(d2.gap_pool, ps.gap_pool)
+    dset.free()
+
+
+@pytest.mark.skipif(not orclib.have_ref(), reason="prebuilt reference library not present")
+def test_against_unmodified_reference(ctx):
+    rng = np.random.default_rng(77)
+    vecs = gen.mixed_vectors(rng, 16, 6, p_null=0.05)
+    ps = bm.PackedSet.pack(vecs)
+    dset = bm.DeviceSet.upload(ctx, ps)
+    for op, g0, g1, flags in [(bm.OP_OR, range(16), None, 0), (bm.OP_OR, range(16), None, C), (bm.OP_AND, [0, 1, 2], None, C),
+                              (bm.OP_AND_SUB, [0, 1], range(2, 16), C)]:
+        got = gpu_aggregate(ctx, ps, op, list(g0), list(g1) if g1 is not None else None, flags, dset)
+        rkind, rpop, rblk, rgap, rany = orclib.ref_aggregate(ps, op, list(g0), list(g1) if g1 is not None else None, flags)
+        assert np.array_equal(got["blocks"], rblk) and np.array_equal(got["pop"], rpop) and np.array_equal(got["kind"], rkind)
+        assert got["any"] == rany
+    dset.free()
+
+
+def test_full_size_properties_c2_shape(ctx):
+    """BASELINE config 2 shape at reduced vector count but full block geometry: size-independent properties
+    (OR idempotence, AND-SUB subset/complement identities, checksum of popcounts vs sampled oracle columns)."""
+    nv, nbk = 64, 512
+    dens = np.full(nv, 0.05); seed = np.arange(100, 100 + nv, dtype=np.uint64)
+    dset = bm.DeviceSet.synth(ctx, nv, nbk, dens, seed, False)
+    r_or = bm.aggregate(ctx, dset, bm.OP_OR, np.arange(nv), None, 0)
+    r_or2 = bm.aggregate(ctx, dset, bm.OP_OR, np.concatenate([np.arange(nv), np.arange(nv)]), None, 0)   # idempotent
+    assert np.array_equal(r_or.meta()[1], r_or2.meta()[1])
+    # |A| = |A & B| + |A - B|
+    a = bm.aggregate(ctx, dset, bm.OP_OR, [0], None, bm.F_COUNT_ONLY).total()[0]
+    ab = bm.aggregate(ctx, dset, bm.OP_AND, [0, 1], None, bm.F_COUNT_ONLY).total()[0]
+    a_b = bm.aggregate(ctx, dset, bm.OP_AND_SUB, [0], [1], bm.F_COUNT_ONLY).total()[0]
+    assert a == ab + a_b
+    # |A ^ B| = |A | B| - |A & B|
+    x = bm.aggregate(ctx, dset, bm.OP_XOR, [0, 1], None, bm.F_COUNT_ONLY).total()[0]
+    o = bm.aggregate(ctx, dset, bm.OP_OR, [0, 1], None, bm.F_COUNT_ONLY).total()[0]
+    assert x == o - ab
+    # sampled columns against the oracle
+    pop = r_or.meta()[1]
+    for nb in (0, 255, 256, 511):
+        ps = dset.download(nb, nb + 1)
+        _, opop, *_ = orclib.oracle_aggregate(ps, bm.OP_OR, np.arange(nv), None, 0)
+        assert pop[nb] == opop[0]
+    dset.free()
