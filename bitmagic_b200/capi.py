@@ -27,7 +27,7 @@ F_COUNT_ONLY, F_OPT_NONE, F_OPT_COMPRESS = 1, 0, 2
 # every symbol include/bmb200.h declares (checked by tests/test_cabi_symbols.py)
 SYMBOLS = [
     "bmb200_init", "bmb200_destroy", "bmb200_error_msg", "bmb200_last_error", "bmb200_ctx_set_stream",
-    "bmb200_ctx_get_stream", "bmb200_ctx_sync", "bmb200_ctx_launch_count", "bmb200_device_info",
+    "bmb200_ctx_get_stream", "bmb200_ctx_sync", "bmb200_ctx_launch_count", "bmb200_device_info", "bmb200_ctx_set_tuning",
     "bmb200_set_upload", "bmb200_set_upload_vectors", "bmb200_set_adopt_device", "bmb200_set_info",
     "bmb200_set_column_sizes", "bmb200_set_download", "bmb200_set_device_ptrs", "bmb200_set_free",
     "bmb200_synth_set", "bmb200_aggregate", "bmb200_result_optimize", "bmb200_result_total",
@@ -145,6 +145,9 @@ class Context:
         s = C.c_void_p(0)
         self.check(lib().bmb200_ctx_get_stream(self._h, C.byref(s)), "ctx_get_stream")
         return int(s.value or 0)
+
+    def set_tuning(self, key: int, value: int):
+        self.check(lib().bmb200_ctx_set_tuning(self._h, int(key), int(value)), "ctx_set_tuning")
 
     def launch_count(self) -> int:
         n = C.c_uint64(0)

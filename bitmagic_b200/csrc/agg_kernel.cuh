@@ -1,24 +1,28 @@
 // agg_kernel.cuh -- N-way block-column aggregation kernel (OR / AND / AND-SUB / XOR) for sm_100a.
 //
 // Replaces, for one block column (i,j) per CTA iteration, the reference's
-//   sort_input_blocks_or/_and      src/bmaggregator.h:2278-2366   (classification pass, warp ballots)
+//   sort_input_blocks_or/_and      src/bmaggregator.h:2278-2366   (classification pass, ordered compaction)
 //   process_bit_blocks_or/_and/_sub src/bmaggregator.h:1924-2205  (bit phase, register accumulator)
 //   process_gap_blocks_or/_and/_sub src/bmaggregator.h:1808-1890  (GAP phase, run scatter into smem)
 //   bit_block_count / calc_block_digest0 / bit_block_calc_change  src/bmfunc.h:5808,1239,6040 (epilogue)
 //   the classification half of opt_copy_bit_block                 src/bmblocks.h:1355-1409
 //
 // Layout / mapping:
-//   * persistent CTAs (grid = SMs x occupancy) pull block columns from an atomic counter, so skewed
-//     columns (NULL / GAP / bit mixes) balance themselves;
+//   * persistent CTAs (grid = SMs x 2) pull block columns from an atomic counter, so skewed columns
+//     (NULL / GAP / bit mixes) balance themselves;
 //   * 512 threads own the 8 KB accumulator in registers: thread t holds words [4t, 4t+4) as one uint4,
 //     every source bit-block is consumed with one coalesced 128-bit streaming load per thread,
 //     8 blocks in flight per thread (64 KB per CTA);
-//   * GAP sources never get expanded on their own: each selected run is applied to an 8 KB kill/union
-//     mask K in shared memory with red.shared (one warp per GAP block, one run per lane), and K meets the
-//     register accumulator only once, in the epilogue:
+//   * GAP sources are never expanded on their own.  The column's GAP segment is contiguous in the arena
+//     (column-major layout), so it is streamed with cp.async.bulk (TMA) in 16 KB chunks into a 4-stage
+//     shared-memory ring tracked by mbarriers -- 64 KB in flight per CTA without a single LSU global load.
+//     One warp per GAP block scatters the selected runs (one run per lane) into an 8 KB mask K in shared
+//     memory with red.shared.  The warp that finishes a chunk last re-arms its stage (no producer warp).
+//     K meets the register accumulator only once, in the epilogue:
 //         OR      : R = U | K            (K = union of 1-runs)
 //         AND-SUB : R = P & ~U & ~K      (K = 0-runs of AND-group GAPs  U  1-runs of SUB-group GAPs)
 //         XOR     : R = X ^ K
+//     Unsorted / sparse member lists fall back to per-block gathers from global memory.
 //   * epilogue fuses popcount, 64-wave digest, run count and the result-kind decision.
 #pragma once
 #include "common.cuh"
@@ -29,6 +33,14 @@ constexpr int kAggThreads = 512;
 constexpr int kAggWarps   = kAggThreads / 32;
 constexpr int kAggChunk   = 1024;   // group members classified per pass
 
+constexpr int      kGapStages     = 4;
+constexpr uint32_t kGapChunkBytes = 16384;
+constexpr uint32_t kRingBytes     = kGapStages * kGapChunkBytes;   // 64 KB, power of two
+constexpr uint32_t kRingWords     = kRingBytes / 4;
+constexpr uint32_t kGapMaxBytes   = 2560;                          // gap_max_buff_len * 2
+constexpr int      kMaxChunks     = (kAggChunk * 4096) / (int)kGapChunkBytes + 4;      // streamed only when span <= n * 4096
+constexpr size_t   kAggDynSmem    = kRingBytes;
+
 struct AggParams {
     SetView   set;
     const uint32_t* group;     // device: n0 + n1 member vector ids (group0 then group1)
@@ -36,6 +48,8 @@ struct AggParams {
     uint32_t  nb_from, n_cols;
     uint32_t  compress;        // classify like opt_copy_bit_block(opt_compress)
     uint32_t  store_blocks;    // 0 = counts only
+    uint32_t  gap_mode;        // 0 = auto (stream when sorted), 1 = always gather
+    uint64_t  gap_pool_bytes;  // readable bytes of gap_pool (including the allocation slack)
     uint32_t* blocks;          // [n_cols][2048]
     uint32_t* popcnt;          // [n_cols]
     uint64_t* digest;          // [n_cols]
@@ -49,6 +63,36 @@ struct AggParams {
 constexpr uint32_t kFlNull0 = 1u;   // a NULL block in group0
 constexpr uint32_t kFlFull0 = 2u;   // a FULL block in group0
 constexpr uint32_t kFlFull1 = 4u;   // a FULL block in group1 (SUB)
+
+// ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 
 template <int OP>
 __device__ __forceinline__ void acc_apply0(uint4& a, const uint4& v)
@@ -82,6 +126,7 @@ __device__ __forceinline__ void bit_phase(const uint4* __restrict__ seg, const u
     }
 }
 
+// apply one run [s, e] (inclusive bit positions) to K
 template <bool XOR>
 __device__ __forceinline__ void apply_run(uint32_t* K, uint32_t s, uint32_t e)
 {
@@ -100,33 +145,56 @@ __device__ __forceinline__ void apply_run(uint32_t* K, uint32_t s, uint32_t e)
     }
 }
 
-// One warp scatters the runs of value `want` of one GAP block into K.
 // GAP format (src/bmfunc.h:1696-1725): buf[0] = header (bit0 first-run value, len = hdr>>3),
 // buf[k] k=1..len inclusive run ends; run k = (buf[k-1], buf[k]], value = first ^ ((k-1)&1).
-// Lane j reads the aligned pair word W[j] = (buf[2j], buf[2j+1]); w_first is W[lane] of the first
-// 32 words (already loaded by the caller so the next block's load overlaps this block's scatter).
+// Pair word W[j] = (buf[2j], buf[2j+1]).  Selected runs (value == want):
+//   odd  k = 2j+1 : start = j ? lo(W[j])+1 : 0 , end = hi(W[j])           j < (len+1)/2
+//   even k = 2j+2 : start = hi(W[j])+1         , end = lo(W[j+1])         j <  len/2
+
+// one warp, GAP block resident in the shared-memory ring at word offset b0 (wrap with mask)
 template <bool XOR>
-__device__ __forceinline__ void gap_scatter(uint32_t* K, const uint32_t* __restrict__ g32, uint32_t w_first,
-                                            uint32_t want, int lane)
+__device__ __forceinline__ void gap_scatter_ring(uint32_t* K, const uint32_t* ring, uint32_t b0, uint32_t want, int lane)
+{
+    const uint32_t hdr = ring[b0] & 0xffffu;
+    const uint32_t len = hdr >> 3;
+    if ((hdr & 1u) == want) {
+        const uint32_t nsel = (len + 1u) >> 1;
+        for (uint32_t j = lane; j < nsel; j += 32) {
+            const uint32_t w = ring[(b0 + j) & (kRingWords - 1u)];
+            const uint32_t s = j ? (w & 0xffffu) + 1u : 0u;
+            apply_run<XOR>(K, s, w >> 16);
+        }
+    } else {
+        const uint32_t nsel = len >> 1;
+        for (uint32_t j = lane; j < nsel; j += 32) {
+            const uint32_t w  = ring[(b0 + j) & (kRingWords - 1u)];
+            const uint32_t w2 = ring[(b0 + j + 1u) & (kRingWords - 1u)];
+            apply_run<XOR>(K, (w >> 16) + 1u, w2 & 0xffffu);
+        }
+    }
+}
+
+// one warp, GAP block read straight from global memory (fallback for unsorted / sparse member lists);
+// w_first = pair word `lane` of the block, loaded by the caller one block ahead
+template <bool XOR>
+__device__ __forceinline__ void gap_scatter_gather(uint32_t* K, const uint32_t* __restrict__ g32, uint32_t w_first,
+                                                   uint32_t want, int lane)
 {
     const uint32_t hdr = __shfl_sync(0xffffffffu, w_first, 0) & 0xffffu;
     const uint32_t len = hdr >> 3;
-    const bool odd = ((hdr & 1u) == want);       // selected runs are k = 1,3,5.. else k = 2,4,6..
-    const uint32_t k0 = odd ? 1u : 2u;
-    const uint32_t stride = odd ? 32u : 31u;
+    const bool odd = ((hdr & 1u) == want);
+    const uint32_t nsel = odd ? (len + 1u) >> 1 : len >> 1;
     uint32_t w = w_first;
-    for (uint32_t base = 0; 2u * base + k0 <= len; base += stride) {
+    for (uint32_t base = 0; base < nsel; base += 32) {
         const uint32_t j = base + lane;
-        // prefetch the next iteration's pair word before scattering this one
-        const uint32_t jn = j + stride;
         uint32_t wn = 0;
-        if (2u * (base + stride) + k0 <= len && 2u * jn <= len) wn = ld_nc_u32(g32 + jn);
-        const uint32_t lo = w & 0xffffu, hi = w >> 16;
-        const uint32_t nlo = __shfl_down_sync(0xffffffffu, lo, 1);
-        uint32_t s, e; bool valid;
-        if (odd) { s = j ? lo + 1u : 0u; e = hi; valid = (2u * j + 1u <= len); }
-        else     { s = hi + 1u; e = nlo; valid = (2u * j + 2u <= len) && (lane < 31); }
-        if (valid) apply_run<XOR>(K, s, e);
+        if (base + 32 < nsel && 2u * (j + 32u) <= len) wn = ld_nc_u32(g32 + j + 32u);   // next iteration's word
+        uint32_t w2 = 0;
+        if (!odd && j < nsel) w2 = ld_nc_u32(g32 + j + 1u);
+        if (j < nsel) {
+            if (odd) apply_run<XOR>(K, j ? (w & 0xffffu) + 1u : 0u, w >> 16);
+            else     apply_run<XOR>(K, (w >> 16) + 1u, w2 & 0xffffu);
+        }
         w = wn;
     }
 }
@@ -134,10 +202,17 @@ __device__ __forceinline__ void gap_scatter(uint32_t* K, const uint32_t* __restr
 template <int OP>
 __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
 {
+    extern __shared__ __align__(128) uint8_t dyn_smem[];
+    uint32_t* ring = reinterpret_cast<uint32_t*>(dyn_smem);
+
     __shared__ __align__(16) uint32_t K[kBlockWords];
     __shared__ uint32_t lst_bit0[kAggChunk];
     __shared__ uint32_t lst_bit1[kAggChunk];
-    __shared__ uint32_t lst_gap[kAggChunk];      // group0 GAPs from the front, group1 GAPs from the back
+    __shared__ uint32_t lst_gap[kAggChunk];      // group0 GAPs from the front, group1 GAPs from the back (both in member order)
+    __shared__ uint32_t s_cfirst[kMaxChunks];    // first list entry starting in each ring chunk
+    __shared__ __align__(8) uint64_t s_full[kGapStages];
+    __shared__ uint32_t s_done[kGapStages];
+    __shared__ uint32_t s_wcnt[4][kAggWarps];    // per-warp counts of the ordered compaction
     __shared__ uint32_t s_cnt[4];                // nbit0, nbit1, ngap0, ngap1 of the current chunk
     __shared__ uint32_t s_stat[4];               // flags, total nbit0, total ngap0, nfull0
     __shared__ uint32_t s_col, s_gap_next;
@@ -147,6 +222,16 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
     const uint32_t M = p.set.n_vec;
     const uint32_t ntot = p.n0 + ((OP == BMB200_OP_AND_SUB) ? p.n1 : 0u);
     uint4* K4 = reinterpret_cast<uint4*>(K);
+    uint32_t fillcnt[kGapStages];                // completed fills per stage so far (phase parity), uniform
+#pragma unroll
+    for (int s = 0; s < kGapStages; ++s) fillcnt[s] = 0;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kGapStages; ++s) mbar_init(&s_full[s], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
     for (;;) {
         if (tid == 0) s_col = atomicAdd(p.work_counter, 1u);
@@ -164,40 +249,48 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
         const uint32_t* drow = p.set.desc + (size_t)nb * M;
         const uint4* bseg = reinterpret_cast<const uint4*>(p.set.bit_pool)
                             + p.set.bit_base[nb] * (size_t)(kBlockWords / 4) + tid;
-        const uint16_t* gseg = p.set.gap_pool + p.set.gap_base[nb] * (size_t)kGapUnit;
+        const uint64_t gseg_unit = p.set.gap_base[nb];
+        const uint16_t* gseg = p.set.gap_pool + gseg_unit * (size_t)kGapUnit;
+        const uint64_t gseg_avail = p.gap_pool_bytes - gseg_unit * 16ull;   // readable bytes from gseg on
+        if (ntot == 0) __syncthreads();
 
         for (uint32_t cs = 0; cs < ntot; cs += kAggChunk) {
             if (tid < 4) s_cnt[tid] = 0u;
             if (tid == 0) s_gap_next = 0u;
             __syncthreads();
-            // ---- classification (sort_input_blocks_*) ----
+            // ---- classification (sort_input_blocks_*): order-preserving compaction into 4 lists ----
             const uint32_t ce = min(cs + (uint32_t)kAggChunk, ntot);
             uint32_t fl = 0, nfull0 = 0;
-            for (uint32_t kb = cs; kb < ce; kb += kAggThreads) {   // warp-uniform trip count
+            for (uint32_t kb = cs; kb < ce; kb += kAggThreads) {   // uniform trip count (<= 2)
                 const uint32_t k = kb + tid;
                 uint32_t kind = 0xffu, rel = 0; bool g1 = false;
                 if (k < ce) {
                     const uint32_t d = drow[p.group[k]];
                     kind = d & 3u; rel = d >> 2; g1 = (k >= p.n0);
                 }
-                const bool b0 = (kind == BMB200_BLK_BIT) && !g1, b1 = (kind == BMB200_BLK_BIT) && g1;
-                const bool q0 = (kind == BMB200_BLK_GAP) && !g1, q1 = (kind == BMB200_BLK_GAP) && g1;
+                const bool c0 = (kind == BMB200_BLK_BIT) && !g1, c1 = (kind == BMB200_BLK_BIT) && g1;
+                const bool c2 = (kind == BMB200_BLK_GAP) && !g1, c3 = (kind == BMB200_BLK_GAP) && g1;
                 if (kind == BMB200_BLK_NULL && !g1) fl |= kFlNull0;
                 if (kind == BMB200_BLK_FULL) { if (g1) fl |= kFlFull1; else { fl |= kFlFull0; ++nfull0; } }
                 const uint32_t lt = (1u << lane) - 1u;
-                uint32_t m, basei;
-                m = __ballot_sync(0xffffffffu, b0);
-                if (m) { if (lane == 0) basei = atomicAdd(&s_cnt[0], __popc(m)); basei = __shfl_sync(0xffffffffu, basei, 0);
-                         if (b0) lst_bit0[basei + __popc(m & lt)] = rel; }
-                m = __ballot_sync(0xffffffffu, b1);
-                if (m) { if (lane == 0) basei = atomicAdd(&s_cnt[1], __popc(m)); basei = __shfl_sync(0xffffffffu, basei, 0);
-                         if (b1) lst_bit1[basei + __popc(m & lt)] = rel; }
-                m = __ballot_sync(0xffffffffu, q0);
-                if (m) { if (lane == 0) basei = atomicAdd(&s_cnt[2], __popc(m)); basei = __shfl_sync(0xffffffffu, basei, 0);
-                         if (q0) lst_gap[basei + __popc(m & lt)] = rel; }
-                m = __ballot_sync(0xffffffffu, q1);
-                if (m) { if (lane == 0) basei = atomicAdd(&s_cnt[3], __popc(m)); basei = __shfl_sync(0xffffffffu, basei, 0);
-                         if (q1) lst_gap[kAggChunk - 1 - (basei + __popc(m & lt))] = rel; }
+                const uint32_t m0 = __ballot_sync(0xffffffffu, c0), m1 = __ballot_sync(0xffffffffu, c1);
+                const uint32_t m2 = __ballot_sync(0xffffffffu, c2), m3 = __ballot_sync(0xffffffffu, c3);
+                if (lane == 0) { s_wcnt[0][warp] = __popc(m0); s_wcnt[1][warp] = __popc(m1);
+                                 s_wcnt[2][warp] = __popc(m2); s_wcnt[3][warp] = __popc(m3); }
+                __syncthreads();
+                uint32_t b0 = s_cnt[0], b1 = s_cnt[1], b2 = s_cnt[2], b3 = s_cnt[3];
+                uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+                for (int w = 0; w < kAggWarps; ++w) {
+                    const uint32_t x0 = s_wcnt[0][w], x1 = s_wcnt[1][w], x2 = s_wcnt[2][w], x3 = s_wcnt[3][w];
+                    if (w < warp) { b0 += x0; b1 += x1; b2 += x2; b3 += x3; }
+                    t0 += x0; t1 += x1; t2 += x2; t3 += x3;
+                }
+                if (c0) lst_bit0[b0 + __popc(m0 & lt)] = rel;
+                if (c1) lst_bit1[b1 + __popc(m1 & lt)] = rel;
+                if (c2) lst_gap[b2 + __popc(m2 & lt)] = rel;
+                if (c3) lst_gap[kAggChunk - 1 - (b3 + __popc(m3 & lt))] = rel;
+                __syncthreads();
+                if (tid == 0) { s_cnt[0] += t0; s_cnt[1] += t1; s_cnt[2] += t2; s_cnt[3] += t3; }
             }
             fl = __reduce_or_sync(0xffffffffu, fl);
             nfull0 = warp_sum(nfull0);
@@ -206,35 +299,121 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
             const uint32_t nbit0 = s_cnt[0], nbit1 = s_cnt[1], ngap0 = s_cnt[2], ngap1 = s_cnt[3];
             if (tid == 0) { s_stat[1] += nbit0; s_stat[2] += ngap0; }
 
+            // ---- GAP lists: decide stream vs gather (uniform), set up the first streamed pass ----
+            // pass 0 = group0 list (front), pass 1 = group1 list (back, read reversed so it is in member order)
+            const uint32_t want0 = (OP == BMB200_OP_AND || OP == BMB200_OP_AND_SUB) ? 0u : 1u;
+            bool stream_ok[2];
+            uint32_t w_lo[2], w_bytes[2], nch[2];
+            {
+                int bad0 = 0, bad1 = 0;
+                for (uint32_t i = tid; i + 1 < ngap0; i += kAggThreads) bad0 |= !(lst_gap[i] < lst_gap[i + 1]);
+                for (uint32_t i = tid; i + 1 < ngap1; i += kAggThreads)
+                    bad1 |= !(lst_gap[kAggChunk - 1 - i] < lst_gap[kAggChunk - 2 - i]);
+                const int anybad = __syncthreads_or((bad0 ? 1 : 0) | (bad1 ? 2 : 0));
+                for (int q = 0; q < 2; ++q) {
+                    const uint32_t n = q ? ngap1 : ngap0;
+                    stream_ok[q] = false; w_lo[q] = 0; w_bytes[q] = 0; nch[q] = 0;
+                    if (n == 0 || p.gap_mode == 1u || (anybad & (1 << q))) continue;
+                    const uint32_t lo = q ? lst_gap[kAggChunk - 1] : lst_gap[0];
+                    const uint32_t hi = q ? lst_gap[kAggChunk - n] : lst_gap[n - 1];
+                    const uint64_t span = (uint64_t)(hi - lo) * 16ull + kGapMaxBytes;
+                    if (span > (uint64_t)n * 4096ull) continue;                   // sparse subset: gather instead
+                    uint64_t avail = gseg_avail - (uint64_t)lo * 16ull;
+                    avail &= ~15ull;
+                    const uint64_t wb = span < avail ? span : avail;
+                    stream_ok[q] = true; w_lo[q] = lo; w_bytes[q] = (uint32_t)wb;
+                    nch[q] = (uint32_t)((wb + kGapChunkBytes - 1) / kGapChunkBytes);
+                }
+            }
+            auto L = [&](int q, uint32_t i) -> uint32_t { return q ? lst_gap[kAggChunk - 1 - i] : lst_gap[i]; };
+            auto issue_fill = [&](int q, uint32_t c) {     // one thread: arm stage c % S and start the bulk copy
+                const uint32_t s = c % kGapStages;
+                const uint32_t off = c * kGapChunkBytes;
+                const uint32_t bytes = min(kGapChunkBytes, w_bytes[q] - off);
+                mbar_arrive_expect_tx(&s_full[s], bytes);
+                bulk_g2s(reinterpret_cast<uint8_t*>(ring) + s * kGapChunkBytes,
+                         reinterpret_cast<const uint8_t*>(gseg) + (size_t)w_lo[q] * 16u + off, bytes, &s_full[s]);
+            };
+            auto stream_setup = [&](int q) {               // all threads; ends with a block barrier
+                const uint32_t n = q ? ngap1 : ngap0;
+                for (uint32_t i = tid; i < n; i += kAggThreads) {
+                    const uint32_t ci = ((L(q, i) - w_lo[q]) * 16u) / kGapChunkBytes;
+                    const int cp = i ? (int)(((L(q, i - 1) - w_lo[q]) * 16u) / kGapChunkBytes) : -1;
+                    for (int c = cp + 1; c <= (int)ci; ++c) s_cfirst[c] = i;
+                    if (i == n - 1) for (uint32_t c = ci + 1; c <= nch[q]; ++c) s_cfirst[c] = n;
+                }
+                if (tid < kGapStages) s_done[tid] = 0u;
+                __syncthreads();
+                if (tid == 0) {
+                    fence_proxy_async();
+                    const uint32_t pre = min((uint32_t)kGapStages, nch[q]);
+                    for (uint32_t c = 0; c < pre; ++c) issue_fill(q, c);
+                }
+            };
+            auto stream_consume = [&](int q, uint32_t want) {   // per warp, no block barriers inside
+                for (uint32_t r = 0; r < nch[q]; ++r) {
+                    const uint32_t s = r % kGapStages;
+                    mbar_wait(&s_full[s], (fillcnt[s] + r / kGapStages) & 1u);
+                    if (r + 1 < nch[q]) {
+                        const uint32_t s1 = (r + 1) % kGapStages;
+                        mbar_wait(&s_full[s1], (fillcnt[s1] + (r + 1) / kGapStages) & 1u);
+                    }
+                    const uint32_t iend = s_cfirst[r + 1];
+                    for (uint32_t i = s_cfirst[r] + warp; i < iend; i += kAggWarps) {
+                        const uint32_t b0 = ((L(q, i) - w_lo[q]) * 4u) & (kRingWords - 1u);
+                        gap_scatter_ring<OP == BMB200_OP_XOR>(K, ring, b0, want, lane);
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        __threadfence_block();
+                        const uint32_t old = atomicAdd(&s_done[s], 1u);
+                        if (old == kAggWarps - 1) {          // last warp out re-arms the stage
+                            atomicExch(&s_done[s], 0u);
+                            if (r + kGapStages < nch[q]) { __threadfence_block(); fence_proxy_async(); issue_fill(q, r + kGapStages); }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < kGapStages; ++s)
+                    fillcnt[s] += (nch[q] > (uint32_t)s) ? (nch[q] - 1u - s) / kGapStages + 1u : 0u;
+            };
+            auto gather_pass = [&](int q, uint32_t want) {       // per warp; dynamic block distribution
+                const uint32_t n = q ? ngap1 : ngap0;
+                uint32_t g = 0;
+                if (lane == 0) g = atomicAdd(&s_gap_next, 1u);
+                g = __shfl_sync(0xffffffffu, g, 0);
+                const uint32_t* g32 = nullptr; uint32_t wf = 0;
+                if (g < n) { g32 = reinterpret_cast<const uint32_t*>(gseg + (size_t)L(q, g) * kGapUnit); wf = ld_nc_u32(g32 + lane); }
+                while (g < n) {
+                    uint32_t gn = 0;
+                    if (lane == 0) gn = atomicAdd(&s_gap_next, 1u);
+                    gn = __shfl_sync(0xffffffffu, gn, 0);
+                    const uint32_t* g32n = nullptr; uint32_t wfn = 0;
+                    if (gn < n) { g32n = reinterpret_cast<const uint32_t*>(gseg + (size_t)L(q, gn) * kGapUnit); wfn = ld_nc_u32(g32n + lane); }
+                    gap_scatter_gather<OP == BMB200_OP_XOR>(K, g32, wf, want, lane);
+                    g = gn; g32 = g32n; wf = wfn;
+                }
+            };
+
+            // the first streamed list starts landing in the ring while the bit-blocks stream through registers
+            const int first_q = stream_ok[0] ? 0 : (stream_ok[1] ? 1 : -1);
+            if (first_q >= 0) stream_setup(first_q);
+
             // ---- bit phase: registers <- streamed bit-blocks ----
             bit_phase<OP, false>(bseg, lst_bit0, nbit0, acc0);
             if (OP == BMB200_OP_AND_SUB) bit_phase<OP, true>(bseg, lst_bit1, nbit1, acc1);
 
-            // ---- GAP phase: one warp per GAP block, runs scattered into K ----
-            const uint32_t ngap = ngap0 + ngap1;
-            const uint32_t want0 = (OP == BMB200_OP_AND || OP == BMB200_OP_AND_SUB) ? 0u : 1u;
-            uint32_t g = 0;
-            if (lane == 0) g = atomicAdd(&s_gap_next, 1u);
-            g = __shfl_sync(0xffffffffu, g, 0);
-            const uint32_t* g32 = nullptr; uint32_t wf = 0;
-            if (g < ngap) {
-                const uint32_t rel = (g < ngap0) ? lst_gap[g] : lst_gap[kAggChunk - 1 - (g - ngap0)];
-                g32 = reinterpret_cast<const uint32_t*>(gseg + (size_t)rel * kGapUnit);
-                wf = ld_nc_u32(g32 + lane);
+            // ---- GAP phase ----
+            if (first_q >= 0) stream_consume(first_q, first_q ? 1u : want0);
+            if (first_q == 0 && stream_ok[1]) {
+                __syncthreads();                     // ring and s_cfirst are reused by the second list
+                stream_setup(1);
+                stream_consume(1, 1u);
             }
-            while (g < ngap) {
-                uint32_t gn = 0;
-                if (lane == 0) gn = atomicAdd(&s_gap_next, 1u);
-                gn = __shfl_sync(0xffffffffu, gn, 0);
-                const uint32_t* g32n = nullptr; uint32_t wfn = 0;
-                if (gn < ngap) {
-                    const uint32_t rel = (gn < ngap0) ? lst_gap[gn] : lst_gap[kAggChunk - 1 - (gn - ngap0)];
-                    g32n = reinterpret_cast<const uint32_t*>(gseg + (size_t)rel * kGapUnit);
-                    wfn = ld_nc_u32(g32n + lane);
-                }
-                const uint32_t want = (g < ngap0) ? want0 : 1u;
-                gap_scatter<OP == BMB200_OP_XOR>(K, g32, wf, want, lane);
-                g = gn; g32 = g32n; wf = wfn;
+            if (ngap0 && !stream_ok[0]) gather_pass(0, want0);
+            if (ngap1 && !stream_ok[1]) {
+                if (ngap0 && !stream_ok[0]) { __syncthreads(); if (tid == 0) s_gap_next = 0u; __syncthreads(); }
+                gather_pass(1, 1u);
             }
             __syncthreads();
         }

@@ -27,6 +27,8 @@ struct bmb200_ctx {
     uint32_t* h_group = nullptr;            // pinned staging for the group ids
     std::vector<uint32_t> last_group;       // ids currently resident in d_group (skip the re-upload when unchanged)
     int agg_ctas_per_sm = 2;
+    int gap_mode = 0;                       // 0 = stream sorted GAP lists through the smem ring, 1 = always gather
+    bool attr_set = false;
 };
 
 struct bmb200_set {
@@ -34,6 +36,7 @@ struct bmb200_set {
     SetView v{};
     bool owns = false;
     uint64_t n_bit_blocks = 0, n_gap_units = 0;
+    uint64_t gap_pool_bytes = 0;            // readable bytes of gap_pool (with the allocation slack when owned)
 };
 
 struct bmb200_result {
@@ -149,6 +152,8 @@ int bmb200_init(int device, bmb200_ctx** out)
     ctx->own_stream = true;
     const char* e = getenv("BMB200_AGG_CTAS_PER_SM");
     if (e && atoi(e) > 0) ctx->agg_ctas_per_sm = atoi(e);
+    e = getenv("BMB200_GAP_MODE");
+    if (e) ctx->gap_mode = atoi(e);
     *out = ctx;
     return BMB200_OK;
 }
@@ -214,6 +219,14 @@ int bmb200_device_info(const bmb200_ctx* ctx, int* sm_count, int* cc_major, int*
     return BMB200_OK;
 }
 
+int bmb200_ctx_set_tuning(bmb200_ctx* ctx, int key, int value)
+{
+    if (!ctx) return BMB200_ERR_BADARG;
+    if (key == BMB200_TUNE_GAP_MODE && (value == 0 || value == 1)) { ctx->gap_mode = value; return BMB200_OK; }
+    if (key == BMB200_TUNE_CTAS_PER_SM && value >= 1 && value <= 2) { ctx->agg_ctas_per_sm = value; return BMB200_OK; }
+    return BMB200_ERR_BADARG;
+}
+
 /* ------------------------------------------------------------------ sets */
 
 static int set_alloc(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, uint64_t n_bit, uint64_t n_gap_units,
@@ -224,6 +237,7 @@ static int set_alloc(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, uint64_
     s->ctx = ctx; s->owns = true;
     s->v.n_vec = n_vec; s->v.n_blocks = n_blocks;
     s->n_bit_blocks = n_bit; s->n_gap_units = n_gap_units;
+    s->gap_pool_bytes = n_gap_units * 16ull + kSlack;
     int rc;
     uint32_t* desc = nullptr; uint64_t *bb = nullptr, *gb = nullptr; uint32_t* bp = nullptr; uint16_t* gp = nullptr;
     if ((rc = dev_alloc(ctx, &desc, (size_t)n_vec * n_blocks)) ||
@@ -337,6 +351,7 @@ int bmb200_set_adopt_device(bmb200_ctx* ctx, const bmb200_packed_set* d, bmb200_
     cudaError_t e3 = cudaStreamSynchronize(ctx->stream);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { delete s; ctx->last_err = "adopt: cannot read bases"; return BMB200_ERR_CUDA; }
     s->n_bit_blocks = tails[0]; s->n_gap_units = tails[1];
+    s->gap_pool_bytes = tails[1] * 16ull;      // no slack known for adopted memory
     *out = s;
     return BMB200_OK;
 }
@@ -475,6 +490,7 @@ int bmb200_synth_set(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks,
     s->v.n_vec = n_vec; s->v.n_blocks = n_blocks;
     s->v.desc = desc; s->v.bit_base = bb; s->v.gap_base = gb; s->v.bit_pool = bp; s->v.gap_pool = gp;
     s->n_bit_blocks = tails[0]; s->n_gap_units = tails[1];
+    s->gap_pool_bytes = tails[1] * 16ull + kSlack;
     *out = s;
     return BMB200_OK;
 }
@@ -555,13 +571,21 @@ int bmb200_aggregate(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_agg_ar
     p.compress = compress ? 1u : 0u; p.store_blocks = store ? 1u : 0u;
     p.blocks = r->blocks; p.popcnt = r->popcnt; p.digest = r->digest; p.nruns = r->nruns; p.kind = r->kind;
     p.total = r->total; p.work_counter = ctx->d_work;
+    p.gap_mode = (uint32_t)ctx->gap_mode; p.gap_pool_bytes = set->gap_pool_bytes;
+    if (!ctx->attr_set) {
+        CU(cudaFuncSetAttribute(agg_kernel<BMB200_OP_OR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggDynSmem));
+        CU(cudaFuncSetAttribute(agg_kernel<BMB200_OP_AND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggDynSmem));
+        CU(cudaFuncSetAttribute(agg_kernel<BMB200_OP_AND_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggDynSmem));
+        CU(cudaFuncSetAttribute(agg_kernel<BMB200_OP_XOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggDynSmem));
+        ctx->attr_set = true;
+    }
     uint32_t grid = (uint32_t)(ctx->sm_count * ctx->agg_ctas_per_sm);
     if (grid > n_cols) grid = n_cols;
     switch (a->op) {
-    case BMB200_OP_OR:      agg_kernel<BMB200_OP_OR><<<grid, kAggThreads, 0, ctx->stream>>>(p); break;
-    case BMB200_OP_AND:     agg_kernel<BMB200_OP_AND><<<grid, kAggThreads, 0, ctx->stream>>>(p); break;
-    case BMB200_OP_AND_SUB: agg_kernel<BMB200_OP_AND_SUB><<<grid, kAggThreads, 0, ctx->stream>>>(p); break;
-    default:                agg_kernel<BMB200_OP_XOR><<<grid, kAggThreads, 0, ctx->stream>>>(p); break;
+    case BMB200_OP_OR:      agg_kernel<BMB200_OP_OR><<<grid, kAggThreads, kAggDynSmem, ctx->stream>>>(p); break;
+    case BMB200_OP_AND:     agg_kernel<BMB200_OP_AND><<<grid, kAggThreads, kAggDynSmem, ctx->stream>>>(p); break;
+    case BMB200_OP_AND_SUB: agg_kernel<BMB200_OP_AND_SUB><<<grid, kAggThreads, kAggDynSmem, ctx->stream>>>(p); break;
+    default:                agg_kernel<BMB200_OP_XOR><<<grid, kAggThreads, kAggDynSmem, ctx->stream>>>(p); break;
     }
     int rc = after_launch(ctx);
     if (rc) { if (!*inout) bmb200_result_free(r); return rc; }

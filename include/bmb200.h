@@ -137,6 +137,11 @@ int bmb200_ctx_sync(bmb200_ctx* ctx);
 /* number of kernels this context has launched so far */
 int bmb200_ctx_launch_count(const bmb200_ctx* ctx, uint64_t* out);
 int bmb200_device_info(const bmb200_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, uint64_t* hbm_bytes);
+/* tuning knobs (results never depend on them): key 0 = GAP phase mode (0 auto: stream sorted member lists
+ * through the shared-memory ring, 1 always gather), key 1 = resident CTAs per SM of the aggregation kernel */
+#define BMB200_TUNE_GAP_MODE     0
+#define BMB200_TUNE_CTAS_PER_SM  1
+int bmb200_ctx_set_tuning(bmb200_ctx* ctx, int key, int value);
 
 /* ---------------- sets ---------------- */
 /* copy a packed set from HOST memory (pinned or pageable) into HBM */

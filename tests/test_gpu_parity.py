@@ -81,6 +81,28 @@ def test_aggregate_random_mixed_vs_oracle(ctx, op, seed):
     dset.free()
 
 
+def test_gap_stream_and_gather_paths_agree(ctx):
+    """Sorted member lists take the TMA-streamed GAP path, tuning key 0 = 1 forces the gather path: same bits."""
+    rng = np.random.default_rng(8)
+    vecs = [bm.BVector.random(4, 0.4 / (k + 1), rng).optimize() for k in range(300)]
+    vecs[7].set_full(1)
+    ps = bm.PackedSet.pack(vecs)
+    dset = bm.DeviceSet.upload(ctx, ps)
+    try:
+        for mode in (0, 1):
+            ctx.set_tuning(0, mode)
+            check_vs_oracle(ctx, ps, bm.OP_AND_SUB, [0, 1], list(range(2, 300)), C, dset)
+            check_vs_oracle(ctx, ps, bm.OP_OR, list(range(100, 300)), None, C, dset)
+            check_vs_oracle(ctx, ps, bm.OP_AND, [280, 290, 299], None, 0, dset)          # GAP sources in the AND group
+            check_vs_oracle(ctx, ps, bm.OP_AND_SUB, list(range(250, 254)), list(range(100, 250)), C, dset)  # both lists streamed
+            check_vs_oracle(ctx, ps, bm.OP_XOR, list(range(60, 300)), None, 0, dset)
+            check_vs_oracle(ctx, ps, bm.OP_OR, list(range(299, 99, -1)), None, 0, dset)   # descending -> gather
+            check_vs_oracle(ctx, ps, bm.OP_OR, [100, 299], None, 0, dset)                 # sparse subset -> gather
+    finally:
+        ctx.set_tuning(0, 0)
+    dset.free()
+
+
 def test_edge_cases(ctx):
     vecs = gen.edge_vectors(4)
     ps = bm.PackedSet.pack(vecs)

@@ -1,0 +1,62 @@
+"""N>1 host logic on CPU: world_size-2 gloo.  Each rank aggregates ITS block range (here with the oracle,
+the CPU checker), the package's exchange_popcounts() merges the shards, and every rank must hold exactly
+what a single unsharded pass produces."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _worker(rank, world, port, n_blocks, q):
+    sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bitmagic_b200 as bm
+    from bitmagic_b200.sharding import exchange_popcounts, shard_range
+    import gen, orclib
+    rng = np.random.default_rng(123)                      # same inputs on every rank
+    ps = bm.PackedSet.pack(gen.mixed_vectors(rng, 6, n_blocks, p_null=0.3, p_gap=0.5))
+    lo, hi = shard_range(n_blocks, world, rank)
+    g0, g1 = [0, 1], list(range(2, 6))
+    pop_local = orclib.oracle_aggregate(ps, bm.OP_AND_SUB, g0, g1, bm.F_OPT_COMPRESS, lo, hi)[1] if hi > lo else np.zeros(0, np.uint32)
+    full, card = exchange_popcounts(torch.from_numpy(pop_local.astype(np.int32)), n_blocks, dist)
+    ref = orclib.oracle_aggregate(ps, bm.OP_AND_SUB, g0, g1, bm.F_OPT_COMPRESS)[1]
+    ok = np.array_equal(full.numpy().astype(np.uint32), ref) and int(card.item()) == int(ref.sum())
+    q.put((rank, ok, lo, hi))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_blocks", [512, 600])
+def test_block_range_sharding_world2(n_blocks):
+    world, port = 2, 29500 + (os.getpid() % 2000)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, n_blocks, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in ps:
+        p.join(timeout=60)
+    res.sort()
+    assert all(ok for _, ok, _, _ in res), res
+    assert res[0][2] == 0 and res[0][3] == res[1][2] and res[1][3] == n_blocks
+    assert res[0][3] % 256 == 0
+
+
+def test_shard_range_properties():
+    from bitmagic_b200.sharding import shard_range, shard_sizes
+    for n_blocks in (1, 255, 256, 257, 4096, 16384, 65536, 65537):
+        for world in (1, 2, 3, 4, 8):
+            rs = [shard_range(n_blocks, world, r) for r in range(world)]
+            assert rs[0][0] == 0 and rs[-1][1] == n_blocks
+            for a, b in zip(rs, rs[1:]):
+                assert a[1] == b[0] and (a[1] % 256 == 0 or a[1] == n_blocks)
+            assert sum(shard_sizes(n_blocks, world)) == n_blocks
+    assert shard_sizes(16384, 8) == [2048] * 8
