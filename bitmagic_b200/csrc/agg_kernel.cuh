@@ -309,7 +309,8 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
                 for (uint32_t i = tid; i + 1 < ngap0; i += kAggThreads) bad0 |= !(lst_gap[i] < lst_gap[i + 1]);
                 for (uint32_t i = tid; i + 1 < ngap1; i += kAggThreads)
                     bad1 |= !(lst_gap[kAggChunk - 1 - i] < lst_gap[kAggChunk - 2 - i]);
-                const int anybad = __syncthreads_or((bad0 ? 1 : 0) | (bad1 ? 2 : 0));
+                // NB: __syncthreads_or returns a predicate, not a bitwise OR -> one vote per list
+                const int anybad = (__syncthreads_or(bad0) ? 1 : 0) | (__syncthreads_or(bad1) ? 2 : 0);
                 for (int q = 0; q < 2; ++q) {
                     const uint32_t n = q ? ngap1 : ngap0;
                     stream_ok[q] = false; w_lo[q] = 0; w_bytes[q] = 0; nch[q] = 0;
