@@ -255,12 +255,12 @@ def main():
     gathered = torch.empty(world * n_cols, dtype=torch.int32, device=dev) if world > 1 else None
     card = torch.zeros(1, dtype=torch.int64, device=dev)
 
+    from bitmagic_b200.sharding import exchange_popcounts
+
     def step():
         bm.aggregate(ctx, dset, op, g0, g1, flags, result=res)
-        if world > 1:
-            card.copy_(pop_t.sum(dtype=torch.int64))
-            dist.all_gather_into_tensor(gathered, pop_t)       # per-block popcounts of every shard
-            dist.all_reduce(card)                              # global cardinality
+        if world > 1:                                          # per-block popcounts of every shard + global cardinality
+            exchange_popcounts(pop_t, world * n_cols, dist, out=gathered)
 
     l0 = ctx.launch_count()
     for _ in range(args.warmup):
@@ -284,9 +284,7 @@ def main():
         bm.aggregate(ctx, dset, op, g0, g1, flags, result=res)
         kev[i][1].record(stream)
         if world > 1:
-            card.copy_(pop_t.sum(dtype=torch.int64))
-            dist.all_gather_into_tensor(gathered, pop_t)
-            dist.all_reduce(card)
+            _, card = exchange_popcounts(pop_t, world * n_cols, dist, out=gathered)
         evs[i + 1].record(stream)
     torch.cuda.synchronize(dev)
     if world > 1:

@@ -33,13 +33,42 @@ constexpr int kAggThreads = 512;
 constexpr int kAggWarps   = kAggThreads / 32;
 constexpr int kAggChunk   = 1024;   // group members classified per pass
 
-constexpr int      kGapStages     = 4;
-constexpr uint32_t kGapChunkBytes = 16384;
+// build-time variants (scripts/build_variants.sh explores them; defaults = best measured)
+#ifndef BMB200_GAP_STAGES
+#define BMB200_GAP_STAGES 4
+#endif
+#ifndef BMB200_GAP_CHUNK
+#define BMB200_GAP_CHUNK 16384
+#endif
+#ifndef BMB200_VAR_SCATTER      /* 0: one run per lane, two u16 loads; 1: one run per lane, u32 load + shuffle; 2: two runs per lane, u64 load */
+#define BMB200_VAR_SCATTER 0
+#endif
+#ifndef BMB200_VAR_PREFETCH     /* fetch the next block's header one block ahead */
+#define BMB200_VAR_PREFETCH 0
+#endif
+#ifndef BMB200_LANES_PER_BLOCK   /* lanes that share one GAP block in the streamed scatter: 32, 16, 8 or 4 */
+#define BMB200_LANES_PER_BLOCK 16
+#endif
+#ifndef BMB200_VAR_ANTIPHASE     /* second resident CTA of an SM runs GAP phase first, bit phase second */
+#define BMB200_VAR_ANTIPHASE 0
+#endif
+#ifndef BMB200_VAR_SLEEP_NS
+#define BMB200_VAR_SLEEP_NS 64
+#endif
+#if BMB200_VAR_SCATTER != 0
+#undef BMB200_LANES_PER_BLOCK
+#define BMB200_LANES_PER_BLOCK 32
+#endif
+constexpr uint32_t kLanesPerBlock = BMB200_LANES_PER_BLOCK;      // `lane` below = lane inside its group
+constexpr uint32_t kGroupsPerWarp = 32u / kLanesPerBlock;
+constexpr int      kGapStages     = BMB200_GAP_STAGES;
+constexpr uint32_t kGapChunkBytes = BMB200_GAP_CHUNK;
 constexpr uint32_t kRingBytes     = kGapStages * kGapChunkBytes;   // 64 KB, power of two
 constexpr uint32_t kRingWords     = kRingBytes / 4;
 constexpr uint32_t kGapMaxBytes   = 2560;                          // gap_max_buff_len * 2
 constexpr int      kMaxChunks     = (kAggChunk * 4096) / (int)kGapChunkBytes + 4;      // streamed only when span <= n * 4096
-constexpr size_t   kAggDynSmem    = kRingBytes;
+constexpr uint32_t kRingTail      = kGapMaxBytes + 512;           // tail mirror (+ over-read slack of one 64-run step)
+constexpr size_t   kAggDynSmem    = kRingBytes + kRingTail;       // blocks never wrap
 
 struct AggParams {
     SetView   set;
@@ -81,8 +110,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "WAIT_LOOP:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra WAIT_DONE;\n\t"
+        "nanosleep.u32 %2;\n\t"
         "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+        "WAIT_DONE:\n\t}\n" :: "r"(smem_u32(bar)), "r"(parity), "n"(BMB200_VAR_SLEEP_NS) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
 {
@@ -93,6 +123,13 @@ __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+
+// raw 32-bit shared-window addresses keep the scatter loop free of generic->shared conversions
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return (uint32_t)v; }
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void reds_or(uint32_t a, uint32_t v)  { asm volatile("red.shared.or.b32 [%0], %1;"  :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void reds_xor(uint32_t a, uint32_t v) { asm volatile("red.shared.xor.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 
 template <int OP>
 __device__ __forceinline__ void acc_apply0(uint4& a, const uint4& v)
@@ -126,58 +163,89 @@ __device__ __forceinline__ void bit_phase(const uint4* __restrict__ seg, const u
     }
 }
 
-// apply one run [s, e] (inclusive bit positions) to K
+// apply one run [s, e] (inclusive bit positions) to the mask K (Ks = shared-window address of K)
 template <bool XOR>
-__device__ __forceinline__ void apply_run(uint32_t* K, uint32_t s, uint32_t e)
+__device__ __forceinline__ void apply_run(uint32_t Ks, uint32_t s, uint32_t e)
 {
     const uint32_t ws = s >> 5, we = e >> 5;
+    const uint32_t m0 = 0xffffffffu << (s & 31u);
+    const uint32_t m1 = 0xffffffffu >> (31u - (e & 31u));
     if (ws == we) {
-        const uint32_t m = bit_range_mask(s & 31u, e & 31u);
-        if (XOR) red_xor_shared(K + ws, m); else red_or_shared(K + ws, m);
+        if (XOR) reds_xor(Ks + ws * 4u, m0 & m1); else reds_or(Ks + ws * 4u, m0 & m1);
     } else {
-        const uint32_t m0 = 0xffffffffu << (s & 31u);
-        const uint32_t m1 = 0xffffffffu >> (31u - (e & 31u));
-        if (XOR) { red_xor_shared(K + ws, m0); red_xor_shared(K + we, m1); }
-        else     { red_or_shared(K + ws, m0);  red_or_shared(K + we, m1); }
+        if (XOR) { reds_xor(Ks + ws * 4u, m0); reds_xor(Ks + we * 4u, m1); }
+        else     { reds_or(Ks + ws * 4u, m0);  reds_or(Ks + we * 4u, m1); }
         for (uint32_t w = ws + 1; w < we; ++w) {
-            if (XOR) red_xor_shared(K + w, 0xffffffffu); else red_or_shared(K + w, 0xffffffffu);
+            if (XOR) reds_xor(Ks + w * 4u, 0xffffffffu); else reds_or(Ks + w * 4u, 0xffffffffu);
         }
     }
 }
 
 // GAP format (src/bmfunc.h:1696-1725): buf[0] = header (bit0 first-run value, len = hdr>>3),
 // buf[k] k=1..len inclusive run ends; run k = (buf[k-1], buf[k]], value = first ^ ((k-1)&1).
-// Pair word W[j] = (buf[2j], buf[2j+1]).  Selected runs (value == want):
-//   odd  k = 2j+1 : start = j ? lo(W[j])+1 : 0 , end = hi(W[j])           j < (len+1)/2
-//   even k = 2j+2 : start = hi(W[j])+1         , end = lo(W[j+1])         j <  len/2
+// Selected runs (value == want), one per lane:
+//   first == want : k = 2j+1, start = j ? buf[2j]+1 : 0 , end = buf[2j+1]      j < (len+1)/2
+//   first != want : k = 2j+2, start = buf[2j+1]+1       , end = buf[2j+2]      j <  len/2
 
-// one warp, GAP block resident in the shared-memory ring at word offset b0 (wrap with mask)
+// one warp, GAP block resident in shared memory at byte address `ba` (16-byte aligned, contiguous thanks to
+// the tail mirror); hdr = its header word.  Two runs per lane and step: one 64-bit load brings
+// buf[4t..4t+3]; the straddling run of the "first != want" case takes buf[4t+4] from the next lane.
 template <bool XOR>
-__device__ __forceinline__ void gap_scatter_ring(uint32_t* K, const uint32_t* ring, uint32_t b0, uint32_t want, int lane)
+__device__ __forceinline__ void gap_scatter_ring(uint32_t Ks, uint32_t ba, uint32_t hdr, uint32_t want, int lane)
 {
-    const uint32_t hdr = ring[b0] & 0xffffu;
     const uint32_t len = hdr >> 3;
+#if BMB200_VAR_SCATTER == 2
     if ((hdr & 1u) == want) {
         const uint32_t nsel = (len + 1u) >> 1;
-        for (uint32_t j = lane; j < nsel; j += 32) {
-            const uint32_t w = ring[(b0 + j) & (kRingWords - 1u)];
-            const uint32_t s = j ? (w & 0xffffu) + 1u : 0u;
-            apply_run<XOR>(K, s, w >> 16);
+        for (uint32_t base = 0; base < nsel; base += 64) {
+            const uint32_t t = (base >> 1) + lane;
+            const uint2 v = lds64(ba + 8u * t);
+            const uint32_t j0 = 2u * t;
+            if (j0 < nsel)      apply_run<XOR>(Ks, j0 ? (v.x & 0xffffu) + 1u : 0u, v.x >> 16);
+            if (j0 + 1u < nsel) apply_run<XOR>(Ks, (v.y & 0xffffu) + 1u, v.y >> 16);
         }
     } else {
         const uint32_t nsel = len >> 1;
-        for (uint32_t j = lane; j < nsel; j += 32) {
-            const uint32_t w  = ring[(b0 + j) & (kRingWords - 1u)];
-            const uint32_t w2 = ring[(b0 + j + 1u) & (kRingWords - 1u)];
-            apply_run<XOR>(K, (w >> 16) + 1u, w2 & 0xffffu);
+        for (uint32_t base = 0; base < nsel; base += 64) {          // warp-uniform trip count (shuffle inside)
+            const uint32_t t = (base >> 1) + lane;
+            const uint2 v = lds64(ba + 8u * t);
+            uint32_t nx = __shfl_down_sync(0xffffffffu, v.x, 1);
+            if (lane == 31) nx = lds16(ba + 8u * t + 8u);
+            const uint32_t j0 = 2u * t;
+            if (j0 < nsel)      apply_run<XOR>(Ks, (v.x >> 16) + 1u, v.y & 0xffffu);
+            if (j0 + 1u < nsel) apply_run<XOR>(Ks, (v.y >> 16) + 1u, nx & 0xffffu);
         }
     }
+#else
+    if ((hdr & 1u) == want) {
+        const uint32_t nsel = (len + 1u) >> 1;
+        for (uint32_t j = lane; j < nsel; j += kLanesPerBlock) {
+            const uint32_t w = lds32(ba + 4u * j);
+            apply_run<XOR>(Ks, j ? (w & 0xffffu) + 1u : 0u, w >> 16);
+        }
+    } else {
+        const uint32_t nsel = len >> 1;
+#if BMB200_VAR_SCATTER == 1
+        for (uint32_t base = 0; base < nsel; base += 31) {          // 31 runs per step: lane 31 only feeds lane 30
+            const uint32_t j = base + lane;
+            const uint32_t w = lds32(ba + 4u * j);
+            const uint32_t nx = __shfl_down_sync(0xffffffffu, w, 1);
+            if (lane < 31 && j < nsel) apply_run<XOR>(Ks, (w >> 16) + 1u, nx & 0xffffu);
+        }
+#else
+        for (uint32_t j = lane; j < nsel; j += kLanesPerBlock) {
+            const uint32_t a = ba + 4u * j;
+            apply_run<XOR>(Ks, lds16(a + 2u) + 1u, lds16(a + 4u));
+        }
+#endif
+    }
+#endif
 }
 
 // one warp, GAP block read straight from global memory (fallback for unsorted / sparse member lists);
 // w_first = pair word `lane` of the block, loaded by the caller one block ahead
 template <bool XOR>
-__device__ __forceinline__ void gap_scatter_gather(uint32_t* K, const uint32_t* __restrict__ g32, uint32_t w_first,
+__device__ __forceinline__ void gap_scatter_gather(uint32_t Ks, const uint32_t* __restrict__ g32, uint32_t w_first,
                                                    uint32_t want, int lane)
 {
     const uint32_t hdr = __shfl_sync(0xffffffffu, w_first, 0) & 0xffffu;
@@ -192,8 +260,8 @@ __device__ __forceinline__ void gap_scatter_gather(uint32_t* K, const uint32_t* 
         uint32_t w2 = 0;
         if (!odd && j < nsel) w2 = ld_nc_u32(g32 + j + 1u);
         if (j < nsel) {
-            if (odd) apply_run<XOR>(K, j ? (w & 0xffffu) + 1u : 0u, w >> 16);
-            else     apply_run<XOR>(K, (w >> 16) + 1u, w2 & 0xffffu);
+            if (odd) apply_run<XOR>(Ks, j ? (w & 0xffffu) + 1u : 0u, w >> 16);
+            else     apply_run<XOR>(Ks, (w >> 16) + 1u, w2 & 0xffffu);
         }
         w = wn;
     }
@@ -222,6 +290,12 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
     const uint32_t M = p.set.n_vec;
     const uint32_t ntot = p.n0 + ((OP == BMB200_OP_AND_SUB) ? p.n1 : 0u);
     uint4* K4 = reinterpret_cast<uint4*>(K);
+    // opaque copies: keeps the shared-window base addresses in registers instead of re-deriving them
+    // (S2UR SR_CgaCtaId + LEA) inside the scatter loop
+    uint32_t Ks, ring_s;
+    asm volatile("mov.u32 %0, %1;" : "=r"(Ks) : "r"(smem_u32(K)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(ring_s) : "r"(smem_u32(ring)));
+    const bool gap_first = BMB200_VAR_ANTIPHASE && (blockIdx.x >= (gridDim.x + 1u) / 2u);
     uint32_t fillcnt[kGapStages];                // completed fills per stage so far (phase parity), uniform
 #pragma unroll
     for (int s = 0; s < kGapStages; ++s) fillcnt[s] = 0;
@@ -331,9 +405,11 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
                 const uint32_t s = c % kGapStages;
                 const uint32_t off = c * kGapChunkBytes;
                 const uint32_t bytes = min(kGapChunkBytes, w_bytes[q] - off);
-                mbar_arrive_expect_tx(&s_full[s], bytes);
-                bulk_g2s(reinterpret_cast<uint8_t*>(ring) + s * kGapChunkBytes,
-                         reinterpret_cast<const uint8_t*>(gseg) + (size_t)w_lo[q] * 16u + off, bytes, &s_full[s]);
+                const uint32_t extra = s ? 0u : min(kGapMaxBytes, bytes);   // stage 0 is mirrored behind the ring
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(gseg) + (size_t)w_lo[q] * 16u + off;
+                mbar_arrive_expect_tx(&s_full[s], bytes + extra);
+                bulk_g2s(reinterpret_cast<uint8_t*>(ring) + s * kGapChunkBytes, src, bytes, &s_full[s]);
+                if (extra) bulk_g2s(reinterpret_cast<uint8_t*>(ring) + kRingBytes, src, extra, &s_full[s]);
             };
             auto stream_setup = [&](int q) {               // all threads; ends with a block barrier
                 const uint32_t n = q ? ngap1 : ngap0;
@@ -352,31 +428,60 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
                 }
             };
             auto stream_consume = [&](int q, uint32_t want) {   // per warp, no block barriers inside
-                for (uint32_t r = 0; r < nch[q]; ++r) {
+                const uint32_t wlo = w_lo[q], nc = nch[q];
+                mbar_wait(&s_full[0], fillcnt[0] & 1u);
+                for (uint32_t r = 0; r < nc; ++r) {
                     const uint32_t s = r % kGapStages;
-                    mbar_wait(&s_full[s], (fillcnt[s] + r / kGapStages) & 1u);
-                    if (r + 1 < nch[q]) {
+                    if (r + 1 < nc) {                 // blocks starting in chunk r may spill into chunk r+1
                         const uint32_t s1 = (r + 1) % kGapStages;
                         mbar_wait(&s_full[s1], (fillcnt[s1] + (r + 1) / kGapStages) & 1u);
                     }
-                    const uint32_t iend = s_cfirst[r + 1];
-                    for (uint32_t i = s_cfirst[r] + warp; i < iend; i += kAggWarps) {
-                        const uint32_t b0 = ((L(q, i) - w_lo[q]) * 4u) & (kRingWords - 1u);
-                        gap_scatter_ring<OP == BMB200_OP_XOR>(K, ring, b0, want, lane);
+                    // block i always goes to warp i % 16, so the per-round remainders rotate over the warps
+                    const uint32_t ibeg = s_cfirst[r], iend = s_cfirst[r + 1];
+#if BMB200_VAR_PREFETCH
+                    uint32_t i = ibeg + ((warp - ibeg) & (kAggWarps - 1));
+                    uint32_t ba = 0, hdr = 0;
+                    if (i < iend) {
+                        const uint32_t rel = q ? lst_gap[kAggChunk - 1 - i] : lst_gap[i];
+                        ba = ring_s + (((rel - wlo) * 16u) & (kRingBytes - 1u));
+                        hdr = lds16(ba);
                     }
+                    while (i < iend) {                        // header of the next block is fetched one block ahead
+                        const uint32_t in = i + kAggWarps;
+                        uint32_t ban = 0, hdrn = 0;
+                        if (in < iend) {
+                            const uint32_t rel = q ? lst_gap[kAggChunk - 1 - in] : lst_gap[in];
+                            ban = ring_s + (((rel - wlo) * 16u) & (kRingBytes - 1u));
+                            hdrn = lds16(ban);
+                        }
+                        gap_scatter_ring<OP == BMB200_OP_XOR>(Ks, ba, hdr, want, lane);
+                        i = in; ba = ban; hdr = hdrn;
+                    }
+#else
+                    {   // block i always goes to slot i % (16 * groups): the per-round remainders rotate over the slots
+                        constexpr uint32_t kSlots = kAggWarps * kGroupsPerWarp;
+                        const uint32_t slot = (uint32_t)warp * kGroupsPerWarp + ((uint32_t)lane / kLanesPerBlock);
+                        const int sub = lane & (int)(kLanesPerBlock - 1u);
+                        for (uint32_t i = ibeg + ((slot - ibeg) & (kSlots - 1u)); i < iend; i += kSlots) {
+                            const uint32_t rel = q ? lst_gap[kAggChunk - 1 - i] : lst_gap[i];
+                            const uint32_t ba = ring_s + (((rel - wlo) * 16u) & (kRingBytes - 1u));
+                            gap_scatter_ring<OP == BMB200_OP_XOR>(Ks, ba, lds16(ba), want, sub);
+                        }
+                    }
+#endif
                     __syncwarp();
                     if (lane == 0) {
                         __threadfence_block();
                         const uint32_t old = atomicAdd(&s_done[s], 1u);
                         if (old == kAggWarps - 1) {          // last warp out re-arms the stage
                             atomicExch(&s_done[s], 0u);
-                            if (r + kGapStages < nch[q]) { __threadfence_block(); fence_proxy_async(); issue_fill(q, r + kGapStages); }
+                            if (r + kGapStages < nc) { __threadfence_block(); fence_proxy_async(); issue_fill(q, r + kGapStages); }
                         }
                     }
                 }
 #pragma unroll
                 for (int s = 0; s < kGapStages; ++s)
-                    fillcnt[s] += (nch[q] > (uint32_t)s) ? (nch[q] - 1u - s) / kGapStages + 1u : 0u;
+                    fillcnt[s] += (nc > (uint32_t)s) ? (nc - 1u - s) / kGapStages + 1u : 0u;
             };
             auto gather_pass = [&](int q, uint32_t want) {       // per warp; dynamic block distribution
                 const uint32_t n = q ? ngap1 : ngap0;
@@ -391,7 +496,7 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
                     gn = __shfl_sync(0xffffffffu, gn, 0);
                     const uint32_t* g32n = nullptr; uint32_t wfn = 0;
                     if (gn < n) { g32n = reinterpret_cast<const uint32_t*>(gseg + (size_t)L(q, gn) * kGapUnit); wfn = ld_nc_u32(g32n + lane); }
-                    gap_scatter_gather<OP == BMB200_OP_XOR>(K, g32, wf, want, lane);
+                    gap_scatter_gather<OP == BMB200_OP_XOR>(Ks, g32, wf, want, lane);
                     g = gn; g32 = g32n; wf = wfn;
                 }
             };
@@ -400,10 +505,13 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
             const int first_q = stream_ok[0] ? 0 : (stream_ok[1] ? 1 : -1);
             if (first_q >= 0) stream_setup(first_q);
 
-            // ---- bit phase: registers <- streamed bit-blocks ----
-            bit_phase<OP, false>(bseg, lst_bit0, nbit0, acc0);
-            if (OP == BMB200_OP_AND_SUB) bit_phase<OP, true>(bseg, lst_bit1, nbit1, acc1);
-
+            // The two phases touch disjoint state (registers vs K), so their order is free.  CTAs of the second
+            // residency wave run GAP first: the two CTAs sharing an SM then keep HBM (bit phase) and the LSU
+            // (GAP scatter) busy at the same time instead of marching in lockstep.
+            if (!gap_first) {
+                bit_phase<OP, false>(bseg, lst_bit0, nbit0, acc0);
+                if (OP == BMB200_OP_AND_SUB) bit_phase<OP, true>(bseg, lst_bit1, nbit1, acc1);
+            }
             // ---- GAP phase ----
             if (first_q >= 0) stream_consume(first_q, first_q ? 1u : want0);
             if (first_q == 0 && stream_ok[1]) {
@@ -415,6 +523,11 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
             if (ngap1 && !stream_ok[1]) {
                 if (ngap0 && !stream_ok[0]) { __syncthreads(); if (tid == 0) s_gap_next = 0u; __syncthreads(); }
                 gather_pass(1, 1u);
+            }
+            // ---- bit phase: registers <- streamed bit-blocks ----
+            if (gap_first) {
+                bit_phase<OP, false>(bseg, lst_bit0, nbit0, acc0);
+                if (OP == BMB200_OP_AND_SUB) bit_phase<OP, true>(bseg, lst_bit1, nbit1, acc1);
             }
             __syncthreads();
         }

@@ -1,0 +1,10 @@
+#!/bin/bash
+# builds kernel variants into scripts/_bin/libbmb200_<name>.so for A/B runs on the GPU box (BMB200_LIB=...)
+set -e
+cd "$(dirname "$0")/.."
+mkdir -p scripts/_bin
+build() { name=$1; shift; nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared "$@" -o scripts/_bin/libbmb200_$name.so bitmagic_b200/csrc/capi.cu -lcudart & }
+build anti
+build noanti -DBMB200_VAR_ANTIPHASE=0
+wait
+ls -la scripts/_bin/
