@@ -1,0 +1,301 @@
+// bmb200_aggregator.hpp -- reference-side binding: bm::b200::aggregator<BV> and friends.
+//
+// This is the header a BitMagic maintainer adds next to src/bmaggregator.h to route the block algebra of
+// bm::aggregator<> / bvector::bit_* / build_rs_index to libbmb200.so (include/bmb200.h).  It needs the
+// reference headers on the include path (bm.h, bmaggregator.h) and only uses their PUBLIC block-manager API,
+// exactly as aggregator itself does (src/bmaggregator.h:1196-1216):
+//     get_blocks_manager(), get_block_ptr(i,j), BM_IS_GAP / BMGAP_PTR / FULL_BLOCK_FAKE_ADDR,
+//     reserve_top_blocks, check_alloc_top_subblock, set_block_ptr, copy_bit_block, allocate_gap_block.
+//
+// Same member names, argument meaning and return values as bm::aggregator<BV>
+// (src/bmaggregator.h:359-388 setters, :503-540 C-style entry points); errors from the C ABI surface as
+// std::runtime_error because the reference's own methods have no error channel.
+#ifndef BMB200_AGGREGATOR_HPP_INCLUDED
+#define BMB200_AGGREGATOR_HPP_INCLUDED
+
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "bm.h"
+#include "bmaggregator.h"
+
+#include "bmb200.h"
+
+namespace bm { namespace b200 {
+
+inline void check(int rc, const char* what)
+{
+    if (rc != BMB200_OK) throw std::runtime_error(std::string(what) + ": " + bmb200_error_msg(rc));
+}
+
+/// process-wide context for one device (the C ABI handle is thread-compatible, not thread-safe)
+class context
+{
+public:
+    explicit context(int device = 0) { check(bmb200_init(device, &ctx_), "bmb200_init"); }
+    ~context() { if (ctx_) bmb200_destroy(ctx_); }
+    context(const context&) = delete; context& operator=(const context&) = delete;
+    bmb200_ctx* get() const { return ctx_; }
+private:
+    bmb200_ctx* ctx_ = nullptr;
+};
+
+namespace detail {
+
+/// walk a bvector's block tree into the kind/pointer arrays bmb200_set_upload_vectors consumes
+template<class BV>
+struct tree_view
+{
+    std::vector<uint8_t> kind;
+    std::vector<const void*> ptr;
+    void build(const BV& bv, uint32_t n_blocks)
+    {
+        kind.assign(n_blocks, BMB200_BLK_NULL); ptr.assign(n_blocks, nullptr);
+        const typename BV::blocks_manager_type& bman = bv.get_blocks_manager();
+        if (!bman.is_init()) return;
+        unsigned top = bman.top_block_size();
+        for (uint32_t nb = 0; nb < n_blocks; ++nb)
+        {
+            unsigned i = nb >> bm::set_array_shift, j = nb & bm::set_array_mask;
+            if (i >= top) break;
+            const bm::word_t* blk = bman.get_block_ptr(i, j);
+            if (!blk) continue;
+            if (blk == FULL_BLOCK_FAKE_ADDR || blk == FULL_BLOCK_REAL_ADDR) { kind[nb] = BMB200_BLK_FULL; continue; }
+            if (BM_IS_GAP(blk)) { kind[nb] = BMB200_BLK_GAP; ptr[nb] = BMGAP_PTR(blk); }
+            else                { kind[nb] = BMB200_BLK_BIT; ptr[nb] = blk; }
+        }
+    }
+};
+
+template<class BV>
+uint32_t blocks_of(const BV& bv)
+{
+    typename BV::size_type sz = bv.size();
+    return (uint32_t)((uint64_t(sz) + 65535ull) >> 16);
+}
+
+/// store a fetched result (per-column flat form) into a cleared target through the public block manager
+template<class BV>
+void store_result(BV& target, typename BV::size_type new_size, uint32_t n_cols,
+                  const uint8_t* kind, const uint64_t* off, const uint32_t* bits, const uint16_t* gaps)
+{
+    target.clear(true);
+    target.resize(new_size);
+    target.init();
+    typename BV::blocks_manager_type& bman = target.get_blocks_manager();
+    BM_DECLARE_TEMP_BLOCK(tb)
+    for (uint32_t c = 0; c < n_cols; ++c)
+    {
+        if (kind[c] == BMB200_BLK_NULL) continue;
+        unsigned i = c >> bm::set_array_shift, j = c & bm::set_array_mask;
+        bman.reserve_top_blocks(i + 1);
+        bman.check_alloc_top_subblock(i);
+        if (kind[c] == BMB200_BLK_FULL)
+        {
+            bman.set_block_ptr(i, j, FULL_BLOCK_FAKE_ADDR);
+            if (j == bm::set_sub_array_size - 1) bman.validate_top_full(i);
+        }
+        else if (kind[c] == BMB200_BLK_BIT)
+        {
+            std::memcpy(tb.begin(), bits + off[c] * (size_t)BMB200_BLOCK_WORDS, BMB200_BLOCK_BYTES);
+            bman.copy_bit_block(i, j, tb.begin());
+        }
+        else
+        {
+            const bm::gap_word_t* g = gaps + off[c];
+            unsigned len = bm::gap_length(g) - 1;
+            int level = bm::gap_calc_level(len, bman.glen());
+            bm::gap_word_t* gb = bman.allocate_gap_block(unsigned(level), g);
+            bman.set_block_ptr(i, j, (bm::word_t*)BMPTR_SETBIT0(gb));
+        }
+    }
+}
+
+} // namespace detail
+
+/// Drop-in for bm::aggregator<BV>: combine_or / combine_and / combine_and_sub on the GPU.
+template<class BV>
+class aggregator
+{
+public:
+    typedef BV bvector_type;
+    typedef const bvector_type* bvector_type_const_ptr;
+    typedef typename BV::size_type size_type;
+
+    explicit aggregator(context& ctx) : ctx_(ctx) {}
+
+    // ---- setters, same meaning as src/bmaggregator.h:359-388 ----
+    void set_optimization(typename BV::optmode opt = BV::opt_compress) { opt_mode_ = opt; }
+    size_t add(const bvector_type* bv, unsigned agr_group = 0)
+    {
+        if (agr_group > 1) throw std::range_error("agr_group");
+        grp_[agr_group].push_back(bv);
+        return grp_[agr_group].size();
+    }
+    void reset() { grp_[0].clear(); grp_[1].clear(); }
+
+    // ---- member forms ----
+    void combine_or(bvector_type& target)  { combine_or(target, grp_[0].data(), grp_[0].size()); }
+    void combine_and(bvector_type& target)
+    {   // member combine_and routes through combine_and_sub with an empty SUB group, src/bmaggregator.h:1030-1039
+        combine_and_sub(target, grp_[0].data(), grp_[0].size(), 0, 0, false);
+    }
+    bool combine_and_sub(bvector_type& target)
+    {
+        return combine_and_sub(target, grp_[0].data(), grp_[0].size(), grp_[1].data(), grp_[1].size(), false);
+    }
+
+    // ---- C-style forms, src/bmaggregator.h:503-540 ----
+    void combine_or(bvector_type& target, const bvector_type_const_ptr* src, size_t n)
+    {
+        if (!n) { target.clear(); return; }                       // :1105-1109
+        std::vector<const BV*> local(src, src + n);
+        reset();                                                  // the reference drops the attached groups here (ag_.reset(), :1111)
+        run(target, BMB200_OP_OR, local.data(), n, 0, 0, opt_mode_ != BV::opt_none);
+    }
+    void combine_and(bvector_type& target, const bvector_type_const_ptr* src, size_t n)
+    {
+        if (n == 1) { target = *src[0]; return; }                 // :1132-1137
+        if (!n) { target.clear(); return; }
+        std::vector<const BV*> local(src, src + n);
+        reset();                                                  // ag_.reset(), :1143
+        run(target, BMB200_OP_AND, local.data(), n, 0, 0, opt_mode_ != BV::opt_none);
+    }
+    bool combine_and_sub(bvector_type& target,
+                         const bvector_type_const_ptr* src_and, size_t n_and,
+                         const bvector_type_const_ptr* src_sub, size_t n_sub, bool any)
+    {
+        (void)any;   // any=true only promises the boolean (:1202-1213); the full result is computed here
+        if (!src_and || !n_and) { target.clear(); return false; } // :1170-1174
+        return run(target, BMB200_OP_AND_SUB, src_and, n_and, src_sub, n_sub, true /* always opt_compress, :1209 */);
+    }
+
+    /// popcount of AND-SUB without materialising the result (pipeline counts mode, :1397-1398)
+    size_type count_and_sub(const bvector_type_const_ptr* src_and, size_t n_and,
+                            const bvector_type_const_ptr* src_sub, size_t n_sub)
+    {
+        if (!n_and) return 0;
+        bmb200_set* set = upload(src_and, n_and, src_sub, n_sub);
+        std::vector<uint32_t> g0(n_and), g1(n_sub);
+        for (size_t k = 0; k < n_and; ++k) g0[k] = (uint32_t)k;
+        for (size_t k = 0; k < n_sub; ++k) g1[k] = (uint32_t)(n_and + k);
+        bmb200_agg_args a{BMB200_OP_AND_SUB, BMB200_F_COUNT_ONLY, g0.data(), (uint32_t)n_and, g1.data(), (uint32_t)n_sub, 0, 0};
+        bmb200_result* res = nullptr;
+        int rc = bmb200_aggregate(ctx_.get(), set, &a, &res);
+        uint64_t total = 0; int any = 0;
+        if (!rc) rc = bmb200_result_total(res, &total, &any);
+        if (res) bmb200_result_free(res);
+        bmb200_set_free(set);
+        check(rc, "bmb200_aggregate(count)");
+        return (size_type)total;
+    }
+
+private:
+    bmb200_set* upload(const bvector_type_const_ptr* s0, size_t n0, const bvector_type_const_ptr* s1, size_t n1)
+    {
+        n_blocks_ = 0; max_size_ = 0;
+        for (size_t k = 0; k < n0 + n1; ++k)
+        {
+            const BV* bv = k < n0 ? s0[k] : s1[k - n0];
+            uint32_t nb = detail::blocks_of(*bv);
+            if (nb > n_blocks_) n_blocks_ = nb;
+            if (bv->size() > max_size_) max_size_ = bv->size();   // resize_target: max over sources, :2238-2248
+        }
+        views_.resize(n0 + n1); vb_.resize(n0 + n1);
+        for (size_t k = 0; k < n0 + n1; ++k)
+        {
+            const BV* bv = k < n0 ? s0[k] : s1[k - n0];
+            views_[k].build(*bv, n_blocks_);
+            vb_[k].n_blocks = n_blocks_; vb_[k].kind = views_[k].kind.data(); vb_[k].ptr = views_[k].ptr.data();
+        }
+        bmb200_set* set = nullptr;
+        check(bmb200_set_upload_vectors(ctx_.get(), (uint32_t)(n0 + n1), n_blocks_, vb_.data(), &set), "bmb200_set_upload_vectors");
+        return set;
+    }
+
+    bool run(bvector_type& target, int op, const bvector_type_const_ptr* s0, size_t n0,
+             const bvector_type_const_ptr* s1, size_t n1, bool compress)
+    {
+        bmb200_set* set = upload(s0, n0, s1, n1);
+        std::vector<uint32_t> g0(n0), g1(n1);
+        for (size_t k = 0; k < n0; ++k) g0[k] = (uint32_t)k;
+        for (size_t k = 0; k < n1; ++k) g1[k] = (uint32_t)(n0 + k);
+        bmb200_agg_args a{op, compress ? BMB200_F_OPT_COMPRESS : BMB200_F_OPT_NONE,
+                          g0.data(), (uint32_t)n0, n1 ? g1.data() : nullptr, (uint32_t)n1, 0, 0};
+        bmb200_result* res = nullptr;
+        int rc = bmb200_aggregate(ctx_.get(), set, &a, &res);
+        uint64_t total = 0; int any = 0, rc2 = 0;
+        std::vector<uint8_t> kind(n_blocks_); std::vector<uint64_t> off(n_blocks_);
+        std::vector<uint32_t> bits; std::vector<uint16_t> gaps;
+        if (!rc) rc = bmb200_result_total(res, &total, &any);
+        if (!rc) { uint64_t nb = 0, ng = 0; rc = bmb200_result_sizes(res, &nb, &ng);
+                   if (!rc) { bits.resize(nb * BMB200_BLOCK_WORDS); gaps.resize(ng);
+                              rc = bmb200_result_fetch(res, kind.data(), off.data(), bits.data(), gaps.data()); } }
+        if (res) rc2 = bmb200_result_free(res);
+        bmb200_set_free(set);
+        check(rc, "bmb200_aggregate"); check(rc2, "bmb200_result_free");
+        detail::store_result(target, max_size_, n_blocks_, kind.data(), off.data(), bits.data(), gaps.data());
+        return any != 0;
+    }
+
+    context& ctx_;
+    typename BV::optmode opt_mode_ = BV::opt_none;
+    std::vector<const BV*> grp_[2];
+    std::vector<detail::tree_view<BV>> views_;
+    std::vector<bmb200_vec_blocks> vb_;
+    uint32_t n_blocks_ = 0;
+    size_type max_size_ = 0;
+};
+
+/// 3-operand bvector ops (src/bm.h:1745-1850): target = a OP b
+template<class BV> void bit_or (context& c, BV& t, const BV& a, const BV& b, typename BV::optmode opt = BV::opt_none)
+{ aggregator<BV> g(c); g.set_optimization(opt); const BV* s[2] = {&a, &b}; g.combine_or(t, s, 2); }
+template<class BV> void bit_and(context& c, BV& t, const BV& a, const BV& b, typename BV::optmode opt = BV::opt_none)
+{ aggregator<BV> g(c); g.set_optimization(opt); const BV* s[2] = {&a, &b}; g.combine_and(t, s, 2); }
+template<class BV> void bit_sub(context& c, BV& t, const BV& a, const BV& b)
+{ aggregator<BV> g(c); const BV* s0[1] = {&a}; const BV* s1[1] = {&b}; g.combine_and_sub(t, s0, 1, s1, 1, false); }
+
+/// build_rs_index on the GPU, delivered through rs_index's own public mutators
+/// (resize / set_total / set_null_super_block / set_full_super_block / register_super_block,
+///  src/bmrs.h:70-113) so the unmodified reference query code (count_to / select) can use it.
+template<class BV>
+void build_rs_index(context& c, const BV& bv, typename BV::rs_index_type* rs)
+{
+    rs->init();
+    if (!bv.get_blocks_manager().is_init()) return;
+    typename BV::size_type last;
+    if (!bv.find_reverse(last)) return;
+    const typename BV::blocks_manager_type& bman = bv.get_blocks_manager();
+    unsigned real_top = bman.find_real_top_blocks(), max_top = bman.find_max_top_blocks();
+    uint64_t nb = uint64_t(last) >> 16;
+    if (nb < uint64_t(max_top) * 256u) nb = uint64_t(max_top) * 256u;          // src/bm.h:2556-2559
+    rs->set_total((typename BV::block_idx_type)(nb + 1));
+    rs->resize((typename BV::block_idx_type)(nb + 1));
+    rs->resize_effective_super_blocks(real_top);
+    uint32_t n_blocks = max_top * 256u;
+    detail::tree_view<BV> view; view.build(bv, n_blocks);
+    bmb200_vec_blocks vb{n_blocks, view.kind.data(), view.ptr.data()};
+    bmb200_set* set = nullptr; bmb200_rs* drs = nullptr;
+    check(bmb200_set_upload_vectors(c.get(), 1, n_blocks, &vb, &set), "bmb200_set_upload_vectors");
+    int rc = bmb200_rs_build(c.get(), set, 0, &drs);
+    std::vector<unsigned> bcount(n_blocks); std::vector<bm::id64_t> sub(n_blocks); std::vector<uint64_t> sb(max_top + 1);
+    static_assert(sizeof(bm::id64_t) == 8 && sizeof(unsigned) == 4, "index field widths");
+    if (!rc) rc = bmb200_rs_export(drs, bcount.data(), (uint64_t*)sub.data(), sb.data());
+    if (drs) bmb200_rs_free(drs);
+    bmb200_set_free(set);
+    check(rc, "bmb200_rs_build");
+    bm::word_t*** root = const_cast<typename BV::blocks_manager_type&>(bman).top_blocks_root();
+    for (unsigned i = 0; i < max_top; ++i)
+    {
+        if (!root[i]) { rs->set_null_super_block(i); continue; }
+        if ((bm::word_t*)root[i] == FULL_BLOCK_FAKE_ADDR) { rs->set_full_super_block(i); continue; }
+        rs->register_super_block(i, &bcount[i * 256u], &sub[i * 256u]);
+    }
+}
+
+}} // namespace bm::b200
+
+#endif

@@ -4,7 +4,7 @@ Every block column is independent for AND/OR/XOR/SUB (the reference loops (i,j) 
 src/bmaggregator.h:1113-1121,1184-1218), so rank g of G owns a contiguous range of block columns of EVERY
 vector, aligned to 256-block superblocks (rs_index rows never straddle ranks).  The only exchange is the
 per-block popcount vector (4 B per column) and the global cardinality -- enqueued on the aggregation stream
-through torch.distributed (NCCL on GPUs, gloo in the CPU tests).
+through torch.distributed (NCCL on GPUs, gloo in the CPU tests): ONE all_gather; the cardinality is its local sum.
 """
 from __future__ import annotations
 
@@ -48,6 +48,6 @@ def exchange_popcounts(pop_local: torch.Tensor, n_blocks: int, dist=None, out: t
         for r, sz in enumerate(sizes):
             out[o:o + sz] = buf[r * m: r * m + sz]
             o += sz
-    card = pop_local.sum(dtype=torch.int64).reshape(1)
-    dist.all_reduce(card)
+    # the per-block vector is complete on every rank now, so the global cardinality needs no second collective
+    card = out.sum(dtype=torch.int64).reshape(1)
     return out, card

@@ -1,0 +1,111 @@
+/*
+ * test_cxx_binding.cpp -- TEST INFRASTRUCTURE.  Drop-in check at the bm::bvector<> level:
+ * the UNMODIFIED reference (bm::aggregator, bvector::build_rs_index; headers from /root/reference/src)
+ * against bm::b200::aggregator / bm::b200::build_rs_index (bitmagic_b200/include/bmb200_aggregator.hpp,
+ * which talks to libbmb200.so).  Parity criterion = the reference's own: compare()==0, equal count(),
+ * equal calc_stat block kinds under opt_compress, equal rs_index fields and query answers
+ * (tests/stress/t.cpp:10887-10921, :2658-2885, :4975-5090).  Built by oracle/Makefile into oracle/_ref/.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+#include <memory>
+
+#include "bm.h"
+#include "bmaggregator.h"
+#include "bmb200_aggregator.hpp"
+
+typedef bm::bvector<> bvect;
+static int g_fail = 0, g_checks = 0;
+#define CHECK(cond, ...) do { ++g_checks; if (!(cond)) { ++g_fail; std::printf("FAIL %s:%d: ", __FILE__, __LINE__); std::printf(__VA_ARGS__); std::printf("\n"); } } while (0)
+
+static void fill(bvect& bv, std::mt19937_64& rng, unsigned n_bits, double density, bool ranges)
+{
+    std::geometric_distribution<unsigned> skip(density);
+    for (uint64_t p = skip(rng); p < n_bits; p += 1 + skip(rng)) bv.set_bit_no_check((bvect::size_type)p);
+    if (ranges) {
+        bv.set_range(70000, 70000 + 200000);            // spans whole blocks -> FULL blocks after optimize
+        bv.set_range(n_bits / 2, n_bits / 2 + 300);
+    }
+}
+
+int main()
+{
+    std::mt19937_64 rng(20260923);
+    const unsigned n_bits = 40u * 65536u + 12345u;
+    bm::b200::context ctx(0);
+    std::vector<std::unique_ptr<bvect>> vs;
+    for (int k = 0; k < 24; ++k) {
+        vs.emplace_back(new bvect());
+        fill(*vs.back(), rng, n_bits, 0.4 / (k + 1), k % 5 == 3);
+        if (k >= 6) { BM_DECLARE_TEMP_BLOCK(tb) vs.back()->optimize(tb, bvect::opt_compress); }
+    }
+    std::vector<const bvect*> all; for (auto& v : vs) all.push_back(v.get());
+
+    for (int opt = 0; opt < 2; ++opt) {
+        bvect::optmode om = opt ? bvect::opt_compress : bvect::opt_none;
+        bm::aggregator<bvect> ref; ref.set_optimization(om);
+        bm::b200::aggregator<bvect> gpu(ctx); gpu.set_optimization(om);
+        for (size_t n : {size_t(1), size_t(2), size_t(7), all.size()}) {
+            bvect t_ref, t_gpu;
+            ref.combine_or(t_ref, all.data(), n); gpu.combine_or(t_gpu, all.data(), n);
+            CHECK(t_ref.compare(t_gpu) == 0, "combine_or n=%zu opt=%d", n, opt);
+            CHECK(t_ref.count() == t_gpu.count(), "combine_or count n=%zu", n);
+            if (opt) { bvect::statistics s1, s2; t_ref.calc_stat(&s1); t_gpu.calc_stat(&s2);
+                       CHECK(s1.bit_blocks == s2.bit_blocks && s1.gap_blocks == s2.gap_blocks, "combine_or kinds n=%zu (%zu/%zu vs %zu/%zu)", n, (size_t)s1.bit_blocks, (size_t)s1.gap_blocks, (size_t)s2.bit_blocks, (size_t)s2.gap_blocks); }
+            ref.combine_and(t_ref, all.data(), n); gpu.combine_and(t_gpu, all.data(), n);
+            CHECK(t_ref.compare(t_gpu) == 0, "combine_and n=%zu opt=%d", n, opt);
+        }
+        for (size_t na : {size_t(1), size_t(2), size_t(3)}) {
+            bvect t_ref, t_gpu;
+            bool f1 = ref.combine_and_sub(t_ref, all.data(), na, all.data() + na, all.size() - na, false);
+            bool f2 = gpu.combine_and_sub(t_gpu, all.data(), na, all.data() + na, all.size() - na, false);
+            CHECK(f1 == f2, "combine_and_sub found na=%zu", na);
+            CHECK(t_ref.compare(t_gpu) == 0, "combine_and_sub na=%zu", na);
+            bvect::statistics s1, s2; t_ref.calc_stat(&s1); t_gpu.calc_stat(&s2);
+            CHECK(s1.bit_blocks == s2.bit_blocks && s1.gap_blocks == s2.gap_blocks, "combine_and_sub kinds na=%zu", na);
+            CHECK(gpu.count_and_sub(all.data(), na, all.data() + na, all.size() - na) == t_ref.count(), "count_and_sub na=%zu", na);
+        }
+    }
+    {   // member forms with add()/reset(), as samples/bvsample16/sample16.cpp uses them
+        bm::aggregator<bvect> ref; bm::b200::aggregator<bvect> gpu(ctx);
+        for (int k = 0; k < 3; ++k) { ref.add(all[k]); gpu.add(all[k]); }
+        for (int k = 10; k < 16; ++k) { ref.add(all[k], 1); gpu.add(all[k], 1); }
+        bvect a, b; ref.combine_or(a); gpu.combine_or(b); CHECK(a.compare(b) == 0, "member combine_or");
+        ref.combine_and(a); gpu.combine_and(b); CHECK(a.compare(b) == 0, "member combine_and");
+        bool f1 = ref.combine_and_sub(a), f2 = gpu.combine_and_sub(b);
+        CHECK(f1 == f2 && a.compare(b) == 0, "member combine_and_sub");
+    }
+    {   // 3-operand ops
+        bvect t1, t2;
+        t1.bit_and(*all[0], *all[9], bvect::opt_none); bm::b200::bit_and(ctx, t2, *all[0], *all[9]); CHECK(t1.compare(t2) == 0, "bit_and");
+        t1.bit_or(*all[2], *all[20], bvect::opt_none); bm::b200::bit_or(ctx, t2, *all[2], *all[20]); CHECK(t1.compare(t2) == 0, "bit_or");
+        t1.bit_sub(*all[1], *all[3], bvect::opt_none); bm::b200::bit_sub(ctx, t2, *all[1], *all[3]); CHECK(t1.compare(t2) == 0, "bit_sub");
+    }
+    // rs_index built on the GPU, consumed by the reference's own count_to / select
+    for (int k : {0, 3, 8, 23}) {
+        const bvect& bv = *all[k];
+        bvect::rs_index_type rs_ref, rs_gpu;
+        bv.build_rs_index(&rs_ref);
+        bm::b200::build_rs_index(ctx, bv, &rs_gpu);
+        CHECK(rs_ref.count() == rs_gpu.count(), "rs count k=%d", k);
+        unsigned nb_tot = (n_bits >> 16) + 1;
+        bool same = true;
+        for (unsigned nb = 0; nb < nb_tot; ++nb)
+            same &= rs_ref.count(nb) == rs_gpu.count(nb) && rs_ref.rcount(nb) == rs_gpu.rcount(nb) &&
+                    (rs_ref.count(nb) == 0 || rs_ref.sub_count(nb) == rs_gpu.sub_count(nb));
+        CHECK(same, "rs fields k=%d", k);
+        bool q = true;
+        for (int i = 0; i < 20000; ++i) {
+            bvect::size_type p = (bvect::size_type)(rng() % n_bits);
+            q &= bv.count_to(p, rs_gpu) == bv.count_to(p, rs_ref);
+            bvect::size_type r = (bvect::size_type)(rng() % (rs_ref.count() + 2)), p1 = 0, p2 = 0;
+            bool f1 = bv.select(r, p1, rs_ref), f2 = bv.select(r, p2, rs_gpu);
+            q &= (f1 == f2) && (!f1 || p1 == p2);
+        }
+        CHECK(q, "rank/select through the reference with the GPU-built index k=%d", k);
+    }
+    std::printf("%s: %d checks, %d failed\n", g_fail ? "FAILED" : "OK", g_checks, g_fail);
+    return g_fail ? 1 : 0;
+}

@@ -300,3 +300,16 @@ def test_full_size_properties_c2_shape(ctx):
         _, opop, *_ = orclib.oracle_aggregate(ps, bm.OP_OR, np.arange(nv), None, 0)
         assert pop[nb] == opop[0]
     dset.free()
+
+
+def test_cxx_binding_against_reference_bvector_level():
+    """bm::b200::aggregator<bm::bvector<>> (bitmagic_b200/include/bmb200_aggregator.hpp) vs bm::aggregator<> on real
+    bvectors: compare()==0, calc_stat kinds, rs_index fields, and the reference's own count_to/select running on
+    the GPU-built index.  The binary is built in the build container (it needs the reference headers)."""
+    import subprocess
+    exe = orclib.ORACLE_DIR / "_ref" / "test_cxx_binding"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/test_cxx_binding not built (needs /root/reference at build time)")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "OK:" in r.stdout
