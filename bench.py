@@ -117,6 +117,19 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def profiled_traffic(workload: str):
+    """dram__bytes_read+write per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    f = ROOT / "profiles" / "r01" / "ncu_agg_kernel_v5.json"
+    key = {"c3": "c3_agg_kernel_and_sub", "c2": "c2_agg_kernel_or"}.get(workload)
+    try:
+        d = json.loads(f.read_text())[key]
+        def gb(x):
+            return float(x["value"]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[x["unit"]]
+        return int(gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"]))
+    except Exception:
+        return None
+
+
 def set_stats(ps_kinds_counts, gap_words_exact, n_result_blocks, n_cols):
     """Algorithmic bytes: stored size of every source block (bit 8192 B, GAP 2*(len+1) B,
     FULL/NULL 0) + 8192 B per non-empty result block written + 12 B of popcount/digest per block column."""
@@ -372,7 +385,9 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps),
             "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "agg_kernel<%s>" % w["op"], "kernel_ms": kern_ms,
+                         "traffic": None if (args.cols and args.cols != w["n_blocks"]) else profiled_traffic(args.workload),
+                         "traffic_source": "profiles/r01/ncu_agg_kernel_v5.json (ncu --set full, same command, full-size shard)",
+                         "kernel": "agg_kernel<%s>" % w["op"], "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "peak_source": peak_src},
             "cpu_baseline": cpu,
             "result_bits": int(total_bits),
