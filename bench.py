@@ -130,11 +130,12 @@ def profiled_traffic(workload: str):
         return None
 
 
-def set_stats(ps_kinds_counts, gap_words_exact, n_result_blocks, n_cols):
+def set_stats(ps_kinds_counts, gap_words_exact, result_bytes, n_cols):
     """Algorithmic bytes: stored size of every source block (bit 8192 B, GAP 2*(len+1) B,
-    FULL/NULL 0) + 8192 B per non-empty result block written + 12 B of popcount/digest per block column."""
+    FULL/NULL 0) + the result blocks actually written (8192 B per bit-block, 2*(len+1) B per GAP block -- the
+    bit->GAP step is fused into the kernel) + 12 B of popcount/digest per block column."""
     n_bit = ps_kinds_counts["bit"]
-    return n_bit * 8192 + gap_words_exact * 2 + n_result_blocks * 8192 + n_cols * 12
+    return n_bit * 8192 + gap_words_exact * 2 + result_bytes + n_cols * 12
 
 
 def device_set_stats(ctx, dset, torch):
@@ -145,7 +146,7 @@ def device_set_stats(ctx, dset, torch):
     class Wrap:
         def __init__(self, addr, nbytes, typestr, shape):
             self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (addr, False), "version": 2}
-    desc = torch.as_tensor(Wrap(ptrs.desc, n * 4, "<i4", (n,)), device=f"cuda:{ctx.device}")
+    desc = torch.as_tensor(Wrap(ptrs.desc, n * 4, "<i4", (n,)), device=f"cuda:{ctx.device}").long() & 0xFFFFFFFF
     kind = desc & 3
     counts = {"null": int((kind == 0).sum()), "full": int((kind == 1).sum()), "bit": int((kind == 2).sum()), "gap": int((kind == 3).sum())}
     gap_words = 0
@@ -154,7 +155,8 @@ def device_set_stats(ctx, dset, torch):
         gb = torch.as_tensor(Wrap(ptrs.gap_base, (dset.n_blocks + 1) * 8, "<i8", (dset.n_blocks + 1,)), device=f"cuda:{ctx.device}")
         col = torch.arange(dset.n_blocks, device=desc.device).repeat_interleave(dset.n_vec)
         isgap = kind == 3
-        off = (gb[col[isgap]] + (desc[isgap] >> 2).long()) * 8
+        dg = desc[isgap]
+        off = (gb[col[isgap]] + ((dg >> 2) & 0x1FFFFFFF)) * 8 + (dg >> 31)      # + lead pad (BMB200_DESC_GAP_PAD)
         hdr = gp[off].long() & 0xFFFF
         gap_words = int(((hdr >> 3) + 1).sum())
     return counts, gap_words
@@ -313,8 +315,8 @@ def main():
 
     total_bits, any_ = res.total()
     kind_r, pop_r, dig_r, nr_r = res.meta()
-    n_res_blocks = int(((kind_r == bm.BLK_BIT) | (kind_r == bm.BLK_GAP)).sum())
-    alg_bytes = set_stats(counts, gap_words, n_res_blocks, n_cols)
+    res_bytes = int((kind_r == bm.BLK_BIT).sum()) * 8192 + int(2 * (nr_r[kind_r == bm.BLK_GAP].astype(np.int64) + 1).sum())
+    alg_bytes = set_stats(counts, gap_words, res_bytes, n_cols)
 
     # whole-job numbers
     src_blocks_all = torch.tensor([n_src_blocks], dtype=torch.int64, device=dev)

@@ -40,24 +40,17 @@ constexpr int kAggChunk   = 1024;   // group members classified per pass
 #ifndef BMB200_GAP_CHUNK
 #define BMB200_GAP_CHUNK 16384
 #endif
-#ifndef BMB200_VAR_SCATTER      /* 0: one run per lane, two u16 loads; 1: one run per lane, u32 load + shuffle; 2: two runs per lane, u64 load */
-#define BMB200_VAR_SCATTER 0
-#endif
-#ifndef BMB200_VAR_PREFETCH     /* fetch the next block's header one block ahead */
-#define BMB200_VAR_PREFETCH 0
-#endif
 #ifndef BMB200_LANES_PER_BLOCK   /* lanes that share one GAP block in the streamed scatter: 32, 16, 8 or 4 */
 #define BMB200_LANES_PER_BLOCK 16
 #endif
 #ifndef BMB200_VAR_ANTIPHASE     /* second resident CTA of an SM runs GAP phase first, bit phase second */
 #define BMB200_VAR_ANTIPHASE 0
 #endif
+#ifndef BMB200_VAR_UNROLL2       /* two scatter steps per loop trip: both loads issued before the first red */
+#define BMB200_VAR_UNROLL2 1
+#endif
 #ifndef BMB200_VAR_SLEEP_NS
 #define BMB200_VAR_SLEEP_NS 64
-#endif
-#if BMB200_VAR_SCATTER != 0
-#undef BMB200_LANES_PER_BLOCK
-#define BMB200_LANES_PER_BLOCK 32
 #endif
 constexpr uint32_t kLanesPerBlock = BMB200_LANES_PER_BLOCK;      // `lane` below = lane inside its group
 constexpr uint32_t kGroupsPerWarp = 32u / kLanesPerBlock;
@@ -84,6 +77,7 @@ struct AggParams {
     uint64_t* digest;          // [n_cols]
     uint32_t* nruns;           // [n_cols]
     uint8_t*  kind;            // [n_cols]
+    uint16_t* gaps;            // [n_cols][1280] GAP form of the columns classified GAP (compress mode), else null
     unsigned long long* total; // sum of popcounts
     uint32_t* work_counter;    // zeroed before launch
 };
@@ -92,6 +86,7 @@ struct AggParams {
 constexpr uint32_t kFlNull0 = 1u;   // a NULL block in group0
 constexpr uint32_t kFlFull0 = 2u;   // a FULL block in group0
 constexpr uint32_t kFlFull1 = 4u;   // a FULL block in group1 (SUB)
+constexpr uint32_t kRelMask = BMB200_DESC_REL_MASK;   // list entries are desc >> 2: unit in the low 29 bits, pad flag in bit 29
 
 // ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -127,7 +122,6 @@ __device__ __forceinline__ void fence_proxy_async()
 // raw 32-bit shared-window addresses keep the scatter loop free of generic->shared conversions
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return (uint32_t)v; }
-__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ void reds_or(uint32_t a, uint32_t v)  { asm volatile("red.shared.or.b32 [%0], %1;"  :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void reds_xor(uint32_t a, uint32_t v) { asm volatile("red.shared.xor.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 
@@ -190,80 +184,68 @@ __device__ __forceinline__ void apply_run(uint32_t Ks, uint32_t s, uint32_t e)
 // one warp, GAP block resident in shared memory at byte address `ba` (16-byte aligned, contiguous thanks to
 // the tail mirror); hdr = its header word.  Two runs per lane and step: one 64-bit load brings
 // buf[4t..4t+3]; the straddling run of the "first != want" case takes buf[4t+4] from the next lane.
+// `ba` = shared address of the block's 16-byte unit, `pad` = 1 when the block sits behind one u16 of lead padding
+// (BMB200_DESC_GAP_PAD).  The (start,end) pair of selected run j lives at A0 + 4j with
+//   A0 = &buf[0] when first == want (runs k = 2j+1), &buf[1] otherwise (runs k = 2j+2);
+// packers choose the pad so that A0 is 4-byte aligned for the 1-runs: one 32-bit load per run.
 template <bool XOR>
-__device__ __forceinline__ void gap_scatter_ring(uint32_t Ks, uint32_t ba, uint32_t hdr, uint32_t want, int lane)
+__device__ __forceinline__ void gap_scatter_ring(uint32_t Ks, uint32_t ba, uint32_t pad, uint32_t want, int lane)
 {
-    const uint32_t len = hdr >> 3;
-#if BMB200_VAR_SCATTER == 2
-    if ((hdr & 1u) == want) {
-        const uint32_t nsel = (len + 1u) >> 1;
-        for (uint32_t base = 0; base < nsel; base += 64) {
-            const uint32_t t = (base >> 1) + lane;
-            const uint2 v = lds64(ba + 8u * t);
-            const uint32_t j0 = 2u * t;
-            if (j0 < nsel)      apply_run<XOR>(Ks, j0 ? (v.x & 0xffffu) + 1u : 0u, v.x >> 16);
-            if (j0 + 1u < nsel) apply_run<XOR>(Ks, (v.y & 0xffffu) + 1u, v.y >> 16);
-        }
-    } else {
-        const uint32_t nsel = len >> 1;
-        for (uint32_t base = 0; base < nsel; base += 64) {          // warp-uniform trip count (shuffle inside)
-            const uint32_t t = (base >> 1) + lane;
-            const uint2 v = lds64(ba + 8u * t);
-            uint32_t nx = __shfl_down_sync(0xffffffffu, v.x, 1);
-            if (lane == 31) nx = lds16(ba + 8u * t + 8u);
-            const uint32_t j0 = 2u * t;
-            if (j0 < nsel)      apply_run<XOR>(Ks, (v.x >> 16) + 1u, v.y & 0xffffu);
-            if (j0 + 1u < nsel) apply_run<XOR>(Ks, (v.y >> 16) + 1u, nx & 0xffffu);
-        }
-    }
-#else
-    if ((hdr & 1u) == want) {
-        const uint32_t nsel = (len + 1u) >> 1;
-        for (uint32_t j = lane; j < nsel; j += kLanesPerBlock) {
-            const uint32_t w = lds32(ba + 4u * j);
-            apply_run<XOR>(Ks, j ? (w & 0xffffu) + 1u : 0u, w >> 16);
-        }
-    } else {
-        const uint32_t nsel = len >> 1;
-#if BMB200_VAR_SCATTER == 1
-        for (uint32_t base = 0; base < nsel; base += 31) {          // 31 runs per step: lane 31 only feeds lane 30
-            const uint32_t j = base + lane;
-            const uint32_t w = lds32(ba + 4u * j);
-            const uint32_t nx = __shfl_down_sync(0xffffffffu, w, 1);
-            if (lane < 31 && j < nsel) apply_run<XOR>(Ks, (w >> 16) + 1u, nx & 0xffffu);
-        }
-#else
-        for (uint32_t j = lane; j < nsel; j += kLanesPerBlock) {
-            const uint32_t a = ba + 4u * j;
-            apply_run<XOR>(Ks, lds16(a + 2u) + 1u, lds16(a + 4u));
-        }
-#endif
-    }
-#endif
-}
-
-// one warp, GAP block read straight from global memory (fallback for unsorted / sparse member lists);
-// w_first = pair word `lane` of the block, loaded by the caller one block ahead
-template <bool XOR>
-__device__ __forceinline__ void gap_scatter_gather(uint32_t Ks, const uint32_t* __restrict__ g32, uint32_t w_first,
-                                                   uint32_t want, int lane)
-{
-    const uint32_t hdr = __shfl_sync(0xffffffffu, w_first, 0) & 0xffffu;
+    const uint32_t h = ba + 2u * pad;
+    const uint32_t hdr = lds16(h);
     const uint32_t len = hdr >> 3;
     const bool odd = ((hdr & 1u) == want);
     const uint32_t nsel = odd ? (len + 1u) >> 1 : len >> 1;
-    uint32_t w = w_first;
-    for (uint32_t base = 0; base < nsel; base += 32) {
-        const uint32_t j = base + lane;
-        uint32_t wn = 0;
-        if (base + 32 < nsel && 2u * (j + 32u) <= len) wn = ld_nc_u32(g32 + j + 32u);   // next iteration's word
-        uint32_t w2 = 0;
-        if (!odd && j < nsel) w2 = ld_nc_u32(g32 + j + 1u);
-        if (j < nsel) {
-            if (odd) apply_run<XOR>(Ks, j ? (w & 0xffffu) + 1u : 0u, w >> 16);
-            else     apply_run<XOR>(Ks, (w >> 16) + 1u, w2 & 0xffffu);
+    const uint32_t A0 = h + (odd ? 0u : 2u);
+    if ((A0 & 2u) == 0u) {
+#if BMB200_VAR_UNROLL2
+        for (uint32_t j = lane; j < nsel; j += 2u * kLanesPerBlock) {
+            const uint32_t a = A0 + 4u * j;
+            const bool v1 = (j + kLanesPerBlock < nsel);
+            const uint32_t w0 = lds32(a);
+            const uint32_t w1 = v1 ? lds32(a + 4u * kLanesPerBlock) : 0u;
+            apply_run<XOR>(Ks, (odd && j == 0u) ? 0u : (w0 & 0xffffu) + 1u, w0 >> 16);
+            if (v1) apply_run<XOR>(Ks, (w1 & 0xffffu) + 1u, w1 >> 16);
         }
-        w = wn;
+#else
+        for (uint32_t j = lane; j < nsel; j += kLanesPerBlock) {
+            const uint32_t w = lds32(A0 + 4u * j);
+            apply_run<XOR>(Ks, (odd && j == 0u) ? 0u : (w & 0xffffu) + 1u, w >> 16);
+        }
+#endif
+    } else {
+#if BMB200_VAR_UNROLL2
+        for (uint32_t j = lane; j < nsel; j += 2u * kLanesPerBlock) {
+            const uint32_t a = A0 + 4u * j;
+            const bool v1 = (j + kLanesPerBlock < nsel);
+            const uint32_t s0 = lds16(a), e0 = lds16(a + 2u);
+            const uint32_t s1 = v1 ? lds16(a + 4u * kLanesPerBlock) : 0u, e1 = v1 ? lds16(a + 4u * kLanesPerBlock + 2u) : 0u;
+            apply_run<XOR>(Ks, (odd && j == 0u) ? 0u : s0 + 1u, e0);
+            if (v1) apply_run<XOR>(Ks, s1 + 1u, e1);
+        }
+#else
+        for (uint32_t j = lane; j < nsel; j += kLanesPerBlock) {
+            const uint32_t a = A0 + 4u * j;
+            const uint32_t sv = lds16(a), ev = lds16(a + 2u);
+            apply_run<XOR>(Ks, (odd && j == 0u) ? 0u : sv + 1u, ev);
+        }
+#endif
+    }
+}
+
+// one warp, GAP block read straight from global memory (fallback for unsorted / sparse member lists);
+// g = &buf[0] (lead pad already skipped)
+template <bool XOR>
+__device__ __forceinline__ void gap_scatter_gather(uint32_t Ks, const uint16_t* __restrict__ g, uint32_t want, int lane)
+{
+    const uint32_t hdr = g[0];
+    const uint32_t len = hdr >> 3;
+    const bool odd = ((hdr & 1u) == want);
+    const uint32_t nsel = odd ? (len + 1u) >> 1 : len >> 1;
+    const uint16_t* a0 = g + (odd ? 0 : 1);
+    for (uint32_t j = lane; j < nsel; j += 32) {
+        const uint32_t sv = a0[2u * j], ev = a0[2u * j + 1u];
+        apply_run<XOR>(Ks, (odd && j == 0u) ? 0u : sv + 1u, ev);
     }
 }
 
@@ -380,17 +362,17 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
             uint32_t w_lo[2], w_bytes[2], nch[2];
             {
                 int bad0 = 0, bad1 = 0;
-                for (uint32_t i = tid; i + 1 < ngap0; i += kAggThreads) bad0 |= !(lst_gap[i] < lst_gap[i + 1]);
+                for (uint32_t i = tid; i + 1 < ngap0; i += kAggThreads) bad0 |= !((lst_gap[i] & kRelMask) < (lst_gap[i + 1] & kRelMask));
                 for (uint32_t i = tid; i + 1 < ngap1; i += kAggThreads)
-                    bad1 |= !(lst_gap[kAggChunk - 1 - i] < lst_gap[kAggChunk - 2 - i]);
+                    bad1 |= !((lst_gap[kAggChunk - 1 - i] & kRelMask) < (lst_gap[kAggChunk - 2 - i] & kRelMask));
                 // NB: __syncthreads_or returns a predicate, not a bitwise OR -> one vote per list
                 const int anybad = (__syncthreads_or(bad0) ? 1 : 0) | (__syncthreads_or(bad1) ? 2 : 0);
                 for (int q = 0; q < 2; ++q) {
                     const uint32_t n = q ? ngap1 : ngap0;
                     stream_ok[q] = false; w_lo[q] = 0; w_bytes[q] = 0; nch[q] = 0;
                     if (n == 0 || p.gap_mode == 1u || (anybad & (1 << q))) continue;
-                    const uint32_t lo = q ? lst_gap[kAggChunk - 1] : lst_gap[0];
-                    const uint32_t hi = q ? lst_gap[kAggChunk - n] : lst_gap[n - 1];
+                    const uint32_t lo = (q ? lst_gap[kAggChunk - 1] : lst_gap[0]) & kRelMask;
+                    const uint32_t hi = (q ? lst_gap[kAggChunk - n] : lst_gap[n - 1]) & kRelMask;
                     const uint64_t span = (uint64_t)(hi - lo) * 16ull + kGapMaxBytes;
                     if (span > (uint64_t)n * 4096ull) continue;                   // sparse subset: gather instead
                     uint64_t avail = gseg_avail - (uint64_t)lo * 16ull;
@@ -400,7 +382,7 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
                     nch[q] = (uint32_t)((wb + kGapChunkBytes - 1) / kGapChunkBytes);
                 }
             }
-            auto L = [&](int q, uint32_t i) -> uint32_t { return q ? lst_gap[kAggChunk - 1 - i] : lst_gap[i]; };
+            auto L = [&](int q, uint32_t i) -> uint32_t { return (q ? lst_gap[kAggChunk - 1 - i] : lst_gap[i]) & kRelMask; };   // 16-byte unit of entry i
             auto issue_fill = [&](int q, uint32_t c) {     // one thread: arm stage c % S and start the bulk copy
                 const uint32_t s = c % kGapStages;
                 const uint32_t off = c * kGapChunkBytes;
@@ -438,37 +420,16 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
                     }
                     // block i always goes to warp i % 16, so the per-round remainders rotate over the warps
                     const uint32_t ibeg = s_cfirst[r], iend = s_cfirst[r + 1];
-#if BMB200_VAR_PREFETCH
-                    uint32_t i = ibeg + ((warp - ibeg) & (kAggWarps - 1));
-                    uint32_t ba = 0, hdr = 0;
-                    if (i < iend) {
-                        const uint32_t rel = q ? lst_gap[kAggChunk - 1 - i] : lst_gap[i];
-                        ba = ring_s + (((rel - wlo) * 16u) & (kRingBytes - 1u));
-                        hdr = lds16(ba);
-                    }
-                    while (i < iend) {                        // header of the next block is fetched one block ahead
-                        const uint32_t in = i + kAggWarps;
-                        uint32_t ban = 0, hdrn = 0;
-                        if (in < iend) {
-                            const uint32_t rel = q ? lst_gap[kAggChunk - 1 - in] : lst_gap[in];
-                            ban = ring_s + (((rel - wlo) * 16u) & (kRingBytes - 1u));
-                            hdrn = lds16(ban);
-                        }
-                        gap_scatter_ring<OP == BMB200_OP_XOR>(Ks, ba, hdr, want, lane);
-                        i = in; ba = ban; hdr = hdrn;
-                    }
-#else
                     {   // block i always goes to slot i % (16 * groups): the per-round remainders rotate over the slots
                         constexpr uint32_t kSlots = kAggWarps * kGroupsPerWarp;
                         const uint32_t slot = (uint32_t)warp * kGroupsPerWarp + ((uint32_t)lane / kLanesPerBlock);
                         const int sub = lane & (int)(kLanesPerBlock - 1u);
                         for (uint32_t i = ibeg + ((slot - ibeg) & (kSlots - 1u)); i < iend; i += kSlots) {
-                            const uint32_t rel = q ? lst_gap[kAggChunk - 1 - i] : lst_gap[i];
-                            const uint32_t ba = ring_s + (((rel - wlo) * 16u) & (kRingBytes - 1u));
-                            gap_scatter_ring<OP == BMB200_OP_XOR>(Ks, ba, lds16(ba), want, sub);
+                            const uint32_t ent = q ? lst_gap[kAggChunk - 1 - i] : lst_gap[i];
+                            const uint32_t ba = ring_s + ((((ent & kRelMask) - wlo) * 16u) & (kRingBytes - 1u));
+                            gap_scatter_ring<OP == BMB200_OP_XOR>(Ks, ba, ent >> 29, want, sub);
                         }
                     }
-#endif
                     __syncwarp();
                     if (lane == 0) {
                         __threadfence_block();
@@ -485,19 +446,13 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
             };
             auto gather_pass = [&](int q, uint32_t want) {       // per warp; dynamic block distribution
                 const uint32_t n = q ? ngap1 : ngap0;
-                uint32_t g = 0;
-                if (lane == 0) g = atomicAdd(&s_gap_next, 1u);
-                g = __shfl_sync(0xffffffffu, g, 0);
-                const uint32_t* g32 = nullptr; uint32_t wf = 0;
-                if (g < n) { g32 = reinterpret_cast<const uint32_t*>(gseg + (size_t)L(q, g) * kGapUnit); wf = ld_nc_u32(g32 + lane); }
-                while (g < n) {
-                    uint32_t gn = 0;
-                    if (lane == 0) gn = atomicAdd(&s_gap_next, 1u);
-                    gn = __shfl_sync(0xffffffffu, gn, 0);
-                    const uint32_t* g32n = nullptr; uint32_t wfn = 0;
-                    if (gn < n) { g32n = reinterpret_cast<const uint32_t*>(gseg + (size_t)L(q, gn) * kGapUnit); wfn = ld_nc_u32(g32n + lane); }
-                    gap_scatter_gather<OP == BMB200_OP_XOR>(Ks, g32, wf, want, lane);
-                    g = gn; g32 = g32n; wf = wfn;
+                for (;;) {
+                    uint32_t g = 0;
+                    if (lane == 0) g = atomicAdd(&s_gap_next, 1u);
+                    g = __shfl_sync(0xffffffffu, g, 0);
+                    if (g >= n) break;
+                    const uint32_t ent = q ? lst_gap[kAggChunk - 1 - g] : lst_gap[g];
+                    gap_scatter_gather<OP == BMB200_OP_XOR>(Ks, gseg + (size_t)(ent & kRelMask) * kGapUnit + (ent >> 29), want, lane);
                 }
             };
 
@@ -562,8 +517,8 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
         if (state == 0) R = make_uint4(0u, 0u, 0u, 0u);
         if (state == 1) R = make_uint4(~0u, ~0u, ~0u, ~0u);
 
-        // popcount, digest (4 waves per warp: 8 threads x 4 words = one 32-word wave), transitions
-        K4[tid] = R;                 // reuse K so each thread can see its left neighbour's last word
+        // popcount, digest (4 waves per warp: 8 threads x 4 words = one 32-word wave), run ends
+        K4[tid] = R;                 // reuse K so each thread can see its right neighbour's first word
         const uint32_t nz = (R.x | R.y | R.z | R.w) != 0u;
         const uint32_t bal = __ballot_sync(0xffffffffu, nz);
         uint32_t dg4 = 0;
@@ -571,17 +526,25 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
         for (int q = 0; q < 4; ++q) if ((bal >> (8 * q)) & 0xffu) dg4 |= (1u << q);
         uint32_t pc = warp_sum(popc4(R));
         __syncthreads();
-        uint32_t prev = tid ? (K[4 * tid - 1] >> 31) : (R.x & 1u);
-        uint32_t tr = __popc(R.x ^ ((R.x << 1) | prev));
-        tr += __popc(R.y ^ ((R.y << 1) | (R.x >> 31)));
-        tr += __popc(R.z ^ ((R.z << 1) | (R.y >> 31)));
-        tr += __popc(R.w ^ ((R.w << 1) | (R.z >> 31)));
-        tr = warp_sum(tr);
-        if (lane == 0) { s_pc[warp] = pc; s_tr[warp] = tr; s_dg[warp] = dg4; }
-        __syncthreads();
-        uint32_t tpc = 0, ttr = 0; uint64_t dg = 0;
+        // x has a bit at every position p whose successor differs (bit_block_calc_change src/bmfunc.h:6040 counts
+        // them; bit_block_to_gap src/bmfunc.h:5540 emits them as run ends); bit 65535 has no successor
+        const uint32_t nxt = (tid + 1 < kAggThreads) ? (K[4 * tid + 4] & 1u) : (R.w >> 31);
+        const uint32_t x0 = R.x ^ ((R.x >> 1) | (R.y << 31)), x1 = R.y ^ ((R.y >> 1) | (R.z << 31));
+        const uint32_t x2 = R.z ^ ((R.z >> 1) | (R.w << 31)), x3 = R.w ^ ((R.w >> 1) | (nxt << 31));
+        const uint32_t cnt = __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3);
+        uint32_t inc = cnt;          // inclusive warp scan of the run-end counts
 #pragma unroll
-        for (int w = 0; w < kAggWarps; ++w) { tpc += s_pc[w]; ttr += s_tr[w]; dg |= (uint64_t)s_dg[w] << (4 * w); }
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+        if (lane == 31) s_tr[warp] = inc;
+        if (lane == 0) { s_pc[warp] = pc; s_dg[warp] = dg4; }
+        __syncthreads();
+        uint32_t tpc = 0, ttr = 0, woff = 0; uint64_t dg = 0;
+#pragma unroll
+        for (int w = 0; w < kAggWarps; ++w) {
+            const uint32_t t = s_tr[w];
+            tpc += s_pc[w]; ttr += t; if (w < warp) woff += t;
+            dg |= (uint64_t)s_dg[w] << (4 * w);
+        }
         const uint32_t runs = ttr + 1u;
 
         // result kind: aggregator stores nothing when the AND/SUB/XOR digest is empty; otherwise
@@ -595,8 +558,24 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
         else if (runs < BMB200_GAP_THRESHOLD) kd = BMB200_BLK_GAP;
         else kd = BMB200_BLK_BIT;
 
-        if (p.store_blocks && (kd == BMB200_BLK_BIT || kd == BMB200_BLK_GAP))
+        if (p.store_blocks && kd == BMB200_BLK_BIT)
             st_stream_v4(reinterpret_cast<uint4*>(p.blocks) + (size_t)col * (kBlockWords / 4) + tid, R);
+        if (p.store_blocks && kd == BMB200_BLK_GAP) {
+            // bit -> GAP fused here (the bit_to_gap branch of opt_copy_bit_block): run ends in order, header last
+            uint16_t* gout = p.gaps + (size_t)col * kGapMax;
+            uint32_t off = 1u + woff + inc - cnt;
+            const uint32_t base = 128u * tid;
+            uint32_t m;
+            m = x0; while (m) { const uint32_t b = __ffs(m) - 1u; m &= m - 1u; gout[off++] = (uint16_t)(base + b); }
+            m = x1; while (m) { const uint32_t b = __ffs(m) - 1u; m &= m - 1u; gout[off++] = (uint16_t)(base + 32u + b); }
+            m = x2; while (m) { const uint32_t b = __ffs(m) - 1u; m &= m - 1u; gout[off++] = (uint16_t)(base + 64u + b); }
+            m = x3; while (m) { const uint32_t b = __ffs(m) - 1u; m &= m - 1u; gout[off++] = (uint16_t)(base + 96u + b); }
+            if (tid == 0) {
+                const uint32_t lvl = runs <= 124u ? 0u : runs <= 252u ? 1u : runs <= 508u ? 2u : 3u;   // gap_calc_level src/bmfunc.h:5418
+                gout[runs] = 65535u;
+                gout[0] = (uint16_t)((R.x & 1u) | (lvl << 1) | (runs << 3));
+            }
+        }
         if (tid == 0) {
             p.popcnt[col] = tpc;
             p.digest[col] = dg;

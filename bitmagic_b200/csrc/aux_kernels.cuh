@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) rs_block_kernel(const SetView set, uint32
         const uint32_t kd = d & 3u, rel = d >> 2;
         uint32_t tot = 0, le0 = 0, le1 = 0, a0 = 0, a1 = 0;
         if (kd == BMB200_BLK_GAP) {
-            const uint16_t* g = set.gap_pool + (set.gap_base[nb] + rel) * (size_t)kGapUnit;
+            const uint16_t* g = set.gap_pool + (set.gap_base[nb] + (rel & BMB200_DESC_REL_MASK)) * (size_t)kGapUnit + (rel >> 29);
             const uint32_t hdr = g[0], len = hdr >> 3, first = hdr & 1u;
             uint32_t lt0 = 0, lt1 = 0;   // run ends < border+1  (for gap_bfind)
             for (uint32_t k = 1 + lane; k <= len; k += 32) {
@@ -147,13 +147,30 @@ __global__ void __launch_bounds__(256) rs_block_kernel(const SetView set, uint32
             a0 = (i0 << 1) | (first ^ ((i0 - 1u) & 1u));
             a1 = (i1 << 1) | (first ^ ((i1 - 1u) & 1u));
         } else if (kd != BMB200_BLK_NULL) {
-            const uint32_t* b = (kd == BMB200_BLK_BIT)
-                                    ? set.bit_pool + (set.bit_base[nb] + rel) * (size_t)kBlockWords : nullptr;
-            for (uint32_t wi = lane; wi < kBlockWords; wi += 32) {
-                const uint32_t w = b ? b[wi] : 0xffffffffu;
-                tot += __popc(w);
-                le0 += cnt_le(w, wi, kRs3B0);   le1 += cnt_le(w, wi, kRs3B1);
-                a0  += cnt_le(w, wi, kRs3B0_1); a1  += cnt_le(w, wi, kRs3B1_1);
+            if (kd == BMB200_BLK_BIT) {
+                // 16 coalesced 512-byte warp loads per block, all issued before the popcounts (8 KB in flight per warp)
+                const uint4* b4 = reinterpret_cast<const uint4*>(set.bit_pool + (set.bit_base[nb] + rel) * (size_t)kBlockWords);
+                uint4 v[16];
+#pragma unroll
+                for (int it = 0; it < 16; ++it) v[it] = ld_stream_v4(b4 + it * 32 + lane);
+#pragma unroll
+                for (int it = 0; it < 16; ++it) {
+                    const uint32_t wi = (uint32_t)(it * 32 + lane) * 4u;
+                    const uint32_t w4[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t w = w4[q];
+                        tot += __popc(w);
+                        le0 += cnt_le(w, wi + q, kRs3B0);   le1 += cnt_le(w, wi + q, kRs3B1);
+                        a0  += cnt_le(w, wi + q, kRs3B0_1); a1  += cnt_le(w, wi + q, kRs3B1_1);
+                    }
+                }
+            } else {   // FULL block: an all-ones block, like BLOCK_ADDR_SAN in src/bm.h:2628
+                for (uint32_t wi = lane; wi < kBlockWords; wi += 32) {
+                    tot += 32u;
+                    le0 += cnt_le(0xffffffffu, wi, kRs3B0);   le1 += cnt_le(0xffffffffu, wi, kRs3B1);
+                    a0  += cnt_le(0xffffffffu, wi, kRs3B0_1); a1  += cnt_le(0xffffffffu, wi, kRs3B1_1);
+                }
             }
             tot = warp_sum(tot); le0 = warp_sum(le0); le1 = warp_sum(le1); a0 = warp_sum(a0); a1 = warp_sum(a1);
         }
@@ -282,7 +299,7 @@ __global__ void __launch_bounds__(256) rs_rank_kernel(const RsView rs, const uin
                 else if ((int32_t)in < ap[best]) c -= bit_count_range(b, in + 1u, (uint32_t)ap[best]);
                 r += c;
             } else {
-                const uint16_t* g = rs.set.gap_pool + (rs.set.gap_base[nb] + rel) * (size_t)kGapUnit;
+                const uint16_t* g = rs.set.gap_pool + (rs.set.gap_base[nb] + (rel & BMB200_DESC_REL_MASK)) * (size_t)kGapUnit + (rel >> 29);
                 uint32_t c;
                 if (in <= kRs3B0)      c = gap_count_from(g, 1u, 0u, in);
                 else if (in <= kRs3B1) c = first + gap_count_from(g, a0 >> 1, kRs3B0 + 1u, in);
@@ -340,7 +357,7 @@ __global__ void __launch_bounds__(256) rs_select_kernel(const RsView rs, const u
                 }
                 bit = wi * 32u + __fns(w, 0, (int)need);
             } else {
-                const uint16_t* g = rs.set.gap_pool + (rs.set.gap_base[nb] + rel) * (size_t)kGapUnit;
+                const uint16_t* g = rs.set.gap_pool + (rs.set.gap_base[nb] + (rel & BMB200_DESC_REL_MASK)) * (size_t)kGapUnit + (rel >> 29);
                 const uint32_t firstv = g[0] & 1u;
                 uint32_t k = 1u, s = 0u, need = rr;
                 if (first + second < rr) { k = a1 >> 1; s = kRs3B1 + 1u; need = rr - first - second; }
@@ -424,12 +441,12 @@ __global__ void __launch_bounds__(kPostThreads) synth_classify_kernel(uint32_t n
         else if (runs < BMB200_GAP_THRESHOLD) kd = BMB200_BLK_GAP;   // optimize_bit_block src/bmblocks.h:1414-1437
         else kd = BMB200_BLK_BIT;
         kind8[item] = (uint8_t)kd;
-        glen[item] = (uint16_t)runs;
+        glen[item] = (uint16_t)((runs & 0x7fffu) | ((w[0] & 1u) << 15));   // bit 15 = first bit (tid 0 owns word 0)
     }
 }
 
 // per column: exclusive scans over the vectors -> descriptors + column totals
-__global__ void __launch_bounds__(256) synth_layout_kernel(uint32_t n_vec, const uint8_t* __restrict__ kind8,
+__global__ void __launch_bounds__(256) synth_layout_kernel(uint32_t n_vec, uint32_t use_pad, const uint8_t* __restrict__ kind8,
                                                            const uint16_t* __restrict__ glen,
                                                            uint32_t* __restrict__ desc,
                                                            uint64_t* __restrict__ col_bits, uint64_t* __restrict__ col_gaps)
@@ -442,11 +459,15 @@ __global__ void __launch_bounds__(256) synth_layout_kernel(uint32_t n_vec, const
     __syncthreads();
     for (uint32_t base = 0; base < n_vec; base += 256u) {
         const uint32_t v = base + tid;
-        uint32_t kd = 0, nbit = 0, ngap = 0;
+        uint32_t kd = 0, nbit = 0, ngap = 0, pad = 0;
         if (v < n_vec) {
             kd = kind8[(size_t)nb * n_vec + v];
             nbit = (kd == BMB200_BLK_BIT);
-            if (kd == BMB200_BLK_GAP) ngap = ((uint32_t)glen[(size_t)nb * n_vec + v] + 1u + kGapUnit - 1u) / kGapUnit;
+            if (kd == BMB200_BLK_GAP) {
+                const uint32_t gl = glen[(size_t)nb * n_vec + v];
+                pad = ((gl >> 15) || !use_pad) ? 0u : 1u;       // BMB200_DESC_GAP_PAD: align the 1-run pairs
+                ngap = ((gl & 0x7fffu) + 1u + pad + kGapUnit - 1u) / kGapUnit;
+            }
         }
         uint32_t ib = nbit, ig = ngap;
 #pragma unroll
@@ -460,7 +481,7 @@ __global__ void __launch_bounds__(256) synth_layout_kernel(uint32_t n_vec, const
         for (int w = 0; w < 8; ++w) { if (w < warp) { ob += s_wb[w]; og += s_wg[w]; } tb += s_wb[w]; tg += s_wg[w]; }
         if (v < n_vec) {
             const uint32_t rel = (kd == BMB200_BLK_BIT) ? ob + ib - nbit : (kd == BMB200_BLK_GAP) ? og + ig - ngap : 0u;
-            desc[(size_t)nb * n_vec + v] = kd | (rel << 2);
+            desc[(size_t)nb * n_vec + v] = kd | (rel << 2) | (pad << 31);
         }
         __syncthreads();
         if (tid == 0) { s_cb += tb; s_cg += tg; }
@@ -509,7 +530,7 @@ __global__ void __launch_bounds__(kPostThreads) synth_write_kernel(uint32_t n_ve
     __shared__ uint32_t s_scan[8];
     const uint64_t item = blockIdx.x;
     const uint32_t nb = (uint32_t)(item / n_vec), v = (uint32_t)(item % n_vec);
-    const uint32_t d = desc[item], kd = d & 3u, rel = d >> 2;
+    const uint32_t d = desc[item], kd = d & 3u, rel = (d >> 2) & BMB200_DESC_REL_MASK, pad = d >> 31;
     if (kd != BMB200_BLK_BIT && kd != BMB200_BLK_GAP) return;
     const int tid = threadIdx.x;
     const uint64_t sd = seed[v]; const uint32_t th = thr[v];
@@ -524,11 +545,13 @@ __global__ void __launch_bounds__(kPostThreads) synth_write_kernel(uint32_t n_ve
 #pragma unroll
         for (int i = 0; i < 8; ++i) s_blk[8 * tid + i] = w[i];
         __syncthreads();
-        uint16_t* out = gap_pool + (gap_base[nb] + rel) * (size_t)kGapUnit;
+        uint16_t* unit = gap_pool + (gap_base[nb] + rel) * (size_t)kGapUnit;
+        uint16_t* out = unit + pad;
         const uint32_t len = block_to_gap_256(s_blk, s_scan, out, kGapMax - 1u);
-        // zero the padding up to the 16-byte unit
-        const uint32_t n = len + 1u, npad = (n + kGapUnit - 1u) / kGapUnit * kGapUnit;
-        if (tid < (int)(npad - n)) out[n + tid] = 0;
+        // zero the lead pad and the tail up to the 16-byte unit
+        const uint32_t n = len + 1u + pad, npad = (n + kGapUnit - 1u) / kGapUnit * kGapUnit;
+        if (tid < (int)(npad - n)) unit[n + tid] = 0;
+        if (tid == 0 && pad) unit[0] = 0;
     }
 }
 

@@ -304,7 +304,9 @@ int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks
                 if (!g) return BMB200_ERR_BADARG;
                 uint32_t words = (uint32_t)(g[0] >> 3) + 1u;
                 if (words > kGapMax) return BMB200_ERR_BADARG;
-                rel = (uint32_t)ngap; ngap += (words + kGapUnit - 1) / kGapUnit;
+                // BMB200_DESC_GAP_PAD is supported by every kernel but measured ~1-2 % slower on B200 (profiles/r01), so off
+                const uint32_t pad = (getenv("BMB200_GAP_PAD") && !(g[0] & 1u)) ? 1u : 0u;
+                rel = (uint32_t)ngap | (pad << 29); ngap += (words + pad + kGapUnit - 1) / kGapUnit;
             } else if (kd > 3u) return BMB200_ERR_BADARG;
             desc[(size_t)nb * n_vec + v] = kd | (rel << 2);
         }
@@ -324,7 +326,7 @@ int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks
                 memcpy(hb + (bb[nb] + rel) * (size_t)kBlockWords, vecs[v].ptr[nb], BMB200_BLOCK_BYTES);
             else if (kd == BMB200_BLK_GAP) {
                 const uint16_t* g = (const uint16_t*)vecs[v].ptr[nb];
-                memcpy(hg + (gb[nb] + rel) * (size_t)kGapUnit, g, ((size_t)(g[0] >> 3) + 1) * 2);
+                memcpy(hg + (gb[nb] + (rel & BMB200_DESC_REL_MASK)) * (size_t)kGapUnit + (rel >> 29), g, ((size_t)(g[0] >> 3) + 1) * 2);
             }
         }
     bmb200_packed_set h{n_vec, n_blocks, desc.data(), bb.data(), gb.data(), hb, hg};
@@ -461,7 +463,7 @@ int bmb200_synth_set(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks,
     cudaMemcpyAsync(d_thr, thr.data(), n_vec * 4, cudaMemcpyHostToDevice, st);
     synth_classify_kernel<<<(unsigned)items, kPostThreads, 0, st>>>(n_vec, n_blocks, d_seed, d_thr, optimize, d_kind, d_glen);
     if ((rc = after_launch(ctx))) { cleanup_tmp(); cudaFree(desc); cudaFree(bb); cudaFree(gb); return rc; }
-    synth_layout_kernel<<<n_blocks, 256, 0, st>>>(n_vec, d_kind, d_glen, desc, d_cb, d_cg);
+    synth_layout_kernel<<<n_blocks, 256, 0, st>>>(n_vec, getenv("BMB200_NO_PAD") ? 0u : 1u, d_kind, d_glen, desc, d_cb, d_cg);
     after_launch(ctx);
     scan_u64_kernel<<<1, 1024, 0, st>>>(d_cb, n_blocks, bb); after_launch(ctx);
     scan_u64_kernel<<<1, 1024, 0, st>>>(d_cg, n_blocks, gb); after_launch(ctx);
@@ -569,7 +571,7 @@ int bmb200_aggregate(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_agg_ar
     p.set = set->v; p.group = ctx->d_group; p.n0 = a->n0; p.n1 = n1;
     p.nb_from = a->nb_from; p.n_cols = n_cols;
     p.compress = compress ? 1u : 0u; p.store_blocks = store ? 1u : 0u;
-    p.blocks = r->blocks; p.popcnt = r->popcnt; p.digest = r->digest; p.nruns = r->nruns; p.kind = r->kind;
+    p.blocks = r->blocks; p.popcnt = r->popcnt; p.digest = r->digest; p.nruns = r->nruns; p.kind = r->kind; p.gaps = r->gaps;
     p.total = r->total; p.work_counter = ctx->d_work;
     p.gap_mode = (uint32_t)ctx->gap_mode; p.gap_pool_bytes = set->gap_pool_bytes;
     if (!ctx->attr_set) {
@@ -590,7 +592,7 @@ int bmb200_aggregate(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_agg_ar
     int rc = after_launch(ctx);
     if (rc) { if (!*inout) bmb200_result_free(r); return rc; }
     *inout = r;
-    if (store && compress) return bmb200_result_optimize(r);
+    if (store && compress) r->gaps_ready = true;      // bit -> GAP conversion is fused into the kernel epilogue
     return BMB200_OK;
 }
 

@@ -192,7 +192,7 @@ class PackedSet:
     gap_pool: np.ndarray   # u16
 
     @classmethod
-    def pack(cls, vectors: list[BVector], n_blocks: int | None = None) -> "PackedSet":
+    def pack(cls, vectors: list[BVector], n_blocks: int | None = None, gap_pad: bool = False) -> "PackedSet":
         """Walk the host block trees column by column (what the binding does with get_block_ptr(i,j))."""
         nv = len(vectors)
         nb_tot = n_blocks if n_blocks is not None else max(v.n_blocks for v in vectors)
@@ -211,12 +211,13 @@ class PackedSet:
                 elif k == BLK_GAP:
                     g = bv.blocks[nb]
                     n = gap_words(g)
-                    units = (n + GAP_UNIT_WORDS - 1) // GAP_UNIT_WORDS
+                    pad = 1 if (gap_pad and not (int(g[0]) & 1)) else 0   # optional lead pad (BMB200_DESC_GAP_PAD)
+                    units = (n + pad + GAP_UNIT_WORDS - 1) // GAP_UNIT_WORDS
                     padded = np.zeros(units * GAP_UNIT_WORDS, dtype=np.uint16)
-                    padded[:n] = g[:n]
-                    rel = ngap; ngap += units
+                    padded[pad:pad + n] = g[:n]
+                    rel = ngap | (pad << 29); ngap += units
                     gaps.append(padded)
-                desc[nb * nv + v] = k | (rel << 2)
+                desc[nb * nv + v] = k | ((rel << 2) & 0xFFFFFFFF)
             bb[nb + 1] = bb[nb] + np.uint64(nbit)
             gb[nb + 1] = gb[nb] + np.uint64(ngap)
         bit_pool = np.concatenate(bits).astype(np.uint32) if bits else np.zeros(0, np.uint32)
@@ -231,7 +232,7 @@ class PackedSet:
             o = (int(self.bit_base[nb]) + rel) * BLOCK_WORDS
             return k, self.bit_pool[o:o + BLOCK_WORDS]
         if k == BLK_GAP:
-            o = (int(self.gap_base[nb]) + rel) * GAP_UNIT_WORDS
+            o = (int(self.gap_base[nb]) + (rel & 0x1FFFFFFF)) * GAP_UNIT_WORDS + (rel >> 29)
             n = (int(self.gap_pool[o]) >> 3) + 1
             return k, self.gap_pool[o:o + n]
         return k, None

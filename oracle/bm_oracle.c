@@ -214,8 +214,8 @@ static inline const uint32_t* set_bit_ptr(const bmb200_packed_set* s, uint32_t n
     return s->bit_pool + (s->bit_base[nb] + rel) * (size_t)BW;
 }
 static inline const uint16_t* set_gap_ptr(const bmb200_packed_set* s, uint32_t nb, uint32_t rel)
-{
-    return s->gap_pool + (s->gap_base[nb] + rel) * (size_t)BMB200_GAP_UNIT_WORDS;
+{   /* rel = desc >> 2: low 29 bits = 16-byte unit, bit 29 (= desc bit 31) = one u16 of lead padding */
+    return s->gap_pool + (s->gap_base[nb] + (rel & BMB200_DESC_REL_MASK)) * (size_t)BMB200_GAP_UNIT_WORDS + (rel >> 29);
 }
 
 void orc_expand_block(const bmb200_packed_set* s, uint32_t vec, uint32_t nb, uint32_t* out)

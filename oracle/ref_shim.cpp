@@ -38,7 +38,7 @@ inline uint32_t set_desc(const bmb200_packed_set* s, uint32_t v, uint32_t nb)
 inline const uint32_t* set_bit_ptr(const bmb200_packed_set* s, uint32_t nb, uint32_t rel)
 { return s->bit_pool + (s->bit_base[nb] + rel) * (size_t)BMB200_BLOCK_WORDS; }
 inline const uint16_t* set_gap_ptr(const bmb200_packed_set* s, uint32_t nb, uint32_t rel)
-{ return s->gap_pool + (s->gap_base[nb] + rel) * (size_t)BMB200_GAP_UNIT_WORDS; }
+{ return s->gap_pool + (s->gap_base[nb] + (rel & BMB200_DESC_REL_MASK)) * (size_t)BMB200_GAP_UNIT_WORDS + (rel >> 29); }
 
 /* vector `v`, block columns [nb_from, nb_to) of the packed set -> a real bvector whose block 0 is nb_from */
 void build_bvector(const bmb200_packed_set* s, uint32_t v, uint32_t nb_from, uint32_t nb_to, bvect& bv)

@@ -4,7 +4,8 @@ set -e
 cd "$(dirname "$0")/.."
 mkdir -p scripts/_bin
 build() { name=$1; shift; nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared "$@" -o scripts/_bin/libbmb200_$name.so bitmagic_b200/csrc/capi.cu -lcudart & }
-build anti
-build noanti -DBMB200_VAR_ANTIPHASE=0
+build new
+build unr2 -DBMB200_VAR_UNROLL2=1
+build unr2g32 -DBMB200_VAR_UNROLL2=1 -DBMB200_LANES_PER_BLOCK=32
 wait
 ls -la scripts/_bin/

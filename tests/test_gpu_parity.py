@@ -103,6 +103,33 @@ def test_gap_stream_and_gather_paths_agree(ctx):
     dset.free()
 
 
+def test_gap_lead_pad_format(ctx):
+    """BMB200_DESC_GAP_PAD: GAP blocks stored behind a 2-byte lead pad must give identical results everywhere
+    (aggregate stream + gather paths, rs_index build, rank, select)."""
+    rng = np.random.default_rng(21)
+    vecs = gen.mixed_vectors(rng, 20, 5, p_null=0.05, p_gap=0.7) + gen.edge_vectors(5)
+    plain, padded = bm.PackedSet.pack(vecs), bm.PackedSet.pack(vecs, gap_pad=True)
+    assert (padded.desc >> 31).any() and not (plain.desc >> 31).any()
+    d0, d1 = bm.DeviceSet.upload(ctx, plain), bm.DeviceSet.upload(ctx, padded)
+    n = len(vecs)
+    for op, g0, g1 in [(bm.OP_OR, list(range(n)), None), (bm.OP_AND_SUB, [0, 1], list(range(2, n))), (bm.OP_AND, [3, 4, 5], None),
+                       (bm.OP_XOR, list(range(n)), None), (bm.OP_OR, list(range(n - 1, -1, -1)), None)]:
+        a = gpu_aggregate(ctx, plain, op, g0, g1, C, d0)
+        b = check_vs_oracle(ctx, padded, op, g0, g1, C, d1)
+        assert np.array_equal(a["blocks"], b["blocks"]) and np.array_equal(a["kind"], b["kind"])
+    for v in (0, 7, n - 2):
+        r0, r1 = bm.DeviceRS(ctx, d0, v), bm.DeviceRS(ctx, d1, v)
+        for x, y in zip(r0.export(), r1.export()):
+            assert np.array_equal(x, y)
+        pos = rng.integers(0, 5 * 65536, 2000).astype(np.uint64)
+        assert np.array_equal(r0.rank(pos), r1.rank(pos))
+        rk = rng.integers(0, r0.total() + 2, 2000).astype(np.uint64)
+        (p0, f0), (p1, f1) = r0.select(rk), r1.select(rk)
+        assert np.array_equal(f0, f1) and np.array_equal(p0[f0], p1[f1])
+        r0.free(); r1.free()
+    d0.free(); d1.free()
+
+
 def test_edge_cases(ctx):
     vecs = gen.edge_vectors(4)
     ps = bm.PackedSet.pack(vecs)
