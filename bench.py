@@ -34,6 +34,9 @@ sys.path.insert(0, str(ROOT / "tests"))
 WORKLOADS = {
     "c3": dict(n_vec=1024, n_blocks=16384, op="and_sub", desc="combine_and_sub 1024 x 2^30 bits, Zipf d_k=0.5/k, optimize()d (bit + GAP), AND={1,2} SUB={3..1024}, opt_compress"),
     "c2": dict(n_vec=256, n_blocks=4096, op="or", desc="combine_or 256 x 2^28 bits, iid 5% density, bit-blocks"),
+    # configs[4]: 4096 x 2^32 bits block-range sharded over 8 GPUs = 8192 block columns per GPU; density is not fixed by
+    # BASELINE (as bit-blocks it would be 2 TiB), SURVEY 8d proposes iid p=0.0025 + optimize() => GAP blocks, ~22 GB per GPU
+    "c5": dict(n_vec=4096, n_blocks=8192, op="or", desc="combine_or 4096 vectors, 8192 block columns per GPU (2^32 bits over 8 GPUs), iid 0.25% density, optimize()d (GAP blocks)"),
 }
 
 
@@ -43,6 +46,10 @@ def workload_inputs(name: str, rank: int):
     if name == "c3":
         dens = np.array([0.5 / (k + 1) for k in range(nv)])
         seed = np.arange(1000, 1000 + nv, dtype=np.uint64) + np.uint64(1_000_003 * rank)
+        optimize = True
+    elif name == "c5":
+        dens = np.full(nv, 0.0025)
+        seed = np.arange(5000, 5000 + nv, dtype=np.uint64) + np.uint64(1_000_003 * rank)
         optimize = True
     else:
         dens = np.full(nv, 0.05)
@@ -56,6 +63,8 @@ def workload_groups(name: str):
     nv = WORKLOADS[name]["n_vec"]
     if name == "c3":
         return bm.OP_AND_SUB, np.array([0, 1], np.uint32), np.arange(2, nv, dtype=np.uint32), bm.F_OPT_COMPRESS
+    if name == "c5":
+        return bm.OP_OR, np.arange(nv, dtype=np.uint32), None, bm.F_OPT_COMPRESS
     return bm.OP_OR, np.arange(nv, dtype=np.uint32), None, bm.F_OPT_NONE
 
 

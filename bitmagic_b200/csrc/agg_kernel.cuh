@@ -34,8 +34,14 @@ constexpr int kAggWarps   = kAggThreads / 32;
 constexpr int kAggChunk   = 1024;   // group members classified per pass
 
 // build-time variants (scripts/build_variants.sh explores them; defaults = best measured)
+#ifndef BMB200_CTAS_PER_SM       /* resident CTAs per SM the kernel is shaped for: 2 (64 regs, 4-stage ring) or 3 (40 regs, 3-stage ring) */
+#define BMB200_CTAS_PER_SM 2
+#endif
 #ifndef BMB200_GAP_STAGES
-#define BMB200_GAP_STAGES 4
+#define BMB200_GAP_STAGES (BMB200_CTAS_PER_SM >= 3 ? 3 : 4)
+#endif
+#ifndef BMB200_BIT_UNROLL        /* bit-blocks in flight per thread */
+#define BMB200_BIT_UNROLL (BMB200_CTAS_PER_SM >= 3 ? 4 : 8)
 #endif
 #ifndef BMB200_GAP_CHUNK
 #define BMB200_GAP_CHUNK 16384
@@ -56,7 +62,9 @@ constexpr uint32_t kLanesPerBlock = BMB200_LANES_PER_BLOCK;      // `lane` below
 constexpr uint32_t kGroupsPerWarp = 32u / kLanesPerBlock;
 constexpr int      kGapStages     = BMB200_GAP_STAGES;
 constexpr uint32_t kGapChunkBytes = BMB200_GAP_CHUNK;
-constexpr uint32_t kRingBytes     = kGapStages * kGapChunkBytes;   // 64 KB, power of two
+constexpr uint32_t kRingBytes     = kGapStages * kGapChunkBytes;   // 64 KB (48 KB with 3 stages); offsets wrap by modulo
+constexpr int      kCtasPerSm     = BMB200_CTAS_PER_SM;
+constexpr int      kBitUnroll     = BMB200_BIT_UNROLL;
 constexpr uint32_t kRingWords     = kRingBytes / 4;
 constexpr uint32_t kGapMaxBytes   = 2560;                          // gap_max_buff_len * 2
 constexpr int      kMaxChunks     = (kAggChunk * 4096) / (int)kGapChunkBytes + 4;      // streamed only when span <= n * 4096
@@ -143,15 +151,15 @@ __device__ __forceinline__ void bit_phase(const uint4* __restrict__ seg, const u
 {
     const uint4 ident = (!ROLE1 && (OP == BMB200_OP_AND || OP == BMB200_OP_AND_SUB))
                             ? make_uint4(~0u, ~0u, ~0u, ~0u) : make_uint4(0u, 0u, 0u, 0u);
-    for (uint32_t i = 0; i < n; i += 8) {
-        uint4 v[8];
+    for (uint32_t i = 0; i < n; i += kBitUnroll) {
+        uint4 v[kBitUnroll];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < kBitUnroll; ++u) {
             if (i + u < n) v[u] = ld_stream_v4(seg + (size_t)lst[i + u] * (kBlockWords / 4));
             else           v[u] = ident;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < kBitUnroll; ++u) {
             if (ROLE1) acc_or(acc, v[u]); else acc_apply0<OP>(acc, v[u]);
         }
     }
@@ -250,7 +258,7 @@ __device__ __forceinline__ void gap_scatter_gather(uint32_t Ks, const uint16_t* 
 }
 
 template <int OP>
-__global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
+__global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggParams p)
 {
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     uint32_t* ring = reinterpret_cast<uint32_t*>(dyn_smem);
@@ -278,9 +286,7 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
     asm volatile("mov.u32 %0, %1;" : "=r"(Ks) : "r"(smem_u32(K)));
     asm volatile("mov.u32 %0, %1;" : "=r"(ring_s) : "r"(smem_u32(ring)));
     const bool gap_first = BMB200_VAR_ANTIPHASE && (blockIdx.x >= (gridDim.x + 1u) / 2u);
-    uint32_t fillcnt[kGapStages];                // completed fills per stage so far (phase parity), uniform
-#pragma unroll
-    for (int s = 0; s < kGapStages; ++s) fillcnt[s] = 0;
+    uint32_t gseq = 0;       // chunks streamed so far by this CTA: chunk g lives in stage g % S, its mbarrier phase is (g / S) & 1
 
     if (tid == 0) {
 #pragma unroll
@@ -358,75 +364,72 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
             // ---- GAP lists: decide stream vs gather (uniform), set up the first streamed pass ----
             // pass 0 = group0 list (front), pass 1 = group1 list (back, read reversed so it is in member order)
             const uint32_t want0 = (OP == BMB200_OP_AND || OP == BMB200_OP_AND_SUB) ? 0u : 1u;
-            bool stream_ok[2];
-            uint32_t w_lo[2], w_bytes[2], nch[2];
+            bool ok0 = false, ok1 = false;                      // list q is streamed (else gathered)
+            uint32_t lo0 = 0, lo1 = 0, wb0 = 0, wb1 = 0, nc0 = 0, nc1 = 0;   // window start unit, bytes, chunks
             {
                 int bad0 = 0, bad1 = 0;
                 for (uint32_t i = tid; i + 1 < ngap0; i += kAggThreads) bad0 |= !((lst_gap[i] & kRelMask) < (lst_gap[i + 1] & kRelMask));
                 for (uint32_t i = tid; i + 1 < ngap1; i += kAggThreads)
                     bad1 |= !((lst_gap[kAggChunk - 1 - i] & kRelMask) < (lst_gap[kAggChunk - 2 - i] & kRelMask));
                 // NB: __syncthreads_or returns a predicate, not a bitwise OR -> one vote per list
-                const int anybad = (__syncthreads_or(bad0) ? 1 : 0) | (__syncthreads_or(bad1) ? 2 : 0);
-                for (int q = 0; q < 2; ++q) {
-                    const uint32_t n = q ? ngap1 : ngap0;
-                    stream_ok[q] = false; w_lo[q] = 0; w_bytes[q] = 0; nch[q] = 0;
-                    if (n == 0 || p.gap_mode == 1u || (anybad & (1 << q))) continue;
-                    const uint32_t lo = (q ? lst_gap[kAggChunk - 1] : lst_gap[0]) & kRelMask;
-                    const uint32_t hi = (q ? lst_gap[kAggChunk - n] : lst_gap[n - 1]) & kRelMask;
+                const bool sorted0 = !__syncthreads_or(bad0), sorted1 = !__syncthreads_or(bad1);
+                auto plan = [&](uint32_t n, bool sorted, uint32_t lo, uint32_t hi, bool& ok, uint32_t& wlo, uint32_t& wb, uint32_t& nc) {
+                    if (n == 0 || p.gap_mode == 1u || !sorted) return;
                     const uint64_t span = (uint64_t)(hi - lo) * 16ull + kGapMaxBytes;
-                    if (span > (uint64_t)n * 4096ull) continue;                   // sparse subset: gather instead
-                    uint64_t avail = gseg_avail - (uint64_t)lo * 16ull;
-                    avail &= ~15ull;
-                    const uint64_t wb = span < avail ? span : avail;
-                    stream_ok[q] = true; w_lo[q] = lo; w_bytes[q] = (uint32_t)wb;
-                    nch[q] = (uint32_t)((wb + kGapChunkBytes - 1) / kGapChunkBytes);
-                }
+                    if (span > (uint64_t)n * 4096ull) return;                    // sparse subset: gather instead
+                    const uint64_t avail = (gseg_avail - (uint64_t)lo * 16ull) & ~15ull;
+                    const uint64_t w = span < avail ? span : avail;
+                    ok = true; wlo = lo; wb = (uint32_t)w; nc = (uint32_t)((w + kGapChunkBytes - 1) / kGapChunkBytes);
+                };
+                if (ngap0) plan(ngap0, sorted0, lst_gap[0] & kRelMask, lst_gap[ngap0 - 1] & kRelMask, ok0, lo0, wb0, nc0);
+                if (ngap1) plan(ngap1, sorted1, lst_gap[kAggChunk - 1] & kRelMask, lst_gap[kAggChunk - ngap1] & kRelMask, ok1, lo1, wb1, nc1);
             }
-            auto L = [&](int q, uint32_t i) -> uint32_t { return (q ? lst_gap[kAggChunk - 1 - i] : lst_gap[i]) & kRelMask; };   // 16-byte unit of entry i
-            auto issue_fill = [&](int q, uint32_t c) {     // one thread: arm stage c % S and start the bulk copy
-                const uint32_t s = c % kGapStages;
+            auto issue_fill = [&](uint32_t wlo, uint32_t wbytes, uint32_t c) {   // one thread: arm the stage of chunk c, start the copy
+                const uint32_t s = (gseq + c) % kGapStages;
                 const uint32_t off = c * kGapChunkBytes;
-                const uint32_t bytes = min(kGapChunkBytes, w_bytes[q] - off);
+                const uint32_t bytes = min(kGapChunkBytes, wbytes - off);
                 const uint32_t extra = s ? 0u : min(kGapMaxBytes, bytes);   // stage 0 is mirrored behind the ring
-                const uint8_t* src = reinterpret_cast<const uint8_t*>(gseg) + (size_t)w_lo[q] * 16u + off;
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(gseg) + (size_t)wlo * 16u + off;
                 mbar_arrive_expect_tx(&s_full[s], bytes + extra);
                 bulk_g2s(reinterpret_cast<uint8_t*>(ring) + s * kGapChunkBytes, src, bytes, &s_full[s]);
                 if (extra) bulk_g2s(reinterpret_cast<uint8_t*>(ring) + kRingBytes, src, extra, &s_full[s]);
             };
             auto stream_setup = [&](int q) {               // all threads; ends with a block barrier
-                const uint32_t n = q ? ngap1 : ngap0;
+                const uint32_t n = q ? ngap1 : ngap0, wlo = q ? lo1 : lo0, nc = q ? nc1 : nc0, wbytes = q ? wb1 : wb0;
                 for (uint32_t i = tid; i < n; i += kAggThreads) {
-                    const uint32_t ci = ((L(q, i) - w_lo[q]) * 16u) / kGapChunkBytes;
-                    const int cp = i ? (int)(((L(q, i - 1) - w_lo[q]) * 16u) / kGapChunkBytes) : -1;
+                    const uint32_t ei = (q ? lst_gap[kAggChunk - 1 - i] : lst_gap[i]) & kRelMask;
+                    const uint32_t ci = ((ei - wlo) * 16u) / kGapChunkBytes;
+                    int cp = -1;
+                    if (i) { const uint32_t ep = (q ? lst_gap[kAggChunk - i] : lst_gap[i - 1]) & kRelMask; cp = (int)(((ep - wlo) * 16u) / kGapChunkBytes); }
                     for (int c = cp + 1; c <= (int)ci; ++c) s_cfirst[c] = i;
-                    if (i == n - 1) for (uint32_t c = ci + 1; c <= nch[q]; ++c) s_cfirst[c] = n;
+                    if (i == n - 1) for (uint32_t c = ci + 1; c <= nc; ++c) s_cfirst[c] = n;
                 }
                 if (tid < kGapStages) s_done[tid] = 0u;
                 __syncthreads();
                 if (tid == 0) {
                     fence_proxy_async();
-                    const uint32_t pre = min((uint32_t)kGapStages, nch[q]);
-                    for (uint32_t c = 0; c < pre; ++c) issue_fill(q, c);
+                    const uint32_t pre = min((uint32_t)kGapStages, nc);
+                    for (uint32_t c = 0; c < pre; ++c) issue_fill(wlo, wbytes, c);
                 }
             };
             auto stream_consume = [&](int q, uint32_t want) {   // per warp, no block barriers inside
-                const uint32_t wlo = w_lo[q], nc = nch[q];
-                mbar_wait(&s_full[0], fillcnt[0] & 1u);
+                const uint32_t wlo = q ? lo1 : lo0, nc = q ? nc1 : nc0, wbytes = q ? wb1 : wb0;
+                const uint32_t rot = (gseq % kGapStages) * kGapChunkBytes;      // ring offset of the window start
+                mbar_wait(&s_full[gseq % kGapStages], (gseq / kGapStages) & 1u);
                 for (uint32_t r = 0; r < nc; ++r) {
-                    const uint32_t s = r % kGapStages;
+                    const uint32_t s = (gseq + r) % kGapStages;
                     if (r + 1 < nc) {                 // blocks starting in chunk r may spill into chunk r+1
-                        const uint32_t s1 = (r + 1) % kGapStages;
-                        mbar_wait(&s_full[s1], (fillcnt[s1] + (r + 1) / kGapStages) & 1u);
+                        const uint32_t g1 = gseq + r + 1;
+                        mbar_wait(&s_full[g1 % kGapStages], (g1 / kGapStages) & 1u);
                     }
-                    // block i always goes to warp i % 16, so the per-round remainders rotate over the warps
-                    const uint32_t ibeg = s_cfirst[r], iend = s_cfirst[r + 1];
                     {   // block i always goes to slot i % (16 * groups): the per-round remainders rotate over the slots
                         constexpr uint32_t kSlots = kAggWarps * kGroupsPerWarp;
                         const uint32_t slot = (uint32_t)warp * kGroupsPerWarp + ((uint32_t)lane / kLanesPerBlock);
                         const int sub = lane & (int)(kLanesPerBlock - 1u);
+                        const uint32_t ibeg = s_cfirst[r], iend = s_cfirst[r + 1];
                         for (uint32_t i = ibeg + ((slot - ibeg) & (kSlots - 1u)); i < iend; i += kSlots) {
                             const uint32_t ent = q ? lst_gap[kAggChunk - 1 - i] : lst_gap[i];
-                            const uint32_t ba = ring_s + ((((ent & kRelMask) - wlo) * 16u) & (kRingBytes - 1u));
+                            const uint32_t ba = ring_s + (rot + ((ent & kRelMask) - wlo) * 16u) % kRingBytes;
                             gap_scatter_ring<OP == BMB200_OP_XOR>(Ks, ba, ent >> 29, want, sub);
                         }
                     }
@@ -436,13 +439,11 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
                         const uint32_t old = atomicAdd(&s_done[s], 1u);
                         if (old == kAggWarps - 1) {          // last warp out re-arms the stage
                             atomicExch(&s_done[s], 0u);
-                            if (r + kGapStages < nc) { __threadfence_block(); fence_proxy_async(); issue_fill(q, r + kGapStages); }
+                            if (r + kGapStages < nc) { __threadfence_block(); fence_proxy_async(); issue_fill(wlo, wbytes, r + kGapStages); }
                         }
                     }
                 }
-#pragma unroll
-                for (int s = 0; s < kGapStages; ++s)
-                    fillcnt[s] += (nc > (uint32_t)s) ? (nc - 1u - s) / kGapStages + 1u : 0u;
+                gseq += nc;
             };
             auto gather_pass = [&](int q, uint32_t want) {       // per warp; dynamic block distribution
                 const uint32_t n = q ? ngap1 : ngap0;
@@ -457,7 +458,7 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
             };
 
             // the first streamed list starts landing in the ring while the bit-blocks stream through registers
-            const int first_q = stream_ok[0] ? 0 : (stream_ok[1] ? 1 : -1);
+            const int first_q = ok0 ? 0 : (ok1 ? 1 : -1);
             if (first_q >= 0) stream_setup(first_q);
 
             // The two phases touch disjoint state (registers vs K), so their order is free.  CTAs of the second
@@ -469,14 +470,14 @@ __global__ void __launch_bounds__(kAggThreads, 2) agg_kernel(const AggParams p)
             }
             // ---- GAP phase ----
             if (first_q >= 0) stream_consume(first_q, first_q ? 1u : want0);
-            if (first_q == 0 && stream_ok[1]) {
+            if (first_q == 0 && ok1) {
                 __syncthreads();                     // ring and s_cfirst are reused by the second list
                 stream_setup(1);
                 stream_consume(1, 1u);
             }
-            if (ngap0 && !stream_ok[0]) gather_pass(0, want0);
-            if (ngap1 && !stream_ok[1]) {
-                if (ngap0 && !stream_ok[0]) { __syncthreads(); if (tid == 0) s_gap_next = 0u; __syncthreads(); }
+            if (ngap0 && !ok0) gather_pass(0, want0);
+            if (ngap1 && !ok1) {
+                if (ngap0 && !ok0) { __syncthreads(); if (tid == 0) s_gap_next = 0u; __syncthreads(); }
                 gather_pass(1, 1u);
             }
             // ---- bit phase: registers <- streamed bit-blocks ----

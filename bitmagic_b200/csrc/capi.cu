@@ -26,7 +26,10 @@ struct bmb200_ctx {
     size_t group_cap = 0;
     uint32_t* h_group = nullptr;            // pinned staging for the group ids
     std::vector<uint32_t> last_group;       // ids currently resident in d_group (skip the re-upload when unchanged)
-    int agg_ctas_per_sm = 2;
+    int agg_ctas_per_sm = kCtasPerSm;
+    bmb200_set* host_set = nullptr;         // device arena kept between bmb200_aggregate_host calls (cudaMalloc/cudaFree
+    bmb200_result* host_res = nullptr;      //   of a multi-GB arena costs ~100 ms per call otherwise)
+    size_t cap_desc = 0, cap_base = 0, cap_bit = 0, cap_gap = 0;
     int gap_mode = 0;                       // 0 = stream sorted GAP lists through the smem ring, 1 = always gather
     bool attr_set = false;
 };
@@ -163,6 +166,8 @@ int bmb200_destroy(bmb200_ctx* ctx)
     if (!ctx) return BMB200_ERR_BADARG;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->host_res) bmb200_result_free(ctx->host_res);
+    if (ctx->host_set) bmb200_set_free(ctx->host_set);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     cudaFree(ctx->d_work); cudaFree(ctx->d_group);
     if (ctx->h_group) cudaFreeHost(ctx->h_group);
@@ -223,7 +228,7 @@ int bmb200_ctx_set_tuning(bmb200_ctx* ctx, int key, int value)
 {
     if (!ctx) return BMB200_ERR_BADARG;
     if (key == BMB200_TUNE_GAP_MODE && (value == 0 || value == 1)) { ctx->gap_mode = value; return BMB200_OK; }
-    if (key == BMB200_TUNE_CTAS_PER_SM && value >= 1 && value <= 2) { ctx->agg_ctas_per_sm = value; return BMB200_OK; }
+    if (key == BMB200_TUNE_CTAS_PER_SM && value >= 1 && value <= kCtasPerSm) { ctx->agg_ctas_per_sm = value; return BMB200_OK; }
     return BMB200_ERR_BADARG;
 }
 
@@ -716,18 +721,41 @@ int bmb200_result_free(bmb200_result* r)
     return BMB200_OK;
 }
 
+// H2D of one packed set into an existing device arena (capacities checked by the caller)
+static int set_copy_in(bmb200_ctx* ctx, bmb200_set* s, const bmb200_packed_set* h, uint64_t n_bit, uint64_t n_gap)
+{
+    cudaStream_t st = ctx->stream;
+    s->v.n_vec = h->n_vec; s->v.n_blocks = h->n_blocks; s->n_bit_blocks = n_bit; s->n_gap_units = n_gap;
+    s->gap_pool_bytes = n_gap * 16ull + kSlack;
+    CU(cudaMemcpyAsync((void*)s->v.desc, h->desc, (size_t)h->n_vec * h->n_blocks * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync((void*)s->v.bit_base, h->bit_base, ((size_t)h->n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync((void*)s->v.gap_base, h->gap_base, ((size_t)h->n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n_bit) CU(cudaMemcpyAsync((void*)s->v.bit_pool, h->bit_pool, (size_t)n_bit * BMB200_BLOCK_BYTES, cudaMemcpyHostToDevice, st));
+    if (n_gap) CU(cudaMemcpyAsync((void*)s->v.gap_pool, h->gap_pool, (size_t)n_gap * kGapUnit * 2, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync((char*)s->v.gap_pool + (size_t)n_gap * kGapUnit * 2, 0, kSlack, st));
+    return BMB200_OK;
+}
+
 int bmb200_aggregate_host(bmb200_ctx* ctx, const bmb200_packed_set* host, const bmb200_agg_args* args,
                           const bmb200_result_meta* meta_out, uint64_t* total_out)
 {
-    if (!ctx || !host || !args) return BMB200_ERR_BADARG;
-    bmb200_set* s = nullptr; bmb200_result* r = nullptr;
-    int rc = bmb200_set_upload(ctx, host, &s);
-    if (rc) return rc;
-    rc = bmb200_aggregate(ctx, s, args, &r);
-    if (!rc && meta_out) rc = bmb200_result_fetch_meta(r, meta_out);
-    if (!rc && total_out) rc = bmb200_result_total(r, total_out, nullptr);
-    if (r) bmb200_result_free(r);
-    bmb200_set_free(s);
+    if (!ctx || !host || !args || !host->n_vec || !host->n_blocks || !host->desc || !host->bit_base || !host->gap_base)
+        return BMB200_ERR_BADARG;
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t n_bit = host->bit_base[host->n_blocks], n_gap = host->gap_base[host->n_blocks];
+    if ((n_bit && !host->bit_pool) || (n_gap && !host->gap_pool)) return BMB200_ERR_BADARG;
+    const size_t need_desc = (size_t)host->n_vec * host->n_blocks, need_base = (size_t)host->n_blocks + 1;
+    // the device arena and the result buffers persist in the context: every call still copies ALL inputs H2D
+    if (!ctx->host_set || need_desc > ctx->cap_desc || need_base > ctx->cap_base || n_bit > ctx->cap_bit || n_gap > ctx->cap_gap) {
+        if (ctx->host_set) { bmb200_set_free(ctx->host_set); ctx->host_set = nullptr; }
+        int rc = set_alloc(ctx, host->n_vec, host->n_blocks, n_bit, n_gap, &ctx->host_set);
+        if (rc) return rc;
+        ctx->cap_desc = need_desc; ctx->cap_base = need_base; ctx->cap_bit = n_bit; ctx->cap_gap = n_gap;
+    }
+    int rc = set_copy_in(ctx, ctx->host_set, host, n_bit, n_gap);
+    if (!rc) rc = bmb200_aggregate(ctx, ctx->host_set, args, &ctx->host_res);
+    if (!rc && meta_out) rc = bmb200_result_fetch_meta(ctx->host_res, meta_out);
+    if (!rc && total_out) rc = bmb200_result_total(ctx->host_res, total_out, nullptr);
     return rc;
 }
 
