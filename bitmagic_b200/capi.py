@@ -34,7 +34,7 @@ SYMBOLS = [
     "bmb200_result_fetch_meta", "bmb200_result_sizes", "bmb200_result_fetch", "bmb200_result_device_ptrs",
     "bmb200_result_free", "bmb200_aggregate_host", "bmb200_rs_build", "bmb200_rs_export", "bmb200_rs_total",
     "bmb200_rank_batch", "bmb200_select_batch", "bmb200_rank_batch_dev", "bmb200_select_batch_dev",
-    "bmb200_rs_free",
+    "bmb200_rs_free", "bmb200_rs_rebuild",
 ]
 
 
@@ -345,6 +345,9 @@ class DeviceRS:
         self.ctx, self.dset, self.vec = ctx, dset, vec
         self._h = C.c_void_p(0)
         ctx.check(lib().bmb200_rs_build(ctx._h, dset._h, int(vec), C.byref(self._h)), "rs_build")
+
+    def rebuild(self):
+        self.ctx.check(lib().bmb200_rs_rebuild(self._h), "rs_rebuild")
 
     def export(self):
         nb = self.dset.n_blocks

@@ -782,16 +782,26 @@ int bmb200_rs_build(bmb200_ctx* ctx, const bmb200_set* set, uint32_t vec, bmb200
     if ((rc = dev_alloc(ctx, &rs->bcount, rs->n_blocks)) || (rc = dev_alloc(ctx, &rs->sub_count, rs->n_blocks)) ||
         (rc = dev_alloc(ctx, &rs->row_cum, rs->n_blocks)) || (rc = dev_alloc(ctx, &rs->sb_tot, rs->nsb)) ||
         (rc = dev_alloc(ctx, &rs->sb_cum, (size_t)rs->nsb + 1))) { bmb200_rs_free(rs); return rc; }
-    uint32_t grid = (rs->n_blocks + 7u) / 8u;
-    const uint32_t maxg = (uint32_t)ctx->sm_count * 16u; if (grid > maxg) grid = maxg;
-    rs_block_kernel<<<grid, 256, 0, ctx->stream>>>(set->v, vec, rs->bcount, rs->sub_count);
-    if ((rc = after_launch(ctx))) { bmb200_rs_free(rs); return rc; }
-    rs_scan_rows_kernel<<<rs->nsb, 256, 0, ctx->stream>>>(rs->bcount, rs->n_blocks, rs->row_cum, rs->sb_tot);
-    if ((rc = after_launch(ctx))) { bmb200_rs_free(rs); return rc; }
-    rs_scan_sb_kernel<<<1, 1024, 0, ctx->stream>>>(rs->sb_tot, rs->nsb, rs->sb_cum);
-    if ((rc = after_launch(ctx))) { bmb200_rs_free(rs); return rc; }
+    rc = bmb200_rs_rebuild(rs);
+    if (rc) { bmb200_rs_free(rs); return rc; }
     *out = rs;
     return BMB200_OK;
+}
+
+int bmb200_rs_rebuild(bmb200_rs* rs)
+{
+    if (!rs) return BMB200_ERR_RS_IDX_MISSING;
+    bmb200_ctx* ctx = rs->ctx;
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    uint32_t grid = (rs->n_blocks + 7u) / 8u;
+    const uint32_t maxg = (uint32_t)ctx->sm_count * 16u; if (grid > maxg) grid = maxg;
+    rs_block_kernel<<<grid, 256, 0, ctx->stream>>>(rs->set->v, rs->vec, rs->bcount, rs->sub_count);
+    if ((rc = after_launch(ctx))) return rc;
+    rs_scan_rows_kernel<<<rs->nsb, 256, 0, ctx->stream>>>(rs->bcount, rs->n_blocks, rs->row_cum, rs->sb_tot);
+    if ((rc = after_launch(ctx))) return rc;
+    rs_scan_sb_kernel<<<1, 1024, 0, ctx->stream>>>(rs->sb_tot, rs->nsb, rs->sb_cum);
+    return after_launch(ctx);
 }
 
 int bmb200_rs_export(bmb200_rs* rs, uint32_t* bcount, uint64_t* sub_count, uint64_t* sb_count)

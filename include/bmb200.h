@@ -209,6 +209,8 @@ int bmb200_aggregate_host(bmb200_ctx* ctx, const bmb200_packed_set* host,
 /* ---------------- rank / select ---------------- */
 /* build the rs_index of vector `vec` of `set`; the set must outlive the index */
 int bmb200_rs_build(bmb200_ctx* ctx, const bmb200_set* set, uint32_t vec, bmb200_rs** out);
+/* recompute the index in place (same set, same vector) -- e.g. after the arena was refilled; no allocation */
+int bmb200_rs_rebuild(bmb200_rs* rs);
 /* index fields exactly as rs_index::register_super_block receives them (src/bmrs.h:688):
  * bcount[n_blocks] u32, sub_count[n_blocks] u64 (first | second<<16 | aux0<<32 | aux1<<48),
  * sb_count[n_superblocks+1] u64 running totals (sblock_count_) */
