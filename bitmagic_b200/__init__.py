@@ -4,11 +4,11 @@ Product code: csrc/ (CUDA kernels + the C ABI of include/bmb200.h, built into li
 host-side mirror of the reference operator surface (aggregator.py, hostfmt.py, capi.py).
 There is no CPU fallback: importing works anywhere, computing needs libbmb200.so and a B200.
 """
-from .capi import (BLK_BIT, BLK_FULL, BLK_GAP, BLK_NULL, F_COUNT_ONLY, F_OPT_COMPRESS, F_OPT_NONE, OP_AND,
+from .capi import (BLK_BIT, BLK_FULL, BLK_GAP, BLK_NULL, F_COUNT_ONLY, F_OPT_COMPRESS, F_OPT_NONE, F_OR_TARGET, OP_AND,
                    OP_AND_SUB, OP_OR, OP_XOR, BMB200Error, Context, DeviceResult, DeviceRS, DeviceSet,
-                   aggregate, aggregate_host, default_context)
+                   aggregate, aggregate_batch, aggregate_host, default_context)
 from .hostfmt import BVector, PackedSet, result_to_bvector
-from .aggregator import (OPT_COMPRESS, OPT_NONE, Aggregator, RSIndex, bit_and, bit_or, bit_sub, bit_xor,
+from .aggregator import (OPT_COMPRESS, OPT_NONE, Aggregator, Pipeline, RSIndex, bit_and, bit_or, bit_sub, bit_xor,
                          build_rs_index, count_and, count_or, count_sub, count_xor)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

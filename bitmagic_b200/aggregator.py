@@ -16,7 +16,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import capi
-from .capi import (BLK_NULL, F_COUNT_ONLY, F_OPT_COMPRESS, F_OPT_NONE, OP_AND, OP_AND_SUB, OP_OR, OP_XOR)
+from .capi import (BLK_NULL, F_COUNT_ONLY, F_OPT_COMPRESS, F_OPT_NONE, F_OR_TARGET, OP_AND, OP_AND_SUB, OP_OR, OP_XOR)
 from .hostfmt import BVector, PackedSet, result_to_bvector
 
 OPT_NONE = 0       # bvector::opt_none
@@ -83,8 +83,10 @@ class Aggregator:
         res, _, _ = _run(self.ctx, bv_src, OP_AND, np.arange(len(bv_src)), None, self._opt)
         return res
 
-    def combine_and_sub(self, bv_src_and: list[BVector] | None = None, bv_src_sub: list[BVector] | None = None,
-                        any_: bool = False) -> tuple[BVector, bool]:
+    def combine_and_sub(self, bv_src_and: "list[BVector] | Pipeline | None" = None, bv_src_sub: list[BVector] | None = None,
+                        any_: bool = False):
+        if isinstance(bv_src_and, Pipeline):               # template<class TPipe> void combine_and_sub(TPipe&), :1291-1453
+            return _run_pipeline(self.ctx, bv_src_and)
         a = self._groups[0] if bv_src_and is None else bv_src_and
         s = self._groups[1] if bv_src_sub is None else bv_src_sub
         if not a:
@@ -103,6 +105,108 @@ class Aggregator:
         _, total, _ = _run(self.ctx, vecs, OP_AND_SUB, np.arange(len(bv_src_and)),
                            np.arange(len(bv_src_and), len(vecs)), OPT_NONE, count_only=True)
         return total
+
+
+class Pipeline:
+    """``bm::aggregator<BV>::pipeline<Opt>`` (reference src/bmaggregator.h:222-341): many (AND set, SUB set) argument groups
+    over a shared family of vectors, executed by ``Aggregator.combine_and_sub(pipeline)`` -- here ONE batched launch.
+
+    ``make_results`` / ``compute_counts`` mirror ``agg_run_options`` (agg_opt_only_counts, agg_opt_bvect_and_counts ...).
+    """
+
+    class ArgGroups:
+        def __init__(self):
+            self.arg_bv0: list[BVector] = []
+            self.arg_bv1: list[BVector] = []
+
+        def add(self, bv: BVector, agr_group: int = 0) -> int:
+            if agr_group not in (0, 1):
+                raise ValueError("agr_group must be 0 or 1")
+            lst = self.arg_bv1 if agr_group else self.arg_bv0
+            lst.append(bv)
+            return len(lst)
+
+    def __init__(self, make_results: bool = True, compute_counts: bool = False):
+        self.make_results, self.compute_counts = make_results, compute_counts
+        self._groups: list[Pipeline.ArgGroups] = []
+        self._complete = False
+        self._or_target = False
+        self._unique: list[BVector] = []
+        self.bv_res_vector: list[BVector | None] = []
+        self.bv_count_vector: list[int] = []
+        self.or_target: BVector | None = None
+
+    def add(self) -> "Pipeline.ArgGroups":
+        if self._complete:
+            raise RuntimeError("pipeline is complete: cannot add()")
+        self._groups.append(Pipeline.ArgGroups())
+        return self._groups[-1]
+
+    def set_or_target(self, enable: bool = True):
+        self._or_target = enable
+
+    def complete(self):
+        """Collect the unique input vectors (the reference's pipeline_bcache, src/bmaggregator.h:187-203)."""
+        seen: dict[int, int] = {}
+        self._unique = []
+        for g in self._groups:
+            for bv in g.arg_bv0 + g.arg_bv1:
+                if id(bv) not in seen:
+                    seen[id(bv)] = len(self._unique)
+                    self._unique.append(bv)
+        self._index = seen
+        self._complete = True
+
+    def is_complete(self) -> bool:
+        return self._complete
+
+    def size(self) -> int:
+        return len(self._groups)
+
+    def unique_vectors(self) -> int:
+        return len(self._unique)
+
+    def get_bv_res_vector(self):
+        return self.bv_res_vector
+
+    def get_bv_count_vector(self):
+        return self.bv_count_vector
+
+
+def _run_pipeline(ctx, pipe: Pipeline):
+    if not pipe.is_complete():
+        raise RuntimeError("pipeline.complete() must be called before execution")
+    ng = pipe.size()
+    pipe.bv_res_vector = [None] * ng
+    pipe.bv_count_vector = [0] * ng
+    pipe.or_target = None
+    if not ng or not pipe._unique:
+        return
+    n_blocks = max(v.n_blocks for v in pipe._unique)
+    dset = capi.DeviceSet.upload_vectors(ctx, pipe._unique, n_blocks)
+    try:
+        groups = [([pipe._index[id(b)] for b in g.arg_bv0], [pipe._index[id(b)] for b in g.arg_bv1]) for g in pipe._groups]
+        flags = F_OPT_COMPRESS | (0 if pipe.make_results else F_COUNT_ONLY) | (F_OR_TARGET if pipe._or_target else 0)
+        res = capi.aggregate_batch(ctx, dset, OP_AND_SUB, groups, flags)
+        try:
+            totals = res.group_totals(ng)
+            pipe.bv_count_vector = [int(t) for t in totals]
+            if pipe.make_results:
+                kind, off, bits, gaps = res.fetch()
+                for g in range(ng):
+                    if totals[g]:                      # empty results stay NULL pointers in the reference
+                        sl = slice(g * n_blocks, (g + 1) * n_blocks)
+                        pipe.bv_res_vector[g] = result_to_bvector(kind[sl], off[sl], bits, gaps)
+            if pipe._or_target:
+                o = res.or_target(n_blocks)
+                try:
+                    pipe.or_target = result_to_bvector(*o.fetch())
+                finally:
+                    o.free()
+        finally:
+            res.free()
+    finally:
+        dset.free()
 
 
 def _binop(op, a: BVector, b: BVector, opt_mode: int, ctx=None):

@@ -22,7 +22,7 @@ BLOCK_WORDS, BLOCK_BYTES, BLOCK_BITS = 2048, 8192, 65536
 GAP_MAX_WORDS, GAP_THRESHOLD, GAP_UNIT_WORDS, SUPERBLOCK = 1280, 1276, 8, 256
 BLK_NULL, BLK_FULL, BLK_BIT, BLK_GAP = 0, 1, 2, 3
 OP_OR, OP_AND, OP_AND_SUB, OP_XOR = 0, 1, 2, 3
-F_COUNT_ONLY, F_OPT_NONE, F_OPT_COMPRESS = 1, 0, 2
+F_COUNT_ONLY, F_OPT_NONE, F_OPT_COMPRESS, F_OR_TARGET = 1, 0, 2, 4
 
 # every symbol include/bmb200.h declares (checked by tests/test_cabi_symbols.py)
 SYMBOLS = [
@@ -34,7 +34,7 @@ SYMBOLS = [
     "bmb200_result_fetch_meta", "bmb200_result_sizes", "bmb200_result_fetch", "bmb200_result_device_ptrs",
     "bmb200_result_free", "bmb200_aggregate_host", "bmb200_rs_build", "bmb200_rs_export", "bmb200_rs_total",
     "bmb200_rank_batch", "bmb200_select_batch", "bmb200_rank_batch_dev", "bmb200_select_batch_dev",
-    "bmb200_rs_free", "bmb200_rs_rebuild",
+    "bmb200_rs_free", "bmb200_rs_rebuild", "bmb200_aggregate_batch", "bmb200_result_group_totals", "bmb200_result_or_target",
 ]
 
 
@@ -55,6 +55,14 @@ class AggArgsC(C.Structure):
         ("op", C.c_int32), ("flags", C.c_uint32),
         ("group0", C.c_void_p), ("n0", C.c_uint32),
         ("group1", C.c_void_p), ("n1", C.c_uint32),
+        ("nb_from", C.c_uint32), ("nb_to", C.c_uint32),
+    ]
+
+
+class BatchArgsC(C.Structure):
+    _fields_ = [
+        ("op", C.c_int32), ("flags", C.c_uint32), ("n_groups", C.c_uint32),
+        ("members", C.c_void_p), ("offsets", C.c_void_p),
         ("nb_from", C.c_uint32), ("nb_to", C.c_uint32),
     ]
 
@@ -293,6 +301,17 @@ class DeviceResult:
                                                  ptr(gaps) if ng.value else C.c_void_p(0)), "result_fetch")
         return kind, off, bits, gaps
 
+    def group_totals(self, n_groups: int) -> np.ndarray:
+        t = np.zeros(n_groups, np.uint64)
+        self.ctx.check(lib().bmb200_result_group_totals(self._h, ptr(t), int(n_groups)), "result_group_totals")
+        return t
+
+    def or_target(self, n_cols: int) -> "DeviceResult":
+        o = DeviceResult(self.ctx)
+        self.ctx.check(lib().bmb200_result_or_target(self._h, C.byref(o._h)), "result_or_target")
+        o.n_cols = n_cols
+        return o
+
     def device_ptrs(self) -> dict:
         b, p, d, f, n = C.c_void_p(0), C.c_void_p(0), C.c_void_p(0), C.c_void_p(0), C.c_uint32(0)
         self.ctx.check(lib().bmb200_result_device_ptrs(self._h, C.byref(b), C.byref(p), C.byref(d), C.byref(f), C.byref(n)), "result_device_ptrs")
@@ -320,6 +339,21 @@ def aggregate(ctx: Context, dset: DeviceSet, op: int, group0, group1=None, flags
     res = result if result is not None else DeviceResult(ctx)
     ctx.check(lib().bmb200_aggregate(ctx._h, dset._h, C.byref(args), C.byref(res._h)), "aggregate")
     res.n_cols = (nb_to if nb_to else dset.n_blocks) - nb_from
+    return res
+
+
+def aggregate_batch(ctx: Context, dset: DeviceSet, op: int, groups, flags: int = 0, nb_from: int = 0, nb_to: int = 0,
+                    result: DeviceResult | None = None) -> DeviceResult:
+    """bmb200_aggregate_batch: `groups` = [(group0, group1), ...]; the result has len(groups) * n_cols columns, group-major."""
+    mem, off = [], [0]
+    for g0, g1 in groups:
+        mem.extend(int(x) for x in g0); off.append(len(mem))
+        mem.extend(int(x) for x in (g1 if g1 is not None else [])); off.append(len(mem))
+    members = np.ascontiguousarray(mem, dtype=np.uint32); offsets = np.ascontiguousarray(off, dtype=np.uint32)
+    args = BatchArgsC(int(op), int(flags), len(groups), ptr(members) if members.size else C.c_void_p(0), ptr(offsets), int(nb_from), int(nb_to))
+    res = result if result is not None else DeviceResult(ctx)
+    ctx.check(lib().bmb200_aggregate_batch(ctx._h, dset._h, C.byref(args), C.byref(res._h)), "aggregate_batch")
+    res.n_cols = ((nb_to if nb_to else dset.n_blocks) - nb_from) * len(groups)
     return res
 
 

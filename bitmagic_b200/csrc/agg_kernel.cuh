@@ -73,8 +73,9 @@ constexpr size_t   kAggDynSmem    = kRingBytes + kRingTail;       // blocks neve
 
 struct AggParams {
     SetView   set;
-    const uint32_t* group;     // device: n0 + n1 member vector ids (group0 then group1)
-    uint32_t  n0, n1;
+    const uint32_t* group;     // device: member vector ids of all argument groups, concatenated
+    const uint32_t* goff;      // device [2*n_groups+1]: group g = members [goff[2g], goff[2g+1]) (group0) + [goff[2g+1], goff[2g+2]) (group1)
+    uint32_t  n_groups;        // 1 for a plain aggregate, > 1 for a pipeline batch
     uint32_t  nb_from, n_cols;
     uint32_t  compress;        // classify like opt_copy_bit_block(opt_compress)
     uint32_t  store_blocks;    // 0 = counts only
@@ -86,7 +87,8 @@ struct AggParams {
     uint32_t* nruns;           // [n_cols]
     uint8_t*  kind;            // [n_cols]
     uint16_t* gaps;            // [n_cols][1280] GAP form of the columns classified GAP (compress mode), else null
-    unsigned long long* total; // sum of popcounts
+    unsigned long long* total; // [n_groups] sum of popcounts per argument group
+    uint32_t* or_blocks;       // [n_cols][2048] OR of every group's result (pipeline set_or_target), or null
     uint32_t* work_counter;    // zeroed before launch
 };
 
@@ -257,6 +259,91 @@ __device__ __forceinline__ void gap_scatter_gather(uint32_t Ks, const uint16_t* 
     }
 }
 
+// Epilogue shared by agg_kernel and finalize_blocks_kernel: R = this thread's 4 words of the result block.
+// state: 0 = nothing stored, 1 = FULL, 2 = computed block.  Fuses bit_block_count, calc_block_digest0,
+// bit_block_calc_change, the opt_copy_bit_block classification and its bit_to_gap branch
+// (src/bmfunc.h:5808,1239,6040,5540; src/bmblocks.h:1355-1409).
+template <bool EMPTY_DIGEST_IS_NULL>
+__device__ __forceinline__ void finish_block(const AggParams& p, uint32_t col, uint32_t colx, uint32_t grp, uint4 R, int state,
+                                             uint32_t* K, uint32_t* s_pc, uint32_t* s_tr, uint32_t* s_dg)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint4* K4 = reinterpret_cast<uint4*>(K);
+    // popcount, digest (4 waves per warp: 8 threads x 4 words = one 32-word wave), run ends
+    K4[tid] = R;                 // reuse K so each thread can see its right neighbour's first word
+    const uint32_t nz = (R.x | R.y | R.z | R.w) != 0u;
+    const uint32_t bal = __ballot_sync(0xffffffffu, nz);
+    uint32_t dg4 = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if ((bal >> (8 * q)) & 0xffu) dg4 |= (1u << q);
+    uint32_t pc = warp_sum(popc4(R));
+    __syncthreads();
+    // x has a bit at every position p whose successor differs (bit_block_calc_change src/bmfunc.h:6040 counts
+    // them; bit_block_to_gap src/bmfunc.h:5540 emits them as run ends); bit 65535 has no successor
+    const uint32_t nxt = (tid + 1 < kAggThreads) ? (K[4 * tid + 4] & 1u) : (R.w >> 31);
+    const uint32_t x0 = R.x ^ ((R.x >> 1) | (R.y << 31)), x1 = R.y ^ ((R.y >> 1) | (R.z << 31));
+    const uint32_t x2 = R.z ^ ((R.z >> 1) | (R.w << 31)), x3 = R.w ^ ((R.w >> 1) | (nxt << 31));
+    const uint32_t cnt = __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3);
+    uint32_t inc = cnt;          // inclusive warp scan of the run-end counts
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) s_tr[warp] = inc;
+    if (lane == 0) { s_pc[warp] = pc; s_dg[warp] = dg4; }
+    __syncthreads();
+    uint32_t tpc = 0, ttr = 0, woff = 0; uint64_t dg = 0;
+#pragma unroll
+    for (int w = 0; w < kAggWarps; ++w) {
+        const uint32_t t = s_tr[w];
+        tpc += s_pc[w]; ttr += t; if (w < warp) woff += t;
+        dg |= (uint64_t)s_dg[w] << (4 * w);
+    }
+    const uint32_t runs = ttr + 1u;
+
+    // result kind: aggregator stores nothing when the AND/SUB/XOR digest is empty; otherwise
+    // copy_bit_block (opt_none) or the opt_copy_bit_block classification (src/bmblocks.h:1355-1409)
+    uint32_t kd;
+    if (state == 0) kd = BMB200_BLK_NULL;
+    else if (state == 1) kd = BMB200_BLK_FULL;
+    else if (EMPTY_DIGEST_IS_NULL && dg == 0) kd = BMB200_BLK_NULL;
+    else if (!p.compress) kd = BMB200_BLK_BIT;
+    else if (runs == 1u) kd = tpc ? BMB200_BLK_FULL : BMB200_BLK_NULL;
+    else if (runs < BMB200_GAP_THRESHOLD) kd = BMB200_BLK_GAP;
+    else kd = BMB200_BLK_BIT;
+
+    if (p.or_blocks && kd != BMB200_BLK_NULL) {      // pipeline OR target: union of all group results of this column
+        uint32_t* ob = p.or_blocks + (size_t)colx * kBlockWords + 4u * tid;
+        if (R.x) atomicOr(ob + 0, R.x);
+        if (R.y) atomicOr(ob + 1, R.y);
+        if (R.z) atomicOr(ob + 2, R.z);
+        if (R.w) atomicOr(ob + 3, R.w);
+    }
+    if (p.store_blocks && kd == BMB200_BLK_BIT)
+        st_stream_v4(reinterpret_cast<uint4*>(p.blocks) + (size_t)col * (kBlockWords / 4) + tid, R);
+    if (p.store_blocks && kd == BMB200_BLK_GAP) {
+        // bit -> GAP fused here (the bit_to_gap branch of opt_copy_bit_block): run ends in order, header last
+        uint16_t* gout = p.gaps + (size_t)col * kGapMax;
+        uint32_t off = 1u + woff + inc - cnt;
+        const uint32_t base = 128u * tid;
+        uint32_t m;
+        m = x0; while (m) { const uint32_t b = __ffs(m) - 1u; m &= m - 1u; gout[off++] = (uint16_t)(base + b); }
+        m = x1; while (m) { const uint32_t b = __ffs(m) - 1u; m &= m - 1u; gout[off++] = (uint16_t)(base + 32u + b); }
+        m = x2; while (m) { const uint32_t b = __ffs(m) - 1u; m &= m - 1u; gout[off++] = (uint16_t)(base + 64u + b); }
+        m = x3; while (m) { const uint32_t b = __ffs(m) - 1u; m &= m - 1u; gout[off++] = (uint16_t)(base + 96u + b); }
+        if (tid == 0) {
+            const uint32_t lvl = runs <= 124u ? 0u : runs <= 252u ? 1u : runs <= 508u ? 2u : 3u;   // gap_calc_level src/bmfunc.h:5418
+            gout[runs] = 65535u;
+            gout[0] = (uint16_t)((R.x & 1u) | (lvl << 1) | (runs << 3));
+        }
+    }
+    if (tid == 0) {
+        p.popcnt[col] = tpc;
+        p.digest[col] = dg;
+        p.nruns[col]  = runs;
+        p.kind[col]   = (uint8_t)kd;
+        if (tpc) atomicAdd(p.total + grp, (unsigned long long)tpc);
+    }
+}
+
 template <int OP>
 __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggParams p)
 {
@@ -278,7 +365,6 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t M = p.set.n_vec;
-    const uint32_t ntot = p.n0 + ((OP == BMB200_OP_AND_SUB) ? p.n1 : 0u);
     uint4* K4 = reinterpret_cast<uint4*>(K);
     // opaque copies: keeps the shared-window base addresses in registers instead of re-deriving them
     // (S2UR SR_CgaCtaId + LEA) inside the scatter loop
@@ -298,9 +384,16 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
     for (;;) {
         if (tid == 0) s_col = atomicAdd(p.work_counter, 1u);
         __syncthreads();
-        const uint32_t col = s_col;
-        if (col >= p.n_cols) break;
-        const uint32_t nb = p.nb_from + col;
+        const uint32_t item = s_col;
+        if (item >= p.n_cols * p.n_groups) break;
+        // groups of one column are adjacent work items: concurrently running CTAs share the column's source blocks in L2
+        const uint32_t colx = item / p.n_groups, grp = item - colx * p.n_groups;
+        const uint32_t col = grp * p.n_cols + colx;          // output slot (group-major)
+        const uint32_t nb = p.nb_from + colx;
+        const uint32_t gb0 = p.goff[2u * grp], gb1 = p.goff[2u * grp + 1u], gb2 = p.goff[2u * grp + 2u];
+        const uint32_t n0 = gb1 - gb0, n1 = (OP == BMB200_OP_AND_SUB) ? gb2 - gb1 : 0u;
+        const uint32_t ntot = n0 + n1;
+        const uint32_t* gmem = p.group + gb0;
 
         K4[tid] = make_uint4(0u, 0u, 0u, 0u);
         if (tid < 4) s_stat[tid] = 0u;
@@ -327,8 +420,8 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                 const uint32_t k = kb + tid;
                 uint32_t kind = 0xffu, rel = 0; bool g1 = false;
                 if (k < ce) {
-                    const uint32_t d = drow[p.group[k]];
-                    kind = d & 3u; rel = d >> 2; g1 = (k >= p.n0);
+                    const uint32_t d = drow[gmem[k]];
+                    kind = d & 3u; rel = d >> 2; g1 = (k >= n0);
                 }
                 const bool c0 = (kind == BMB200_BLK_BIT) && !g1, c1 = (kind == BMB200_BLK_BIT) && g1;
                 const bool c2 = (kind == BMB200_BLK_GAP) && !g1, c3 = (kind == BMB200_BLK_GAP) && g1;
@@ -508,9 +601,9 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
             const uint32_t inv = (tot_full0 & 1u) ? 0xffffffffu : 0u;
             R = make_uint4(acc0.x ^ k4.x ^ inv, acc0.y ^ k4.y ^ inv, acc0.z ^ k4.z ^ inv, acc0.w ^ k4.w ^ inv);
         } else {
-            if ((flags & kFlNull0) || p.n0 == 0) state = 0;
+            if ((flags & kFlNull0) || n0 == 0) state = 0;
             else if (flags & kFlFull1) state = 0;
-            else if (tot_bit0 + tot_gap0 == 0 && (OP == BMB200_OP_AND || p.n1 == 0)) state = 1;
+            else if (tot_bit0 + tot_gap0 == 0 && (OP == BMB200_OP_AND || n1 == 0)) state = 1;
             else state = 2;
             R = make_uint4(acc0.x & ~(acc1.x | k4.x), acc0.y & ~(acc1.y | k4.y),
                            acc0.z & ~(acc1.z | k4.z), acc0.w & ~(acc1.w | k4.w));
@@ -518,72 +611,21 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
         if (state == 0) R = make_uint4(0u, 0u, 0u, 0u);
         if (state == 1) R = make_uint4(~0u, ~0u, ~0u, ~0u);
 
-        // popcount, digest (4 waves per warp: 8 threads x 4 words = one 32-word wave), run ends
-        K4[tid] = R;                 // reuse K so each thread can see its right neighbour's first word
-        const uint32_t nz = (R.x | R.y | R.z | R.w) != 0u;
-        const uint32_t bal = __ballot_sync(0xffffffffu, nz);
-        uint32_t dg4 = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) if ((bal >> (8 * q)) & 0xffu) dg4 |= (1u << q);
-        uint32_t pc = warp_sum(popc4(R));
-        __syncthreads();
-        // x has a bit at every position p whose successor differs (bit_block_calc_change src/bmfunc.h:6040 counts
-        // them; bit_block_to_gap src/bmfunc.h:5540 emits them as run ends); bit 65535 has no successor
-        const uint32_t nxt = (tid + 1 < kAggThreads) ? (K[4 * tid + 4] & 1u) : (R.w >> 31);
-        const uint32_t x0 = R.x ^ ((R.x >> 1) | (R.y << 31)), x1 = R.y ^ ((R.y >> 1) | (R.z << 31));
-        const uint32_t x2 = R.z ^ ((R.z >> 1) | (R.w << 31)), x3 = R.w ^ ((R.w >> 1) | (nxt << 31));
-        const uint32_t cnt = __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3);
-        uint32_t inc = cnt;          // inclusive warp scan of the run-end counts
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
-        if (lane == 31) s_tr[warp] = inc;
-        if (lane == 0) { s_pc[warp] = pc; s_dg[warp] = dg4; }
-        __syncthreads();
-        uint32_t tpc = 0, ttr = 0, woff = 0; uint64_t dg = 0;
-#pragma unroll
-        for (int w = 0; w < kAggWarps; ++w) {
-            const uint32_t t = s_tr[w];
-            tpc += s_pc[w]; ttr += t; if (w < warp) woff += t;
-            dg |= (uint64_t)s_dg[w] << (4 * w);
-        }
-        const uint32_t runs = ttr + 1u;
+        finish_block<OP != BMB200_OP_OR>(p, col, colx, grp, R, state, K, s_pc, s_tr, s_dg);
+    }
+}
 
-        // result kind: aggregator stores nothing when the AND/SUB/XOR digest is empty; otherwise
-        // copy_bit_block (opt_none) or the opt_copy_bit_block classification (src/bmblocks.h:1355-1409)
-        uint32_t kd;
-        if (state == 0) kd = BMB200_BLK_NULL;
-        else if (state == 1) kd = BMB200_BLK_FULL;
-        else if (OP != BMB200_OP_OR && dg == 0) kd = BMB200_BLK_NULL;
-        else if (!p.compress) kd = BMB200_BLK_BIT;
-        else if (runs == 1u) kd = tpc ? BMB200_BLK_FULL : BMB200_BLK_NULL;
-        else if (runs < BMB200_GAP_THRESHOLD) kd = BMB200_BLK_GAP;
-        else kd = BMB200_BLK_BIT;
 
-        if (p.store_blocks && kd == BMB200_BLK_BIT)
-            st_stream_v4(reinterpret_cast<uint4*>(p.blocks) + (size_t)col * (kBlockWords / 4) + tid, R);
-        if (p.store_blocks && kd == BMB200_BLK_GAP) {
-            // bit -> GAP fused here (the bit_to_gap branch of opt_copy_bit_block): run ends in order, header last
-            uint16_t* gout = p.gaps + (size_t)col * kGapMax;
-            uint32_t off = 1u + woff + inc - cnt;
-            const uint32_t base = 128u * tid;
-            uint32_t m;
-            m = x0; while (m) { const uint32_t b = __ffs(m) - 1u; m &= m - 1u; gout[off++] = (uint16_t)(base + b); }
-            m = x1; while (m) { const uint32_t b = __ffs(m) - 1u; m &= m - 1u; gout[off++] = (uint16_t)(base + 32u + b); }
-            m = x2; while (m) { const uint32_t b = __ffs(m) - 1u; m &= m - 1u; gout[off++] = (uint16_t)(base + 64u + b); }
-            m = x3; while (m) { const uint32_t b = __ffs(m) - 1u; m &= m - 1u; gout[off++] = (uint16_t)(base + 96u + b); }
-            if (tid == 0) {
-                const uint32_t lvl = runs <= 124u ? 0u : runs <= 252u ? 1u : runs <= 508u ? 2u : 3u;   // gap_calc_level src/bmfunc.h:5418
-                gout[runs] = 65535u;
-                gout[0] = (uint16_t)((R.x & 1u) | (lvl << 1) | (runs << 3));
-            }
-        }
-        if (tid == 0) {
-            p.popcnt[col] = tpc;
-            p.digest[col] = dg;
-            p.nruns[col]  = runs;
-            p.kind[col]   = (uint8_t)kd;
-            if (tpc) atomicAdd(p.total, (unsigned long long)tpc);
-        }
+// OR target of a pipeline batch: the per-column union was accumulated with global red.or by agg_kernel; this kernel
+// only runs the epilogue (counts, digest, kind, bit->GAP) over those blocks.  One CTA per column, grid-stride.
+__global__ void __launch_bounds__(kAggThreads, kCtasPerSm) finalize_blocks_kernel(const AggParams p, const uint32_t* __restrict__ src)
+{
+    __shared__ __align__(16) uint32_t K[kBlockWords];
+    __shared__ uint32_t s_pc[kAggWarps], s_tr[kAggWarps], s_dg[kAggWarps];
+    for (uint32_t col = blockIdx.x; col < p.n_cols; col += gridDim.x) {
+        const uint4 R = reinterpret_cast<const uint4*>(src)[(size_t)col * (kBlockWords / 4) + threadIdx.x];
+        finish_block<true>(p, col, col, 0u, R, 2, K, s_pc, s_tr, s_dg);
+        __syncthreads();
     }
 }
 

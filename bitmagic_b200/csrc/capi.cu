@@ -22,7 +22,7 @@ struct bmb200_ctx {
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     size_t hbm_bytes = 0;
     uint32_t* d_work = nullptr;             // work counter for the persistent kernel
-    uint32_t* d_group = nullptr;            // group member ids
+    uint32_t* d_group = nullptr;            // group member ids, then the 2*n_groups+1 offsets
     size_t group_cap = 0;
     uint32_t* h_group = nullptr;            // pinned staging for the group ids
     std::vector<uint32_t> last_group;       // ids currently resident in d_group (skip the re-upload when unchanged)
@@ -44,7 +44,9 @@ struct bmb200_set {
 
 struct bmb200_result {
     bmb200_ctx* ctx = nullptr;
-    uint32_t n_cols = 0;
+    uint32_t n_cols = 0;                    // total columns = n_groups * cols_per_group
+    uint32_t n_groups = 1, cols_per_group = 0;
+    uint32_t* or_blocks = nullptr;          // [cols_per_group][2048] union of all groups (BMB200_F_OR_TARGET)
     bool has_blocks = false, compress = false, gaps_ready = false;
     uint32_t* blocks = nullptr;
     uint32_t* popcnt = nullptr;
@@ -110,7 +112,7 @@ void free_result_arrays(bmb200_result* r)
 {
     if (!r) return;
     cudaFree(r->blocks); cudaFree(r->popcnt); cudaFree(r->digest); cudaFree(r->nruns);
-    cudaFree(r->kind); cudaFree(r->gaps); cudaFree(r->total);
+    cudaFree(r->kind); cudaFree(r->gaps); cudaFree(r->total); cudaFree(r->or_blocks);
 }
 
 }  // namespace
@@ -504,15 +506,16 @@ int bmb200_synth_set(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks,
 
 /* ------------------------------------------------------------------ aggregation */
 
-static int result_alloc(bmb200_ctx* ctx, uint32_t n_cols, bool blocks, bool gaps, bmb200_result** out)
+static int result_alloc(bmb200_ctx* ctx, uint32_t n_cols, uint32_t n_groups, bool blocks, bool gaps, bool or_target, bmb200_result** out)
 {
     bmb200_result* r = new (std::nothrow) bmb200_result();
     if (!r) return BMB200_ERR_BADALLOC;
-    r->ctx = ctx; r->n_cols = n_cols;
+    r->ctx = ctx; r->n_cols = n_cols; r->n_groups = n_groups; r->cols_per_group = n_cols / n_groups;
     int rc;
     if ((rc = dev_alloc(ctx, &r->popcnt, n_cols)) || (rc = dev_alloc(ctx, &r->digest, n_cols)) ||
         (rc = dev_alloc(ctx, &r->nruns, n_cols)) || (rc = dev_alloc(ctx, &r->kind, n_cols)) ||
-        (rc = dev_alloc(ctx, &r->total, 1)) ||
+        (rc = dev_alloc(ctx, &r->total, n_groups)) ||
+        (or_target && (rc = dev_alloc(ctx, &r->or_blocks, (size_t)(n_cols / n_groups) * kBlockWords))) ||
         (blocks && (rc = dev_alloc(ctx, &r->blocks, (size_t)n_cols * kBlockWords))) ||
         (gaps && (rc = dev_alloc(ctx, &r->gaps, (size_t)n_cols * kGapMax)))) {
         free_result_arrays(r); delete r; return rc;
@@ -522,70 +525,81 @@ static int result_alloc(bmb200_ctx* ctx, uint32_t n_cols, bool blocks, bool gaps
     return BMB200_OK;
 }
 
-int bmb200_aggregate(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_agg_args* a, bmb200_result** inout)
+static void set_agg_attrs(bmb200_ctx* ctx, cudaError_t* e)
 {
-    if (!ctx || !set || !a || !inout || set->ctx != ctx) return BMB200_ERR_BADARG;
+    if (ctx->attr_set) return;
+    *e = cudaFuncSetAttribute(agg_kernel<BMB200_OP_OR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggDynSmem);
+    if (*e == cudaSuccess) *e = cudaFuncSetAttribute(agg_kernel<BMB200_OP_AND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggDynSmem);
+    if (*e == cudaSuccess) *e = cudaFuncSetAttribute(agg_kernel<BMB200_OP_AND_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggDynSmem);
+    if (*e == cudaSuccess) *e = cudaFuncSetAttribute(agg_kernel<BMB200_OP_XOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggDynSmem);
+    if (*e == cudaSuccess) ctx->attr_set = true;
+}
+
+int bmb200_aggregate_batch(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_batch_args* a, bmb200_result** inout)
+{
+    if (!ctx || !set || !a || !inout || set->ctx != ctx || !a->n_groups || !a->offsets) return BMB200_ERR_BADARG;
     if (a->op < BMB200_OP_OR || a->op > BMB200_OP_XOR) return BMB200_ERR_BADARG;
     const uint32_t nb_to = a->nb_to ? a->nb_to : set->v.n_blocks;
     if (a->nb_from >= nb_to || nb_to > set->v.n_blocks) return BMB200_ERR_RANGE;
-    const uint32_t n1 = (a->op == BMB200_OP_AND_SUB) ? a->n1 : 0u;
-    if ((a->n0 && !a->group0) || (n1 && !a->group1)) return BMB200_ERR_BADARG;
-    for (uint32_t k = 0; k < a->n0; ++k) if (a->group0[k] >= set->v.n_vec) return BMB200_ERR_RANGE;
-    for (uint32_t k = 0; k < n1; ++k) if (a->group1[k] >= set->v.n_vec) return BMB200_ERR_RANGE;
+    const uint32_t ng = a->n_groups;
+    const size_t nmem = a->offsets[2 * (size_t)ng];
+    for (uint32_t k = 0; k < 2 * ng; ++k) if (a->offsets[k] > a->offsets[k + 1]) return BMB200_ERR_BADARG;
+    if (nmem && !a->members) return BMB200_ERR_BADARG;
+    for (size_t k = 0; k < nmem; ++k) if (a->members[k] >= set->v.n_vec) return BMB200_ERR_RANGE;
+    const uint64_t tot_cols = (uint64_t)(nb_to - a->nb_from) * ng;
+    if (tot_cols > 0x7fffffffull) return BMB200_ERR_RANGE;
     CU(cudaSetDevice(ctx->device));
-    const uint32_t n_cols = nb_to - a->nb_from;
+    const uint32_t cols = nb_to - a->nb_from, n_cols = (uint32_t)tot_cols;
     const bool store = !(a->flags & BMB200_F_COUNT_ONLY);
     const bool compress = (a->flags & BMB200_F_OPT_COMPRESS) != 0;
+    const bool or_target = (a->flags & BMB200_F_OR_TARGET) != 0;
 
     bmb200_result* r = *inout;
-    if (r && (r->ctx != ctx || r->n_cols != n_cols || (store && !r->blocks) || (store && compress && !r->gaps))) {
+    if (r && (r->ctx != ctx || r->n_cols != n_cols || r->n_groups != ng || (store && !r->blocks) ||
+              (store && compress && !r->gaps) || (or_target && !r->or_blocks))) {
         bmb200_result_free(r); r = nullptr; *inout = nullptr;
     }
     if (!r) {
-        int rc = result_alloc(ctx, n_cols, store, store && compress, &r);
+        int rc = result_alloc(ctx, n_cols, ng, store, store && compress, or_target, &r);
         if (rc) return rc;
     }
     r->has_blocks = store; r->compress = compress; r->gaps_ready = false;
 
-    // group ids -> device (pinned staging keeps the copy asynchronous)
-    const size_t ng = (size_t)a->n0 + n1;
-    if (ng > ctx->group_cap) {
+    // member ids + offsets -> device (pinned staging keeps the copy asynchronous; skipped when unchanged)
+    const size_t nwords = nmem + 2 * (size_t)ng + 1;
+    if (nwords > ctx->group_cap) {
         cudaStreamSynchronize(ctx->stream);
         cudaFree(ctx->d_group); if (ctx->h_group) cudaFreeHost(ctx->h_group);
         ctx->d_group = nullptr; ctx->h_group = nullptr; ctx->group_cap = 0; ctx->last_group.clear();
-        size_t cap = ng < 1024 ? 1024 : ng;
+        size_t cap = nwords < 1024 ? 1024 : nwords;
         if (cudaMalloc((void**)&ctx->d_group, cap * 4) != cudaSuccess || cudaMallocHost((void**)&ctx->h_group, cap * 4) != cudaSuccess) {
             ctx->last_err = "group buffer allocation"; if (!*inout) bmb200_result_free(r); return BMB200_ERR_BADALLOC;
         }
         ctx->group_cap = cap;
     }
-    bool same = (ctx->last_group.size() == ng) && ng &&
-                memcmp(ctx->last_group.data(), a->group0, (size_t)a->n0 * 4) == 0 &&
-                (!n1 || memcmp(ctx->last_group.data() + a->n0, a->group1, (size_t)n1 * 4) == 0);
-    if (ng && !same) {
+    const bool same = ctx->last_group.size() == nwords &&
+                      (!nmem || memcmp(ctx->last_group.data(), a->members, nmem * 4) == 0) &&
+                      memcmp(ctx->last_group.data() + nmem, a->offsets, (2 * (size_t)ng + 1) * 4) == 0;
+    if (!same) {
         cudaStreamSynchronize(ctx->stream);    // the staging buffer may still feed a previous launch
-        memcpy(ctx->h_group, a->group0, (size_t)a->n0 * 4);
-        if (n1) memcpy(ctx->h_group + a->n0, a->group1, (size_t)n1 * 4);
-        CU(cudaMemcpyAsync(ctx->d_group, ctx->h_group, ng * 4, cudaMemcpyHostToDevice, ctx->stream));
-        try { ctx->last_group.assign(ctx->h_group, ctx->h_group + ng); } catch (...) { ctx->last_group.clear(); }
+        if (nmem) memcpy(ctx->h_group, a->members, nmem * 4);
+        memcpy(ctx->h_group + nmem, a->offsets, (2 * (size_t)ng + 1) * 4);
+        CU(cudaMemcpyAsync(ctx->d_group, ctx->h_group, nwords * 4, cudaMemcpyHostToDevice, ctx->stream));
+        try { ctx->last_group.assign(ctx->h_group, ctx->h_group + nwords); } catch (...) { ctx->last_group.clear(); }
     }
     CU(cudaMemsetAsync(ctx->d_work, 0, 4, ctx->stream));
-    CU(cudaMemsetAsync(r->total, 0, 8, ctx->stream));
+    CU(cudaMemsetAsync(r->total, 0, 8 * (size_t)ng, ctx->stream));
+    if (or_target) CU(cudaMemsetAsync(r->or_blocks, 0, (size_t)cols * BMB200_BLOCK_BYTES, ctx->stream));
 
     AggParams p{};
-    p.set = set->v; p.group = ctx->d_group; p.n0 = a->n0; p.n1 = n1;
-    p.nb_from = a->nb_from; p.n_cols = n_cols;
+    p.set = set->v; p.group = ctx->d_group; p.goff = ctx->d_group + nmem; p.n_groups = ng;
+    p.nb_from = a->nb_from; p.n_cols = cols;
     p.compress = compress ? 1u : 0u; p.store_blocks = store ? 1u : 0u;
     p.blocks = r->blocks; p.popcnt = r->popcnt; p.digest = r->digest; p.nruns = r->nruns; p.kind = r->kind; p.gaps = r->gaps;
-    p.total = r->total; p.work_counter = ctx->d_work;
+    p.total = r->total; p.work_counter = ctx->d_work; p.or_blocks = or_target ? r->or_blocks : nullptr;
     p.gap_mode = (uint32_t)ctx->gap_mode; p.gap_pool_bytes = set->gap_pool_bytes;
-    if (!ctx->attr_set) {
-        CU(cudaFuncSetAttribute(agg_kernel<BMB200_OP_OR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggDynSmem));
-        CU(cudaFuncSetAttribute(agg_kernel<BMB200_OP_AND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggDynSmem));
-        CU(cudaFuncSetAttribute(agg_kernel<BMB200_OP_AND_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggDynSmem));
-        CU(cudaFuncSetAttribute(agg_kernel<BMB200_OP_XOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggDynSmem));
-        ctx->attr_set = true;
-    }
+    cudaError_t ae = cudaSuccess; set_agg_attrs(ctx, &ae);
+    if (ae != cudaSuccess) { ctx->last_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ae); if (!*inout) bmb200_result_free(r); return BMB200_ERR_CUDA; }
     uint32_t grid = (uint32_t)(ctx->sm_count * ctx->agg_ctas_per_sm);
     if (grid > n_cols) grid = n_cols;
     switch (a->op) {
@@ -598,6 +612,51 @@ int bmb200_aggregate(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_agg_ar
     if (rc) { if (!*inout) bmb200_result_free(r); return rc; }
     *inout = r;
     if (store && compress) r->gaps_ready = true;      // bit -> GAP conversion is fused into the kernel epilogue
+    return BMB200_OK;
+}
+
+int bmb200_aggregate(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_agg_args* a, bmb200_result** inout)
+{
+    if (!a) return BMB200_ERR_BADARG;
+    const uint32_t n1 = (a->op == BMB200_OP_AND_SUB) ? a->n1 : 0u;
+    if ((a->n0 && !a->group0) || (n1 && !a->group1)) return BMB200_ERR_BADARG;
+    std::vector<uint32_t> mem;
+    try { mem.reserve((size_t)a->n0 + n1); mem.insert(mem.end(), a->group0, a->group0 + a->n0); if (n1) mem.insert(mem.end(), a->group1, a->group1 + n1); }
+    catch (...) { return BMB200_ERR_BADALLOC; }
+    const uint32_t off[3] = {0u, a->n0, a->n0 + n1};
+    bmb200_batch_args b{a->op, a->flags & ~BMB200_F_OR_TARGET, 1u, mem.data(), off, a->nb_from, a->nb_to};
+    return bmb200_aggregate_batch(ctx, set, &b, inout);
+}
+
+int bmb200_result_group_totals(bmb200_result* r, uint64_t* totals, uint32_t n_groups)
+{
+    if (!r || !totals || n_groups != r->n_groups) return BMB200_ERR_BADARG;
+    bmb200_ctx* ctx = r->ctx;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(totals, r->total, 8 * (size_t)n_groups, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BMB200_OK;
+}
+
+int bmb200_result_or_target(bmb200_result* r, bmb200_result** out)
+{
+    if (!r || !out || !r->or_blocks) return BMB200_ERR_BADARG;
+    bmb200_ctx* ctx = r->ctx;
+    CU(cudaSetDevice(ctx->device));
+    bmb200_result* o = nullptr;
+    int rc = result_alloc(ctx, r->cols_per_group, 1u, true, r->compress, false, &o);
+    if (rc) return rc;
+    o->has_blocks = true; o->compress = r->compress; o->gaps_ready = r->compress;
+    CU(cudaMemsetAsync(o->total, 0, 8, ctx->stream));
+    AggParams p{};
+    p.n_groups = 1; p.n_cols = r->cols_per_group; p.compress = r->compress ? 1u : 0u; p.store_blocks = 1u;
+    p.blocks = o->blocks; p.popcnt = o->popcnt; p.digest = o->digest; p.nruns = o->nruns; p.kind = o->kind; p.gaps = o->gaps;
+    p.total = o->total; p.or_blocks = nullptr;
+    uint32_t grid = (uint32_t)(ctx->sm_count * ctx->agg_ctas_per_sm); if (grid > p.n_cols) grid = p.n_cols;
+    finalize_blocks_kernel<<<grid, kAggThreads, 0, ctx->stream>>>(p, r->or_blocks);
+    rc = after_launch(ctx);
+    if (rc) { bmb200_result_free(o); return rc; }
+    *out = o;
     return BMB200_OK;
 }
 
@@ -620,9 +679,10 @@ int bmb200_result_total(bmb200_result* r, uint64_t* total, int* any)
     if (!r) return BMB200_ERR_BADARG;
     bmb200_ctx* ctx = r->ctx;
     CU(cudaSetDevice(ctx->device));
-    unsigned long long t = 0;
-    CU(cudaMemcpyAsync(&t, r->total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<unsigned long long> tv(r->n_groups, 0ull);
+    CU(cudaMemcpyAsync(tv.data(), r->total, 8 * (size_t)r->n_groups, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    unsigned long long t = 0; for (auto x : tv) t += x;
     if (total) *total = t;
     if (any) *any = t ? 1 : 0;
     return BMB200_OK;

@@ -15,6 +15,8 @@
 
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -164,6 +166,14 @@ public:
         reset();                                                  // ag_.reset(), :1143
         run(target, BMB200_OP_AND, local.data(), n, 0, 0, opt_mode_ != BV::opt_none);
     }
+    /// N-way XOR (bvector::bit_xor chained, src/bm.h:6072); not a member of the reference aggregator
+    void combine_xor(bvector_type& target, const bvector_type_const_ptr* src, size_t n)
+    {
+        if (!n) { target.clear(); return; }
+        run(target, BMB200_OP_XOR, src, n, 0, 0, opt_mode_ != BV::opt_none);
+    }
+    /// template<class TPipe> void combine_and_sub(TPipe&), src/bmaggregator.h:427
+    template<class TPipe> void combine_and_sub(TPipe& pipe) { pipe.run(); }
     bool combine_and_sub(bvector_type& target,
                          const bvector_type_const_ptr* src_and, size_t n_and,
                          const bvector_type_const_ptr* src_sub, size_t n_sub, bool any)
@@ -250,6 +260,101 @@ private:
     size_type max_size_ = 0;
 };
 
+/// Drop-in for aggregator::pipeline<agg_opt_bvect_and_counts> + aggregator::combine_and_sub(TPipe&)
+/// (src/bmaggregator.h:222-341, 1291-1453): every argument group of the pipeline runs in ONE batched launch
+/// (bmb200_aggregate_batch); unique input vectors are uploaded once (the reference's pipeline_bcache).
+template<class BV>
+class pipeline
+{
+public:
+    typedef typename BV::size_type size_type;
+    struct arg_groups
+    {
+        std::vector<const BV*> arg_bv0, arg_bv1;
+        size_t add(const BV* bv, unsigned agr_group) { (agr_group ? arg_bv1 : arg_bv0).push_back(bv); return (agr_group ? arg_bv1 : arg_bv0).size(); }
+    };
+    explicit pipeline(context& c) : ctx_(c) {}
+    ~pipeline() { for (BV* p : bv_res_) delete p; }
+    pipeline(const pipeline&) = delete; pipeline& operator=(const pipeline&) = delete;
+
+    arg_groups* add() { args_.emplace_back(new arg_groups()); return args_.back().get(); }
+    void set_or_target(BV* bv_or) { bv_or_ = bv_or; }
+    void complete() { complete_ = true; }
+    bool is_complete() const { return complete_; }
+    size_type size() const { return (size_type)args_.size(); }
+    std::vector<BV*>& get_bv_res_vector() { return bv_res_; }                 ///< null for an empty result, like the reference
+    std::vector<size_type>& get_bv_count_vector() { return count_res_; }
+
+    /// aggregator::combine_and_sub(TPipe&)
+    void run()
+    {
+        if (!complete_) throw std::logic_error("pipeline::complete() not called");
+        for (BV* p : bv_res_) delete p;
+        const size_t ng = args_.size();
+        bv_res_.assign(ng, nullptr); count_res_.assign(ng, 0);
+        std::vector<const BV*> uniq; std::vector<uint32_t> members, offsets(1, 0u);
+        auto index_of = [&](const BV* bv) -> uint32_t {
+            for (size_t k = 0; k < uniq.size(); ++k) if (uniq[k] == bv) return (uint32_t)k;
+            uniq.push_back(bv); return (uint32_t)(uniq.size() - 1);
+        };
+        for (auto& a : args_) {
+            for (const BV* bv : a->arg_bv0) members.push_back(index_of(bv));
+            offsets.push_back((uint32_t)members.size());
+            for (const BV* bv : a->arg_bv1) members.push_back(index_of(bv));
+            offsets.push_back((uint32_t)members.size());
+        }
+        if (!ng || uniq.empty()) return;
+        uint32_t n_blocks = 0; size_type max_size = 0;
+        for (const BV* bv : uniq) { n_blocks = std::max(n_blocks, detail::blocks_of(*bv)); if (bv->size() > max_size) max_size = bv->size(); }
+        std::vector<detail::tree_view<BV>> views(uniq.size()); std::vector<bmb200_vec_blocks> vb(uniq.size());
+        for (size_t k = 0; k < uniq.size(); ++k) {
+            views[k].build(*uniq[k], n_blocks);
+            vb[k].n_blocks = n_blocks; vb[k].kind = views[k].kind.data(); vb[k].ptr = views[k].ptr.data();
+        }
+        bmb200_set* set = nullptr;
+        check(bmb200_set_upload_vectors(ctx_.get(), (uint32_t)uniq.size(), n_blocks, vb.data(), &set), "bmb200_set_upload_vectors");
+        bmb200_batch_args a{BMB200_OP_AND_SUB, BMB200_F_OPT_COMPRESS | (bv_or_ ? BMB200_F_OR_TARGET : 0u), (uint32_t)ng,
+                            members.data(), offsets.data(), 0, 0};
+        bmb200_result* res = nullptr; bmb200_result* ores = nullptr;
+        int rc = bmb200_aggregate_batch(ctx_.get(), set, &a, &res);
+        std::vector<uint64_t> totals(ng);
+        const size_t ncols = (size_t)ng * n_blocks;
+        std::vector<uint8_t> kind(ncols); std::vector<uint64_t> off(ncols); std::vector<uint32_t> bits; std::vector<uint16_t> gaps;
+        if (!rc) rc = bmb200_result_group_totals(res, totals.data(), (uint32_t)ng);
+        if (!rc) { uint64_t nb = 0, ngw = 0; rc = bmb200_result_sizes(res, &nb, &ngw);
+                   if (!rc) { bits.resize(nb * BMB200_BLOCK_WORDS); gaps.resize(ngw);
+                              rc = bmb200_result_fetch(res, kind.data(), off.data(), bits.data(), gaps.data()); } }
+        std::vector<uint8_t> okind(n_blocks); std::vector<uint64_t> ooff(n_blocks); std::vector<uint32_t> obits; std::vector<uint16_t> ogaps;
+        if (!rc && bv_or_) {
+            rc = bmb200_result_or_target(res, &ores);
+            if (!rc) { uint64_t nb = 0, ngw = 0; rc = bmb200_result_sizes(ores, &nb, &ngw);
+                       if (!rc) { obits.resize(nb * BMB200_BLOCK_WORDS); ogaps.resize(ngw);
+                                  rc = bmb200_result_fetch(ores, okind.data(), ooff.data(), obits.data(), ogaps.data()); } }
+        }
+        if (ores) bmb200_result_free(ores);
+        if (res) bmb200_result_free(res);
+        bmb200_set_free(set);
+        check(rc, "bmb200_aggregate_batch");
+        for (size_t g = 0; g < ng; ++g) {
+            count_res_[g] = (size_type)totals[g];
+            if (!totals[g]) continue;
+            bv_res_[g] = new BV();
+            detail::store_result(*bv_res_[g], max_size, n_blocks, kind.data() + g * n_blocks, off.data() + g * n_blocks, bits.data(), gaps.data());
+        }
+        if (bv_or_) {     // the reference ORs into the caller's vector (combine_operation_block_or); same here
+            BV tmp; detail::store_result(tmp, max_size, n_blocks, okind.data(), ooff.data(), obits.data(), ogaps.data());
+            bv_or_->bit_or(tmp);
+        }
+    }
+private:
+    context& ctx_;
+    std::vector<std::unique_ptr<arg_groups>> args_;
+    std::vector<BV*> bv_res_;
+    std::vector<size_type> count_res_;
+    BV* bv_or_ = nullptr;
+    bool complete_ = false;
+};
+
 /// 3-operand bvector ops (src/bm.h:1745-1850): target = a OP b
 template<class BV> void bit_or (context& c, BV& t, const BV& a, const BV& b, typename BV::optmode opt = BV::opt_none)
 { aggregator<BV> g(c); g.set_optimization(opt); const BV* s[2] = {&a, &b}; g.combine_or(t, s, 2); }
@@ -257,6 +362,8 @@ template<class BV> void bit_and(context& c, BV& t, const BV& a, const BV& b, typ
 { aggregator<BV> g(c); g.set_optimization(opt); const BV* s[2] = {&a, &b}; g.combine_and(t, s, 2); }
 template<class BV> void bit_sub(context& c, BV& t, const BV& a, const BV& b)
 { aggregator<BV> g(c); const BV* s0[1] = {&a}; const BV* s1[1] = {&b}; g.combine_and_sub(t, s0, 1, s1, 1, false); }
+template<class BV> void bit_xor(context& c, BV& t, const BV& a, const BV& b, typename BV::optmode opt = BV::opt_none)
+{ aggregator<BV> g(c); g.set_optimization(opt); const BV* s[2] = {&a, &b}; g.combine_xor(t, s, 2); }
 
 /// build_rs_index on the GPU, delivered through rs_index's own public mutators
 /// (resize / set_total / set_null_super_block / set_full_super_block / register_super_block,

@@ -74,6 +74,7 @@ extern "C" {
 #define BMB200_F_COUNT_ONLY  1u  /* per-column popcount/digest only; no result blocks stored */
 #define BMB200_F_OPT_NONE    0u  /* result kinds as aggregator opt_mode_ == opt_none           */
 #define BMB200_F_OPT_COMPRESS 2u /* classify + bit->GAP like opt_copy_bit_block(opt_compress) */
+#define BMB200_F_OR_TARGET   4u  /* batch only: also accumulate the union of all group results (pipeline::set_or_target) */
 
 typedef struct bmb200_ctx    bmb200_ctx;     /* one per process per GPU                      */
 typedef struct bmb200_set    bmb200_set;     /* device-resident column-major set of vectors  */
@@ -121,6 +122,19 @@ typedef struct bmb200_agg_args {
     uint32_t        nb_from;   /* block-column range [nb_from, nb_to)            */
     uint32_t        nb_to;     /* 0 == n_blocks                                  */
 } bmb200_agg_args;
+
+/* A pipeline batch: n_groups argument groups over ONE shared set (aggregator::pipeline, src/bmaggregator.h:222-341).
+ * Group g uses members[offsets[2g] .. offsets[2g+1]) as group0 (AND / OR / XOR sources) and
+ * members[offsets[2g+1] .. offsets[2g+2]) as group1 (SUB sources, OP_AND_SUB only). */
+typedef struct bmb200_batch_args {
+    int32_t         op;
+    uint32_t        flags;      /* BMB200_F_* ; BMB200_F_COUNT_ONLY = pipeline<agg_opt_only_counts> */
+    uint32_t        n_groups;
+    const uint32_t* members;    /* vector indices inside the set, all groups concatenated */
+    const uint32_t* offsets;    /* [2 * n_groups + 1] */
+    uint32_t        nb_from;
+    uint32_t        nb_to;      /* 0 == n_blocks */
+} bmb200_batch_args;
 
 /* Per-column result metadata (host arrays of n_cols = nb_to - nb_from entries; any may be NULL) */
 typedef struct bmb200_result_meta {
@@ -184,6 +198,14 @@ int bmb200_synth_set(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks,
  * *reuse (may be NULL): pass a previous result of the same shape to recycle its buffers. */
 int bmb200_aggregate(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_agg_args* args,
                      bmb200_result** inout);
+/* aggregator::combine_and_sub(TPipe&) (src/bmaggregator.h:1291-1453): every group in ONE launch.  The result has
+ * n_groups * n_cols columns, group-major (column c of group g at index g * n_cols + c); metadata / fetch calls work
+ * on that flat range. */
+int bmb200_aggregate_batch(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_batch_args* args, bmb200_result** inout);
+/* per-group cardinalities (pipeline::get_bv_count_vector) */
+int bmb200_result_group_totals(bmb200_result* res, uint64_t* totals, uint32_t n_groups);
+/* finalize the OR target of a batch launched with BMB200_F_OR_TARGET into its own n_cols-column result */
+int bmb200_result_or_target(bmb200_result* res, bmb200_result** out);
 /* classify every result column like opt_copy_bit_block and convert runs < 1276 to GAP on device */
 int bmb200_result_optimize(bmb200_result* res);
 /* total popcount over all columns and "any bit found" (combine_and_sub's return value) */

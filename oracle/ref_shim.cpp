@@ -344,6 +344,51 @@ int ref_rank_select(const bmb200_packed_set* s, uint32_t v,
 }
 
 /*
+ * aggregator::pipeline (src/bmaggregator.h:222-341) executed by combine_and_sub(TPipe&) (:1291-1453) on the real
+ * reference, options agg_opt_bvect_and_counts: per-group result vectors + counts, optional OR target.
+ * members/offsets as in bmb200_batch_args.  Outputs: counts[n_groups]; kind/popcnt/blocks for n_groups*n_blocks
+ * columns (group-major); or_kind/or_blocks for the OR target (n_blocks columns) when want_or != 0.
+ */
+int ref_pipeline(const bmb200_packed_set* s, uint32_t n_groups, const uint32_t* members, const uint32_t* offsets, int want_or,
+                 uint64_t* counts, uint8_t* kind, uint32_t* popcnt, uint32_t* blocks, uint8_t* or_kind, uint32_t* or_blocks)
+{
+    try {
+        std::vector<std::unique_ptr<bvect>> own(s->n_vec);
+        auto get = [&](uint32_t v) -> const bvect* {
+            if (!own[v]) { own[v].reset(new bvect()); build_bvector(s, v, 0, s->n_blocks, *own[v]); }
+            return own[v].get();
+        };
+        bm::aggregator<bvect> agg;
+        bm::aggregator<bvect>::pipeline<bm::agg_opt_bvect_and_counts> pipe;
+        bvect bv_or;
+        if (want_or) { bv_or.init(); pipe.set_or_target(&bv_or); }
+        for (uint32_t g = 0; g < n_groups; ++g) {
+            bm::aggregator<bvect>::arg_groups* args = pipe.add();
+            for (uint32_t k = offsets[2 * g]; k < offsets[2 * g + 1]; ++k) args->add(get(members[k]), 0);
+            for (uint32_t k = offsets[2 * g + 1]; k < offsets[2 * g + 2]; ++k) args->add(get(members[k]), 1);
+        }
+        pipe.complete();
+        agg.combine_and_sub(pipe);
+        auto& res = pipe.get_bv_res_vector();
+        auto& cnt = pipe.get_bv_count_vector();
+        for (uint32_t g = 0; g < n_groups; ++g) {
+            if (counts) counts[g] = (uint64_t)cnt[g];
+            const bvect* bv = res[g];
+            size_t o = (size_t)g * s->n_blocks;
+            if (bv) export_bvector(*bv, s->n_blocks, kind ? kind + o : 0, popcnt ? popcnt + o : 0,
+                                   blocks ? blocks + o * BMB200_BLOCK_WORDS : 0, 0);
+            else {
+                if (kind) std::memset(kind + o, 0, s->n_blocks);
+                if (popcnt) std::memset(popcnt + o, 0, sizeof(uint32_t) * s->n_blocks);
+                if (blocks) std::memset(blocks + o * BMB200_BLOCK_WORDS, 0, (size_t)s->n_blocks * BMB200_BLOCK_BYTES);
+            }
+        }
+        if (want_or) export_bvector(bv_or, s->n_blocks, or_kind, 0, or_blocks, 0);
+        return 0;
+    } catch (...) { return 1; }
+}
+
+/*
  * CPU baseline timing.  The reference aggregator is single-threaded; for an all-cores figure each of
  * `threads` workers owns its own bm::aggregator and its own copy of the inputs restricted to a
  * contiguous range of block columns.  Columns [nb_from, nb_to) are split evenly.

@@ -83,6 +83,33 @@ int main()
         t1.bit_or(*all[2], *all[20], bvect::opt_none); bm::b200::bit_or(ctx, t2, *all[2], *all[20]); CHECK(t1.compare(t2) == 0, "bit_or");
         t1.bit_sub(*all[1], *all[3], bvect::opt_none); bm::b200::bit_sub(ctx, t2, *all[1], *all[3]); CHECK(t1.compare(t2) == 0, "bit_sub");
     }
+    {   // pipeline: many argument groups over shared vectors (tests/stress/t.cpp:10383-10640)
+        bm::aggregator<bvect> ref; bm::b200::aggregator<bvect> gpu(ctx);
+        bm::aggregator<bvect>::pipeline<bm::agg_opt_bvect_and_counts> rp;
+        bm::b200::pipeline<bvect> gp(ctx);
+        bvect or_ref, or_gpu; or_ref.init(); or_gpu.init();
+        rp.set_or_target(&or_ref); gp.set_or_target(&or_gpu);
+        for (int g = 0; g < 12; ++g) {
+            auto* a1 = rp.add(); auto* a2 = gp.add();
+            int na = 1 + g % 3, ns = (g * 5) % 9;
+            for (int k = 0; k < na; ++k) { a1->add(all[(g + k) % 24], 0); a2->add(all[(g + k) % 24], 0); }
+            for (int k = 0; k < ns; ++k) { a1->add(all[(g * 7 + k + 3) % 24], 1); a2->add(all[(g * 7 + k + 3) % 24], 1); }
+        }
+        rp.complete(); gp.complete();
+        ref.combine_and_sub(rp); gpu.combine_and_sub(gp);
+        auto& r1 = rp.get_bv_res_vector(); auto& c1 = rp.get_bv_count_vector();
+        auto& r2 = gp.get_bv_res_vector(); auto& c2 = gp.get_bv_count_vector();
+        CHECK(r1.size() == r2.size() && c1.size() == c2.size(), "pipeline sizes");
+        for (size_t g = 0; g < r2.size(); ++g) {
+            CHECK((size_t)c1[g] == (size_t)c2[g], "pipeline count g=%zu", g);
+            CHECK((r1[g] == 0) == (r2[g] == 0), "pipeline null-ness g=%zu", g);
+            if (r1[g] && r2[g]) CHECK(r1[g]->compare(*r2[g]) == 0, "pipeline result g=%zu", g);
+        }
+        CHECK(or_ref.compare(or_gpu) == 0, "pipeline OR target");
+    }
+    {   bvect t1, t2;
+        t1.bit_xor(*all[4], *all[11], bvect::opt_none); bm::b200::bit_xor(ctx, t2, *all[4], *all[11]); CHECK(t1.compare(t2) == 0, "bit_xor");
+    }
     // rs_index built on the GPU, consumed by the reference's own count_to / select
     for (int k : {0, 3, 8, 23}) {
         const bvect& bv = *all[k];

@@ -176,3 +176,21 @@ def ref_time_aggregate(ps, op, g0, g1=None, flags=0, threads=1, repeats=3, nb_fr
     rc = ref(addr64).ref_time_aggregate(C.byref(c), C.byref(a), int(threads), int(repeats), C.byref(best), C.byref(tot))
     assert rc == 0
     return best.value, tot.value
+
+
+def ref_pipeline(ps, groups, want_or=False):
+    """The real aggregator::pipeline -> counts[n_groups], kind/pop/blocks [n_groups][n_blocks], (or_kind, or_blocks)"""
+    mem, off = [], [0]
+    for g0, g1 in groups:
+        mem.extend(int(x) for x in g0); off.append(len(mem))
+        mem.extend(int(x) for x in (g1 if g1 is not None else [])); off.append(len(mem))
+    members = np.ascontiguousarray(mem, dtype=np.uint32); offsets = np.ascontiguousarray(off, dtype=np.uint32)
+    ng, nb = len(groups), ps.n_blocks
+    counts = np.zeros(ng, np.uint64); kind = np.zeros((ng, nb), np.uint8); pop = np.zeros((ng, nb), np.uint32)
+    blocks = np.zeros((ng, nb, BLOCK_WORDS), np.uint32)
+    or_kind = np.zeros(nb, np.uint8); or_blocks = np.zeros((nb, BLOCK_WORDS), np.uint32)
+    c = _pc(ps)
+    rc = ref().ref_pipeline(C.byref(c), ng, ptr(members), ptr(offsets), int(want_or), ptr(counts), ptr(kind), ptr(pop), ptr(blocks),
+                            ptr(or_kind), ptr(or_blocks))
+    assert rc == 0
+    return counts, kind, pop, blocks, or_kind, or_blocks

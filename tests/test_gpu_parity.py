@@ -130,6 +130,64 @@ def test_gap_lead_pad_format(ctx):
     d0.free(); d1.free()
 
 
+def test_pipeline_batch(ctx):
+    """bmb200_aggregate_batch (aggregator::pipeline): every group equals its own single aggregate / the oracle;
+    counts, OR target, counts-only mode; and the unmodified reference pipeline when its library is present."""
+    rng = np.random.default_rng(31)
+    vecs = gen.mixed_vectors(rng, 18, 6, p_null=0.05, p_full=0.03)
+    ps = bm.PackedSet.pack(vecs)
+    dset = bm.DeviceSet.upload(ctx, ps)
+    groups = []
+    for _ in range(9):
+        perm = rng.permutation(18)
+        na = int(rng.integers(1, 4)); ns = int(rng.integers(0, 8))
+        groups.append((sorted(perm[:na].tolist()), sorted(perm[na:na + ns].tolist())))
+    groups.append(([0], []))
+    groups.append(([2, 3], [2]))                      # empty by construction
+    nb = ps.n_blocks
+    res = bm.aggregate_batch(ctx, dset, bm.OP_AND_SUB, groups, C | bm.F_OR_TARGET)
+    kind, pop, dig, nr = res.meta()
+    totals = res.group_totals(len(groups))
+    fk, off, bits, gaps = res.fetch()
+    union = np.zeros((nb, 2048), np.uint32)
+    for g, (g0, g1) in enumerate(groups):
+        okind, opop, odig, onr, oblk, ogap = orclib.oracle_aggregate(ps, bm.OP_AND_SUB, g0, g1, C)
+        sl = slice(g * nb, (g + 1) * nb)
+        assert np.array_equal(kind[sl], okind) and np.array_equal(pop[sl], opop) and np.array_equal(dig[sl], odig) and np.array_equal(nr[sl], onr)
+        assert totals[g] == int(opop.sum())
+        bv = bm.result_to_bvector(fk[sl], off[sl], bits, gaps)
+        assert np.array_equal(np.stack([bv.block_words(c) for c in range(nb)]), oblk)
+        union |= oblk
+    o = res.or_target(nb)
+    obv = bm.result_to_bvector(*o.fetch())
+    assert np.array_equal(np.stack([obv.block_words(c) for c in range(nb)]), union)
+    o.free(); res.free()
+    # counts only
+    res = bm.aggregate_batch(ctx, dset, bm.OP_AND_SUB, groups, bm.F_COUNT_ONLY)
+    assert np.array_equal(res.group_totals(len(groups)), totals)
+    res.free()
+    # host mirror: Pipeline / Aggregator.combine_and_sub(pipeline)
+    pipe = bm.Pipeline(make_results=True, compute_counts=True)
+    for g0, g1 in groups:
+        a = pipe.add()
+        for v in g0: a.add(vecs[v], 0)
+        for v in g1: a.add(vecs[v], 1)
+    pipe.set_or_target()
+    pipe.complete()
+    bm.Aggregator(ctx).combine_and_sub(pipe)
+    assert pipe.get_bv_count_vector() == [int(t) for t in totals]
+    assert pipe.get_bv_res_vector()[-1] is None and pipe.get_bv_res_vector()[0] is not None
+    assert np.array_equal(np.stack([pipe.or_target.block_words(c) for c in range(nb)]), union)
+    if orclib.have_ref():
+        rc, rkind, rpop, rblk, rok, rob = orclib.ref_pipeline(ps, groups, want_or=True)
+        assert np.array_equal(rc, totals)
+        assert np.array_equal(rblk.reshape(-1, 2048), np.concatenate([
+            np.stack([bm.result_to_bvector(fk[g * nb:(g + 1) * nb], off[g * nb:(g + 1) * nb], bits, gaps).block_words(c) for c in range(nb)])
+            for g in range(len(groups))]))
+        assert np.array_equal(rob, union)
+    dset.free()
+
+
 def test_edge_cases(ctx):
     vecs = gen.edge_vectors(4)
     ps = bm.PackedSet.pack(vecs)

@@ -168,3 +168,21 @@ def test_reference_known_answers_sample16():
         assert list(np.flatnonzero(bm.hostfmt.words_to_bits(blk[0]))) == [10000, 20000]
         blk = f(ps, bm.OP_AND_SUB, [0, 1, 2], [3], bm.F_OPT_COMPRESS)
         assert list(np.flatnonzero(bm.hostfmt.words_to_bits(blk[0]))) == [20000]
+
+
+@needs_ref
+def test_pipeline_oracle_matches_reference():
+    """aggregator::pipeline + combine_and_sub(TPipe&) (src/bmaggregator.h:222-341,1291-1453): counts, per-group
+    results (kinds included) and the OR target equal the per-group oracle."""
+    rng = np.random.default_rng(31)
+    vecs = gen.mixed_vectors(rng, 14, 5, p_null=0.05, p_full=0.03)
+    ps = bm.PackedSet.pack(vecs)
+    groups = [([0, 1], [2, 3, 4]), ([5], []), ([2, 3], [2]), ([6, 7, 8], [9, 10, 11, 12, 13]), ([1], [0])]
+    counts, rkind, rpop, rblk, rok, rob = orclib.ref_pipeline(ps, groups, want_or=True)
+    union = np.zeros((5, 2048), np.uint32)
+    for g, (g0, g1) in enumerate(groups):
+        okind, opop, odig, onr, oblk, _ = orclib.oracle_aggregate(ps, bm.OP_AND_SUB, g0, g1, bm.F_OPT_COMPRESS)
+        assert counts[g] == int(opop.sum())
+        assert np.array_equal(rblk[g], oblk) and np.array_equal(rpop[g], opop) and np.array_equal(rkind[g], okind)
+        union |= oblk
+    assert np.array_equal(rob, union)
