@@ -398,3 +398,81 @@ def test_cxx_binding_against_reference_bvector_level():
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "OK:" in r.stdout
+
+
+def test_more_than_65536_blocks_64bit_address_range(ctx):
+    """n_blocks > 65536 (beyond the 32-bit address mode of the reference): aggregate + rs_index + rank/select vs the oracle."""
+    nbk = 66000
+    rng = np.random.default_rng(64)
+    vs = []
+    for k in range(3):
+        v = bm.BVector(nbk)
+        for nb in sorted(set(rng.integers(0, nbk, 40).tolist() + [0, 65535, 65536, nbk - 1])):
+            w = hf_bits(rng, 0.01 * (k + 1))
+            if k == 2:
+                v.set_gap(nb, bm.hostfmt.bits_to_gap(hf_bits(rng, 0.001)))
+            else:
+                v.set_bits(nb, w)
+        vs.append(v)
+    vs[1].set_full(65537)
+    ps = bm.PackedSet.pack(vs)
+    dset = bm.DeviceSet.upload(ctx, ps)
+    for op, g0, g1 in [(bm.OP_OR, [0, 1, 2], None), (bm.OP_AND_SUB, [0], [1, 2])]:
+        res = bm.aggregate(ctx, dset, op, g0, g1, C)
+        kind, pop, dig, nr = res.meta()
+        okind, opop, odig, onr, _, _ = orclib.oracle_aggregate(ps, op, g0, g1, C)
+        assert np.array_equal(kind, okind) and np.array_equal(pop, opop) and np.array_equal(dig, odig) and np.array_equal(nr, onr)
+        res.free()
+    rs = bm.DeviceRS(ctx, dset, 1)
+    obc, osc, osb = orclib.oracle_rs_build(ps, 1)
+    bc, sc, sb = rs.export()
+    assert np.array_equal(bc, obc) and np.array_equal(sc, osc) and np.array_equal(sb, osb)
+    pos = np.concatenate([rng.integers(0, nbk * 65536, 3000), [2**32 - 1, 2**32, 2**32 + 65536 + 5, nbk * 65536 - 1]]).astype(np.uint64)
+    assert np.array_equal(rs.rank(pos), orclib.oracle_rank(ps, 1, pos))
+    rank = rng.integers(0, rs.total() + 2, 3000).astype(np.uint64)
+    p, f = rs.select(rank); op_, of = orclib.oracle_select(ps, 1, rank)
+    assert np.array_equal(f, of) and np.array_equal(p[f], op_[of]) and int(p[f].max()) >= 2**32
+    rs.rebuild()
+    assert np.array_equal(rs.rank(pos), orclib.oracle_rank(ps, 1, pos))
+    rs.free(); dset.free()
+
+
+def hf_bits(rng, d):
+    return bm.hostfmt.bits_to_words(rng.random(65536) < d)
+
+
+def test_adopt_device_memory_and_no_leaks(ctx):
+    """bmb200_set_adopt_device over torch-owned HBM; repeated create/free cycles return all device memory."""
+    import ctypes as Cc
+    import torch
+    from bitmagic_b200 import capi
+    rng = np.random.default_rng(5)
+    ps = bm.PackedSet.pack(gen.mixed_vectors(rng, 8, 5))
+    dev = torch.device("cuda:0")
+    def up(a, pad=0):
+        t = torch.zeros(a.nbytes + pad, dtype=torch.uint8, device=dev)
+        t[: a.nbytes] = torch.from_numpy(a.view(np.uint8)).to(dev)
+        return t
+    t_desc, t_bb, t_gb = up(ps.desc), up(ps.bit_base), up(ps.gap_base)
+    t_bp, t_gp = up(ps.bit_pool, 512), up(ps.gap_pool, 512)        # caller-owned pools need the 512-byte read slack
+    c = capi.PackedSetC(ps.n_vec, ps.n_blocks, t_desc.data_ptr(), t_bb.data_ptr(), t_gb.data_ptr(), t_bp.data_ptr(), t_gp.data_ptr())
+    h = Cc.c_void_p(0)
+    ctx.check(capi.lib().bmb200_set_adopt_device(ctx._h, Cc.byref(c), Cc.byref(h)), "set_adopt_device")
+    dset = capi.DeviceSet(ctx, h)
+    g0, g1 = [0, 1], [2, 3, 4, 5, 6, 7]
+    res = bm.aggregate(ctx, dset, bm.OP_AND_SUB, g0, g1, C)
+    okind, opop, *_ = orclib.oracle_aggregate(ps, bm.OP_AND_SUB, g0, g1, C)
+    kind, pop, _, _ = res.meta()
+    assert np.array_equal(kind, okind) and np.array_equal(pop, opop)
+    res.free(); dset.free()
+    assert bool((t_bp[: ps.bit_pool.nbytes].cpu().numpy().view(np.uint32) == ps.bit_pool).all())   # adopted memory untouched, still owned by torch
+    ctx.sync(); torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info(0)[0]
+    for _ in range(20):
+        d = bm.DeviceSet.upload(ctx, ps)
+        r = bm.aggregate(ctx, d, bm.OP_OR, list(range(8)), None, C)
+        rs = bm.DeviceRS(ctx, d, 3)
+        r.fetch(); rs.rank(np.arange(10, dtype=np.uint64))
+        rs.free(); r.free(); d.free()
+    ctx.sync()
+    assert torch.cuda.mem_get_info(0)[0] >= free0 - (4 << 20), "device memory leaked across create/free cycles"
