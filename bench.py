@@ -165,7 +165,7 @@ def device_set_stats(ctx, dset, torch):
         col = torch.arange(dset.n_blocks, device=desc.device).repeat_interleave(dset.n_vec)
         isgap = kind == 3
         dg = desc[isgap]
-        off = (gb[col[isgap]] + ((dg >> 2) & 0x1FFFFFFF)) * 8 + (dg >> 31)      # + lead pad (BMB200_DESC_GAP_PAD)
+        off = (gb[col[isgap]] + ((dg >> 2) & 0x0FFFFFFF)) * 8 + (dg >> 31)      # + lead pad (BMB200_DESC_GAP_PAD)
         hdr = gp[off].long() & 0xFFFF
         gap_words = int(((hdr >> 3) + 1).sum())
     return counts, gap_words

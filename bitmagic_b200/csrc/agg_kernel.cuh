@@ -16,12 +16,20 @@
 //   * GAP sources are never expanded on their own.  The column's GAP segment is contiguous in the arena
 //     (column-major layout), so it is streamed with cp.async.bulk (TMA) in 16 KB chunks into a 4-stage
 //     shared-memory ring tracked by mbarriers -- 64 KB in flight per CTA without a single LSU global load.
-//     One warp per GAP block scatters the selected runs (one run per lane) into an 8 KB mask K in shared
-//     memory with red.shared.  The warp that finishes a chunk last re-arms its stage (no producer warp).
-//     K meets the register accumulator only once, in the epilogue:
-//         OR      : R = U | K            (K = union of 1-runs)
-//         AND-SUB : R = P & ~U & ~K      (K = 0-runs of AND-group GAPs  U  1-runs of SUB-group GAPs)
-//         XOR     : R = X ^ K
+//     The bit phase runs first and is folded into an 8 KB "live" mask L in shared memory; GAP runs then only
+//     ever CLEAR bits of L (red.shared.and), so a run whose word of L is already dead costs one shared load
+//     and no atomic (the reference gets the same effect from its digest, src/bmfunc.h:7615):
+//         OR      : L = ~U,      selected runs = 1-runs,                       R = ~L
+//         AND-SUB : L = P & ~U,  selected runs = 0-runs of AND-group GAPs and
+//                                                1-runs of SUB-group GAPs,     R = L
+//         XOR     : L = X,       runs are XOR-ed in (red.shared.xor),          R = L
+//     Two consumers of the ring:
+//       - FLAT (OR sources / SUB group): when every GAP block of the streamed window belongs to the list and is
+//         stored in the BMB200_DESC_GAP_FLAT form, the window is just an array of aligned (prev_end, end) u16
+//         pairs -- headers, pads and tail fill decode to empty runs -- so 512 threads eat it with 128-bit
+//         shared loads, 4 runs per load, no per-block bookkeeping at all;
+//       - per block (AND-group GAPs, XOR, subsets of the pool, legacy layout): 16 lanes share one GAP block.
+//     The warp that finishes a chunk last re-arms its stage (no producer warp).
 //     Unsorted / sparse member lists fall back to per-block gathers from global memory.
 //   * epilogue fuses popcount, 64-wave digest, run count and the result-kind decision.
 #pragma once
@@ -48,9 +56,6 @@ constexpr int kAggChunk   = 1024;   // group members classified per pass
 #endif
 #ifndef BMB200_LANES_PER_BLOCK   /* lanes that share one GAP block in the streamed scatter: 32, 16, 8 or 4 */
 #define BMB200_LANES_PER_BLOCK 16
-#endif
-#ifndef BMB200_VAR_ANTIPHASE     /* second resident CTA of an SM runs GAP phase first, bit phase second */
-#define BMB200_VAR_ANTIPHASE 0
 #endif
 #ifndef BMB200_VAR_UNROLL2       /* two scatter steps per loop trip: both loads issued before the first red */
 #define BMB200_VAR_UNROLL2 1
@@ -96,7 +101,9 @@ struct AggParams {
 constexpr uint32_t kFlNull0 = 1u;   // a NULL block in group0
 constexpr uint32_t kFlFull0 = 2u;   // a FULL block in group0
 constexpr uint32_t kFlFull1 = 4u;   // a FULL block in group1 (SUB)
-constexpr uint32_t kRelMask = BMB200_DESC_REL_MASK;   // list entries are desc >> 2: unit in the low 29 bits, pad flag in bit 29
+constexpr uint32_t kRelMask = BMB200_DESC_REL_MASK;   // list entries are desc >> 2: unit in the low 28 bits, FLAT in bit 28, pad in bit 29
+constexpr uint32_t kEntFlat = BMB200_DESC_GAP_FLAT >> 2;
+constexpr uint32_t kFlatMinBlocks = 16u;              // shorter lists take the per-block path
 
 // ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -132,8 +139,17 @@ __device__ __forceinline__ void fence_proxy_async()
 // raw 32-bit shared-window addresses keep the scatter loop free of generic->shared conversions
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return (uint32_t)v; }
-__device__ __forceinline__ void reds_or(uint32_t a, uint32_t v)  { asm volatile("red.shared.or.b32 [%0], %1;"  :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ void reds_and(uint32_t a, uint32_t v) { asm volatile("red.shared.and.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void reds_xor(uint32_t a, uint32_t v) { asm volatile("red.shared.xor.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+// mask of `width` bits starting at bit `pos` (pos < 32; bits beyond bit 31 are dropped) -- SASS BMSK
+__device__ __forceinline__ uint32_t bmsk(uint32_t pos, uint32_t width)
+{
+    uint32_t m; asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(m) : "r"(pos), "r"(width)); return m;
+}
 
 template <int OP>
 __device__ __forceinline__ void acc_apply0(uint4& a, const uint4& v)
@@ -167,22 +183,73 @@ __device__ __forceinline__ void bit_phase(const uint4* __restrict__ seg, const u
     }
 }
 
-// apply one run [s, e] (inclusive bit positions) to the mask K (Ks = shared-window address of K)
+// apply one run [s, e] (inclusive bit positions) to the live mask L (Ls = its shared-window address):
+// clear the bits (OR / AND / AND-SUB) or flip them (XOR)
 template <bool XOR>
-__device__ __forceinline__ void apply_run(uint32_t Ks, uint32_t s, uint32_t e)
+__device__ __forceinline__ void apply_word(uint32_t a, uint32_t m)
+{
+    if (XOR) reds_xor(a, m); else reds_and(a, ~m);
+}
+template <bool XOR>
+__device__ __forceinline__ void apply_run(uint32_t Ls, uint32_t s, uint32_t e)
 {
     const uint32_t ws = s >> 5, we = e >> 5;
     const uint32_t m0 = 0xffffffffu << (s & 31u);
     const uint32_t m1 = 0xffffffffu >> (31u - (e & 31u));
     if (ws == we) {
-        if (XOR) reds_xor(Ks + ws * 4u, m0 & m1); else reds_or(Ks + ws * 4u, m0 & m1);
+        apply_word<XOR>(Ls + ws * 4u, m0 & m1);
     } else {
-        if (XOR) { reds_xor(Ks + ws * 4u, m0); reds_xor(Ks + we * 4u, m1); }
-        else     { reds_or(Ks + ws * 4u, m0);  reds_or(Ks + we * 4u, m1); }
-        for (uint32_t w = ws + 1; w < we; ++w) {
-            if (XOR) reds_xor(Ks + w * 4u, 0xffffffffu); else reds_or(Ks + w * 4u, 0xffffffffu);
-        }
+        apply_word<XOR>(Ls + ws * 4u, m0);
+        apply_word<XOR>(Ls + we * 4u, m1);
+        for (uint32_t w = ws + 1; w < we; ++w) apply_word<XOR>(Ls + w * 4u, 0xffffffffu);
     }
+}
+
+// FLAT consumer: one aligned u32 of a flat window = (prev_end, end) of a 1-run, or a header / pad / fill pair
+// (prev_end >= end: nothing to do).  Four pairs per call, branch-free on the common path: the mask of an empty
+// pair is 0, the atomic is predicated, and only runs that continue past their first word take the slow branch.
+// TEST: look at the word of L first -- bits only ever get cleared, so a stale read can only cause a redundant
+// atomic, never a missed one.
+__device__ __forceinline__ void reds_and_if(uint32_t a, uint32_t v, uint32_t cond)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.and.b32 [%0], %1;\n\t}"
+                 :: "r"(a), "r"(v), "r"(cond) : "memory");
+}
+__device__ __noinline__ void flat_pair_tail(uint32_t Ls, uint32_t w)      // words after the first of a long run
+{
+    const uint32_t lo = w & 0xffffu, hi = w >> 16;
+    if (lo >= hi) return;
+    const uint32_t s = lo + 1u, sb = s & 31u, wd = hi - lo;
+    if (sb + wd <= 32u) return;
+    uint32_t rem = sb + wd - 32u;
+    uint32_t a = Ls + ((s >> 5) << 2) + 4u;
+    for (; rem >= 32u; rem -= 32u, a += 4u) reds_and(a, 0u);
+    if (rem) reds_and(a, 0xffffffffu << rem);
+}
+template <bool TEST>
+__device__ __forceinline__ void flat_quad(uint32_t Ls, const uint4& q)
+{
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t a[4], m[4], reach = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t lo = w[i] & 0xffffu, hi = w[i] >> 16;
+        const uint32_t s = lo + 1u, sb = s & 31u, wd = max(hi, lo) - lo;     // wd == 0: no run
+        m[i] = bmsk(sb, wd);
+        a[i] = Ls + ((s >> 3) & 0x1ffcu);                                     // s == 65536 (pad / terminator) wraps to word 0, mask 0
+        reach = max(reach, sb + wd);
+    }
+    if (TEST) {
+        uint32_t v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = lds32(a[i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) reds_and_if(a[i], ~m[i], v[i] & m[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) reds_and_if(a[i], ~m[i], m[i]);
+    }
+    if (reach > 32u) { flat_pair_tail(Ls, q.x); flat_pair_tail(Ls, q.y); flat_pair_tail(Ls, q.z); flat_pair_tail(Ls, q.w); }
 }
 
 // GAP format (src/bmfunc.h:1696-1725): buf[0] = header (bit0 first-run value, len = hdr>>3),
@@ -350,7 +417,7 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     uint32_t* ring = reinterpret_cast<uint32_t*>(dyn_smem);
 
-    __shared__ __align__(16) uint32_t K[kBlockWords];
+    __shared__ __align__(16) uint32_t K[kBlockWords];   // the live mask L (see the header comment)
     __shared__ uint32_t lst_bit0[kAggChunk];
     __shared__ uint32_t lst_bit1[kAggChunk];
     __shared__ uint32_t lst_gap[kAggChunk];      // group0 GAPs from the front, group1 GAPs from the back (both in member order)
@@ -360,8 +427,13 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
     __shared__ uint32_t s_wcnt[4][kAggWarps];    // per-warp counts of the ordered compaction
     __shared__ uint32_t s_cnt[4];                // nbit0, nbit1, ngap0, ngap1 of the current chunk
     __shared__ uint32_t s_stat[4];               // flags, total nbit0, total ngap0, nfull0
+    __shared__ uint32_t s_flat[3];               // GAP blocks inside the flat window, first unit behind it, non-FLAT members
     __shared__ uint32_t s_col, s_gap_next;
     __shared__ uint32_t s_pc[kAggWarps], s_tr[kAggWarps], s_dg[kAggWarps];
+
+    constexpr bool kIsXor = (OP == BMB200_OP_XOR);
+    constexpr bool kIsAnd = (OP == BMB200_OP_AND || OP == BMB200_OP_AND_SUB);
+    constexpr int  kFlatList = (OP == BMB200_OP_OR) ? 0 : (OP == BMB200_OP_AND_SUB) ? 1 : -1;   // the list of 1-run sources
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t M = p.set.n_vec;
@@ -371,7 +443,6 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
     uint32_t Ks, ring_s;
     asm volatile("mov.u32 %0, %1;" : "=r"(Ks) : "r"(smem_u32(K)));
     asm volatile("mov.u32 %0, %1;" : "=r"(ring_s) : "r"(smem_u32(ring)));
-    const bool gap_first = BMB200_VAR_ANTIPHASE && (blockIdx.x >= (gridDim.x + 1u) / 2u);
     uint32_t gseq = 0;       // chunks streamed so far by this CTA: chunk g lives in stage g % S, its mbarrier phase is (g / S) & 1
 
     if (tid == 0) {
@@ -395,10 +466,10 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
         const uint32_t ntot = n0 + n1;
         const uint32_t* gmem = p.group + gb0;
 
-        K4[tid] = make_uint4(0u, 0u, 0u, 0u);
+        // live mask: everything alive (nothing covered yet / every bit still a candidate); XOR starts from zero
+        K4[tid] = kIsXor ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(~0u, ~0u, ~0u, ~0u);
         if (tid < 4) s_stat[tid] = 0u;
-        uint4 acc0 = (OP == BMB200_OP_AND || OP == BMB200_OP_AND_SUB) ? make_uint4(~0u, ~0u, ~0u, ~0u)
-                                                                      : make_uint4(0u, 0u, 0u, 0u);
+        uint4 acc0 = kIsAnd ? make_uint4(~0u, ~0u, ~0u, ~0u) : make_uint4(0u, 0u, 0u, 0u);
         uint4 acc1 = make_uint4(0u, 0u, 0u, 0u);   // union of SUB-group bit-blocks
 
         const uint32_t* drow = p.set.desc + (size_t)nb * M;
@@ -411,11 +482,11 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
 
         for (uint32_t cs = 0; cs < ntot; cs += kAggChunk) {
             if (tid < 4) s_cnt[tid] = 0u;
-            if (tid == 0) s_gap_next = 0u;
+            if (tid == 0) { s_gap_next = 0u; s_flat[0] = 0u; s_flat[1] = 0xffffffffu; s_flat[2] = 0u; }
             __syncthreads();
             // ---- classification (sort_input_blocks_*): order-preserving compaction into 4 lists ----
             const uint32_t ce = min(cs + (uint32_t)kAggChunk, ntot);
-            uint32_t fl = 0, nfull0 = 0;
+            uint32_t fl = 0, nfull0 = 0, nonflat = 0;
             for (uint32_t kb = cs; kb < ce; kb += kAggThreads) {   // uniform trip count (<= 2)
                 const uint32_t k = kb + tid;
                 uint32_t kind = 0xffu, rel = 0; bool g1 = false;
@@ -427,6 +498,7 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                 const bool c2 = (kind == BMB200_BLK_GAP) && !g1, c3 = (kind == BMB200_BLK_GAP) && g1;
                 if (kind == BMB200_BLK_NULL && !g1) fl |= kFlNull0;
                 if (kind == BMB200_BLK_FULL) { if (g1) fl |= kFlFull1; else { fl |= kFlFull0; ++nfull0; } }
+                if ((kFlatList == 0 ? c2 : c3) && !(rel & kEntFlat)) nonflat = 1u;
                 const uint32_t lt = (1u << lane) - 1u;
                 const uint32_t m0 = __ballot_sync(0xffffffffu, c0), m1 = __ballot_sync(0xffffffffu, c1);
                 const uint32_t m2 = __ballot_sync(0xffffffffu, c2), m3 = __ballot_sync(0xffffffffu, c3);
@@ -449,15 +521,17 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
             }
             fl = __reduce_or_sync(0xffffffffu, fl);
             nfull0 = warp_sum(nfull0);
-            if (lane == 0) { if (fl) atomicOr(&s_stat[0], fl); if (nfull0) atomicAdd(&s_stat[3], nfull0); }
+            nonflat = __reduce_or_sync(0xffffffffu, nonflat);
+            if (lane == 0) { if (fl) atomicOr(&s_stat[0], fl); if (nfull0) atomicAdd(&s_stat[3], nfull0); if (nonflat) s_flat[2] = 1u; }
             __syncthreads();
             const uint32_t nbit0 = s_cnt[0], nbit1 = s_cnt[1], ngap0 = s_cnt[2], ngap1 = s_cnt[3];
             if (tid == 0) { s_stat[1] += nbit0; s_stat[2] += ngap0; }
 
-            // ---- GAP lists: decide stream vs gather (uniform), set up the first streamed pass ----
+            // ---- GAP lists: decide flat / stream / gather (uniform), set up the first streamed pass ----
             // pass 0 = group0 list (front), pass 1 = group1 list (back, read reversed so it is in member order)
-            const uint32_t want0 = (OP == BMB200_OP_AND || OP == BMB200_OP_AND_SUB) ? 0u : 1u;
-            bool ok0 = false, ok1 = false;                      // list q is streamed (else gathered)
+            const uint32_t want0 = kIsAnd ? 0u : 1u;
+            bool ok0 = false, ok1 = false;                      // list q is streamed per block (else gathered)
+            bool flat = false;                                  // list kFlatList is streamed flat
             uint32_t lo0 = 0, lo1 = 0, wb0 = 0, wb1 = 0, nc0 = 0, nc1 = 0;   // window start unit, bytes, chunks
             {
                 int bad0 = 0, bad1 = 0;
@@ -466,6 +540,33 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                     bad1 |= !((lst_gap[kAggChunk - 1 - i] & kRelMask) < (lst_gap[kAggChunk - 2 - i] & kRelMask));
                 // NB: __syncthreads_or returns a predicate, not a bitwise OR -> one vote per list
                 const bool sorted0 = !__syncthreads_or(bad0), sorted1 = !__syncthreads_or(bad1);
+                // FLAT window: the units [lo, end) hold exactly the list's GAP blocks, all in FLAT form
+                if (kFlatList >= 0 && p.gap_mode == 0u) {
+                    const uint32_t nq = kFlatList ? ngap1 : ngap0;
+                    const bool sortedq = kFlatList ? sorted1 : sorted0;
+                    if (nq >= kFlatMinBlocks && sortedq && !s_flat[2] && M <= 8u * nq + 1024u) {   // uniform
+                        const uint32_t lo = (kFlatList ? lst_gap[kAggChunk - 1] : lst_gap[0]) & kRelMask;
+                        const uint32_t hi = (kFlatList ? lst_gap[kAggChunk - nq] : lst_gap[nq - 1]) & kRelMask;
+                        uint32_t c = 0, e = (uint32_t)(p.set.gap_base[nb + 1] - gseg_unit);
+                        for (uint32_t v = tid; v < M; v += kAggThreads) {
+                            const uint32_t d = drow[v];
+                            if ((d & 3u) == BMB200_BLK_GAP) {
+                                const uint32_t u = (d >> 2) & kRelMask;
+                                if (u >= lo && u <= hi) ++c; else if (u > hi) e = min(e, u);
+                            }
+                        }
+                        c = warp_sum(c); e = __reduce_min_sync(0xffffffffu, e);
+                        if (lane == 0) { if (c) atomicAdd(&s_flat[0], c); atomicMin(&s_flat[1], e); }
+                        __syncthreads();
+                        const uint32_t end = s_flat[1];
+                        if (s_flat[0] == nq && end > hi) {
+                            flat = true;
+                            const uint32_t w = (end - lo) * 16u;
+                            if (kFlatList) { lo1 = lo; wb1 = w; nc1 = (w + kGapChunkBytes - 1u) / kGapChunkBytes; }
+                            else           { lo0 = lo; wb0 = w; nc0 = (w + kGapChunkBytes - 1u) / kGapChunkBytes; }
+                        }
+                    }
+                }
                 auto plan = [&](uint32_t n, bool sorted, uint32_t lo, uint32_t hi, bool& ok, uint32_t& wlo, uint32_t& wb, uint32_t& nc) {
                     if (n == 0 || p.gap_mode == 1u || !sorted) return;
                     const uint64_t span = (uint64_t)(hi - lo) * 16ull + kGapMaxBytes;
@@ -474,35 +575,48 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                     const uint64_t w = span < avail ? span : avail;
                     ok = true; wlo = lo; wb = (uint32_t)w; nc = (uint32_t)((w + kGapChunkBytes - 1) / kGapChunkBytes);
                 };
-                if (ngap0) plan(ngap0, sorted0, lst_gap[0] & kRelMask, lst_gap[ngap0 - 1] & kRelMask, ok0, lo0, wb0, nc0);
-                if (ngap1) plan(ngap1, sorted1, lst_gap[kAggChunk - 1] & kRelMask, lst_gap[kAggChunk - ngap1] & kRelMask, ok1, lo1, wb1, nc1);
+                if (ngap0 && !(flat && kFlatList == 0)) plan(ngap0, sorted0, lst_gap[0] & kRelMask, lst_gap[ngap0 - 1] & kRelMask, ok0, lo0, wb0, nc0);
+                if (ngap1 && !(flat && kFlatList == 1)) plan(ngap1, sorted1, lst_gap[kAggChunk - 1] & kRelMask, lst_gap[kAggChunk - ngap1] & kRelMask, ok1, lo1, wb1, nc1);
             }
-            auto issue_fill = [&](uint32_t wlo, uint32_t wbytes, uint32_t c) {   // one thread: arm the stage of chunk c, start the copy
+            auto issue_fill = [&](uint32_t wlo, uint32_t wbytes, uint32_t c, bool mirror) {   // one thread: arm the stage of chunk c, start the copy
                 const uint32_t s = (gseq + c) % kGapStages;
                 const uint32_t off = c * kGapChunkBytes;
                 const uint32_t bytes = min(kGapChunkBytes, wbytes - off);
-                const uint32_t extra = s ? 0u : min(kGapMaxBytes, bytes);   // stage 0 is mirrored behind the ring
+                const uint32_t extra = (s || !mirror) ? 0u : min(kGapMaxBytes, bytes);   // stage 0 is mirrored behind the ring
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(gseg) + (size_t)wlo * 16u + off;
                 mbar_arrive_expect_tx(&s_full[s], bytes + extra);
                 bulk_g2s(reinterpret_cast<uint8_t*>(ring) + s * kGapChunkBytes, src, bytes, &s_full[s]);
                 if (extra) bulk_g2s(reinterpret_cast<uint8_t*>(ring) + kRingBytes, src, extra, &s_full[s]);
             };
-            auto stream_setup = [&](int q) {               // all threads; ends with a block barrier
+            auto stream_setup = [&](int q, bool isflat) {               // all threads; ends with a block barrier
                 const uint32_t n = q ? ngap1 : ngap0, wlo = q ? lo1 : lo0, nc = q ? nc1 : nc0, wbytes = q ? wb1 : wb0;
-                for (uint32_t i = tid; i < n; i += kAggThreads) {
-                    const uint32_t ei = (q ? lst_gap[kAggChunk - 1 - i] : lst_gap[i]) & kRelMask;
-                    const uint32_t ci = ((ei - wlo) * 16u) / kGapChunkBytes;
-                    int cp = -1;
-                    if (i) { const uint32_t ep = (q ? lst_gap[kAggChunk - i] : lst_gap[i - 1]) & kRelMask; cp = (int)(((ep - wlo) * 16u) / kGapChunkBytes); }
-                    for (int c = cp + 1; c <= (int)ci; ++c) s_cfirst[c] = i;
-                    if (i == n - 1) for (uint32_t c = ci + 1; c <= nc; ++c) s_cfirst[c] = n;
+                if (!isflat) {
+                    for (uint32_t i = tid; i < n; i += kAggThreads) {
+                        const uint32_t ei = (q ? lst_gap[kAggChunk - 1 - i] : lst_gap[i]) & kRelMask;
+                        const uint32_t ci = ((ei - wlo) * 16u) / kGapChunkBytes;
+                        int cp = -1;
+                        if (i) { const uint32_t ep = (q ? lst_gap[kAggChunk - i] : lst_gap[i - 1]) & kRelMask; cp = (int)(((ep - wlo) * 16u) / kGapChunkBytes); }
+                        for (int c = cp + 1; c <= (int)ci; ++c) s_cfirst[c] = i;
+                        if (i == n - 1) for (uint32_t c = ci + 1; c <= nc; ++c) s_cfirst[c] = n;
+                    }
                 }
                 if (tid < kGapStages) s_done[tid] = 0u;
                 __syncthreads();
                 if (tid == 0) {
                     fence_proxy_async();
                     const uint32_t pre = min((uint32_t)kGapStages, nc);
-                    for (uint32_t c = 0; c < pre; ++c) issue_fill(wlo, wbytes, c);
+                    for (uint32_t c = 0; c < pre; ++c) issue_fill(wlo, wbytes, c, !isflat);
+                }
+            };
+            auto stage_release = [&](uint32_t s, uint32_t r, uint32_t nc, uint32_t wlo, uint32_t wbytes, bool mirror) {   // per warp, after its share of chunk r
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    const uint32_t old = atomicAdd(&s_done[s], 1u);
+                    if (old == kAggWarps - 1) {          // last warp out re-arms the stage
+                        atomicExch(&s_done[s], 0u);
+                        if (r + kGapStages < nc) { __threadfence_block(); fence_proxy_async(); issue_fill(wlo, wbytes, r + kGapStages, mirror); }
+                    }
                 }
             };
             auto stream_consume = [&](int q, uint32_t want) {   // per warp, no block barriers inside
@@ -523,18 +637,38 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                         for (uint32_t i = ibeg + ((slot - ibeg) & (kSlots - 1u)); i < iend; i += kSlots) {
                             const uint32_t ent = q ? lst_gap[kAggChunk - 1 - i] : lst_gap[i];
                             const uint32_t ba = ring_s + (rot + ((ent & kRelMask) - wlo) * 16u) % kRingBytes;
-                            gap_scatter_ring<OP == BMB200_OP_XOR>(Ks, ba, ent >> 29, want, sub);
+                            gap_scatter_ring<kIsXor>(Ks, ba, ent >> 29, want, sub);
                         }
                     }
-                    __syncwarp();
-                    if (lane == 0) {
-                        __threadfence_block();
-                        const uint32_t old = atomicAdd(&s_done[s], 1u);
-                        if (old == kAggWarps - 1) {          // last warp out re-arms the stage
-                            atomicExch(&s_done[s], 0u);
-                            if (r + kGapStages < nc) { __threadfence_block(); fence_proxy_async(); issue_fill(wlo, wbytes, r + kGapStages); }
-                        }
+                    stage_release(s, r, nc, wlo, wbytes, true);
+                }
+                gseq += nc;
+            };
+            auto flat_consume = [&](int q) {                     // per warp, no block barriers inside
+                const uint32_t wlo = q ? lo1 : lo0, nc = q ? nc1 : nc0, wbytes = q ? wb1 : wb0;
+                for (uint32_t r = 0; r < nc; ++r) {
+                    const uint32_t g = gseq + r, s = g % kGapStages;
+                    mbar_wait(&s_full[s], (g / kGapStages) & 1u);
+                    const uint32_t bytes = min(kGapChunkBytes, wbytes - r * kGapChunkBytes);
+                    // 1024-bit sample of L: below 25 % alive the test-first form wins (one shared load, rarely an atomic)
+                    const uint32_t smp = lds32(Ks + ((((uint32_t)lane * 65u + (uint32_t)warp * 5u + r) & (kBlockWords - 1u)) << 2));
+                    const bool test = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(smp)) < 256u;
+                    const uint32_t off = (uint32_t)tid * 16u;
+                    const uint32_t src = ring_s + s * kGapChunkBytes + off;
+                    constexpr uint32_t kHalf = kAggThreads * 16u;
+                    static_assert(kGapChunkBytes % kHalf == 0, "chunk must be a whole number of 512-thread sweeps");
+                    uint4 q4[kGapChunkBytes / kHalf];
+#pragma unroll
+                    for (uint32_t h = 0; h < kGapChunkBytes / kHalf; ++h)
+                        q4[h] = (off + h * kHalf < bytes) ? lds128(src + h * kHalf) : make_uint4(0u, 0u, 0u, 0u);
+                    if (test) {
+#pragma unroll
+                        for (uint32_t h = 0; h < kGapChunkBytes / kHalf; ++h) flat_quad<true>(Ks, q4[h]);
+                    } else {
+#pragma unroll
+                        for (uint32_t h = 0; h < kGapChunkBytes / kHalf; ++h) flat_quad<false>(Ks, q4[h]);
                     }
+                    stage_release(s, r, nc, wlo, wbytes, false);
                 }
                 gseq += nc;
             };
@@ -546,37 +680,51 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                     g = __shfl_sync(0xffffffffu, g, 0);
                     if (g >= n) break;
                     const uint32_t ent = q ? lst_gap[kAggChunk - 1 - g] : lst_gap[g];
-                    gap_scatter_gather<OP == BMB200_OP_XOR>(Ks, gseg + (size_t)(ent & kRelMask) * kGapUnit + (ent >> 29), want, lane);
+                    gap_scatter_gather<kIsXor>(Ks, gseg + (size_t)(ent & kRelMask) * kGapUnit + (ent >> 29), want, lane);
                 }
             };
 
             // the first streamed list starts landing in the ring while the bit-blocks stream through registers
-            const int first_q = ok0 ? 0 : (ok1 ? 1 : -1);
-            if (first_q >= 0) stream_setup(first_q);
+            const bool flat0 = flat && kFlatList == 0, flat1 = flat && kFlatList == 1;
+            const bool str0 = ok0 || flat0, str1 = ok1 || flat1;
+            const int first_q = flat ? kFlatList : (ok0 ? 0 : (ok1 ? 1 : -1));
+            if (first_q >= 0) stream_setup(first_q, flat);
 
-            // The two phases touch disjoint state (registers vs K), so their order is free.  CTAs of the second
-            // residency wave run GAP first: the two CTAs sharing an SM then keep HBM (bit phase) and the LSU
-            // (GAP scatter) busy at the same time instead of marching in lockstep.
-            if (!gap_first) {
-                bit_phase<OP, false>(bseg, lst_bit0, nbit0, acc0);
-                if (OP == BMB200_OP_AND_SUB) bit_phase<OP, true>(bseg, lst_bit1, nbit1, acc1);
+            // ---- bit phase: registers <- streamed bit-blocks, then folded into the live mask ----
+            bit_phase<OP, false>(bseg, lst_bit0, nbit0, acc0);
+            if (OP == BMB200_OP_AND_SUB) bit_phase<OP, true>(bseg, lst_bit1, nbit1, acc1);
+            {
+                uint4 l = K4[tid];
+                if (kIsXor)      { l.x ^= acc0.x; l.y ^= acc0.y; l.z ^= acc0.z; l.w ^= acc0.w; acc0 = make_uint4(0u, 0u, 0u, 0u); }
+                else if (kIsAnd) { l.x &= acc0.x & ~acc1.x; l.y &= acc0.y & ~acc1.y; l.z &= acc0.z & ~acc1.z; l.w &= acc0.w & ~acc1.w; }
+                else             { l.x &= ~acc0.x; l.y &= ~acc0.y; l.z &= ~acc0.z; l.w &= ~acc0.w; }
+                K4[tid] = l;
             }
-            // ---- GAP phase ----
-            if (first_q >= 0) stream_consume(first_q, first_q ? 1u : want0);
-            if (first_q == 0 && ok1) {
-                __syncthreads();                     // ring and s_cfirst are reused by the second list
-                stream_setup(1);
-                stream_consume(1, 1u);
+            __syncthreads();
+
+            // ---- GAP phase: runs clear (XOR: flip) bits of the live mask ----
+            if (flat) {
+                // a FLAT block without lead pad starts with a 1-run whose pair slot holds the header: the flat pass
+                // clears at most a suffix of (0 .. buf[1]); clear the whole run here
+                const uint32_t n = kFlatList ? ngap1 : ngap0;
+                for (uint32_t i = tid; i < n; i += kAggThreads) {
+                    const uint32_t ent = kFlatList ? lst_gap[kAggChunk - 1 - i] : lst_gap[i];
+                    if (!(ent >> 29)) apply_run<false>(Ks, 0u, gseg[(size_t)(ent & kRelMask) * kGapUnit + 1u]);
+                }
+                flat_consume(kFlatList);
+            } else if (first_q >= 0) stream_consume(first_q, first_q ? 1u : want0);
+            {
+                const int second_q = (first_q == 0 && str1) ? 1 : (first_q == 1 && str0 ? 0 : -1);
+                if (second_q >= 0) {
+                    __syncthreads();                     // ring and s_cfirst are reused by the second list
+                    stream_setup(second_q, false);
+                    stream_consume(second_q, second_q ? 1u : want0);
+                }
             }
-            if (ngap0 && !ok0) gather_pass(0, want0);
-            if (ngap1 && !ok1) {
-                if (ngap0 && !ok0) { __syncthreads(); if (tid == 0) s_gap_next = 0u; __syncthreads(); }
+            if (ngap0 && !str0) gather_pass(0, want0);
+            if (ngap1 && !str1) {
+                if (ngap0 && !str0) { __syncthreads(); if (tid == 0) s_gap_next = 0u; __syncthreads(); }
                 gather_pass(1, 1u);
-            }
-            // ---- bit phase: registers <- streamed bit-blocks ----
-            if (gap_first) {
-                bit_phase<OP, false>(bseg, lst_bit0, nbit0, acc0);
-                if (OP == BMB200_OP_AND_SUB) bit_phase<OP, true>(bseg, lst_bit1, nbit1, acc1);
             }
             __syncthreads();
         }
@@ -595,18 +743,17 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                 const int ones = __syncthreads_and((acc0.x & acc0.y & acc0.z & acc0.w) == 0xffffffffu);
                 if (ones && tot_bit0 >= 2) state = 1;
             }
-            R = make_uint4(acc0.x | k4.x, acc0.y | k4.y, acc0.z | k4.z, acc0.w | k4.w);
+            R = make_uint4(~k4.x, ~k4.y, ~k4.z, ~k4.w);
         } else if (OP == BMB200_OP_XOR) {
             state = (tot_bit0 + tot_gap0 + tot_full0) ? 2 : 0;
             const uint32_t inv = (tot_full0 & 1u) ? 0xffffffffu : 0u;
-            R = make_uint4(acc0.x ^ k4.x ^ inv, acc0.y ^ k4.y ^ inv, acc0.z ^ k4.z ^ inv, acc0.w ^ k4.w ^ inv);
+            R = make_uint4(k4.x ^ inv, k4.y ^ inv, k4.z ^ inv, k4.w ^ inv);
         } else {
             if ((flags & kFlNull0) || n0 == 0) state = 0;
             else if (flags & kFlFull1) state = 0;
             else if (tot_bit0 + tot_gap0 == 0 && (OP == BMB200_OP_AND || n1 == 0)) state = 1;
             else state = 2;
-            R = make_uint4(acc0.x & ~(acc1.x | k4.x), acc0.y & ~(acc1.y | k4.y),
-                           acc0.z & ~(acc1.z | k4.z), acc0.w & ~(acc1.w | k4.w));
+            R = k4;
         }
         if (state == 0) R = make_uint4(0u, 0u, 0u, 0u);
         if (state == 1) R = make_uint4(~0u, ~0u, ~0u, ~0u);

@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(kPostThreads) synth_classify_kernel(uint32_t n
 }
 
 // per column: exclusive scans over the vectors -> descriptors + column totals
-__global__ void __launch_bounds__(256) synth_layout_kernel(uint32_t n_vec, uint32_t use_pad, const uint8_t* __restrict__ kind8,
+__global__ void __launch_bounds__(256) synth_layout_kernel(uint32_t n_vec, uint32_t flat_form, const uint8_t* __restrict__ kind8,
                                                            const uint16_t* __restrict__ glen,
                                                            uint32_t* __restrict__ desc,
                                                            uint64_t* __restrict__ col_bits, uint64_t* __restrict__ col_gaps)
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(256) synth_layout_kernel(uint32_t n_vec, uint3
             nbit = (kd == BMB200_BLK_BIT);
             if (kd == BMB200_BLK_GAP) {
                 const uint32_t gl = glen[(size_t)nb * n_vec + v];
-                pad = ((gl >> 15) || !use_pad) ? 0u : 1u;       // BMB200_DESC_GAP_PAD: align the 1-run pairs
+                pad = ((gl >> 15) || !flat_form) ? 0u : 1u;     // BMB200_DESC_GAP_FLAT: lead pad iff the first run is 0
                 ngap = ((gl & 0x7fffu) + 1u + pad + kGapUnit - 1u) / kGapUnit;
             }
         }
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(256) synth_layout_kernel(uint32_t n_vec, uint3
         for (int w = 0; w < 8; ++w) { if (w < warp) { ob += s_wb[w]; og += s_wg[w]; } tb += s_wb[w]; tg += s_wg[w]; }
         if (v < n_vec) {
             const uint32_t rel = (kd == BMB200_BLK_BIT) ? ob + ib - nbit : (kd == BMB200_BLK_GAP) ? og + ig - ngap : 0u;
-            desc[(size_t)nb * n_vec + v] = kd | (rel << 2) | (pad << 31);
+            desc[(size_t)nb * n_vec + v] = kd | (rel << 2) | (pad << 31) | ((kd == BMB200_BLK_GAP && flat_form) ? BMB200_DESC_GAP_FLAT : 0u);
         }
         __syncthreads();
         if (tid == 0) { s_cb += tb; s_cg += tg; }
@@ -548,10 +548,10 @@ __global__ void __launch_bounds__(kPostThreads) synth_write_kernel(uint32_t n_ve
         uint16_t* unit = gap_pool + (gap_base[nb] + rel) * (size_t)kGapUnit;
         uint16_t* out = unit + pad;
         const uint32_t len = block_to_gap_256(s_blk, s_scan, out, kGapMax - 1u);
-        // zero the lead pad and the tail up to the 16-byte unit
+        // lead pad = 0xFFFF, zeros from buf[len] to the end of the 16-byte unit (BMB200_DESC_GAP_FLAT contract)
         const uint32_t n = len + 1u + pad, npad = (n + kGapUnit - 1u) / kGapUnit * kGapUnit;
         if (tid < (int)(npad - n)) unit[n + tid] = 0;
-        if (tid == 0 && pad) unit[0] = 0;
+        if (tid == 0 && pad) unit[0] = 0xffffu;
     }
 }
 

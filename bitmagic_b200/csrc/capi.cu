@@ -311,9 +311,11 @@ int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks
                 if (!g) return BMB200_ERR_BADARG;
                 uint32_t words = (uint32_t)(g[0] >> 3) + 1u;
                 if (words > kGapMax) return BMB200_ERR_BADARG;
-                // BMB200_DESC_GAP_PAD is supported by every kernel but measured ~1-2 % slower on B200 (profiles/r01), so off
-                const uint32_t pad = (getenv("BMB200_GAP_PAD") && !(g[0] & 1u)) ? 1u : 0u;
-                rel = (uint32_t)ngap | (pad << 29); ngap += (words + pad + kGapUnit - 1) / kGapUnit;
+                // flat-streamable form (BMB200_DESC_GAP_FLAT): lead pad iff the first run is 0; BMB200_GAP_LEGACY=1 keeps the raw form
+                const bool legacy = getenv("BMB200_GAP_LEGACY") != nullptr;
+                const uint32_t pad = (!legacy && !(g[0] & 1u)) ? 1u : 0u;
+                if (ngap + (words + pad + kGapUnit - 1) / kGapUnit > (uint64_t)BMB200_DESC_REL_MASK) return BMB200_ERR_RANGE;
+                rel = (uint32_t)ngap | (pad << 29) | (legacy ? 0u : (BMB200_DESC_GAP_FLAT >> 2)); ngap += (words + pad + kGapUnit - 1) / kGapUnit;
             } else if (kd > 3u) return BMB200_ERR_BADARG;
             desc[(size_t)nb * n_vec + v] = kd | (rel << 2);
         }
@@ -333,7 +335,9 @@ int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks
                 memcpy(hb + (bb[nb] + rel) * (size_t)kBlockWords, vecs[v].ptr[nb], BMB200_BLOCK_BYTES);
             else if (kd == BMB200_BLK_GAP) {
                 const uint16_t* g = (const uint16_t*)vecs[v].ptr[nb];
-                memcpy(hg + (gb[nb] + (rel & BMB200_DESC_REL_MASK)) * (size_t)kGapUnit + (rel >> 29), g, ((size_t)(g[0] >> 3) + 1) * 2);
+                uint16_t* dst = hg + (gb[nb] + (rel & BMB200_DESC_REL_MASK)) * (size_t)kGapUnit;
+                if (rel >> 29) dst[0] = 0xffffu;
+                memcpy(dst + (rel >> 29), g, ((size_t)(g[0] >> 3) + 1) * 2);
             }
         }
     bmb200_packed_set h{n_vec, n_blocks, desc.data(), bb.data(), gb.data(), hb, hg};
@@ -470,7 +474,7 @@ int bmb200_synth_set(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks,
     cudaMemcpyAsync(d_thr, thr.data(), n_vec * 4, cudaMemcpyHostToDevice, st);
     synth_classify_kernel<<<(unsigned)items, kPostThreads, 0, st>>>(n_vec, n_blocks, d_seed, d_thr, optimize, d_kind, d_glen);
     if ((rc = after_launch(ctx))) { cleanup_tmp(); cudaFree(desc); cudaFree(bb); cudaFree(gb); return rc; }
-    synth_layout_kernel<<<n_blocks, 256, 0, st>>>(n_vec, getenv("BMB200_NO_PAD") ? 0u : 1u, d_kind, d_glen, desc, d_cb, d_cg);
+    synth_layout_kernel<<<n_blocks, 256, 0, st>>>(n_vec, getenv("BMB200_GAP_LEGACY") ? 0u : 1u, d_kind, d_glen, desc, d_cb, d_cg);
     after_launch(ctx);
     scan_u64_kernel<<<1, 1024, 0, st>>>(d_cb, n_blocks, bb); after_launch(ctx);
     scan_u64_kernel<<<1, 1024, 0, st>>>(d_cg, n_blocks, gb); after_launch(ctx);

@@ -192,8 +192,10 @@ class PackedSet:
     gap_pool: np.ndarray   # u16
 
     @classmethod
-    def pack(cls, vectors: list[BVector], n_blocks: int | None = None, gap_pad: bool = False) -> "PackedSet":
-        """Walk the host block trees column by column (what the binding does with get_block_ptr(i,j))."""
+    def pack(cls, vectors: list[BVector], n_blocks: int | None = None, gap_flat: bool = True) -> "PackedSet":
+        """Walk the host block trees column by column (what the binding does with get_block_ptr(i,j)).
+        gap_flat: store GAP blocks in the flat-streamable form (BMB200_DESC_GAP_FLAT, include/bmb200.h): lead pad
+        0xFFFF iff the first run is 0, zero fill to the 16-byte unit.  False = raw blocks, no flags."""
         nv = len(vectors)
         nb_tot = n_blocks if n_blocks is not None else max(v.n_blocks for v in vectors)
         desc = np.zeros(nb_tot * nv, dtype=np.uint32)
@@ -211,11 +213,13 @@ class PackedSet:
                 elif k == BLK_GAP:
                     g = bv.blocks[nb]
                     n = gap_words(g)
-                    pad = 1 if (gap_pad and not (int(g[0]) & 1)) else 0   # optional lead pad (BMB200_DESC_GAP_PAD)
+                    pad = 1 if (gap_flat and not (int(g[0]) & 1)) else 0
                     units = (n + pad + GAP_UNIT_WORDS - 1) // GAP_UNIT_WORDS
                     padded = np.zeros(units * GAP_UNIT_WORDS, dtype=np.uint16)
+                    if pad:
+                        padded[0] = 0xFFFF
                     padded[pad:pad + n] = g[:n]
-                    rel = ngap | (pad << 29); ngap += units
+                    rel = ngap | (pad << 29) | ((1 << 28) if gap_flat else 0); ngap += units
                     gaps.append(padded)
                 desc[nb * nv + v] = k | ((rel << 2) & 0xFFFFFFFF)
             bb[nb + 1] = bb[nb] + np.uint64(nbit)
@@ -232,7 +236,7 @@ class PackedSet:
             o = (int(self.bit_base[nb]) + rel) * BLOCK_WORDS
             return k, self.bit_pool[o:o + BLOCK_WORDS]
         if k == BLK_GAP:
-            o = (int(self.gap_base[nb]) + (rel & 0x1FFFFFFF)) * GAP_UNIT_WORDS + (rel >> 29)
+            o = (int(self.gap_base[nb]) + (rel & 0x0FFFFFFF)) * GAP_UNIT_WORDS + (rel >> 29)
             n = (int(self.gap_pool[o]) >> 3) + 1
             return k, self.gap_pool[o:o + n]
         return k, None

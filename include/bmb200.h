@@ -62,7 +62,8 @@ extern "C" {
 #define BMB200_BLK_BIT   2u
 #define BMB200_BLK_GAP   3u
 #define BMB200_DESC_GAP_PAD  0x80000000u   /* GAP block stored with a 2-byte lead pad (see bmb200_packed_set) */
-#define BMB200_DESC_REL_MASK 0x1fffffffu   /* rel = (desc >> 2) & mask */
+#define BMB200_DESC_GAP_FLAT 0x40000000u   /* GAP block stored in the flat-streamable form (see bmb200_packed_set) */
+#define BMB200_DESC_REL_MASK 0x0fffffffu   /* rel = (desc >> 2) & mask */
 
 /* ---- operations ---- */
 #define BMB200_OP_OR       0   /* group0 = sources                       */
@@ -85,11 +86,17 @@ typedef struct bmb200_rs     bmb200_rs;      /* device-resident rank-select inde
  * Packed (column-major) set of n_vec vectors x n_blocks block columns.
  *   desc[nb*n_vec + v] = kind | (rel << 2)
  *      BIT: rel = index of the block inside column nb's bit segment
- *      GAP: rel = offset inside column nb's GAP segment, in 16-byte units (29 bits); bit 31 of desc
- *           (BMB200_DESC_GAP_PAD) = the block is stored after ONE leading u16 of padding, which makes every
- *           (start,end) pair of the 1-runs of a block whose first run is 0 a 4-byte aligned word (one 32-bit
- *           shared load per run instead of two 16-bit ones).  Optional: all kernels accept both forms; the
- *           library's own packers leave it off (no measurable gain on B200, see profiles/r01/SUMMARY.md).
+ *      GAP: rel = offset inside column nb's GAP segment, in 16-byte units (28 bits).
+ *           bit 31 (BMB200_DESC_GAP_PAD): the block is stored after ONE leading u16 of padding.
+ *           bit 30 (BMB200_DESC_GAP_FLAT): the block is in the flat-streamable form --
+ *             - the (previous run end, run end) u16 pair of every 1-run is a 4-byte aligned word: a block whose
+ *               first run is 0 carries the lead pad, a block whose first run is 1 does not;
+ *             - the lead pad holds 0xFFFF and the bytes between buf[len] and the next 16-byte unit hold 0, so
+ *               header, pad, terminator and fill all read as pairs with first >= second (= no run);
+ *             - the units between two FLAT blocks of a column hold nothing else (no holes with stale data).
+ *           A window of FLAT blocks is then a plain array of 1-runs that the aggregation kernel consumes with
+ *           128-bit shared loads and no per-block work (agg_kernel.cuh).  Both bits are optional per block:
+ *           every kernel accepts every form; the library's own packers and bmb200_synth_set write FLAT.
  *   bit segment of column nb = bit_pool blocks [bit_base[nb], bit_base[nb+1])
  *   GAP segment of column nb = gap_pool units  [gap_base[nb], gap_base[nb+1])
  * All blocks of one column are contiguous, so one CTA streams one column.

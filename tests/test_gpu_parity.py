@@ -98,18 +98,23 @@ def test_gap_stream_and_gather_paths_agree(ctx):
             check_vs_oracle(ctx, ps, bm.OP_XOR, list(range(60, 300)), None, 0, dset)
             check_vs_oracle(ctx, ps, bm.OP_OR, list(range(299, 99, -1)), None, 0, dset)   # descending -> gather
             check_vs_oracle(ctx, ps, bm.OP_OR, [100, 299], None, 0, dset)                 # sparse subset -> gather
+            check_vs_oracle(ctx, ps, bm.OP_OR, list(range(100, 300, 2)), None, C, dset)   # non-members inside the window -> per-block stream
+            check_vs_oracle(ctx, ps, bm.OP_AND_SUB, [0, 150], list(range(100, 300)), C, dset)   # an AND member inside the SUB window
+            check_vs_oracle(ctx, ps, bm.OP_AND_SUB, [3], list(range(60, 300)) + [5], C, dset)   # unsorted tail member
     finally:
         ctx.set_tuning(0, 0)
     dset.free()
 
 
-def test_gap_lead_pad_format(ctx):
-    """BMB200_DESC_GAP_PAD: GAP blocks stored behind a 2-byte lead pad must give identical results everywhere
-    (aggregate stream + gather paths, rs_index build, rank, select)."""
+def test_gap_flat_and_raw_formats(ctx):
+    """BMB200_DESC_GAP_FLAT / _PAD: GAP blocks in the flat-streamable form (lead pad 0xFFFF iff first run is 0) and raw
+    GAP blocks must give identical results everywhere (aggregate flat / stream / gather paths, rs_index build, rank, select)."""
     rng = np.random.default_rng(21)
     vecs = gen.mixed_vectors(rng, 20, 5, p_null=0.05, p_gap=0.7) + gen.edge_vectors(5)
-    plain, padded = bm.PackedSet.pack(vecs), bm.PackedSet.pack(vecs, gap_pad=True)
-    assert (padded.desc >> 31).any() and not (plain.desc >> 31).any()
+    plain, padded = bm.PackedSet.pack(vecs, gap_flat=False), bm.PackedSet.pack(vecs)
+    assert (padded.desc >> 31).any() and not (plain.desc >> 30).any()
+    isgap = (padded.desc & 3) == bm.BLK_GAP
+    assert ((padded.desc[isgap] >> 30) & 1).all() and not (padded.desc[isgap] >> 31).all()   # first-run-1 blocks carry no pad
     d0, d1 = bm.DeviceSet.upload(ctx, plain), bm.DeviceSet.upload(ctx, padded)
     n = len(vecs)
     for op, g0, g1 in [(bm.OP_OR, list(range(n)), None), (bm.OP_AND_SUB, [0, 1], list(range(2, n))), (bm.OP_AND, [3, 4, 5], None),
@@ -128,6 +133,32 @@ def test_gap_lead_pad_format(ctx):
         assert np.array_equal(f0, f1) and np.array_equal(p0[f0], p1[f1])
         r0.free(); r1.free()
     d0.free(); d1.free()
+
+
+@pytest.mark.parametrize("seed", [3, 4])
+def test_flat_window_all_gap_styles(ctx, seed):
+    """The FLAT consumer (whole-pool OR / SUB groups, >= 16 GAP blocks per column) on every GAP style the generator knows:
+    sparse bits, few long runs (multi-word runs), ~1270 runs, word-aligned runs, mostly-ones blocks (first run = 1, long
+    runs), all-zero / all-one GAP blocks; dense and sparse live masks (test-first and always-atomic modes)."""
+    rng = np.random.default_rng(seed)
+    vecs = gen.mixed_vectors(rng, 56, 6, p_null=0.03, p_full=0.0, p_gap=0.85) + gen.edge_vectors(6)[:2]
+    dense = bm.BVector(6)
+    for nb in range(6):
+        dense.set_bits(nb, rng.integers(0, 2**32, 2048, dtype=np.uint64).astype(np.uint32) | rng.integers(0, 2**32, 2048, dtype=np.uint64).astype(np.uint32))
+    sparse = bm.BVector.random(6, 0.02, rng)
+    vecs = [dense, sparse] + vecs
+    n = len(vecs)
+    ps = bm.PackedSet.pack(vecs)
+    raw = bm.PackedSet.pack(vecs, gap_flat=False)
+    dset, draw = bm.DeviceSet.upload(ctx, ps), bm.DeviceSet.upload(ctx, raw)
+    for op, g0, g1 in [(bm.OP_OR, list(range(2, n)), None), (bm.OP_OR, list(range(1, n)), None),
+                       (bm.OP_AND_SUB, [0], list(range(2, n))), (bm.OP_AND_SUB, [1], list(range(2, n))),
+                       (bm.OP_AND_SUB, [0, 1], list(range(2, n))), (bm.OP_AND_SUB, [0], list(range(10, 40)))]:
+        for flags in (0, C):
+            a = check_vs_oracle(ctx, ps, op, g0, g1, flags, dset)
+            b = gpu_aggregate(ctx, raw, op, g0, g1, flags, draw)
+            assert np.array_equal(a["blocks"], b["blocks"]) and np.array_equal(a["kind"], b["kind"])
+    dset.free(); draw.free()
 
 
 def test_pipeline_batch(ctx):
