@@ -49,7 +49,7 @@ constexpr int kAggChunk   = 1024;   // group members classified per pass
 #define BMB200_GAP_STAGES (BMB200_CTAS_PER_SM >= 3 ? 3 : 4)
 #endif
 #ifndef BMB200_BIT_UNROLL        /* bit-blocks in flight per thread */
-#define BMB200_BIT_UNROLL (BMB200_CTAS_PER_SM >= 3 ? 4 : 8)
+#define BMB200_BIT_UNROLL 4
 #endif
 #ifndef BMB200_GAP_CHUNK
 #define BMB200_GAP_CHUNK 16384
@@ -75,6 +75,10 @@ constexpr uint32_t kGapMaxBytes   = 2560;                          // gap_max_bu
 constexpr int      kMaxChunks     = (kAggChunk * 4096) / (int)kGapChunkBytes + 4;      // streamed only when span <= n * 4096
 constexpr uint32_t kRingTail      = kGapMaxBytes + 512;           // tail mirror (+ over-read slack of one 64-run step)
 constexpr size_t   kAggDynSmem    = kRingBytes + kRingTail;       // blocks never wrap
+// FLAT consumer: the ring is cut into one private slot per warp; warp w streams chunks w, w+16, ... of the window through
+// its own slot and its own mbarrier -- no cross-warp hand-off, the per-chunk overhead is paid once per slot, not 16 times
+constexpr uint32_t kFlatChunk     = kRingBytes / kAggWarps;       // 4 KB with the 64 KB ring
+static_assert(kFlatChunk % 1024u == 0 && kFlatChunk >= 1024u, "a flat slot is a whole number of 32-lane x 16 B x 2 sweeps");
 
 struct AggParams {
     SetView   set;
@@ -126,6 +130,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t}\n" :: "r"(smem_u32(bar)), "r"(parity), "n"(BMB200_VAR_SLEEP_NS) : "memory");
 }
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity)       // same, raw shared-window address
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP_A:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE_A;\n\t"
+        "nanosleep.u32 %2;\n\t"
+        "bra WAIT_LOOP_A;\n\t"
+        "WAIT_DONE_A:\n\t}\n" :: "r"(bar_addr), "r"(parity), "n"(BMB200_VAR_SLEEP_NS) : "memory");
+}
+__device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v)
+{
+    uint32_t old; asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory"); return old;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -230,12 +250,14 @@ template <bool TEST>
 __device__ __forceinline__ void flat_quad(uint32_t Ls, const uint4& q)
 {
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-    uint32_t a[4], m[4], reach = 0;
+    uint32_t a[4], m[4], nm[4], reach = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint32_t lo = w[i] & 0xffffu, hi = w[i] >> 16;
-        const uint32_t s = lo + 1u, sb = s & 31u, wd = max(hi, lo) - lo;     // wd == 0: no run
+        const uint32_t s = lo + 1u, sb = s & 31u;
+        const uint32_t wd = (uint32_t)max((int)hi - (int)lo, 0);              // wd == 0: no run
         m[i] = bmsk(sb, wd);
+        nm[i] = ~m[i];
         a[i] = Ls + ((s >> 3) & 0x1ffcu);                                     // s == 65536 (pad / terminator) wraps to word 0, mask 0
         reach = max(reach, sb + wd);
     }
@@ -244,10 +266,10 @@ __device__ __forceinline__ void flat_quad(uint32_t Ls, const uint4& q)
 #pragma unroll
         for (int i = 0; i < 4; ++i) v[i] = lds32(a[i]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) reds_and_if(a[i], ~m[i], v[i] & m[i]);
+        for (int i = 0; i < 4; ++i) reds_and_if(a[i], nm[i], v[i] & m[i]);
     } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) reds_and_if(a[i], ~m[i], m[i]);
+        for (int i = 0; i < 4; ++i) reds_and_if(a[i], nm[i], m[i]);
     }
     if (reach > 32u) { flat_pair_tail(Ls, q.x); flat_pair_tail(Ls, q.y); flat_pair_tail(Ls, q.z); flat_pair_tail(Ls, q.w); }
 }
@@ -424,8 +446,8 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
     __shared__ uint32_t s_cfirst[kMaxChunks];    // first list entry starting in each ring chunk
     __shared__ __align__(8) uint64_t s_full[kGapStages];
     __shared__ uint32_t s_done[kGapStages];
-    __shared__ uint32_t s_wcnt[4][kAggWarps];    // per-warp counts of the ordered compaction
-    __shared__ uint32_t s_cnt[4];                // nbit0, nbit1, ngap0, ngap1 of the current chunk
+    __shared__ __align__(8) uint64_t s_wfull[kAggWarps];   // FLAT consumer: one "slot filled" barrier per warp
+    __shared__ uint2 s_wpk[2][kAggWarps];        // per-warp counts of the ordered compaction, packed (bit0 | bit1<<16, gap0 | gap1<<16); one buffer per trip
     __shared__ uint32_t s_stat[4];               // flags, total nbit0, total ngap0, nfull0
     __shared__ uint32_t s_flat[3];               // GAP blocks inside the flat window, first unit behind it, non-FLAT members
     __shared__ uint32_t s_col, s_gap_next;
@@ -443,20 +465,30 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
     uint32_t Ks, ring_s;
     asm volatile("mov.u32 %0, %1;" : "=r"(Ks) : "r"(smem_u32(K)));
     asm volatile("mov.u32 %0, %1;" : "=r"(ring_s) : "r"(smem_u32(ring)));
+    uint32_t done_s, wfull_s;
+    asm volatile("mov.u32 %0, %1;" : "=r"(done_s) : "r"(smem_u32(s_done)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(wfull_s) : "r"(smem_u32(&s_wfull[warp])));
+    uint32_t wseq = 0;       // chunks this warp has pulled through its flat slot so far (mbarrier phase = wseq & 1)
     uint32_t gseq = 0;       // chunks streamed so far by this CTA: chunk g lives in stage g % S, its mbarrier phase is (g / S) & 1
 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kGapStages; ++s) mbar_init(&s_full[s], 1u);
+#pragma unroll
+        for (int w = 0; w < kAggWarps; ++w) mbar_init(&s_wfull[w], 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // work items are claimed one iteration ahead: the round trip of the global atomic hides behind the current column
+    uint32_t next_item = 0;
+    if (tid == 0) next_item = atomicAdd(p.work_counter, 1u);
     __syncthreads();
 
     for (;;) {
-        if (tid == 0) s_col = atomicAdd(p.work_counter, 1u);
+        if (tid == 0) s_col = next_item;
         __syncthreads();
         const uint32_t item = s_col;
         if (item >= p.n_cols * p.n_groups) break;
+        if (tid == 0) next_item = atomicAdd(p.work_counter, 1u);
         // groups of one column are adjacent work items: concurrently running CTAs share the column's source blocks in L2
         const uint32_t colx = item / p.n_groups, grp = item - colx * p.n_groups;
         const uint32_t col = grp * p.n_cols + colx;          // output slot (group-major)
@@ -481,13 +513,15 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
         if (ntot == 0) __syncthreads();
 
         for (uint32_t cs = 0; cs < ntot; cs += kAggChunk) {
-            if (tid < 4) s_cnt[tid] = 0u;
             if (tid == 0) { s_gap_next = 0u; s_flat[0] = 0u; s_flat[1] = 0xffffffffu; s_flat[2] = 0u; }
-            __syncthreads();
             // ---- classification (sort_input_blocks_*): order-preserving compaction into 4 lists ----
+            // per trip: 4 ballots, one packed count pair per warp, ONE block barrier, then every warp scans the 16 warp
+            // counts with shuffles; the running list lengths stay in (uniform) registers
             const uint32_t ce = min(cs + (uint32_t)kAggChunk, ntot);
             uint32_t fl = 0, nfull0 = 0, nonflat = 0;
-            for (uint32_t kb = cs; kb < ce; kb += kAggThreads) {   // uniform trip count (<= 2)
+            uint32_t run01 = 0, run23 = 0;                       // nbit0 | nbit1 << 16, ngap0 | ngap1 << 16 so far
+            int trip = 0;
+            for (uint32_t kb = cs; kb < ce; kb += kAggThreads, trip ^= 1) {   // uniform trip count (<= 2)
                 const uint32_t k = kb + tid;
                 uint32_t kind = 0xffu, rel = 0; bool g1 = false;
                 if (k < ce) {
@@ -502,30 +536,31 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                 const uint32_t lt = (1u << lane) - 1u;
                 const uint32_t m0 = __ballot_sync(0xffffffffu, c0), m1 = __ballot_sync(0xffffffffu, c1);
                 const uint32_t m2 = __ballot_sync(0xffffffffu, c2), m3 = __ballot_sync(0xffffffffu, c3);
-                if (lane == 0) { s_wcnt[0][warp] = __popc(m0); s_wcnt[1][warp] = __popc(m1);
-                                 s_wcnt[2][warp] = __popc(m2); s_wcnt[3][warp] = __popc(m3); }
+                if (lane == 0) s_wpk[trip][warp] = make_uint2(__popc(m0) | (__popc(m1) << 16), __popc(m2) | (__popc(m3) << 16));
                 __syncthreads();
-                uint32_t b0 = s_cnt[0], b1 = s_cnt[1], b2 = s_cnt[2], b3 = s_cnt[3];
-                uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-                for (int w = 0; w < kAggWarps; ++w) {
-                    const uint32_t x0 = s_wcnt[0][w], x1 = s_wcnt[1][w], x2 = s_wcnt[2][w], x3 = s_wcnt[3][w];
-                    if (w < warp) { b0 += x0; b1 += x1; b2 += x2; b3 += x3; }
-                    t0 += x0; t1 += x1; t2 += x2; t3 += x3;
+                uint2 x = (lane < kAggWarps) ? s_wpk[trip][lane] : make_uint2(0u, 0u);
+#pragma unroll
+                for (int o = 1; o < kAggWarps; o <<= 1) {        // inclusive scan over the warps (16-bit fields never overflow: <= 1024)
+                    const uint32_t y0 = __shfl_up_sync(0xffffffffu, x.x, o), y1 = __shfl_up_sync(0xffffffffu, x.y, o);
+                    if (lane >= o) { x.x += y0; x.y += y1; }
                 }
-                if (c0) lst_bit0[b0 + __popc(m0 & lt)] = rel;
-                if (c1) lst_bit1[b1 + __popc(m1 & lt)] = rel;
-                if (c2) lst_gap[b2 + __popc(m2 & lt)] = rel;
-                if (c3) lst_gap[kAggChunk - 1 - (b3 + __popc(m3 & lt))] = rel;
-                __syncthreads();
-                if (tid == 0) { s_cnt[0] += t0; s_cnt[1] += t1; s_cnt[2] += t2; s_cnt[3] += t3; }
+                const uint32_t t01 = __shfl_sync(0xffffffffu, x.x, kAggWarps - 1), t23 = __shfl_sync(0xffffffffu, x.y, kAggWarps - 1);
+                uint32_t e01 = __shfl_sync(0xffffffffu, x.x, (warp + 31) & 31), e23 = __shfl_sync(0xffffffffu, x.y, (warp + 31) & 31);
+                if (warp == 0) { e01 = 0u; e23 = 0u; }
+                e01 += run01; e23 += run23;
+                if (c0) lst_bit0[(e01 & 0xffffu) + __popc(m0 & lt)] = rel;
+                if (c1) lst_bit1[(e01 >> 16) + __popc(m1 & lt)] = rel;
+                if (c2) lst_gap[(e23 & 0xffffu) + __popc(m2 & lt)] = rel;
+                if (c3) lst_gap[kAggChunk - 1 - ((e23 >> 16) + __popc(m3 & lt))] = rel;
+                run01 += t01; run23 += t23;
             }
             fl = __reduce_or_sync(0xffffffffu, fl);
             nfull0 = warp_sum(nfull0);
             nonflat = __reduce_or_sync(0xffffffffu, nonflat);
             if (lane == 0) { if (fl) atomicOr(&s_stat[0], fl); if (nfull0) atomicAdd(&s_stat[3], nfull0); if (nonflat) s_flat[2] = 1u; }
-            __syncthreads();
-            const uint32_t nbit0 = s_cnt[0], nbit1 = s_cnt[1], ngap0 = s_cnt[2], ngap1 = s_cnt[3];
+            const uint32_t nbit0 = run01 & 0xffffu, nbit1 = run01 >> 16, ngap0 = run23 & 0xffffu, ngap1 = run23 >> 16;
             if (tid == 0) { s_stat[1] += nbit0; s_stat[2] += ngap0; }
+            __syncthreads();
 
             // ---- GAP lists: decide flat / stream / gather (uniform), set up the first streamed pass ----
             // pass 0 = group0 list (front), pass 1 = group1 list (back, read reversed so it is in member order)
@@ -588,9 +623,21 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                 bulk_g2s(reinterpret_cast<uint8_t*>(ring) + s * kGapChunkBytes, src, bytes, &s_full[s]);
                 if (extra) bulk_g2s(reinterpret_cast<uint8_t*>(ring) + kRingBytes, src, extra, &s_full[s]);
             };
+            auto flat_fill = [&](uint32_t wlo, uint32_t wbytes, uint32_t c) {   // lane 0 of the owning warp: chunk c -> this warp's slot
+                const uint32_t off = c * kFlatChunk;
+                const uint32_t bytes = min(kFlatChunk, wbytes - off);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(wfull_s), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(ring_s + (uint32_t)warp * kFlatChunk), "l"(reinterpret_cast<const uint8_t*>(gseg) + (size_t)wlo * 16u + off),
+                                "r"(bytes), "r"(wfull_s) : "memory");
+            };
             auto stream_setup = [&](int q, bool isflat) {               // all threads; ends with a block barrier
                 const uint32_t n = q ? ngap1 : ngap0, wlo = q ? lo1 : lo0, nc = q ? nc1 : nc0, wbytes = q ? wb1 : wb0;
-                if (!isflat) {
+                if (isflat) {      // the ring is idle here (block barrier at the end of the previous pass / column)
+                    if (lane == 0 && (uint32_t)warp * kFlatChunk < wbytes) { fence_proxy_async(); flat_fill(wlo, wbytes, (uint32_t)warp); }
+                    return;
+                }
+                {
                     for (uint32_t i = tid; i < n; i += kAggThreads) {
                         const uint32_t ei = (q ? lst_gap[kAggChunk - 1 - i] : lst_gap[i]) & kRelMask;
                         const uint32_t ci = ((ei - wlo) * 16u) / kGapChunkBytes;
@@ -612,9 +659,9 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                 __syncwarp();
                 if (lane == 0) {
                     __threadfence_block();
-                    const uint32_t old = atomicAdd(&s_done[s], 1u);
+                    const uint32_t old = atoms_add(done_s + 4u * s, 1u);
                     if (old == kAggWarps - 1) {          // last warp out re-arms the stage
-                        atomicExch(&s_done[s], 0u);
+                        sts32(done_s + 4u * s, 0u);      // nobody touches the counter again before the refill has landed
                         if (r + kGapStages < nc) { __threadfence_block(); fence_proxy_async(); issue_fill(wlo, wbytes, r + kGapStages, mirror); }
                     }
                 }
@@ -644,33 +691,27 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                 }
                 gseq += nc;
             };
-            auto flat_consume = [&](int q) {                     // per warp, no block barriers inside
-                const uint32_t wlo = q ? lo1 : lo0, nc = q ? nc1 : nc0, wbytes = q ? wb1 : wb0;
-                for (uint32_t r = 0; r < nc; ++r) {
-                    const uint32_t g = gseq + r, s = g % kGapStages;
-                    mbar_wait(&s_full[s], (g / kGapStages) & 1u);
-                    const uint32_t bytes = min(kGapChunkBytes, wbytes - r * kGapChunkBytes);
+            auto flat_consume = [&](int q) {                     // per warp, no cross-warp synchronisation at all
+                const uint32_t wlo = q ? lo1 : lo0, wbytes = q ? wb1 : wb0;
+                const uint32_t nfc = (wbytes + kFlatChunk - 1u) / kFlatChunk;
+                const uint32_t src = ring_s + (uint32_t)warp * kFlatChunk + (uint32_t)lane * 16u;
+                for (uint32_t c = (uint32_t)warp; c < nfc; c += kAggWarps) {
+                    mbar_wait_a(wfull_s, wseq & 1u); ++wseq;
+                    const uint32_t bytes = min(kFlatChunk, wbytes - c * kFlatChunk);
                     // 1024-bit sample of L: below 25 % alive the test-first form wins (one shared load, rarely an atomic)
-                    const uint32_t smp = lds32(Ks + ((((uint32_t)lane * 65u + (uint32_t)warp * 5u + r) & (kBlockWords - 1u)) << 2));
+                    const uint32_t smp = lds32(Ks + ((((uint32_t)lane * 65u + c * 7u) & (kBlockWords - 1u)) << 2));
                     const bool test = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(smp)) < 256u;
-                    const uint32_t off = (uint32_t)tid * 16u;
-                    const uint32_t src = ring_s + s * kGapChunkBytes + off;
-                    constexpr uint32_t kHalf = kAggThreads * 16u;
-                    static_assert(kGapChunkBytes % kHalf == 0, "chunk must be a whole number of 512-thread sweeps");
-                    uint4 q4[kGapChunkBytes / kHalf];
-#pragma unroll
-                    for (uint32_t h = 0; h < kGapChunkBytes / kHalf; ++h)
-                        q4[h] = (off + h * kHalf < bytes) ? lds128(src + h * kHalf) : make_uint4(0u, 0u, 0u, 0u);
-                    if (test) {
-#pragma unroll
-                        for (uint32_t h = 0; h < kGapChunkBytes / kHalf; ++h) flat_quad<true>(Ks, q4[h]);
-                    } else {
-#pragma unroll
-                        for (uint32_t h = 0; h < kGapChunkBytes / kHalf; ++h) flat_quad<false>(Ks, q4[h]);
+#pragma unroll 1
+                    for (uint32_t h = 0; h < kFlatChunk; h += 1024u) {   // 32 lanes x 16 B x 2 per sweep
+                        const uint32_t off = (uint32_t)lane * 16u + h;
+                        const uint4 qa = (off < bytes) ? lds128(src + h) : make_uint4(0u, 0u, 0u, 0u);
+                        const uint4 qb = (off + 512u < bytes) ? lds128(src + h + 512u) : make_uint4(0u, 0u, 0u, 0u);
+                        if (test) { flat_quad<true>(Ks, qa);  flat_quad<true>(Ks, qb); }
+                        else      { flat_quad<false>(Ks, qa); flat_quad<false>(Ks, qb); }
                     }
-                    stage_release(s, r, nc, wlo, wbytes, false);
+                    __syncwarp();
+                    if (lane == 0 && c + kAggWarps < nfc) { __threadfence_block(); fence_proxy_async(); flat_fill(wlo, wbytes, c + kAggWarps); }
                 }
-                gseq += nc;
             };
             auto gather_pass = [&](int q, uint32_t want) {       // per warp; dynamic block distribution
                 const uint32_t n = q ? ngap1 : ngap0;

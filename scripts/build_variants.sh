@@ -3,10 +3,11 @@
 set -e
 cd "$(dirname "$0")/.."
 mkdir -p scripts/_bin
+rm -f scripts/_bin/*.so
 build() { name=$1; shift; nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared "$@" -o scripts/_bin/libbmb200_$name.so bitmagic_b200/csrc/capi.cu -lcudart & }
-build ctas2
-build ctas3 -DBMB200_CTAS_PER_SM=3
-build ctas3u8 -DBMB200_CTAS_PER_SM=3 -DBMB200_BIT_UNROLL=8
-build ctas3g32 -DBMB200_CTAS_PER_SM=3 -DBMB200_LANES_PER_BLOCK=32
+build w4u4 -DBMB200_BIT_UNROLL=4
+build w4u8
+build w3u4 -DBMB200_BIT_UNROLL=4 -DBMB200_GAP_STAGES=3
+build w2u4 -DBMB200_BIT_UNROLL=4 -DBMB200_GAP_STAGES=2
 wait
 ls -la scripts/_bin/

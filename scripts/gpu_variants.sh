@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/pytest_gpu.log
-BMB200_LIB=$PWD/scripts/_bin/libbmb200_ctas3.so timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/pytest_gpu_ctas3.log
 run() { v=$1; w=$2
   BMB200_LIB=$PWD/scripts/_bin/libbmb200_$v.so timeout 300 python bench.py --workload $w --steps 10 --no-e2e --no-cpu 2>&1 | tail -1 > gpurun_out/var_${v}_$w.log
   python - <<PY
@@ -13,4 +12,4 @@ except Exception as e:
     print('$v $w', 'FAILED', open('gpurun_out/var_${v}_$w.log').read()[-400:])
 PY
 }
-for w in c3 c5 c2; do for v in ctas2 ctas3 ctas3u8 ctas3g32; do run $v $w; done; done 2>&1 | tee gpurun_out/variants.txt
+for w in ${WORKLOADS:-c3 c5 c2}; do for v in $VARIANTS; do run $v $w; done; done 2>&1 | tee gpurun_out/variants.txt

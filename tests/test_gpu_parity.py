@@ -261,6 +261,23 @@ def test_large_groups_chunked_classification(ctx):
     dset.free()
 
 
+def test_flat_windows_over_several_classification_passes(ctx):
+    """C5 shape in small: 2600 sparse GAP vectors -> three member passes per column, each streaming its own flat window;
+    the live mask goes from dense (always-atomic form) to sparse (test-first form) inside one column."""
+    nv, nbk = 2600, 2
+    dens = np.full(nv, 0.0025)
+    dens[::97] = 0.006
+    seed = np.arange(7000, 7000 + nv, dtype=np.uint64)
+    dset = bm.DeviceSet.synth(ctx, nv, nbk, dens, seed, True)
+    ps = dset.download()
+    assert (ps.kinds() == bm.BLK_GAP).all()
+    check_vs_oracle(ctx, ps, bm.OP_OR, list(range(nv)), None, C, dset)
+    check_vs_oracle(ctx, ps, bm.OP_OR, list(range(5, 2300)), None, 0, dset)
+    check_vs_oracle(ctx, ps, bm.OP_AND_SUB, [0, 1, 2], list(range(3, nv)), C, dset)
+    check_vs_oracle(ctx, ps, bm.OP_AND_SUB, [7], list(range(1000, 2400)), C, dset)
+    dset.free()
+
+
 def test_upload_vectors_and_host_mirror_api(ctx):
     """bm::aggregator-style surface: add/combine_*; 2-operand bit_*; count_*."""
     rng = np.random.default_rng(9)
