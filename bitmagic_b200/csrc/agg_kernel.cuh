@@ -77,7 +77,11 @@ constexpr uint32_t kRingTail      = kGapMaxBytes + 512;           // tail mirror
 constexpr size_t   kAggDynSmem    = kRingBytes + kRingTail;       // blocks never wrap
 // FLAT consumer: the ring is cut into one private slot per warp; warp w streams chunks w, w+16, ... of the window through
 // its own slot and its own mbarrier -- no cross-warp hand-off, the per-chunk overhead is paid once per slot, not 16 times
-constexpr uint32_t kFlatChunk     = kRingBytes / kAggWarps;       // 4 KB with the 64 KB ring
+#ifndef BMB200_FLAT_SLOTS         /* private slots per warp: 2 = one being consumed while the other one fills */
+#define BMB200_FLAT_SLOTS 2
+#endif
+constexpr uint32_t kFlatSlots     = BMB200_FLAT_SLOTS;
+constexpr uint32_t kFlatChunk     = kRingBytes / (kAggWarps * kFlatSlots);   // 2 KB with the 64 KB ring
 static_assert(kFlatChunk % 1024u == 0 && kFlatChunk >= 1024u, "a flat slot is a whole number of 32-lane x 16 B x 2 sweeps");
 
 struct AggParams {
@@ -446,7 +450,8 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
     __shared__ uint32_t s_cfirst[kMaxChunks];    // first list entry starting in each ring chunk
     __shared__ __align__(8) uint64_t s_full[kGapStages];
     __shared__ uint32_t s_done[kGapStages];
-    __shared__ __align__(8) uint64_t s_wfull[kAggWarps];   // FLAT consumer: one "slot filled" barrier per warp
+    __shared__ __align__(8) uint64_t s_wfull[kAggWarps * kFlatSlots];   // FLAT consumer: one "slot filled" barrier per private slot
+    __shared__ uint32_t s_flat_next;             // next unclaimed chunk of the flat window
     __shared__ uint2 s_wpk[2][kAggWarps];        // per-warp counts of the ordered compaction, packed (bit0 | bit1<<16, gap0 | gap1<<16); one buffer per trip
     __shared__ uint32_t s_stat[4];               // flags, total nbit0, total ngap0, nfull0
     __shared__ uint32_t s_flat[3];               // GAP blocks inside the flat window, first unit behind it, non-FLAT members
@@ -467,15 +472,16 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
     asm volatile("mov.u32 %0, %1;" : "=r"(ring_s) : "r"(smem_u32(ring)));
     uint32_t done_s, wfull_s;
     asm volatile("mov.u32 %0, %1;" : "=r"(done_s) : "r"(smem_u32(s_done)));
-    asm volatile("mov.u32 %0, %1;" : "=r"(wfull_s) : "r"(smem_u32(&s_wfull[warp])));
-    uint32_t wseq = 0;       // chunks this warp has pulled through its flat slot so far (mbarrier phase = wseq & 1)
+    asm volatile("mov.u32 %0, %1;" : "=r"(wfull_s) : "r"(smem_u32(&s_wfull[warp * kFlatSlots])));
+    uint32_t wphase = 0;     // bit k = phase of this warp's slot k barrier
+    uint32_t wchunk[kFlatSlots];   // chunk in flight / resident in slot k (warp-uniform)
     uint32_t gseq = 0;       // chunks streamed so far by this CTA: chunk g lives in stage g % S, its mbarrier phase is (g / S) & 1
 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kGapStages; ++s) mbar_init(&s_full[s], 1u);
 #pragma unroll
-        for (int w = 0; w < kAggWarps; ++w) mbar_init(&s_wfull[w], 1u);
+        for (int w = 0; w < kAggWarps * (int)kFlatSlots; ++w) mbar_init(&s_wfull[w], 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // work items are claimed one iteration ahead: the round trip of the global atomic hides behind the current column
@@ -503,6 +509,7 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
         if (tid < 4) s_stat[tid] = 0u;
         uint4 acc0 = kIsAnd ? make_uint4(~0u, ~0u, ~0u, ~0u) : make_uint4(0u, 0u, 0u, 0u);
         uint4 acc1 = make_uint4(0u, 0u, 0u, 0u);   // union of SUB-group bit-blocks
+        bool flat_test = false;                    // FLAT consumer form of this column (warp-uniform): test-first once L is sparse
 
         const uint32_t* drow = p.set.desc + (size_t)nb * M;
         const uint4* bseg = reinterpret_cast<const uint4*>(p.set.bit_pool)
@@ -513,7 +520,7 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
         if (ntot == 0) __syncthreads();
 
         for (uint32_t cs = 0; cs < ntot; cs += kAggChunk) {
-            if (tid == 0) { s_gap_next = 0u; s_flat[0] = 0u; s_flat[1] = 0xffffffffu; s_flat[2] = 0u; }
+            if (tid == 0) { s_gap_next = 0u; s_flat_next = 0u; s_flat[0] = 0u; s_flat[1] = 0xffffffffu; s_flat[2] = 0u; }
             // ---- classification (sort_input_blocks_*): order-preserving compaction into 4 lists ----
             // per trip: 4 ballots, one packed count pair per warp, ONE block barrier, then every warp scans the 16 warp
             // counts with shuffles; the running list lengths stay in (uniform) registers
@@ -623,18 +630,32 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                 bulk_g2s(reinterpret_cast<uint8_t*>(ring) + s * kGapChunkBytes, src, bytes, &s_full[s]);
                 if (extra) bulk_g2s(reinterpret_cast<uint8_t*>(ring) + kRingBytes, src, extra, &s_full[s]);
             };
-            auto flat_fill = [&](uint32_t wlo, uint32_t wbytes, uint32_t c) {   // lane 0 of the owning warp: chunk c -> this warp's slot
-                const uint32_t off = c * kFlatChunk;
-                const uint32_t bytes = min(kFlatChunk, wbytes - off);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(wfull_s), "r"(bytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             :: "r"(ring_s + (uint32_t)warp * kFlatChunk), "l"(reinterpret_cast<const uint8_t*>(gseg) + (size_t)wlo * 16u + off),
-                                "r"(bytes), "r"(wfull_s) : "memory");
+            // FLAT: warps claim pieces of the window from a shared counter (one claim = kFlatSlots consecutive chunks, one per
+            // private slot) and pull them through their slots
+            auto flat_claim = [&]() -> uint32_t {                // whole warp; returns the first chunk of the claimed piece
+                uint32_t c = 0;
+                if (lane == 0) c = atomicAdd(&s_flat_next, 1u) * kFlatSlots;
+                return __shfl_sync(0xffffffffu, c, 0);
+            };
+            auto flat_fill = [&](uint32_t wlo, uint32_t wbytes, uint32_t c, uint32_t k) {   // whole warp: chunk c -> slot k (caller checked c < nfc)
+                if (lane == 0) {
+                    const uint32_t off = c * kFlatChunk;
+                    const uint32_t bytes = min(kFlatChunk, wbytes - off);
+                    const uint32_t bar = wfull_s + 8u * k;
+                    fence_proxy_async();
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 :: "r"(ring_s + ((uint32_t)warp * kFlatSlots + k) * kFlatChunk),
+                                    "l"(reinterpret_cast<const uint8_t*>(gseg) + (size_t)wlo * 16u + off), "r"(bytes), "r"(bar) : "memory");
+                }
             };
             auto stream_setup = [&](int q, bool isflat) {               // all threads; ends with a block barrier
                 const uint32_t n = q ? ngap1 : ngap0, wlo = q ? lo1 : lo0, nc = q ? nc1 : nc0, wbytes = q ? wb1 : wb0;
                 if (isflat) {      // the ring is idle here (block barrier at the end of the previous pass / column)
-                    if (lane == 0 && (uint32_t)warp * kFlatChunk < wbytes) { fence_proxy_async(); flat_fill(wlo, wbytes, (uint32_t)warp); }
+                    const uint32_t nfc = (wbytes + kFlatChunk - 1u) / kFlatChunk;
+                    const uint32_t c0 = flat_claim();
+#pragma unroll
+                    for (uint32_t k = 0; k < kFlatSlots; ++k) { wchunk[k] = c0 + k; if (c0 + k < nfc) flat_fill(wlo, wbytes, c0 + k, k); }
                     return;
                 }
                 {
@@ -691,26 +712,46 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                 }
                 gseq += nc;
             };
-            auto flat_consume = [&](int q) {                     // per warp, no cross-warp synchronisation at all
-                const uint32_t wlo = q ? lo1 : lo0, wbytes = q ? wb1 : wb0;
-                const uint32_t nfc = (wbytes + kFlatChunk - 1u) / kFlatChunk;
-                const uint32_t src = ring_s + (uint32_t)warp * kFlatChunk + (uint32_t)lane * 16u;
-                for (uint32_t c = (uint32_t)warp; c < nfc; c += kAggWarps) {
-                    mbar_wait_a(wfull_s, wseq & 1u); ++wseq;
-                    const uint32_t bytes = min(kFlatChunk, wbytes - c * kFlatChunk);
-                    // 1024-bit sample of L: below 25 % alive the test-first form wins (one shared load, rarely an atomic)
-                    const uint32_t smp = lds32(Ks + ((((uint32_t)lane * 65u + c * 7u) & (kBlockWords - 1u)) << 2));
-                    const bool test = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(smp)) < 256u;
-#pragma unroll 1
-                    for (uint32_t h = 0; h < kFlatChunk; h += 1024u) {   // 32 lanes x 16 B x 2 per sweep
-                        const uint32_t off = (uint32_t)lane * 16u + h;
-                        const uint4 qa = (off < bytes) ? lds128(src + h) : make_uint4(0u, 0u, 0u, 0u);
-                        const uint4 qb = (off + 512u < bytes) ? lds128(src + h + 512u) : make_uint4(0u, 0u, 0u, 0u);
+            auto flat_sweep = [&](uint32_t src, uint32_t bytes, bool test) {       // one slot: 32 lanes x 16 B x 2 per step
+                if (bytes == kFlatChunk) {
+#pragma unroll
+                    for (uint32_t h = 0; h < kFlatChunk; h += 1024u) {
+                        const uint4 qa = lds128(src + h), qb = lds128(src + h + 512u);
                         if (test) { flat_quad<true>(Ks, qa);  flat_quad<true>(Ks, qb); }
                         else      { flat_quad<false>(Ks, qa); flat_quad<false>(Ks, qb); }
                     }
-                    __syncwarp();
-                    if (lane == 0 && c + kAggWarps < nfc) { __threadfence_block(); fence_proxy_async(); flat_fill(wlo, wbytes, c + kAggWarps); }
+                } else {                                                            // last chunk of the window
+#pragma unroll 1
+                    for (uint32_t h = (uint32_t)lane * 16u; h < bytes; h += 512u) {
+                        const uint4 qa = lds128(src + h - (uint32_t)lane * 16u);
+                        if (test) flat_quad<true>(Ks, qa); else flat_quad<false>(Ks, qa);
+                    }
+                }
+            };
+            auto flat_consume = [&](int q) {                     // per warp, no cross-warp synchronisation at all
+                const uint32_t wlo = q ? lo1 : lo0, wbytes = q ? wb1 : wb0;
+                const uint32_t nfc = (wbytes + kFlatChunk - 1u) / kFlatChunk;
+                for (;;) {
+                    if (wchunk[0] >= nfc) break;                 // chunks of a piece are consecutive: slot 0 empty = nothing left
+#pragma unroll
+                    for (uint32_t k = 0; k < kFlatSlots; ++k) {
+                        const uint32_t c = wchunk[k];
+                        if (c < nfc) {
+                            mbar_wait_a(wfull_s + 8u * k, (wphase >> k) & 1u); wphase ^= 1u << k;
+                            const uint32_t bytes = min(kFlatChunk, wbytes - c * kFlatChunk);
+                            if (!flat_test) {   // 1024-bit sample of L: below 25 % alive the test-first form wins (one shared load, rarely
+                                                // an atomic); bits of L only ever get cleared, so the switch is one-way per column
+                                const uint32_t smp = lds32(Ks + ((((uint32_t)lane * 65u + c * 7u) & (kBlockWords - 1u)) << 2));
+                                flat_test = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(smp)) < 256u;
+                            }
+                            flat_sweep(ring_s + ((uint32_t)warp * kFlatSlots + k) * kFlatChunk + (uint32_t)lane * 16u, bytes, flat_test);
+                            __syncwarp();
+                        }
+                        // slot k is free: the next piece is claimed when slot 0 frees up, its chunk k goes into slot k
+                        const uint32_t cn = (k == 0) ? flat_claim() : wchunk[0] + k;
+                        wchunk[k] = cn;
+                        if (cn < nfc) flat_fill(wlo, wbytes, cn, k);
+                    }
                 }
             };
             auto gather_pass = [&](int q, uint32_t want) {       // per warp; dynamic block distribution

@@ -5,9 +5,7 @@ cd "$(dirname "$0")/.."
 mkdir -p scripts/_bin
 rm -f scripts/_bin/*.so
 build() { name=$1; shift; nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared "$@" -o scripts/_bin/libbmb200_$name.so bitmagic_b200/csrc/capi.cu -lcudart & }
-build w4u4 -DBMB200_BIT_UNROLL=4
-build w4u8
-build w3u4 -DBMB200_BIT_UNROLL=4 -DBMB200_GAP_STAGES=3
-build w2u4 -DBMB200_BIT_UNROLL=4 -DBMB200_GAP_STAGES=2
+build e1
+build e2 -DBMB200_FLAT_SLOTS=2
 wait
 ls -la scripts/_bin/
