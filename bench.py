@@ -128,8 +128,8 @@ def measured_peak_gbs():
 
 def profiled_traffic(workload: str):
     """dram__bytes_read+write per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
-    f = ROOT / "profiles" / "r01" / "ncu_agg_kernel_v6.json"
-    key = {"c3": "c3_agg_kernel_and_sub", "c2": "c2_agg_kernel_or"}.get(workload)
+    f = ROOT / "profiles" / "r01" / "ncu_agg_kernel.json"
+    key = {"c3": "c3_agg_kernel_and_sub", "c2": "c2_agg_kernel_or", "c5": "c5_agg_kernel_or"}.get(workload)
     try:
         d = json.loads(f.read_text())[key]
         def gb(x):
@@ -397,7 +397,7 @@ def main():
             "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if (args.cols and args.cols != w["n_blocks"]) else profiled_traffic(args.workload),
-                         "traffic_source": "profiles/r01/ncu_agg_kernel_v6.json (ncu --set full, same command, full-size shard)",
+                         "traffic_source": "profiles/r01/ncu_agg_kernel.json (ncu --set full, same command, full-size shard)",
                          "kernel": "agg_kernel<%s>" % w["op"], "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "peak_source": peak_src},
             "cpu_baseline": cpu,

@@ -35,6 +35,7 @@ SYMBOLS = [
     "bmb200_result_free", "bmb200_aggregate_host", "bmb200_rs_build", "bmb200_rs_export", "bmb200_rs_total",
     "bmb200_rank_batch", "bmb200_select_batch", "bmb200_rank_batch_dev", "bmb200_select_batch_dev",
     "bmb200_rs_free", "bmb200_rs_rebuild", "bmb200_aggregate_batch", "bmb200_result_group_totals", "bmb200_result_or_target",
+    "bmb200_scan",
 ]
 
 
@@ -65,6 +66,19 @@ class BatchArgsC(C.Structure):
         ("members", C.c_void_p), ("offsets", C.c_void_p),
         ("nb_from", C.c_uint32), ("nb_to", C.c_uint32),
     ]
+
+
+class ScanArgsC(C.Structure):
+    _fields_ = [
+        ("plane0", C.c_uint32), ("n_planes", C.c_uint32), ("universe", C.c_uint32),
+        ("pred", C.c_int32), ("flags", C.c_uint32),
+        ("values", C.c_void_p), ("n_values", C.c_uint32),
+        ("nb_from", C.c_uint32), ("nb_to", C.c_uint32),
+    ]
+
+
+SCAN_EQ, SCAN_GT, SCAN_GE, SCAN_LT, SCAN_LE, SCAN_RANGE = range(6)
+NO_UNIVERSE = 0xFFFFFFFF
 
 
 class ResultMetaC(C.Structure):
@@ -354,6 +368,21 @@ def aggregate_batch(ctx: Context, dset: DeviceSet, op: int, groups, flags: int =
     res = result if result is not None else DeviceResult(ctx)
     ctx.check(lib().bmb200_aggregate_batch(ctx._h, dset._h, C.byref(args), C.byref(res._h)), "aggregate_batch")
     res.n_cols = ((nb_to if nb_to else dset.n_blocks) - nb_from) * len(groups)
+    return res
+
+
+def scan(ctx: Context, dset: DeviceSet, pred: int, values, plane0: int, n_planes: int, universe: int = NO_UNIVERSE,
+         flags: int = 0, nb_from: int = 0, nb_to: int = 0, result: DeviceResult | None = None) -> DeviceResult:
+    """bmb200_scan: bit-sliced comparison of the sparse vector whose plane j is set vector plane0 + j against every search
+    value (SCAN_RANGE: rows of (lo, hi)); the result has n_values * n_cols columns, value-major."""
+    vals = np.ascontiguousarray(values, dtype=np.uint64)
+    nv = vals.shape[0] if pred == SCAN_RANGE else vals.size
+    if pred == SCAN_RANGE and (vals.ndim != 2 or vals.shape[1] != 2):
+        raise ValueError("SCAN_RANGE takes an array of (lo, hi) rows")
+    args = ScanArgsC(int(plane0), int(n_planes), int(universe), int(pred), int(flags), ptr(vals), int(nv), int(nb_from), int(nb_to))
+    res = result if result is not None else DeviceResult(ctx)
+    ctx.check(lib().bmb200_scan(ctx._h, dset._h, C.byref(args), C.byref(res._h)), "scan")
+    res.n_cols = ((nb_to if nb_to else dset.n_blocks) - nb_from) * int(nv)
     return res
 
 

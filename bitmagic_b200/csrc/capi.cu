@@ -10,6 +10,7 @@
 
 #include "agg_kernel.cuh"
 #include "aux_kernels.cuh"
+#include "scan_kernel.cuh"
 
 using namespace bmb200;
 
@@ -630,6 +631,70 @@ int bmb200_aggregate(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_agg_ar
     const uint32_t off[3] = {0u, a->n0, a->n0 + n1};
     bmb200_batch_args b{a->op, a->flags & ~BMB200_F_OR_TARGET, 1u, mem.data(), off, a->nb_from, a->nb_to};
     return bmb200_aggregate_batch(ctx, set, &b, inout);
+}
+
+int bmb200_scan(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_scan_args* a, bmb200_result** inout)
+{
+    if (!ctx || !set || !a || !inout || set->ctx != ctx || !a->values || !a->n_values) return BMB200_ERR_BADARG;
+    if (a->pred < BMB200_SCAN_EQ || a->pred > BMB200_SCAN_RANGE || !a->n_planes || a->n_planes > 64u) return BMB200_ERR_BADARG;
+    if ((uint64_t)a->plane0 + a->n_planes > set->v.n_vec) return BMB200_ERR_RANGE;
+    if (a->universe != 0xffffffffu && a->universe >= set->v.n_vec) return BMB200_ERR_RANGE;
+    const uint32_t nb_to = a->nb_to ? a->nb_to : set->v.n_blocks;
+    if (a->nb_from >= nb_to || nb_to > set->v.n_blocks) return BMB200_ERR_RANGE;
+    const uint32_t cols = nb_to - a->nb_from, nv = a->n_values;
+    const uint64_t tot_cols = (uint64_t)cols * nv;
+    if (tot_cols > 0x7fffffffull) return BMB200_ERR_RANGE;
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t n_cols = (uint32_t)tot_cols;
+    const bool store = !(a->flags & BMB200_F_COUNT_ONLY);
+    const bool compress = (a->flags & BMB200_F_OPT_COMPRESS) != 0;
+
+    bmb200_result* r = *inout;
+    if (r && (r->ctx != ctx || r->n_cols != n_cols || r->n_groups != nv || (store && !r->blocks) ||
+              (store && compress && !r->gaps) || r->or_blocks)) {
+        bmb200_result_free(r); r = nullptr; *inout = nullptr;
+    }
+    if (!r) {
+        int rc = result_alloc(ctx, n_cols, nv, store, store && compress, false, &r);
+        if (rc) return rc;
+    }
+    r->has_blocks = store; r->compress = compress; r->gaps_ready = false;
+
+    // search values -> device through the (pinned) group staging buffer, 2 words per value
+    const size_t nvals = (size_t)nv * (a->pred == BMB200_SCAN_RANGE ? 2 : 1), nwords = 2 * nvals;
+    if (nwords > ctx->group_cap) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(ctx->d_group); if (ctx->h_group) cudaFreeHost(ctx->h_group);
+        ctx->d_group = nullptr; ctx->h_group = nullptr; ctx->group_cap = 0;
+        size_t cap = nwords < 1024 ? 1024 : nwords;
+        if (cudaMalloc((void**)&ctx->d_group, cap * 4) != cudaSuccess || cudaMallocHost((void**)&ctx->h_group, cap * 4) != cudaSuccess) {
+            ctx->last_err = "group buffer allocation"; if (!*inout) bmb200_result_free(r); return BMB200_ERR_BADALLOC;
+        }
+        ctx->group_cap = cap;
+    }
+    ctx->last_group.clear();                   // the buffer no longer holds aggregate member ids
+    cudaStreamSynchronize(ctx->stream);        // the staging buffer may still feed a previous launch
+    memcpy(ctx->h_group, a->values, nvals * 8);
+    CU(cudaMemcpyAsync(ctx->d_group, ctx->h_group, nvals * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_work, 0, 4, ctx->stream));
+    CU(cudaMemsetAsync(r->total, 0, 8 * (size_t)nv, ctx->stream));
+
+    ScanParams sp{};
+    AggParams& p = sp.out;
+    p.set = set->v; p.n_groups = nv; p.nb_from = a->nb_from; p.n_cols = cols;
+    p.compress = compress ? 1u : 0u; p.store_blocks = store ? 1u : 0u;
+    p.blocks = r->blocks; p.popcnt = r->popcnt; p.digest = r->digest; p.nruns = r->nruns; p.kind = r->kind; p.gaps = r->gaps;
+    p.total = r->total; p.work_counter = ctx->d_work; p.or_blocks = nullptr;
+    sp.plane0 = a->plane0; sp.n_planes = a->n_planes; sp.universe = a->universe; sp.pred = (uint32_t)a->pred;
+    sp.values = reinterpret_cast<const uint64_t*>(ctx->d_group);
+    uint32_t grid = (uint32_t)(ctx->sm_count * ctx->agg_ctas_per_sm);
+    if (grid > n_cols) grid = n_cols;
+    scan_kernel<<<grid, kAggThreads, 0, ctx->stream>>>(sp);
+    int rc = after_launch(ctx);
+    if (rc) { if (!*inout) bmb200_result_free(r); return rc; }
+    *inout = r;
+    if (store && compress) r->gaps_ready = true;
+    return BMB200_OK;
 }
 
 int bmb200_result_group_totals(bmb200_result* r, uint64_t* totals, uint32_t n_groups)

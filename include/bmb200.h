@@ -19,6 +19,8 @@
  *   bmb200_aggregate  OP_XOR      <- bvector::bit_xor              src/bm.h:6072 (bit_block_xor src/bmfunc.h:9191)
  *   BMB200_F_COUNT_ONLY           <- bm::count_and/or/xor/sub      src/bmalgo.h:48-51, pipeline counts src/bmaggregator.h:1397
  *   bmb200_result_optimize        <- blocks_manager::opt_copy_bit_block src/bmblocks.h:1355-1409
+ *   bmb200_scan                   <- sparse_vector_scanner::find_eq/find_gt/find_ge/find_lt/find_le/find_range
+ *                                                                   src/bmsparsevec_algo.h:1083-1182,2593-2632,4360-4395
  *   bmb200_rs_build               <- bvector::build_rs_index       src/bm.h:2531-2660, rs_index src/bmrs.h:688-715
  *   bmb200_rank_batch             <- bvector::count_to             src/bm.h:3120-3167
  *   bmb200_select_batch           <- bvector::select               src/bm.h:5350-5385
@@ -228,6 +230,32 @@ int bmb200_result_fetch(bmb200_result* res, uint8_t* kind, uint64_t* off,
 int bmb200_result_device_ptrs(const bmb200_result* res, void** blocks, void** popcnt,
                               void** digest, void** flag, uint32_t* n_cols);
 int bmb200_result_free(bmb200_result* res);
+
+/* ---------------- sparse-vector scanner (bit-sliced comparison) ---------------- */
+/* sparse_vector_scanner<SV> searches over the bit-planes ("slices", bm::sparse_vector::get_slice(i),
+ * src/bmsparsevec.h) of ONE unsigned sparse vector stored as vectors of a set: plane j (bit j of every element) is set
+ * vector plane0 + j.  One launch answers n_values searches; the result has n_values * n_cols columns, value-major,
+ * exactly like a pipeline batch (per-value cardinalities through bmb200_result_group_totals). */
+#define BMB200_SCAN_EQ     0   /* find_eq    src/bmsparsevec_algo.h:1083  elements == value                    */
+#define BMB200_SCAN_GT     1   /* find_gt    :1135                        elements >  value                    */
+#define BMB200_SCAN_GE     2   /* find_ge    :1144                                                             */
+#define BMB200_SCAN_LT     3   /* find_lt    :1154                                                             */
+#define BMB200_SCAN_LE     4   /* find_le    :1163                                                             */
+#define BMB200_SCAN_RANGE  5   /* find_range :1174  values[2k] <= element <= values[2k+1] (reversed bounds are swapped, :2871) */
+typedef struct bmb200_scan_args {
+    uint32_t        plane0;     /* first plane vector inside the set                                          */
+    uint32_t        n_planes;   /* 1..64 (sparse_vector::effective_slices())                                  */
+    uint32_t        universe;   /* set vector with the searchable indexes: [0, size) for a non-nullable vector,
+                                 * the NOT-NULL plane for a nullable one (what finalize_search_result and
+                                 * invert_internal apply, :2426,1686); 0xffffffff = every index of the columns */
+    int32_t         pred;       /* BMB200_SCAN_*                                                              */
+    uint32_t        flags;      /* BMB200_F_COUNT_ONLY / BMB200_F_OPT_COMPRESS                                */
+    const uint64_t* values;     /* HOST: n_values search values (RANGE: 2 * n_values, lo then hi)             */
+    uint32_t        n_values;
+    uint32_t        nb_from;
+    uint32_t        nb_to;      /* 0 == n_blocks */
+} bmb200_scan_args;
+int bmb200_scan(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_scan_args* args, bmb200_result** inout);
 
 /* end-to-end convenience: HOST packed set in, HOST metadata out, in one call
  * (H2D of the set, kernel, D2H of kind/popcnt/digest [+ result blocks when bits != NULL]) */

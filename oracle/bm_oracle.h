@@ -43,6 +43,10 @@ int orc_aggregate(const bmb200_packed_set* set, const bmb200_agg_args* args,
                   uint8_t* kind, uint32_t* popcnt, uint64_t* digest, uint32_t* nruns,
                   uint32_t* blocks, uint16_t* gaps);
 
+/* ---- sparse-vector scanner searches (bmb200_scan): n_values * n_cols columns, value-major ---- */
+int orc_scan(const bmb200_packed_set* set, const bmb200_scan_args* args,
+             uint8_t* kind, uint32_t* popcnt, uint64_t* digest, uint32_t* nruns, uint32_t* blocks, uint16_t* gaps);
+
 /* ---- rank / select over vector `vec` of a packed set ---- */
 int orc_rs_build(const bmb200_packed_set* set, uint32_t vec,
                  uint32_t* bcount, uint64_t* sub_count, uint64_t* sb_count);

@@ -26,6 +26,8 @@
 #include "bmaggregator.h"
 #include "bmalgo.h"
 #include "bmrs.h"
+#include "bmsparsevec.h"
+#include "bmsparsevec_algo.h"
 
 #include "../include/bmb200.h"
 
@@ -384,6 +386,77 @@ int ref_pipeline(const bmb200_packed_set* s, uint32_t n_groups, const uint32_t* 
             }
         }
         if (want_or) export_bvector(bv_or, s->n_blocks, or_kind, 0, or_blocks, 0);
+        return 0;
+    } catch (...) { return 1; }
+}
+
+/*
+ * bm::sparse_vector<unsigned, bvector<>> + bm::sparse_vector_scanner<> (src/bmsparsevec.h, src/bmsparsevec_algo.h:1083-1182)
+ * on the real reference.  values[n] (+ optional nulls[n] != 0 => set_null) -> optimize()d sparse vector.
+ *   ref_sv_planes: the vector's own bit-planes (get_slice(j), j < effective_slices()) and, last, the searchable
+ *                  universe (NOT-NULL plane of a nullable vector, else [0, n)) as per-column kind / blocks / GAP words,
+ *                  (n_planes + 1) * n_cols columns, plane-major -- the GPU scan runs on exactly these blocks.
+ *   ref_sv_scan:   pred = BMB200_SCAN_*; one result vector per search value (RANGE: (lo, hi) pairs), value-major.
+ */
+typedef bm::sparse_vector<unsigned, bvect> svect;
+
+static void build_sv(svect& sv, const uint32_t* values, const uint8_t* nulls, uint64_t n)
+{
+    sv.resize((svect::size_type)n);
+    for (uint64_t i = 0; i < n; ++i) {
+        if (nulls && nulls[i]) continue;             /* stays NULL (resize(.., set_null)) */
+        sv.set((svect::size_type)i, values[i]);
+    }
+    BM_DECLARE_TEMP_BLOCK(tb)
+    sv.optimize(tb);
+}
+
+int ref_sv_planes(const uint32_t* values, const uint8_t* nulls, uint64_t n, uint32_t n_cols, uint32_t max_planes,
+                  uint32_t* n_planes_out, uint8_t* kind, uint32_t* blocks, uint16_t* gaps)
+{
+    try {
+        svect sv(nulls ? bm::use_null : bm::no_null);
+        build_sv(sv, values, nulls, n);
+        unsigned np = sv.effective_slices();
+        while (np > 1 && !sv.get_slice(np - 1)) --np;           /* trailing absent planes carry no bits */
+        if (np > max_planes) return 3;
+        *n_planes_out = np;
+        bvect empty;
+        for (unsigned j = 0; j <= np; ++j) {
+            const bvect* bv;
+            bvect uni;
+            if (j < np) bv = sv.get_slice(j);
+            else if (nulls) bv = sv.get_null_bvector();
+            else { if (n) uni.set_range(0, (bvect::size_type)(n - 1)); uni.optimize(); bv = &uni; }
+            size_t o = (size_t)j * n_cols;
+            export_bvector(bv ? *bv : empty, n_cols, kind + o, 0, blocks + o * BMB200_BLOCK_WORDS, gaps + o * BMB200_GAP_MAX_WORDS);
+        }
+        return 0;
+    } catch (...) { return 1; }
+}
+
+int ref_sv_scan(const uint32_t* values, const uint8_t* nulls, uint64_t n, int pred, const uint32_t* search, uint32_t n_search,
+                uint32_t n_cols, uint64_t* counts, uint8_t* kind, uint32_t* popcnt, uint32_t* blocks)
+{
+    try {
+        svect sv(nulls ? bm::use_null : bm::no_null);
+        build_sv(sv, values, nulls, n);
+        bm::sparse_vector_scanner<svect> scanner;
+        for (uint32_t k = 0; k < n_search; ++k) {
+            bvect bv;
+            switch (pred) {
+            case BMB200_SCAN_EQ: scanner.find_eq(sv, search[k], bv); break;
+            case BMB200_SCAN_GT: scanner.find_gt(sv, search[k], bv); break;
+            case BMB200_SCAN_GE: scanner.find_ge(sv, search[k], bv); break;
+            case BMB200_SCAN_LT: scanner.find_lt(sv, search[k], bv); break;
+            case BMB200_SCAN_LE: scanner.find_le(sv, search[k], bv); break;
+            case BMB200_SCAN_RANGE: scanner.find_range(sv, search[2 * k], search[2 * k + 1], bv); break;
+            default: return 2;
+            }
+            if (counts) counts[k] = (uint64_t)bv.count();
+            size_t o = (size_t)k * n_cols;
+            export_bvector(bv, n_cols, kind ? kind + o : 0, popcnt ? popcnt + o : 0, blocks ? blocks + o * BMB200_BLOCK_WORDS : 0, 0);
+        }
         return 0;
     } catch (...) { return 1; }
 }

@@ -15,6 +15,7 @@
 #include "bm.h"
 #include "bmaggregator.h"
 #include "bmb200_aggregator.hpp"
+#include "bmb200_scanner.hpp"
 
 typedef bm::bvector<> bvect;
 static int g_fail = 0, g_checks = 0;
@@ -132,6 +133,41 @@ int main()
             q &= (f1 == f2) && (!f1 || p1 == p2);
         }
         CHECK(q, "rank/select through the reference with the GPU-built index k=%d", k);
+    }
+    // sparse_vector_scanner vs bm::b200::scanner on real bm::sparse_vector<unsigned> objects (plain and nullable)
+    for (int nullable = 0; nullable < 2; ++nullable) {
+        typedef bm::sparse_vector<unsigned, bvect> svect;
+        svect sv(nullable ? bm::use_null : bm::no_null);
+        const unsigned n = 5u * 65536u + 777u;
+        sv.resize(n);
+        for (unsigned i = 0; i < n; ++i) {
+            if (nullable && rng() % 9 == 0) continue;
+            unsigned v = (rng() % 3 == 0) ? 0u : unsigned(rng() % 3000);
+            if (i > 100000 && i < 104000) v = 55;
+            if (rng() % 1500 == 0) v |= 1u << 18;
+            sv.set(i, v);
+        }
+        { BM_DECLARE_TEMP_BLOCK(tb) sv.optimize(tb); }
+        bm::sparse_vector_scanner<svect> ref_sc;
+        bm::b200::scanner<svect> gpu_sc(ctx, sv);
+        for (unsigned v : {0u, 1u, 55u, 2999u, 3000u, (1u << 18) + 5u, 1u << 25}) {
+            bvect a, b;
+            ref_sc.find_eq(sv, v, a); gpu_sc.find_eq(v, b); CHECK(a.compare(b) == 0, "scanner find_eq(%u) nullable=%d", v, nullable);
+            ref_sc.find_gt(sv, v, a); gpu_sc.find_gt(v, b); CHECK(a.compare(b) == 0, "scanner find_gt(%u) nullable=%d", v, nullable);
+            ref_sc.find_ge(sv, v, a); gpu_sc.find_ge(v, b); CHECK(a.compare(b) == 0, "scanner find_ge(%u) nullable=%d", v, nullable);
+            ref_sc.find_lt(sv, v, a); gpu_sc.find_lt(v, b); CHECK(a.compare(b) == 0, "scanner find_lt(%u) nullable=%d", v, nullable);
+            ref_sc.find_le(sv, v, a); gpu_sc.find_le(v, b); CHECK(a.compare(b) == 0, "scanner find_le(%u) nullable=%d", v, nullable);
+            ref_sc.find_range(sv, v / 2, v, a); gpu_sc.find_range(v / 2, v, b); CHECK(a.compare(b) == 0, "scanner find_range(%u,%u) nullable=%d", v / 2, v, nullable);
+        }
+        { bvect a, b; ref_sc.find_nonzero(sv, a); gpu_sc.find_nonzero(b); CHECK(a.compare(b) == 0, "scanner find_nonzero nullable=%d", nullable);
+          ref_sc.find_zero(sv, a); gpu_sc.find_zero(b); CHECK(a.compare(b) == 0, "scanner find_zero nullable=%d", nullable); }
+        std::vector<uint64_t> vals = {7, 55, 0, 2500, 99999};
+        std::vector<bvect> outs; std::vector<bvect::size_type> cnts;
+        gpu_sc.find_batch(BMB200_SCAN_EQ, vals, outs); gpu_sc.count_batch(BMB200_SCAN_EQ, vals, cnts);
+        for (size_t k = 0; k < vals.size(); ++k) {
+            bvect a; ref_sc.find_eq(sv, (unsigned)vals[k], a);
+            CHECK(a.compare(outs[k]) == 0 && a.count() == cnts[k], "scanner batch eq k=%zu nullable=%d", k, nullable);
+        }
     }
     std::printf("%s: %d checks, %d failed\n", g_fail ? "FAILED" : "OK", g_checks, g_fail);
     return g_fail ? 1 : 0;

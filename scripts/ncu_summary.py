@@ -29,7 +29,7 @@ def rep(path):
     d = {}
     for h, u, v in zip(hdr, units, vals):
         if h in KEYS or h == "Kernel Name":
-            d[h] = f"{v} {u}".strip()
+            d[h] = {"value": v, "unit": u}
     return d
 
 if __name__ == "__main__":

@@ -52,8 +52,31 @@ def rs_fixture(name, vecs, seed):
     print(name, "bytes", (OUT / f"{name}.npz").stat().st_size)
 
 
+def scan_fixture(name, seed, nullable):
+    """A real bm::sparse_vector<unsigned>: its own optimize()d planes (+ universe) and bm::sparse_vector_scanner<> answers."""
+    import test_oracle_vs_reference as tor
+    vals, nulls = tor.scan_inputs(seed, n=100000, nullable=nullable)
+    planes = orclib.ref_sv_planes(vals, nulls)
+    ps = bm.PackedSet.pack(planes)
+    d = pack_fields(ps)
+    d["values"] = vals
+    d["nulls"] = nulls if nulls is not None else np.zeros(0, np.uint8)
+    d["n_cases"] = len(tor.SCAN_CASES)
+    for i, (pred, search) in enumerate(tor.SCAN_CASES):
+        counts, kind, pop, blk = orclib.ref_sv_scan(vals, nulls, pred, search)
+        d[f"c{i}_pred"] = pred; d[f"c{i}_search"] = np.asarray(search, np.uint64); d[f"c{i}_counts"] = counts
+        d[f"c{i}_pop"] = pop; d[f"c{i}_blk"] = blk
+    np.savez_compressed(OUT / f"{name}.npz", **d)
+    print(name, "cases", len(tor.SCAN_CASES), "bytes", (OUT / f"{name}.npz").stat().st_size)
+
+
 if __name__ == "__main__":
     assert orclib.have_ref(), "build oracle/_ref first (make -C oracle)"
+    if "scan" in sys.argv[1:] or len(sys.argv) == 1:
+        scan_fixture("scan_plain", 31, False)
+        scan_fixture("scan_nullable", 32, True)
+        if "scan" in sys.argv[1:]:
+            sys.exit(0)
     C = bm.F_OPT_COMPRESS
     rng = np.random.default_rng(20260923)
     vecs = gen.mixed_vectors(rng, 12, 6)

@@ -35,6 +35,14 @@ def load_rs(name):
     return ps, vs
 
 
+def load_scan(name):
+    z = np.load(GOLDEN / f"{name}.npz")
+    ps = load_set(z)
+    cases = [dict(pred=int(z[f"c{i}_pred"]), search=z[f"c{i}_search"], counts=z[f"c{i}_counts"], pop=z[f"c{i}_pop"], blk=z[f"c{i}_blk"])
+             for i in range(int(z["n_cases"]))]
+    return ps, z["values"], (z["nulls"] if z["nulls"].size else None), cases
+
+
 def check_agg_case(case, kind, pop, blocks, gaps_flat=None, check_kind=True):
     """Compare one aggregate output (kind[n], pop[n], blocks[n][2048], optional concatenated GAP words) with the fixture."""
     assert np.array_equal(blocks, case["blk"]), "result bits differ from the reference"

@@ -9,7 +9,7 @@ from pathlib import Path
 
 import numpy as np
 
-from bitmagic_b200.capi import (AggArgsC, BLOCK_WORDS, GAP_MAX_WORDS, PackedSetC, packed_c, ptr)
+from bitmagic_b200.capi import (AggArgsC, BLOCK_WORDS, GAP_MAX_WORDS, PackedSetC, ScanArgsC, SCAN_RANGE, packed_c, ptr)
 
 ROOT = Path(__file__).resolve().parent.parent
 ORACLE_DIR = ROOT / "oracle"
@@ -194,3 +194,61 @@ def ref_pipeline(ps, groups, want_or=False):
                             ptr(or_kind), ptr(or_blocks))
     assert rc == 0
     return counts, kind, pop, blocks, or_kind, or_blocks
+
+
+def oracle_scan(ps, pred, values, plane0, n_planes, universe=0xFFFFFFFF, flags=0, nb_from=0, nb_to=0):
+    """orc_scan -> kind, popcnt, digest, nruns, blocks[n_values*n_cols][2048], gaps[...][1280] (value-major)"""
+    vals = np.ascontiguousarray(values, dtype=np.uint64)
+    nv = vals.shape[0] if pred == SCAN_RANGE else vals.size
+    n = ((nb_to if nb_to else ps.n_blocks) - nb_from) * nv
+    a = ScanArgsC(int(plane0), int(n_planes), int(universe), int(pred), int(flags), ptr(vals), int(nv), int(nb_from), int(nb_to))
+    kind = np.zeros(n, np.uint8); pop = np.zeros(n, np.uint32); dig = np.zeros(n, np.uint64); nr = np.zeros(n, np.uint32)
+    blocks = np.zeros((n, BLOCK_WORDS), np.uint32); gaps = np.zeros((n, GAP_MAX_WORDS), np.uint16)
+    c = _pc(ps)
+    rc = oracle().orc_scan(C.byref(c), C.byref(a), ptr(kind), ptr(pop), ptr(dig), ptr(nr), ptr(blocks), ptr(gaps))
+    assert rc == 0, f"orc_scan rc={rc}"
+    return kind, pop, dig, nr, blocks, gaps
+
+
+def ref_sv_planes(values, nulls=None, max_planes=64):
+    """The real bm::sparse_vector<unsigned>: its optimize()d planes + the universe as a list of BVector (planes..., universe)."""
+    import bitmagic_b200 as bm
+    v = np.ascontiguousarray(values, dtype=np.uint32)
+    nl = None if nulls is None else np.ascontiguousarray(nulls, dtype=np.uint8)
+    n_cols = max(1, (v.size + 65535) // 65536)
+    kind = np.zeros((max_planes + 1) * n_cols, np.uint8)
+    blocks = np.zeros(((max_planes + 1) * n_cols, BLOCK_WORDS), np.uint32)
+    gaps = np.zeros(((max_planes + 1) * n_cols, GAP_MAX_WORDS), np.uint16)
+    npl = C.c_uint32(0)
+    rc = ref().ref_sv_planes(ptr(v), ptr(nl) if nl is not None else C.c_void_p(0), C.c_uint64(v.size), C.c_uint32(n_cols), C.c_uint32(max_planes),
+                             C.byref(npl), ptr(kind), ptr(blocks), ptr(gaps))
+    assert rc == 0, f"ref_sv_planes rc={rc}"
+    out = []
+    for j in range(npl.value + 1):
+        bv = bm.BVector(n_cols)
+        for c in range(n_cols):
+            k = int(kind[j * n_cols + c])
+            if k == bm.BLK_FULL:
+                bv.set_full(c)
+            elif k == bm.BLK_BIT:
+                bv.set_bits(c, blocks[j * n_cols + c])
+            elif k == bm.BLK_GAP:
+                g = gaps[j * n_cols + c]
+                bv.set_gap(c, g[:(int(g[0]) >> 3) + 1])
+        out.append(bv)
+    return out
+
+
+def ref_sv_scan(values, nulls, pred, search):
+    """The real sparse_vector_scanner -> counts[n_search], kind, popcnt, blocks[n_search*n_cols][2048] (value-major)"""
+    v = np.ascontiguousarray(values, dtype=np.uint32)
+    nl = None if nulls is None else np.ascontiguousarray(nulls, dtype=np.uint8)
+    sv = np.ascontiguousarray(search, dtype=np.uint32)
+    ns = sv.shape[0] if pred == SCAN_RANGE else sv.size
+    n_cols = max(1, (v.size + 65535) // 65536)
+    counts = np.zeros(ns, np.uint64); kind = np.zeros(ns * n_cols, np.uint8); pop = np.zeros(ns * n_cols, np.uint32)
+    blocks = np.zeros((ns * n_cols, BLOCK_WORDS), np.uint32)
+    rc = ref().ref_sv_scan(ptr(v), ptr(nl) if nl is not None else C.c_void_p(0), C.c_uint64(v.size), int(pred), ptr(sv), C.c_uint32(ns),
+                           C.c_uint32(n_cols), ptr(counts), ptr(kind), ptr(pop), ptr(blocks))
+    assert rc == 0, f"ref_sv_scan rc={rc}"
+    return counts, kind, pop, blocks

@@ -39,3 +39,18 @@ def test_oracle_rs_vs_golden():
         pos, found = orclib.oracle_select(ps, v, g["rank"])
         assert np.array_equal(found, g["sel_found"])
         assert np.array_equal(pos[found], g["sel_pos"][g["sel_found"]])
+
+
+@pytest.mark.parametrize("name", ["scan_plain", "scan_nullable"])
+def test_oracle_scan_vs_golden(name):
+    """orc_scan on the reference's own planes == the committed answers of bm::sparse_vector_scanner<>."""
+    ps, vals, nulls, cases = gu.load_scan(name)
+    npl = ps.n_vec - 1
+    for case in cases:
+        kind, pop, dig, nr, blk, gaps = orclib.oracle_scan(ps, case["pred"], case["search"], 0, npl, npl, bm.F_OPT_COMPRESS)
+        assert np.array_equal(blk, case["blk"]) and np.array_equal(pop, case["pop"])
+        assert np.array_equal(pop.reshape(len(case["search"]), -1).sum(1), case["counts"])
+    # the planes are the bit-transposed values
+    live = np.ones(vals.size, bool) if nulls is None else nulls == 0
+    kind, pop, dig, nr, blk, gaps = orclib.oracle_scan(ps, bm.SCAN_EQ, [55], 0, npl, npl, 0)
+    assert int(pop.sum()) == int(((vals == 55) & live).sum())

@@ -524,3 +524,79 @@ def test_adopt_device_memory_and_no_leaks(ctx):
         rs.free(); r.free(); d.free()
     ctx.sync()
     assert torch.cuda.mem_get_info(0)[0] >= free0 - (4 << 20), "device memory leaked across create/free cycles"
+
+
+def check_scan(ctx, ps, dset, pred, search, plane0, npl, uni, flags=C):
+    res = bm.scan(ctx, dset, pred, search, plane0, npl, uni, flags)
+    kind, pop, dig, nr = res.meta()
+    nv = len(search)
+    tot = res.group_totals(nv)
+    fk, off, bits, gaps = res.fetch()
+    bv = bm.result_to_bvector(fk, off, bits, gaps)
+    blocks = np.stack([bv.block_words(c) for c in range(kind.size)])
+    res.free()
+    okind, opop, odig, onr, oblk, ogap = orclib.oracle_scan(ps, pred, search, plane0, npl, uni, flags)
+    assert np.array_equal(blocks, oblk), f"scan pred {pred}: bits differ"
+    assert np.array_equal(pop, opop) and np.array_equal(dig, odig) and np.array_equal(nr, onr) and np.array_equal(kind, okind)
+    assert np.array_equal(tot, opop.reshape(nv, -1).sum(1))
+    for c in np.nonzero(okind == bm.BLK_GAP)[0]:
+        n = (int(ogap[c, 0]) >> 3) + 1
+        assert np.array_equal(bv.blocks[c], ogap[c, :n])
+    return blocks
+
+
+def test_scan_vs_oracle_random_planes(ctx):
+    """bmb200_scan on planes of every block kind (NULL / FULL / bit / GAP, both GAP storage forms), plane window inside a larger
+    set, universe given / absent, 1..40 planes, values above the top plane."""
+    import test_oracle_vs_reference as tor
+    rng = np.random.default_rng(77)
+    vecs = gen.mixed_vectors(rng, 44, 3, p_null=0.15, p_full=0.1, p_gap=0.45)
+    for flat in (True, False):
+        ps = bm.PackedSet.pack(vecs, gap_flat=flat)
+        dset = bm.DeviceSet.upload(ctx, ps)
+        for plane0, npl, uni in [(2, 40, 43), (0, 7, 1), (10, 1, bm.NO_UNIVERSE), (5, 13, bm.NO_UNIVERSE)]:
+            top = (1 << npl) - 1
+            vals = [0, 1, top, top // 3, int(rng.integers(0, top + 1)), top + 1 if npl < 64 else top]
+            for pred in (bm.SCAN_EQ, bm.SCAN_GT, bm.SCAN_GE, bm.SCAN_LT, bm.SCAN_LE):
+                check_scan(ctx, ps, dset, pred, vals, plane0, npl, uni, C if pred % 2 else 0)
+            check_scan(ctx, ps, dset, bm.SCAN_RANGE, [[0, top], [3, 3], [top // 2, top // 4], [1, top + 5]], plane0, npl, uni)
+        dset.free()
+
+
+@pytest.mark.skipif(not orclib.have_ref(), reason="prebuilt reference library not present")
+@pytest.mark.parametrize("nullable", [False, True])
+def test_scan_against_reference_sparse_vector_scanner(ctx, nullable):
+    """The real bm::sparse_vector<unsigned>'s own planes -> GPU scan == bm::sparse_vector_scanner<> results, and the host mirror
+    (SparseVector / SparseVectorScanner) gives the same sets from the raw values."""
+    import test_oracle_vs_reference as tor
+    vals, nulls = tor.scan_inputs(9 + nullable, nullable=nullable)
+    planes = orclib.ref_sv_planes(vals, nulls)
+    ps = bm.PackedSet.pack(planes)
+    npl = len(planes) - 1
+    dset = bm.DeviceSet.upload(ctx, ps)
+    sv = bm.SparseVector.from_values(vals, nulls)
+    sc = bm.SparseVectorScanner(sv, ctx)
+    fn = {bm.SCAN_EQ: sc.find_eq, bm.SCAN_GT: sc.find_gt, bm.SCAN_GE: sc.find_ge, bm.SCAN_LT: sc.find_lt, bm.SCAN_LE: sc.find_le, bm.SCAN_RANGE: sc.find_range}
+    for pred, search in tor.SCAN_CASES:
+        blocks = check_scan(ctx, ps, dset, pred, search, 0, npl, npl)
+        counts, rkind, rpop, rblk = orclib.ref_sv_scan(vals, nulls, pred, search)
+        assert np.array_equal(blocks, rblk)
+        got = fn[pred](np.array(search, np.uint64))
+        nb = ps.n_blocks
+        for k, bv in enumerate(got):
+            assert np.array_equal(np.stack([bv.block_words(c) for c in range(nb)]), rblk[k * nb:(k + 1) * nb])
+    assert sc.count_eq(77) == int(((vals == 77) & (nulls == 0 if nulls is not None else True)).sum())
+    assert sc.find_zero().count() == int(((vals == 0) & (nulls == 0 if nulls is not None else True)).sum())
+    sc.close(); dset.free()
+
+
+@pytest.mark.parametrize("name", ["scan_plain", "scan_nullable"])
+def test_scan_vs_golden(ctx, name):
+    """bmb200_scan on the committed planes of a real bm::sparse_vector<unsigned> == the committed scanner answers."""
+    ps, vals, nulls, cases = gu.load_scan(name)
+    npl = ps.n_vec - 1
+    dset = bm.DeviceSet.upload(ctx, ps)
+    for case in cases:
+        blocks = check_scan(ctx, ps, dset, case["pred"], case["search"], 0, npl, npl)
+        assert np.array_equal(blocks, case["blk"])
+    dset.free()

@@ -186,3 +186,35 @@ def test_pipeline_oracle_matches_reference():
         assert np.array_equal(rblk[g], oblk) and np.array_equal(rpop[g], opop) and np.array_equal(rkind[g], okind)
         union |= oblk
     assert np.array_equal(rob, union)
+
+
+SCAN_CASES = [(bm.SCAN_EQ, [0, 17, 4999, 70000, 65536 + 77, 1 << 20]), (bm.SCAN_GT, [0, 100, 4998, 5000, 65535, 1 << 20]), (bm.SCAN_GE, [0, 1, 2500, 5000, 65536]),
+              (bm.SCAN_LT, [0, 1, 3000, 9999, 70000]), (bm.SCAN_LE, [0, 4999, 12, 65536]), (bm.SCAN_RANGE, [[10, 20], [0, 0], [0, 4999], [30, 10], [4000, 1 << 22], [65536, 70000]])]
+
+
+def scan_inputs(seed, n=150000, nullable=False):
+    rng = np.random.default_rng(seed)
+    vals = rng.integers(0, 5000, n).astype(np.uint32)
+    vals[rng.random(n) < 0.3] = 0
+    vals[n // 2: n // 2 + 4000] = 77                     # a long run of one value
+    vals[rng.random(n) < 0.0008] |= np.uint32(1 << 16)   # a sparse high plane (GAP blocks); planes 13..15 stay absent
+    nulls = (rng.random(n) < 0.1).astype(np.uint8) if nullable else None
+    return vals, nulls
+
+
+@needs_ref
+@pytest.mark.parametrize("nullable", [False, True])
+def test_scan_oracle_matches_reference_scanner(nullable):
+    """orc_scan (restated contract) == bm::sparse_vector_scanner<> on the reference's own optimize()d planes."""
+    vals, nulls = scan_inputs(5 + nullable, nullable=nullable)
+    planes = orclib.ref_sv_planes(vals, nulls)
+    ps = bm.PackedSet.pack(planes)
+    npl = len(planes) - 1
+    kinds = ps.kinds()
+    assert npl == 17 and (kinds == bm.BLK_GAP).any() and (kinds == bm.BLK_BIT).any() and (kinds == bm.BLK_NULL).any()
+    for pred, search in SCAN_CASES:
+        okind, opop, odig, onr, oblk, ogap = orclib.oracle_scan(ps, pred, search, 0, npl, npl, bm.F_OPT_COMPRESS)
+        counts, rkind, rpop, rblk = orclib.ref_sv_scan(vals, nulls, pred, search)
+        assert np.array_equal(oblk, rblk), f"pred {pred}"
+        assert np.array_equal(opop, rpop)
+        assert np.array_equal(opop.reshape(len(search), -1).sum(1), counts)
