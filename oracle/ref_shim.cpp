@@ -461,6 +461,40 @@ int ref_sv_scan(const uint32_t* values, const uint8_t* nulls, uint64_t n, int pr
     } catch (...) { return 1; }
 }
 
+/* wall time (seconds, best of `repeats`) of the n_search scanner calls alone -- the vector is built and optimize()d
+ * before the clock starts; total = sum of result cardinalities */
+int ref_sv_time_scan(const uint32_t* values, const uint8_t* nulls, uint64_t n, int pred, const uint32_t* search, uint32_t n_search,
+                     int repeats, double* best_sec, uint64_t* total)
+{
+    try {
+        svect sv(nulls ? bm::use_null : bm::no_null);
+        build_sv(sv, values, nulls, n);
+        bm::sparse_vector_scanner<svect> scanner;
+        double best = 1e30; uint64_t tot = 0;
+        for (int r = 0; r < repeats; ++r) {
+            tot = 0;
+            auto t0 = std::chrono::steady_clock::now();
+            for (uint32_t k = 0; k < n_search; ++k) {
+                bvect bv;
+                switch (pred) {
+                case BMB200_SCAN_EQ: scanner.find_eq(sv, search[k], bv); break;
+                case BMB200_SCAN_GT: scanner.find_gt(sv, search[k], bv); break;
+                case BMB200_SCAN_GE: scanner.find_ge(sv, search[k], bv); break;
+                case BMB200_SCAN_LT: scanner.find_lt(sv, search[k], bv); break;
+                case BMB200_SCAN_LE: scanner.find_le(sv, search[k], bv); break;
+                case BMB200_SCAN_RANGE: scanner.find_range(sv, search[2 * k], search[2 * k + 1], bv); break;
+                default: return 2;
+                }
+                tot += (uint64_t)bv.count();
+            }
+            double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (sec < best) best = sec;
+        }
+        *best_sec = best; *total = tot;
+        return 0;
+    } catch (...) { return 1; }
+}
+
 /*
  * CPU baseline timing.  The reference aggregator is single-threaded; for an all-cores figure each of
  * `threads` workers owns its own bm::aggregator and its own copy of the inputs restricted to a

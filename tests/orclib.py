@@ -252,3 +252,16 @@ def ref_sv_scan(values, nulls, pred, search):
                            C.c_uint32(n_cols), ptr(counts), ptr(kind), ptr(pop), ptr(blocks))
     assert rc == 0, f"ref_sv_scan rc={rc}"
     return counts, kind, pop, blocks
+
+
+def ref_sv_time_scan(values, nulls, pred, search, repeats=2):
+    """seconds (best of repeats) for the reference scanner to answer all `search` values + the summed cardinality"""
+    v = np.ascontiguousarray(values, dtype=np.uint32)
+    nl = None if nulls is None else np.ascontiguousarray(nulls, dtype=np.uint8)
+    sv = np.ascontiguousarray(search, dtype=np.uint32)
+    ns = sv.shape[0] if pred == SCAN_RANGE else sv.size
+    sec, tot = C.c_double(0), C.c_uint64(0)
+    rc = ref().ref_sv_time_scan(ptr(v), ptr(nl) if nl is not None else C.c_void_p(0), C.c_uint64(v.size), int(pred), ptr(sv), C.c_uint32(ns),
+                                int(repeats), C.byref(sec), C.byref(tot))
+    assert rc == 0, f"ref_sv_time_scan rc={rc}"
+    return sec.value, tot.value
