@@ -5,7 +5,7 @@ host-side mirror of the reference operator surface (aggregator.py, scanner.py, h
 There is no CPU fallback: importing works anywhere, computing needs libbmb200.so and a B200.
 """
 from .capi import (BLK_BIT, BLK_FULL, BLK_GAP, BLK_NULL, F_COUNT_ONLY, F_OPT_COMPRESS, F_OPT_NONE, F_OR_TARGET, OP_AND,
-                   OP_AND_SUB, OP_OR, OP_XOR, BMB200Error, Context, DeviceResult, DeviceRS, DeviceSet,
+                   OP_AND_SUB, OP_OR, OP_XOR, OP_SHIFT_R_AND, BMB200Error, Context, DeviceResult, DeviceRS, DeviceSet,
                    aggregate, aggregate_batch, aggregate_host, default_context, scan,
                    SCAN_EQ, SCAN_GE, SCAN_GT, SCAN_LE, SCAN_LT, SCAN_RANGE, NO_UNIVERSE)
 from .hostfmt import BVector, PackedSet, result_to_bvector

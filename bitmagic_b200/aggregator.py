@@ -2,7 +2,7 @@
 
 Same names, argument meaning and error behaviour as the reference:
   * ``Aggregator``            <- ``bm::aggregator<BV>``            (reference src/bmaggregator.h:56-1060)
-        add / reset / set_optimization / combine_or / combine_and / combine_and_sub
+        add / reset / set_optimization / combine_or / combine_and / combine_and_sub / combine_shift_right_and
   * ``bit_and / bit_or / bit_xor / bit_sub`` <- 3-operand ``bvector::bit_*`` (src/bm.h:1745-1850)
   * ``count_and / count_or / count_xor / count_sub`` <- ``bm::count_*`` (src/bmalgo.h:48-51)
   * ``RSIndex / build_rs_index / count_to / select`` <- ``rs_index``, ``bvector::build_rs_index``,
@@ -16,15 +16,15 @@ from __future__ import annotations
 import numpy as np
 
 from . import capi
-from .capi import (BLK_NULL, F_COUNT_ONLY, F_OPT_COMPRESS, F_OPT_NONE, F_OR_TARGET, OP_AND, OP_AND_SUB, OP_OR, OP_XOR)
+from .capi import (BLK_NULL, F_COUNT_ONLY, F_OPT_COMPRESS, F_OPT_NONE, F_OR_TARGET, OP_AND, OP_AND_SUB, OP_OR, OP_SHIFT_R_AND, OP_XOR)
 from .hostfmt import BVector, PackedSet, result_to_bvector
 
 OPT_NONE = 0       # bvector::opt_none
 OPT_COMPRESS = 3   # bvector::opt_compress (reference src/bm.h:132-138)
 
 
-def _run(ctx, vectors, op, g0, g1, opt_mode, count_only=False):
-    n_blocks = max(v.n_blocks for v in vectors)
+def _run(ctx, vectors, op, g0, g1, opt_mode, count_only=False, spare_blocks=0):
+    n_blocks = max(v.n_blocks for v in vectors) + spare_blocks
     dset = capi.DeviceSet.upload_vectors(ctx, vectors, n_blocks)
     try:
         flags = (F_OPT_COMPRESS if opt_mode else F_OPT_NONE) | (F_COUNT_ONLY if count_only else 0)
@@ -95,6 +95,16 @@ class Aggregator:
         # combine_and_sub always stores through opt_copy_bit_block(opt_compress), :1209
         res, total, found = _run(self.ctx, vecs, OP_AND_SUB, np.arange(len(a)),
                                  np.arange(len(a), len(vecs)), OPT_COMPRESS)
+        return res, found
+
+    def combine_shift_right_and(self, bv_src_and: list[BVector] | None = None, any_: bool = False):
+        """aggregator::combine_shift_right_and (src/bmaggregator.h:2494-2530): T_0 = v_0, T_k = (T_{k-1} >> 1) & v_k.
+        Returns (result, found).  One spare block column receives the bits carried out of the last source block
+        (the reference keeps walking top blocks while carry-overs are pending, :2506-2511)."""
+        src = self._groups[0] if bv_src_and is None else bv_src_and
+        if not src:
+            return BVector(0), False                           # :2499-2503
+        res, total, found = _run(self.ctx, src, OP_SHIFT_R_AND, np.arange(len(src)), None, self._opt, spare_blocks=1)
         return res, found
 
     def count_and_sub(self, bv_src_and, bv_src_sub) -> int:

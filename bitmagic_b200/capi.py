@@ -21,7 +21,7 @@ ERR_CUDA, ERR_NODEVICE = 200, 201
 BLOCK_WORDS, BLOCK_BYTES, BLOCK_BITS = 2048, 8192, 65536
 GAP_MAX_WORDS, GAP_THRESHOLD, GAP_UNIT_WORDS, SUPERBLOCK = 1280, 1276, 8, 256
 BLK_NULL, BLK_FULL, BLK_BIT, BLK_GAP = 0, 1, 2, 3
-OP_OR, OP_AND, OP_AND_SUB, OP_XOR = 0, 1, 2, 3
+OP_OR, OP_AND, OP_AND_SUB, OP_XOR, OP_SHIFT_R_AND = 0, 1, 2, 3, 4
 F_COUNT_ONLY, F_OPT_NONE, F_OPT_COMPRESS, F_OR_TARGET = 1, 0, 2, 4
 
 # every symbol include/bmb200.h declares (checked by tests/test_cabi_symbols.py)

@@ -11,6 +11,7 @@
 #include "agg_kernel.cuh"
 #include "aux_kernels.cuh"
 #include "scan_kernel.cuh"
+#include "shift_kernel.cuh"
 
 using namespace bmb200;
 
@@ -543,7 +544,7 @@ static void set_agg_attrs(bmb200_ctx* ctx, cudaError_t* e)
 int bmb200_aggregate_batch(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_batch_args* a, bmb200_result** inout)
 {
     if (!ctx || !set || !a || !inout || set->ctx != ctx || !a->n_groups || !a->offsets) return BMB200_ERR_BADARG;
-    if (a->op < BMB200_OP_OR || a->op > BMB200_OP_XOR) return BMB200_ERR_BADARG;
+    if (a->op < BMB200_OP_OR || a->op > BMB200_OP_SHIFT_R_AND) return BMB200_ERR_BADARG;
     const uint32_t nb_to = a->nb_to ? a->nb_to : set->v.n_blocks;
     if (a->nb_from >= nb_to || nb_to > set->v.n_blocks) return BMB200_ERR_RANGE;
     const uint32_t ng = a->n_groups;
@@ -551,6 +552,8 @@ int bmb200_aggregate_batch(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_
     for (uint32_t k = 0; k < 2 * ng; ++k) if (a->offsets[k] > a->offsets[k + 1]) return BMB200_ERR_BADARG;
     if (nmem && !a->members) return BMB200_ERR_BADARG;
     for (size_t k = 0; k < nmem; ++k) if (a->members[k] >= set->v.n_vec) return BMB200_ERR_RANGE;
+    if (a->op == BMB200_OP_SHIFT_R_AND)
+        for (uint32_t g = 0; g < ng; ++g) if (a->offsets[2 * g + 1] - a->offsets[2 * g] > 65536u) return BMB200_ERR_RANGE;
     const uint64_t tot_cols = (uint64_t)(nb_to - a->nb_from) * ng;
     if (tot_cols > 0x7fffffffull) return BMB200_ERR_RANGE;
     CU(cudaSetDevice(ctx->device));
@@ -611,6 +614,7 @@ int bmb200_aggregate_batch(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_
     case BMB200_OP_OR:      agg_kernel<BMB200_OP_OR><<<grid, kAggThreads, kAggDynSmem, ctx->stream>>>(p); break;
     case BMB200_OP_AND:     agg_kernel<BMB200_OP_AND><<<grid, kAggThreads, kAggDynSmem, ctx->stream>>>(p); break;
     case BMB200_OP_AND_SUB: agg_kernel<BMB200_OP_AND_SUB><<<grid, kAggThreads, kAggDynSmem, ctx->stream>>>(p); break;
+    case BMB200_OP_SHIFT_R_AND: shift_and_kernel<<<grid, kAggThreads, 0, ctx->stream>>>(p); break;
     default:                agg_kernel<BMB200_OP_XOR><<<grid, kAggThreads, kAggDynSmem, ctx->stream>>>(p); break;
     }
     int rc = after_launch(ctx);

@@ -183,6 +183,19 @@ public:
         return run(target, BMB200_OP_AND_SUB, src_and, n_and, src_sub, n_sub, true /* always opt_compress, :1209 */);
     }
 
+    /// aggregator::combine_shift_right_and, src/bmaggregator.h:473,552,2494-2530: T_0 = v_0, T_k = (T_{k-1} >> 1) & v_k
+    void combine_shift_right_and(bvector_type& target)
+    { combine_shift_right_and(target, grp_[0].data(), grp_[0].size(), false); }
+    bool combine_shift_right_and(bvector_type& target, const bvector_type_const_ptr* src_and, size_t n_and, bool any)
+    {
+        (void)any;
+        if (!n_and) { target.clear(); return false; }             // :2499-2503
+        spare_blocks_ = 1;    // bits carried out of the last source block land in the next one (:2506-2511 keeps walking)
+        bool found = run(target, BMB200_OP_SHIFT_R_AND, src_and, n_and, 0, 0, opt_mode_ != BV::opt_none);
+        spare_blocks_ = 0;
+        return found;
+    }
+
     /// popcount of AND-SUB without materialising the result (pipeline counts mode, :1397-1398)
     size_type count_and_sub(const bvector_type_const_ptr* src_and, size_t n_and,
                             const bvector_type_const_ptr* src_sub, size_t n_sub)
@@ -214,6 +227,7 @@ private:
             if (nb > n_blocks_) n_blocks_ = nb;
             if (bv->size() > max_size_) max_size_ = bv->size();   // resize_target: max over sources, :2238-2248
         }
+        if (spare_blocks_ && n_blocks_ < 65536u) n_blocks_ += spare_blocks_;
         views_.resize(n0 + n1); vb_.resize(n0 + n1);
         for (size_t k = 0; k < n0 + n1; ++k)
         {
@@ -257,6 +271,7 @@ private:
     std::vector<detail::tree_view<BV>> views_;
     std::vector<bmb200_vec_blocks> vb_;
     uint32_t n_blocks_ = 0;
+    uint32_t spare_blocks_ = 0;
     size_type max_size_ = 0;
 };
 

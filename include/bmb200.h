@@ -17,6 +17,7 @@
  *   bmb200_aggregate  OP_AND      <- aggregator::combine_and       src/bmaggregator.h:1126-1157,1668-1716
  *   bmb200_aggregate  OP_AND_SUB  <- aggregator::combine_and_sub   src/bmaggregator.h:1162-1220,1720-1803
  *   bmb200_aggregate  OP_XOR      <- bvector::bit_xor              src/bm.h:6072 (bit_block_xor src/bmfunc.h:9191)
+ *   bmb200_aggregate  OP_SHIFT_R_AND <- aggregator::combine_shift_right_and  src/bmaggregator.h:2494-2669
  *   BMB200_F_COUNT_ONLY           <- bm::count_and/or/xor/sub      src/bmalgo.h:48-51, pipeline counts src/bmaggregator.h:1397
  *   bmb200_result_optimize        <- blocks_manager::opt_copy_bit_block src/bmblocks.h:1355-1409
  *   bmb200_scan                   <- sparse_vector_scanner::find_eq/find_gt/find_ge/find_lt/find_le/find_range
@@ -72,6 +73,10 @@ extern "C" {
 #define BMB200_OP_AND      1   /* group0 = sources                       */
 #define BMB200_OP_AND_SUB  2   /* group0 = AND sources, group1 = SUB set */
 #define BMB200_OP_XOR      3   /* group0 = sources (2-operand in the reference, N-way here) */
+#define BMB200_OP_SHIFT_R_AND 4 /* group0 = v_0 .. v_{n-1} IN ORDER: T_0 = v_0, T_k = (T_{k-1} >> 1) & v_k, result = T_{n-1}
+                                 * (aggregator::combine_shift_right_and; ">> 1" = every bit to the next higher index);
+                                 * n <= 65536.  Bits pushed past the last block column of the set are dropped: give the
+                                 * set one spare (NULL) column if the sources can carry out of their last block. */
 
 /* ---- flags for bmb200_aggregate ---- */
 #define BMB200_F_COUNT_ONLY  1u  /* per-column popcount/digest only; no result blocks stored */

@@ -340,11 +340,69 @@ static int column_xor(const bmb200_packed_set* s, uint32_t nb, const uint32_t* g
     return any ? 2 : 0;
 }
 
+/* aggregator::combine_shift_right_and, src/bmaggregator.h:2494-2669, restated with its own data flow: blocks in order,
+ * one carry bit per source handed from block to block (carry_overs[], :2485-2489); per block the first source is
+ * copied, every further source k does  blk = shift_r1(blk, carry_overs[k]) & arg  (process_shift_right_and :2634-2693,
+ * bit_block_shift_r1 src/bmfunc.h:6391-6410: w = (w << 1) | carry).  The digest shortcuts of the reference only skip
+ * work on empty blocks and are not restated.  A non-empty block is stored through opt_copy_bit_block(opt_mode). */
+static int orc_shift_right_and(const bmb200_packed_set* s, const bmb200_agg_args* a,
+                               uint8_t* kind, uint32_t* popcnt, uint64_t* digest, uint32_t* nruns, uint32_t* blocks, uint16_t* gaps)
+{
+    uint32_t nb_to = a->nb_to ? a->nb_to : s->n_blocks;
+    int compress = (a->flags & BMB200_F_OPT_COMPRESS) != 0;
+    uint32_t n = a->n0;
+    uint32_t* tb = (uint32_t*)malloc(BMB200_BLOCK_BYTES);
+    uint32_t* arg = (uint32_t*)malloc(BMB200_BLOCK_BYTES);
+    uint16_t* tg = (uint16_t*)malloc(sizeof(uint16_t) * 65540);
+    uint8_t* carry = (uint8_t*)calloc(n ? n : 1, 1);
+    if (!tb || !arg || !tg || !carry) { free(tb); free(arg); free(tg); free(carry); return BMB200_ERR_BADALLOC; }
+    /* blocks before nb_from still feed carries into the range: walk from block 0 */
+    for (uint32_t nb = 0; nb < nb_to; ++nb) {
+        if (n) orc_expand_block(s, a->group0[0], nb, tb); else memset(tb, 0, BMB200_BLOCK_BYTES);
+        carry[0] = 0;
+        for (uint32_t k = 1; k < n; ++k) {
+            uint32_t co = carry[k];
+            for (uint32_t i = 0; i < BW; ++i) { uint32_t w = tb[i]; uint32_t co1 = w >> 31; tb[i] = (w << 1) | co; co = co1; }
+            carry[k] = (uint8_t)co;
+            orc_expand_block(s, a->group0[k], nb, arg);
+            for (uint32_t i = 0; i < BW; ++i) tb[i] &= arg[i];
+        }
+        if (nb < a->nb_from) continue;
+        uint32_t c = nb - a->nb_from;
+        uint32_t pc = orc_bit_block_count(tb), nr = orc_bit_block_calc_change(tb);
+        uint64_t dg = orc_block_digest(tb);
+        uint8_t kd;
+        if (dg == 0) kd = BMB200_BLK_NULL;                     /* if (digest) ... opt_copy_bit_block, :2617-2632 */
+        else if (!compress) kd = BMB200_BLK_BIT;
+        else if (nr == 1) kd = BMB200_BLK_FULL;
+        else if (nr < BMB200_GAP_THRESHOLD) kd = BMB200_BLK_GAP;
+        else kd = BMB200_BLK_BIT;
+        if (kind) kind[c] = kd;
+        if (popcnt) popcnt[c] = pc;
+        if (digest) digest[c] = dg;
+        if (nruns) nruns[c] = nr;
+        if (blocks) memcpy(blocks + (size_t)c * BW, tb, BMB200_BLOCK_BYTES);
+        if (gaps) {
+            uint16_t* gout = gaps + (size_t)c * GMAX;
+            memset(gout, 0, sizeof(uint16_t) * GMAX);
+            if (kd == BMB200_BLK_GAP) { uint32_t len = orc_bit_to_gap(tg, tb); memcpy(gout, tg, sizeof(uint16_t) * (len + 1)); }
+        }
+    }
+    free(tb); free(arg); free(tg); free(carry);
+    return BMB200_OK;
+}
+
 int orc_aggregate(const bmb200_packed_set* s, const bmb200_agg_args* a,
                   uint8_t* kind, uint32_t* popcnt, uint64_t* digest, uint32_t* nruns,
                   uint32_t* blocks, uint16_t* gaps)
 {
     if (!s || !a) return BMB200_ERR_BADARG;
+    if (a->op == BMB200_OP_SHIFT_R_AND) {
+        uint32_t nbt = a->nb_to ? a->nb_to : s->n_blocks;
+        if (a->nb_from > nbt || nbt > s->n_blocks) return BMB200_ERR_RANGE;
+        for (uint32_t k = 0; k < a->n0; ++k) if (a->group0[k] >= s->n_vec) return BMB200_ERR_RANGE;
+        return orc_shift_right_and(s, a, kind, popcnt, digest, nruns, blocks, gaps);
+    }
     uint32_t nb_to = a->nb_to ? a->nb_to : s->n_blocks;
     if (a->nb_from > nb_to || nb_to > s->n_blocks) return BMB200_ERR_RANGE;
     for (uint32_t k = 0; k < a->n0; ++k) if (a->group0[k] >= s->n_vec) return BMB200_ERR_RANGE;

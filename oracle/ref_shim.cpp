@@ -155,6 +155,9 @@ bool run_op(bm::aggregator<bvect>& agg, const bmb200_agg_args* a, const Built& b
         any = agg.combine_and_sub(target, b.g0.data(), b.g0.size(),
                                   b.g1.empty() ? 0 : b.g1.data(), b.g1.size(), false);
         break;
+    case BMB200_OP_SHIFT_R_AND:
+        any = agg.combine_shift_right_and(target, b.g0.data(), b.g0.size(), false);
+        break;
     case BMB200_OP_XOR:
         target.clear(true);
         if (!b.g0.empty()) {

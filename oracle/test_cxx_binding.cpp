@@ -78,6 +78,23 @@ int main()
         bool f1 = ref.combine_and_sub(a), f2 = gpu.combine_and_sub(b);
         CHECK(f1 == f2 && a.compare(b) == 0, "member combine_and_sub");
     }
+    {   // SHIFT-R-AND (tests/stress/t.cpp AggregatorTest shift-and cases): dense sources so a few steps survive
+        std::vector<std::unique_ptr<bvect>> ds; std::vector<const bvect*> dp;
+        for (int k = 0; k < 6; ++k) {
+            ds.emplace_back(new bvect()); fill(*ds.back(), rng, n_bits, 0.7, k % 2 == 1);
+            ds.back()->set_bit(n_bits - 1); ds.back()->set_bit(65535); ds.back()->set_bit(65536);
+            if (k >= 3) { BM_DECLARE_TEMP_BLOCK(tb) ds.back()->optimize(tb, bvect::opt_compress); }
+            dp.push_back(ds.back().get());
+        }
+        for (int opt = 0; opt < 2; ++opt)
+            for (size_t n : {size_t(1), size_t(2), size_t(4), size_t(6)}) {
+                bm::aggregator<bvect> ref; bm::b200::aggregator<bvect> gpu(ctx);
+                ref.set_optimization(opt ? bvect::opt_compress : bvect::opt_none); gpu.set_optimization(opt ? bvect::opt_compress : bvect::opt_none);
+                bvect a, b;
+                bool f1 = ref.combine_shift_right_and(a, dp.data(), n, false), f2 = gpu.combine_shift_right_and(b, dp.data(), n, false);
+                CHECK(f1 == f2 && a.compare(b) == 0 && a.count() == b.count(), "combine_shift_right_and n=%zu opt=%d (%u vs %u bits)", n, opt, (unsigned)a.count(), (unsigned)b.count());
+            }
+    }
     {   // 3-operand ops
         bvect t1, t2;
         t1.bit_and(*all[0], *all[9], bvect::opt_none); bm::b200::bit_and(ctx, t2, *all[0], *all[9]); CHECK(t1.compare(t2) == 0, "bit_and");

@@ -600,3 +600,27 @@ def test_scan_vs_golden(ctx, name):
         blocks = check_scan(ctx, ps, dset, case["pred"], case["search"], 0, npl, npl)
         assert np.array_equal(blocks, case["blk"])
     dset.free()
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_shift_right_and_vs_oracle(ctx, seed):
+    """OP_SHIFT_R_AND (aggregator::combine_shift_right_and): every block kind in the current and the previous block of a source,
+    shifts below and above one word / one word-quad, repeated sources, sub-ranges, both GAP storage forms, the Python mirror."""
+    import test_oracle_vs_reference as tor
+    vecs = tor.shift_and_inputs(seed, n_vec=12, n_blocks=5)
+    rng = np.random.default_rng(seed)
+    for flat in (True, False):
+        ps = bm.PackedSet.pack(vecs, gap_flat=flat)
+        dset = bm.DeviceSet.upload(ctx, ps)
+        for n in (1, 2, 3, 5, 12, 33, 34, 70, 130, 200):
+            g = rng.integers(0, len(vecs), n) if n > len(vecs) else rng.permutation(len(vecs))[:n]
+            check_vs_oracle(ctx, ps, bm.OP_SHIFT_R_AND, g, None, C if n % 2 else 0, dset)
+        # long chains over FULL / dense blocks keep bits alive: same vector repeated
+        full_like = max(range(len(vecs)), key=lambda v: vecs[v].count())
+        got = check_vs_oracle(ctx, ps, bm.OP_SHIFT_R_AND, [full_like] * 40, None, C, dset)
+        assert got["total"] > 0
+        dset.free()
+    agg = bm.Aggregator(ctx)
+    res, found = agg.combine_shift_right_and(vecs[:3])
+    okind, opop, odig, onr, oblk, ogap = orclib.oracle_aggregate(bm.PackedSet.pack(vecs[:3], 6), bm.OP_SHIFT_R_AND, [0, 1, 2], None, 0)
+    assert found == bool(opop.sum()) and np.array_equal(np.stack([res.block_words(c) for c in range(6)]), oblk)

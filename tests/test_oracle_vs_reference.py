@@ -218,3 +218,45 @@ def test_scan_oracle_matches_reference_scanner(nullable):
         assert np.array_equal(oblk, rblk), f"pred {pred}"
         assert np.array_equal(opop, rpop)
         assert np.array_equal(opop.reshape(len(search), -1).sum(1), counts)
+
+
+def shift_and_inputs(seed, n_vec=10, n_blocks=5):
+    """Vectors dense enough that (T >> 1) & v keeps bits alive for a few steps, all block kinds, carries across block borders."""
+    rng = np.random.default_rng(seed)
+    vecs = gen.mixed_vectors(rng, n_vec, n_blocks, p_null=0.08, p_full=0.25, p_gap=0.3)
+    for v in vecs[: n_vec // 2]:                       # dense bit / GAP blocks with bits at both block borders
+        for nb in range(n_blocks - 1):
+            w = rng.integers(0, 2**32, 2048, dtype=np.uint64).astype(np.uint32) | rng.integers(0, 2**32, 2048, dtype=np.uint64).astype(np.uint32)
+            w[0] |= 1; w[2047] |= 0x80000000
+            if nb % 2:
+                v.set_bits(nb, w)
+        v.kind[n_blocks - 1] = bm.BLK_NULL; v.blocks.pop(n_blocks - 1, None)    # spare column for the carry out of the last block
+    for v in vecs:
+        v.kind[n_blocks - 1] = bm.BLK_NULL; v.blocks.pop(n_blocks - 1, None)
+    return vecs
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_shift_right_and_oracle_matches_reference(seed):
+    """orc_aggregate(OP_SHIFT_R_AND) == aggregator::combine_shift_right_and on real bvectors (bits, kinds, GAP bytes)."""
+    vecs = shift_and_inputs(seed)
+    ps = bm.PackedSet.pack(vecs)
+    rng = np.random.default_rng(seed)
+    for n in (1, 2, 3, 7, 10, 40):
+        g = rng.integers(0, len(vecs), n) if n > len(vecs) else rng.permutation(len(vecs))[:n]
+        for flags in (0, bm.F_OPT_COMPRESS):
+            okind, opop, odig, onr, oblk, ogap = orclib.oracle_aggregate(ps, bm.OP_SHIFT_R_AND, g, None, flags)
+            rkind, rpop, rblk, rgap, rany = orclib.ref_aggregate(ps, bm.OP_SHIFT_R_AND, g, None, flags)
+            assert np.array_equal(oblk, rblk), f"n={n}"
+            assert np.array_equal(opop, rpop) and rany == bool(opop.sum())
+            assert np.array_equal(okind, rkind)
+            assert np.array_equal(ogap, rgap)
+    # closed form: result[p] = AND_k v_k[p - (n-1-k)]
+    g = [0, 1, 2]
+    _, _, _, _, oblk, _ = orclib.oracle_aggregate(ps, bm.OP_SHIFT_R_AND, g, None, 0)
+    bits = [np.unpackbits(np.concatenate([vecs[v].block_words(c) for c in range(ps.n_blocks)]).view(np.uint8), bitorder="little") for v in g]
+    want = np.roll(bits[0], 2) & np.roll(bits[1], 1) & bits[2]
+    want[:2] = 0                                        # v_0 contributes zeros shifted in from before position 0
+    got = np.unpackbits(oblk.reshape(-1).view(np.uint8), bitorder="little")
+    assert got.any() and np.array_equal(got, want)
