@@ -17,7 +17,7 @@ LIB_PATH = Path(os.environ.get("BMB200_LIB", str(_HERE / "libbmb200.so")))   # o
 # ---- constants (mirror include/bmb200.h) ----
 OK = 0
 ERR_BADALLOC, ERR_BADARG, ERR_RANGE, ERR_RS_IDX_MISSING = 1, 2, 3, 7
-ERR_CUDA, ERR_NODEVICE = 200, 201
+ERR_CUDA, ERR_NODEVICE, ERR_UNSUPPORTED = 200, 201, 202
 BLOCK_WORDS, BLOCK_BYTES, BLOCK_BITS = 2048, 8192, 65536
 GAP_MAX_WORDS, GAP_THRESHOLD, GAP_UNIT_WORDS, SUPERBLOCK = 1280, 1276, 8, 256
 BLK_NULL, BLK_FULL, BLK_BIT, BLK_GAP = 0, 1, 2, 3
@@ -35,7 +35,7 @@ SYMBOLS = [
     "bmb200_result_free", "bmb200_aggregate_host", "bmb200_rs_build", "bmb200_rs_export", "bmb200_rs_total",
     "bmb200_rank_batch", "bmb200_select_batch", "bmb200_rank_batch_dev", "bmb200_select_batch_dev",
     "bmb200_rs_free", "bmb200_rs_rebuild", "bmb200_aggregate_batch", "bmb200_result_group_totals", "bmb200_result_or_target",
-    "bmb200_scan",
+    "bmb200_scan", "bmb200_set_upload_blobs",
 ]
 
 
@@ -66,6 +66,10 @@ class BatchArgsC(C.Structure):
         ("members", C.c_void_p), ("offsets", C.c_void_p),
         ("nb_from", C.c_uint32), ("nb_to", C.c_uint32),
     ]
+
+
+class BlobC(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("size", C.c_uint64)]
 
 
 class ScanArgsC(C.Structure):
@@ -230,6 +234,18 @@ class DeviceSet:
             arr[i] = VecBlocksC(v.n_blocks, ptr(kind), ptr(ptrs))
         h = C.c_void_p(0)
         ctx.check(lib().bmb200_set_upload_vectors(ctx._h, len(vectors), int(n_blocks), arr, C.byref(h)), "set_upload_vectors")
+        return cls(ctx, h)
+
+    @classmethod
+    def upload_blobs(cls, ctx: Context, blobs, n_blocks: int) -> "DeviceSet":
+        """bmb200_set_upload_blobs: every vector arrives as a BitMagic serialization BLOB (bytes / uint8 array) and is decoded
+        on the GPU (deserialize-to-device); raises BMB200Error(ERR_UNSUPPORTED) for encodings the device decoder does not cover."""
+        arrs = [np.ascontiguousarray(np.frombuffer(b, dtype=np.uint8) if isinstance(b, (bytes, bytearray)) else b, dtype=np.uint8) for b in blobs]
+        carr = (BlobC * len(arrs))()
+        for i, a in enumerate(arrs):
+            carr[i].data = a.ctypes.data; carr[i].size = a.size
+        h = C.c_void_p(0)
+        ctx.check(lib().bmb200_set_upload_blobs(ctx._h, len(arrs), int(n_blocks), carr, C.byref(h)), "set_upload_blobs")
         return cls(ctx, h)
 
     @classmethod

@@ -12,6 +12,7 @@
 #include "aux_kernels.cuh"
 #include "scan_kernel.cuh"
 #include "shift_kernel.cuh"
+#include "blob_kernel.cuh"
 
 using namespace bmb200;
 
@@ -32,6 +33,8 @@ struct bmb200_ctx {
     bmb200_set* host_set = nullptr;         // device arena kept between bmb200_aggregate_host calls (cudaMalloc/cudaFree
     bmb200_result* host_res = nullptr;      //   of a multi-GB arena costs ~100 ms per call otherwise)
     size_t cap_desc = 0, cap_base = 0, cap_bit = 0, cap_gap = 0;
+    uint8_t* h_stage = nullptr;             // pinned staging for serialized BLOBs (bmb200_set_upload_blobs), grown on demand
+    size_t h_stage_cap = 0;
     int gap_mode = 0;                       // 0 = stream sorted GAP lists through the smem ring, 1 = always gather
     bool attr_set = false;
 };
@@ -131,6 +134,7 @@ const char* bmb200_error_msg(int code)
     case BMB200_ERR_RS_IDX_MISSING: return "rank-select index missing";
     case BMB200_ERR_CUDA: return "CUDA runtime error (see bmb200_last_error)";
     case BMB200_ERR_NODEVICE: return "no sm_100 (B200) device available; libbmb200 has no CPU fallback";
+    case BMB200_ERR_UNSUPPORTED: return "serialized BLOB uses a block encoding the device decoder does not cover";
     default: return "unknown error";
     }
 }
@@ -175,6 +179,7 @@ int bmb200_destroy(bmb200_ctx* ctx)
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     cudaFree(ctx->d_work); cudaFree(ctx->d_group);
     if (ctx->h_group) cudaFreeHost(ctx->h_group);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     delete ctx;
     return BMB200_OK;
 }
@@ -348,6 +353,176 @@ int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks
     if (hb) cudaFreeHost(hb);
     if (hg) cudaFreeHost(hg);
     return rc;
+}
+
+/* ---- deserialize-to-device: host side = token walk only (type + payload extent of every block), no decoding ---- */
+namespace {
+struct BlobTok { uint32_t nb; uint32_t type; uint64_t off; uint32_t aux, first; uint32_t gap_words; uint8_t kind; };
+
+struct ByteRd {
+    const uint8_t* b; uint64_t n, p = 0; bool bad = false;
+    uint32_t u8()  { if (p + 1 > n) { bad = true; return 0; } return b[p++]; }
+    uint32_t u16() { uint32_t a = u8(); return a | (u8() << 8); }
+    uint32_t u32() { uint32_t a = u16(); return a | (u16() << 16); }
+    void skip(uint64_t k) { if (p + k > n) bad = true; else p += k; }
+};
+
+// walks one serialized bvector (src/bmserial.h:5578-6090 token loop); appends one BlobTok per BIT / GAP block, marks FULL blocks
+int walk_blob(const uint8_t* blob, uint64_t size, uint32_t n_blocks, std::vector<BlobTok>& toks, std::vector<uint8_t>& full)
+{
+    ByteRd r{blob, size};
+    const uint32_t hf = r.u8();
+    if (!(hf & (1u << 3))) r.u8();                                 // byte order
+    if (hf & ((1u << 2) | (1u << 5) | (1u << 6))) return BMB200_ERR_UNSUPPORTED;   // id list / 64-bit / XOR compression
+    if (!(hf & (1u << 4))) r.skip(8);                              // GAP levels
+    if (hf & (1u << 1)) r.u32();                                   // size
+    uint64_t nb = 0;
+    auto ones = [&](uint64_t cnt) { for (uint64_t c = nb; c < nb + cnt && c < n_blocks; ++c) full[c] = 1; nb += cnt; };
+    while (!r.bad) {
+        const uint32_t bt = r.u8();
+        if (r.bad) return BMB200_ERR_BADARG;
+        if (bt & 0x80u) { nb += bt & 0x7fu; continue; }
+        BlobTok t{}; t.nb = (uint32_t)nb; t.off = r.p; bool blk = true;
+        switch (bt) {
+        case 0: case 9: return BMB200_OK;                          // set_block_end / set_block_azero
+        case 1: blk = false; break;
+        case 3: nb += r.u8(); continue;
+        case 5: nb += r.u16(); continue;
+        case 7: nb += r.u32(); continue;
+        case 10: ones(nb < n_blocks ? n_blocks - nb : 0); return BMB200_OK;
+        case 2: ones(1); continue;
+        case 4: ones(r.u8()); continue;
+        case 6: ones(r.u16()); continue;
+        case 8: ones(r.u32()); continue;
+        case 11: t.type = DB_BIT; t.kind = BMB200_BLK_BIT; r.skip(BMB200_BLOCK_BYTES); break;
+        case 17: { const uint32_t head = r.u16(), tail = r.u16(); if (tail >= BMB200_BLOCK_WORDS || head > tail) return BMB200_ERR_BADARG;
+                   t.type = DB_BIT_INTERVAL; t.kind = BMB200_BLK_BIT; r.skip(4ull * (tail - head + 1)); break; }
+        case 22: { uint32_t rt = r.u8(), j = 0;
+                   while (j < BMB200_BLOCK_WORDS && !r.bad) { const uint32_t len = r.u16(); if (rt) r.skip(4ull * len); j += len; rt ^= 1u; }
+                   if (j != BMB200_BLOCK_WORDS) return BMB200_ERR_BADARG;
+                   t.type = DB_BIT_0RUNS; t.kind = BMB200_BLK_BIT; break; }
+        case 34: { uint64_t d0 = r.u32(); d0 |= (uint64_t)r.u32() << 32; t.type = DB_BIT_DIGEST0; t.kind = BMB200_BLK_BIT;
+                   r.skip(128ull * (uint64_t)__builtin_popcountll(d0)); break; }
+        case 16: case 30: { const uint32_t n = r.u16(); t.type = bt == 16 ? DB_ARRBIT : DB_ARRBIT_INV; t.kind = BMB200_BLK_BIT; r.skip(2ull * n); break; }
+        case 14: case 15: { const uint32_t hdr = r.u16(), len = hdr >> 3; if (len < 1 || len > BMB200_GAP_MAX_WORDS - 5) return BMB200_ERR_UNSUPPORTED;
+                   t.type = DB_GAP16; t.kind = BMB200_BLK_GAP; t.first = hdr & 1u; t.gap_words = len + 1; r.skip(2ull * (len - 1)); break; }
+        case 19: { const uint32_t pos = r.u16(); t.type = DB_ARRGAP; t.kind = BMB200_BLK_GAP; t.aux = 1; t.off = r.p - 2;
+                   t.first = pos == 0; t.gap_words = 4; break; }
+        case 18: case 24: { const uint32_t n = r.u16(); if (!n || n > 2048u) return BMB200_ERR_UNSUPPORTED;
+                   const uint64_t a0 = r.p; r.skip(2ull * n); if (r.bad) return BMB200_ERR_BADARG;
+                   const uint32_t first_pos = blob[a0] | ((uint32_t)blob[a0 + 1] << 8);
+                   t.type = bt == 18 ? DB_ARRGAP : DB_ARRGAP_INV; t.kind = BMB200_BLK_GAP; t.aux = n; t.off = a0;
+                   t.first = (first_pos == 0) ^ (bt == 24); t.gap_words = std::min<uint32_t>(2 * n + 2, BMB200_GAP_MAX_WORDS); break; }
+        case 67: {   // set_block_gap_egamma_v3: bit stream of 32-bit words, LSB first: gamma(len-1), start bit, use_gamma bit, values
+                   const uint64_t w0 = r.p; uint64_t acc = 0; uint32_t have = 0, used = 0, zeros = 0;
+                   auto need = [&](uint32_t nbits) { while (have < nbits && !r.bad) { acc |= (uint64_t)r.u32() << have; have += 32; } };
+                   for (;;) { need(1); if (r.bad || (acc & 1ull)) break; acc >>= 1; --have; ++used; if (++zeros > 31) break; }
+                   if (r.bad || zeros > 31) return BMB200_ERR_BADARG;
+                   acc >>= 1; --have; ++used;
+                   uint32_t v = 0; if (zeros) { need(zeros); v = (uint32_t)(acc & ((1ull << zeros) - 1)); acc >>= zeros; have -= zeros; used += zeros; }
+                   const uint32_t len = (v | (1u << zeros)) + 1u;
+                   need(2); const uint32_t start = acc & 1u, use_gamma = (acc >> 1) & 1u; used += 2;
+                   if (use_gamma || len > BMB200_GAP_MAX_WORDS - 5) return BMB200_ERR_UNSUPPORTED;
+                   const uint64_t total_bits = (uint64_t)used + 16ull * (len - 1);
+                   r.p = w0; r.skip(4ull * ((total_bits + 31) / 32));
+                   t.type = DB_GAP_V3; t.kind = BMB200_BLK_GAP; t.off = w0; t.aux = used | (len << 8); t.first = start; t.gap_words = len + 1; break; }
+        default: return BMB200_ERR_UNSUPPORTED;
+        }
+        if (r.bad) return BMB200_ERR_BADARG;
+        if (blk && nb < n_blocks) toks.push_back(t);
+        ++nb;
+    }
+    return BMB200_ERR_BADARG;       // ran off the end without an end token
+}
+}  // namespace
+
+int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, const bmb200_blob* blobs, bmb200_set** out)
+{
+    if (!ctx || !blobs || !out || !n_vec || !n_blocks) return BMB200_ERR_BADARG;
+    for (uint32_t v = 0; v < n_vec; ++v) if (!blobs[v].data || blobs[v].size < 2) return BMB200_ERR_BADARG;
+    std::vector<std::vector<BlobTok>> toks(n_vec);
+    std::vector<uint8_t> full;
+    std::vector<uint32_t> desc; std::vector<uint64_t> bb, gb, stg_off(n_vec);
+    std::vector<BlobRec> recs;
+    try {
+        full.assign((size_t)n_vec * n_blocks, 0);
+        std::vector<uint8_t> fv(n_blocks);
+        uint64_t so = 0;
+        for (uint32_t v = 0; v < n_vec; ++v) {
+            std::fill(fv.begin(), fv.end(), 0);
+            int rc = walk_blob((const uint8_t*)blobs[v].data, blobs[v].size, n_blocks, toks[v], fv);
+            if (rc) return rc;
+            for (uint32_t nb = 0; nb < n_blocks; ++nb) full[(size_t)nb * n_vec + v] = fv[nb];
+            stg_off[v] = so; so += (blobs[v].size + 15ull) & ~15ull;
+        }
+        desc.assign((size_t)n_vec * n_blocks, 0u); bb.assign((size_t)n_blocks + 1, 0); gb.assign((size_t)n_blocks + 1, 0);
+        // per-column layout in vector order; tokens of one vector are already in block order
+        std::vector<size_t> cur(n_vec, 0);
+        for (uint32_t nb = 0; nb < n_blocks; ++nb) {
+            uint64_t nbit = 0, ngap = 0;
+            for (uint32_t v = 0; v < n_vec; ++v) {
+                uint32_t d = full[(size_t)nb * n_vec + v] ? BMB200_BLK_FULL : BMB200_BLK_NULL;
+                if (cur[v] < toks[v].size() && toks[v][cur[v]].nb == nb) {
+                    const BlobTok& t = toks[v][cur[v]++];
+                    BlobRec r{}; r.src = stg_off[v] + t.off; r.type = t.type; r.aux = t.aux;
+                    if (t.kind == BMB200_BLK_BIT) { d = BMB200_BLK_BIT | ((uint32_t)nbit << 2); r.dst = bb[nb] + nbit; ++nbit; }
+                    else {
+                        const uint32_t pad = t.first ? 0u : 1u;
+                        const uint64_t units = (t.gap_words + pad + kGapUnit - 1) / kGapUnit;
+                        if (ngap + units > (uint64_t)BMB200_DESC_REL_MASK) return BMB200_ERR_RANGE;
+                        d = BMB200_BLK_GAP | ((uint32_t)ngap << 2) | (pad ? BMB200_DESC_GAP_PAD : 0u) | BMB200_DESC_GAP_FLAT;
+                        r.dst = gb[nb] + ngap; r.aux2 = pad | (t.first << 1); ngap += units;
+                    }
+                    recs.push_back(r);
+                }
+                desc[(size_t)nb * n_vec + v] = d;
+            }
+            bb[nb + 1] = bb[nb] + nbit; gb[nb + 1] = gb[nb] + ngap;
+        }
+    } catch (...) { return BMB200_ERR_BADALLOC; }
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t n_bit = bb[n_blocks], n_gap = gb[n_blocks];
+    bmb200_set* s = nullptr;
+    int rc = set_alloc(ctx, n_vec, n_blocks, n_bit, n_gap, &s);
+    if (rc) return rc;
+    uint64_t stg_bytes = 0; for (uint32_t v = 0; v < n_vec; ++v) stg_bytes = stg_off[v] + ((blobs[v].size + 15ull) & ~15ull);
+    uint8_t* d_stg = nullptr; BlobRec* d_recs = nullptr;
+    cudaStream_t st = ctx->stream;
+    cudaError_t e = cudaMalloc((void**)&d_stg, stg_bytes + 64);
+    if (e == cudaSuccess && !recs.empty()) e = cudaMalloc((void**)&d_recs, recs.size() * sizeof(BlobRec));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_stg + stg_bytes, 0, 64, st);
+    // the compressed bytes are all that crosses PCIe (plus descriptors and the token table): gathered into one pinned
+    // buffer so the copy is a single DMA at link speed instead of one pageable copy per vector
+    if (e == cudaSuccess && stg_bytes > ctx->h_stage_cap) {
+        cudaStreamSynchronize(st);
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+        e = cudaMallocHost((void**)&ctx->h_stage, stg_bytes);
+        if (e == cudaSuccess) ctx->h_stage_cap = stg_bytes;
+    }
+    if (e == cudaSuccess) {
+        cudaStreamSynchronize(st);                     // a previous call may still be reading the staging buffer
+        for (uint32_t v = 0; v < n_vec; ++v) memcpy(ctx->h_stage + stg_off[v], blobs[v].data, blobs[v].size);
+        e = cudaMemcpyAsync(d_stg, ctx->h_stage, stg_bytes, cudaMemcpyHostToDevice, st);
+    }
+    if (e == cudaSuccess && !recs.empty()) e = cudaMemcpyAsync(d_recs, recs.data(), recs.size() * sizeof(BlobRec), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync((void*)s->v.desc, desc.data(), desc.size() * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync((void*)s->v.bit_base, bb.data(), bb.size() * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync((void*)s->v.gap_base, gb.data(), gb.size() * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && n_gap) e = cudaMemsetAsync((void*)s->v.gap_pool, 0, n_gap * 16ull, st);   // fill + holes of the FLAT form
+    if (e == cudaSuccess && !recs.empty()) {
+        uint32_t grid = (uint32_t)std::min<size_t>(recs.size(), (size_t)ctx->sm_count * 16u);
+        blob_decode_kernel<<<grid, kBlobThreads, 0, st>>>(d_stg, d_recs, (uint32_t)recs.size(), (uint32_t*)s->v.bit_pool, (uint16_t*)s->v.gap_pool);
+        rc = after_launch(ctx);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(st);      // recs / desc staging vectors go out of scope
+    cudaFree(d_stg); cudaFree(d_recs);
+    if (e != cudaSuccess || e2 != cudaSuccess || rc) {
+        if (!rc) { ctx->last_err = std::string("set_upload_blobs: ") + cudaGetErrorString(e != cudaSuccess ? e : e2); rc = BMB200_ERR_CUDA; }
+        free_set_arrays(s); delete s; return rc;
+    }
+    *out = s;
+    return BMB200_OK;
 }
 
 int bmb200_set_adopt_device(bmb200_ctx* ctx, const bmb200_packed_set* d, bmb200_set** out)

@@ -20,6 +20,7 @@
  *   bmb200_aggregate  OP_SHIFT_R_AND <- aggregator::combine_shift_right_and  src/bmaggregator.h:2494-2669
  *   BMB200_F_COUNT_ONLY           <- bm::count_and/or/xor/sub      src/bmalgo.h:48-51, pipeline counts src/bmaggregator.h:1397
  *   bmb200_result_optimize        <- blocks_manager::opt_copy_bit_block src/bmblocks.h:1355-1409
+ *   bmb200_set_upload_blobs       <- bm::deserialize / deserializer<BV>::deserialize  src/bmserial.h:4152,5578-6090
  *   bmb200_scan                   <- sparse_vector_scanner::find_eq/find_gt/find_ge/find_lt/find_le/find_range
  *                                                                   src/bmsparsevec_algo.h:1083-1182,2593-2632,4360-4395
  *   bmb200_rs_build               <- bvector::build_rs_index       src/bm.h:2531-2660, rs_index src/bmrs.h:688-715
@@ -49,6 +50,7 @@ extern "C" {
 #define BMB200_ERR_RS_IDX_MISSING  7
 #define BMB200_ERR_CUDA            200  /* a CUDA runtime call failed; see bmb200_last_error */
 #define BMB200_ERR_NODEVICE        201  /* no sm_100 device: this library has NO CPU fallback */
+#define BMB200_ERR_UNSUPPORTED     202  /* serialized BLOB uses a block encoding the device decoder does not cover */
 
 /* ---- geometry ---- */
 #define BMB200_BLOCK_WORDS     2048u
@@ -183,6 +185,15 @@ int bmb200_set_upload(bmb200_ctx* ctx, const bmb200_packed_set* host, bmb200_set
 /* gather per-vector block pointers (the host block tree) into a packed device set */
 int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks,
                               const bmb200_vec_blocks* vecs, bmb200_set** out);
+/* deserialize-to-device: vector v of the set arrives as a BitMagic serialization BLOB (bm::serializer<>, src/bmserial.h) and
+ * is decoded on the GPU straight into the arena -- what bm::deserialize(bv, buf) (src/bmserial.h:4152) + an upload of the
+ * materialised blocks would produce (same bits, same block kinds), with only the compressed bytes crossing PCIe.
+ * Covered: every block encoding whose length is explicit in the stream (serializer compression levels 0..2 completely:
+ * zero / one runs, plain bit, bit interval, bit 0-runs, bit digest0, single bit, GAP with 16-bit run ends; plus the
+ * bit / GAP position arrays of level 3).  BLOBs with gamma / interpolative / XOR / super-block encodings return
+ * BMB200_ERR_UNSUPPORTED (no CPU fallback). */
+typedef struct bmb200_blob { const void* data; uint64_t size; } bmb200_blob;
+int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, const bmb200_blob* blobs, bmb200_set** out);
 /* adopt pointers that already live in HBM (caller keeps ownership of the memory) */
 int bmb200_set_adopt_device(bmb200_ctx* ctx, const bmb200_packed_set* dev, bmb200_set** out);
 /* sizes: total bit blocks, total GAP 16-B units, stored bytes of all source blocks */

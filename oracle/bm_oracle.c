@@ -457,6 +457,152 @@ int orc_aggregate(const bmb200_packed_set* s, const bmb200_agg_args* a,
 }
 
 /* ------------------------------------------------------------------ */
+/* bm::deserialize (src/bmserial.h:4152, deserializer::deserialize :5578-6090) into an EMPTY vector, restated for the
+ * tokens whose length is explicit in the stream (what serializer levels 0..2 emit, plus the array tokens of level 3):
+ *   zero / one runs (set_block_1zero .. set_block_aone, the 0x80 | n short zero run :5716-5722), set_block_bit :5493,
+ *   set_block_bit_1bit :5825, set_block_bit_0runs :4738, set_block_bit_interval :5511, set_block_bit_digest0 (read_digest0_block),
+ *   set_block_arrbit :5539, set_block_arrbit_inv :5424, set_block_gap / _gapbit :5243-5300, set_block_arrgap(_inv) :4833-4845,
+ *   set_block_gap_egamma_v3 with plain 16-bit values :5050-5082 (bit stream: 32-bit words, LSB first, src/encoding.h:1313,2506).
+ * Block kinds follow the reference: bit tokens -> bit-blocks, GAP / array-of-GAP tokens and single bits -> GAP blocks
+ * (new_blocks_strat BM_GAP, :5687), capacity level from gap_calc_level(gap_length).  Returns BMB200_ERR_UNSUPPORTED for
+ * every other token (gamma / interpolative / XOR / super-block / bookmark encodings). */
+typedef struct { const uint8_t* p; const uint8_t* end; } rd_t;
+static uint32_t rd8(rd_t* r)  { if (r->p + 1 > r->end) { r->p = r->end + 1; return 0; } return *r->p++; }
+static uint32_t rd16(rd_t* r) { uint32_t a = rd8(r); return a | (rd8(r) << 8); }
+static uint32_t rd32(rd_t* r) { uint32_t a = rd16(r); return a | (rd16(r) << 16); }
+static uint64_t rd64(rd_t* r) { uint64_t a = rd32(r); return a | ((uint64_t)rd32(r) << 32); }
+
+static void gap_from_sorted(uint16_t* g, const uint16_t* a, uint32_t n, int invert)
+{   /* gap_set_array (src/bmfunc.h) + optional gap_invert: positions a[0..n) ascending */
+    uint32_t len = 0, first = (n && a[0] == 0) ? 1u : 0u;
+    for (uint32_t k = 0; k < n; ) {
+        uint32_t s = a[k], e = s;
+        while (k + 1 < n && a[k + 1] == e + 1) { ++k; ++e; }
+        ++k;
+        if (s > 0) g[++len] = (uint16_t)(s - 1);
+        if (e < 65535) g[++len] = (uint16_t)e;
+    }
+    g[++len] = 65535;
+    int level = gap_calc_level(len + 1); if (level < 0) level = 3;
+    g[0] = (uint16_t)((first ^ (invert ? 1u : 0u)) | ((uint32_t)level << 1) | (len << 3));
+}
+
+int orc_deserialize(const uint8_t* blob, uint64_t size, uint32_t n_cols, uint8_t* kind, uint32_t* blocks, uint16_t* gaps)
+{
+    rd_t r = { blob, blob + size };
+    memset(kind, 0, n_cols);
+    if (blocks) memset(blocks, 0, (size_t)n_cols * BMB200_BLOCK_BYTES);
+    if (gaps) memset(gaps, 0, (size_t)n_cols * GMAX * 2);
+    uint32_t hf = rd8(&r);
+    if (!(hf & (1u << 3))) rd8(&r);                       /* byte order (BM_HM_NO_BO) */
+    if (hf & (1u << 5)) return BMB200_ERR_UNSUPPORTED;    /* BM_HM_64_BIT */
+    if (hf & (1u << 2)) return BMB200_ERR_UNSUPPORTED;    /* BM_HM_ID_LIST */
+    if (hf & (1u << 6)) return BMB200_ERR_UNSUPPORTED;    /* BM_HM_HXOR */
+    if (!(hf & (1u << 4))) for (int k = 0; k < 4; ++k) rd16(&r);   /* GAP levels */
+    if (hf & (1u << 1)) rd32(&r);                         /* BM_HM_RESIZE: size */
+    uint32_t* tb = (uint32_t*)malloc(BMB200_BLOCK_BYTES);
+    uint16_t* tg = (uint16_t*)malloc(sizeof(uint16_t) * 65540);
+    uint16_t* arr = (uint16_t*)malloc(sizeof(uint16_t) * 65536);
+    if (!tb || !tg || !arr) { free(tb); free(tg); free(arr); return BMB200_ERR_BADALLOC; }
+    int rc = BMB200_OK;
+    uint64_t nb = 0;
+    while (rc == BMB200_OK && r.p <= r.end) {
+        uint32_t bt = rd8(&r);
+        if (r.p > r.end) { rc = BMB200_ERR_BADARG; break; }
+        if (bt & 0x80u) { nb += bt & 0x7fu; continue; }
+        uint64_t ones = 0; int is_bit = 0, is_gap = 0;
+        switch (bt) {
+        case 0: case 9: nb = 1ull << 40; break;                           /* set_block_end / set_block_azero */
+        case 1: break;                                                    /* set_block_1zero */
+        case 3: nb += rd8(&r); continue;
+        case 5: nb += rd16(&r); continue;
+        case 7: nb += rd32(&r); continue;
+        case 10: ones = (nb < n_cols) ? n_cols - nb : 0; for (uint64_t c = nb; c < n_cols; ++c) kind[c] = BMB200_BLK_FULL; nb = 1ull << 40; break;
+        case 2: ones = 1; break;
+        case 4: ones = rd8(&r); break;
+        case 6: ones = rd16(&r); break;
+        case 8: ones = rd32(&r); break;
+        case 11: for (uint32_t i = 0; i < BW; ++i) tb[i] = rd32(&r); is_bit = 1; break;
+        case 19: { arr[0] = (uint16_t)rd16(&r); gap_from_sorted(tg, arr, 1, 0); is_gap = 1; break; }
+        case 22: {
+            memset(tb, 0, BMB200_BLOCK_BYTES);
+            uint32_t run_type = rd8(&r);
+            for (uint32_t j = 0; j < BW && r.p <= r.end; run_type = !run_type) {
+                uint32_t run_len = rd16(&r);
+                if (run_type) { uint32_t e = j + run_len; if (e > BW) { rc = BMB200_ERR_BADARG; break; } for (; j < e; ++j) tb[j] = rd32(&r); }
+                else j += run_len;
+            }
+            is_bit = 1; break; }
+        case 17: {
+            uint32_t head = rd16(&r), tail = rd16(&r);
+            memset(tb, 0, BMB200_BLOCK_BYTES);
+            if (tail >= BW || head > tail) { rc = BMB200_ERR_BADARG; break; }
+            for (uint32_t i = head; i <= tail; ++i) tb[i] = rd32(&r);
+            is_bit = 1; break; }
+        case 34: {
+            uint64_t d0 = rd64(&r);
+            memset(tb, 0, BMB200_BLOCK_BYTES);
+            for (uint32_t w = 0; w < 64; ++w) if ((d0 >> w) & 1u) for (uint32_t i = 0; i < 32; ++i) tb[w * 32 + i] = rd32(&r);
+            is_bit = 1; break; }
+        case 16: case 30: {
+            uint32_t n = rd16(&r);
+            memset(tb, bt == 30 ? 0xFF : 0, BMB200_BLOCK_BYTES);
+            for (uint32_t k = 0; k < n; ++k) { uint32_t b = rd16(&r); if (bt == 30) tb[b >> 5] &= ~(1u << (b & 31)); else tb[b >> 5] |= 1u << (b & 31); }
+            is_bit = 1; break; }
+        case 14: case 15: {
+            uint32_t hdr = rd16(&r), len = hdr >> 3;
+            if (len < 1 || len + 1 > GMAX) { rc = BMB200_ERR_UNSUPPORTED; break; }
+            for (uint32_t k = 1; k < len; ++k) tg[k] = (uint16_t)rd16(&r);
+            tg[len] = 65535;
+            int level = gap_calc_level(len + 1); if (level < 0) { rc = BMB200_ERR_UNSUPPORTED; break; }
+            tg[0] = (uint16_t)((hdr & 1u) | ((uint32_t)level << 1) | (len << 3));
+            is_gap = 1; break; }
+        case 18: case 24: {
+            uint32_t n = rd16(&r);
+            for (uint32_t k = 0; k < n; ++k) arr[k] = (uint16_t)rd16(&r);
+            gap_from_sorted(tg, arr, n, bt == 24);
+            if ((tg[0] >> 3) + 1u > GMAX - 4) { rc = BMB200_ERR_UNSUPPORTED; break; }
+            is_gap = 1; break; }
+        case 67: {                                                        /* set_block_gap_egamma_v3 */
+            uint64_t acc = 0; uint32_t have = 0;                          /* bit stream of 32-bit words, LSB first */
+            #define NEED(nbits) while (have < (nbits)) { acc |= (uint64_t)rd32(&r) << have; have += 32; }
+            uint32_t zeros = 0;
+            for (;;) { NEED(1) if (acc & 1u) break; acc >>= 1; --have; ++zeros; if (zeros > 31) break; }
+            if (zeros > 31) { rc = BMB200_ERR_BADARG; break; }
+            acc >>= 1; --have;
+            uint32_t v = 0; if (zeros) { NEED(zeros) v = (uint32_t)(acc & ((1ull << zeros) - 1)); acc >>= zeros; have -= zeros; }
+            uint32_t len = (v | (1u << zeros)) + 1u;                       /* gamma() + 1 */
+            NEED(2) uint32_t start = (uint32_t)(acc & 1u), use_gamma = (uint32_t)((acc >> 1) & 1u); acc >>= 2; have -= 2;
+            if (use_gamma) { rc = BMB200_ERR_UNSUPPORTED; break; }
+            if (len + 1 > GMAX) { rc = BMB200_ERR_UNSUPPORTED; break; }
+            for (uint32_t k = 1; k < len; ++k) { NEED(16) tg[k] = (uint16_t)(acc & 0xffffu); acc >>= 16; have -= 16; }
+            #undef NEED
+            tg[len] = 65535;
+            int level = gap_calc_level(len + 1); if (level < 0) { rc = BMB200_ERR_UNSUPPORTED; break; }
+            tg[0] = (uint16_t)(start | ((uint32_t)level << 1) | (len << 3));
+            is_gap = 1; break; }
+        default: rc = BMB200_ERR_UNSUPPORTED; break;
+        }
+        if (rc != BMB200_OK) break;
+        if (r.p > r.end) { rc = BMB200_ERR_BADARG; break; }
+        if (ones && bt != 10) { for (uint64_t c = nb; c < nb + ones && c < n_cols; ++c) kind[c] = BMB200_BLK_FULL; nb += ones; continue; }
+        if (nb < n_cols) {
+            if (is_bit) { kind[nb] = BMB200_BLK_BIT; if (blocks) memcpy(blocks + nb * BW, tb, BMB200_BLOCK_BYTES); }
+            if (is_gap) {
+                kind[nb] = BMB200_BLK_GAP;
+                if (gaps) memcpy(gaps + nb * GMAX, tg, ((size_t)(tg[0] >> 3) + 1) * 2);
+                if (blocks) orc_gap_convert_to_bitset(blocks + nb * BW, tg);
+            }
+        }
+        if (nb >= (1ull << 40)) break;
+        ++nb;
+    }
+    if (blocks) for (uint32_t c = 0; c < n_cols; ++c) if (kind[c] == BMB200_BLK_FULL) memset(blocks + (size_t)c * BW, 0xFF, BMB200_BLOCK_BYTES);
+    free(tb); free(tg); free(arr);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ */
 /* sparse_vector_scanner searches, restated from their contract (src/bmsparsevec_algo.h:1083-1176: "search result is a
  * vector of 1s when sv[i] == / > / >= / < / <= value", find_range: closed interval [from, to]; NULL elements and
  * indexes >= size() never match, :2426 finalize_search_result, :1686 invert_internal).  Element i of the sparse

@@ -26,6 +26,7 @@
 #include "bmaggregator.h"
 #include "bmalgo.h"
 #include "bmrs.h"
+#include "bmserial.h"
 #include "bmsparsevec.h"
 #include "bmsparsevec_algo.h"
 
@@ -460,6 +461,37 @@ int ref_sv_scan(const uint32_t* values, const uint8_t* nulls, uint64_t n, int pr
             size_t o = (size_t)k * n_cols;
             export_bvector(bv, n_cols, kind ? kind + o : 0, popcnt ? popcnt + o : 0, blocks ? blocks + o * BMB200_BLOCK_WORDS : 0, 0);
         }
+        return 0;
+    } catch (...) { return 1; }
+}
+
+/*
+ * bm::serializer<> / bm::deserialize (src/bmserial.h) on the real reference.
+ *   ref_serialize:   vector v of the packed set -> BLOB at the given compression level (serializer::set_compression_level,
+ *                    :1454), default header (byte order + GAP levels).  *size = bytes written (<= cap).
+ *   ref_deserialize: BLOB -> bvector (bm::deserialize, :4152) -> per-column kind / popcount / bits / GAP words.
+ */
+int ref_serialize(const bmb200_packed_set* s, uint32_t v, int level, unsigned char* out, uint64_t cap, uint64_t* size)
+{
+    try {
+        bvect bv; build_bvector(s, v, 0, s->n_blocks, bv);
+        bm::serializer<bvect> ser;
+        ser.set_compression_level((unsigned)level);
+        bm::serializer<bvect>::buffer buf;
+        ser.serialize(bv, buf);
+        if (buf.size() > cap) return 3;
+        std::memcpy(out, buf.data(), buf.size());
+        *size = buf.size();
+        return 0;
+    } catch (...) { return 1; }
+}
+
+int ref_deserialize(const unsigned char* blob, uint32_t n_cols, uint8_t* kind, uint32_t* popcnt, uint32_t* blocks, uint16_t* gaps)
+{
+    try {
+        bvect bv;
+        bm::deserialize(bv, blob);
+        export_bvector(bv, n_cols, kind, popcnt, blocks, gaps);
         return 0;
     } catch (...) { return 1; }
 }

@@ -43,6 +43,16 @@ def load_scan(name):
     return ps, z["values"], (z["nulls"] if z["nulls"].size else None), cases
 
 
+def load_blobs(name="blobs"):
+    """-> n_vec, n_blocks, {level: [blob per vector]}, {level: [kind per vector]}, [bits per vector], {level: [flat GAP words per vector]}"""
+    z = np.load(GOLDEN / f"{name}.npz")
+    nv, nb = int(z["n_vec"]), int(z["n_blocks"])
+    blobs = {int(l): [z[f"l{int(l)}_v{v}_blob"] for v in range(nv)] for l in z["levels"]}
+    kinds = {int(l): [z[f"l{int(l)}_v{v}_kind"] for v in range(nv)] for l in z["levels"]}
+    gaps = {int(l): [z[f"l{int(l)}_v{v}_gaps"] for v in range(nv)] for l in z["levels"]}
+    return nv, nb, blobs, kinds, [z[f"v{v}_blk"] for v in range(nv)], gaps
+
+
 def check_agg_case(case, kind, pop, blocks, gaps_flat=None, check_kind=True):
     """Compare one aggregate output (kind[n], pop[n], blocks[n][2048], optional concatenated GAP words) with the fixture."""
     assert np.array_equal(blocks, case["blk"]), "result bits differ from the reference"

@@ -265,3 +265,32 @@ def ref_sv_time_scan(values, nulls, pred, search, repeats=2):
                                 int(repeats), C.byref(sec), C.byref(tot))
     assert rc == 0, f"ref_sv_time_scan rc={rc}"
     return sec.value, tot.value
+
+
+def ref_serialize(ps, v, level):
+    """bm::serializer<> at `level` on vector v of the packed set -> bytes"""
+    cap = int(ps.n_blocks) * 8300 + 4096
+    out = np.zeros(cap, np.uint8); size = C.c_uint64(0)
+    c = _pc(ps)
+    rc = ref().ref_serialize(C.byref(c), C.c_uint32(v), int(level), ptr(out), C.c_uint64(cap), C.byref(size))
+    assert rc == 0, f"ref_serialize rc={rc}"
+    return out[:size.value].copy()
+
+
+def ref_deserialize(blob, n_cols):
+    """bm::deserialize -> kind, popcnt, blocks[n_cols][2048], gaps[n_cols][1280]"""
+    b = np.ascontiguousarray(blob, dtype=np.uint8)
+    kind = np.zeros(n_cols, np.uint8); pop = np.zeros(n_cols, np.uint32)
+    blocks = np.zeros((n_cols, BLOCK_WORDS), np.uint32); gaps = np.zeros((n_cols, GAP_MAX_WORDS), np.uint16)
+    rc = ref().ref_deserialize(ptr(b), C.c_uint32(n_cols), ptr(kind), ptr(pop), ptr(blocks), ptr(gaps))
+    assert rc == 0, f"ref_deserialize rc={rc}"
+    return kind, pop, blocks, gaps
+
+
+def oracle_deserialize(blob, n_cols):
+    """orc_deserialize -> rc, kind, blocks[n_cols][2048], gaps[n_cols][1280]"""
+    b = np.ascontiguousarray(blob, dtype=np.uint8)
+    kind = np.zeros(n_cols, np.uint8)
+    blocks = np.zeros((n_cols, BLOCK_WORDS), np.uint32); gaps = np.zeros((n_cols, GAP_MAX_WORDS), np.uint16)
+    rc = oracle().orc_deserialize(ptr(b), C.c_uint64(b.size), C.c_uint32(n_cols), ptr(kind), ptr(blocks), ptr(gaps))
+    return rc, kind, blocks, gaps

@@ -54,3 +54,16 @@ def test_oracle_scan_vs_golden(name):
     live = np.ones(vals.size, bool) if nulls is None else nulls == 0
     kind, pop, dig, nr, blk, gaps = orclib.oracle_scan(ps, bm.SCAN_EQ, [55], 0, npl, npl, 0)
     assert int(pop.sum()) == int(((vals == 55) & live).sum())
+
+
+def test_oracle_deserialize_vs_golden():
+    """orc_deserialize on the committed serializer BLOBs (levels 0..2) == the committed bm::deserialize output."""
+    nv, nb, blobs, kinds, blks, gapsf = gu.load_blobs()
+    for level, bl in blobs.items():
+        for v in range(nv):
+            rc, kind, blk, gaps = orclib.oracle_deserialize(bl[v], nb)
+            assert rc == 0
+            assert np.array_equal(kind, kinds[level][v]) and np.array_equal(blk, blks[v])
+            glen = np.where(kind == bm.BLK_GAP, (gaps[:, 0] >> 3) + 1, 0)
+            flat = np.concatenate([gaps[c, :glen[c]] for c in range(nb)]) if glen.sum() else np.zeros(0, np.uint16)
+            assert np.array_equal(flat, gapsf[level][v])

@@ -624,3 +624,36 @@ def test_shift_right_and_vs_oracle(ctx, seed):
     res, found = agg.combine_shift_right_and(vecs[:3])
     okind, opop, odig, onr, oblk, ogap = orclib.oracle_aggregate(bm.PackedSet.pack(vecs[:3], 6), bm.OP_SHIFT_R_AND, [0, 1, 2], None, 0)
     assert found == bool(opop.sum()) and np.array_equal(np.stack([res.block_words(c) for c in range(6)]), oblk)
+
+
+def test_deserialize_to_device_vs_golden_and_oracle(ctx):
+    """bmb200_set_upload_blobs: serializer BLOBs (levels 0..2, committed fixtures written by the reference) decoded on the GPU ==
+    bm::deserialize (block kinds, bits, GAP words); the decoded set then aggregates like the plainly uploaded one; BLOBs with
+    entropy-coded blocks are refused loudly."""
+    nv, nb, blobs, kinds, blks, gapsf = gu.load_blobs()
+    for level, bl in blobs.items():
+        dset = bm.DeviceSet.upload_blobs(ctx, bl, nb)
+        ps = dset.download()
+        isgap = (ps.desc & 3) == bm.BLK_GAP
+        assert ((ps.desc[isgap] >> 30) & 1).all()                      # decoded GAP blocks are in the flat-streamable form
+        for v in range(nv):
+            bv = ps.vector(v)
+            assert np.array_equal(bv.kind, kinds[level][v]), f"level {level} vector {v}: kinds"
+            assert np.array_equal(np.stack([bv.block_words(c) for c in range(nb)]), blks[v]), f"level {level} vector {v}: bits"
+            flat = [bv.blocks[c] for c in range(nb) if bv.kind[c] == bm.BLK_GAP]
+            assert np.array_equal(np.concatenate(flat) if flat else np.zeros(0, np.uint16), gapsf[level][v]), f"level {level} vector {v}: GAP words"
+        check_vs_oracle(ctx, ps, bm.OP_OR, list(range(nv)), None, C, dset)
+        check_vs_oracle(ctx, ps, bm.OP_AND_SUB, [0, 1], list(range(2, nv)), C, dset)
+        rs = bm.DeviceRS(ctx, dset, 3)
+        pos = np.arange(0, nb * 65536, 997, dtype=np.uint64)
+        assert np.array_equal(rs.rank(pos), orclib.oracle_rank(ps, 3, pos))
+        rs.free(); dset.free()
+    if orclib.have_ref():
+        import test_oracle_vs_reference as tor
+        psr = bm.PackedSet.pack(tor.blob_inputs())
+        bad = [orclib.ref_serialize(psr, v, 5) for v in range(psr.n_vec)]
+        with pytest.raises(bm.BMB200Error) as e:
+            bm.DeviceSet.upload_blobs(ctx, bad, psr.n_blocks)
+        assert e.value.code == bm.capi.ERR_UNSUPPORTED
+    with pytest.raises(bm.BMB200Error):
+        bm.DeviceSet.upload_blobs(ctx, [blobs[2][0][: blobs[2][0].size // 2]], nb)

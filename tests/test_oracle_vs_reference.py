@@ -260,3 +260,49 @@ def test_shift_right_and_oracle_matches_reference(seed):
     want[:2] = 0                                        # v_0 contributes zeros shifted in from before position 0
     got = np.unpackbits(oblk.reshape(-1).view(np.uint8), bitorder="little")
     assert got.any() and np.array_equal(got, want)
+
+
+def blob_inputs(seed=5, n_blocks=12):
+    """Vectors that make the serializer pick every explicit-length block encoding: mixed kinds, edge GAP blocks, a single-bit
+    block, a narrow interval, sparse words (0-runs / digest0), an almost-full block, long zero / one block runs."""
+    rng = np.random.default_rng(seed)
+    vecs = gen.mixed_vectors(rng, 10, n_blocks, p_null=0.15, p_full=0.15, p_gap=0.4) + gen.edge_vectors(n_blocks)
+    v = bm.BVector(n_blocks)
+    w = np.zeros(2048, np.uint32); w[100] = 1 << 7; v.set_bits(0, w)
+    w = np.zeros(2048, np.uint32); w[500:520] = rng.integers(1, 2**32, 20, dtype=np.uint64).astype(np.uint32); v.set_bits(1, w)
+    w = np.zeros(2048, np.uint32); w[::64] = 0xFFFF0000; v.set_bits(2, w)
+    w = np.full(2048, 0xFFFFFFFF, np.uint32); w[7] = 0xFFFFFFF7; v.set_bits(3, w)
+    w = np.zeros(2048, np.uint32); w[3] = 5; w[900] = 1 << 31; w[2047] = 1; v.set_bits(4, w)
+    for nb in range(6, n_blocks):
+        v.set_full(nb)
+    vecs.append(v)
+    v = bm.BVector(n_blocks); v.set_gap(n_blocks - 1, gen.gap_from_runs([65534, 65535], 0)); v.set_gap(0, gen.gap_from_runs([0, 65535], 1)); vecs.append(v)
+    return vecs
+
+
+@needs_ref
+def test_deserialize_oracle_matches_reference():
+    """orc_deserialize == bm::deserialize on BLOBs written by bm::serializer<> at every compression level: exact (bits, block
+    kinds, GAP bytes) for levels 0..2, and never silently wrong above (either exact or BMB200_ERR_UNSUPPORTED)."""
+    vecs = blob_inputs()
+    ps = bm.PackedSet.pack(vecs)
+    seen = set()
+    for level in range(0, 7):
+        n_ok = 0
+        for v in range(ps.n_vec):
+            blob = orclib.ref_serialize(ps, v, level)
+            rkind, rpop, rblk, rgap = orclib.ref_deserialize(blob, ps.n_blocks)
+            assert np.array_equal(rblk, np.stack([vecs[v].block_words(c) for c in range(ps.n_blocks)]))
+            rc, kind, blk, gaps = orclib.oracle_deserialize(blob, ps.n_blocks)
+            if level <= 2:
+                assert rc == 0, f"level {level} vector {v}: rc={rc}"
+            else:
+                assert rc in (0, 202)
+            if rc == 0:
+                n_ok += 1
+                assert np.array_equal(blk, rblk) and np.array_equal(kind, rkind) and np.array_equal(gaps, rgap), f"level {level} vector {v}"
+        if level <= 2:
+            assert n_ok == ps.n_vec
+    # truncated / corrupt streams are rejected, not read past the end
+    blob = orclib.ref_serialize(ps, 0, 2)
+    assert orclib.oracle_deserialize(blob[: blob.size // 2], ps.n_blocks)[0] != 0
