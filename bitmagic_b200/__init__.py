@@ -10,7 +10,7 @@ from .capi import (BLK_BIT, BLK_FULL, BLK_GAP, BLK_NULL, F_COUNT_ONLY, F_OPT_COM
                    SCAN_EQ, SCAN_GE, SCAN_GT, SCAN_LE, SCAN_LT, SCAN_RANGE, NO_UNIVERSE)
 from .hostfmt import BVector, PackedSet, result_to_bvector
 from .scanner import SparseVector, SparseVectorScanner
-from .aggregator import (OPT_COMPRESS, OPT_NONE, Aggregator, Pipeline, RSIndex, bit_and, bit_or, bit_sub, bit_xor,
+from .aggregator import (OPT_COMPRESS, OPT_NONE, Aggregator, Pipeline, RSIndex, bit_and, bit_or, bit_or_and, bit_sub, bit_xor, merge,
                          build_rs_index, count_and, count_or, count_sub, count_xor)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

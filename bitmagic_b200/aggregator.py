@@ -244,6 +244,16 @@ def bit_sub(a: BVector, b: BVector, opt_mode: int = OPT_NONE, ctx=None) -> BVect
     return _binop("sub", a, b, opt_mode, ctx)
 
 
+def bit_or_and(target: BVector, a: BVector, b: BVector, opt_mode: int = OPT_NONE, ctx=None) -> BVector:
+    """bvector::bit_or_and (src/bm.h:1787,6283): target | (a & b) -- two launches."""
+    return bit_or(target, bit_and(a, b, opt_mode, ctx), opt_mode, ctx)
+
+
+def merge(target: BVector, src: BVector, ctx=None) -> BVector:
+    """bvector::merge (src/bm.h:1000,5883): target | src (the reference may steal src's blocks; here src is left untouched)."""
+    return bit_or(target, src, OPT_NONE, ctx)
+
+
 def _count(op, a, b, ctx=None) -> int:
     ctx = ctx or capi.default_context()
     if op == "sub":

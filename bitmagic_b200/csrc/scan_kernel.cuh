@@ -59,7 +59,7 @@ __device__ __forceinline__ void scan_step(uint4& eq, uint4& gt, const uint4& P, 
 
 __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) scan_kernel(const ScanParams sp)
 {
-    __shared__ __align__(16) uint32_t K[kBlockWords];
+    __shared__ __align__(16) uint32_t K[kScanBatch][kBlockWords];   // expansion buffers: the GAP planes of one batch are expanded together
     __shared__ uint32_t s_desc[65];                          // descriptors of the planes (+ universe) of this column
     __shared__ uint32_t s_col;
     __shared__ uint32_t s_pc[kAggWarps], s_tr[kAggWarps], s_dg[kAggWarps];
@@ -67,8 +67,8 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) scan_kernel(const Sca
     const AggParams& p = sp.out;
     const int tid = threadIdx.x;
     const uint32_t M = p.set.n_vec;
-    uint4* K4 = reinterpret_cast<uint4*>(K);
-    const uint32_t Ks = smem_u32(K);
+    uint4* K4 = reinterpret_cast<uint4*>(K[0]);
+    const uint32_t Ks = smem_u32(K[0]);
     const bool is_range = (sp.pred == BMB200_SCAN_RANGE);
 
     uint32_t next_item = 0;
@@ -118,17 +118,34 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) scan_kernel(const Sca
         for (int jt = (int)sp.n_planes - 1; jt >= 0; jt -= kScanBatch) {
             uint4 P[kScanBatch];
             uint32_t d[kScanBatch];
+            bool any_gap = false;
 #pragma unroll
             for (int u = 0; u < kScanBatch; ++u) {           // issue the bit-plane loads of the batch together
                 const int j = jt - u;
                 d[u] = (j >= 0) ? s_desc[j] : BMB200_BLK_NULL;
-                if ((d[u] & 3u) != BMB200_BLK_GAP) P[u] = load_now(d[u]);
+                if ((d[u] & 3u) != BMB200_BLK_GAP) P[u] = load_now(d[u]); else any_gap = true;
+            }
+            if (any_gap) {                                   // uniform: the GAP planes of the batch share one pair of barriers
+#pragma unroll
+                for (int u = 0; u < kScanBatch; ++u)
+                    if ((d[u] & 3u) == BMB200_BLK_GAP) reinterpret_cast<uint4*>(K[u])[tid] = make_uint4(0u, 0u, 0u, 0u);
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < kScanBatch; ++u)
+                    if ((d[u] & 3u) == BMB200_BLK_GAP) {
+                        const uint32_t rel = d[u] >> 2;
+                        gap_expand_block(Ks + (uint32_t)u * kBlockWords * 4u, gseg + (size_t)(rel & kRelMask) * kGapUnit + (rel >> 29), tid);
+                    }
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < kScanBatch; ++u)
+                    if ((d[u] & 3u) == BMB200_BLK_GAP) P[u] = reinterpret_cast<const uint4*>(K[u])[tid];
+                __syncthreads();                             // the buffers are rewritten by the next batch
             }
 #pragma unroll
             for (int u = 0; u < kScanBatch; ++u) {
                 const int j = jt - u;
                 if (j < 0) break;
-                if ((d[u] & 3u) == BMB200_BLK_GAP) P[u] = load_gap(d[u]);     // uniform branch
                 scan_step(eqA, gtA, P[u], (va >> j) & 1ull);
                 if (is_range) scan_step(eqB, gtB, P[u], (vb >> j) & 1ull);
             }
@@ -146,7 +163,7 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) scan_kernel(const Sca
                            (gtA.z | eqA.z) & U.z & ~gtB.z, (gtA.w | eqA.w) & U.w & ~gtB.w);
             break;
         }
-        finish_block<true>(p, col, colx, vi, R, 2, K, s_pc, s_tr, s_dg);
+        finish_block<true>(p, col, colx, vi, R, 2, K[0], s_pc, s_tr, s_dg);
     }
 }
 

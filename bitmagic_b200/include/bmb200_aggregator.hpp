@@ -380,6 +380,20 @@ template<class BV> void bit_sub(context& c, BV& t, const BV& a, const BV& b)
 template<class BV> void bit_xor(context& c, BV& t, const BV& a, const BV& b, typename BV::optmode opt = BV::opt_none)
 { aggregator<BV> g(c); g.set_optimization(opt); const BV* s[2] = {&a, &b}; g.combine_xor(t, s, 2); }
 
+/// bvector::bit_or_and (src/bm.h:1787,6283): target |= a & b -- two launches (AND, then OR with the target)
+template<class BV> void bit_or_and(context& c, BV& t, const BV& a, const BV& b, typename BV::optmode opt = BV::opt_none)
+{
+    BV tmp; bit_and(c, tmp, a, b, opt);
+    BV res; aggregator<BV> g(c); g.set_optimization(opt); const BV* s[2] = {&t, &tmp}; g.combine_or(res, s, 2);
+    t.swap(res);
+}
+/// bvector::merge (src/bm.h:1000,5883): t |= src; the reference may steal src's blocks, so src is left cleared here too
+template<class BV> void merge(context& c, BV& t, BV& src)
+{
+    BV res; aggregator<BV> g(c); const BV* s[2] = {&t, &src}; g.combine_or(res, s, 2);
+    t.swap(res); src.clear(true);
+}
+
 /// build_rs_index on the GPU, delivered through rs_index's own public mutators
 /// (resize / set_total / set_null_super_block / set_full_super_block / register_super_block,
 ///  src/bmrs.h:70-113) so the unmodified reference query code (count_to / select) can use it.

@@ -125,6 +125,12 @@ int main()
         }
         CHECK(or_ref.compare(or_gpu) == 0, "pipeline OR target");
     }
+    {   // bit_or_and / merge (src/bm.h:6283,5883)
+        bvect t1(*all[5]), t2(*all[5]);
+        t1.bit_or_and(*all[0], *all[7]); bm::b200::bit_or_and(ctx, t2, *all[0], *all[7]); CHECK(t1.compare(t2) == 0, "bit_or_and");
+        bvect m1(*all[2]), m2(*all[2]), s1(*all[13]), s2(*all[13]);
+        m1.merge(s1); bm::b200::merge(ctx, m2, s2); CHECK(m1.compare(m2) == 0 && m1.count() == m2.count(), "merge");
+    }
     {   bvect t1, t2;
         t1.bit_xor(*all[4], *all[11], bvect::opt_none); bm::b200::bit_xor(ctx, t2, *all[4], *all[11]); CHECK(t1.compare(t2) == 0, "bit_xor");
     }
