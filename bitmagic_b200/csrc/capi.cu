@@ -866,9 +866,18 @@ int bmb200_scan(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_scan_args* 
     p.total = r->total; p.work_counter = ctx->d_work; p.or_blocks = nullptr;
     sp.plane0 = a->plane0; sp.n_planes = a->n_planes; sp.universe = a->universe; sp.pred = (uint32_t)a->pred;
     sp.values = reinterpret_cast<const uint64_t*>(ctx->d_group);
+    // values per pass: find_eq keeps one state per value (4 values share a pass), the inequalities two (2 values), RANGE four (2 values);
+    // single searches use the narrow kernels
+    const int mode = a->pred == BMB200_SCAN_EQ ? 0 : a->pred == BMB200_SCAN_RANGE ? 2 : 1;
+    const uint32_t vg = nv == 1 ? 1u : (mode == 0 && nv >= 4 ? 4u : 2u);
+    const uint64_t items = (uint64_t)cols * ((nv + vg - 1) / vg);
     uint32_t grid = (uint32_t)(ctx->sm_count * ctx->agg_ctas_per_sm);
-    if (grid > n_cols) grid = n_cols;
-    scan_kernel<<<grid, kAggThreads, 0, ctx->stream>>>(sp);
+    if (grid > items) grid = (uint32_t)items;
+    #define BMB200_SCAN_LAUNCH(VG, MODE) scan_kernel<VG, MODE><<<grid, kAggThreads, 0, ctx->stream>>>(sp)
+    if (mode == 0)      { if (vg == 4) BMB200_SCAN_LAUNCH(4, 0); else if (vg == 2) BMB200_SCAN_LAUNCH(2, 0); else BMB200_SCAN_LAUNCH(1, 0); }
+    else if (mode == 1) { if (vg == 2) BMB200_SCAN_LAUNCH(2, 1); else BMB200_SCAN_LAUNCH(1, 1); }
+    else                { if (vg == 2) BMB200_SCAN_LAUNCH(2, 2); else BMB200_SCAN_LAUNCH(1, 2); }
+    #undef BMB200_SCAN_LAUNCH
     int rc = after_launch(ctx);
     if (rc) { if (!*inout) bmb200_result_free(r); return rc; }
     *inout = r;

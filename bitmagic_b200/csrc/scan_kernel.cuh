@@ -15,6 +15,8 @@
 // (column, value) work item; the values of one column are adjacent work items so the planes come from L2 after the
 // first one (the same batching as aggregator::pipeline, agg_kernel.cuh).
 //
+// Up to 4 search values of a column share one pass (their states sit side by side in registers), so the plane loads and the
+// GAP expansions are paid once per group of values.
 // Plane blocks may be NULL / FULL / bit / GAP like any other block of the set; GAP planes are expanded through the
 // 8 KB shared mask (block-wide run scatter), bit planes stream through 128-bit loads, four planes in flight.
 // The result goes through the same epilogue as the aggregation kernel (popcount, digest, run count, kind, bit->GAP).
@@ -57,11 +59,19 @@ __device__ __forceinline__ void scan_step(uint4& eq, uint4& gt, const uint4& P, 
     }
 }
 
+// VG search values share one pass over the planes of a column (their states live side by side in registers), so plane loads
+// and GAP expansions are paid once per VG searches; RANGE keeps two state pairs per value and therefore groups fewer values.
+// MODE 0: find_eq only (no GT state), 1: one (EQ, GT) pair per value, 2: RANGE (two pairs per value)
+template <int VG, int MODE>
 __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) scan_kernel(const ScanParams sp)
 {
+    constexpr bool RANGE = (MODE == 2), EQ_ONLY = (MODE == 0);
+    constexpr int kStateRegs = VG * (EQ_ONLY ? 4 : RANGE ? 16 : 8);
+    constexpr int kBatch = kStateRegs > 16 ? 2 : kScanBatch;                // planes in flight: bounded by the register budget
     __shared__ __align__(16) uint32_t K[kScanBatch][kBlockWords];   // expansion buffers: the GAP planes of one batch are expanded together
     __shared__ uint32_t s_desc[65];                          // descriptors of the planes (+ universe) of this column
     __shared__ uint32_t s_col;
+    __shared__ uint64_t s_va[VG], s_vb[VG];                  // the group's search values (kept out of the register file)
     __shared__ uint32_t s_pc[kAggWarps], s_tr[kAggWarps], s_dg[kAggWarps];
 
     const AggParams& p = sp.out;
@@ -69,7 +79,7 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) scan_kernel(const Sca
     const uint32_t M = p.set.n_vec;
     uint4* K4 = reinterpret_cast<uint4*>(K[0]);
     const uint32_t Ks = smem_u32(K[0]);
-    const bool is_range = (sp.pred == BMB200_SCAN_RANGE);
+    const uint32_t n_vg = (p.n_groups + VG - 1) / VG;        // value groups per column
 
     uint32_t next_item = 0;
     if (tid == 0) next_item = atomicAdd(p.work_counter, 1u);
@@ -78,19 +88,21 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) scan_kernel(const Sca
         if (tid == 0) s_col = next_item;
         __syncthreads();
         const uint32_t item = s_col;
-        if (item >= p.n_cols * p.n_groups) break;
+        if (item >= p.n_cols * n_vg) break;
         if (tid == 0) next_item = atomicAdd(p.work_counter, 1u);
-        const uint32_t colx = item / p.n_groups, vi = item - colx * p.n_groups;
-        const uint32_t col = vi * p.n_cols + colx;           // output slot (value-major)
+        const uint32_t colx = item / n_vg, v0 = (item - colx * n_vg) * VG;
         const uint32_t nb = p.nb_from + colx;
         const uint32_t* drow = p.set.desc + (size_t)nb * M;
         if (tid < (int)sp.n_planes) s_desc[tid] = drow[sp.plane0 + tid];
         if (tid == 64) s_desc[64] = (sp.universe == 0xffffffffu) ? BMB200_BLK_FULL : drow[sp.universe];
         const uint4* bseg = reinterpret_cast<const uint4*>(p.set.bit_pool) + p.set.bit_base[nb] * (size_t)(kBlockWords / 4) + tid;
         const uint16_t* gseg = p.set.gap_pool + p.set.gap_base[nb] * (size_t)kGapUnit;
-        uint64_t va = sp.values[is_range ? 2u * vi : vi];
-        uint64_t vb = is_range ? sp.values[2u * vi + 1u] : 0ull;
-        if (is_range && vb < va) { const uint64_t t = va; va = vb; vb = t; }      // find_range swaps reversed bounds, :2871-2872
+        if (tid < VG) {
+            const uint32_t vi = min(v0 + (uint32_t)tid, p.n_groups - 1u);         // a short last group repeats its last value
+            uint64_t a = sp.values[RANGE ? 2u * vi : vi], b = RANGE ? sp.values[2u * vi + 1u] : 0ull;
+            if (RANGE && b < a) { const uint64_t t = a; a = b; b = t; }           // find_range swaps reversed bounds, :2871-2872
+            s_va[tid] = a; s_vb[tid] = b;
+        }
         __syncthreads();
 
         // one block of the column as this thread's 4 words: GAP blocks go through the shared mask (2 block barriers)
@@ -100,7 +112,9 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) scan_kernel(const Sca
             const uint32_t rel = d >> 2;
             gap_expand_block(Ks, gseg + (size_t)(rel & kRelMask) * kGapUnit + (rel >> 29), tid);
             __syncthreads();
-            return K4[tid];
+            const uint4 r = K4[tid];
+            __syncthreads();
+            return r;
         };
         auto load_now = [&](uint32_t d) -> uint4 {           // NULL / FULL / bit (GAP handled by the caller)
             const uint32_t kind = d & 3u;
@@ -110,60 +124,81 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) scan_kernel(const Sca
 
         const uint32_t du = s_desc[64];
         const uint4 U = ((du & 3u) == BMB200_BLK_GAP) ? load_gap(du) : load_now(du);
-        uint4 eqA = U, gtA = make_uint4(0u, 0u, 0u, 0u), eqB = U, gtB = make_uint4(0u, 0u, 0u, 0u);
-        // a value with bits above the top plane is greater than every element
-        if (sp.n_planes < 64u && (va >> sp.n_planes)) { eqA = make_uint4(0u, 0u, 0u, 0u); va = 0ull; }
-        if (sp.n_planes < 64u && (vb >> sp.n_planes)) { eqB = make_uint4(0u, 0u, 0u, 0u); vb = 0ull; }
+        uint4 eqA[VG], gtA[EQ_ONLY ? 1 : VG], eqB[RANGE ? VG : 1], gtB[RANGE ? VG : 1];
+#pragma unroll
+        for (int g = 0; g < VG; ++g) {
+            eqA[g] = U; if (!EQ_ONLY) gtA[g] = make_uint4(0u, 0u, 0u, 0u);
+            // a value with bits above the top plane is greater than every element: it starts with an empty EQ state (and its low
+            // bits then only feed GT |= EQ & P = 0, so they need no masking)
+            if (sp.n_planes < 64u && (s_va[g] >> sp.n_planes)) eqA[g] = make_uint4(0u, 0u, 0u, 0u);
+            if (RANGE) {
+                eqB[g] = U; gtB[g] = make_uint4(0u, 0u, 0u, 0u);
+                if (sp.n_planes < 64u && (s_vb[g] >> sp.n_planes)) eqB[g] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
 
-        for (int jt = (int)sp.n_planes - 1; jt >= 0; jt -= kScanBatch) {
-            uint4 P[kScanBatch];
-            uint32_t d[kScanBatch];
+        for (int jt = (int)sp.n_planes - 1; jt >= 0; jt -= kBatch) {
+            uint4 P[kBatch];
+            uint32_t d[kBatch];
             bool any_gap = false;
 #pragma unroll
-            for (int u = 0; u < kScanBatch; ++u) {           // issue the bit-plane loads of the batch together
+            for (int u = 0; u < kBatch; ++u) {               // issue the bit-plane loads of the batch together
                 const int j = jt - u;
                 d[u] = (j >= 0) ? s_desc[j] : BMB200_BLK_NULL;
                 if ((d[u] & 3u) != BMB200_BLK_GAP) P[u] = load_now(d[u]); else any_gap = true;
             }
             if (any_gap) {                                   // uniform: the GAP planes of the batch share one pair of barriers
 #pragma unroll
-                for (int u = 0; u < kScanBatch; ++u)
+                for (int u = 0; u < kBatch; ++u)
                     if ((d[u] & 3u) == BMB200_BLK_GAP) reinterpret_cast<uint4*>(K[u])[tid] = make_uint4(0u, 0u, 0u, 0u);
                 __syncthreads();
 #pragma unroll
-                for (int u = 0; u < kScanBatch; ++u)
+                for (int u = 0; u < kBatch; ++u)
                     if ((d[u] & 3u) == BMB200_BLK_GAP) {
                         const uint32_t rel = d[u] >> 2;
                         gap_expand_block(Ks + (uint32_t)u * kBlockWords * 4u, gseg + (size_t)(rel & kRelMask) * kGapUnit + (rel >> 29), tid);
                     }
                 __syncthreads();
 #pragma unroll
-                for (int u = 0; u < kScanBatch; ++u)
+                for (int u = 0; u < kBatch; ++u)
                     if ((d[u] & 3u) == BMB200_BLK_GAP) P[u] = reinterpret_cast<const uint4*>(K[u])[tid];
                 __syncthreads();                             // the buffers are rewritten by the next batch
             }
 #pragma unroll
-            for (int u = 0; u < kScanBatch; ++u) {
+            for (int u = 0; u < kBatch; ++u) {
                 const int j = jt - u;
                 if (j < 0) break;
-                scan_step(eqA, gtA, P[u], (va >> j) & 1ull);
-                if (is_range) scan_step(eqB, gtB, P[u], (vb >> j) & 1ull);
+#pragma unroll
+                for (int g = 0; g < VG; ++g) {
+                    if (EQ_ONLY) {
+                        const uint32_t f = ((s_va[g] >> j) & 1ull) ? 0u : 0xffffffffu;       // EQ &= value bit ? P : ~P
+                        eqA[g].x &= P[u].x ^ f; eqA[g].y &= P[u].y ^ f; eqA[g].z &= P[u].z ^ f; eqA[g].w &= P[u].w ^ f;
+                    } else scan_step(eqA[g], gtA[g], P[u], (s_va[g] >> j) & 1ull);
+                    if (RANGE) scan_step(eqB[g], gtB[g], P[u], (s_vb[g] >> j) & 1ull);
+                }
             }
         }
 
-        uint4 R;
-        switch (sp.pred) {
-        case BMB200_SCAN_EQ: R = eqA; break;
-        case BMB200_SCAN_GT: R = gtA; break;
-        case BMB200_SCAN_GE: R = make_uint4(gtA.x | eqA.x, gtA.y | eqA.y, gtA.z | eqA.z, gtA.w | eqA.w); break;
-        case BMB200_SCAN_LT: R = make_uint4(U.x & ~(gtA.x | eqA.x), U.y & ~(gtA.y | eqA.y), U.z & ~(gtA.z | eqA.z), U.w & ~(gtA.w | eqA.w)); break;
-        case BMB200_SCAN_LE: R = make_uint4(U.x & ~gtA.x, U.y & ~gtA.y, U.z & ~gtA.z, U.w & ~gtA.w); break;
-        default:             // RANGE: ge(a) & le(b)
-            R = make_uint4((gtA.x | eqA.x) & U.x & ~gtB.x, (gtA.y | eqA.y) & U.y & ~gtB.y,
-                           (gtA.z | eqA.z) & U.z & ~gtB.z, (gtA.w | eqA.w) & U.w & ~gtB.w);
-            break;
+#pragma unroll
+        for (int g = 0; g < VG; ++g) {
+            const uint32_t vi = v0 + (uint32_t)g;
+            if (vi >= p.n_groups) break;                     // uniform
+            const uint4 e = eqA[g], t = gtA[EQ_ONLY ? 0 : g];
+            uint4 R;
+            switch (sp.pred) {
+            case BMB200_SCAN_EQ: R = e; break;
+            case BMB200_SCAN_GT: R = t; break;
+            case BMB200_SCAN_GE: R = make_uint4(t.x | e.x, t.y | e.y, t.z | e.z, t.w | e.w); break;
+            case BMB200_SCAN_LT: R = make_uint4(U.x & ~(t.x | e.x), U.y & ~(t.y | e.y), U.z & ~(t.z | e.z), U.w & ~(t.w | e.w)); break;
+            case BMB200_SCAN_LE: R = make_uint4(U.x & ~t.x, U.y & ~t.y, U.z & ~t.z, U.w & ~t.w); break;
+            default: {           // RANGE: ge(a) & le(b)
+                const uint4 tb = gtB[RANGE ? g : 0];
+                R = make_uint4((t.x | e.x) & U.x & ~tb.x, (t.y | e.y) & U.y & ~tb.y, (t.z | e.z) & U.z & ~tb.z, (t.w | e.w) & U.w & ~tb.w);
+                break; }
+            }
+            if (g) __syncthreads();                          // the epilogue scratch (K[0]) of the previous value is still being read
+            finish_block<true>(p, vi * p.n_cols + colx, colx, vi, R, 2, K[0], s_pc, s_tr, s_dg);
         }
-        finish_block<true>(p, col, colx, vi, R, 2, K[0], s_pc, s_tr, s_dg);
     }
 }
 
