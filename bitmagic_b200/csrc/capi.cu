@@ -304,6 +304,7 @@ int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks
     for (uint32_t v = 0; v < n_vec; ++v)
         if (vecs[v].n_blocks > n_blocks || (vecs[v].n_blocks && (!vecs[v].kind || !vecs[v].ptr))) return BMB200_ERR_BADARG;
     // host-side gather of the block tree into the packed column-major layout (the block manager stays on the host)
+    const bool legacy = getenv("BMB200_GAP_LEGACY") != nullptr;     // experiments only: raw GAP blocks, no FLAT form
     std::vector<uint32_t> desc; std::vector<uint64_t> bb, gb;
     try { desc.assign((size_t)n_vec * n_blocks, 0u); bb.assign((size_t)n_blocks + 1, 0); gb.assign((size_t)n_blocks + 1, 0); }
     catch (...) { return BMB200_ERR_BADALLOC; }
@@ -319,7 +320,6 @@ int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks
                 uint32_t words = (uint32_t)(g[0] >> 3) + 1u;
                 if (words > kGapMax) return BMB200_ERR_BADARG;
                 // flat-streamable form (BMB200_DESC_GAP_FLAT): lead pad iff the first run is 0; BMB200_GAP_LEGACY=1 keeps the raw form
-                const bool legacy = getenv("BMB200_GAP_LEGACY") != nullptr;
                 const uint32_t pad = (!legacy && !(g[0] & 1u)) ? 1u : 0u;
                 if (ngap + (words + pad + kGapUnit - 1) / kGapUnit > (uint64_t)BMB200_DESC_REL_MASK) return BMB200_ERR_RANGE;
                 rel = (uint32_t)ngap | (pad << 29) | (legacy ? 0u : (BMB200_DESC_GAP_FLAT >> 2)); ngap += (words + pad + kGapUnit - 1) / kGapUnit;

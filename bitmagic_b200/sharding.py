@@ -23,6 +23,14 @@ def shard_range(n_blocks: int, world: int, rank: int, align: int = SUPERBLOCK) -
     return min(lo_sb * align, n_blocks), min(hi_sb * align, n_blocks)
 
 
+def shard_range_with_halo(n_blocks: int, world: int, rank: int, halo: int = 1, align: int = SUPERBLOCK) -> tuple[int, int, int]:
+    """(lo_stored, lo, hi): the range a rank must HOLD for SHIFT-R-AND.  result[p] = AND_k v_k[p - s_k] reads up to n-1 bits of
+    block lo - 1 (csrc/shift_kernel.cuh), so a shard stores `halo` extra block columns in front of the ones it owns and
+    aggregates with nb_from = lo - lo_stored; everything else is the plain block-range partition."""
+    lo, hi = shard_range(n_blocks, world, rank, align)
+    return max(0, lo - halo), lo, hi
+
+
 def shard_sizes(n_blocks: int, world: int, align: int = SUPERBLOCK) -> list[int]:
     return [hi - lo for lo, hi in (shard_range(n_blocks, world, r, align) for r in range(world))]
 

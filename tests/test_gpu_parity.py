@@ -615,6 +615,12 @@ def test_shift_right_and_vs_oracle(ctx, seed):
         for n in (1, 2, 3, 5, 12, 33, 34, 70, 130, 200):
             g = rng.integers(0, len(vecs), n) if n > len(vecs) else rng.permutation(len(vecs))[:n]
             check_vs_oracle(ctx, ps, bm.OP_SHIFT_R_AND, g, None, C if n % 2 else 0, dset)
+        # a shard: columns [2, 5) of a set that also holds the halo column 1 (and 0) -- equals the same columns of the full result
+        g = rng.permutation(len(vecs))[:6]
+        res = bm.aggregate(ctx, dset, bm.OP_SHIFT_R_AND, g, None, 0, nb_from=2, nb_to=5)
+        kind, pop, dig, nr = res.meta(); res.free()
+        okind, opop, odig, onr, oblk, ogap = orclib.oracle_aggregate(ps, bm.OP_SHIFT_R_AND, g, None, 0)
+        assert np.array_equal(pop, opop[2:5]) and np.array_equal(dig, odig[2:5]) and np.array_equal(kind, okind[2:5])
         # long chains over FULL / dense blocks keep bits alive: same vector repeated
         full_like = max(range(len(vecs)), key=lambda v: vecs[v].count())
         got = check_vs_oracle(ctx, ps, bm.OP_SHIFT_R_AND, [full_like] * 40, None, C, dset)

@@ -60,3 +60,15 @@ def test_shard_range_properties():
                 assert a[1] == b[0] and (a[1] % 256 == 0 or a[1] == n_blocks)
             assert sum(shard_sizes(n_blocks, world)) == n_blocks
     assert shard_sizes(16384, 8) == [2048] * 8
+
+
+def test_shift_and_shards_carry_a_one_column_halo():
+    from bitmagic_b200.sharding import shard_range, shard_range_with_halo
+    for nb, world in ((16384, 8), (1000, 3), (256, 2)):
+        prev_hi = 0
+        for r in range(world):
+            st, lo, hi = shard_range_with_halo(nb, world, r)
+            assert (lo, hi) == shard_range(nb, world, r) and lo == prev_hi
+            assert st == max(0, lo - 1)
+            prev_hi = hi
+        assert prev_hi == nb
