@@ -176,7 +176,7 @@ def run_reference(args):
     cores, all threads, on a bounded column sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     import torch
     import bitmagic_b200 as bm
     import orclib
@@ -215,10 +215,34 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "blocks/s", "cores": threads, "kind": kind, "sample": sample,
                              "simd": orclib.ref().ref_simd().decode() if kind == "reference" else "scalar"},
             "e2e": {"value": value, "unit": "blocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    return line
+
+
+class _StdoutToStderr:
+    """Everything libraries print while the bench runs (NCCL's version banner, warnings ...) goes to stderr, so that stdout
+    carries exactly ONE line: the JSON result."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
 
 
 def main():
+    with _StdoutToStderr():
+        line = _main()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -403,9 +427,11 @@ def main():
             "cpu_baseline": cpu,
             "result_bits": int(total_bits),
         }
-        print(json.dumps(line), flush=True)
+    else:
+        line = None
     if world > 1:
         dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":
