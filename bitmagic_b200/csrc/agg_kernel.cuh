@@ -8,14 +8,14 @@
 //   the classification half of opt_copy_bit_block                 src/bmblocks.h:1355-1409
 //
 // Layout / mapping:
-//   * persistent CTAs (grid = SMs x 2) pull block columns from an atomic counter, so skewed columns
-//     (NULL / GAP / bit mixes) balance themselves;
+//   * persistent CTAs (grid = SMs x 2) pull block columns from an atomic counter (claimed one column ahead), so
+//     skewed columns (NULL / GAP / bit mixes) balance themselves;
 //   * 512 threads own the 8 KB accumulator in registers: thread t holds words [4t, 4t+4) as one uint4,
 //     every source bit-block is consumed with one coalesced 128-bit streaming load per thread,
-//     8 blocks in flight per thread (64 KB per CTA);
+//     4 blocks in flight per thread (32 KB per CTA);
 //   * GAP sources are never expanded on their own.  The column's GAP segment is contiguous in the arena
-//     (column-major layout), so it is streamed with cp.async.bulk (TMA) in 16 KB chunks into a 4-stage
-//     shared-memory ring tracked by mbarriers -- 64 KB in flight per CTA without a single LSU global load.
+//     (column-major layout), so it is streamed with cp.async.bulk (TMA) into a 64 KB shared-memory ring tracked
+//     by mbarriers -- without a single LSU global load.
 //     The bit phase runs first and is folded into an 8 KB "live" mask L in shared memory; GAP runs then only
 //     ever CLEAR bits of L (red.shared.and), so a run whose word of L is already dead costs one shared load
 //     and no atomic (the reference gets the same effect from its digest, src/bmfunc.h:7615):
@@ -26,10 +26,12 @@
 //     Two consumers of the ring:
 //       - FLAT (OR sources / SUB group): when every GAP block of the streamed window belongs to the list and is
 //         stored in the BMB200_DESC_GAP_FLAT form, the window is just an array of aligned (prev_end, end) u16
-//         pairs -- headers, pads and tail fill decode to empty runs -- so 512 threads eat it with 128-bit
-//         shared loads, 4 runs per load, no per-block bookkeeping at all;
-//       - per block (AND-group GAPs, XOR, subsets of the pool, legacy layout): 16 lanes share one GAP block.
-//     The warp that finishes a chunk last re-arms its stage (no producer warp).
+//         pairs -- headers, pads and tail fill decode to empty runs.  The ring is cut into two private 2 KB slots
+//         per warp (one mbarrier each); warps claim 4 KB pieces of the window from a shared counter, refill their
+//         own slots and eat them with 128-bit shared loads, 4 runs per load: no per-block bookkeeping, no
+//         cross-warp hand-off;
+//       - per block (AND-group GAPs, XOR, subsets of the pool, raw GAP layout): 16 KB chunks in a 4-stage ring,
+//         16 lanes share one GAP block, the warp that finishes a chunk last re-arms its stage (no producer warp).
 //     Unsorted / sparse member lists fall back to per-block gathers from global memory.
 //   * epilogue fuses popcount, 64-wave digest, run count and the result-kind decision.
 #pragma once
