@@ -5,7 +5,7 @@
  * function cites the reference lines (relative to the reference tree) it follows.
  * Arithmetic is u16/u32/u64 integer only; results must be bit-exact.
  */
-#include "bm_oracle.h"
+#include "bm_oracle_int.h"
 #include <string.h>
 #include <stdlib.h>
 
@@ -466,12 +466,6 @@ int orc_aggregate(const bmb200_packed_set* s, const bmb200_agg_args* a,
  * Block kinds follow the reference: bit tokens -> bit-blocks, GAP / array-of-GAP tokens and single bits -> GAP blocks
  * (new_blocks_strat BM_GAP, :5687), capacity level from gap_calc_level(gap_length).  Returns BMB200_ERR_UNSUPPORTED for
  * every other token (gamma / interpolative / XOR / super-block / bookmark encodings). */
-typedef struct { const uint8_t* p; const uint8_t* end; } rd_t;
-static uint32_t rd8(rd_t* r)  { if (r->p + 1 > r->end) { r->p = r->end + 1; return 0; } return *r->p++; }
-static uint32_t rd16(rd_t* r) { uint32_t a = rd8(r); return a | (rd8(r) << 8); }
-static uint32_t rd32(rd_t* r) { uint32_t a = rd16(r); return a | (rd16(r) << 16); }
-static uint64_t rd64(rd_t* r) { uint64_t a = rd32(r); return a | ((uint64_t)rd32(r) << 32); }
-
 static void gap_from_sorted(uint16_t* g, const uint16_t* a, uint32_t n, int invert)
 {   /* gap_set_array (src/bmfunc.h) + optional gap_invert: positions a[0..n) ascending */
     uint32_t len = 0, first = (n && a[0] == 0) ? 1u : 0u;
@@ -486,6 +480,9 @@ static void gap_from_sorted(uint16_t* g, const uint16_t* a, uint32_t n, int inve
     int level = gap_calc_level(len + 1); if (level < 0) level = 3;
     g[0] = (uint16_t)((first ^ (invert ? 1u : 0u)) | ((uint32_t)level << 1) | (len << 3));
 }
+
+static uint32_t* g_token_hist = 0;      /* optional token-type histogram (256 counters) filled by orc_deserialize: test coverage evidence */
+void orc_set_token_hist(uint32_t* hist) { g_token_hist = hist; }
 
 int orc_deserialize(const uint8_t* blob, uint64_t size, uint32_t n_cols, uint8_t* kind, uint32_t* blocks, uint16_t* gaps)
 {
@@ -509,6 +506,7 @@ int orc_deserialize(const uint8_t* blob, uint64_t size, uint32_t n_cols, uint8_t
     while (rc == BMB200_OK && r.p <= r.end) {
         uint32_t bt = rd8(&r);
         if (r.p > r.end) { rc = BMB200_ERR_BADARG; break; }
+        if (g_token_hist) g_token_hist[bt & 0x80u ? 0x80u : bt]++;
         if (bt & 0x80u) { nb += bt & 0x7fu; continue; }
         uint64_t ones = 0; int is_bit = 0, is_gap = 0;
         switch (bt) {
@@ -563,24 +561,57 @@ int orc_deserialize(const uint8_t* blob, uint64_t size, uint32_t n_cols, uint8_t
             gap_from_sorted(tg, arr, n, bt == 24);
             if ((tg[0] >> 3) + 1u > GMAX - 4) { rc = BMB200_ERR_UNSUPPORTED; break; }
             is_gap = 1; break; }
-        case 67: {                                                        /* set_block_gap_egamma_v3 */
-            uint64_t acc = 0; uint32_t have = 0;                          /* bit stream of 32-bit words, LSB first */
-            #define NEED(nbits) while (have < (nbits)) { acc |= (uint64_t)rd32(&r) << have; have += 32; }
-            uint32_t zeros = 0;
-            for (;;) { NEED(1) if (acc & 1u) break; acc >>= 1; --have; ++zeros; if (zeros > 31) break; }
-            if (zeros > 31) { rc = BMB200_ERR_BADARG; break; }
-            acc >>= 1; --have;
-            uint32_t v = 0; if (zeros) { NEED(zeros) v = (uint32_t)(acc & ((1ull << zeros) - 1)); acc >>= zeros; have -= zeros; }
-            uint32_t len = (v | (1u << zeros)) + 1u;                       /* gamma() + 1 */
-            NEED(2) uint32_t start = (uint32_t)(acc & 1u), use_gamma = (uint32_t)((acc >> 1) & 1u); acc >>= 2; have -= 2;
-            if (use_gamma) { rc = BMB200_ERR_UNSUPPORTED; break; }
-            if (len + 1 > GMAX) { rc = BMB200_ERR_UNSUPPORTED; break; }
-            for (uint32_t k = 1; k < len; ++k) { NEED(16) tg[k] = (uint16_t)(acc & 0xffffu); acc >>= 16; have -= 16; }
-            #undef NEED
-            tg[len] = 65535;
-            int level = gap_calc_level(len + 1); if (level < 0) { rc = BMB200_ERR_UNSUPPORTED; break; }
-            tg[0] = (uint16_t)(start | ((uint32_t)level << 1) | (len << 3));
-            is_gap = 1; break; }
+        case 47: rd16(&r); continue;                                      /* set_nb_bookmark16/24/32: skip offsets (:5897-5920) */
+        case 48: rd16(&r); rd8(&r); continue;
+        case 49: rd32(&r); continue;
+        case 50: rd8(&r); continue;                                       /* set_nb_sync_mark8..64 */
+        case 51: rd16(&r); continue;
+        case 52: rd16(&r); rd8(&r); continue;
+        case 53: rd32(&r); continue;
+        case 54: rd32(&r); rd16(&r); continue;
+        case 55: rd64(&r); continue;
+        case 56: case 68: {                                               /* super-block position lists (decode_arr_sblock :5458) */
+            uint32_t* sarr = (uint32_t*)malloc(sizeof(uint32_t) * 65536u);
+            uint32_t slen = 0, sb = 0;
+            if (!sarr) { rc = BMB200_ERR_BADALLOC; break; }
+            rc = orc_sblock_token(&r, bt, sarr, &slen, &sb);
+            if (rc == BMB200_OK && (uint64_t)sb * 256u != (nb & ~255ull)) rc = BMB200_ERR_BADARG;
+            if (rc == BMB200_OK) {
+                /* bv.set_bit_no_check into empty blocks under BM_GAP strategy: every touched block becomes a GAP block */
+                for (uint32_t k = 0; k < slen; ) {
+                    uint32_t c = sarr[k] >> 16, k2 = k;
+                    if (c >= 256u) { rc = BMB200_ERR_BADARG; break; }
+                    memset(tb, 0, BMB200_BLOCK_BYTES);
+                    while (k2 < slen && (sarr[k2] >> 16) == c) { tb[(sarr[k2] & 65535u) >> 5] |= 1u << (sarr[k2] & 31u); ++k2; }
+                    uint64_t col = (uint64_t)sb * 256u + c;
+                    if (col < n_cols) {
+                        uint32_t len = orc_bit_to_gap(tg, tb);
+                        int level = gap_calc_level(len + 1);
+                        if (level < 0) { kind[col] = BMB200_BLK_BIT; }
+                        else { kind[col] = BMB200_BLK_GAP; tg[0] = (uint16_t)((tg[0] & 1u) | ((uint32_t)level << 1) | (len << 3));
+                               if (gaps) memcpy(gaps + col * GMAX, tg, ((size_t)len + 1) * 2); }
+                        if (blocks) memcpy(blocks + col * BW, tb, BMB200_BLOCK_BYTES);
+                    }
+                    k = k2;
+                }
+            }
+            free(sarr);
+            if (rc != BMB200_OK) break;
+            nb = (nb & ~255ull) + 256u;
+            continue; }
+        case 20: case 21: case 23: case 27: case 28: case 29: case 31: case 32: case 33: case 43: case 44: case 45: case 57:
+        case 61: case 62: case 63: case 64: case 65: case 66: case 67: { /* entropy-coded blocks: bm_oracle_entropy.c */
+            int gapf = 0;
+            memset(tb, 0, BMB200_BLOCK_BYTES);
+            rc = orc_entropy_token(&r, bt, tb, &gapf);
+            if (rc != BMB200_OK) break;
+            if (gapf) {                                                   /* clone_gap_block: GAP unless it does not fit (src/bmblocks.h:838) */
+                uint32_t len = orc_bit_to_gap(tg, tb);
+                int level = gap_calc_level(len + 1);
+                if (level < 0) is_bit = 1;
+                else { tg[0] = (uint16_t)((tg[0] & 1u) | ((uint32_t)level << 1) | (len << 3)); is_gap = 1; }
+            } else is_bit = 1;
+            break; }
         default: rc = BMB200_ERR_UNSUPPORTED; break;
         }
         if (rc != BMB200_OK) break;

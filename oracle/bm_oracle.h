@@ -46,6 +46,8 @@ int orc_aggregate(const bmb200_packed_set* set, const bmb200_agg_args* args,
 /* ---- bm::deserialize of a serialized bvector BLOB into an empty vector (explicit-length token subset) ----
  * kind[n_cols]; blocks[n_cols*2048] logical bits (may be NULL); gaps[n_cols*1280] GAP form of the GAP-kind columns (may be NULL) */
 int orc_deserialize(const uint8_t* blob, uint64_t size, uint32_t n_cols, uint8_t* kind, uint32_t* blocks, uint16_t* gaps);
+/* optional: 256 counters, one per token type met by orc_deserialize (index 0x80 = packed short zero run); NULL switches it off */
+void orc_set_token_hist(uint32_t* hist);
 
 /* ---- sparse-vector scanner searches (bmb200_scan): n_values * n_cols columns, value-major ---- */
 int orc_scan(const bmb200_packed_set* set, const bmb200_scan_args* args,

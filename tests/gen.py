@@ -81,3 +81,66 @@ def edge_vectors(n_blocks=4):
     v.set_gap(3, gap_from_runs([21823, 21824, 43647, 43648, 65535], 1)); vs.append(v)
     v = bm.BVector(n_blocks); vs.append(v)   # all NULL
     return vs
+
+
+def entropy_vectors(rng, n_vec=14, n_blocks=10):
+    """Vectors that drive bm::serializer<> (levels 3..6) through its entropy-coded encodings: iid bits over five decades of
+    density and their complements (interpolative arrays, plain and inverted), run lists with regular strides (delta-range
+    reduction, min0/min1), runs with isolated single-bit holes and spikes (GAP exception lists), clustered bits (windowed
+    restore), dense blocks with word-aligned structure, very sparse super-blocks (super-block position lists)."""
+    vecs = []
+    for k in range(n_vec):
+        v = bm.BVector(n_blocks)
+        for nb in range(n_blocks):
+            style = (k + nb) % 9
+            bits = np.zeros(BLOCK_BITS, np.uint8)
+            if style == 0:                       # iid, density 10^-4.5 .. 0.3
+                bits = (rng.random(BLOCK_BITS) < 10 ** rng.uniform(-4.5, -0.5)).astype(np.uint8)
+            elif style == 1:                     # complement of sparse
+                bits = (rng.random(BLOCK_BITS) >= 10 ** rng.uniform(-4.0, -1.0)).astype(np.uint8)
+            elif style == 2:                     # regular stride runs with jitter
+                stride = int(rng.integers(20, 400)); rl = int(rng.integers(1, max(2, stride // 2)))
+                for s in range(int(rng.integers(0, stride)), BLOCK_BITS - stride, stride):
+                    s2 = s + int(rng.integers(0, 3)); bits[s2:s2 + rl + int(rng.integers(0, 2))] = 1
+            elif style == 3:                     # long runs with isolated holes and spikes
+                cuts = np.sort(rng.choice(np.arange(1, BLOCK_BITS), size=int(rng.integers(4, 300)), replace=False))
+                val = int(rng.integers(0, 2)); prev = 0
+                for c in list(cuts) + [BLOCK_BITS]:
+                    bits[prev:c] = val; val ^= 1; prev = c
+                flips = rng.choice(BLOCK_BITS, size=int(rng.integers(1, 200)), replace=False)
+                bits[flips] ^= 1
+            elif style == 4:                     # clusters
+                for _ in range(int(rng.integers(1, 30))):
+                    c = int(rng.integers(0, BLOCK_BITS - 600)); n = int(rng.integers(2, 300))
+                    bits[c + rng.integers(0, 512, n)] = 1
+            elif style == 5:                     # a handful of bits (super-block lists when the whole vector is like this)
+                bits[rng.choice(BLOCK_BITS, size=int(rng.integers(1, 12)), replace=False)] = 1
+            elif style == 6:                     # dense random words in a few waves
+                w = np.zeros(2048, np.uint32)
+                for s in rng.choice(64, size=int(rng.integers(1, 20)), replace=False):
+                    w[s * 32:(s + 1) * 32] = rng.integers(0, 2**32, 32, dtype=np.uint64).astype(np.uint32)
+                bits = np.unpackbits(w.view(np.uint8), bitorder="little")
+            elif style == 7:                     # short runs of equal length, equal gaps (min0 / min1 > 1)
+                g0 = int(rng.integers(3, 60)); g1 = int(rng.integers(2, 40)); p = int(rng.integers(0, 50))
+                while p + g1 < BLOCK_BITS:
+                    bits[p:p + g1 + int(rng.integers(0, 3))] = 1; p += g1 + g0 + int(rng.integers(0, 4))
+            else:                                # mid density iid (bit-block or inverted array territory)
+                bits = (rng.random(BLOCK_BITS) < rng.uniform(0.02, 0.98)).astype(np.uint8)
+            if not bits.any():
+                continue
+            w = bits_to_words(bits)
+            if int(np.count_nonzero(bits[1:] != bits[:-1])) + 1 < 1276 and rng.random() < 0.8:
+                v.set_gap(nb, bits_to_gap(w))
+            else:
+                v.set_bits(nb, w)
+        vecs.append(v)
+    # whole vectors of very sparse blocks: the serializer folds each super-block into one position list (levels 5, 6)
+    for dens in (1, 3, 40):
+        v = bm.BVector(n_blocks)
+        for nb in range(n_blocks):
+            bits = np.zeros(BLOCK_BITS, np.uint8)
+            bits[rng.choice(BLOCK_BITS, size=int(rng.integers(1, dens + 1)), replace=False)] = 1
+            if nb % 4 != 3:
+                v.set_gap(nb, bits_to_gap(bits_to_words(bits)))
+        vecs.append(v)
+    return vecs
