@@ -28,7 +28,7 @@ struct BlobRec {
     uint32_t type;       // DB_*
     uint32_t aux;        // DB_GAP_V3: bit offset of the first run end | len << 8 ... see capi.cu; DB_ARRGAP*: element count (1bit: 1)
     uint32_t aux2;       // GAP kinds: bit 0 = lead pad, bit 1 = first-run value
-    uint32_t pad_;
+    uint32_t kind;       // entropy-coded tokens (blob_entropy.cuh): BMB200_BLK_BIT / BMB200_BLK_GAP of the decoded block
 };
 
 constexpr int kBlobThreads = 256;

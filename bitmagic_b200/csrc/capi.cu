@@ -13,6 +13,7 @@
 #include "scan_kernel.cuh"
 #include "shift_kernel.cuh"
 #include "blob_kernel.cuh"
+#include "blob_entropy.cuh"
 
 using namespace bmb200;
 
@@ -357,7 +358,6 @@ int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks
 
 /* ---- deserialize-to-device: host side = token walk only (type + payload extent of every block), no decoding ---- */
 namespace {
-struct BlobTok { uint32_t nb; uint32_t type; uint64_t off; uint32_t aux, first; uint32_t gap_words; uint8_t kind; };
 
 struct ByteRd {
     const uint8_t* b; uint64_t n, p = 0; bool bad = false;
@@ -442,57 +442,42 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
     for (uint32_t v = 0; v < n_vec; ++v) if (!blobs[v].data || blobs[v].size < 2) return BMB200_ERR_BADARG;
     std::vector<std::vector<BlobTok>> toks(n_vec);
     std::vector<uint8_t> full;
-    std::vector<uint32_t> desc; std::vector<uint64_t> bb, gb, stg_off(n_vec);
-    std::vector<BlobRec> recs;
+    std::vector<uint32_t> desc; std::vector<uint64_t> bb, gb, stg_off(n_vec), blob_size(n_vec);
+    std::vector<BlobRec> recs, erecs;           // explicit-length tokens (blob_decode_kernel) / entropy-coded tokens (blob_entropy_kernel)
+    bool device_walk = false;                   // some BLOB holds entropy-coded tokens: its stream can only be walked by decoding it
+    uint64_t stg_bytes = 0;
     try {
         full.assign((size_t)n_vec * n_blocks, 0);
         std::vector<uint8_t> fv(n_blocks);
-        uint64_t so = 0;
         for (uint32_t v = 0; v < n_vec; ++v) {
+            stg_off[v] = stg_bytes; blob_size[v] = blobs[v].size; stg_bytes += (blobs[v].size + 15ull) & ~15ull;
+            if (device_walk) continue;
             std::fill(fv.begin(), fv.end(), 0);
             int rc = walk_blob((const uint8_t*)blobs[v].data, blobs[v].size, n_blocks, toks[v], fv);
+            if (rc == BMB200_ERR_UNSUPPORTED) { device_walk = true; continue; }
             if (rc) return rc;
             for (uint32_t nb = 0; nb < n_blocks; ++nb) full[(size_t)nb * n_vec + v] = fv[nb];
-            stg_off[v] = so; so += (blobs[v].size + 15ull) & ~15ull;
-        }
-        desc.assign((size_t)n_vec * n_blocks, 0u); bb.assign((size_t)n_blocks + 1, 0); gb.assign((size_t)n_blocks + 1, 0);
-        // per-column layout in vector order; tokens of one vector are already in block order
-        std::vector<size_t> cur(n_vec, 0);
-        for (uint32_t nb = 0; nb < n_blocks; ++nb) {
-            uint64_t nbit = 0, ngap = 0;
-            for (uint32_t v = 0; v < n_vec; ++v) {
-                uint32_t d = full[(size_t)nb * n_vec + v] ? BMB200_BLK_FULL : BMB200_BLK_NULL;
-                if (cur[v] < toks[v].size() && toks[v][cur[v]].nb == nb) {
-                    const BlobTok& t = toks[v][cur[v]++];
-                    BlobRec r{}; r.src = stg_off[v] + t.off; r.type = t.type; r.aux = t.aux;
-                    if (t.kind == BMB200_BLK_BIT) { d = BMB200_BLK_BIT | ((uint32_t)nbit << 2); r.dst = bb[nb] + nbit; ++nbit; }
-                    else {
-                        const uint32_t pad = t.first ? 0u : 1u;
-                        const uint64_t units = (t.gap_words + pad + kGapUnit - 1) / kGapUnit;
-                        if (ngap + units > (uint64_t)BMB200_DESC_REL_MASK) return BMB200_ERR_RANGE;
-                        d = BMB200_BLK_GAP | ((uint32_t)ngap << 2) | (pad ? BMB200_DESC_GAP_PAD : 0u) | BMB200_DESC_GAP_FLAT;
-                        r.dst = gb[nb] + ngap; r.aux2 = pad | (t.first << 1); ngap += units;
-                    }
-                    recs.push_back(r);
-                }
-                desc[(size_t)nb * n_vec + v] = d;
-            }
-            bb[nb + 1] = bb[nb] + nbit; gb[nb + 1] = gb[nb] + ngap;
         }
     } catch (...) { return BMB200_ERR_BADALLOC; }
     CU(cudaSetDevice(ctx->device));
-    const uint64_t n_bit = bb[n_blocks], n_gap = gb[n_blocks];
-    bmb200_set* s = nullptr;
-    int rc = set_alloc(ctx, n_vec, n_blocks, n_bit, n_gap, &s);
-    if (rc) return rc;
-    uint64_t stg_bytes = 0; for (uint32_t v = 0; v < n_vec; ++v) stg_bytes = stg_off[v] + ((blobs[v].size + 15ull) & ~15ull);
-    uint8_t* d_stg = nullptr; BlobRec* d_recs = nullptr;
     cudaStream_t st = ctx->stream;
-    cudaError_t e = cudaMalloc((void**)&d_stg, stg_bytes + 64);
-    if (e == cudaSuccess && !recs.empty()) e = cudaMalloc((void**)&d_recs, recs.size() * sizeof(BlobRec));
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_stg + stg_bytes, 0, 64, st);
-    // the compressed bytes are all that crosses PCIe (plus descriptors and the token table): gathered into one pinned
+    // ---- the compressed bytes are all that crosses PCIe (plus descriptors and the token table): gathered into one pinned
     // buffer so the copy is a single DMA at link speed instead of one pageable copy per vector
+    uint8_t* d_stg = nullptr; BlobRec *d_recs = nullptr, *d_erecs = nullptr;
+    uint64_t *d_boff = nullptr, *d_bsize = nullptr; BlobTok* d_toks = nullptr; uint32_t* d_ntoks = nullptr; int* d_status = nullptr;
+    uint8_t *d_full = nullptr, *d_scratch = nullptr;
+    bmb200_set* s = nullptr;
+    auto cleanup = [&]() { cudaFree(d_stg); cudaFree(d_recs); cudaFree(d_erecs); cudaFree(d_boff); cudaFree(d_bsize); cudaFree(d_toks);
+                           cudaFree(d_ntoks); cudaFree(d_status); cudaFree(d_full); cudaFree(d_scratch); };
+    auto fail = [&](int rc, cudaError_t e) {
+        cudaStreamSynchronize(st);
+        if (rc == BMB200_ERR_CUDA || (!rc && e != cudaSuccess)) { ctx->last_err = std::string("set_upload_blobs: ") + cudaGetErrorString(e); rc = BMB200_ERR_CUDA; }
+        cleanup();
+        if (s) { free_set_arrays(s); delete s; }
+        return rc;
+    };
+    cudaError_t e = cudaMalloc((void**)&d_stg, stg_bytes + 64);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_stg + stg_bytes, 0, 64, st);
     if (e == cudaSuccess && stg_bytes > ctx->h_stage_cap) {
         cudaStreamSynchronize(st);
         if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -505,22 +490,114 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
         for (uint32_t v = 0; v < n_vec; ++v) memcpy(ctx->h_stage + stg_off[v], blobs[v].data, blobs[v].size);
         e = cudaMemcpyAsync(d_stg, ctx->h_stage, stg_bytes, cudaMemcpyHostToDevice, st);
     }
-    if (e == cudaSuccess && !recs.empty()) e = cudaMemcpyAsync(d_recs, recs.data(), recs.size() * sizeof(BlobRec), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? BMB200_ERR_BADALLOC : BMB200_ERR_CUDA, e);
+    const uint32_t ent_grid_max = (uint32_t)ctx->sm_count * 8u;       // warps that decode at the same time (one scratch slot each)
+    if (device_walk) {
+        // ---- pass 1 on the device: one warp per vector walks (and, for entropy-coded tokens, decodes) its token stream
+        const uint32_t tok_cap = n_blocks + n_blocks / 256u + 2u;
+        const uint32_t grid = std::min(n_vec, ent_grid_max);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_boff, 8ull * n_vec);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_bsize, 8ull * n_vec);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_toks, sizeof(BlobTok) * (size_t)n_vec * tok_cap);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_ntoks, 4ull * n_vec);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_status, 4ull * (n_vec + 1));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_full, (size_t)n_vec * n_blocks);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_scratch, (size_t)ent_grid_max * kEntScratchBytes);
+        if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? BMB200_ERR_BADALLOC : BMB200_ERR_CUDA, e);
+        e = cudaMemcpyAsync(d_boff, stg_off.data(), 8ull * n_vec, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_bsize, blob_size.data(), 8ull * n_vec, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_full, 0, (size_t)n_vec * n_blocks, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_status, 0, 4ull * (n_vec + 1), st);
+        if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
+        blob_walk_kernel<<<grid, kEntThreads, 0, st>>>(d_stg, d_boff, d_bsize, n_vec, n_blocks, d_toks, tok_cap, d_ntoks, d_status, d_full, d_scratch);
+        int rc = after_launch(ctx);
+        if (rc) return fail(rc, cudaGetLastError());
+        std::vector<uint32_t> ntoks; std::vector<int> status;
+        try { ntoks.resize(n_vec); status.resize(n_vec); } catch (...) { return fail(BMB200_ERR_BADALLOC, cudaSuccess); }
+        e = cudaMemcpyAsync(ntoks.data(), d_ntoks, 4ull * n_vec, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(status.data(), d_status, 4ull * n_vec, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(full.data(), d_full, (size_t)n_vec * n_blocks, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
+        for (uint32_t v = 0; v < n_vec; ++v) if (status[v]) return fail(status[v], cudaSuccess);
+        try {
+            for (uint32_t v = 0; v < n_vec; ++v) {
+                if (ntoks[v] > tok_cap) return fail(BMB200_ERR_RANGE, cudaSuccess);
+                toks[v].resize(ntoks[v]);
+                if (ntoks[v]) e = cudaMemcpyAsync(toks[v].data(), d_toks + (size_t)v * tok_cap, sizeof(BlobTok) * ntoks[v], cudaMemcpyDeviceToHost, st);
+                if (e != cudaSuccess) break;
+            }
+        } catch (...) { return fail(BMB200_ERR_BADALLOC, cudaSuccess); }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
+    }
+    // ---- arena layout: per column in vector order; the tokens of one vector are already in block order
+    try {
+        desc.assign((size_t)n_vec * n_blocks, 0u); bb.assign((size_t)n_blocks + 1, 0); gb.assign((size_t)n_blocks + 1, 0);
+        std::vector<size_t> cur(n_vec, 0);
+        for (uint32_t nb = 0; nb < n_blocks; ++nb) {
+            uint64_t nbit = 0, ngap = 0;
+            for (uint32_t v = 0; v < n_vec; ++v) {
+                uint32_t d = full[(size_t)nb * n_vec + v] ? BMB200_BLK_FULL : BMB200_BLK_NULL;
+                // a super-block token precedes its member blocks: one rec for the whole token, no slot of its own
+                while (cur[v] < toks[v].size() && toks[v][cur[v]].type == (kTokEntropy | 68u) && toks[v][cur[v]].nb <= nb) {
+                    const BlobTok& t = toks[v][cur[v]++];
+                    BlobRec r{}; r.src = stg_off[v] + t.off; r.type = t.type; r.aux = v; r.dst = t.aux;
+                    erecs.push_back(r);
+                }
+                if (cur[v] < toks[v].size() && toks[v][cur[v]].nb == nb) {
+                    const BlobTok& t = toks[v][cur[v]++];
+                    const bool entropy = (t.type & kTokEntropy) != 0, member = (t.type == kTokSbMember);
+                    BlobRec r{}; r.src = stg_off[v] + t.off; r.type = t.type; r.aux = entropy ? v : t.aux; r.kind = t.kind;
+                    if (t.kind == BMB200_BLK_BIT) { d = BMB200_BLK_BIT | ((uint32_t)nbit << 2); r.dst = bb[nb] + nbit; ++nbit; }
+                    else if (t.kind == BMB200_BLK_GAP) {
+                        if (t.gap_words < 2u || t.gap_words > BMB200_GAP_MAX_WORDS) return fail(BMB200_ERR_BADARG, cudaSuccess);
+                        const uint32_t pad = t.first ? 0u : 1u;
+                        const uint64_t units = (t.gap_words + pad + kGapUnit - 1) / kGapUnit;
+                        if (ngap + units > (uint64_t)BMB200_DESC_REL_MASK) return fail(BMB200_ERR_RANGE, cudaSuccess);
+                        d = BMB200_BLK_GAP | ((uint32_t)ngap << 2) | (pad ? BMB200_DESC_GAP_PAD : 0u) | BMB200_DESC_GAP_FLAT;
+                        r.dst = gb[nb] + ngap; r.aux2 = pad | (t.first << 1); ngap += units;
+                    } else return fail(BMB200_ERR_BADARG, cudaSuccess);
+                    if (!member) (entropy ? erecs : recs).push_back(r);
+                }
+                desc[(size_t)nb * n_vec + v] = d;
+            }
+            bb[nb + 1] = bb[nb] + nbit; gb[nb + 1] = gb[nb] + ngap;
+        }
+    } catch (...) { return fail(BMB200_ERR_BADALLOC, cudaSuccess); }
+    const uint64_t n_bit = bb[n_blocks], n_gap = gb[n_blocks];
+    int rc = set_alloc(ctx, n_vec, n_blocks, n_bit, n_gap, &s);
+    if (rc) { s = nullptr; return fail(rc, cudaSuccess); }
+    if (!recs.empty()) e = cudaMalloc((void**)&d_recs, recs.size() * sizeof(BlobRec));
+    if (e == cudaSuccess && !erecs.empty()) e = cudaMalloc((void**)&d_erecs, erecs.size() * sizeof(BlobRec));
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? BMB200_ERR_BADALLOC : BMB200_ERR_CUDA, e);
+    if (!recs.empty()) e = cudaMemcpyAsync(d_recs, recs.data(), recs.size() * sizeof(BlobRec), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && !erecs.empty()) e = cudaMemcpyAsync(d_erecs, erecs.data(), erecs.size() * sizeof(BlobRec), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync((void*)s->v.desc, desc.data(), desc.size() * 4, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync((void*)s->v.bit_base, bb.data(), bb.size() * 8, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync((void*)s->v.gap_base, gb.data(), gb.size() * 8, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && n_gap) e = cudaMemsetAsync((void*)s->v.gap_pool, 0, n_gap * 16ull, st);   // fill + holes of the FLAT form
-    if (e == cudaSuccess && !recs.empty()) {
+    if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
+    if (!recs.empty()) {
         uint32_t grid = (uint32_t)std::min<size_t>(recs.size(), (size_t)ctx->sm_count * 16u);
         blob_decode_kernel<<<grid, kBlobThreads, 0, st>>>(d_stg, d_recs, (uint32_t)recs.size(), (uint32_t*)s->v.bit_pool, (uint16_t*)s->v.gap_pool);
-        rc = after_launch(ctx);
+        if ((rc = after_launch(ctx))) return fail(rc, cudaGetLastError());
     }
-    cudaError_t e2 = cudaStreamSynchronize(st);      // recs / desc staging vectors go out of scope
-    cudaFree(d_stg); cudaFree(d_recs);
-    if (e != cudaSuccess || e2 != cudaSuccess || rc) {
-        if (!rc) { ctx->last_err = std::string("set_upload_blobs: ") + cudaGetErrorString(e != cudaSuccess ? e : e2); rc = BMB200_ERR_CUDA; }
-        free_set_arrays(s); delete s; return rc;
+    int ent_status = 0;
+    if (!erecs.empty()) {
+        // ---- pass 2: every entropy-coded token of every vector in parallel (their offsets are known now), one warp per token
+        uint32_t grid = (uint32_t)std::min<size_t>(erecs.size(), (size_t)ent_grid_max);
+        SetView sv{n_vec, n_blocks, s->v.desc, s->v.bit_base, s->v.gap_base, s->v.bit_pool, s->v.gap_pool};
+        blob_entropy_kernel<<<grid, kEntThreads, 0, st>>>(d_stg, d_boff, d_bsize, d_erecs, (uint32_t)erecs.size(), sv, (uint32_t*)s->v.bit_pool,
+                                                          (uint16_t*)s->v.gap_pool, d_status + n_vec, d_scratch);
+        if ((rc = after_launch(ctx))) return fail(rc, cudaGetLastError());
+        e = cudaMemcpyAsync(&ent_status, d_status + n_vec, 4, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
     }
+    e = cudaStreamSynchronize(st);      // recs / desc staging vectors go out of scope
+    if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
+    if (ent_status) return fail(ent_status, cudaSuccess);
+    cleanup();
     *out = s;
     return BMB200_OK;
 }

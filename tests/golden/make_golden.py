@@ -70,20 +70,22 @@ def scan_fixture(name, seed, nullable):
     print(name, "cases", len(tor.SCAN_CASES), "bytes", (OUT / f"{name}.npz").stat().st_size)
 
 
-def blob_fixture(name):
-    """BLOBs written by bm::serializer<> (levels 0, 1, 2) + what bm::deserialize makes of them (kinds, bits, GAP words)."""
+def blob_fixture(name, vecs=None, levels=(0, 1, 2)):
+    """BLOBs written by bm::serializer<> at the given compression levels + what bm::deserialize makes of them (kinds, bits, GAP
+    words).  "blobs": explicit-length encodings (levels 0..2); "blobs_entropy": gamma / interpolative / super-block encodings
+    (levels 3..6) over tests/gen.entropy_vectors."""
     import test_oracle_vs_reference as tor
-    vecs = tor.blob_inputs()
+    vecs = tor.blob_inputs() if vecs is None else vecs
     ps = bm.PackedSet.pack(vecs)
-    d = dict(n_vec=ps.n_vec, n_blocks=ps.n_blocks, levels=np.array([0, 1, 2]))
-    for level in (0, 1, 2):
+    d = dict(n_vec=ps.n_vec, n_blocks=ps.n_blocks, levels=np.array(levels))
+    for level in levels:
         for v in range(ps.n_vec):
             blob = orclib.ref_serialize(ps, v, level)
             kind, pop, blk, gaps = orclib.ref_deserialize(blob, ps.n_blocks)
             d[f"l{level}_v{v}_blob"] = blob; d[f"l{level}_v{v}_kind"] = kind
             glen = np.where(kind == bm.BLK_GAP, (gaps[:, 0] >> 3) + 1, 0)
             d[f"l{level}_v{v}_gaps"] = np.concatenate([gaps[c, :glen[c]] for c in range(len(kind))]) if glen.sum() else np.zeros(0, np.uint16)
-            if level == 2:
+            if level == levels[-1]:
                 d[f"v{v}_blk"] = blk
     np.savez_compressed(OUT / f"{name}.npz", **d)
     print(name, "bytes", (OUT / f"{name}.npz").stat().st_size)
@@ -93,6 +95,8 @@ if __name__ == "__main__":
     assert orclib.have_ref(), "build oracle/_ref first (make -C oracle)"
     if "blob" in sys.argv[1:] or len(sys.argv) == 1:
         blob_fixture("blobs")
+        import test_oracle_vs_reference as tor
+        blob_fixture("blobs_entropy", tor.entropy_inputs(), (3, 4, 5, 6))
         if "blob" in sys.argv[1:]:
             sys.exit(0)
     if "scan" in sys.argv[1:] or len(sys.argv) == 1:

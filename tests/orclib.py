@@ -22,8 +22,8 @@ def oracle() -> C.CDLL:
     global _oracle
     if _oracle is None:
         so = ORACLE_DIR / "liboracle.so"
-        src = ORACLE_DIR / "bm_oracle.c"
-        if not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
+        srcs = [ORACLE_DIR / "bm_oracle.c", ORACLE_DIR / "bm_oracle_entropy.c"]
+        if not so.exists() or so.stat().st_mtime < max(x.stat().st_mtime for x in srcs):
             subprocess.run(["make", "-C", str(ORACLE_DIR), str(so)], check=True, capture_output=True)
         _oracle = C.CDLL(str(so))
         _oracle.orc_bit_block_count.restype = C.c_uint32
@@ -294,3 +294,36 @@ def oracle_deserialize(blob, n_cols):
     blocks = np.zeros((n_cols, BLOCK_WORDS), np.uint32); gaps = np.zeros((n_cols, GAP_MAX_WORDS), np.uint16)
     rc = oracle().orc_deserialize(ptr(b), C.c_uint64(b.size), C.c_uint32(n_cols), ptr(kind), ptr(blocks), ptr(gaps))
     return rc, kind, blocks, gaps
+
+
+_blobhost = None
+
+
+def blobhost() -> C.CDLL:
+    """Host build of the product's BLOB walker / entropy decoder header (oracle/blob_host_check.cpp): a checker, not a product path."""
+    global _blobhost
+    if _blobhost is None:
+        so = ORACLE_DIR / "libblobhost.so"
+        srcs = [ORACLE_DIR / "blob_host_check.cpp", ROOT / "bitmagic_b200" / "csrc" / "blob_entropy.cuh"]
+        if not so.exists() or so.stat().st_mtime < max(x.stat().st_mtime for x in srcs):
+            subprocess.run(["make", "-C", str(ORACLE_DIR), str(so)], check=True, capture_output=True)
+        _blobhost = C.CDLL(str(so))
+    return _blobhost
+
+
+def blob_host_check(blob, n_cols):
+    """-> rc, kind, decoded (1 = block came from an entropy-coded token), gap_words, blocks, gaps, n_entropy_tokens"""
+    b = np.ascontiguousarray(blob, dtype=np.uint8)
+    kind = np.zeros(n_cols, np.uint8); dec = np.zeros(n_cols, np.uint8); gw = np.zeros(n_cols, np.uint32)
+    blocks = np.zeros((n_cols, BLOCK_WORDS), np.uint32); gaps = np.zeros((n_cols, GAP_MAX_WORDS), np.uint16)
+    n_ent = C.c_uint32(0)
+    rc = blobhost().blob_host_check(ptr(b), C.c_uint64(b.size), C.c_uint32(n_cols), ptr(kind), ptr(dec), ptr(gw), ptr(blocks), ptr(gaps),
+                                    C.byref(n_ent))
+    return rc, kind, dec, gw, blocks, gaps, n_ent.value
+
+
+def oracle_token_hist(enable=True):
+    """256 counters filled by orc_deserialize (one per serializer token type met); call with False to switch off"""
+    h = np.zeros(256, np.uint32)
+    oracle().orc_set_token_hist(ptr(h) if enable else C.c_void_p(0))
+    return h

@@ -56,9 +56,11 @@ def test_oracle_scan_vs_golden(name):
     assert int(pop.sum()) == int(((vals == 55) & live).sum())
 
 
-def test_oracle_deserialize_vs_golden():
-    """orc_deserialize on the committed serializer BLOBs (levels 0..2) == the committed bm::deserialize output."""
-    nv, nb, blobs, kinds, blks, gapsf = gu.load_blobs()
+@pytest.mark.parametrize("name", ["blobs", "blobs_entropy"])
+def test_oracle_deserialize_vs_golden(name):
+    """orc_deserialize on the committed serializer BLOBs (levels 0..2: explicit-length encodings; levels 3..6: gamma /
+    interpolative / super-block encodings) == the committed bm::deserialize output."""
+    nv, nb, blobs, kinds, blks, gapsf = gu.load_blobs(name)
     for level, bl in blobs.items():
         for v in range(nv):
             rc, kind, blk, gaps = orclib.oracle_deserialize(bl[v], nb)
@@ -67,3 +69,27 @@ def test_oracle_deserialize_vs_golden():
             glen = np.where(kind == bm.BLK_GAP, (gaps[:, 0] >> 3) + 1, 0)
             flat = np.concatenate([gaps[c, :glen[c]] for c in range(nb)]) if glen.sum() else np.zeros(0, np.uint16)
             assert np.array_equal(flat, gapsf[level][v])
+
+
+def test_device_decoder_host_build_vs_golden():
+    """Host build of the product's BLOB walker / entropy decoder (oracle/blob_host_check.cpp over bitmagic_b200/csrc/blob_entropy.cuh)
+    on the committed entropy-coded BLOBs == the committed bm::deserialize output (kinds of all blocks; bits / GAP words of the
+    blocks decoded from entropy-coded tokens)."""
+    nv, nb, blobs, kinds, blks, gapsf = gu.load_blobs("blobs_entropy")
+    n_ent = 0
+    for level, bl in blobs.items():
+        for v in range(nv):
+            rc, kind, dec, gw, blk, gaps, n = orclib.blob_host_check(bl[v], nb)
+            assert rc == 0, f"level {level} vector {v}: rc={rc}"
+            n_ent += n
+            assert np.array_equal(kind, kinds[level][v])
+            want, cur = {}, 0                                   # split the flat golden GAP words by their headers
+            for c in np.flatnonzero(kind == bm.BLK_GAP):
+                n = (int(gapsf[level][v][cur]) >> 3) + 1
+                want[int(c)] = gapsf[level][v][cur:cur + n]; cur += n
+            for c in np.flatnonzero(dec):
+                if kind[c] == bm.BLK_BIT:
+                    assert np.array_equal(blk[c], blks[v][c])
+                else:
+                    assert int(gw[c]) == want[int(c)].size and np.array_equal(gaps[c, :gw[c]], want[int(c)])
+    assert n_ent > 300

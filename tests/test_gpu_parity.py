@@ -632,34 +632,70 @@ def test_shift_right_and_vs_oracle(ctx, seed):
     assert found == bool(opop.sum()) and np.array_equal(np.stack([res.block_words(c) for c in range(6)]), oblk)
 
 
-def test_deserialize_to_device_vs_golden_and_oracle(ctx):
-    """bmb200_set_upload_blobs: serializer BLOBs (levels 0..2, committed fixtures written by the reference) decoded on the GPU ==
-    bm::deserialize (block kinds, bits, GAP words); the decoded set then aggregates like the plainly uploaded one; BLOBs with
-    entropy-coded blocks are refused loudly."""
-    nv, nb, blobs, kinds, blks, gapsf = gu.load_blobs()
+def _check_decoded_set(ctx, dset, nv, nb, kinds, blks, gapsf, label):
+    ps = dset.download()
+    isgap = (ps.desc & 3) == bm.BLK_GAP
+    assert ((ps.desc[isgap] >> 30) & 1).all()                      # decoded GAP blocks are in the flat-streamable form
+    for v in range(nv):
+        bv = ps.vector(v)
+        assert np.array_equal(bv.kind, kinds[v]), f"{label} vector {v}: kinds {bv.kind} vs {kinds[v]}"
+        assert np.array_equal(np.stack([bv.block_words(c) for c in range(nb)]), blks[v]), f"{label} vector {v}: bits"
+        flat = [bv.blocks[c] for c in range(nb) if bv.kind[c] == bm.BLK_GAP]
+        assert np.array_equal(np.concatenate(flat) if flat else np.zeros(0, np.uint16), gapsf[v]), f"{label} vector {v}: GAP words"
+    return ps
+
+
+@pytest.mark.parametrize("name", ["blobs", "blobs_entropy"])
+def test_deserialize_to_device_vs_golden_and_oracle(ctx, name):
+    """bmb200_set_upload_blobs: serializer BLOBs (committed fixtures written by the reference; "blobs" = levels 0..2, explicit-length
+    encodings, host token walk; "blobs_entropy" = levels 3..6, gamma / interpolative / super-block encodings, token walk + entropy
+    decode on the GPU) decoded on the GPU == bm::deserialize (block kinds, bits, GAP words); the decoded set then aggregates
+    like the plainly uploaded one; streams the decoder does not cover and truncated streams are refused loudly."""
+    nv, nb, blobs, kinds, blks, gapsf = gu.load_blobs(name)
     for level, bl in blobs.items():
         dset = bm.DeviceSet.upload_blobs(ctx, bl, nb)
-        ps = dset.download()
-        isgap = (ps.desc & 3) == bm.BLK_GAP
-        assert ((ps.desc[isgap] >> 30) & 1).all()                      # decoded GAP blocks are in the flat-streamable form
-        for v in range(nv):
-            bv = ps.vector(v)
-            assert np.array_equal(bv.kind, kinds[level][v]), f"level {level} vector {v}: kinds"
-            assert np.array_equal(np.stack([bv.block_words(c) for c in range(nb)]), blks[v]), f"level {level} vector {v}: bits"
-            flat = [bv.blocks[c] for c in range(nb) if bv.kind[c] == bm.BLK_GAP]
-            assert np.array_equal(np.concatenate(flat) if flat else np.zeros(0, np.uint16), gapsf[level][v]), f"level {level} vector {v}: GAP words"
+        ps = _check_decoded_set(ctx, dset, nv, nb, kinds[level], blks, gapsf[level], f"{name} level {level}")
         check_vs_oracle(ctx, ps, bm.OP_OR, list(range(nv)), None, C, dset)
         check_vs_oracle(ctx, ps, bm.OP_AND_SUB, [0, 1], list(range(2, nv)), C, dset)
         rs = bm.DeviceRS(ctx, dset, 3)
         pos = np.arange(0, nb * 65536, 997, dtype=np.uint64)
         assert np.array_equal(rs.rank(pos), orclib.oracle_rank(ps, 3, pos))
         rs.free(); dset.free()
-    if orclib.have_ref():
+    top = max(blobs)
+    # a mixed set: every vector at a different level (host-walkable and entropy-coded BLOBs side by side)
+    levels = sorted(blobs)
+    mixed = [blobs[levels[v % len(levels)]][v] for v in range(nv)]
+    dset = bm.DeviceSet.upload_blobs(ctx, mixed, nb)
+    _check_decoded_set(ctx, dset, nv, nb, [kinds[levels[v % len(levels)]][v] for v in range(nv)], blks,
+                       [gapsf[levels[v % len(levels)]][v] for v in range(nv)], f"{name} mixed levels")
+    dset.free()
+    # fewer columns than the BLOBs hold: the tail is decoded (to find the token ends) but not stored
+    dset = bm.DeviceSet.upload_blobs(ctx, blobs[top], nb - 3)
+    ps = dset.download()
+    for v in range(nv):
+        assert np.array_equal(np.stack([ps.vector(v).block_words(c) for c in range(nb - 3)]), blks[v][: nb - 3])
+    dset.free()
+    bad = blobs[top][0].copy(); bad[0] |= 1 << 5                       # BM_HM_64_BIT header: not covered
+    with pytest.raises(bm.BMB200Error) as e:
+        bm.DeviceSet.upload_blobs(ctx, [bad], nb)
+    assert e.value.code == bm.capi.ERR_UNSUPPORTED
+    for v in range(min(nv, 6)):                                        # truncated streams: rejected, never read past the end
+        with pytest.raises(bm.BMB200Error):
+            bm.DeviceSet.upload_blobs(ctx, [blobs[top][v][: max(2, blobs[top][v].size // 2)]], nb)
+    if orclib.have_ref():                                              # fresh BLOBs of the real serializer, all levels
         import test_oracle_vs_reference as tor
-        psr = bm.PackedSet.pack(tor.blob_inputs())
-        bad = [orclib.ref_serialize(psr, v, 5) for v in range(psr.n_vec)]
-        with pytest.raises(bm.BMB200Error) as e:
-            bm.DeviceSet.upload_blobs(ctx, bad, psr.n_blocks)
-        assert e.value.code == bm.capi.ERR_UNSUPPORTED
-    with pytest.raises(bm.BMB200Error):
-        bm.DeviceSet.upload_blobs(ctx, [blobs[2][0][: blobs[2][0].size // 2]], nb)
+        vecs = tor.entropy_inputs(7) if name == "blobs_entropy" else tor.blob_inputs()
+        psr = bm.PackedSet.pack(vecs)
+        for level in range(0, 7):
+            bl = [orclib.ref_serialize(psr, v, level) for v in range(psr.n_vec)]
+            want = [orclib.ref_deserialize(b, psr.n_blocks) for b in bl]
+            dset = bm.DeviceSet.upload_blobs(ctx, bl, psr.n_blocks)
+            got = dset.download()
+            for v in range(psr.n_vec):
+                bv = got.vector(v)
+                assert np.array_equal(bv.kind, want[v][0]), f"level {level} vector {v}: kinds"
+                assert np.array_equal(np.stack([bv.block_words(c) for c in range(psr.n_blocks)]), want[v][2]), f"level {level} vector {v}: bits"
+                for c in range(psr.n_blocks):
+                    if bv.kind[c] == bm.BLK_GAP:
+                        assert np.array_equal(bv.blocks[c], want[v][3][c][: bv.blocks[c].size]), f"level {level} vector {v} column {c}: GAP words"
+            dset.free()

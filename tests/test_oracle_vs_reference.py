@@ -280,29 +280,66 @@ def blob_inputs(seed=5, n_blocks=12):
     return vecs
 
 
+def entropy_inputs(seed=20260923):
+    """The vectors behind tests/golden/blobs_entropy.npz (tests/gen.entropy_vectors)."""
+    return gen.entropy_vectors(np.random.default_rng(seed))
+
+
+# entropy-coded tokens the serializer of this reference version emits at levels 3..6 (measured); all must be met by the corpus
+ENTROPY_TOKENS = (21, 23, 61, 62, 63, 65, 66, 67, 68)
+
+
 @needs_ref
 def test_deserialize_oracle_matches_reference():
-    """orc_deserialize == bm::deserialize on BLOBs written by bm::serializer<> at every compression level: exact (bits, block
-    kinds, GAP bytes) for levels 0..2, and never silently wrong above (either exact or BMB200_ERR_UNSUPPORTED)."""
-    vecs = blob_inputs()
-    ps = bm.PackedSet.pack(vecs)
-    seen = set()
-    for level in range(0, 7):
-        n_ok = 0
-        for v in range(ps.n_vec):
-            blob = orclib.ref_serialize(ps, v, level)
-            rkind, rpop, rblk, rgap = orclib.ref_deserialize(blob, ps.n_blocks)
-            assert np.array_equal(rblk, np.stack([vecs[v].block_words(c) for c in range(ps.n_blocks)]))
-            rc, kind, blk, gaps = orclib.oracle_deserialize(blob, ps.n_blocks)
-            if level <= 2:
+    """orc_deserialize == bm::deserialize on BLOBs written by bm::serializer<> at every compression level (0..6): bits, block
+    kinds and GAP bytes, over vectors that make the serializer use every encoding it has (token histogram checked)."""
+    hist = orclib.oracle_token_hist()
+    seen = np.zeros(256, np.uint64)
+    for vecs in (blob_inputs(), entropy_inputs(), entropy_inputs(7)):
+        ps = bm.PackedSet.pack(vecs)
+        for level in range(0, 7):
+            for v in range(ps.n_vec):
+                blob = orclib.ref_serialize(ps, v, level)
+                rkind, rpop, rblk, rgap = orclib.ref_deserialize(blob, ps.n_blocks)
+                assert np.array_equal(rblk, np.stack([vecs[v].block_words(c) for c in range(ps.n_blocks)]))
+                rc, kind, blk, gaps = orclib.oracle_deserialize(blob, ps.n_blocks)
                 assert rc == 0, f"level {level} vector {v}: rc={rc}"
-            else:
-                assert rc in (0, 202)
-            if rc == 0:
-                n_ok += 1
                 assert np.array_equal(blk, rblk) and np.array_equal(kind, rkind) and np.array_equal(gaps, rgap), f"level {level} vector {v}"
-        if level <= 2:
-            assert n_ok == ps.n_vec
+    seen += hist
+    orclib.oracle_token_hist(False)
+    for t in ENTROPY_TOKENS + (11, 16, 18, 19, 22, 24, 30, 34):
+        assert seen[t] > 0, f"serializer token {t} not exercised"
+    vecs = blob_inputs(); ps = bm.PackedSet.pack(vecs)
     # truncated / corrupt streams are rejected, not read past the end
     blob = orclib.ref_serialize(ps, 0, 2)
     assert orclib.oracle_deserialize(blob[: blob.size // 2], ps.n_blocks)[0] != 0
+
+
+@needs_ref
+def test_device_decoder_host_build_matches_reference():
+    """The product's BLOB walker + entropy decoder (bitmagic_b200/csrc/blob_entropy.cuh), built for the host as a checker
+    (oracle/blob_host_check.cpp: same functions, a team of one lane instead of a warp), == bm::deserialize: block kinds for every
+    block, and for every block that came from an entropy-coded token the exact bits / GAP words pass 2 stores in the arena."""
+    n_ent = 0
+    for vecs in (blob_inputs(), entropy_inputs(), entropy_inputs(7)):
+        ps = bm.PackedSet.pack(vecs)
+        for level in range(0, 7):
+            for v in range(ps.n_vec):
+                blob = orclib.ref_serialize(ps, v, level)
+                rkind, rpop, rblk, rgap = orclib.ref_deserialize(blob, ps.n_blocks)
+                rc, kind, dec, gw, blk, gaps, n = orclib.blob_host_check(blob, ps.n_blocks)
+                assert rc == 0, f"level {level} vector {v}: rc={rc}"
+                n_ent += n
+                assert np.array_equal(kind, rkind), f"level {level} vector {v}: kinds"
+                for c in np.flatnonzero(dec):
+                    if kind[c] == bm.BLK_BIT:
+                        assert np.array_equal(blk[c], rblk[c]), f"level {level} vector {v} column {c}: bits"
+                    else:
+                        assert np.array_equal(gaps[c], rgap[c]), f"level {level} vector {v} column {c}: GAP words"
+    assert n_ent > 500
+    # truncated streams and a header the decoder does not cover are rejected
+    vecs = entropy_inputs(); ps = bm.PackedSet.pack(vecs)
+    blob = orclib.ref_serialize(ps, 2, 5)
+    assert orclib.blob_host_check(blob[: blob.size // 2], ps.n_blocks)[0] != 0
+    bad = blob.copy(); bad[0] |= 1 << 5                           # BM_HM_64_BIT
+    assert orclib.blob_host_check(bad, ps.n_blocks)[0] == 202
