@@ -122,6 +122,13 @@ class BVector:
         self.kind[nb] = BLK_BIT
         self.blocks[nb] = np.ascontiguousarray(words, dtype=np.uint32)
 
+    def slice(self, lo: int, hi: int) -> "BVector":
+        """Block columns [lo, hi) as a vector of their own (the shard a rank holds under block-range sharding)."""
+        out = BVector(hi - lo)
+        out.kind[:] = self.kind[lo:hi]
+        out.blocks = {nb - lo: b for nb, b in self.blocks.items() if lo <= nb < hi}
+        return out
+
     def optimize(self) -> "BVector":
         """In place, like bvector::optimize(opt_compress): empty -> NULL, all-ones -> FULL,
         runs < 1276 -> GAP (reference src/bmblocks.h:1414-1437)."""

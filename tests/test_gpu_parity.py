@@ -699,3 +699,54 @@ def test_deserialize_to_device_vs_golden_and_oracle(ctx, name):
                     if bv.kind[c] == bm.BLK_GAP:
                         assert np.array_equal(bv.blocks[c], want[v][3][c][: bv.blocks[c].size]), f"level {level} vector {v} column {c}: GAP words"
             dset.free()
+
+
+def test_sharded_rs_device_callables_two_shards_one_gpu(ctx):
+    """ShardedRS over the device kernels: the vector is cut into two block-range shards that both live on this GPU (each with its own
+    DeviceSet + DeviceRS, queried through the *_dev entry points on torch CUDA tensors); the two shards' contributions are summed by
+    hand (what the all_reduce does) and must equal the unsharded oracle -- positions past the end, rank 0 and ranks above the
+    cardinality included."""
+    import torch
+    from bitmagic_b200.sharding import ShardedRS, device_rs_callables, shard_range
+    rng = np.random.default_rng(78)
+    n_blocks = 600
+    vec = gen.mixed_vectors(rng, 1, n_blocks, p_null=0.3, p_full=0.1, p_gap=0.4)[0]
+    whole = bm.PackedSet.pack([vec])
+    card = vec.count()
+    dev = torch.device("cuda", 0)
+    old = ctx.get_stream()
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    try:
+        pos = np.concatenate([rng.integers(0, n_blocks * 65536, 20000), [0, 65535, 65536, 256 * 65536 - 1, 256 * 65536, n_blocks * 65536 - 1,
+                              n_blocks * 65536, n_blocks * 65536 + 999]]).astype(np.int64)
+        rk = np.concatenate([rng.integers(1, card + 1, 20000), [0, 1, card, card + 1, card + 77]]).astype(np.int64)
+        tpos, trk = torch.from_numpy(pos).to(dev), torch.from_numpy(rk).to(dev)
+        totals = [vec.slice(*shard_range(n_blocks, 2, r)).count() for r in range(2)]
+
+        class TwoShards:                                   # stands in for torch.distributed: shard cardinalities known, no reduction
+            def __init__(self, r): self.r = r
+            def is_initialized(self): return True
+            def get_world_size(self): return 2
+            def get_rank(self): return self.r
+            def all_gather_into_tensor(self, out, t): out.copy_(torch.tensor(totals, dtype=torch.int64, device=out.device))
+            def all_reduce(self, t): pass
+
+        acc_rank = torch.zeros_like(tpos); acc_pos = torch.zeros_like(trk); acc_found = torch.zeros_like(trk, dtype=torch.bool)
+        for r in range(2):
+            lo, hi = shard_range(n_blocks, 2, r)
+            dset = bm.DeviceSet.upload(ctx, bm.PackedSet.pack([vec.slice(lo, hi)]))
+            rs = bm.DeviceRS(ctx, dset, 0)
+            assert rs.total() == totals[r]
+            srs = ShardedRS(rs.total(), *device_rs_callables(rs), n_blocks, TwoShards(r), dev)
+            acc_rank += srs.rank(tpos)
+            p, f = srs.select(trk)
+            acc_pos += p; acc_found |= f
+            torch.cuda.synchronize(dev)
+            rs.free(); dset.free()
+        want_rank = orclib.oracle_rank(whole, 0, pos.astype(np.uint64)).astype(np.int64)
+        want_pos, want_found = orclib.oracle_select(whole, 0, rk.astype(np.uint64))
+        assert np.array_equal(acc_rank.cpu().numpy(), want_rank)
+        assert np.array_equal(acc_found.cpu().numpy(), want_found)
+        assert np.array_equal(acc_pos.cpu().numpy()[want_found], want_pos.astype(np.int64)[want_found])
+    finally:
+        ctx.set_stream(old)

@@ -72,3 +72,55 @@ def test_shift_and_shards_carry_a_one_column_halo():
             assert st == max(0, lo - 1)
             prev_hi = hi
         assert prev_hi == nb
+
+
+def _rs_worker(rank, world, port, n_blocks, q):
+    sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bitmagic_b200 as bm
+    from bitmagic_b200.sharding import ShardedRS, shard_range
+    import gen, orclib
+    rng = np.random.default_rng(77)                       # same vector and same queries on every rank
+    vec = gen.mixed_vectors(rng, 1, n_blocks, p_null=0.3, p_full=0.1, p_gap=0.4)[0]
+    whole = bm.PackedSet.pack([vec])
+    lo, hi = shard_range(n_blocks, world, rank)
+    shard = bm.PackedSet.pack([vec.slice(lo, hi)]) if hi > lo else None
+    total = int(sum(vec.slice(lo, hi).count() for _ in [0])) if hi > lo else 0
+
+    def local_rank(p):
+        return torch.from_numpy(orclib.oracle_rank(shard, 0, p.numpy().astype(np.uint64)).astype(np.int64))
+
+    def local_select(r):
+        pos, found = orclib.oracle_select(shard, 0, r.numpy().astype(np.uint64))
+        return torch.from_numpy(pos.astype(np.int64)), torch.from_numpy(found)
+
+    srs = ShardedRS(total, local_rank, local_select, n_blocks, dist)
+    card = vec.count()
+    pos = np.concatenate([rng.integers(0, n_blocks * 65536, 4000), [0, 65535, 65536, 256 * 65536 - 1, 256 * 65536, n_blocks * 65536 - 1,
+                          n_blocks * 65536, n_blocks * 65536 + 12345]]).astype(np.int64)
+    rk = np.concatenate([rng.integers(1, card + 1, 4000), [0, 1, card, card + 1, card + 1000]]).astype(np.int64)
+    got_rank = srs.rank(torch.from_numpy(pos)).numpy()
+    got_pos, got_found = srs.select(torch.from_numpy(rk))
+    want_rank = orclib.oracle_rank(whole, 0, pos.astype(np.uint64)).astype(np.int64)
+    want_pos, want_found = orclib.oracle_select(whole, 0, rk.astype(np.uint64))
+    ok = (srs.grand_total == card and np.array_equal(got_rank, want_rank) and np.array_equal(got_found.numpy(), want_found)
+          and np.array_equal(got_pos.numpy()[want_found], want_pos.astype(np.int64)[want_found]))
+    q.put((rank, bool(ok), lo, hi))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_blocks", [512, 700])
+def test_sharded_rank_select_world2(n_blocks):
+    """rank / select over a block-range sharded vector (ShardedRS: one all_gather of shard cardinalities, one all_reduce of the
+    answers) == the unsharded oracle, including positions past the end, rank 0 and ranks above the cardinality."""
+    world, port = 2, 31500 + (os.getpid() % 2000)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_rs_worker, args=(r, world, port, n_blocks, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in ps:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _, _ in res), res
