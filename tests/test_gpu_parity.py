@@ -701,7 +701,7 @@ def test_deserialize_to_device_vs_golden_and_oracle(ctx, name):
             dset.free()
 
 
-def test_sharded_rs_device_callables_two_shards_one_gpu(ctx):
+def test_sharded_rs_device_callables_two_shards_one_gpu():
     """ShardedRS over the device kernels: the vector is cut into two block-range shards that both live on this GPU (each with its own
     DeviceSet + DeviceRS, queried through the *_dev entry points on torch CUDA tensors); the two shards' contributions are summed by
     hand (what the all_reduce does) and must equal the unsharded oracle -- positions past the end, rank 0 and ranks above the
@@ -714,7 +714,7 @@ def test_sharded_rs_device_callables_two_shards_one_gpu(ctx):
     whole = bm.PackedSet.pack([vec])
     card = vec.count()
     dev = torch.device("cuda", 0)
-    old = ctx.get_stream()
+    ctx = bm.Context(0)                                    # a context of its own, bound to torch's current stream
     ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
     try:
         pos = np.concatenate([rng.integers(0, n_blocks * 65536, 20000), [0, 65535, 65536, 256 * 65536 - 1, 256 * 65536, n_blocks * 65536 - 1,
@@ -749,4 +749,4 @@ def test_sharded_rs_device_callables_two_shards_one_gpu(ctx):
         assert np.array_equal(acc_found.cpu().numpy(), want_found)
         assert np.array_equal(acc_pos.cpu().numpy()[want_found], want_pos.astype(np.int64)[want_found])
     finally:
-        ctx.set_stream(old)
+        ctx.close()
