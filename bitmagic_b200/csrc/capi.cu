@@ -12,6 +12,9 @@
 #include "aux_kernels.cuh"
 #include "scan_kernel.cuh"
 #include "shift_kernel.cuh"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include "blob_kernel.cuh"
 #include "blob_entropy.cuh"
 
@@ -86,6 +89,22 @@ constexpr size_t kSlack = 512;   // readable bytes past the end of each pool (GA
             return BMB200_ERR_CUDA;                                                     \
         }                                                                               \
     } while (0)
+
+// BMB200_TRACE=1: phase timings of the host-side entry points on stderr (wall clock; each mark synchronizes the stream first,
+// so the time of a phase is attributed to it -- tracing changes the overlap, never the results)
+struct PhaseTrace {
+    bool on; const char* fn; cudaStream_t st; std::chrono::steady_clock::time_point t0, t_prev;
+    PhaseTrace(const char* f, cudaStream_t s) : on(getenv("BMB200_TRACE") != nullptr), fn(f), st(s) { if (on) t0 = t_prev = std::chrono::steady_clock::now(); }
+    void mark(const char* what)
+    {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bmb200] %s: %-28s %9.3f ms  (total %9.3f ms)\n", fn, what,
+                std::chrono::duration<double, std::milli>(t - t_prev).count(), std::chrono::duration<double, std::milli>(t - t0).count());
+        t_prev = t;
+    }
+};
 
 int after_launch(bmb200_ctx* ctx)
 {
@@ -461,6 +480,8 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
     } catch (...) { return BMB200_ERR_BADALLOC; }
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    PhaseTrace tr("set_upload_blobs", st);
+    tr.mark(device_walk ? "host walk (gave up: entropy)" : "host token walk");
     // ---- the compressed bytes are all that crosses PCIe (plus descriptors and the token table): gathered into one pinned
     // buffer so the copy is a single DMA at link speed instead of one pageable copy per vector
     uint8_t* d_stg = nullptr; BlobRec *d_recs = nullptr, *d_erecs = nullptr;
@@ -491,6 +512,7 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
         e = cudaMemcpyAsync(d_stg, ctx->h_stage, stg_bytes, cudaMemcpyHostToDevice, st);
     }
     if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? BMB200_ERR_BADALLOC : BMB200_ERR_CUDA, e);
+    tr.mark("stage + H2D of BLOB bytes");
     const uint32_t ent_grid_max = (uint32_t)ctx->sm_count * 8u;       // warps that decode at the same time (one scratch slot each)
     if (device_walk) {
         // ---- pass 1 on the device: one warp per vector walks (and, for entropy-coded tokens, decodes) its token stream
@@ -509,9 +531,11 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
         if (e == cudaSuccess) e = cudaMemsetAsync(d_full, 0, (size_t)n_vec * n_blocks, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(d_status, 0, 4ull * (n_vec + 1), st);
         if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
+        tr.mark("walk buffers");
         blob_walk_kernel<<<grid, kEntThreads, 0, st>>>(d_stg, d_boff, d_bsize, n_vec, n_blocks, d_toks, tok_cap, d_ntoks, d_status, d_full, d_scratch);
         int rc = after_launch(ctx);
         if (rc) return fail(rc, cudaGetLastError());
+        tr.mark("blob_walk_kernel");
         std::vector<uint32_t> ntoks; std::vector<int> status;
         try { ntoks.resize(n_vec); status.resize(n_vec); } catch (...) { return fail(BMB200_ERR_BADALLOC, cudaSuccess); }
         e = cudaMemcpyAsync(ntoks.data(), d_ntoks, 4ull * n_vec, cudaMemcpyDeviceToHost, st);
@@ -531,6 +555,7 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
     }
+    tr.mark("token table D2H");
     // ---- arena layout: per column in vector order; the tokens of one vector are already in block order
     try {
         desc.assign((size_t)n_vec * n_blocks, 0u); bb.assign((size_t)n_blocks + 1, 0); gb.assign((size_t)n_blocks + 1, 0);
@@ -566,6 +591,7 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
         }
     } catch (...) { return fail(BMB200_ERR_BADALLOC, cudaSuccess); }
     const uint64_t n_bit = bb[n_blocks], n_gap = gb[n_blocks];
+    tr.mark("arena layout (host)");
     int rc = set_alloc(ctx, n_vec, n_blocks, n_bit, n_gap, &s);
     if (rc) { s = nullptr; return fail(rc, cudaSuccess); }
     if (!recs.empty()) e = cudaMalloc((void**)&d_recs, recs.size() * sizeof(BlobRec));
@@ -578,10 +604,12 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
     if (e == cudaSuccess) e = cudaMemcpyAsync((void*)s->v.gap_base, gb.data(), gb.size() * 8, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && n_gap) e = cudaMemsetAsync((void*)s->v.gap_pool, 0, n_gap * 16ull, st);   // fill + holes of the FLAT form
     if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
+    tr.mark("set alloc + tables H2D");
     if (!recs.empty()) {
         uint32_t grid = (uint32_t)std::min<size_t>(recs.size(), (size_t)ctx->sm_count * 16u);
         blob_decode_kernel<<<grid, kBlobThreads, 0, st>>>(d_stg, d_recs, (uint32_t)recs.size(), (uint32_t*)s->v.bit_pool, (uint16_t*)s->v.gap_pool);
         if ((rc = after_launch(ctx))) return fail(rc, cudaGetLastError());
+        tr.mark("blob_decode_kernel");
     }
     int ent_status = 0;
     if (!erecs.empty()) {
@@ -597,7 +625,9 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
     e = cudaStreamSynchronize(st);      // recs / desc staging vectors go out of scope
     if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
     if (ent_status) return fail(ent_status, cudaSuccess);
+    tr.mark("blob_entropy_kernel + sync");
     cleanup();
+    tr.mark("free temporaries");
     *out = s;
     return BMB200_OK;
 }

@@ -188,10 +188,15 @@ int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks
 /* deserialize-to-device: vector v of the set arrives as a BitMagic serialization BLOB (bm::serializer<>, src/bmserial.h) and
  * is decoded on the GPU straight into the arena -- what bm::deserialize(bv, buf) (src/bmserial.h:4152) + an upload of the
  * materialised blocks would produce (same bits, same block kinds), with only the compressed bytes crossing PCIe.
- * Covered: every block encoding whose length is explicit in the stream (serializer compression levels 0..2 completely:
- * zero / one runs, plain bit, bit interval, bit 0-runs, bit digest0, single bit, GAP with 16-bit run ends; plus the
- * bit / GAP position arrays of level 3).  BLOBs with gamma / interpolative / XOR / super-block encodings return
- * BMB200_ERR_UNSUPPORTED (no CPU fallback). */
+ * Covered: every block encoding bm::serializer<> of this reference version writes for a plain bvector at compression levels
+ * 0..6 (6 = its default): the explicit-length ones (zero / one runs, plain bit, bit interval, bit 0-runs, bit digest0, single
+ * bit, bit / GAP position arrays, GAP with 16-bit run ends) are located by a host walk of the token bytes and decoded one CTA
+ * per block; as soon as one BLOB of the call holds an entropy-coded token (Elias-gamma arrays and GAP blocks, binary
+ * interpolative GAP / bit-array blocks v3 / v3s with delta-range reduction and exception lists, super-block position lists,
+ * bookmarks) the token streams are walked ON THE DEVICE (one warp per vector, csrc/blob_entropy.cuh) and every entropy-coded
+ * token is then decoded by a warp of its own.  Not covered (BMB200_ERR_UNSUPPORTED, no CPU fallback): XOR-reference compression
+ * (BM_HM_HXOR, sparse-vector serialization), id-list and 64-bit-address streams, and the legacy encodings the reference can
+ * still read but no longer writes (tokens 20, 27-29, 31, 32, 43-45, 56, 57).  Malformed / truncated streams: BMB200_ERR_BADARG. */
 typedef struct bmb200_blob { const void* data; uint64_t size; } bmb200_blob;
 int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, const bmb200_blob* blobs, bmb200_set** out);
 /* adopt pointers that already live in HBM (caller keeps ownership of the memory) */
