@@ -156,7 +156,14 @@ struct EntRd {
     BME_HD uint32_t u32()
     {
         if (p + 4 > end) { bad = 1; p = end; return 0; }
+#ifdef __CUDA_ARCH__
+        // any alignment: two aligned loads + funnel shift (the staging buffer is 256-byte aligned and carries 64 bytes of slack)
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(s + (p & ~3ull));
+        const uint32_t sh = (uint32_t)(p & 3ull) * 8u, lo = w[0];
+        const uint32_t v = sh ? __funnelshift_r(lo, w[1], sh) : lo;
+#else
         const uint32_t v = (uint32_t)s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16) | ((uint32_t)s[p + 3] << 24);
+#endif
         p += 4; return v;
     }
     BME_HD uint64_t u64() { const uint64_t lo = u32(); return lo | ((uint64_t)u32() << 32); }
@@ -217,12 +224,12 @@ struct EntBits {
     {
         if (!r) return 0u;
         if (r > 0x7ffffff0u) { this->r->bad = 1; return 0u; }
-        const uint32_t logv = 31u - bme_clz(r + 1u);
-        const uint32_t c = (uint32_t)((1ull << (logv + 1u)) - r - 1u);
-        const int64_t half_c = c >> 1, half_r = r >> 1;
-        const int64_t lo1 = half_r - half_c - (int64_t)((r + 1u) & 1u), hi1 = half_r + half_c + 1;
+        const uint32_t logv = 31u - bme_clz(r + 1u);                   // <= 30: everything below fits 32-bit signed arithmetic
+        const uint32_t c = (1u << (logv + 1u)) - r - 1u;
+        const int32_t half_c = (int32_t)(c >> 1), half_r = (int32_t)(r >> 1);
+        const int32_t lo1 = half_r - half_c - (int32_t)((r + 1u) & 1u), hi1 = half_r + half_c + 1;
         uint32_t val = bits(logv);
-        if ((int64_t)val <= lo1 || (int64_t)val >= hi1) val += bit() << logv;
+        if ((int32_t)val <= lo1 || (int32_t)val >= hi1) val += bit() << logv;
         return val;
     }
 };
@@ -231,23 +238,32 @@ struct EntBits {
 template <typename T>
 BME_HDN void ent_bic_decode(EntBits& b, T* out, uint32_t sz, uint32_t lo, uint32_t hi)
 {
-    constexpr uint32_t kMask = (sizeof(T) == 2) ? 0xffffu : 0xffffffffu;       // the reference narrows lo / hi to T at every call
-    uint32_t st_off[20], st_sz[20], st_lo[20], st_hi[20]; int sp = 0;
+    constexpr bool k16 = (sizeof(T) == 2);
+    constexpr uint32_t kMask = k16 ? 0xffffu : 0xffffffffu;                    // the reference narrows lo / hi to T at every call
+    // pending right halves: (first index | size << 16) -- a right half of at most 65536 values holds < 32768 -- and their value range
+    // (16-bit: lo | hi << 16 in one word)
+    uint32_t st_seg[20], st_lo[20], st_hi[k16 ? 1 : 20]; int sp = 0;
+    if (sz > 65536u) { b.r->bad = 1; return; }
     uint32_t off = 0;
     for (;;) {
         while (sz) {
             if (b.r->bad) return;
-            uint32_t val = b.bic((hi - lo - sz + 1u) & 0xffffffffu);
+            uint32_t val = b.bic(hi - lo - sz + 1u);
             const uint32_t mid = sz >> 1;
             val += lo + mid;
             out[off + mid] = (T)val;
             if (sz <= 1u) break;
-            if (sp < 20) { st_off[sp] = off + mid + 1u; st_sz[sp] = sz - mid - 1u; st_lo[sp] = (val + 1u) & kMask; st_hi[sp] = hi; ++sp; }
-            else { b.r->bad = 1; return; }
+            if (sz - mid - 1u) {                         // a non-empty right half waits on the stack (its first index is <= 65535 then)
+                if (sp >= 20) { b.r->bad = 1; return; }
+                st_seg[sp] = (off + mid + 1u) | ((sz - mid - 1u) << 16);
+                if (k16) st_lo[sp] = ((val + 1u) & kMask) | (hi << 16); else { st_lo[sp] = val + 1u; st_hi[k16 ? 0 : sp] = hi; }
+                ++sp;
+            }
             sz = mid; hi = (val - 1u) & kMask;          // left half next; off and lo stay
         }
         if (!sp) return;
-        --sp; off = st_off[sp]; sz = st_sz[sp]; lo = st_lo[sp]; hi = st_hi[sp];
+        --sp; off = st_seg[sp] & 0xffffu; sz = st_seg[sp] >> 16;
+        if (k16) { lo = st_lo[sp] & 0xffffu; hi = st_lo[sp] >> 16; } else { lo = st_lo[sp]; hi = st_hi[k16 ? 0 : sp]; }
     }
 }
 

@@ -39,6 +39,8 @@ struct bmb200_ctx {
     size_t cap_desc = 0, cap_base = 0, cap_bit = 0, cap_gap = 0;
     uint8_t* h_stage = nullptr;             // pinned staging for serialized BLOBs (bmb200_set_upload_blobs), grown on demand
     size_t h_stage_cap = 0;
+    void* d_tmp[10] = {};                   // device temporaries of bmb200_set_upload_blobs (staging, token tables, decode scratch): kept
+    size_t d_tmp_cap[10] = {};              //   between calls, grown on demand -- cudaMalloc / cudaFree of a few hundred MB costs tens of ms each
     int gap_mode = 0;                       // 0 = stream sorted GAP lists through the smem ring, 1 = always gather
     bool attr_set = false;
 };
@@ -200,6 +202,7 @@ int bmb200_destroy(bmb200_ctx* ctx)
     cudaFree(ctx->d_work); cudaFree(ctx->d_group);
     if (ctx->h_group) cudaFreeHost(ctx->h_group);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (void* q : ctx->d_tmp) if (q) cudaFree(q);
     delete ctx;
     return BMB200_OK;
 }
@@ -488,16 +491,26 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
     uint64_t *d_boff = nullptr, *d_bsize = nullptr; BlobTok* d_toks = nullptr; uint32_t* d_ntoks = nullptr; int* d_status = nullptr;
     uint8_t *d_full = nullptr, *d_scratch = nullptr;
     bmb200_set* s = nullptr;
-    auto cleanup = [&]() { cudaFree(d_stg); cudaFree(d_recs); cudaFree(d_erecs); cudaFree(d_boff); cudaFree(d_bsize); cudaFree(d_toks);
-                           cudaFree(d_ntoks); cudaFree(d_status); cudaFree(d_full); cudaFree(d_scratch); };
+    // temporaries live in the context's grow-only pool (slot i of ctx->d_tmp); the stream is synchronized before this function
+    // returns, so the next call may reuse them
+    auto tmp_alloc = [&](int slot, void** ptr, size_t bytes) -> cudaError_t {
+        if (bytes > ctx->d_tmp_cap[slot]) {
+            if (ctx->d_tmp[slot]) { cudaStreamSynchronize(st); cudaFree(ctx->d_tmp[slot]); ctx->d_tmp[slot] = nullptr; ctx->d_tmp_cap[slot] = 0; }
+            cudaError_t ae = cudaMalloc(&ctx->d_tmp[slot], bytes);
+            if (ae != cudaSuccess) return ae;
+            ctx->d_tmp_cap[slot] = bytes;
+        }
+        *ptr = ctx->d_tmp[slot];
+        return cudaSuccess;
+    };
+    auto cleanup = [&]() {};
     auto fail = [&](int rc, cudaError_t e) {
         cudaStreamSynchronize(st);
         if (rc == BMB200_ERR_CUDA || (!rc && e != cudaSuccess)) { ctx->last_err = std::string("set_upload_blobs: ") + cudaGetErrorString(e); rc = BMB200_ERR_CUDA; }
-        cleanup();
         if (s) { free_set_arrays(s); delete s; }
         return rc;
     };
-    cudaError_t e = cudaMalloc((void**)&d_stg, stg_bytes + 64);
+    cudaError_t e = tmp_alloc(0, (void**)&d_stg, stg_bytes + 64);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_stg + stg_bytes, 0, 64, st);
     if (e == cudaSuccess && stg_bytes > ctx->h_stage_cap) {
         cudaStreamSynchronize(st);
@@ -518,13 +531,13 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
         // ---- pass 1 on the device: one warp per vector walks (and, for entropy-coded tokens, decodes) its token stream
         const uint32_t tok_cap = n_blocks + n_blocks / 256u + 2u;
         const uint32_t grid = std::min(n_vec, ent_grid_max);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&d_boff, 8ull * n_vec);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&d_bsize, 8ull * n_vec);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&d_toks, sizeof(BlobTok) * (size_t)n_vec * tok_cap);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&d_ntoks, 4ull * n_vec);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&d_status, 4ull * (n_vec + 1));
-        if (e == cudaSuccess) e = cudaMalloc((void**)&d_full, (size_t)n_vec * n_blocks);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&d_scratch, (size_t)ent_grid_max * kEntScratchBytes);
+        if (e == cudaSuccess) e = tmp_alloc(1, (void**)&d_boff, 8ull * n_vec);
+        if (e == cudaSuccess) e = tmp_alloc(2, (void**)&d_bsize, 8ull * n_vec);
+        if (e == cudaSuccess) e = tmp_alloc(3, (void**)&d_toks, sizeof(BlobTok) * (size_t)n_vec * tok_cap);
+        if (e == cudaSuccess) e = tmp_alloc(4, (void**)&d_ntoks, 4ull * n_vec);
+        if (e == cudaSuccess) e = tmp_alloc(5, (void**)&d_status, 4ull * (n_vec + 1));
+        if (e == cudaSuccess) e = tmp_alloc(6, (void**)&d_full, (size_t)n_vec * n_blocks);
+        if (e == cudaSuccess) e = tmp_alloc(7, (void**)&d_scratch, (size_t)ent_grid_max * kEntScratchBytes);
         if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? BMB200_ERR_BADALLOC : BMB200_ERR_CUDA, e);
         e = cudaMemcpyAsync(d_boff, stg_off.data(), 8ull * n_vec, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_bsize, blob_size.data(), 8ull * n_vec, cudaMemcpyHostToDevice, st);
@@ -594,8 +607,8 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
     tr.mark("arena layout (host)");
     int rc = set_alloc(ctx, n_vec, n_blocks, n_bit, n_gap, &s);
     if (rc) { s = nullptr; return fail(rc, cudaSuccess); }
-    if (!recs.empty()) e = cudaMalloc((void**)&d_recs, recs.size() * sizeof(BlobRec));
-    if (e == cudaSuccess && !erecs.empty()) e = cudaMalloc((void**)&d_erecs, erecs.size() * sizeof(BlobRec));
+    if (!recs.empty()) e = tmp_alloc(8, (void**)&d_recs, recs.size() * sizeof(BlobRec));
+    if (e == cudaSuccess && !erecs.empty()) e = tmp_alloc(9, (void**)&d_erecs, erecs.size() * sizeof(BlobRec));
     if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? BMB200_ERR_BADALLOC : BMB200_ERR_CUDA, e);
     if (!recs.empty()) e = cudaMemcpyAsync(d_recs, recs.data(), recs.size() * sizeof(BlobRec), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && !erecs.empty()) e = cudaMemcpyAsync(d_erecs, erecs.data(), erecs.size() * sizeof(BlobRec), cudaMemcpyHostToDevice, st);
