@@ -236,7 +236,7 @@ struct EntBits {
 
 // bic_decode_u16_cm / _u32_cm: out[0..sz) ascending in [lo, hi]; pre-order (node, left half, right half) with an explicit stack
 template <typename T>
-BME_HDN void ent_bic_decode(EntBits& b, T* out, uint32_t sz, uint32_t lo, uint32_t hi)
+BME_HD void ent_bic_decode(EntBits& b, T* out, uint32_t sz, uint32_t lo, uint32_t hi)
 {
     constexpr bool k16 = (sizeof(T) == 2);
     constexpr uint32_t kMask = k16 ? 0xffffu : 0xffffffffu;                    // the reference narrows lo / hi to T at every call
@@ -293,7 +293,7 @@ BME_HDN void ent_restore_min_w(uint16_t* arr, uint32_t n, uint32_t wlen, uint32_
 
 // bit_in::decode_array (src/encoding.h:2698-2798).  out / tmp: lists of kEntListCap u16, wf: 2048 words.  Returns the flag byte
 // (>= 0) with *sz set, or -1.
-BME_HDN int ent_decode_array(EntBits& b, uint16_t* out, uint16_t* tmp, uint32_t* wf, uint32_t* sz, uint32_t default_sz)
+BME_HD int ent_decode_array(EntBits& b, uint16_t* out, uint16_t* tmp, uint32_t* wf, uint32_t* sz, uint32_t default_sz)
 {
     const uint32_t h = b.bits(8u);
     if ((h & 3u) == 3u && (h & 0x80u)) { *sz = 0; return (int)h; }                                     // no-op
@@ -452,7 +452,7 @@ BME_HD void ent_write_bits(const EntCtx& c, uint32_t* dst)
 // copy is the one that counts).  Returns 0 or a BMB200_ERR_* value (team-uniform); *gap_family = the reference materialises
 // the token through a GAP block (deserialize_gap) and keeps it a GAP block when it fits.
 // ------------------------------------------------------------------------------------------------------------------
-BME_HDN int ent_decode_block(const EntCtx& c, uint32_t code, EntRd& rd, uint32_t* gap_family)
+BME_HD int ent_decode_block_impl(const EntCtx& c, uint32_t code, EntRd& rd, uint32_t* gap_family)
 {
     const bool lead = (c.t.lane == 0u);
     EntBits b; b.init(&rd);
@@ -581,8 +581,18 @@ BME_HDN int ent_decode_block(const EntCtx& c, uint32_t code, EntRd& rd, uint32_t
     return err ? BMB200_ERR_BADARG : BMB200_OK;
 }
 
+// the reader state is copied into locals so that, with everything above inlined, the bit accumulator and the stream position live in
+// registers during the (sequential, latency-bound) decode loops instead of in the caller's stack frame
+BME_HDN int ent_decode_block(const EntCtx& c, uint32_t code, EntRd& rd_io, uint32_t* gap_family)
+{
+    EntRd rd = rd_io;
+    const int rc = ent_decode_block_impl(c, code, rd, gap_family);
+    rd_io = rd;
+    return rc;
+}
+
 // super-block token 68 (set_sblock_bienc_v3): lane 0 decodes the ascending 24-bit positions into `arr` (65536 u32 = lists a + b)
-BME_HDN int ent_decode_sblock(EntRd& rd, uint32_t* arr, uint32_t* len_out, uint32_t* sb_out)
+BME_HD int ent_decode_sblock_impl(EntRd& rd, uint32_t* arr, uint32_t* len_out, uint32_t* sb_out)
 {
     EntBits b; b.init(&rd);
     const uint32_t flag = b.bits(8u);
@@ -603,6 +613,13 @@ BME_HDN int ent_decode_sblock(EntRd& rd, uint32_t* arr, uint32_t* len_out, uint3
     if (arr[len - 1u] >= 256u * 65536u) return BMB200_ERR_BADARG;
     *len_out = len; *sb_out = sb;
     return BMB200_OK;
+}
+BME_HDN int ent_decode_sblock(EntRd& rd_io, uint32_t* arr, uint32_t* len_out, uint32_t* sb_out)
+{
+    EntRd rd = rd_io;
+    const int rc = ent_decode_sblock_impl(rd, arr, len_out, sb_out);
+    rd_io = rd;
+    return rc;
 }
 // positions [k0, k1) of a decoded super-block list that fall into block `blk` -> bitmap (cleared first)
 BME_HD void ent_sblock_fill(const EntCtx& c, const uint32_t* arr, uint32_t k0, uint32_t k1)
