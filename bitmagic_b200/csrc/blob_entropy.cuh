@@ -32,6 +32,7 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
+#include <vector>
 
 #if defined(__CUDACC__)
 #define BME_HD __host__ __device__ __forceinline__
@@ -641,12 +642,27 @@ BME_HD void ent_push(EntWalkOut& o, const BlobTok& t, uint32_t* err) { if (o.n <
 
 // explicit-length tokens are only measured here (type + extent, exactly what the host walker of capi.cu records); their payload
 // is decoded by blob_decode_kernel.  Entropy-coded tokens are decoded to find their end and their block shape.
-BME_HDN int ent_walk_vector(const EntCtx& c, const uint8_t* stg, uint64_t blob_off, uint64_t blob_size, uint32_t n_blocks, EntWalkOut& o)
+//
+// One call walks one SEGMENT of a vector's stream: the bytes [seg.start, seg.end) of the BLOB, beginning at block seg.nb0.  A BLOB
+// without bookmarks is a single segment that starts at its header (seg.start == 0, header parsed here) and runs to its end token;
+// a BLOB written with serializer::set_bookmarks (src/bmserial.h:1487, process_bookmark :3567) is cut at its sync marks by
+// ent_find_segments, and the segments of one vector are walked by different warps at the same time.
+struct EntSeg {
+    uint64_t blob_off, blob_size;   // the BLOB inside the staging buffer
+    uint64_t start, end;            // segment bytes, relative to the BLOB; start == 0: begin at the header
+    uint32_t nb0;                   // block index at `start`
+    uint32_t bounded;               // 1: the segment ends exactly at `end` (a sync mark follows), 0: it ends with an end-of-stream token
+    uint32_t vec;                   // vector the segment belongs to
+    uint32_t tok_base;              // first BlobTok slot of this segment in the token table
+};
+
+BME_HDN int ent_walk_segment(const EntCtx& c, const uint8_t* stg, const EntSeg& sg, uint32_t n_blocks, EntWalkOut& o)
 {
     const bool lead = (c.t.lane == 0u);
-    EntRd rd{stg, blob_off, blob_off + blob_size, 0u};
+    const uint64_t blob_off = sg.blob_off;
+    EntRd rd{stg, blob_off + sg.start, blob_off + (sg.bounded ? sg.end : sg.blob_size), 0u};
     uint32_t err = 0;
-    if (lead) {
+    if (lead && sg.start == 0u) {
         const uint32_t hf = rd.u8();
         if (!(hf & (1u << 3))) rd.u8();                                              // byte order
         if (hf & ((1u << 2) | (1u << 5) | (1u << 6))) err = BMB200_ERR_UNSUPPORTED;  // id list / 64-bit / XOR compression
@@ -656,11 +672,12 @@ BME_HDN int ent_walk_vector(const EntCtx& c, const uint8_t* stg, uint64_t blob_o
     }
     err = bme_bcast(err);
     if (err) return (int)err;
-    uint64_t nb = 0;
+    uint64_t nb = sg.nb0;
     for (;;) {
         // ---- lane 0 reads the token byte and settles everything that needs no team work ----
         uint32_t act = 0, code = 0, cnt = 0;      // act: 0 next token, 1 end, 2 all-ones run of cnt blocks, 3 entropy block, 4 super-block, 5 error (code)
-        if (lead) {
+        if (lead && sg.bounded && rd.p == rd.end) act = 1;                           // reached the sync mark that closes this segment
+        else if (lead) {
             const uint32_t bt = rd.u8();
             BlobTok t; t.nb = (uint32_t)nb; t.type = 0; t.off = rd.p - blob_off; t.aux = 0; t.first = 0; t.gap_words = 0; t.kind = BMB200_BLK_BIT;
             bool blk = false;
@@ -841,6 +858,55 @@ BME_HDN int ent_emit(const EntCtx& c, const uint8_t* stg, uint64_t src, uint64_t
     return BMB200_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// host side of pass 1: cut a BLOB at its bookmarks.  Pure byte parsing (no decoding): header, then the chain
+//   [set_nb_bookmark16/24/32, offset] ... tokens ... [set_nb_sync_mark8/16/24/32, blocks since the bookmark] [bookmark] ...
+// (serializer::process_bookmark, src/bmserial.h:3567-3665; reader :5897-5950).  offset = bytes from the end of the offset field
+// to the sync mark; 0 = the bookmark was never closed (the last one).  Returns segments relative to the BLOB; a BLOB without a
+// leading bookmark is one unbounded segment starting at its header.
+// ------------------------------------------------------------------------------------------------------------------
+inline int ent_find_segments(const uint8_t* blob, uint64_t size, uint32_t vec, uint64_t blob_off, std::vector<EntSeg>& out)
+{
+    auto whole = [&]() { EntSeg s{}; s.blob_off = blob_off; s.blob_size = size; s.start = 0; s.end = size; s.nb0 = 0; s.bounded = 0; s.vec = vec; out.push_back(s); return BMB200_OK; };
+    if (size < 2) return BMB200_ERR_BADARG;
+    uint64_t p = 0;
+    const uint32_t hf = blob[p++];
+    if (!(hf & (1u << 3))) ++p;
+    if (!(hf & (1u << 4))) p += 8;
+    if (hf & (1u << 1)) p += 4;
+    if (p >= size) return BMB200_ERR_BADARG;
+    if (blob[p] < 47u || blob[p] > 49u) return whole();              // no bookmark right after the header
+    const size_t first = out.size();
+    uint64_t nb = 0; bool head = true;
+    for (;;) {
+        if (p >= size) return BMB200_ERR_BADARG;
+        const uint32_t bt = blob[p];
+        if (bt < 47u || bt > 49u) {                                   // the chain ends: the rest is one unbounded segment
+            EntSeg s{}; s.blob_off = blob_off; s.blob_size = size; s.start = p; s.end = size; s.nb0 = (uint32_t)nb; s.bounded = 0; s.vec = vec;
+            out.push_back(s); break;
+        }
+        const uint32_t fsz = bt == 47u ? 2u : bt == 48u ? 3u : 4u;
+        if (p + 1 + fsz > size) return BMB200_ERR_BADARG;
+        uint64_t ofs = 0; for (uint32_t i = 0; i < fsz; ++i) ofs |= (uint64_t)blob[p + 1 + i] << (8 * i);
+        const uint64_t body = p + 1 + fsz;
+        EntSeg s{}; s.blob_off = blob_off; s.blob_size = size; s.vec = vec; s.nb0 = (uint32_t)nb;
+        s.start = head ? 0 : body;                                    // the first segment starts at the header (and meets its own bookmark token)
+        head = false;
+        if (!ofs) { s.end = size; s.bounded = 0; out.push_back(s); break; }
+        const uint64_t sync = body + ofs;
+        if (sync + 2 > size) return BMB200_ERR_BADARG;
+        const uint32_t st = blob[sync];
+        if (st < 50u || st > 53u) { out.resize(first); return whole(); }   // not a mark this walker follows: fall back to one segment
+        const uint32_t dsz = st - 49u;
+        if (sync + 1 + dsz > size) return BMB200_ERR_BADARG;
+        uint64_t delta = 0; for (uint32_t i = 0; i < dsz; ++i) delta |= (uint64_t)blob[sync + 1 + i] << (8 * i);
+        s.end = sync; s.bounded = 1; out.push_back(s);
+        nb += delta; if (nb > 0xffffffffull) return BMB200_ERR_BADARG;
+        p = sync + 1 + dsz;
+    }
+    return BMB200_OK;
+}
+
 }  // namespace bmb200
 
 // ======================================================================================================================
@@ -866,18 +932,20 @@ __device__ __forceinline__ EntCtx ent_make_ctx(uint32_t* s_bm, uint8_t* scratch_
     return c;
 }
 
-// pass 1: one warp per vector.  toks: [n_vec][tok_cap]; n_toks, status: [n_vec]; full: [n_blocks][n_vec] (zeroed by the caller)
-__global__ void __launch_bounds__(kEntThreads) blob_walk_kernel(const uint8_t* __restrict__ stg, const uint64_t* __restrict__ blob_off,
-                                                                const uint64_t* __restrict__ blob_size, uint32_t n_vec, uint32_t n_blocks,
-                                                                BlobTok* __restrict__ toks, uint32_t tok_cap, uint32_t* __restrict__ n_toks,
-                                                                int* __restrict__ status, uint8_t* __restrict__ full, uint8_t* __restrict__ scratch)
+// pass 1: one warp per segment (a whole vector, or one bookmark interval of it).  toks: token table, segment i writes from
+// segs[i].tok_base (at most tok_cap[i] records); n_toks, status: [n_segs]; full: [n_blocks][n_vec] (zeroed by the caller)
+__global__ void __launch_bounds__(kEntThreads) blob_walk_kernel(const uint8_t* __restrict__ stg, const EntSeg* __restrict__ segs, const uint32_t* __restrict__ tok_cap,
+                                                                uint32_t n_segs, uint32_t n_vec, uint32_t n_blocks, BlobTok* __restrict__ toks,
+                                                                uint32_t* __restrict__ n_toks, int* __restrict__ status, uint8_t* __restrict__ full,
+                                                                uint8_t* __restrict__ scratch)
 {
     __shared__ __align__(16) uint32_t s_bm[kEntWords];
     const EntCtx c = ent_make_ctx(s_bm, scratch, blockIdx.x);
-    for (uint32_t v = blockIdx.x; v < n_vec; v += gridDim.x) {
-        EntWalkOut o; o.toks = toks + (size_t)v * tok_cap; o.cap = tok_cap; o.n = 0; o.full = full + v; o.full_stride = n_vec;
-        const int rc = ent_walk_vector(c, stg, blob_off[v], blob_size[v], n_blocks, o);
-        if (c.t.lane == 0) { n_toks[v] = o.n; status[v] = rc; }
+    for (uint32_t i = blockIdx.x; i < n_segs; i += gridDim.x) {
+        const EntSeg sg = segs[i];
+        EntWalkOut o; o.toks = toks + sg.tok_base; o.cap = tok_cap[i]; o.n = 0; o.full = full + sg.vec; o.full_stride = n_vec;
+        const int rc = ent_walk_segment(c, stg, sg, n_blocks, o);
+        if (c.t.lane == 0) { n_toks[i] = o.n; status[i] = rc; }
         __syncwarp();
     }
 }

@@ -39,8 +39,8 @@ struct bmb200_ctx {
     size_t cap_desc = 0, cap_base = 0, cap_bit = 0, cap_gap = 0;
     uint8_t* h_stage = nullptr;             // pinned staging for serialized BLOBs (bmb200_set_upload_blobs), grown on demand
     size_t h_stage_cap = 0;
-    void* d_tmp[10] = {};                   // device temporaries of bmb200_set_upload_blobs (staging, token tables, decode scratch): kept
-    size_t d_tmp_cap[10] = {};              //   between calls, grown on demand -- cudaMalloc / cudaFree of a few hundred MB costs tens of ms each
+    void* d_tmp[12] = {};                   // device temporaries of bmb200_set_upload_blobs (staging, token tables, decode scratch): kept
+    size_t d_tmp_cap[12] = {};              //   between calls, grown on demand -- cudaMalloc / cudaFree of a few hundred MB costs tens of ms each
     int gap_mode = 0;                       // 0 = stream sorted GAP lists through the smem ring, 1 = always gather
     bool attr_set = false;
 };
@@ -527,46 +527,69 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
     if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? BMB200_ERR_BADALLOC : BMB200_ERR_CUDA, e);
     tr.mark("stage + H2D of BLOB bytes");
     const uint32_t ent_grid_max = (uint32_t)ctx->sm_count * 8u;       // warps that decode at the same time (one scratch slot each)
+    uint32_t n_status = 0;                                             // d_status[n_status] = status word of pass 2
+    EntSeg* d_segs = nullptr; uint32_t* d_segcap = nullptr;
     if (device_walk) {
-        // ---- pass 1 on the device: one warp per vector walks (and, for entropy-coded tokens, decodes) its token stream
-        const uint32_t tok_cap = n_blocks + n_blocks / 256u + 2u;
-        const uint32_t grid = std::min(n_vec, ent_grid_max);
+        // ---- pass 1 on the device: one warp per segment (a whole vector, or one bookmark interval of it) walks -- and, for
+        // entropy-coded tokens, decodes -- its piece of the token stream
+        std::vector<EntSeg> segs; std::vector<uint32_t> seg_cap;
+        uint64_t tok_total = 0;
+        try {
+            for (uint32_t v = 0; v < n_vec; ++v) {
+                const size_t first = segs.size();
+                int rc = ent_find_segments((const uint8_t*)blobs[v].data, blobs[v].size, v, stg_off[v], segs);
+                if (rc) return fail(rc, cudaSuccess);
+                for (size_t k = first; k < segs.size(); ++k) {            // token slots: one per block the segment can reach (+ super-block records)
+                    const uint64_t lo = std::min<uint64_t>(segs[k].nb0, n_blocks);
+                    const uint64_t hi = (k + 1 < segs.size()) ? std::min<uint64_t>(std::max<uint64_t>(segs[k + 1].nb0, segs[k].nb0), n_blocks) : n_blocks;
+                    const uint64_t cap = (hi - lo) + (hi - lo) / 256u + 2u;
+                    segs[k].tok_base = (uint32_t)tok_total; seg_cap.push_back((uint32_t)cap); tok_total += cap;
+                    if (tok_total > 0xfffffff0ull) return fail(BMB200_ERR_RANGE, cudaSuccess);
+                }
+            }
+        } catch (...) { return fail(BMB200_ERR_BADALLOC, cudaSuccess); }
+        const uint32_t n_segs = (uint32_t)segs.size();
+        const uint32_t grid = std::min(n_segs, ent_grid_max);
         if (e == cudaSuccess) e = tmp_alloc(1, (void**)&d_boff, 8ull * n_vec);
         if (e == cudaSuccess) e = tmp_alloc(2, (void**)&d_bsize, 8ull * n_vec);
-        if (e == cudaSuccess) e = tmp_alloc(3, (void**)&d_toks, sizeof(BlobTok) * (size_t)n_vec * tok_cap);
-        if (e == cudaSuccess) e = tmp_alloc(4, (void**)&d_ntoks, 4ull * n_vec);
-        if (e == cudaSuccess) e = tmp_alloc(5, (void**)&d_status, 4ull * (n_vec + 1));
+        if (e == cudaSuccess) e = tmp_alloc(3, (void**)&d_toks, sizeof(BlobTok) * (size_t)tok_total);
+        if (e == cudaSuccess) e = tmp_alloc(4, (void**)&d_ntoks, 4ull * n_segs);
+        if (e == cudaSuccess) e = tmp_alloc(5, (void**)&d_status, 4ull * (n_segs + 1));
         if (e == cudaSuccess) e = tmp_alloc(6, (void**)&d_full, (size_t)n_vec * n_blocks);
         if (e == cudaSuccess) e = tmp_alloc(7, (void**)&d_scratch, (size_t)ent_grid_max * kEntScratchBytes);
+        if (e == cudaSuccess) e = tmp_alloc(10, (void**)&d_segs, sizeof(EntSeg) * (size_t)n_segs);
+        if (e == cudaSuccess) e = tmp_alloc(11, (void**)&d_segcap, 4ull * n_segs);
         if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? BMB200_ERR_BADALLOC : BMB200_ERR_CUDA, e);
         e = cudaMemcpyAsync(d_boff, stg_off.data(), 8ull * n_vec, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_bsize, blob_size.data(), 8ull * n_vec, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_segs, segs.data(), sizeof(EntSeg) * (size_t)n_segs, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_segcap, seg_cap.data(), 4ull * n_segs, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(d_full, 0, (size_t)n_vec * n_blocks, st);
-        if (e == cudaSuccess) e = cudaMemsetAsync(d_status, 0, 4ull * (n_vec + 1), st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_status, 0, 4ull * (n_segs + 1), st);
         if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
         tr.mark("walk buffers");
-        blob_walk_kernel<<<grid, kEntThreads, 0, st>>>(d_stg, d_boff, d_bsize, n_vec, n_blocks, d_toks, tok_cap, d_ntoks, d_status, d_full, d_scratch);
+        blob_walk_kernel<<<grid, kEntThreads, 0, st>>>(d_stg, d_segs, d_segcap, n_segs, n_vec, n_blocks, d_toks, d_ntoks, d_status, d_full, d_scratch);
         int rc = after_launch(ctx);
         if (rc) return fail(rc, cudaGetLastError());
         tr.mark("blob_walk_kernel");
-        std::vector<uint32_t> ntoks; std::vector<int> status;
-        try { ntoks.resize(n_vec); status.resize(n_vec); } catch (...) { return fail(BMB200_ERR_BADALLOC, cudaSuccess); }
-        e = cudaMemcpyAsync(ntoks.data(), d_ntoks, 4ull * n_vec, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(status.data(), d_status, 4ull * n_vec, cudaMemcpyDeviceToHost, st);
+        std::vector<uint32_t> ntoks; std::vector<int> status; std::vector<BlobTok> all;
+        try { ntoks.resize(n_segs); status.resize(n_segs); all.resize(tok_total); } catch (...) { return fail(BMB200_ERR_BADALLOC, cudaSuccess); }
+        e = cudaMemcpyAsync(ntoks.data(), d_ntoks, 4ull * n_segs, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(status.data(), d_status, 4ull * n_segs, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(full.data(), d_full, (size_t)n_vec * n_blocks, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && tok_total) e = cudaMemcpyAsync(all.data(), d_toks, sizeof(BlobTok) * (size_t)tok_total, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
-        for (uint32_t v = 0; v < n_vec; ++v) if (status[v]) return fail(status[v], cudaSuccess);
+        for (uint32_t k = 0; k < n_segs; ++k) if (status[k]) return fail(status[k], cudaSuccess);
         try {
-            for (uint32_t v = 0; v < n_vec; ++v) {
-                if (ntoks[v] > tok_cap) return fail(BMB200_ERR_RANGE, cudaSuccess);
-                toks[v].resize(ntoks[v]);
-                if (ntoks[v]) e = cudaMemcpyAsync(toks[v].data(), d_toks + (size_t)v * tok_cap, sizeof(BlobTok) * ntoks[v], cudaMemcpyDeviceToHost, st);
-                if (e != cudaSuccess) break;
+            for (uint32_t v = 0; v < n_vec; ++v) toks[v].clear();
+            for (uint32_t k = 0; k < n_segs; ++k) {                       // segments are in stream order per vector: concatenate
+                if (ntoks[k] > seg_cap[k]) return fail(BMB200_ERR_RANGE, cudaSuccess);
+                std::vector<BlobTok>& tv = toks[segs[k].vec];
+                tv.insert(tv.end(), all.begin() + segs[k].tok_base, all.begin() + segs[k].tok_base + ntoks[k]);
             }
         } catch (...) { return fail(BMB200_ERR_BADALLOC, cudaSuccess); }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
+        n_status = n_segs;
     }
     tr.mark("token table D2H");
     // ---- arena layout: per column in vector order; the tokens of one vector are already in block order
@@ -602,6 +625,8 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
             }
             bb[nb + 1] = bb[nb] + nbit; gb[nb + 1] = gb[nb] + ngap;
         }
+        // every record must have found its column: block indexes that go backwards (a bookmark chain that lies) are a format error
+        for (uint32_t v = 0; v < n_vec; ++v) if (cur[v] != toks[v].size()) return fail(BMB200_ERR_BADARG, cudaSuccess);
     } catch (...) { return fail(BMB200_ERR_BADALLOC, cudaSuccess); }
     const uint64_t n_bit = bb[n_blocks], n_gap = gb[n_blocks];
     tr.mark("arena layout (host)");
@@ -630,9 +655,9 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
         uint32_t grid = (uint32_t)std::min<size_t>(erecs.size(), (size_t)ent_grid_max);
         SetView sv{n_vec, n_blocks, s->v.desc, s->v.bit_base, s->v.gap_base, s->v.bit_pool, s->v.gap_pool};
         blob_entropy_kernel<<<grid, kEntThreads, 0, st>>>(d_stg, d_boff, d_bsize, d_erecs, (uint32_t)erecs.size(), sv, (uint32_t*)s->v.bit_pool,
-                                                          (uint16_t*)s->v.gap_pool, d_status + n_vec, d_scratch);
+                                                          (uint16_t*)s->v.gap_pool, d_status + n_status, d_scratch);
         if ((rc = after_launch(ctx))) return fail(rc, cudaGetLastError());
-        e = cudaMemcpyAsync(&ent_status, d_status + n_vec, 4, cudaMemcpyDeviceToHost, st);
+        e = cudaMemcpyAsync(&ent_status, d_status + n_status, 4, cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
     }
     e = cudaStreamSynchronize(st);      // recs / desc staging vectors go out of scope

@@ -21,7 +21,7 @@
 using namespace bmb200;
 
 extern "C" int blob_host_check(const uint8_t* blob, uint64_t size, uint32_t n_blocks, uint8_t* kind, uint8_t* decoded,
-                               uint32_t* gap_words, uint32_t* blocks, uint16_t* gaps, uint32_t* n_entropy_tokens)
+                               uint32_t* gap_words, uint32_t* blocks, uint16_t* gaps, uint32_t* n_entropy_tokens, uint32_t* n_segments)
 {
     std::vector<uint8_t> stg(size + 64, 0);
     memcpy(stg.data(), blob, size);
@@ -30,12 +30,21 @@ extern "C" int blob_host_check(const uint8_t* blob, uint64_t size, uint32_t n_bl
     EntCtx c; c.t.lane = 0; c.t.nl = 1; c.bm = bm.data();
     c.la = reinterpret_cast<uint16_t*>(scratch.data()); c.lb = c.la + kEntListCap; c.lc = c.lb + kEntListCap;
     c.wf = reinterpret_cast<uint32_t*>(c.lc + kEntListCap);
+    // pass 1 the way bmb200_set_upload_blobs runs it: cut the BLOB at its bookmarks, walk every segment on its own, concatenate
+    std::vector<EntSeg> segs;
+    int rc = ent_find_segments(blob, size, 0u, 0u, segs);
+    if (rc) return rc;
     const uint32_t cap = n_blocks + n_blocks / 256u + 2u;
-    std::vector<BlobTok> toks(cap);
+    std::vector<BlobTok> toks(cap), seg_toks(cap);
     std::vector<uint8_t> full(n_blocks, 0);
     EntWalkOut o; o.toks = toks.data(); o.cap = cap; o.n = 0; o.full = full.data(); o.full_stride = 1;
-    int rc = ent_walk_vector(c, stg.data(), 0, size, n_blocks, o);
-    if (rc) return rc;
+    for (const EntSeg& sg : segs) {
+        EntWalkOut so; so.toks = seg_toks.data(); so.cap = cap; so.n = 0; so.full = full.data(); so.full_stride = 1;
+        rc = ent_walk_segment(c, stg.data(), sg, n_blocks, so);
+        if (rc) return rc;
+        for (uint32_t k = 0; k < so.n; ++k) { if (o.n >= cap) return BMB200_ERR_RANGE; toks[o.n++] = seg_toks[k]; }
+    }
+    if (n_segments) *n_segments = (uint32_t)segs.size();
     memset(kind, 0, n_blocks); memset(decoded, 0, n_blocks); memset(gap_words, 0, 4ull * n_blocks);
     for (uint32_t nb = 0; nb < n_blocks; ++nb) if (full[nb]) kind[nb] = BMB200_BLK_FULL;
     // single-vector arena: column nb holds at most one block (same descriptor encoding as bmb200_set_upload_blobs)

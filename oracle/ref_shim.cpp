@@ -486,6 +486,23 @@ int ref_serialize(const bmb200_packed_set* s, uint32_t v, int level, unsigned ch
     } catch (...) { return 1; }
 }
 
+/* same with serializer::set_bookmarks(true, interval) (src/bmserial.h:1487): skip marks every `interval` blocks */
+int ref_serialize_bookmarks(const bmb200_packed_set* s, uint32_t v, int level, uint32_t interval, unsigned char* out, uint64_t cap, uint64_t* size)
+{
+    try {
+        bvect bv; build_bvector(s, v, 0, s->n_blocks, bv);
+        bm::serializer<bvect> ser;
+        ser.set_compression_level((unsigned)level);
+        ser.set_bookmarks(true, interval);
+        bm::serializer<bvect>::buffer buf;
+        ser.serialize(bv, buf);
+        if (buf.size() > cap) return 3;
+        std::memcpy(out, buf.data(), buf.size());
+        *size = buf.size();
+        return 0;
+    } catch (...) { return 1; }
+}
+
 int ref_deserialize(const unsigned char* blob, uint32_t n_cols, uint8_t* kind, uint32_t* popcnt, uint32_t* blocks, uint16_t* gaps)
 {
     try {

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Deserialize-to-device row: bmb200_set_upload_blobs vs bm::deserialize on the same BLOBs.
-  python scripts/bench_blob.py [n_vec] [n_blocks] [level]   -> one JSON line
+  python scripts/bench_blob.py [n_vec] [n_blocks] [level] [bookmark_interval]   -> one JSON line
 The set is the C3 recipe scaled down (Zipf densities, optimize()d); every vector is serialized by the reference's own
 bm::serializer<> at the given compression level (default 2 = explicit-length encodings, host token walk; 6 = the serializer's
 default: gamma / interpolative encodings, token walk + entropy decode on the GPU).  GPU time = token walk + H2D of the BLOB
@@ -23,12 +23,13 @@ def main():
     nv = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     nbk = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     level = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    bmi = int(sys.argv[4]) if len(sys.argv) > 4 else 0          # > 0: serializer::set_bookmarks(true, bmi) -- the walk of a vector splits there
     ctx = bm.Context(0)
     dens = np.array([0.5 / (k + 1) for k in range(nv)])
     seed = np.arange(1000, 1000 + nv, dtype=np.uint64)
     dset = bm.DeviceSet.synth(ctx, nv, nbk, dens, seed, True)
     ps = dset.download()
-    blobs = [orclib.ref_serialize(ps, v, level) for v in range(nv)]
+    blobs = [orclib.ref_serialize_bookmarks(ps, v, level, bmi) if bmi else orclib.ref_serialize(ps, v, level) for v in range(nv)]
     blob_bytes = int(sum(b.size for b in blobs))
     t0 = time.perf_counter()
     for b in blobs:
@@ -50,7 +51,7 @@ def main():
     g = list(range(nv))
     r1 = bm.aggregate(ctx, d2, bm.OP_AND_SUB, [0, 1], g[2:], bm.F_OPT_COMPRESS); r2 = bm.aggregate(ctx, dset, bm.OP_AND_SUB, [0, 1], g[2:], bm.F_OPT_COMPRESS)
     agg_same = r1.total() == r2.total()
-    print(json.dumps({"bench": "blob", "level": level, "n_vec": nv, "n_blocks": nbk, "stored_bytes": int(ps.stored_bytes()), "blob_bytes": blob_bytes,
+    print(json.dumps({"bench": "blob", "level": level, "bookmark_interval": bmi, "n_vec": nv, "n_blocks": nbk, "stored_bytes": int(ps.stored_bytes()), "blob_bytes": blob_bytes,
                       "upload_blobs_ms": t_gpu * 1e3, "upload_blobs_GBps_of_blob": blob_bytes / t_gpu / 1e9,
                       "upload_blobs_GBps_of_blocks": ps.stored_bytes() / t_gpu / 1e9, "upload_raw_packed_ms": t_raw * 1e3,
                       "ref_deserialize_1core_ms": t_ref * 1e3, "ref_deserialize_GBps_of_blocks": ps.stored_bytes() / t_ref / 1e9,

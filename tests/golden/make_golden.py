@@ -80,7 +80,8 @@ def blob_fixture(name, vecs=None, levels=(0, 1, 2)):
     d = dict(n_vec=ps.n_vec, n_blocks=ps.n_blocks, levels=np.array(levels))
     for level in levels:
         for v in range(ps.n_vec):
-            blob = orclib.ref_serialize(ps, v, level)
+            # pseudo-levels 100 + l: level l written with serializer::set_bookmarks(true, 4) (skip marks every 4 blocks)
+            blob = orclib.ref_serialize_bookmarks(ps, v, level - 100, 4) if level >= 100 else orclib.ref_serialize(ps, v, level)
             kind, pop, blk, gaps = orclib.ref_deserialize(blob, ps.n_blocks)
             d[f"l{level}_v{v}_blob"] = blob; d[f"l{level}_v{v}_kind"] = kind
             glen = np.where(kind == bm.BLK_GAP, (gaps[:, 0] >> 3) + 1, 0)
@@ -96,7 +97,7 @@ if __name__ == "__main__":
     if "blob" in sys.argv[1:] or len(sys.argv) == 1:
         blob_fixture("blobs")
         import test_oracle_vs_reference as tor
-        blob_fixture("blobs_entropy", tor.entropy_inputs(), (3, 4, 5, 6))
+        blob_fixture("blobs_entropy", tor.entropy_inputs(), (3, 4, 5, 106, 6))
         if "blob" in sys.argv[1:]:
             sys.exit(0)
     if "scan" in sys.argv[1:] or len(sys.argv) == 1:

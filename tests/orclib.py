@@ -277,6 +277,16 @@ def ref_serialize(ps, v, level):
     return out[:size.value].copy()
 
 
+def ref_serialize_bookmarks(ps, v, level, interval):
+    """bm::serializer<> with set_bookmarks(true, interval): BLOB of vector v at the given compression level"""
+    cap = 64 + ps.n_blocks * (BLOCK_WORDS * 4 + 64)
+    out = np.zeros(cap, np.uint8); size = C.c_uint64(0)
+    c = _pc(ps)
+    rc = ref().ref_serialize_bookmarks(C.byref(c), C.c_uint32(v), C.c_int(level), C.c_uint32(interval), ptr(out), C.c_uint64(cap), C.byref(size))
+    assert rc == 0, f"ref_serialize_bookmarks rc={rc}"
+    return out[:size.value].copy()
+
+
 def ref_deserialize(blob, n_cols):
     """bm::deserialize -> kind, popcnt, blocks[n_cols][2048], gaps[n_cols][1280]"""
     b = np.ascontiguousarray(blob, dtype=np.uint8)
@@ -316,9 +326,10 @@ def blob_host_check(blob, n_cols):
     b = np.ascontiguousarray(blob, dtype=np.uint8)
     kind = np.zeros(n_cols, np.uint8); dec = np.zeros(n_cols, np.uint8); gw = np.zeros(n_cols, np.uint32)
     blocks = np.zeros((n_cols, BLOCK_WORDS), np.uint32); gaps = np.zeros((n_cols, GAP_MAX_WORDS), np.uint16)
-    n_ent = C.c_uint32(0)
+    n_ent = C.c_uint32(0); n_seg = C.c_uint32(0)
     rc = blobhost().blob_host_check(ptr(b), C.c_uint64(b.size), C.c_uint32(n_cols), ptr(kind), ptr(dec), ptr(gw), ptr(blocks), ptr(gaps),
-                                    C.byref(n_ent))
+                                    C.byref(n_ent), C.byref(n_seg))
+    blob_host_check.last_segments = n_seg.value
     return rc, kind, dec, gw, blocks, gaps, n_ent.value
 
 

@@ -316,6 +316,29 @@ def test_deserialize_oracle_matches_reference():
 
 
 @needs_ref
+def test_bookmarked_blobs_oracle_and_device_decoder_host_build():
+    """BLOBs written with serializer::set_bookmarks(true, interval): the oracle skips the marks; the product's walker cuts the stream
+    at them (ent_find_segments) and walks every segment on its own -- both == bm::deserialize."""
+    vecs = gen.entropy_vectors(np.random.default_rng(5), n_vec=8, n_blocks=40)
+    ps = bm.PackedSet.pack(vecs)
+    max_segments = 0
+    for level in (2, 4, 6):
+        for interval in (4, 16):
+            for v in range(ps.n_vec):
+                blob = orclib.ref_serialize_bookmarks(ps, v, level, interval)
+                rkind, rpop, rblk, rgap = orclib.ref_deserialize(blob, ps.n_blocks)
+                assert np.array_equal(rblk, np.stack([vecs[v].block_words(c) for c in range(ps.n_blocks)]))
+                rc, kind, blk, gaps = orclib.oracle_deserialize(blob, ps.n_blocks)
+                assert rc == 0 and np.array_equal(blk, rblk) and np.array_equal(kind, rkind) and np.array_equal(gaps, rgap)
+                rc, kind, dec, gw, blk, gaps, n = orclib.blob_host_check(blob, ps.n_blocks)
+                assert rc == 0 and np.array_equal(kind, rkind), f"level {level} interval {interval} vector {v}"
+                max_segments = max(max_segments, orclib.blob_host_check.last_segments)
+                for c in np.flatnonzero(dec):
+                    assert np.array_equal(blk[c], rblk[c]) if kind[c] == bm.BLK_BIT else np.array_equal(gaps[c], rgap[c])
+    assert max_segments >= 8
+
+
+@needs_ref
 def test_device_decoder_host_build_matches_reference():
     """The product's BLOB walker + entropy decoder (bitmagic_b200/csrc/blob_entropy.cuh), built for the host as a checker
     (oracle/blob_host_check.cpp: same functions, a team of one lane instead of a warp), == bm::deserialize: block kinds for every
