@@ -410,7 +410,9 @@ BME_HD uint32_t ent_count_runs(const EntCtx& c)
         const uint32_t x = c.bm[w], nxt = (w + 1u < kEntWords) ? (c.bm[w + 1u] & 1u) : (x >> 31);
         cnt += bme_popc(x ^ ((x >> 1) | (nxt << 31)));
     }
-    return bme_sum(cnt) + 1u;
+    const uint32_t runs = bme_sum(cnt) + 1u;
+    bme_sync();                                  // the bitmap may be rewritten right after (next token)
+    return runs;
 }
 // bit_block_to_gap (src/bmfunc.h:5540): out[0] = header, out[1..len] run ends; len = runs (computed by ent_count_runs)
 BME_HD void ent_write_gap(const EntCtx& c, uint16_t* out, uint32_t len)
