@@ -936,14 +936,25 @@ __device__ __forceinline__ EntCtx ent_make_ctx(uint32_t* s_bm, uint8_t* scratch_
 
 // pass 1: one warp per segment (a whole vector, or one bookmark interval of it).  toks: token table, segment i writes from
 // segs[i].tok_base (at most tok_cap[i] records); n_toks, status: [n_segs]; full: [n_blocks][n_vec] (zeroed by the caller)
+// Work items are pulled from a counter in the order the host sorted them (longest stream first): the items are sequential decodes
+// of very different lengths, and the launch ends with its slowest warp.
+__device__ __forceinline__ uint32_t ent_next_item(uint32_t* counter)
+{
+    uint32_t i = 0;
+    if ((threadIdx.x & 31u) == 0u) i = atomicAdd(counter, 1u);
+    return __shfl_sync(0xffffffffu, i, 0);
+}
+
 __global__ void __launch_bounds__(kEntThreads) blob_walk_kernel(const uint8_t* __restrict__ stg, const EntSeg* __restrict__ segs, const uint32_t* __restrict__ tok_cap,
+                                                                const uint32_t* __restrict__ order, uint32_t* __restrict__ counter,
                                                                 uint32_t n_segs, uint32_t n_vec, uint32_t n_blocks, BlobTok* __restrict__ toks,
                                                                 uint32_t* __restrict__ n_toks, int* __restrict__ status, uint8_t* __restrict__ full,
                                                                 uint8_t* __restrict__ scratch)
 {
     __shared__ __align__(16) uint32_t s_bm[kEntWords];
     const EntCtx c = ent_make_ctx(s_bm, scratch, blockIdx.x);
-    for (uint32_t i = blockIdx.x; i < n_segs; i += gridDim.x) {
+    for (uint32_t q = ent_next_item(counter); q < n_segs; q = ent_next_item(counter)) {
+        const uint32_t i = order[q];
         const EntSeg sg = segs[i];
         EntWalkOut o; o.toks = toks + sg.tok_base; o.cap = tok_cap[i]; o.n = 0; o.full = full + sg.vec; o.full_stride = n_vec;
         const int rc = ent_walk_segment(c, stg, sg, n_blocks, o);
@@ -958,13 +969,13 @@ __global__ void __launch_bounds__(kEntThreads) blob_walk_kernel(const uint8_t* _
 // descriptor table.
 __global__ void __launch_bounds__(kEntThreads) blob_entropy_kernel(const uint8_t* __restrict__ stg, const uint64_t* __restrict__ blob_off,
                                                                    const uint64_t* __restrict__ blob_size, const BlobRec* __restrict__ recs,
-                                                                   uint32_t n_recs, const SetView set, uint32_t* __restrict__ bit_pool,
+                                                                   uint32_t n_recs, uint32_t* __restrict__ counter, const SetView set, uint32_t* __restrict__ bit_pool,
                                                                    uint16_t* __restrict__ gap_pool, int* __restrict__ status, uint8_t* __restrict__ scratch)
 {
     __shared__ __align__(16) uint32_t s_bm[kEntWords];
     const EntCtx c = ent_make_ctx(s_bm, scratch, blockIdx.x);
     const EntSetView sv{set.n_vec, set.n_blocks, set.desc, set.bit_base, set.gap_base};
-    for (uint32_t ri = blockIdx.x; ri < n_recs; ri += gridDim.x) {
+    for (uint32_t ri = ent_next_item(counter); ri < n_recs; ri = ent_next_item(counter)) {      // recs arrive sorted, longest payload first
         const BlobRec r = recs[ri];
         const uint32_t v = r.aux;
         const int rc = ent_emit(c, stg, r.src, blob_off[v] + blob_size[v], r.type & 0xffu, v, r.dst, r.kind, r.aux2, sv, bit_pool, gap_pool);

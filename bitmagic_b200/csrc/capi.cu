@@ -12,6 +12,7 @@
 #include "aux_kernels.cuh"
 #include "scan_kernel.cuh"
 #include "shift_kernel.cuh"
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -554,21 +555,27 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
         if (e == cudaSuccess) e = tmp_alloc(2, (void**)&d_bsize, 8ull * n_vec);
         if (e == cudaSuccess) e = tmp_alloc(3, (void**)&d_toks, sizeof(BlobTok) * (size_t)tok_total);
         if (e == cudaSuccess) e = tmp_alloc(4, (void**)&d_ntoks, 4ull * n_segs);
-        if (e == cudaSuccess) e = tmp_alloc(5, (void**)&d_status, 4ull * (n_segs + 1));
+        if (e == cudaSuccess) e = tmp_alloc(5, (void**)&d_status, 4ull * (n_segs + 3));
         if (e == cudaSuccess) e = tmp_alloc(6, (void**)&d_full, (size_t)n_vec * n_blocks);
         if (e == cudaSuccess) e = tmp_alloc(7, (void**)&d_scratch, (size_t)ent_grid_max * kEntScratchBytes);
         if (e == cudaSuccess) e = tmp_alloc(10, (void**)&d_segs, sizeof(EntSeg) * (size_t)n_segs);
-        if (e == cudaSuccess) e = tmp_alloc(11, (void**)&d_segcap, 4ull * n_segs);
+        if (e == cudaSuccess) e = tmp_alloc(11, (void**)&d_segcap, 8ull * n_segs);            // capacities, then the processing order
         if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? BMB200_ERR_BADALLOC : BMB200_ERR_CUDA, e);
         e = cudaMemcpyAsync(d_boff, stg_off.data(), 8ull * n_vec, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_bsize, blob_size.data(), 8ull * n_vec, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_segs, segs.data(), sizeof(EntSeg) * (size_t)n_segs, cudaMemcpyHostToDevice, st);
+        std::vector<uint32_t> order(n_segs);                              // longest stream first (the launch ends with its slowest warp)
+        for (uint32_t k = 0; k < n_segs; ++k) order[k] = k;
+        auto seg_len = [&](uint32_t k) { return (segs[k].bounded ? segs[k].end : segs[k].blob_size) - segs[k].start; };
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return seg_len(a) > seg_len(b); });
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_segcap, seg_cap.data(), 4ull * n_segs, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_segcap + n_segs, order.data(), 4ull * n_segs, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(d_full, 0, (size_t)n_vec * n_blocks, st);
-        if (e == cudaSuccess) e = cudaMemsetAsync(d_status, 0, 4ull * (n_segs + 1), st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_status, 0, 4ull * (n_segs + 3), st);
         if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
         tr.mark("walk buffers");
-        blob_walk_kernel<<<grid, kEntThreads, 0, st>>>(d_stg, d_segs, d_segcap, n_segs, n_vec, n_blocks, d_toks, d_ntoks, d_status, d_full, d_scratch);
+        blob_walk_kernel<<<grid, kEntThreads, 0, st>>>(d_stg, d_segs, d_segcap, d_segcap + n_segs, (uint32_t*)d_status + n_segs + 1, n_segs, n_vec, n_blocks, d_toks,
+                                                       d_ntoks, d_status, d_full, d_scratch);
         int rc = after_launch(ctx);
         if (rc) return fail(rc, cudaGetLastError());
         tr.mark("blob_walk_kernel");
@@ -604,6 +611,9 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
                 while (cur[v] < toks[v].size() && toks[v][cur[v]].type == (kTokEntropy | 68u) && toks[v][cur[v]].nb <= nb) {
                     const BlobTok& t = toks[v][cur[v]++];
                     BlobRec r{}; r.src = stg_off[v] + t.off; r.type = t.type; r.aux = v; r.dst = t.aux;
+                    size_t k = cur[v]; while (k < toks[v].size() && toks[v][k].off == t.off) ++k;      // its member blocks share its offset
+                    const uint64_t nxt = k < toks[v].size() ? toks[v][k].off : blob_size[v];
+                    r.aux2 = (uint32_t)std::min<uint64_t>(nxt > t.off ? nxt - t.off : 0, 0x3fffffffu) << 2;
                     erecs.push_back(r);
                 }
                 if (cur[v] < toks[v].size() && toks[v][cur[v]].nb == nb) {
@@ -619,6 +629,10 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
                         d = BMB200_BLK_GAP | ((uint32_t)ngap << 2) | (pad ? BMB200_DESC_GAP_PAD : 0u) | BMB200_DESC_GAP_FLAT;
                         r.dst = gb[nb] + ngap; r.aux2 = pad | (t.first << 1); ngap += units;
                     } else return fail(BMB200_ERR_BADARG, cudaSuccess);
+                    if (entropy) {      // payload length (to the next record of the vector, or the end of the BLOB): the work estimate pass 2 is sorted by
+                        const uint64_t nxt = cur[v] < toks[v].size() ? toks[v][cur[v]].off : blob_size[v];
+                        r.aux2 |= (uint32_t)std::min<uint64_t>(nxt > t.off ? nxt - t.off : 0, 0x3fffffffu) << 2;
+                    }
                     if (!member) (entropy ? erecs : recs).push_back(r);
                 }
                 desc[(size_t)nb * n_vec + v] = d;
@@ -629,6 +643,7 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
         for (uint32_t v = 0; v < n_vec; ++v) if (cur[v] != toks[v].size()) return fail(BMB200_ERR_BADARG, cudaSuccess);
     } catch (...) { return fail(BMB200_ERR_BADALLOC, cudaSuccess); }
     const uint64_t n_bit = bb[n_blocks], n_gap = gb[n_blocks];
+    std::stable_sort(erecs.begin(), erecs.end(), [](const BlobRec& a, const BlobRec& b) { return (a.aux2 >> 2) > (b.aux2 >> 2); });
     tr.mark("arena layout (host)");
     int rc = set_alloc(ctx, n_vec, n_blocks, n_bit, n_gap, &s);
     if (rc) { s = nullptr; return fail(rc, cudaSuccess); }
@@ -654,7 +669,7 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
         // ---- pass 2: every entropy-coded token of every vector in parallel (their offsets are known now), one warp per token
         uint32_t grid = (uint32_t)std::min<size_t>(erecs.size(), (size_t)ent_grid_max);
         SetView sv{n_vec, n_blocks, s->v.desc, s->v.bit_base, s->v.gap_base, s->v.bit_pool, s->v.gap_pool};
-        blob_entropy_kernel<<<grid, kEntThreads, 0, st>>>(d_stg, d_boff, d_bsize, d_erecs, (uint32_t)erecs.size(), sv, (uint32_t*)s->v.bit_pool,
+        blob_entropy_kernel<<<grid, kEntThreads, 0, st>>>(d_stg, d_boff, d_bsize, d_erecs, (uint32_t)erecs.size(), (uint32_t*)d_status + n_status + 2, sv, (uint32_t*)s->v.bit_pool,
                                                           (uint16_t*)s->v.gap_pool, d_status + n_status, d_scratch);
         if ((rc = after_launch(ctx))) return fail(rc, cudaGetLastError());
         e = cudaMemcpyAsync(&ent_status, d_status + n_status, 4, cudaMemcpyDeviceToHost, st);
