@@ -970,7 +970,8 @@ __global__ void __launch_bounds__(kEntThreads) blob_walk_kernel(const uint8_t* _
 __global__ void __launch_bounds__(kEntThreads) blob_entropy_kernel(const uint8_t* __restrict__ stg, const uint64_t* __restrict__ blob_off,
                                                                    const uint64_t* __restrict__ blob_size, const BlobRec* __restrict__ recs,
                                                                    uint32_t n_recs, uint32_t* __restrict__ counter, const SetView set, uint32_t* __restrict__ bit_pool,
-                                                                   uint16_t* __restrict__ gap_pool, int* __restrict__ status, uint8_t* __restrict__ scratch)
+                                                                   uint16_t* __restrict__ gap_pool, int* __restrict__ status, uint8_t* __restrict__ scratch,
+                                                                   unsigned long long* __restrict__ dur /* BMB200_TRACE: clocks per rec, or null */)
 {
     __shared__ __align__(16) uint32_t s_bm[kEntWords];
     const EntCtx c = ent_make_ctx(s_bm, scratch, blockIdx.x);
@@ -978,8 +979,10 @@ __global__ void __launch_bounds__(kEntThreads) blob_entropy_kernel(const uint8_t
     for (uint32_t ri = ent_next_item(counter); ri < n_recs; ri = ent_next_item(counter)) {      // recs arrive sorted, longest payload first
         const BlobRec r = recs[ri];
         const uint32_t v = r.aux;
+        const long long t0 = dur ? clock64() : 0;
         const int rc = ent_emit(c, stg, r.src, blob_off[v] + blob_size[v], r.type & 0xffu, v, r.dst, r.kind, r.aux2, sv, bit_pool, gap_pool);
         if (rc && c.t.lane == 0u) atomicCAS(status, 0, rc);
+        if (dur && c.t.lane == 0u) dur[ri] = (unsigned long long)(clock64() - t0);
         __syncwarp();
     }
 }

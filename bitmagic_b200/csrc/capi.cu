@@ -40,8 +40,8 @@ struct bmb200_ctx {
     size_t cap_desc = 0, cap_base = 0, cap_bit = 0, cap_gap = 0;
     uint8_t* h_stage = nullptr;             // pinned staging for serialized BLOBs (bmb200_set_upload_blobs), grown on demand
     size_t h_stage_cap = 0;
-    void* d_tmp[12] = {};                   // device temporaries of bmb200_set_upload_blobs (staging, token tables, decode scratch): kept
-    size_t d_tmp_cap[12] = {};              //   between calls, grown on demand -- cudaMalloc / cudaFree of a few hundred MB costs tens of ms each
+    void* d_tmp[13] = {};                   // device temporaries of bmb200_set_upload_blobs (staging, token tables, decode scratch): kept
+    size_t d_tmp_cap[13] = {};              //   between calls, grown on demand -- cudaMalloc / cudaFree of a few hundred MB costs tens of ms each
     int gap_mode = 0;                       // 0 = stream sorted GAP lists through the smem ring, 1 = always gather
     bool attr_set = false;
 };
@@ -669,9 +669,23 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
         // ---- pass 2: every entropy-coded token of every vector in parallel (their offsets are known now), one warp per token
         uint32_t grid = (uint32_t)std::min<size_t>(erecs.size(), (size_t)ent_grid_max);
         SetView sv{n_vec, n_blocks, s->v.desc, s->v.bit_base, s->v.gap_base, s->v.bit_pool, s->v.gap_pool};
+        unsigned long long* d_dur = nullptr;
+        if (tr.on) { e = tmp_alloc(12, (void**)&d_dur, 8ull * erecs.size()); if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e); }
         blob_entropy_kernel<<<grid, kEntThreads, 0, st>>>(d_stg, d_boff, d_bsize, d_erecs, (uint32_t)erecs.size(), (uint32_t*)d_status + n_status + 2, sv, (uint32_t*)s->v.bit_pool,
-                                                          (uint16_t*)s->v.gap_pool, d_status + n_status, d_scratch);
+                                                          (uint16_t*)s->v.gap_pool, d_status + n_status, d_scratch, d_dur);
         if ((rc = after_launch(ctx))) return fail(rc, cudaGetLastError());
+        if (tr.on) {                                   // the five slowest work items of pass 2
+            std::vector<unsigned long long> dur(erecs.size());
+            if (cudaMemcpyAsync(dur.data(), d_dur, 8ull * erecs.size(), cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess) {
+                std::vector<uint32_t> idx(erecs.size()); for (uint32_t k = 0; k < idx.size(); ++k) idx[k] = k;
+                std::partial_sort(idx.begin(), idx.begin() + std::min<size_t>(5, idx.size()), idx.end(), [&](uint32_t a, uint32_t b) { return dur[a] > dur[b]; });
+                unsigned long long sum = 0; for (auto d : dur) sum += d;
+                fprintf(stderr, "[bmb200] set_upload_blobs: pass 2: %zu items, %.1f Mclk in total\n", erecs.size(), sum / 1e6);
+                for (size_t k = 0; k < std::min<size_t>(5, idx.size()); ++k)
+                    fprintf(stderr, "[bmb200]   item %u: token %u, vector %u, payload %u B, kind %u, %.2f Mclk\n", idx[k], erecs[idx[k]].type & 0xffu, erecs[idx[k]].aux,
+                            erecs[idx[k]].aux2 >> 2, erecs[idx[k]].kind, dur[idx[k]] / 1e6);
+            }
+        }
         e = cudaMemcpyAsync(&ent_status, d_status + n_status, 4, cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
     }
