@@ -380,6 +380,60 @@ template<class BV> void bit_sub(context& c, BV& t, const BV& a, const BV& b)
 template<class BV> void bit_xor(context& c, BV& t, const BV& a, const BV& b, typename BV::optmode opt = BV::opt_none)
 { aggregator<BV> g(c); g.set_optimization(opt); const BV* s[2] = {&a, &b}; g.combine_xor(t, s, 2); }
 
+/// Operands that arrive as serialization BLOBs (bm::serializer<BV> output, any compression level incl. the default 6): the BLOBs
+/// are decoded ON THE GPU (bmb200_set_upload_blobs) and aggregated there -- the bvectors are never materialised on the host.
+/// Reference equivalent: bm::deserialize(bv_k, buf_k) for every operand (src/bmserial.h:4152) followed by
+/// aggregator::combine_or / combine_and_sub (src/bmaggregator.h:1101,1162); bm::operation_deserializer<BV> (src/bmserial.h:1070)
+/// is the reference's own one-BLOB-at-a-time form of "operate on a BLOB without keeping the vector".
+/// `size` = size() of the serialized vectors (the result is resized to it, like resize_target does with max(source sizes)).
+template<class BV>
+class blob_aggregator
+{
+public:
+    typedef typename BV::size_type size_type;
+    blob_aggregator(context& c, size_type size) : ctx_(c), size_(size), n_blocks_((uint32_t)((uint64_t(size) + 65535ull) >> 16)) {}
+    void set_optimization(typename BV::optmode opt = BV::opt_compress) { opt_mode_ = opt; }
+    /// attach a BLOB (not owned) to group 0 (OR / AND sources) or group 1 (SUB sources), like aggregator::add(bv, group)
+    size_t add(const unsigned char* buf, size_t buf_size, unsigned group = 0) { bmb200_blob b{buf, (uint64_t)buf_size}; grp_[group ? 1 : 0].push_back(b); return grp_[group ? 1 : 0].size(); }
+    void reset() { grp_[0].clear(); grp_[1].clear(); }
+    void combine_or(BV& target) { run(target, BMB200_OP_OR, false); }
+    void combine_and(BV& target) { run(target, BMB200_OP_AND_SUB, true); }
+    bool combine_and_sub(BV& target) { return run(target, BMB200_OP_AND_SUB, true); }
+private:
+    bool run(BV& target, int op, bool use_sub)
+    {
+        const size_t n0 = grp_[0].size(), n1 = use_sub ? grp_[1].size() : 0;
+        if (!n0) { target.clear(true); return false; }
+        std::vector<bmb200_blob> all(grp_[0]); if (n1) all.insert(all.end(), grp_[1].begin(), grp_[1].end());
+        bmb200_set* set = nullptr;
+        check(bmb200_set_upload_blobs(ctx_.get(), (uint32_t)all.size(), n_blocks_, all.data(), &set), "bmb200_set_upload_blobs");
+        std::vector<uint32_t> g0(n0), g1(n1);
+        for (size_t k = 0; k < n0; ++k) g0[k] = (uint32_t)k;
+        for (size_t k = 0; k < n1; ++k) g1[k] = (uint32_t)(n0 + k);
+        const bool compress = (op == BMB200_OP_AND_SUB) || opt_mode_ != BV::opt_none;      // combine_and_sub always stores through opt_compress (:1209)
+        bmb200_agg_args a{op, compress ? BMB200_F_OPT_COMPRESS : BMB200_F_OPT_NONE, g0.data(), (uint32_t)n0, n1 ? g1.data() : nullptr, (uint32_t)n1, 0, 0};
+        bmb200_result* res = nullptr;
+        int rc = bmb200_aggregate(ctx_.get(), set, &a, &res);
+        uint64_t total = 0; int any = 0, rc2 = 0;
+        std::vector<uint8_t> kind(n_blocks_); std::vector<uint64_t> off(n_blocks_);
+        std::vector<uint32_t> bits; std::vector<uint16_t> gaps;
+        if (!rc) rc = bmb200_result_total(res, &total, &any);
+        if (!rc) { uint64_t nb = 0, ng = 0; rc = bmb200_result_sizes(res, &nb, &ng);
+                   if (!rc) { bits.resize(nb * BMB200_BLOCK_WORDS); gaps.resize(ng);
+                              rc = bmb200_result_fetch(res, kind.data(), off.data(), bits.data(), gaps.data()); } }
+        if (res) rc2 = bmb200_result_free(res);
+        bmb200_set_free(set);
+        check(rc, "bmb200_aggregate"); check(rc2, "bmb200_result_free");
+        detail::store_result(target, size_, n_blocks_, kind.data(), off.data(), bits.data(), gaps.data());
+        return any != 0;
+    }
+    context& ctx_;
+    size_type size_;
+    uint32_t n_blocks_;
+    typename BV::optmode opt_mode_ = BV::opt_none;
+    std::vector<bmb200_blob> grp_[2];
+};
+
 /// bvector::bit_or_and (src/bm.h:1787,6283): target |= a & b -- two launches (AND, then OR with the target)
 template<class BV> void bit_or_and(context& c, BV& t, const BV& a, const BV& b, typename BV::optmode opt = BV::opt_none)
 {

@@ -14,6 +14,7 @@
 
 #include "bm.h"
 #include "bmaggregator.h"
+#include "bmserial.h"
 #include "bmb200_aggregator.hpp"
 #include "bmb200_scanner.hpp"
 
@@ -190,6 +191,34 @@ int main()
         for (size_t k = 0; k < vals.size(); ++k) {
             bvect a; ref_sc.find_eq(sv, (unsigned)vals[k], a);
             CHECK(a.compare(outs[k]) == 0 && a.count() == cnts[k], "scanner batch eq k=%zu nullable=%d", k, nullable);
+        }
+    }
+    // ---- operands as serialization BLOBs (bm::serializer<>, every compression level, with and without bookmarks): decoded on the
+    // GPU and aggregated there (bm::b200::blob_aggregator) == bm::deserialize + bm::aggregator on the host
+    for (unsigned level = 0; level <= 6; ++level) {
+        for (int bookmarks = 0; bookmarks < 2; ++bookmarks) {
+            if (bookmarks && level != 2 && level != 6) continue;
+            std::vector<bm::serializer<bvect>::buffer> bufs(all.size());
+            for (size_t k = 0; k < all.size(); ++k) {
+                bm::serializer<bvect> ser; ser.set_compression_level(level);
+                if (bookmarks) ser.set_bookmarks(true, 8);
+                ser.serialize(*all[k], bufs[k]);
+            }
+            bm::aggregator<bvect> ref; ref.set_optimization(bvect::opt_compress);
+            bm::b200::blob_aggregator<bvect> gpu(ctx, n_bits); gpu.set_optimization(bvect::opt_compress);
+            // the host side of the comparison goes through bm::deserialize, like an application holding BLOBs would
+            std::vector<std::unique_ptr<bvect>> back;
+            for (size_t k = 0; k < all.size(); ++k) { back.emplace_back(new bvect()); bm::deserialize(*back.back(), bufs[k].data()); }
+            std::vector<const bvect*> bp; for (auto& v : back) bp.push_back(v.get());
+            for (size_t k = 0; k < all.size(); ++k) gpu.add(bufs[k].data(), bufs[k].size(), k < 3 ? 0 : 1);
+            bvect t_ref, t_gpu;
+            bool f_ref = ref.combine_and_sub(t_ref, bp.data(), 3, bp.data() + 3, bp.size() - 3, false);
+            bool f_gpu = gpu.combine_and_sub(t_gpu);
+            CHECK(f_ref == f_gpu && t_ref.compare(t_gpu) == 0 && t_ref.count() == t_gpu.count(), "blob combine_and_sub level=%u bookmarks=%d", level, bookmarks);
+            gpu.reset();
+            for (size_t k = 0; k < all.size(); ++k) gpu.add(bufs[k].data(), bufs[k].size());
+            ref.combine_or(t_ref, bp.data(), bp.size()); gpu.combine_or(t_gpu);
+            CHECK(t_ref.compare(t_gpu) == 0 && t_ref.count() == t_gpu.count(), "blob combine_or level=%u bookmarks=%d", level, bookmarks);
         }
     }
     std::printf("%s: %d checks, %d failed\n", g_fail ? "FAILED" : "OK", g_checks, g_fail);
