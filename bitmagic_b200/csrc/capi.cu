@@ -468,6 +468,7 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
     std::vector<uint32_t> desc; std::vector<uint64_t> bb, gb, stg_off(n_vec), blob_size(n_vec);
     std::vector<BlobRec> recs, erecs;           // explicit-length tokens (blob_decode_kernel) / entropy-coded tokens (blob_entropy_kernel)
     bool device_walk = false;                   // some BLOB holds entropy-coded tokens: its stream can only be walked by decoding it
+    PhaseTrace tr("set_upload_blobs", ctx->stream);
     uint64_t stg_bytes = 0;
     try {
         full.assign((size_t)n_vec * n_blocks, 0);
@@ -484,7 +485,6 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
     } catch (...) { return BMB200_ERR_BADALLOC; }
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    PhaseTrace tr("set_upload_blobs", st);
     tr.mark(device_walk ? "host walk (gave up: entropy)" : "host token walk");
     // ---- the compressed bytes are all that crosses PCIe (plus descriptors and the token table): gathered into one pinned
     // buffer so the copy is a single DMA at link speed instead of one pageable copy per vector
