@@ -50,7 +50,15 @@ extern "C" int blob_host_check(const uint8_t* blob, uint64_t size, uint32_t n_bl
     // single-vector arena: column nb holds at most one block (same descriptor encoding as bmb200_set_upload_blobs)
     std::vector<uint32_t> desc(n_blocks, 0); std::vector<uint64_t> bb(n_blocks + 1, 0), gb(n_blocks + 1, 0);
     std::vector<const BlobTok*> at(n_blocks, nullptr);
-    for (uint32_t k = 0; k < o.n; ++k) { const BlobTok& t = toks[k]; if ((t.type & 0xffu) == 68u && (t.type & kTokEntropy)) continue; if (t.nb < n_blocks) at[t.nb] = &t; }
+    // like the layout loop of bmb200_set_upload_blobs: records must arrive in strictly increasing block order (a bookmark chain that
+    // lies about block indexes is a format error), super-block records aside
+    int64_t last_nb = -1;
+    for (uint32_t k = 0; k < o.n; ++k) {
+        const BlobTok& t = toks[k];
+        if ((t.type & 0xffu) == 68u && (t.type & kTokEntropy)) continue;
+        if ((int64_t)t.nb <= last_nb || t.nb >= n_blocks) return BMB200_ERR_BADARG;
+        last_nb = t.nb; at[t.nb] = &t;
+    }
     for (uint32_t nb = 0; nb < n_blocks; ++nb) {
         uint64_t nbit = 0, ngap = 0;
         if (const BlobTok* t = at[nb]) {
