@@ -144,3 +144,16 @@ def entropy_vectors(rng, n_vec=14, n_blocks=10):
                 v.set_gap(nb, bits_to_gap(bits_to_words(bits)))
         vecs.append(v)
     return vecs
+
+
+def c1_vectors():
+    """BASELINE.json configs[0] (SURVEY 8d "C1"): two vectors of 2^20 bits, each bit set iid with p = 0.10 (seeds 1, 2), no
+    optimize() -> 16 bit-blocks each."""
+    out = []
+    for seed in (1, 2):
+        bits = np.random.default_rng(seed).random(1 << 20) < 0.10
+        v = bm.BVector(16)
+        for nb in range(16):
+            v.set_bits(nb, bits_to_words(bits[nb * BLOCK_BITS:(nb + 1) * BLOCK_BITS]))
+        out.append(v)
+    return out

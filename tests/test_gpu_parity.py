@@ -750,3 +750,19 @@ def test_sharded_rs_device_callables_two_shards_one_gpu():
         assert np.array_equal(acc_pos.cpu().numpy()[want_found], want_pos.astype(np.int64)[want_found])
     finally:
         ctx.close()
+
+
+def test_c1_config_bit_and_count(ctx):
+    """BASELINE configs[0]: two bvectors of 2^20 bits, 10 % random fill: bit_and + count() and count_and through the C ABI == the oracle
+    (and the reference when its library travelled); bytes touched = 3 * 16 * 8192."""
+    vecs = gen.c1_vectors()
+    ps = bm.PackedSet.pack(vecs)
+    t = bm.bit_and(vecs[0], vecs[1], bm.OPT_NONE, ctx)
+    want = np.stack([vecs[0].block_words(c) & vecs[1].block_words(c) for c in range(16)])
+    assert np.array_equal(np.stack([t.block_words(c) for c in range(16)]), want)
+    okind, opop, odig, onr, oblk, ogap = orclib.oracle_aggregate(ps, bm.OP_AND, [0, 1], None, 0)
+    assert np.array_equal(t.kind, okind) and t.count() == int(opop.sum()) == bm.count_and(vecs[0], vecs[1], ctx)
+    assert bm.count_or(vecs[0], vecs[1], ctx) == vecs[0].count() + vecs[1].count() - t.count()
+    if orclib.have_ref():
+        rkind, rpop, rblk, rcnt = orclib.ref_binop(ps, 1, 0, 1)
+        assert np.array_equal(rblk, want) and rcnt == t.count() == orclib.ref_count_op(ps, 1, 0, 1)

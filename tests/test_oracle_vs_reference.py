@@ -366,3 +366,17 @@ def test_device_decoder_host_build_matches_reference():
     assert orclib.blob_host_check(blob[: blob.size // 2], ps.n_blocks)[0] != 0
     bad = blob.copy(); bad[0] |= 1 << 5                           # BM_HM_64_BIT
     assert orclib.blob_host_check(bad, ps.n_blocks)[0] == 202
+
+
+@needs_ref
+def test_c1_config_bit_and_count():
+    """BASELINE configs[0]: two bvectors of 2^20 bits, 10 % random fill: t.bit_and(a, b, opt_none); t.count() and bm::count_and(a, b)
+    on the reference == the oracle (the reference's own CPU-runnable case; the GPU runs it in test_gpu_parity.py)."""
+    vecs = gen.c1_vectors()
+    ps = bm.PackedSet.pack(vecs)
+    rkind, rpop, rblk, rcnt = orclib.ref_binop(ps, 1, 0, 1)
+    okind, opop, odig, onr, oblk, ogap = orclib.oracle_aggregate(ps, bm.OP_AND, [0, 1], None, 0)
+    want = np.stack([vecs[0].block_words(c) & vecs[1].block_words(c) for c in range(16)])
+    assert np.array_equal(rblk, want) and np.array_equal(oblk, want) and np.array_equal(okind, rkind)
+    assert rcnt == int(opop.sum()) == orclib.ref_count_op(ps, 1, 0, 1) == int(np.unpackbits(want.view(np.uint8)).sum())
+    assert 9000 < rcnt < 12000                                      # 2^20 * 0.01 = 10 486 expected
