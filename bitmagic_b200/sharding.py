@@ -95,6 +95,7 @@ class ShardedRS:
         self.totals = allt
         self.prefix = torch.cumsum(allt, 0) - allt                  # exclusive scan of the shard cardinalities
         self.grand_total = int(allt.sum().item())
+        self._p0 = int(self.prefix[self.rank_id].item()); self._t = int(allt[self.rank_id].item())   # host copies: no sync per query batch
 
     def _reduce(self, t: torch.Tensor) -> torch.Tensor:
         if self.dist:
@@ -108,14 +109,14 @@ class ShardedRS:
         own = (pos >= lo_bit) & (pos < hi_bit)
         idx = own.nonzero(as_tuple=True)[0]
         if idx.numel():
-            out[idx] = self.local_rank((pos[idx] - lo_bit).contiguous()) + self.prefix[self.rank_id]
+            out[idx] = self.local_rank((pos[idx] - lo_bit).contiguous()) + self._p0
         if self.rank_id == self.world - 1:                           # past the last indexed bit: the grand total (src/bm.h:3132-3136)
             out[pos >= self.n_blocks * 65536] = self.grand_total
         return self._reduce(out)
 
     def select(self, r: torch.Tensor):
         """r: int64 tensor of 1-based global ranks -> (int64 positions, bool found), complete on every rank."""
-        p0 = int(self.prefix[self.rank_id].item()); t = int(self.totals[self.rank_id].item())
+        p0, t = self._p0, self._t
         pos = torch.zeros_like(r); found = torch.zeros_like(r)
         own = (r > p0) & (r <= p0 + t)
         idx = own.nonzero(as_tuple=True)[0]
