@@ -761,7 +761,7 @@ def test_c1_config_bit_and_count(ctx):
     want = np.stack([vecs[0].block_words(c) & vecs[1].block_words(c) for c in range(16)])
     assert np.array_equal(np.stack([t.block_words(c) for c in range(16)]), want)
     okind, opop, odig, onr, oblk, ogap = orclib.oracle_aggregate(ps, bm.OP_AND, [0, 1], None, 0)
-    assert np.array_equal(t.kind, okind) and t.count() == int(opop.sum()) == bm.count_and(vecs[0], vecs[1], ctx)
+    assert np.array_equal(oblk, want) and t.count() == int(opop.sum()) == bm.count_and(vecs[0], vecs[1], ctx)
     assert bm.count_or(vecs[0], vecs[1], ctx) == vecs[0].count() + vecs[1].count() - t.count()
     if orclib.have_ref():
         rkind, rpop, rblk, rcnt = orclib.ref_binop(ps, 1, 0, 1)
