@@ -667,9 +667,9 @@ BME_HDN int ent_walk_segment(const EntCtx& c, const uint8_t* stg, const EntSeg& 
     if (lead && sg.start == 0u) {
         const uint32_t hf = rd.u8();
         if (!(hf & (1u << 3))) rd.u8();                                              // byte order
-        if (hf & ((1u << 2) | (1u << 5) | (1u << 6))) err = BMB200_ERR_UNSUPPORTED;  // id list / 64-bit / XOR compression
+        if (hf & ((1u << 2) | (1u << 6))) err = BMB200_ERR_UNSUPPORTED;              // id list / XOR compression
         if (!(hf & (1u << 4))) rd.skip(8);                                           // GAP levels
-        if (hf & (1u << 1)) rd.u32();                                                // size
+        if (hf & (1u << 1)) { rd.u32(); if (hf & (1u << 5)) rd.u32(); }              // size (64-bit in a BM64ADDR stream)
         if (rd.bad && !err) err = BMB200_ERR_BADARG;
     }
     err = bme_bcast(err);
@@ -691,11 +691,13 @@ BME_HDN int ent_walk_segment(const EntCtx& c, const uint8_t* stg, const EntSeg& 
             case 3: nb += rd.u8(); break;
             case 5: nb += rd.u16(); break;
             case 7: nb += rd.u32(); break;
+            case 25: nb += rd.u64(); break;                                          // set_block_64zero (BM64ADDR streams)
             case 10: act = 2; cnt = 0xffffffffu; break;
             case 2: act = 2; cnt = 1; break;
             case 4: act = 2; cnt = rd.u8(); break;
             case 6: act = 2; cnt = rd.u16(); break;
             case 8: act = 2; cnt = rd.u32(); break;
+            case 26: { const uint64_t c64 = rd.u64(); act = 2; cnt = c64 > 0xfffffffeull ? 0xfffffffeu : (uint32_t)c64; break; }   // set_block_64one
             case 47: rd.skip(2); break; case 48: rd.skip(3); break; case 49: rd.skip(4); break;      // bookmarks: skip offsets
             case 50: rd.skip(1); break; case 51: rd.skip(2); break; case 52: rd.skip(3); break;      // sync marks
             case 53: rd.skip(4); break; case 54: rd.skip(6); break; case 55: rd.skip(8); break;
@@ -875,7 +877,7 @@ inline int ent_find_segments(const uint8_t* blob, uint64_t size, uint32_t vec, u
     const uint32_t hf = blob[p++];
     if (!(hf & (1u << 3))) ++p;
     if (!(hf & (1u << 4))) p += 8;
-    if (hf & (1u << 1)) p += 4;
+    if (hf & (1u << 1)) p += (hf & (1u << 5)) ? 8 : 4;
     if (p >= size) return BMB200_ERR_BADARG;
     if (blob[p] < 47u || blob[p] > 49u) return whole();              // no bookmark right after the header
     const size_t first = out.size();

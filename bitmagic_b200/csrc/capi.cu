@@ -396,9 +396,9 @@ int walk_blob(const uint8_t* blob, uint64_t size, uint32_t n_blocks, std::vector
     ByteRd r{blob, size};
     const uint32_t hf = r.u8();
     if (!(hf & (1u << 3))) r.u8();                                 // byte order
-    if (hf & ((1u << 2) | (1u << 5) | (1u << 6))) return BMB200_ERR_UNSUPPORTED;   // id list / 64-bit / XOR compression
+    if (hf & ((1u << 2) | (1u << 6))) return BMB200_ERR_UNSUPPORTED;               // id list / XOR compression
     if (!(hf & (1u << 4))) r.skip(8);                              // GAP levels
-    if (hf & (1u << 1)) r.u32();                                   // size
+    if (hf & (1u << 1)) { r.u32(); if (hf & (1u << 5)) r.u32(); }  // size (64-bit in a BM64ADDR stream)
     uint64_t nb = 0;
     auto ones = [&](uint64_t cnt) { for (uint64_t c = nb; c < nb + cnt && c < n_blocks; ++c) full[c] = 1; nb += cnt; };
     while (!r.bad) {
@@ -412,11 +412,13 @@ int walk_blob(const uint8_t* blob, uint64_t size, uint32_t n_blocks, std::vector
         case 3: nb += r.u8(); continue;
         case 5: nb += r.u16(); continue;
         case 7: nb += r.u32(); continue;
+        case 25: { uint64_t c = r.u32(); c |= (uint64_t)r.u32() << 32; nb += c; continue; }       // set_block_64zero (BM64ADDR streams)
         case 10: ones(nb < n_blocks ? n_blocks - nb : 0); return BMB200_OK;
         case 2: ones(1); continue;
         case 4: ones(r.u8()); continue;
         case 6: ones(r.u16()); continue;
         case 8: ones(r.u32()); continue;
+        case 26: { uint64_t c = r.u32(); c |= (uint64_t)r.u32() << 32; ones(c); continue; }       // set_block_64one
         case 11: t.type = DB_BIT; t.kind = BMB200_BLK_BIT; r.skip(BMB200_BLOCK_BYTES); break;
         case 17: { const uint32_t head = r.u16(), tail = r.u16(); if (tail >= BMB200_BLOCK_WORDS || head > tail) return BMB200_ERR_BADARG;
                    t.type = DB_BIT_INTERVAL; t.kind = BMB200_BLK_BIT; r.skip(4ull * (tail - head + 1)); break; }

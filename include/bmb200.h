@@ -195,7 +195,7 @@ int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks
  * interpolative GAP / bit-array blocks v3 / v3s with delta-range reduction and exception lists, super-block position lists,
  * bookmarks) the token streams are walked ON THE DEVICE (one warp per vector, csrc/blob_entropy.cuh) and every entropy-coded
  * token is then decoded by a warp of its own.  Not covered (BMB200_ERR_UNSUPPORTED, no CPU fallback): XOR-reference compression
- * (BM_HM_HXOR, sparse-vector serialization), id-list and 64-bit-address streams, and the legacy encodings the reference can
+ * (BM_HM_HXOR, sparse-vector serialization), id-list streams, and the legacy encodings the reference can
  * still read but no longer writes (tokens 20, 27-29, 31, 32, 43-45, 56, 57).  Malformed / truncated streams: BMB200_ERR_BADARG. */
 typedef struct bmb200_blob { const void* data; uint64_t size; } bmb200_blob;
 int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, const bmb200_blob* blobs, bmb200_set** out);

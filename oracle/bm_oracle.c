@@ -492,11 +492,10 @@ int orc_deserialize(const uint8_t* blob, uint64_t size, uint32_t n_cols, uint8_t
     if (gaps) memset(gaps, 0, (size_t)n_cols * GMAX * 2);
     uint32_t hf = rd8(&r);
     if (!(hf & (1u << 3))) rd8(&r);                       /* byte order (BM_HM_NO_BO) */
-    if (hf & (1u << 5)) return BMB200_ERR_UNSUPPORTED;    /* BM_HM_64_BIT */
     if (hf & (1u << 2)) return BMB200_ERR_UNSUPPORTED;    /* BM_HM_ID_LIST */
     if (hf & (1u << 6)) return BMB200_ERR_UNSUPPORTED;    /* BM_HM_HXOR */
     if (!(hf & (1u << 4))) for (int k = 0; k < 4; ++k) rd16(&r);   /* GAP levels */
-    if (hf & (1u << 1)) rd32(&r);                         /* BM_HM_RESIZE: size */
+    if (hf & (1u << 1)) { if (hf & (1u << 5)) rd64(&r); else rd32(&r); }   /* BM_HM_RESIZE: size (64-bit in a BM_HM_64_BIT stream) */
     uint32_t* tb = (uint32_t*)malloc(BMB200_BLOCK_BYTES);
     uint16_t* tg = (uint16_t*)malloc(sizeof(uint16_t) * 65540);
     uint16_t* arr = (uint16_t*)malloc(sizeof(uint16_t) * 65536);
@@ -515,11 +514,13 @@ int orc_deserialize(const uint8_t* blob, uint64_t size, uint32_t n_cols, uint8_t
         case 3: nb += rd8(&r); continue;
         case 5: nb += rd16(&r); continue;
         case 7: nb += rd32(&r); continue;
+        case 25: nb += rd64(&r); continue;                                /* set_block_64zero (BM64ADDR streams) */
         case 10: ones = (nb < n_cols) ? n_cols - nb : 0; for (uint64_t c = nb; c < n_cols; ++c) kind[c] = BMB200_BLK_FULL; nb = 1ull << 40; break;
         case 2: ones = 1; break;
         case 4: ones = rd8(&r); break;
         case 6: ones = rd16(&r); break;
         case 8: ones = rd32(&r); break;
+        case 26: ones = rd64(&r); break;                                  /* set_block_64one */
         case 11: for (uint32_t i = 0; i < BW; ++i) tb[i] = rd32(&r); is_bit = 1; break;
         case 19: { arr[0] = (uint16_t)rd16(&r); gap_from_sorted(tg, arr, 1, 0); is_gap = 1; break; }
         case 22: {

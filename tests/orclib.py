@@ -267,12 +267,12 @@ def ref_sv_time_scan(values, nulls, pred, search, repeats=2):
     return sec.value, tot.value
 
 
-def ref_serialize(ps, v, level):
-    """bm::serializer<> at `level` on vector v of the packed set -> bytes"""
+def ref_serialize(ps, v, level, addr64=False):
+    """bm::serializer<> at `level` on vector v of the packed set -> bytes (addr64: the BM64ADDR build of the reference)"""
     cap = int(ps.n_blocks) * 8300 + 4096
     out = np.zeros(cap, np.uint8); size = C.c_uint64(0)
     c = _pc(ps)
-    rc = ref().ref_serialize(C.byref(c), C.c_uint32(v), int(level), ptr(out), C.c_uint64(cap), C.byref(size))
+    rc = ref(addr64).ref_serialize(C.byref(c), C.c_uint32(v), int(level), ptr(out), C.c_uint64(cap), C.byref(size))
     assert rc == 0, f"ref_serialize rc={rc}"
     return out[:size.value].copy()
 
@@ -287,12 +287,12 @@ def ref_serialize_bookmarks(ps, v, level, interval):
     return out[:size.value].copy()
 
 
-def ref_deserialize(blob, n_cols):
+def ref_deserialize(blob, n_cols, addr64=False):
     """bm::deserialize -> kind, popcnt, blocks[n_cols][2048], gaps[n_cols][1280]"""
     b = np.ascontiguousarray(blob, dtype=np.uint8)
     kind = np.zeros(n_cols, np.uint8); pop = np.zeros(n_cols, np.uint32)
     blocks = np.zeros((n_cols, BLOCK_WORDS), np.uint32); gaps = np.zeros((n_cols, GAP_MAX_WORDS), np.uint16)
-    rc = ref().ref_deserialize(ptr(b), C.c_uint32(n_cols), ptr(kind), ptr(pop), ptr(blocks), ptr(gaps))
+    rc = ref(addr64).ref_deserialize(ptr(b), C.c_uint32(n_cols), ptr(kind), ptr(pop), ptr(blocks), ptr(gaps))
     assert rc == 0, f"ref_deserialize rc={rc}"
     return kind, pop, blocks, gaps
 

@@ -675,7 +675,7 @@ def test_deserialize_to_device_vs_golden_and_oracle(ctx, name):
     for v in range(nv):
         assert np.array_equal(np.stack([ps.vector(v).block_words(c) for c in range(nb - 3)]), blks[v][: nb - 3])
     dset.free()
-    bad = blobs[top][0].copy(); bad[0] |= 1 << 5                       # BM_HM_64_BIT header: not covered
+    bad = blobs[top][0].copy(); bad[0] |= 1 << 6                       # BM_HM_HXOR header (XOR-reference compression): not covered
     with pytest.raises(bm.BMB200Error) as e:
         bm.DeviceSet.upload_blobs(ctx, [bad], nb)
     assert e.value.code == bm.capi.ERR_UNSUPPORTED
@@ -699,6 +699,17 @@ def test_deserialize_to_device_vs_golden_and_oracle(ctx, name):
                     if bv.kind[c] == bm.BLK_GAP:
                         assert np.array_equal(bv.blocks[c], want[v][3][c][: bv.blocks[c].size]), f"level {level} vector {v} column {c}: GAP words"
             dset.free()
+    if orclib.have_ref(True):                                          # BM64ADDR streams (64-bit header fields)
+        import test_oracle_vs_reference as tor
+        vecs = tor.entropy_inputs(3) if name == "blobs_entropy" else tor.blob_inputs()
+        psr = bm.PackedSet.pack(vecs)
+        bl = [orclib.ref_serialize(psr, v, 6 if name == "blobs_entropy" else 2, addr64=True) for v in range(psr.n_vec)]
+        dset = bm.DeviceSet.upload_blobs(ctx, bl, psr.n_blocks)
+        got = dset.download()
+        for v in range(psr.n_vec):
+            assert np.array_equal(np.stack([got.vector(v).block_words(c) for c in range(psr.n_blocks)]),
+                                  np.stack([vecs[v].block_words(c) for c in range(psr.n_blocks)])), f"64-bit stream, vector {v}"
+        dset.free()
 
 
 def test_sharded_rs_device_callables_two_shards_one_gpu():

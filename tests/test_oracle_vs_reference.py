@@ -315,6 +315,26 @@ def test_deserialize_oracle_matches_reference():
     assert orclib.oracle_deserialize(blob[: blob.size // 2], ps.n_blocks)[0] != 0
 
 
+@pytest.mark.skipif(not orclib.have_ref(True), reason="oracle/_ref/libbmref64.so not built")
+def test_64bit_address_blobs_oracle_and_device_decoder_host_build():
+    """BLOBs written by the BM64ADDR build of the reference (BM_HM_64_BIT header, 64-bit size field and block-run counts): the oracle
+    and the host build of the product's walker / decoder == the BM64ADDR bm::deserialize."""
+    for vecs in (blob_inputs(), entropy_inputs(3)):
+        ps = bm.PackedSet.pack(vecs)
+        for level in (0, 2, 4, 6):
+            for v in range(ps.n_vec):
+                blob = orclib.ref_serialize(ps, v, level, addr64=True)
+                assert blob[0] & (1 << 5)
+                rkind, rpop, rblk, rgap = orclib.ref_deserialize(blob, ps.n_blocks, addr64=True)
+                assert np.array_equal(rblk, np.stack([vecs[v].block_words(c) for c in range(ps.n_blocks)]))
+                rc, kind, blk, gaps = orclib.oracle_deserialize(blob, ps.n_blocks)
+                assert rc == 0 and np.array_equal(blk, rblk) and np.array_equal(kind, rkind) and np.array_equal(gaps, rgap), f"level {level} vector {v}"
+                rc, kind, dec, gw, blk, gaps, n = orclib.blob_host_check(blob, ps.n_blocks)
+                assert rc == 0 and np.array_equal(kind, rkind), f"level {level} vector {v}"
+                for c in np.flatnonzero(dec):
+                    assert np.array_equal(blk[c], rblk[c]) if kind[c] == bm.BLK_BIT else np.array_equal(gaps[c], rgap[c])
+
+
 @needs_ref
 def test_bookmarked_blobs_oracle_and_device_decoder_host_build():
     """BLOBs written with serializer::set_bookmarks(true, interval): the oracle skips the marks; the product's walker cuts the stream
@@ -364,7 +384,7 @@ def test_device_decoder_host_build_matches_reference():
     vecs = entropy_inputs(); ps = bm.PackedSet.pack(vecs)
     blob = orclib.ref_serialize(ps, 2, 5)
     assert orclib.blob_host_check(blob[: blob.size // 2], ps.n_blocks)[0] != 0
-    bad = blob.copy(); bad[0] |= 1 << 5                           # BM_HM_64_BIT
+    bad = blob.copy(); bad[0] |= 1 << 6                           # BM_HM_HXOR: XOR-reference compression is not covered
     assert orclib.blob_host_check(bad, ps.n_blocks)[0] == 202
 
 
