@@ -168,6 +168,17 @@ struct EntRd {
         p += 4; return v;
     }
     BME_HD uint64_t u64() { const uint64_t lo = u32(); return lo | ((uint64_t)u32() << 32); }
+    // 32 bits at byte offset `at` (at + 4 <= end), no state change: the fast readers keep their own position
+    BME_HD uint32_t peek32(uint64_t at) const
+    {
+#ifdef __CUDA_ARCH__
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(s + (at & ~3ull));
+        const uint32_t sh = (uint32_t)(at & 3ull) * 8u, lo = w[0];
+        return sh ? __funnelshift_r(lo, w[1], sh) : lo;
+#else
+        return (uint32_t)s[at] | ((uint32_t)s[at + 1] << 8) | ((uint32_t)s[at + 2] << 16) | ((uint32_t)s[at + 3] << 24);
+#endif
+    }
     BME_HD void skip(uint64_t k) { if (p + k > end) { bad = 1; p = end; } else p += k; }
 };
 
@@ -244,28 +255,50 @@ BME_HD void ent_bic_decode(EntBits& b, T* out, uint32_t sz, uint32_t lo, uint32_
     // pending right halves: (first index | size << 16) -- a right half of at most 65536 values holds < 32768 -- and their value range
     // (16-bit: lo | hi << 16 in one word)
     uint32_t st_seg[20], st_lo[20], st_hi[k16 ? 1 : 20]; int sp = 0;
-    if (sz > 65536u) { b.r->bad = 1; return; }
+    EntRd* const r = b.r;
+    if (sz > 65536u) { r->bad = 1; return; }
+    if (r->bad) return;
+    // This loop is the hot spot of both passes (one lane, one dependent chain), so it runs on a private copy of the bit reader that
+    // keeps >= 32 bits in the window: one refill test per value, no branch inside a code word.  The window may run ONE word ahead
+    // of what bm::bit_in would have fetched; that word is handed back on exit, so the stream position after the array is the lazy
+    // one (start + 4 * ceil(bits / 32)) and the bits left in the accumulator are the ones a lazy reader would hold.
+    uint64_t acc = b.acc; uint32_t have = b.have, malformed = 0;
+    uint64_t p = r->p; const uint64_t end = r->end;
     uint32_t off = 0;
     for (;;) {
         while (sz) {
-            if (b.r->bad) return;
-            uint32_t val = b.bic(hi - lo - sz + 1u);
+            if (have < 32u) { const uint32_t w = (p + 4u <= end) ? r->peek32(p) : 0u; p += 4u; acc |= (uint64_t)w << have; have += 32u; }
+            const uint32_t rr = hi - lo - sz + 1u;
+            uint32_t val = 0;
+            if (rr) {                                   // one centered-minimal code word (src/encoding.h:2224-2237)
+                if (rr > 0x7ffffff0u) { malformed = 1; sp = 0; break; }
+                const uint32_t logv = 31u - bme_clz(rr + 1u);                  // <= 30
+                const uint32_t c = (1u << (logv + 1u)) - rr - 1u;
+                const int32_t half_c = (int32_t)(c >> 1), half_r = (int32_t)(rr >> 1);
+                const int32_t lo1 = half_r - half_c - (int32_t)((rr + 1u) & 1u), hi1 = half_r + half_c + 1;
+                val = (uint32_t)acc & ((1u << logv) - 1u);
+                acc >>= logv; have -= logv;
+                if ((int32_t)val <= lo1 || (int32_t)val >= hi1) { val += ((uint32_t)acc & 1u) << logv; acc >>= 1; have -= 1u; }
+            }
             const uint32_t mid = sz >> 1;
             val += lo + mid;
             out[off + mid] = (T)val;
             if (sz <= 1u) break;
             if (sz - mid - 1u) {                         // a non-empty right half waits on the stack (its first index is <= 65535 then)
-                if (sp >= 20) { b.r->bad = 1; return; }
+                if (sp >= 20) { malformed = 1; sp = 0; break; }
                 st_seg[sp] = (off + mid + 1u) | ((sz - mid - 1u) << 16);
                 if (k16) st_lo[sp] = ((val + 1u) & kMask) | (hi << 16); else { st_lo[sp] = val + 1u; st_hi[k16 ? 0 : sp] = hi; }
                 ++sp;
             }
             sz = mid; hi = (val - 1u) & kMask;          // left half next; off and lo stay
         }
-        if (!sp) return;
+        if (!sp) break;
         --sp; off = st_seg[sp] & 0xffffu; sz = st_seg[sp] >> 16;
         if (k16) { lo = st_lo[sp] & 0xffffu; hi = st_lo[sp] >> 16; } else { lo = st_lo[sp]; hi = st_hi[k16 ? 0 : sp]; }
     }
+    if (have >= 32u) { p -= 4u; have -= 32u; acc &= have ? ((1ull << have) - 1ull) : 0ull; }     // hand the look-ahead word back
+    if (p > end || malformed) { r->bad = 1; p = p > end ? end : p; }
+    r->p = p; b.acc = acc; b.have = have;
 }
 
 // arr_restore_min_w (src/bmfunc.h:2526-2581), T = u16: per-window minimal delta put back
