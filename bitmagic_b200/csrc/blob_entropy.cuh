@@ -628,7 +628,7 @@ BME_HDN int ent_decode_block(const EntCtx& c, uint32_t code, EntRd& rd_io, uint3
 }
 
 // super-block token 68 (set_sblock_bienc_v3): lane 0 decodes the ascending 24-bit positions into `arr` (65536 u32 = lists a + b)
-BME_HD int ent_decode_sblock_impl(EntRd& rd, uint32_t* arr, uint32_t* len_out, uint32_t* sb_out)
+BME_HD int ent_decode_sblock_impl(EntRd& rd, uint32_t* arr, uint32_t* len_out, uint32_t* sb_out, uint32_t* min0_out)
 {
     EntBits b; b.init(&rd);
     const uint32_t flag = b.bits(8u);
@@ -643,19 +643,32 @@ BME_HD int ent_decode_sblock_impl(EntRd& rd, uint32_t* arr, uint32_t* len_out, u
     if (len < 2u || len > 65536u || rd.bad) return BMB200_ERR_BADARG;
     arr[0] = min_v; arr[len - 1u] = max_v;
     if (len > 2u) ent_bic_decode<uint32_t>(b, arr + 1, len - 2u, min_v + 1u, max_v - 1u);
-    if (min0) { uint32_t dacc = 0; for (uint32_t i = 1; i < len; ++i) { arr[i] += min0 + dacc; dacc += min0; } }
     if (rd.bad) return BMB200_ERR_BADARG;
-    for (uint32_t i = 1; i < len; ++i) if (arr[i] <= arr[i - 1u]) return BMB200_ERR_BADARG;       // a valid list is strictly ascending
-    if (arr[len - 1u] >= 256u * 65536u) return BMB200_ERR_BADARG;
-    *len_out = len; *sb_out = sb;
+    *len_out = len; *sb_out = sb; *min0_out = min0;
     return BMB200_OK;
 }
-BME_HDN int ent_decode_sblock(EntRd& rd_io, uint32_t* arr, uint32_t* len_out, uint32_t* sb_out)
+// Team-wide: lane 0 decodes the interpolative list (the only sequential part); putting the minimal delta back (arr_restore_min,
+// src/bmfunc.h:2657: arr[i] += i * min0 in closed form) and the validity check (strictly ascending, inside the super-block) are
+// done by all lanes -- as lane-0 loops over the list in global memory they cost more than the decode itself.
+BME_HDN int ent_decode_sblock(const EntCtx& c, EntRd& rd_io, uint32_t* arr, uint32_t* len_out, uint32_t* sb_out)
 {
-    EntRd rd = rd_io;
-    const int rc = ent_decode_sblock_impl(rd, arr, len_out, sb_out);
-    rd_io = rd;
-    return rc;
+    uint32_t rc = 0, len = 0, sb = 0, min0 = 0;
+    if (c.t.lane == 0u) {
+        EntRd rd = rd_io;
+        rc = (uint32_t)ent_decode_sblock_impl(rd, arr, &len, &sb, &min0);
+        rd_io = rd;
+    }
+    rc = bme_bcast(rc); len = bme_bcast(len); sb = bme_bcast(sb); min0 = bme_bcast(min0);
+    if (rc) return (int)rc;
+    bme_sync();
+    if (min0) { for (uint32_t i = 1u + c.t.lane; i < len; i += c.t.nl) arr[i] += i * min0; bme_sync(); }
+    uint32_t bad = 0;
+    for (uint32_t i = 1u + c.t.lane; i < len; i += c.t.nl) bad |= (arr[i] <= arr[i - 1u]) ? 1u : 0u;
+    if (c.t.lane == 0u && arr[len - 1u] >= 256u * 65536u) bad = 1u;
+    if (bme_sum(bad)) return BMB200_ERR_BADARG;
+    bme_sync();
+    *len_out = len; *sb_out = sb;
+    return BMB200_OK;
 }
 // positions [k0, k1) of a decoded super-block list that fall into block `blk` -> bitmap (cleared first)
 BME_HD void ent_sblock_fill(const EntCtx& c, const uint32_t* arr, uint32_t k0, uint32_t k1)
@@ -810,9 +823,8 @@ BME_HDN int ent_walk_segment(const EntCtx& c, const uint8_t* stg, const EntSeg& 
         {
             const uint64_t off = rd.p - blob_off;
             uint32_t* arr = reinterpret_cast<uint32_t*>(c.la);            // lists a + b are contiguous: 65536 u32
-            uint32_t len = 0, sb = 0, rc = 0;
-            if (lead) rc = (uint32_t)ent_decode_sblock(rd, arr, &len, &sb);
-            rc = bme_bcast(rc); len = bme_bcast(len); sb = bme_bcast(sb);
+            uint32_t len = 0, sb = 0;
+            const uint32_t rc = (uint32_t)ent_decode_sblock(c, rd, arr, &len, &sb);
             if (rc) return (int)rc;
             const uint64_t nb0 = nb & ~255ull;
             if ((uint64_t)sb * 256u != nb0) return BMB200_ERR_BADARG;
@@ -861,14 +873,12 @@ BME_HD void ent_store_gap(const EntCtx& c, uint16_t* unit, uint32_t pad)
 BME_HDN int ent_emit(const EntCtx& c, const uint8_t* stg, uint64_t src, uint64_t end, uint32_t code, uint32_t v, uint64_t dst, uint32_t kind,
                      uint32_t aux2, const EntSetView& set, uint32_t* bit_pool, uint16_t* gap_pool)
 {
-    const bool lead = (c.t.lane == 0u);
     EntRd rd{stg, src, end, 0u};
     bme_sync();
     if (code == 68u) {
         uint32_t* arr = reinterpret_cast<uint32_t*>(c.la);
-        uint32_t len = 0, sb = 0, rc = 0;
-        if (lead) rc = (uint32_t)ent_decode_sblock(rd, arr, &len, &sb);
-        rc = bme_bcast(rc); len = bme_bcast(len);
+        uint32_t len = 0, sb = 0;
+        const uint32_t rc = (uint32_t)ent_decode_sblock(c, rd, arr, &len, &sb);
         if (rc) return (int)rc;
         bme_sync();
         for (uint32_t k = 0; k < len; ) {
