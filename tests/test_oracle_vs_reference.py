@@ -400,3 +400,31 @@ def test_c1_config_bit_and_count():
     assert np.array_equal(rblk, want) and np.array_equal(oblk, want) and np.array_equal(okind, rkind)
     assert rcnt == int(opop.sum()) == orclib.ref_count_op(ps, 1, 0, 1) == int(np.unpackbits(want.view(np.uint8)).sum())
     assert 9000 < rcnt < 12000                                      # 2^20 * 0.01 = 10 486 expected
+
+
+@needs_ref
+def test_multi_superblock_blobs_with_bookmarks():
+    """BLOBs that span more than one 256-block super-block (super-block position lists next to ordinary tokens, 24-bit bookmark offsets,
+    sync marks): oracle and the host build of the product's decoder == bm::deserialize."""
+    rng = np.random.default_rng(31)
+    nbk = 270
+    vecs = gen.entropy_vectors(rng, n_vec=5, n_blocks=nbk)
+    v = bm.BVector(nbk)
+    for nb in range(0, nbk, 3):
+        bits = np.zeros(65536, np.uint8); bits[rng.choice(65536, size=int(rng.integers(1, 30)), replace=False)] = 1
+        v.set_gap(nb, bm.hostfmt.bits_to_gap(bm.hostfmt.bits_to_words(bits)))
+    vecs.append(v)
+    ps = bm.PackedSet.pack(vecs)
+    n_ent = 0
+    for level, interval in ((5, 0), (6, 16), (6, 256)):
+        for vi in range(ps.n_vec):
+            blob = orclib.ref_serialize_bookmarks(ps, vi, level, interval) if interval else orclib.ref_serialize(ps, vi, level)
+            rkind, rpop, rblk, rgap = orclib.ref_deserialize(blob, ps.n_blocks)
+            rc, kind, blk, gaps = orclib.oracle_deserialize(blob, ps.n_blocks)
+            assert rc == 0 and np.array_equal(blk, rblk) and np.array_equal(kind, rkind) and np.array_equal(gaps, rgap), f"oracle: level {level} vector {vi}"
+            rc, kind, dec, gw, blk, gaps, n = orclib.blob_host_check(blob, ps.n_blocks)
+            assert rc == 0 and np.array_equal(kind, rkind), f"decoder: level {level} vector {vi}"
+            n_ent += n
+            for c in np.flatnonzero(dec):
+                assert np.array_equal(blk[c], rblk[c]) if kind[c] == bm.BLK_BIT else np.array_equal(gaps[c], rgap[c])
+    assert n_ent > 1000
