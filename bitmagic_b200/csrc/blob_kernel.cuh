@@ -13,8 +13,9 @@
 //   DB_GAP16        set_block_gap / _gapbit  deserialize_gap             :5243   header + (len-1) u16 run ends
 //   DB_GAP_V3       set_block_gap_egamma_v3  read_gap_block              :5050   bit stream: gamma(len-1), start, 0, 16-bit run ends
 //   DB_ARRGAP(_INV) set_block_arrgap(_inv), set_block_bit_1bit  :4833-4845, gap_set_array  sorted positions -> GAP runs
-// Encodings that need a sequential entropy decoder (gamma values, binary interpolative, XOR chains) are rejected by the
-// host walker with BMB200_ERR_UNSUPPORTED -- there is no CPU fallback.
+// Encodings that need a sequential entropy decoder (gamma values, binary interpolative coding, super-block lists) make the host
+// walker give up (BMB200_ERR_UNSUPPORTED internally): bmb200_set_upload_blobs then walks and decodes the streams on the device,
+// blob_entropy.cuh.  There is no CPU fallback.
 #pragma once
 #include "common.cuh"
 
