@@ -6,17 +6,27 @@ A "step" is ONE pass of the aggregator over one synthetic vector set:
       bm::aggregator::combine_and_sub over 1024 vectors x 2^30 bits, Zipf density mix d_k = 0.5/k,
       every vector optimize()d (k <~ 51 bit-blocks, the rest GAP), AND = {1,2}, SUB = {3..1024}, opt_compress
   workload c2 (configs[1]): combine_or over 256 vectors x 2^28 bits, 5 % density, bit-blocks only
-Multi-GPU (torchrun, one rank per GPU): the block range is sharded -- every rank owns a contiguous range of
-block columns of every vector (weak scaling: a full-size shard per rank), aggregates it locally and the ranks
-exchange per-block popcounts with one NCCL all_gather + one all_reduce of the cardinality on the same stream.
+  workload c5 (configs[4]): one GPU's shard of combine_or over 4096 vectors x 2^32 bits sharded over 8 GPUs
+Multi-GPU (torchrun, one rank per GPU): the block range is sharded -- every rank owns a contiguous range of block columns of
+every vector (weak scaling: a full-size shard per rank), aggregates it locally, and the ranks exchange per-block popcounts +
+cardinalities with ONE ncclAllGather issued by the library itself (bmb200_exchange_popcounts) on a side stream, so the
+exchange of step i overlaps the kernel of step i+1.  torch.distributed only carries the barrier / max-over-ranks plumbing.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c2]
+What one run reports (one JSON line):
+  value / roofline  device-resident aggregation, CUDA events on the launching stream
+  parity            ALL result columns (kind, popcount, digest, GAP length) against the unmodified reference running on the
+                    host cores over inputs regenerated on the HOST by an independent implementation of the generator
+  e2e               through bm::b200::aggregator on REAL bm::bvector<> objects (oracle/_ref/libbmb200_e2e.so): cold =
+                    tree walk + pack + H2D + kernel + D2H + result bvector every step (the contract's e2e), warm = sources
+                    resident in a bm::b200::device_set (upload once), split of the cold step, result compared with bm::aggregator
+  cpu_baseline      the reference on 1 thread (bounded sample) and on all cores (whole workload)
 
-Prints ONE JSON line (see README / DESIGN.md section "Measurement").
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c2|c5]
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -38,6 +48,8 @@ WORKLOADS = {
     # BASELINE (as bit-blocks it would be 2 TiB), SURVEY 8d proposes iid p=0.0025 + optimize() => GAP blocks, ~22 GB per GPU
     "c5": dict(n_vec=4096, n_blocks=8192, op="or", desc="combine_or 4096 vectors, 8192 block columns per GPU (2^32 bits over 8 GPUs), iid 0.25% density, optimize()d (GAP blocks)"),
 }
+OPS = {"or": 0, "and": 1, "and_sub": 2}
+F_OPT_NONE, F_OPT_COMPRESS = 0, 2
 
 
 def workload_inputs(name: str, rank: int):
@@ -59,13 +71,26 @@ def workload_inputs(name: str, rank: int):
 
 
 def workload_groups(name: str):
-    import bitmagic_b200 as bm
     nv = WORKLOADS[name]["n_vec"]
     if name == "c3":
-        return bm.OP_AND_SUB, np.array([0, 1], np.uint32), np.arange(2, nv, dtype=np.uint32), bm.F_OPT_COMPRESS
+        return OPS["and_sub"], np.array([0, 1], np.uint32), np.arange(2, nv, dtype=np.uint32), F_OPT_COMPRESS
     if name == "c5":
-        return bm.OP_OR, np.arange(nv, dtype=np.uint32), None, bm.F_OPT_COMPRESS
-    return bm.OP_OR, np.arange(nv, dtype=np.uint32), None, bm.F_OPT_NONE
+        return OPS["or"], np.arange(nv, dtype=np.uint32), None, F_OPT_COMPRESS
+    return OPS["or"], np.arange(nv, dtype=np.uint32), None, F_OPT_NONE
+
+
+def cpu_model() -> str:
+    try:
+        return next(ln.split(":", 1)[1].strip() for ln in open("/proc/cpuinfo") if ln.startswith("model name"))
+    except Exception:
+        return "unknown"
+
+
+def mem_available_gb() -> float:
+    try:
+        return int(next(ln for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")).split()[1]) / 2**20
+    except Exception:
+        return 1e9
 
 
 class ClockSampler:
@@ -127,24 +152,19 @@ def measured_peak_gbs():
 
 
 def profiled_traffic(workload: str):
-    """dram__bytes_read+write per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
-    f = ROOT / "profiles" / "r01" / "ncu_agg_kernel.json"
+    """dram__bytes_read+write per launch of the dominant kernel from the newest committed ncu capture (profiles/), or None."""
     key = {"c3": "c3_agg_kernel_and_sub", "c2": "c2_agg_kernel_or", "c5": "c5_agg_kernel_or"}.get(workload)
-    try:
-        d = json.loads(f.read_text())[key]
-        def gb(x):
-            return float(x["value"]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[x["unit"]]
-        return int(gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"]))
-    except Exception:
-        return None
+    for rnd in ("r02", "r01"):
+        f = ROOT / "profiles" / rnd / "ncu_agg_kernel.json"
+        try:
+            d = json.loads(f.read_text())[key]
 
-
-def set_stats(ps_kinds_counts, gap_words_exact, result_bytes, n_cols):
-    """Algorithmic bytes: stored size of every source block (bit 8192 B, GAP 2*(len+1) B,
-    FULL/NULL 0) + the result blocks actually written (8192 B per bit-block, 2*(len+1) B per GAP block -- the
-    bit->GAP step is fused into the kernel) + 12 B of popcount/digest per block column."""
-    n_bit = ps_kinds_counts["bit"]
-    return n_bit * 8192 + gap_words_exact * 2 + result_bytes + n_cols * 12
+            def gb(x):
+                return float(x["value"]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[x["unit"]]
+            return int(gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"])), f"profiles/{rnd}/ncu_agg_kernel.json (ncu --set full, same command, full-size shard)"
+        except Exception:
+            continue
+    return None, None
 
 
 def device_set_stats(ctx, dset, torch):
@@ -171,51 +191,188 @@ def device_set_stats(ctx, dset, torch):
     return counts, gap_words
 
 
+# ----------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
-    """--impl reference: the unmodified reference (oracle/_ref/libbmref.so; else the C oracle port) on the host
-    cores, all threads, on a bounded column sample of the same workload."""
+    """--impl reference: the UNMODIFIED reference (oracle/_ref/libbmref*.so, compiled from /root/reference/src) on the host cores.
+    Inputs come from the host restatement of the generator (oracle/bm_synth.c): no GPU, no product library in this process.
+    The bvectors are built once; every step is one pass of bm::aggregator over the WHOLE workload on T = nproc worker threads,
+    each with its own aggregator over a contiguous range of block columns."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
-    import torch
-    import bitmagic_b200 as bm
     import orclib
     w = WORKLOADS[args.workload]
+    n_cols = args.cols or w["n_blocks"]
     cores = os.cpu_count() or 1
-    threads = max(1, min(cores, args.ref_threads or cores))
-    # every worker gets whole 256-block superblocks (the reference walks all 256 sub-blocks of a top block
-    # once a group has > 32 vectors, src/bmaggregator.h:1565-1566), so threads <= n_blocks / 256
-    threads = max(1, min(threads, w["n_blocks"] // 256))
-    sample_cols = min(w["n_blocks"], args.ref_cols or 256 * threads)
+    threads = max(1, min(args.ref_threads or cores, n_cols))
     dens, seed, optimize = workload_inputs(args.workload, 0)
     op, g0, g1, flags = workload_groups(args.workload)
-    ctx = bm.default_context(0)
-    dset = bm.DeviceSet.synth(ctx, w["n_vec"], sample_cols, dens, seed, optimize)     # same generator, first columns
-    ps = dset.download()
-    kinds = ps.kinds()
-    n_src_blocks = int((kinds != 0).sum())
-    dset.free()
-    kind = "reference" if orclib.have_ref() else "port"
-    times = []
-    for it in range(args.warmup + args.steps):
-        if kind == "reference":
-            sec, tot = orclib.ref_time_aggregate(ps, op, g0, g1, flags, threads=threads, repeats=1)
-        else:
-            t0 = time.perf_counter(); orclib.oracle_aggregate(ps, op, g0, g1, flags); sec = time.perf_counter() - t0
-            threads = 1
-        if it >= args.warmup:
-            times.append(sec)
-    ms = 1e3 * float(np.mean(times))
+    need_gb = 2.3 * (13.5 if args.workload == "c3" else 22.5 if args.workload == "c5" else 8.1) * n_cols / w["n_blocks"]
+    if mem_available_gb() < need_gb:
+        return {"impl": "reference", "unavailable": f"host has {mem_available_gb():.0f} GB available, the workload needs {need_gb:.0f} GB"}
+    t0 = time.time()
+    hs = orclib.HostSynth(w["n_vec"], n_cols, dens, seed, optimize, threads=cores)
+    t_synth = time.time() - t0
+    ps = hs.ps
+    n_src_blocks = int((ps.kinds() != 0).sum())
+    stored = ps.stored_bytes()
+    have = orclib.have_ref()
+    rows = {}
+    variants = [False] + (["avx512"] if (have and orclib.have_ref("avx512") and orclib.cpu_has_avx512()) else [])
+    if not have:
+        # the C port (oracle/bm_oracle.c), 1 thread -- only when oracle/_ref was not built (no /root/reference at build time)
+        t0 = time.perf_counter(); orclib.oracle_aggregate(ps, op, g0, g1, flags, 0, min(n_cols, 256)); sec = time.perf_counter() - t0
+        frac = min(n_cols, 256) / n_cols
+        rows["port"] = {"ms": 1e3 * sec / frac, "threads": 1, "simd": "scalar", "result_bits": None, "extrapolated_from_cols": min(n_cols, 256)}
+    for var in variants if have else []:
+        t0 = time.time()
+        job = orclib.RefJob(ps, op, g0, g1, flags, threads=threads, variant=var)
+        t_build = time.time() - t0
+        job.run(max(1, args.warmup))
+        sec, tot = job.run(args.steps)
+        rows[orclib.ref(var).ref_simd().decode()] = {"ms": 1e3 * float(np.mean(sec)), "ms_min": 1e3 * float(np.min(sec)), "threads": job.threads,
+                                                     "simd": orclib.ref(var).ref_simd().decode(), "result_bits": int(tot), "build_s": round(t_build, 2)}
+        job.free()
+    best = min(rows, key=lambda k: rows[k]["ms"])
+    ms = rows[best]["ms"]
     value = n_src_blocks / (ms * 1e-3)
-    sample = f"{sample_cols} of {w['n_blocks']} block columns x {w['n_vec']} vectors per step ({ps.stored_bytes() / 2**20:.0f} MiB)"
-    line = {"impl": "reference", "metric": "aggregator input 64Kbit-blocks/s", "value": value, "unit": "blocks/s",
+    kind = "reference" if have else "port"
+    sample = f"all {n_cols} block columns x {w['n_vec']} vectors per step ({stored / 2**20:.0f} MiB), bvectors built once"
+    hs.free()
+    return {"impl": "reference", "metric": "aggregator input 64Kbit-blocks/s", "value": value, "unit": "blocks/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": args.workload + ": " + w["desc"], "sample": sample},
-            "cpu_baseline": {"value": value, "unit": "blocks/s", "cores": threads, "kind": kind, "sample": sample,
-                             "simd": orclib.ref().ref_simd().decode() if kind == "reference" else "scalar"},
-            "e2e": {"value": value, "unit": "blocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    return line
+            "config": {"workload": args.workload + ": " + w["desc"], "sample": sample, "reduced": bool(args.cols and args.cols != w["n_blocks"]),
+                       "inputs": f"host generator oracle/bm_synth.c, {t_synth:.1f} s on {cores} threads"},
+            "cpu_baseline": {"value": value, "unit": "blocks/s", "cores": rows[best]["threads"], "kind": kind, "sample": sample,
+                             "simd": rows[best]["simd"], "nproc": cores, "cpu": cpu_model(), "rows": rows,
+                             "gbs": stored / (ms * 1e-3) / 1e9},
+            "e2e": {"value": value, "unit": "blocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "result_bits": rows[best]["result_bits"]}
+
+
+# ----------------------------------------------------------------------------------------------- parity + e2e helpers
+def full_parity(workload, n_cols, rank, res_meta, threads):
+    """ALL columns of the GPU result against the unmodified reference over host-generated inputs (rank's own seeds)."""
+    import orclib
+    w = WORKLOADS[workload]
+    dens, seed, optimize = workload_inputs(workload, rank)
+    op, g0, g1, flags = workload_groups(workload)
+    kind_r, pop_r, dig_r, nr_r = res_meta
+    t0 = time.time()
+    hs = orclib.HostSynth(w["n_vec"], n_cols, dens, seed, optimize, threads=threads)
+    t_synth = time.time() - t0
+    out = {"cols": int(n_cols), "fields": ["kind", "popcnt", "digest", "gap_len"], "inputs": "regenerated on the host (oracle/bm_synth.c)",
+           "host_synth_s": round(t_synth, 2)}
+    if orclib.have_ref():
+        t0 = time.time()
+        job = orclib.RefJob(hs.ps, op, g0, g1, flags, threads=threads)
+        t_build = time.time() - t0
+        job.run(1)
+        sec, tot = job.run(3)
+        k, p, d, gl = job.export()
+        job.free()
+        out.update(against="oracle/_ref/libbmref.so (unmodified reference, bm::aggregator)", ref_threads=int(threads), ref_build_s=round(t_build, 2),
+                   ref_ms=1e3 * float(np.mean(sec)), ref_ms_min=1e3 * float(np.min(sec)))
+        gap = k == 3
+        eq = {"kind": bool(np.array_equal(k, kind_r)), "popcnt": bool(np.array_equal(p, pop_r)), "digest": bool(np.array_equal(d, dig_r)),
+              "gap_len": bool(np.array_equal(gl[gap], nr_r[gap]))}
+    else:   # GPU box without oracle/_ref (should not happen: the prebuilt files travel): the C port on a bounded range
+        nc = min(n_cols, 512)
+        k, p, d, nr, _, _ = orclib.oracle_aggregate(hs.ps, op, g0, g1, flags, 0, nc)
+        out.update(against="oracle/liboracle.so (C port)", cols=int(nc))
+        eq = {"kind": bool(np.array_equal(k, kind_r[:nc])), "popcnt": bool(np.array_equal(p, pop_r[:nc])), "digest": bool(np.array_equal(d, dig_r[:nc])),
+              "gap_len": bool(np.array_equal(nr[k == 3], nr_r[:nc][k == 3]))}
+    src_blocks = int((hs.ps.kinds() != 0).sum())
+    stored = hs.ps.stored_bytes()
+    hs.free()
+    out["equal"] = all(eq.values())
+    out["per_field"] = eq
+    return out, src_blocks, stored
+
+
+class E2E:
+    """ctypes face of oracle/_ref/libbmb200_e2e.so (oracle/e2e_harness.cpp): bm::b200::aggregator on real bm::bvector<> objects."""
+
+    def __init__(self):
+        so = ROOT / "oracle" / "_ref" / "libbmb200_e2e.so"
+        self.lib = C.CDLL(str(so)) if so.exists() else None
+        if self.lib:
+            self.lib.e2e_create_empty.restype = C.c_void_p
+            self.lib.e2e_free.restype = None
+        self.h = None
+
+    def ok(self):
+        return self.lib is not None
+
+
+def run_e2e(args, ctx, dset, device, world, dist, torch, op, g0, g1, flags, total_bits, src_blocks_all):
+    """cold / warm end-to-end through the C++ binding on real bvectors built from this rank's (downloaded) inputs"""
+    from bitmagic_b200.capi import packed_c, ptr
+    e = E2E()
+    if not e.ok():
+        return {"unavailable": "oracle/_ref/libbmb200_e2e.so not built (needs the reference headers at build time)"}
+    need_gb = 1.3 * dset.stored_bytes() / 2**30 * world + 8          # every rank of this node keeps its bvectors on the host
+    if mem_available_gb() < need_gb:
+        return {"unavailable": f"host memory: {mem_available_gb():.0f} GB available, e2e needs {need_gb:.0f} GB for the host bvectors"}
+    cores = os.cpu_count() or 1
+    thr = max(1, cores // max(1, world))
+    lib = e.lib
+    g1a = g1 if g1 is not None else np.zeros(0, np.uint32)
+    node = C.c_int(-1)
+    # real bm::bvector<> objects, filled chunk by chunk from the device copy of this rank's inputs (the download is setup, not timed)
+    h = C.c_void_p(lib.e2e_create_empty(C.c_uint32(dset.n_vec), C.c_uint32(dset.n_blocks), int(device), 1, C.byref(node)))
+    assert h, "e2e_create_empty failed"
+    step_cols = 1024
+    for lo in range(0, dset.n_blocks, step_cols):
+        ps = dset.download(lo, min(dset.n_blocks, lo + step_cols))
+        c = packed_c(ps.n_vec, ps.n_blocks, ps.desc, ps.bit_base, ps.gap_base, ps.bit_pool, ps.gap_pool)
+        rc = lib.e2e_append(h, C.byref(c), C.c_uint32(lo), int(thr))
+        assert rc == 0, "e2e_append failed"
+        del ps
+    n0, n1 = int(g0.size), int(g1a.size)
+    compress = 1 if flags & F_OPT_COMPRESS else 0
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+    # ---- cold: tree walk + pack + H2D + kernel + D2H + bvector, every step ----
+    ms = np.zeros(args.e2e_steps + 1); cnt = C.c_uint64(0); h2d = C.c_uint64(0); d2h = C.c_uint64(0)
+    sync_all()
+    rc = lib.e2e_cold(h, int(op), compress, ptr(g0), n0, ptr(g1a), n1, int(args.e2e_steps + 1), ptr(ms), C.byref(cnt), C.byref(h2d), C.byref(d2h))
+    assert rc == 0, "e2e_cold failed"
+    assert cnt.value == total_bits, f"e2e (cold) result count {cnt.value} != device-resident run {total_bits}"
+    cold_ms = float(np.mean(ms[1:]))                          # step 0 allocates the pinned ring and the result buffers
+    a_ms, g_ms = C.c_double(0), C.c_double(0)
+    rc = lib.e2e_cold_split(h, int(op), compress, ptr(g0), n0, ptr(g1a), n1, C.byref(a_ms), C.byref(g_ms))
+    assert rc == 0
+    # ---- warm: sources resident in a device_set ----
+    wms = np.zeros(args.steps); wd2h = C.c_uint64(0)
+    sync_all()
+    rc = lib.e2e_warm(h, int(op), compress, ptr(g0), n0, ptr(g1a), n1, 3, int(args.steps), ptr(wms), C.byref(cnt), C.byref(wd2h))
+    assert rc == 0, f"e2e_warm failed rc={rc}"
+    assert cnt.value == total_bits, "e2e (warm) result differs from the device-resident run"
+    warm_ms = float(np.mean(wms))
+    # ---- result bvector vs the reference aggregator on the same bvectors (rank 0 only: single-threaded reference) ----
+    chk = None
+    if int(os.environ.get("RANK", "0")) == 0 and not args.no_e2e_check:
+        eq = C.c_int(0); rcnt = C.c_uint64(0); rms = C.c_double(0)
+        rc = lib.e2e_check(h, int(op), compress, ptr(g0), n0, ptr(g1a), n1, C.byref(eq), C.byref(rcnt), C.byref(rms))
+        assert rc == 0
+        chk = {"compare_eq_0_and_calc_stat_equal": bool(eq.value), "reference_count": int(rcnt.value), "reference_1thread_ms": rms.value}
+        assert eq.value, "bm::b200::aggregator result differs from bm::aggregator on the same bvectors"
+    lib.e2e_free(h)
+    t = torch.tensor([cold_ms, warm_ms], dtype=torch.float64, device=f"cuda:{device}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cold_ms, warm_ms = float(t[0].item()), float(t[1].item())
+    return {"value": src_blocks_all / (cold_ms * 1e-3), "unit": "blocks/s", "ms_per_step": cold_ms,
+            "h2d_bytes_per_step": int(h2d.value), "d2h_bytes_per_step": int(d2h.value), "h2d_gbs": h2d.value / cold_ms / 1e6,
+            "path": "cold: bm::b200::aggregator::combine_* on real bm::bvector<> sources, nothing resident (tree walk + pack + H2D + kernel + D2H + result bvector per step)",
+            "cold_split_ms": {"device_set_assign(walk+layout+pack+H2D)": a_ms.value, "aggregate_on_resident(kernel+D2H+bvector)": g_ms.value},
+            "warm": {"value": src_blocks_all / (warm_ms * 1e-3), "unit": "blocks/s", "ms_per_step": warm_ms, "h2d_bytes_per_step": 4 * (n0 + n1),
+                     "d2h_bytes_per_step": int(wd2h.value), "path": "sources resident in bm::b200::device_set (uploaded once from the same bvectors); combine_* -> kernel -> D2H -> result bvector"},
+            "host_threads": thr, "numa_node": node.value, "check": chk}
 
 
 class _StdoutToStderr:
@@ -242,6 +399,55 @@ def main():
         print(json.dumps(line), flush=True)
 
 
+def timed_resident(args, bm, torch, ctx, dset, op, g0, g1, flags, world, dist, dev, stream, n_cols, rank, sample_clocks=True):
+    """W warm-up + K timed steps of the device-resident aggregation (+ the library's own exchange when world > 1)."""
+    res = bm.aggregate(ctx, dset, op, g0, g1, flags)     # allocates the result buffers once
+    ctx.sync()
+
+    def step():
+        bm.aggregate(ctx, dset, op, g0, g1, flags, result=res)
+        if world > 1:
+            ctx.exchange_popcounts(res)                  # side stream: overlaps the next step's kernel
+
+    l0 = ctx.launch_count()
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        ctx.exchange_fence()
+    torch.cuda.synchronize(dev)
+    launches_per_step = (ctx.launch_count() - l0) // args.warmup
+
+    sampler = ClockSampler(dev.index) if (rank == 0 and sample_clocks) else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # a dedicated event pair around the dominant kernel of every step (aggregate launch only)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0.record(stream)
+    for i in range(args.steps):
+        kev[i][0].record(stream)
+        bm.aggregate(ctx, dset, op, g0, g1, flags, result=res)
+        kev[i][1].record(stream)
+        if world > 1:
+            ctx.exchange_popcounts(res)
+    if world > 1:
+        ctx.exchange_fence()                             # the launching stream waits for every exchange: they are inside the timed region
+    ev1.record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return res, float(t.item()) / args.steps, kern_ms, clocks, launches_per_step
+
+
 def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -252,9 +458,11 @@ def _main():
     ap.add_argument("--cols", type=int, default=0, help="override block columns per GPU (reduced runs are flagged)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-check", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-cols", type=int, default=256, help="block columns in the cpu_baseline sample")
-    ap.add_argument("--ref-cols", type=int, default=0, help="block columns per step for --impl reference (0 = 256 per thread)")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the extra config-5 shard line that 8-GPU runs carry")
+    ap.add_argument("--cpu-cols", type=int, default=256, help="block columns in the 1-thread cpu_baseline sample")
     ap.add_argument("--ref-threads", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -280,8 +488,20 @@ def _main():
     w = WORKLOADS[args.workload]
     n_cols = args.cols or w["n_blocks"]
     ctx = bm.Context(local)
+    all_cpus = os.sched_getaffinity(0)
+    numa_node = ctx.bind_host_numa()          # host threads + pinned staging next to this GPU's PCIe root (GPUs 0-3 / 4-7 sit on different nodes)
+    gpu_cpus = os.sched_getaffinity(0)
     stream = torch.cuda.current_stream(dev)
     ctx.set_stream(stream.cuda_stream)
+    exchange = None
+    if world > 1:
+        # the library's own communicator: rank 0 makes the id, torch.distributed only ships its 128 bytes
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ctx.comm_init(world, rank, bytes(idt.cpu().numpy().tobytes()))
+        exchange = "bmb200_exchange_popcounts: one ncclAllGather of (columns + 2) u32 per rank on a side stream, step i's exchange overlaps step i+1's kernel; the last one is fenced inside the timed region"
 
     dens, seed, optimize = workload_inputs(args.workload, rank)
     op, g0, g1, flags = workload_groups(args.workload)
@@ -292,144 +512,126 @@ def _main():
     counts, gap_words = device_set_stats(ctx, dset, torch)
     n_src_blocks = counts["bit"] + counts["gap"] + counts["full"]
 
-    res = bm.aggregate(ctx, dset, op, g0, g1, flags)     # allocates the result buffers once
-    ctx.sync()
-    rp = res.device_ptrs()
-
-    class Wrap:
-        def __init__(self, addr, typestr, shape):
-            self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (addr, False), "version": 2}
-    pop_t = torch.as_tensor(Wrap(rp["popcnt"], "<i4", (n_cols,)), device=dev)
-    gathered = torch.empty(world * n_cols, dtype=torch.int32, device=dev) if world > 1 else None
-    card = torch.zeros(1, dtype=torch.int64, device=dev)
-
-    from bitmagic_b200.sharding import exchange_popcounts
-
-    def step():
-        bm.aggregate(ctx, dset, op, g0, g1, flags, result=res)
-        if world > 1:                                          # per-block popcounts of every shard + global cardinality
-            exchange_popcounts(pop_t, world * n_cols, dist, out=gathered)
-
-    l0 = ctx.launch_count()
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize(dev)
-    launches_per_step = (ctx.launch_count() - l0) // args.warmup
-
-    # ---- timed region: device-resident inputs, CUDA events on the launching stream ----
-    sampler = ClockSampler(local) if rank == 0 else None
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    if sampler:
-        sampler.start()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    # a dedicated event pair around the dominant kernel of every step (aggregate launch only)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    evs[0].record(stream)
-    for i in range(args.steps):
-        kev[i][0].record(stream)
-        bm.aggregate(ctx, dset, op, g0, g1, flags, result=res)
-        kev[i][1].record(stream)
-        if world > 1:
-            _, card = exchange_popcounts(pop_t, world * n_cols, dist, out=gathered)
-        evs[i + 1].record(stream)
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    total_ms = evs[0].elapsed_time(evs[-1])
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    clocks = sampler.stop() if sampler else None
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
+    res, ms_per_step, kern_ms, clocks, launches_per_step = timed_resident(args, bm, torch, ctx, dset, op, g0, g1, flags, world, dist, dev, stream, n_cols, rank)
 
     total_bits, any_ = res.total()
     kind_r, pop_r, dig_r, nr_r = res.meta()
     res_bytes = int((kind_r == bm.BLK_BIT).sum()) * 8192 + int(2 * (nr_r[kind_r == bm.BLK_GAP].astype(np.int64) + 1).sum())
-    alg_bytes = set_stats(counts, gap_words, res_bytes, n_cols)
+    # algorithmic bytes: stored source bytes (bit 8192 B, GAP 2*(len+1) B) + result blocks written + 12 B meta per column
+    alg_bytes = counts["bit"] * 8192 + gap_words * 2 + res_bytes + n_cols * 12
+    xchg = None
+    if world > 1:
+        gtot, rtot, _ = ctx.exchange_fetch(world, n_cols, want_popcounts=False)
+        assert int(rtot[rank]) == int(total_bits), "exchange: this rank's cardinality did not come back"
+        xchg = {"global_result_bits": int(gtot), "collective": exchange}
 
-    # whole-job numbers
     src_blocks_all = torch.tensor([n_src_blocks], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(src_blocks_all)
-    value = float(src_blocks_all.item()) / (ms_per_step * 1e-3)
+    src_blocks_all = float(src_blocks_all.item())
+    value = src_blocks_all / (ms_per_step * 1e-3)
 
-    # ---- e2e through the host C-ABI call: pinned HOST buffers -> H2D -> kernel -> D2H of the metadata ----
+    # ---- parity: every column against the reference on the host (rank 0; its own shard) ----
+    parity = None
+    cpu = None
+    if rank == 0 and not args.no_parity:
+        need = 2.3 * dset.stored_bytes() / 2**30
+        if mem_available_gb() > need + 8:
+            os.sched_setaffinity(0, all_cpus)     # the reference gets every core of the box, not only this GPU's NUMA node
+            parity, host_src_blocks, host_stored = full_parity(args.workload, n_cols, rank, (kind_r, pop_r, dig_r, nr_r), os.cpu_count() or 1)
+            parity["ranks_checked"] = [0]
+            parity["inputs_equal"] = bool(host_src_blocks == n_src_blocks and host_stored == dset.stored_bytes())
+            os.sched_setaffinity(0, gpu_cpus)
+            assert parity["equal"] and parity["inputs_equal"], f"PARITY FAILURE against the reference: {parity}"
+        else:
+            parity = {"skipped": f"host memory {mem_available_gb():.0f} GB < {need + 8:.0f} GB"}
+
+    # ---- e2e: real bvectors through the C++ binding ----
     e2e = None
     if not args.no_e2e:
-        ps = dset.download()
-        for a in (ps.desc, ps.bit_base, ps.gap_base, ps.bit_pool, ps.gap_pool):
-            if a.size:
-                torch.cuda.cudart().cudaHostRegister(a.ctypes.data, a.nbytes, 0)
-        h2d = ps.desc.nbytes + ps.bit_base.nbytes + ps.gap_base.nbytes + ps.bit_pool.nbytes + ps.gap_pool.nbytes + (g0.size + (g1.size if g1 is not None else 0)) * 4
-        d2h = n_cols * (1 + 4 + 8 + 4) + 8
-        bm.aggregate_host(ctx, ps, op, g0, g1, flags)        # warm-up
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            k2, p2, d2, n2, tot2 = bm.aggregate_host(ctx, ps, op, g0, g1, flags)
-        torch.cuda.synchronize(dev)
-        e_ms = (time.perf_counter() - t0) * 1e3 / args.e2e_steps
-        te = torch.tensor([e_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e_ms = float(te.item())
-        assert tot2 == total_bits and np.array_equal(p2, pop_r), "e2e result differs from the device-resident run"
-        e2e = {"value": float(src_blocks_all.item()) / (e_ms * 1e-3), "unit": "blocks/s", "ms_per_step": e_ms,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "h2d_gbs": h2d / e_ms / 1e6}
-        for a in (ps.desc, ps.bit_base, ps.gap_base, ps.bit_pool, ps.gap_pool):
-            if a.size:
-                torch.cuda.cudart().cudaHostUnregister(a.ctypes.data)
-        del ps
+        e2e = run_e2e(args, ctx, dset, local, world, dist, torch, op, g0, g1, flags, total_bits, src_blocks_all)
 
-    # ---- CPU baseline (rank 0, N=1 only): the reference on a bounded sample of the same workload ----
-    cpu = None
+    # ---- CPU baseline rows (rank 0): 1 thread on a bounded sample; all cores = the parity run above (whole workload) ----
     if rank == 0 and world == 1 and not args.no_cpu:
         import orclib
         ncs = min(args.cpu_cols, n_cols)
         ps_s = dset.download(0, ncs)
         src_s = int((ps_s.kinds() != 0).sum())
+        os.sched_setaffinity(0, all_cpus)
         if orclib.have_ref():
-            sec, tot = orclib.ref_time_aggregate(ps_s, op, g0, g1, flags, threads=1, repeats=2)
+            job = orclib.RefJob(ps_s, op, g0, g1, flags, threads=1)
+            job.run(1)
+            sec, tot = job.run(3)
+            sec = float(np.min(sec)); job.free()
             kind_c, simd = "reference", orclib.ref().ref_simd().decode()
         else:
             t0 = time.perf_counter(); o = orclib.oracle_aggregate(ps_s, op, g0, g1, flags); sec = time.perf_counter() - t0
             tot = int(o[1].sum()); kind_c, simd = "port", "scalar"
         assert tot == int(pop_r[:ncs].sum()), "CPU baseline and GPU disagree on the sampled columns"
-        cpu = {"value": src_s / sec, "unit": "blocks/s", "cores": 1, "kind": kind_c, "simd": simd,
-               "sample": f"first {ncs} of {n_cols} block columns x {w['n_vec']} vectors ({ps_s.stored_bytes() / 2**20:.0f} MiB), {sec * 1e3:.0f} ms",
+        cpu = {"value": src_s / sec, "unit": "blocks/s", "cores": 1, "kind": kind_c, "simd": simd, "nproc": os.cpu_count(), "cpu": cpu_model(),
+               "sample": f"first {ncs} of {n_cols} block columns x {w['n_vec']} vectors ({ps_s.stored_bytes() / 2**20:.0f} MiB), {sec * 1e3:.0f} ms, bvectors built before the clock starts",
                "gbs": ps_s.stored_bytes() / sec / 1e9, "checked_equal_popcount": True}
+        if parity and "ref_ms" in parity:
+            cpu["all_cores"] = {"value": n_src_blocks / (parity["ref_ms"] * 1e-3), "unit": "blocks/s", "cores": parity["ref_threads"],
+                                "ms": parity["ref_ms"], "sample": "the whole workload (the parity run)"}
+
+    # ---- config 5 rides along on 8-GPU runs: each rank's shard IS configs[4] (4096 x 2^32 bits over 8 GPUs) ----
+    c5 = None
+    if world == 8 and args.workload == "c3" and not args.no_c5:
+        dset.free(); res.free()
+        w5 = WORKLOADS["c5"]
+        d5, s5, o5 = workload_inputs("c5", rank)
+        op5, g05, g15, f5 = workload_groups("c5")
+        ds5 = bm.DeviceSet.synth(ctx, w5["n_vec"], w5["n_blocks"], d5, s5, o5)
+        ctx.sync()
+        cnt5, gw5 = device_set_stats(ctx, ds5, torch)
+        a5 = argparse.Namespace(**vars(args)); a5.steps = min(args.steps, 10)
+        r5, ms5, k5, _, _ = timed_resident(a5, bm, torch, ctx, ds5, op5, g05, g15, f5, world, dist, dev, stream, w5["n_blocks"], rank, sample_clocks=False)
+        kk, pp, dd, nn = r5.meta()
+        rb5 = int((kk == bm.BLK_BIT).sum()) * 8192 + int(2 * (nn[kk == bm.BLK_GAP].astype(np.int64) + 1).sum())
+        alg5 = cnt5["bit"] * 8192 + gw5 * 2 + rb5 + w5["n_blocks"] * 12
+        nb5 = torch.tensor([cnt5["bit"] + cnt5["gap"] + cnt5["full"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(nb5)
+        g5, _, _ = ctx.exchange_fetch(world, w5["n_blocks"], want_popcounts=False)
+        peak, _ = measured_peak_gbs()
+        c5 = {"workload": "c5: " + w5["desc"], "n_gpus": world, "steps": a5.steps, "ms_per_step": ms5, "value": float(nb5.item()) / (ms5 * 1e-3), "unit": "blocks/s",
+              "kernel_ms": k5, "algorithmic_bytes_per_gpu": int(alg5), "gbs_per_gpu": alg5 / (k5 * 1e-3) / 1e9, "frac_of_peak": alg5 / (k5 * 1e-3) / 1e9 / peak,
+              "global_result_bits": int(g5)}
+        r5.free(); ds5.free()
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        reduced = bool(args.cols and args.cols != w["n_blocks"])
+        traffic, traffic_src = (None, None) if reduced else profiled_traffic(args.workload)
         line = {
             "metric": "aggregator input 64Kbit-blocks/s", "value": value, "unit": "blocks/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": args.workload + ": " + w["desc"], "n_vec": w["n_vec"], "block_columns_per_gpu": n_cols,
-                       "reduced": bool(args.cols and args.cols != w["n_blocks"]),
+                       "reduced": reduced,
                        "l2": f"inputs ({alg_bytes / 2**30:.2f} GiB per GPU) larger than the 126 MB L2; no flush needed",
-                       "parallelism": f"block-range sharded x{world}", "source_blocks": counts, "synth_s": round(t_synth, 2)},
+                       "parallelism": f"block-range sharded x{world}", "source_blocks": counts, "synth_s": round(t_synth, 2),
+                       "exchange": exchange, "numa_node": numa_node},
             "gbs_per_gpu": alg_bytes / (ms_per_step * 1e-3) / 1e9,
             "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps),
             "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None if (args.cols and args.cols != w["n_blocks"]) else profiled_traffic(args.workload),
-                         "traffic_source": "profiles/r01/ncu_agg_kernel.json (ncu --set full, same command, full-size shard)",
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "agg_kernel<%s>" % w["op"], "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "peak_source": peak_src},
             "cpu_baseline": cpu,
+            "parity": parity,
             "result_bits": int(total_bits),
         }
+        if xchg:
+            line["exchange"] = xchg
+        if c5:
+            line["c5"] = c5
     else:
         line = None
     if world > 1:
+        ctx.comm_destroy()
         dist.destroy_process_group()
     return line
 

@@ -35,8 +35,12 @@ SYMBOLS = [
     "bmb200_result_free", "bmb200_aggregate_host", "bmb200_rs_build", "bmb200_rs_export", "bmb200_rs_total",
     "bmb200_rank_batch", "bmb200_select_batch", "bmb200_rank_batch_dev", "bmb200_select_batch_dev",
     "bmb200_rs_free", "bmb200_rs_rebuild", "bmb200_aggregate_batch", "bmb200_result_group_totals", "bmb200_result_or_target",
-    "bmb200_scan", "bmb200_set_upload_blobs",
+    "bmb200_scan", "bmb200_set_upload_blobs", "bmb200_result_fetch_view", "bmb200_ctx_bind_host_numa",
+    "bmb200_shard_range", "bmb200_comm_unique_id", "bmb200_comm_init", "bmb200_comm_info", "bmb200_comm_destroy",
+    "bmb200_exchange_popcounts", "bmb200_exchange_fence", "bmb200_exchange_fetch",
 ]
+COMM_ID_BYTES = 128
+TUNE_GAP_MODE, TUNE_CTAS_PER_SM, TUNE_HOST_THREADS = 0, 1, 2
 
 
 class PackedSetC(C.Structure):
@@ -179,6 +183,41 @@ class Context:
         n = C.c_uint64(0)
         self.check(lib().bmb200_ctx_launch_count(self._h, C.byref(n)), "launch_count")
         return int(n.value)
+
+    def bind_host_numa(self) -> int:
+        """Pin the calling thread to the CPUs of this GPU's NUMA node (bmb200_ctx_bind_host_numa); -> node or -1."""
+        node = C.c_int(-1)
+        self.check(lib().bmb200_ctx_bind_host_numa(self._h, C.byref(node)), "ctx_bind_host_numa")
+        return node.value
+
+    # ---- multi-GPU exchange (one process per GPU): see include/bmb200.h "multi-GPU" ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        rc = lib().bmb200_comm_unique_id(buf)
+        if rc != OK:
+            raise BMB200Error(rc, "comm_unique_id")
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, comm_id: bytes):
+        assert len(comm_id) == COMM_ID_BYTES
+        self.check(lib().bmb200_comm_init(self._h, int(nranks), int(rank), C.c_char_p(comm_id)), "comm_init")
+
+    def comm_destroy(self):
+        self.check(lib().bmb200_comm_destroy(self._h), "comm_destroy")
+
+    def exchange_popcounts(self, res: "DeviceResult", cols_per_rank: int = 0):
+        self.check(lib().bmb200_exchange_popcounts(res._h, int(cols_per_rank)), "exchange_popcounts")
+
+    def exchange_fence(self):
+        self.check(lib().bmb200_exchange_fence(self._h), "exchange_fence")
+
+    def exchange_fetch(self, nranks: int, cols_per_rank: int, want_popcounts: bool = True):
+        """-> (global cardinality, per-rank cardinalities [nranks], per-column popcounts [nranks, cols_per_rank] or None)"""
+        tot = C.c_uint64(0); rt = np.zeros(nranks, np.uint64)
+        pop = np.zeros((nranks, cols_per_rank), np.uint32) if want_popcounts else None
+        self.check(lib().bmb200_exchange_fetch(self._h, C.byref(tot), ptr(rt), ptr(pop), None, None), "exchange_fetch")
+        return tot.value, rt, pop
 
     def device_info(self) -> dict:
         sm, ma, mi, hbm = C.c_int(0), C.c_int(0), C.c_int(0), C.c_uint64(0)

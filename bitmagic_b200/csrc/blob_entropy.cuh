@@ -63,6 +63,25 @@ struct BlobTok {
     uint32_t kind;       // BMB200_BLK_BIT / BMB200_BLK_GAP
 };
 
+// set_block_arrgap(_inv): n ascending u16 positions at p (byte aligned).  A well-formed token has strictly ascending positions and the
+// GAP block gap_set_array builds from them fits the largest GAP capacity; anything else (crafted / corrupt streams: up to 2n+1 runs
+// for n <= 2048 isolated bits) is refused instead of being written past its arena slot.  Returns the u16 words the block needs
+// (header + run ends), or 0 for a malformed / oversized list.
+BME_HDN inline uint32_t arrgap_measure(const uint8_t* p, uint32_t n)
+{
+    uint32_t ends = 0, prev = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint32_t s = (uint32_t)p[2u * k] | ((uint32_t)p[2u * k + 1u] << 8);
+        if (k && s <= prev) return 0u;
+        const bool st = (k == 0u) || prev + 1u != s;
+        if (st) { if (k && prev < 65535u) ++ends; if (s > 0u) ++ends; }      // close the previous 1-run, open this one
+        prev = s;
+    }
+    if (n && prev < 65535u) ++ends;
+    const uint32_t words = ends + 2u;                                          // header + ends + the final 65535
+    return words - 1u <= kGapFitWords ? words : 0u;      // longer lists are bit-blocks in the reference (gap_calc_level < 0); no serializer writes them
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // lane helpers: on the device a "team" is one warp; on the host the same code runs with one lane
 // ------------------------------------------------------------------------------------------------------------------
@@ -770,7 +789,9 @@ BME_HDN int ent_walk_segment(const EntCtx& c, const uint8_t* stg, const EntSeg& 
                        const uint32_t first_pos = (uint32_t)stg[a0] | ((uint32_t)stg[a0 + 1] << 8);
                        t.type = bt == 18 ? 8u : 9u /*DB_ARRGAP(_INV)*/; t.kind = BMB200_BLK_GAP; t.aux = n; t.off = a0 - blob_off;
                        t.first = (uint32_t)(first_pos == 0u) ^ (uint32_t)(bt == 24);
-                       t.gap_words = (2u * n + 2u < BMB200_GAP_MAX_WORDS) ? 2u * n + 2u : BMB200_GAP_MAX_WORDS; blk = true; break; }
+                       t.gap_words = arrgap_measure(stg + a0, n);
+                       if (!t.gap_words) { act = 5; code = BMB200_ERR_BADARG; break; }
+                       blk = true; break; }
             case 67: {                                   // plain 16-bit run ends -> explicit token, gamma-coded -> entropy token
                        const uint64_t w0 = rd.p; EntBits pb; pb.init(&rd);
                        const uint32_t len = pb.gamma() + 1u, start = pb.bit(), use_gamma = pb.bit();

@@ -28,7 +28,7 @@ struct BlobRec {
     uint64_t dst;        // bit kinds: block index in bit_pool; GAP kinds: absolute 16-byte unit in gap_pool
     uint32_t type;       // DB_*
     uint32_t aux;        // DB_GAP_V3: bit offset of the first run end | len << 8 ... see capi.cu; DB_ARRGAP*: element count (1bit: 1)
-    uint32_t aux2;       // GAP kinds: bit 0 = lead pad, bit 1 = first-run value
+    uint32_t aux2;       // GAP kinds: bit 0 = lead pad, bit 1 = first-run value; explicit-length GAP tokens: u16 words of the arena slot << 8
     uint32_t kind;       // entropy-coded tokens (blob_entropy.cuh): BMB200_BLK_BIT / BMB200_BLK_GAP of the decoded block
 };
 
@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(kBlobThreads) blob_decode_kernel(const uint8_t
             uint32_t woff = 0, total = 0;
             for (int w = 0; w < kBlobThreads / 32; ++w) { const uint32_t t = s_scan[w]; if (w < warp) woff += t; total += t; }
             uint32_t pos = 1u + woff + inc - cnt;
+            if (total + 2u > (r.aux2 >> 8)) continue;        // never write past the slot the walker measured (uniform; the walkers reject such lists)
             for (uint32_t k = tid * kPer; k < min(n, (tid + 1) * kPer); ++k) {
                 const uint32_t s = a[k];
                 const bool st = (k == 0) || (uint32_t)a[k - 1] + 1u != s, en = (k + 1 == n) || s + 1u != (uint32_t)a[k + 1];

@@ -18,6 +18,10 @@
 #include <cstdlib>
 #include "blob_kernel.cuh"
 #include "blob_entropy.cuh"
+#include "host_pack.hpp"
+#include "comm.hpp"
+#include <sched.h>
+#include <fstream>
 
 using namespace bmb200;
 
@@ -44,6 +48,15 @@ struct bmb200_ctx {
     size_t d_tmp_cap[13] = {};              //   between calls, grown on demand -- cudaMalloc / cudaFree of a few hundred MB costs tens of ms each
     int gap_mode = 0;                       // 0 = stream sorted GAP lists through the smem ring, 1 = always gather
     bool attr_set = false;
+    int host_threads = 0;                   // host threads of bmb200_set_upload_vectors (0 = hardware concurrency, at most 64)
+    uint8_t* h_ring[kStageSlots] = {};      // pinned staging ring of bmb200_set_upload_vectors (grow-only)
+    size_t h_ring_cap = 0;
+    cudaEvent_t ring_ev[kStageSlots] = {};
+    void* d_pool[6] = {};                   // grow-only device scratch of the fetch / rank / select entry points (no cudaMalloc per call)
+    size_t d_pool_cap[6] = {};
+    void* h_pool[5] = {};                   // grow-only pinned scratch of the same entry points
+    size_t h_pool_cap[5] = {};
+    CommState comm;                         // multi-GPU exchange (bmb200_comm_*), unused on one GPU
 };
 
 struct bmb200_set {
@@ -143,6 +156,47 @@ void free_result_arrays(bmb200_result* r)
     cudaFree(r->kind); cudaFree(r->gaps); cudaFree(r->total); cudaFree(r->or_blocks);
 }
 
+// grow-only scratch owned by the context: the hot entry points never call cudaMalloc / cudaMallocHost once warm.
+// The caller has synchronized (or is ordered on) the context stream before it reuses a slot.
+int pool_dev(bmb200_ctx* ctx, int slot, size_t bytes, void** out)
+{
+    if (bytes > ctx->d_pool_cap[slot]) {
+        if (ctx->d_pool[slot]) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->d_pool[slot]); ctx->d_pool[slot] = nullptr; ctx->d_pool_cap[slot] = 0; }
+        const size_t cap = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&ctx->d_pool[slot], cap);
+        if (e != cudaSuccess) { ctx->last_err = std::string("cudaMalloc(pool): ") + cudaGetErrorString(e); return e == cudaErrorMemoryAllocation ? BMB200_ERR_BADALLOC : BMB200_ERR_CUDA; }
+        ctx->d_pool_cap[slot] = cap;
+    }
+    *out = ctx->d_pool[slot];
+    return BMB200_OK;
+}
+int pool_host(bmb200_ctx* ctx, int slot, size_t bytes, void** out)
+{
+    if (bytes > ctx->h_pool_cap[slot]) {
+        if (ctx->h_pool[slot]) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->h_pool[slot]); ctx->h_pool[slot] = nullptr; ctx->h_pool_cap[slot] = 0; }
+        const size_t cap = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&ctx->h_pool[slot], cap);
+        if (e != cudaSuccess) { ctx->last_err = std::string("cudaMallocHost(pool): ") + cudaGetErrorString(e); return BMB200_ERR_BADALLOC; }
+        ctx->h_pool_cap[slot] = cap;
+    }
+    *out = ctx->h_pool[slot];
+    return BMB200_OK;
+}
+
+void comm_release(bmb200_ctx* ctx)
+{
+    CommState& c = ctx->comm;
+    if (c.side) cudaStreamSynchronize(c.side);
+    for (int k = 0; k < 2; ++k) {
+        if (c.ready[k]) cudaEventDestroy(c.ready[k]);
+        if (c.done[k]) cudaEventDestroy(c.done[k]);
+        cudaFree(c.stage[k]); cudaFree(c.gathered[k]);
+    }
+    if (c.comm && nccl_api().CommDestroy) nccl_api().CommDestroy(c.comm);
+    if (c.side) cudaStreamDestroy(c.side);
+    c = CommState();
+}
+
 }  // namespace
 
 extern "C" {
@@ -184,10 +238,13 @@ int bmb200_init(int device, bmb200_ctx** out)
         delete ctx; return BMB200_ERR_CUDA;
     }
     ctx->own_stream = true;
+    // environment overrides go through the same checks as bmb200_ctx_set_tuning (out-of-range values are ignored)
     const char* e = getenv("BMB200_AGG_CTAS_PER_SM");
-    if (e && atoi(e) > 0) ctx->agg_ctas_per_sm = atoi(e);
+    if (e) bmb200_ctx_set_tuning(ctx, BMB200_TUNE_CTAS_PER_SM, atoi(e));
     e = getenv("BMB200_GAP_MODE");
-    if (e) ctx->gap_mode = atoi(e);
+    if (e) bmb200_ctx_set_tuning(ctx, BMB200_TUNE_GAP_MODE, atoi(e));
+    e = getenv("BMB200_HOST_THREADS");
+    if (e) bmb200_ctx_set_tuning(ctx, BMB200_TUNE_HOST_THREADS, atoi(e));
     *out = ctx;
     return BMB200_OK;
 }
@@ -204,6 +261,10 @@ int bmb200_destroy(bmb200_ctx* ctx)
     if (ctx->h_group) cudaFreeHost(ctx->h_group);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (void* q : ctx->d_tmp) if (q) cudaFree(q);
+    for (void* q : ctx->d_pool) if (q) cudaFree(q);
+    for (void* q : ctx->h_pool) if (q) cudaFreeHost(q);
+    for (uint32_t k = 0; k < kStageSlots; ++k) { if (ctx->h_ring[k]) cudaFreeHost(ctx->h_ring[k]); if (ctx->ring_ev[k]) cudaEventDestroy(ctx->ring_ev[k]); }
+    comm_release(ctx);
     delete ctx;
     return BMB200_OK;
 }
@@ -262,6 +323,7 @@ int bmb200_ctx_set_tuning(bmb200_ctx* ctx, int key, int value)
     if (!ctx) return BMB200_ERR_BADARG;
     if (key == BMB200_TUNE_GAP_MODE && (value == 0 || value == 1)) { ctx->gap_mode = value; return BMB200_OK; }
     if (key == BMB200_TUNE_CTAS_PER_SM && value >= 1 && value <= kCtasPerSm) { ctx->agg_ctas_per_sm = value; return BMB200_OK; }
+    if (key == BMB200_TUNE_HOST_THREADS && value >= 0 && value <= 64) { ctx->host_threads = value; return BMB200_OK; }
     return BMB200_ERR_BADARG;
 }
 
@@ -327,56 +389,79 @@ int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks
     if (!ctx || !vecs || !out || !n_vec || !n_blocks) return BMB200_ERR_BADARG;
     for (uint32_t v = 0; v < n_vec; ++v)
         if (vecs[v].n_blocks > n_blocks || (vecs[v].n_blocks && (!vecs[v].kind || !vecs[v].ptr))) return BMB200_ERR_BADARG;
-    // host-side gather of the block tree into the packed column-major layout (the block manager stays on the host)
-    const bool legacy = getenv("BMB200_GAP_LEGACY") != nullptr;     // experiments only: raw GAP blocks, no FLAT form
-    std::vector<uint32_t> desc; std::vector<uint64_t> bb, gb;
-    try { desc.assign((size_t)n_vec * n_blocks, 0u); bb.assign((size_t)n_blocks + 1, 0); gb.assign((size_t)n_blocks + 1, 0); }
-    catch (...) { return BMB200_ERR_BADALLOC; }
-    for (uint32_t nb = 0; nb < n_blocks; ++nb) {
-        uint64_t nbit = 0, ngap = 0;
-        for (uint32_t v = 0; v < n_vec; ++v) {
-            uint32_t kd = (nb < vecs[v].n_blocks) ? vecs[v].kind[nb] : BMB200_BLK_NULL;
-            uint32_t rel = 0;
-            if (kd == BMB200_BLK_BIT) rel = (uint32_t)nbit++;
-            else if (kd == BMB200_BLK_GAP) {
-                const uint16_t* g = (const uint16_t*)vecs[v].ptr[nb];
-                if (!g) return BMB200_ERR_BADARG;
-                uint32_t words = (uint32_t)(g[0] >> 3) + 1u;
-                if (words > kGapMax) return BMB200_ERR_BADARG;
-                // flat-streamable form (BMB200_DESC_GAP_FLAT): lead pad iff the first run is 0; BMB200_GAP_LEGACY=1 keeps the raw form
-                const uint32_t pad = (!legacy && !(g[0] & 1u)) ? 1u : 0u;
-                if (ngap + (words + pad + kGapUnit - 1) / kGapUnit > (uint64_t)BMB200_DESC_REL_MASK) return BMB200_ERR_RANGE;
-                rel = (uint32_t)ngap | (pad << 29) | (legacy ? 0u : (BMB200_DESC_GAP_FLAT >> 2)); ngap += (words + pad + kGapUnit - 1) / kGapUnit;
-            } else if (kd > 3u) return BMB200_ERR_BADARG;
-            desc[(size_t)nb * n_vec + v] = kd | (rel << 2);
-        }
-        bb[nb + 1] = bb[nb] + nbit; gb[nb + 1] = gb[nb] + ngap;
-    }
-    const uint64_t n_bit = bb[n_blocks], n_gap = gb[n_blocks];
+    // the block manager stays on the host: its blocks are gathered into the packed column-major layout by a team of host threads
+    // (host_pack.hpp) and streamed through a ring of pinned slots -- packing of chunk c+1 overlaps the DMA of chunk c
+    PhaseTrace tr("set_upload_vectors", ctx->stream);
+    PackLayout L;
+    std::vector<PackChunk> chunks;
+    try {
+        pack_layout(n_vec, n_blocks, vecs, (unsigned)ctx->host_threads, L);
+        if (L.rc) return L.rc;
+    } catch (...) { return BMB200_ERR_BADALLOC; }
+    tr.mark("layout (descriptors, prefix sums)");
+    const uint64_t n_bit = L.bb[n_blocks], n_gap = L.gb[n_blocks];
+    const uint64_t total = n_bit * (uint64_t)BMB200_BLOCK_BYTES + n_gap * 16ull;
     CU(cudaSetDevice(ctx->device));
-    uint32_t* hb = nullptr; uint16_t* hg = nullptr;
-    if (n_bit) CU(cudaMallocHost((void**)&hb, (size_t)n_bit * BMB200_BLOCK_BYTES));
-    if (n_gap) { cudaError_t e = cudaMallocHost((void**)&hg, (size_t)n_gap * kGapUnit * 2);
-                 if (e != cudaSuccess) { if (hb) cudaFreeHost(hb); ctx->last_err = "cudaMallocHost"; return BMB200_ERR_BADALLOC; } }
-    if (hg) memset(hg, 0, (size_t)n_gap * kGapUnit * 2);
-    for (uint32_t nb = 0; nb < n_blocks; ++nb)
-        for (uint32_t v = 0; v < n_vec; ++v) {
-            const uint32_t d = desc[(size_t)nb * n_vec + v], kd = d & 3u, rel = d >> 2;
-            if (kd == BMB200_BLK_BIT)
-                memcpy(hb + (bb[nb] + rel) * (size_t)kBlockWords, vecs[v].ptr[nb], BMB200_BLOCK_BYTES);
-            else if (kd == BMB200_BLK_GAP) {
-                const uint16_t* g = (const uint16_t*)vecs[v].ptr[nb];
-                uint16_t* dst = hg + (gb[nb] + (rel & BMB200_DESC_REL_MASK)) * (size_t)kGapUnit;
-                if (rel >> 29) dst[0] = 0xffffu;
-                memcpy(dst + (rel >> 29), g, ((size_t)(g[0] >> 3) + 1) * 2);
+    cudaStream_t st = ctx->stream;
+    bmb200_set* s = nullptr;
+    int rc = set_alloc(ctx, n_vec, n_blocks, n_bit, n_gap, &s);
+    if (rc) return rc;
+    auto fail = [&](int code, cudaError_t e) {
+        cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { ctx->last_err = std::string("set_upload_vectors: ") + cudaGetErrorString(e); code = BMB200_ERR_CUDA; }
+        free_set_arrays(s); delete s;
+        return code;
+    };
+    cudaError_t e = cudaMemcpyAsync((void*)s->v.desc, L.desc.data(), L.desc.size() * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync((void*)s->v.bit_base, L.bb.data(), L.bb.size() * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync((void*)s->v.gap_base, L.gb.data(), L.gb.size() * 8, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
+    if (total) {
+        // slot size: 64 MB (PCIe runs at link speed from ~16 MB copies on), never less than the largest column, small sets get small slots
+        uint64_t slot_bytes;
+        try {
+            const uint64_t maxcol = pack_max_column_bytes(L, n_blocks);
+            slot_bytes = std::min<uint64_t>(64ull << 20, (total + kStageSlots - 1) / kStageSlots);
+            slot_bytes = std::max<uint64_t>(std::max<uint64_t>(slot_bytes, maxcol), 1ull << 16);
+            slot_bytes = (slot_bytes + 4095ull) & ~4095ull;
+            pack_chunks(L, n_blocks, slot_bytes, chunks);
+        } catch (...) { return fail(BMB200_ERR_BADALLOC, cudaSuccess); }
+        if (slot_bytes > ctx->h_ring_cap) {
+            cudaStreamSynchronize(st);
+            for (uint32_t k = 0; k < kStageSlots; ++k) { if (ctx->h_ring[k]) cudaFreeHost(ctx->h_ring[k]); ctx->h_ring[k] = nullptr; }
+            ctx->h_ring_cap = 0;
+            for (uint32_t k = 0; k < kStageSlots; ++k) {
+                e = cudaMallocHost((void**)&ctx->h_ring[k], slot_bytes);
+                if (e != cudaSuccess) return fail(BMB200_ERR_BADALLOC, cudaSuccess);
+                if (!ctx->ring_ev[k] && (e = cudaEventCreateWithFlags(&ctx->ring_ev[k], cudaEventDisableTiming)) != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
             }
+            ctx->h_ring_cap = slot_bytes;
         }
-    bmb200_packed_set h{n_vec, n_blocks, desc.data(), bb.data(), gb.data(), hb, hg};
-    int rc = bmb200_set_upload(ctx, &h, out);
-    cudaStreamSynchronize(ctx->stream);
-    if (hb) cudaFreeHost(hb);
-    if (hg) cudaFreeHost(hg);
-    return rc;
+        tr.mark("device arena + staging ring");
+        cudaStreamSynchronize(st);                  // a previous upload may still be reading the ring
+        try {
+            PackPipeline pipe(n_vec, n_blocks, vecs, &L, &chunks, ctx->h_ring);
+            pipe.start((unsigned)ctx->host_threads);
+            const uint32_t nch = (uint32_t)chunks.size();
+            for (uint32_t c = 0; c < nch && e == cudaSuccess; ++c) {
+                pipe.wait_chunk(c);
+                const PackChunk& ch = chunks[c];
+                uint8_t* base = ctx->h_ring[c % kStageSlots];
+                if (ch.bit_bytes) e = cudaMemcpyAsync((uint8_t*)s->v.bit_pool + L.bb[ch.c0] * (uint64_t)BMB200_BLOCK_BYTES, base, ch.bit_bytes, cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess && ch.gap_bytes) e = cudaMemcpyAsync((uint8_t*)s->v.gap_pool + L.gb[ch.c0] * 16ull, base + ch.bit_bytes, ch.gap_bytes, cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) e = cudaEventRecord(ctx->ring_ev[c % kStageSlots], st);
+                // the copy of chunk c is queued behind the one of chunk c-1: once c-1 has landed its slot goes back to the packers
+                if (e == cudaSuccess && c >= 1) { e = cudaEventSynchronize(ctx->ring_ev[(c - 1) % kStageSlots]); pipe.release_through(c); }
+            }
+            pipe.join();
+        } catch (...) { return fail(BMB200_ERR_BADALLOC, cudaSuccess); }
+        if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
+    }
+    e = cudaStreamSynchronize(st);                  // L.desc / the ring are host memory of this call
+    if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
+    tr.mark("pack + H2D (pipelined)");
+    *out = s;
+    return BMB200_OK;
 }
 
 /* ---- deserialize-to-device: host side = token walk only (type + payload extent of every block), no decoding ---- */
@@ -437,7 +522,8 @@ int walk_blob(const uint8_t* blob, uint64_t size, uint32_t n_blocks, std::vector
                    const uint64_t a0 = r.p; r.skip(2ull * n); if (r.bad) return BMB200_ERR_BADARG;
                    const uint32_t first_pos = blob[a0] | ((uint32_t)blob[a0 + 1] << 8);
                    t.type = bt == 18 ? DB_ARRGAP : DB_ARRGAP_INV; t.kind = BMB200_BLK_GAP; t.aux = n; t.off = a0;
-                   t.first = (first_pos == 0) ^ (bt == 24); t.gap_words = std::min<uint32_t>(2 * n + 2, BMB200_GAP_MAX_WORDS); break; }
+                   t.first = (first_pos == 0) ^ (bt == 24); t.gap_words = arrgap_measure(blob + a0, n);
+                   if (!t.gap_words) return BMB200_ERR_BADARG; break; }
         case 67: {   // set_block_gap_egamma_v3: bit stream of 32-bit words, LSB first: gamma(len-1), start bit, use_gamma bit, values
                    const uint64_t w0 = r.p; uint64_t acc = 0; uint32_t have = 0, used = 0, zeros = 0;
                    auto need = [&](uint32_t nbits) { while (have < nbits && !r.bad) { acc |= (uint64_t)r.u32() << have; have += 32; } };
@@ -506,7 +592,6 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
         *ptr = ctx->d_tmp[slot];
         return cudaSuccess;
     };
-    auto cleanup = [&]() {};
     auto fail = [&](int rc, cudaError_t e) {
         cudaStreamSynchronize(st);
         if (rc == BMB200_ERR_CUDA || (!rc && e != cudaSuccess)) { ctx->last_err = std::string("set_upload_blobs: ") + cudaGetErrorString(e); rc = BMB200_ERR_CUDA; }
@@ -629,7 +714,7 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
                         const uint64_t units = (t.gap_words + pad + kGapUnit - 1) / kGapUnit;
                         if (ngap + units > (uint64_t)BMB200_DESC_REL_MASK) return fail(BMB200_ERR_RANGE, cudaSuccess);
                         d = BMB200_BLK_GAP | ((uint32_t)ngap << 2) | (pad ? BMB200_DESC_GAP_PAD : 0u) | BMB200_DESC_GAP_FLAT;
-                        r.dst = gb[nb] + ngap; r.aux2 = pad | (t.first << 1); ngap += units;
+                        r.dst = gb[nb] + ngap; r.aux2 = pad | (t.first << 1) | (entropy ? 0u : t.gap_words << 8); ngap += units;
                     } else return fail(BMB200_ERR_BADARG, cudaSuccess);
                     if (entropy) {      // payload length (to the next record of the vector, or the end of the BLOB): the work estimate pass 2 is sorted by
                         const uint64_t nxt = cur[v] < toks[v].size() ? toks[v][cur[v]].off : blob_size[v];
@@ -695,8 +780,6 @@ int bmb200_set_upload_blobs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, 
     if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
     if (ent_status) return fail(ent_status, cudaSuccess);
     tr.mark("blob_entropy_kernel + sync");
-    cleanup();
-    tr.mark("free temporaries");
     *out = s;
     return BMB200_OK;
 }
@@ -823,18 +906,20 @@ int bmb200_synth_set(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks,
         (rc = dev_alloc(ctx, &gb, (size_t)n_blocks + 1))) {
         cleanup_tmp(); cudaFree(desc); cudaFree(bb); cudaFree(gb); return rc;
     }
-    cudaMemcpyAsync(d_seed, seed, n_vec * 8, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(d_thr, thr.data(), n_vec * 4, cudaMemcpyHostToDevice, st);
-    synth_classify_kernel<<<(unsigned)items, kPostThreads, 0, st>>>(n_vec, n_blocks, d_seed, d_thr, optimize, d_kind, d_glen);
-    if ((rc = after_launch(ctx))) { cleanup_tmp(); cudaFree(desc); cudaFree(bb); cudaFree(gb); return rc; }
-    synth_layout_kernel<<<n_blocks, 256, 0, st>>>(n_vec, getenv("BMB200_GAP_LEGACY") ? 0u : 1u, d_kind, d_glen, desc, d_cb, d_cg);
-    after_launch(ctx);
-    scan_u64_kernel<<<1, 1024, 0, st>>>(d_cb, n_blocks, bb); after_launch(ctx);
-    scan_u64_kernel<<<1, 1024, 0, st>>>(d_cg, n_blocks, gb); after_launch(ctx);
+    cudaError_t e = cudaMemcpyAsync(d_seed, seed, n_vec * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_thr, thr.data(), n_vec * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        synth_classify_kernel<<<(unsigned)items, kPostThreads, 0, st>>>(n_vec, n_blocks, d_seed, d_thr, optimize, d_kind, d_glen);
+        rc = after_launch(ctx);
+        if (!rc) { synth_layout_kernel<<<n_blocks, 256, 0, st>>>(n_vec, 1u, d_kind, d_glen, desc, d_cb, d_cg); rc = after_launch(ctx); }
+        if (!rc) { scan_u64_kernel<<<1, 1024, 0, st>>>(d_cb, n_blocks, bb); rc = after_launch(ctx); }
+        if (!rc) { scan_u64_kernel<<<1, 1024, 0, st>>>(d_cg, n_blocks, gb); rc = after_launch(ctx); }
+    }
+    if (rc) { cleanup_tmp(); cudaFree(desc); cudaFree(bb); cudaFree(gb); return rc; }
     uint64_t tails[2] = {0, 0};
-    cudaMemcpyAsync(&tails[0], bb + n_blocks, 8, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(&tails[1], gb + n_blocks, 8, cudaMemcpyDeviceToHost, st);
-    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&tails[0], bb + n_blocks, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&tails[1], gb + n_blocks, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { ctx->last_err = std::string("synth: ") + cudaGetErrorString(e); cleanup_tmp(); cudaFree(desc); cudaFree(bb); cudaFree(gb); return BMB200_ERR_CUDA; }
     uint32_t* bp = nullptr; uint16_t* gp = nullptr;
     if ((rc = dev_alloc(ctx, &bp, (size_t)tails[0] * kBlockWords, kSlack)) ||
@@ -943,12 +1028,21 @@ int bmb200_aggregate_batch(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_
         cudaStreamSynchronize(ctx->stream);    // the staging buffer may still feed a previous launch
         if (nmem) memcpy(ctx->h_group, a->members, nmem * 4);
         memcpy(ctx->h_group + nmem, a->offsets, (2 * (size_t)ng + 1) * 4);
-        CU(cudaMemcpyAsync(ctx->d_group, ctx->h_group, nwords * 4, cudaMemcpyHostToDevice, ctx->stream));
-        try { ctx->last_group.assign(ctx->h_group, ctx->h_group + nwords); } catch (...) { ctx->last_group.clear(); }
+        ctx->last_group.clear();
     }
-    CU(cudaMemsetAsync(ctx->d_work, 0, 4, ctx->stream));
-    CU(cudaMemsetAsync(r->total, 0, 8 * (size_t)ng, ctx->stream));
-    if (or_target) CU(cudaMemsetAsync(r->or_blocks, 0, (size_t)cols * BMB200_BLOCK_BYTES, ctx->stream));
+    {   // a freshly allocated result must not leak when one of these fails
+        cudaError_t ce = cudaSuccess;
+        if (!same) ce = cudaMemcpyAsync(ctx->d_group, ctx->h_group, nwords * 4, cudaMemcpyHostToDevice, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaMemsetAsync(ctx->d_work, 0, 4, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaMemsetAsync(r->total, 0, 8 * (size_t)ng, ctx->stream);
+        if (ce == cudaSuccess && or_target) ce = cudaMemsetAsync(r->or_blocks, 0, (size_t)cols * BMB200_BLOCK_BYTES, ctx->stream);
+        if (ce != cudaSuccess) {
+            ctx->last_err = std::string("aggregate: ") + cudaGetErrorString(ce);
+            if (!*inout) bmb200_result_free(r);
+            return BMB200_ERR_CUDA;
+        }
+        if (!same) { try { ctx->last_group.assign(ctx->h_group, ctx->h_group + nwords); } catch (...) { ctx->last_group.clear(); } }
+    }
 
     AggParams p{};
     p.set = set->v; p.group = ctx->d_group; p.goff = ctx->d_group + nmem; p.n_groups = ng;
@@ -1080,7 +1174,7 @@ int bmb200_result_or_target(bmb200_result* r, bmb200_result** out)
     int rc = result_alloc(ctx, r->cols_per_group, 1u, true, r->compress, false, &o);
     if (rc) return rc;
     o->has_blocks = true; o->compress = r->compress; o->gaps_ready = r->compress;
-    CU(cudaMemsetAsync(o->total, 0, 8, ctx->stream));
+    if (cudaMemsetAsync(o->total, 0, 8, ctx->stream) != cudaSuccess) { ctx->last_err = "result_or_target: memset"; bmb200_result_free(o); return BMB200_ERR_CUDA; }
     AggParams p{};
     p.n_groups = 1; p.n_cols = r->cols_per_group; p.compress = r->compress ? 1u : 0u; p.store_blocks = 1u;
     p.blocks = o->blocks; p.popcnt = o->popcnt; p.digest = o->digest; p.nruns = o->nruns; p.kind = o->kind; p.gaps = o->gaps;
@@ -1176,20 +1270,62 @@ int bmb200_result_fetch(bmb200_result* r, uint8_t* kind_out, uint64_t* off_out, 
     memcpy(kind_out, kind.data(), r->n_cols);
     memcpy(off_out, off.data(), (size_t)r->n_cols * 8);
     if (!nb && !ng) return BMB200_OK;
-    uint64_t* d_off = nullptr; uint32_t* d_bits = nullptr; uint16_t* d_gaps = nullptr;
-    if ((rc = dev_alloc(ctx, &d_off, r->n_cols)) || (rc = dev_alloc(ctx, &d_bits, (size_t)nb * kBlockWords)) ||
-        (rc = dev_alloc(ctx, &d_gaps, (size_t)ng))) { cudaFree(d_off); cudaFree(d_bits); cudaFree(d_gaps); return rc; }
-    cudaMemcpyAsync(d_off, off.data(), (size_t)r->n_cols * 8, cudaMemcpyHostToDevice, ctx->stream);
+    // compaction scratch and the offsets' staging come from the context's grow-only pools (no allocation once warm)
+    uint64_t* d_off = nullptr; uint32_t* d_bits = nullptr; uint16_t* d_gaps = nullptr; uint64_t* h_off = nullptr;
+    if ((rc = pool_dev(ctx, 0, (size_t)r->n_cols * 8, (void**)&d_off)) || (rc = pool_dev(ctx, 1, (size_t)nb * BMB200_BLOCK_BYTES + 16, (void**)&d_bits)) ||
+        (rc = pool_dev(ctx, 2, (size_t)ng * 2 + 16, (void**)&d_gaps)) || (rc = pool_host(ctx, 0, (size_t)r->n_cols * 8, (void**)&h_off))) return rc;
+    memcpy(h_off, off.data(), (size_t)r->n_cols * 8);
+    CU(cudaMemcpyAsync(d_off, h_off, (size_t)r->n_cols * 8, cudaMemcpyHostToDevice, ctx->stream));
     uint32_t grid = (uint32_t)ctx->sm_count * 8u; if (grid > r->n_cols) grid = r->n_cols;
     result_compact_kernel<<<grid, 256, 0, ctx->stream>>>(r->blocks, r->gaps, r->kind, d_off, d_bits, d_gaps, r->n_cols);
-    rc = after_launch(ctx);
-    cudaError_t e = cudaSuccess;
-    if (!rc && nb) e = cudaMemcpyAsync(bits, d_bits, (size_t)nb * BMB200_BLOCK_BYTES, cudaMemcpyDeviceToHost, ctx->stream);
-    if (!rc && e == cudaSuccess && ng) e = cudaMemcpyAsync(gaps, d_gaps, (size_t)ng * 2, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_off); cudaFree(d_bits); cudaFree(d_gaps);
+    if ((rc = after_launch(ctx))) return rc;
+    if (nb) CU(cudaMemcpyAsync(bits, d_bits, (size_t)nb * BMB200_BLOCK_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ng) CU(cudaMemcpyAsync(gaps, d_gaps, (size_t)ng * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BMB200_OK;
+}
+
+int bmb200_result_fetch_view(bmb200_result* r, const uint8_t** kind_out, const uint64_t** off_out, const uint32_t** bits_out,
+                             const uint16_t** gaps_out, uint64_t* n_bit_blocks, uint64_t* n_gap_words, uint64_t* total_out)
+{
+    if (!r || !r->has_blocks || !kind_out || !off_out || !bits_out || !gaps_out) return BMB200_ERR_BADARG;
+    bmb200_ctx* ctx = r->ctx;
+    if (r->compress && !r->gaps_ready) { int rc0 = bmb200_result_optimize(r); if (rc0) return rc0; }
+    CU(cudaSetDevice(ctx->device));
+    // one pinned block of the context: kind | nruns | totals | off ; two stream synchronisations per call, no allocation once warm
+    const size_t n = r->n_cols, o_nr = (n + 7) & ~(size_t)7, o_tot = o_nr + n * 4 + ((n & 1) ? 4 : 0), o_off = o_tot + 8 * (size_t)r->n_groups;
+    uint8_t* h = nullptr;
+    int rc = pool_host(ctx, 2, o_off + n * 8, (void**)&h);
     if (rc) return rc;
-    if (e != cudaSuccess || e2 != cudaSuccess) { ctx->last_err = std::string("result_fetch: ") + cudaGetErrorString(e != cudaSuccess ? e : e2); return BMB200_ERR_CUDA; }
+    uint8_t* kind = h; uint32_t* nruns = (uint32_t*)(h + o_nr); uint64_t* tot = (uint64_t*)(h + o_tot); uint64_t* off = (uint64_t*)(h + o_off);
+    CU(cudaMemcpyAsync(kind, r->kind, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(nruns, r->nruns, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(tot, r->total, 8 * (size_t)r->n_groups, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    uint64_t nb = 0, ng = 0;
+    for (size_t c = 0; c < n; ++c) {
+        off[c] = 0;
+        if (kind[c] == BMB200_BLK_BIT) off[c] = nb++;
+        else if (kind[c] == BMB200_BLK_GAP) { off[c] = ng; ng += ((uint64_t)nruns[c] + 1 + kGapUnit - 1) / kGapUnit * kGapUnit; }
+    }
+    uint32_t* hb = nullptr; uint16_t* hg = nullptr;
+    if (nb || ng) {
+        uint64_t* d_off = nullptr; uint32_t* d_bits = nullptr; uint16_t* d_gaps = nullptr;
+        if ((rc = pool_dev(ctx, 0, n * 8, (void**)&d_off)) || (rc = pool_dev(ctx, 1, (size_t)nb * BMB200_BLOCK_BYTES + 16, (void**)&d_bits)) ||
+            (rc = pool_dev(ctx, 2, (size_t)ng * 2 + 16, (void**)&d_gaps)) ||
+            (rc = pool_host(ctx, 3, (size_t)nb * BMB200_BLOCK_BYTES + 16, (void**)&hb)) || (rc = pool_host(ctx, 4, (size_t)ng * 2 + 16, (void**)&hg))) return rc;
+        CU(cudaMemcpyAsync(d_off, off, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        uint32_t grid = (uint32_t)ctx->sm_count * 8u; if (grid > r->n_cols) grid = r->n_cols;
+        result_compact_kernel<<<grid, 256, 0, ctx->stream>>>(r->blocks, r->gaps, r->kind, d_off, d_bits, d_gaps, r->n_cols);
+        if ((rc = after_launch(ctx))) return rc;
+        if (nb) CU(cudaMemcpyAsync(hb, d_bits, (size_t)nb * BMB200_BLOCK_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ng) CU(cudaMemcpyAsync(hg, d_gaps, (size_t)ng * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    *kind_out = kind; *off_out = off; *bits_out = hb; *gaps_out = hg;
+    if (n_bit_blocks) *n_bit_blocks = nb;
+    if (n_gap_words) *n_gap_words = ng;
+    if (total_out) { uint64_t t = 0; for (uint32_t g = 0; g < r->n_groups; ++g) t += tot[g]; *total_out = t; }
     return BMB200_OK;
 }
 
@@ -1250,6 +1386,161 @@ int bmb200_aggregate_host(bmb200_ctx* ctx, const bmb200_packed_set* host, const 
     if (!rc && meta_out) rc = bmb200_result_fetch_meta(ctx->host_res, meta_out);
     if (!rc && total_out) rc = bmb200_result_total(ctx->host_res, total_out, nullptr);
     return rc;
+}
+
+/* ------------------------------------------------------------------ multi-GPU: block-range shards + one exchange */
+
+int bmb200_shard_range(uint32_t n_blocks, int nranks, int rank, uint32_t* nb_from, uint32_t* nb_to)
+{
+    if (nranks < 1 || rank < 0 || rank >= nranks || !nb_from || !nb_to) return BMB200_ERR_BADARG;
+    // whole 256-block superblocks per rank, so rs_index rows never straddle shards
+    const uint64_t nsb = ((uint64_t)n_blocks + BMB200_SUPERBLOCK - 1) / BMB200_SUPERBLOCK;
+    const uint64_t lo = nsb * (uint64_t)rank / (uint64_t)nranks * BMB200_SUPERBLOCK, hi = nsb * ((uint64_t)rank + 1) / (uint64_t)nranks * BMB200_SUPERBLOCK;
+    *nb_from = (uint32_t)std::min<uint64_t>(lo, n_blocks); *nb_to = (uint32_t)std::min<uint64_t>(hi, n_blocks);
+    return BMB200_OK;
+}
+
+int bmb200_comm_unique_id(void* id)
+{
+    if (!id) return BMB200_ERR_BADARG;
+    NcclApi& api = nccl_api();
+    if (!api.load()) return BMB200_ERR_UNSUPPORTED;
+    NcclApi::UniqueId u;
+    if (api.GetUniqueId(&u) != 0) return BMB200_ERR_CUDA;
+    memcpy(id, &u, BMB200_COMM_ID_BYTES);
+    return BMB200_OK;
+}
+
+int bmb200_comm_init(bmb200_ctx* ctx, int nranks, int rank, const void* id)
+{
+    if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return BMB200_ERR_BADARG;
+    NcclApi& api = nccl_api();
+    if (!api.load()) { ctx->last_err = api.err; return BMB200_ERR_UNSUPPORTED; }
+    CU(cudaSetDevice(ctx->device));
+    comm_release(ctx);
+    CommState& c = ctx->comm;
+    NcclApi::UniqueId u; memcpy(&u, id, BMB200_COMM_ID_BYTES);
+    const int nrc = api.CommInitRank(&c.comm, nranks, u, rank);
+    if (nrc != 0) { ctx->last_err = std::string("ncclCommInitRank: ") + api.GetErrorString(nrc); c.comm = nullptr; return BMB200_ERR_CUDA; }
+    c.nranks = nranks; c.rank = rank;
+    cudaError_t e = cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+        e = cudaEventCreateWithFlags(&c.ready[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c.done[k], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) { ctx->last_err = std::string("comm_init: ") + cudaGetErrorString(e); comm_release(ctx); return BMB200_ERR_CUDA; }
+    return BMB200_OK;
+}
+
+int bmb200_comm_info(const bmb200_ctx* ctx, int* nranks, int* rank)
+{
+    if (!ctx) return BMB200_ERR_BADARG;
+    if (nranks) *nranks = ctx->comm.comm ? ctx->comm.nranks : 1;
+    if (rank) *rank = ctx->comm.comm ? ctx->comm.rank : 0;
+    return BMB200_OK;
+}
+
+int bmb200_comm_destroy(bmb200_ctx* ctx)
+{
+    if (!ctx) return BMB200_ERR_BADARG;
+    cudaSetDevice(ctx->device);
+    comm_release(ctx);
+    return BMB200_OK;
+}
+
+int bmb200_exchange_popcounts(bmb200_result* r, uint32_t cols_per_rank)
+{
+    if (!r || r->n_groups != 1 || (cols_per_rank && cols_per_rank < r->n_cols)) return BMB200_ERR_BADARG;
+    bmb200_ctx* ctx = r->ctx;
+    CommState& c = ctx->comm;
+    if (!c.comm) return BMB200_ERR_BADARG;
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = cols_per_rank ? cols_per_rank : r->n_cols, words = n + 2;
+    if (n > c.cap_cols) {
+        CU(cudaStreamSynchronize(c.side));
+        for (int k = 0; k < 2; ++k) { cudaFree(c.stage[k]); cudaFree(c.gathered[k]); c.stage[k] = c.gathered[k] = nullptr; c.pending[k] = false; }
+        c.cap_cols = 0;
+        for (int k = 0; k < 2; ++k) {
+            CU(cudaMalloc((void**)&c.stage[k], words * 4));
+            CU(cudaMalloc((void**)&c.gathered[k], words * 4 * (size_t)c.nranks));
+        }
+        c.cap_cols = n;
+    }
+    const int k = (int)(c.seq & 1u);
+    // slot k was last used by the exchange two steps back: the copy below must not overtake that all-gather
+    if (c.pending[k]) CU(cudaStreamWaitEvent(ctx->stream, c.done[k], 0));
+    if (n > r->n_cols) CU(cudaMemsetAsync(c.stage[k] + r->n_cols, 0, (n - r->n_cols) * 4, ctx->stream));     // ragged shards: zero padding
+    CU(cudaMemcpyAsync(c.stage[k], r->popcnt, (size_t)r->n_cols * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(c.stage[k] + n, r->total, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaEventRecord(c.ready[k], ctx->stream));
+    CU(cudaStreamWaitEvent(c.side, c.ready[k], 0));
+    const int nrc = nccl_api().AllGather(c.stage[k], c.gathered[k], words, kNcclUint32, c.comm, c.side);
+    if (nrc != 0) { ctx->last_err = std::string("ncclAllGather: ") + nccl_api().GetErrorString(nrc); return BMB200_ERR_CUDA; }
+    CU(cudaEventRecord(c.done[k], c.side));
+    c.pending[k] = true; c.cols[k] = (uint32_t)n; c.seq++;
+    return BMB200_OK;
+}
+
+int bmb200_exchange_fence(bmb200_ctx* ctx)
+{
+    if (!ctx || !ctx->comm.comm) return BMB200_ERR_BADARG;
+    CU(cudaSetDevice(ctx->device));
+    for (int k = 0; k < 2; ++k) if (ctx->comm.pending[k]) CU(cudaStreamWaitEvent(ctx->stream, ctx->comm.done[k], 0));
+    return BMB200_OK;
+}
+
+int bmb200_exchange_fetch(bmb200_ctx* ctx, uint64_t* global_total, uint64_t* rank_totals, uint32_t* popcnt, const uint32_t** d_gathered, uint32_t* stride)
+{
+    if (!ctx || !ctx->comm.comm || !ctx->comm.seq) return BMB200_ERR_BADARG;
+    CommState& c = ctx->comm;
+    CU(cudaSetDevice(ctx->device));
+    const int k = (int)((c.seq - 1) & 1u);
+    const size_t n = c.cols[k], words = n + 2;
+    CU(cudaEventSynchronize(c.done[k]));
+    if (d_gathered) *d_gathered = c.gathered[k];
+    if (stride) *stride = (uint32_t)words;
+    if (global_total || rank_totals || popcnt) {
+        uint32_t* h = nullptr;
+        int rc = pool_host(ctx, 1, words * 4 * (size_t)c.nranks, (void**)&h);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(h, c.gathered[k], words * 4 * (size_t)c.nranks, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        uint64_t tot = 0;
+        for (int q = 0; q < c.nranks; ++q) {
+            uint64_t t; memcpy(&t, h + (size_t)q * words + n, 8);
+            if (rank_totals) rank_totals[q] = t;
+            tot += t;
+            if (popcnt) memcpy(popcnt + (size_t)q * n, h + (size_t)q * words, n * 4);
+        }
+        if (global_total) *global_total = tot;
+    }
+    return BMB200_OK;
+}
+
+int bmb200_ctx_bind_host_numa(bmb200_ctx* ctx, int* node_out)
+{
+    if (!ctx) return BMB200_ERR_BADARG;
+    if (node_out) *node_out = -1;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, ctx->device) != cudaSuccess) { cudaGetLastError(); return BMB200_OK; }
+    for (char* q = bus; *q; ++q) if (*q >= 'A' && *q <= 'Z') *q = (char)(*q - 'A' + 'a');
+    int node = -1;
+    { std::ifstream f(std::string("/sys/bus/pci/devices/") + bus + "/numa_node"); if (!(f >> node)) node = -1; }
+    if (node < 0) return BMB200_OK;                       // single-node box or no topology information: nothing to do
+    std::string list;
+    { std::ifstream f("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist"); std::getline(f, list); }
+    cpu_set_t cs; CPU_ZERO(&cs); int ncpu = 0;
+    for (size_t i = 0; i < list.size();) {               // "0-31,64-95"
+        size_t j = i; long a = 0, b; while (j < list.size() && isdigit((unsigned char)list[j])) a = a * 10 + (list[j++] - '0');
+        b = a;
+        if (j < list.size() && list[j] == '-') { ++j; b = 0; while (j < list.size() && isdigit((unsigned char)list[j])) b = b * 10 + (list[j++] - '0'); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET((int)c, &cs); ++ncpu; }
+        while (j < list.size() && !isdigit((unsigned char)list[j])) ++j;
+        if (j == i) break;
+        i = j;
+    }
+    if (ncpu && sched_setaffinity(0, sizeof cs, &cs) == 0 && node_out) *node_out = node;
+    return BMB200_OK;
 }
 
 /* ------------------------------------------------------------------ rank / select */
@@ -1351,16 +1642,13 @@ int bmb200_rank_batch(bmb200_rs* rs, const uint64_t* pos, uint64_t n, uint64_t* 
     if (!pos || !out) return BMB200_ERR_BADARG;
     bmb200_ctx* ctx = rs->ctx;
     CU(cudaSetDevice(ctx->device));
-    uint64_t *d_in = nullptr, *d_out = nullptr;
+    uint64_t *d_in = nullptr, *d_out = nullptr;       // context pools: no cudaMalloc / cudaFree per call
     int rc;
-    if ((rc = dev_alloc(ctx, &d_in, n)) || (rc = dev_alloc(ctx, &d_out, n))) { cudaFree(d_in); cudaFree(d_out); return rc; }
-    cudaError_t e = cudaMemcpyAsync(d_in, pos, n * 8, cudaMemcpyHostToDevice, ctx->stream);
-    rc = bmb200_rank_batch_dev(rs, d_in, n, d_out);
-    if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_in); cudaFree(d_out);
-    if (rc) return rc;
-    if (e != cudaSuccess || e2 != cudaSuccess) { ctx->last_err = std::string("rank_batch: ") + cudaGetErrorString(e != cudaSuccess ? e : e2); return BMB200_ERR_CUDA; }
+    if ((rc = pool_dev(ctx, 3, n * 8, (void**)&d_in)) || (rc = pool_dev(ctx, 4, n * 8, (void**)&d_out))) return rc;
+    CU(cudaMemcpyAsync(d_in, pos, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = bmb200_rank_batch_dev(rs, d_in, n, d_out))) return rc;
+    CU(cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return BMB200_OK;
 }
 
@@ -1373,17 +1661,12 @@ int bmb200_select_batch(bmb200_rs* rs, const uint64_t* rank, uint64_t n, uint64_
     CU(cudaSetDevice(ctx->device));
     uint64_t *d_in = nullptr, *d_pos = nullptr; uint8_t* d_f = nullptr;
     int rc;
-    if ((rc = dev_alloc(ctx, &d_in, n)) || (rc = dev_alloc(ctx, &d_pos, n)) || (rc = dev_alloc(ctx, &d_f, n))) {
-        cudaFree(d_in); cudaFree(d_pos); cudaFree(d_f); return rc;
-    }
-    cudaError_t e = cudaMemcpyAsync(d_in, rank, n * 8, cudaMemcpyHostToDevice, ctx->stream);
-    rc = bmb200_select_batch_dev(rs, d_in, n, d_pos, d_f);
-    if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(pos, d_pos, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
-    if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(found, d_f, n, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_in); cudaFree(d_pos); cudaFree(d_f);
-    if (rc) return rc;
-    if (e != cudaSuccess || e2 != cudaSuccess) { ctx->last_err = std::string("select_batch: ") + cudaGetErrorString(e != cudaSuccess ? e : e2); return BMB200_ERR_CUDA; }
+    if ((rc = pool_dev(ctx, 3, n * 8, (void**)&d_in)) || (rc = pool_dev(ctx, 4, n * 8, (void**)&d_pos)) || (rc = pool_dev(ctx, 5, n, (void**)&d_f))) return rc;
+    CU(cudaMemcpyAsync(d_in, rank, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = bmb200_select_batch_dev(rs, d_in, n, d_pos, d_f))) return rc;
+    CU(cudaMemcpyAsync(pos, d_pos, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(found, d_f, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return BMB200_OK;
 }
 

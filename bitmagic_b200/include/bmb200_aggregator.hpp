@@ -19,6 +19,8 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "bm.h"
@@ -82,7 +84,7 @@ uint32_t blocks_of(const BV& bv)
 /// store a fetched result (per-column flat form) into a cleared target through the public block manager
 template<class BV>
 void store_result(BV& target, typename BV::size_type new_size, uint32_t n_cols,
-                  const uint8_t* kind, const uint64_t* off, const uint32_t* bits, const uint16_t* gaps)
+                  const uint8_t* kind, const uint64_t* off, const uint32_t* bits, const uint16_t* gaps, uint32_t nb_off = 0)
 {
     target.clear(true);
     target.resize(new_size);
@@ -92,7 +94,7 @@ void store_result(BV& target, typename BV::size_type new_size, uint32_t n_cols,
     for (uint32_t c = 0; c < n_cols; ++c)
     {
         if (kind[c] == BMB200_BLK_NULL) continue;
-        unsigned i = c >> bm::set_array_shift, j = c & bm::set_array_mask;
+        unsigned i = (c + nb_off) >> bm::set_array_shift, j = (c + nb_off) & bm::set_array_mask;
         bman.reserve_top_blocks(i + 1);
         bman.check_alloc_top_subblock(i);
         if (kind[c] == BMB200_BLK_FULL)
@@ -116,7 +118,83 @@ void store_result(BV& target, typename BV::size_type new_size, uint32_t n_cols,
     }
 }
 
+/// walk the block trees of n vectors with a team of host threads (one vector at a time per thread); blocks [nb_from, nb_from + n_blocks)
+template<class BV>
+void build_views(const BV* const* vecs, size_t n, uint32_t nb_from, uint32_t n_blocks,
+                 std::vector<tree_view<BV>>& views, std::vector<bmb200_vec_blocks>& vb)
+{
+    views.resize(n); vb.resize(n);
+    unsigned T = std::thread::hardware_concurrency(); if (!T) T = 1; if (T > 32) T = 32; if (T > n) T = (unsigned)n;
+    auto work = [&](unsigned t) {
+        for (size_t k = t; k < n; k += T) {
+            views[k].build(*vecs[k], nb_from + n_blocks);
+            vb[k].n_blocks = n_blocks; vb[k].kind = views[k].kind.data() + nb_from; vb[k].ptr = views[k].ptr.data() + nb_from;
+        }
+    };
+    if (T <= 1 || (uint64_t)n * n_blocks < (1u << 16)) { for (unsigned t = 0; t < T; ++t) work(t); return; }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < T; ++t) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+}
+
 } // namespace detail
+
+/// Residency: a set of bvectors uploaded ONCE (block trees walked and blocks packed by host threads, H2D pipelined -- all inside
+/// bmb200_set_upload_vectors) and then addressed by bvector ADDRESS in every aggregator call that is given this set
+/// (aggregator::set_device_set).  This is the upload / cache API SURVEY section 7 asks for: at 6+ TB/s the aggregation of a
+/// 12 GiB set takes ~2.4 ms, its H2D takes ~250 ms, so repeated queries over long-lived vectors must not re-upload.
+/// Validity: the copy is a snapshot.  Frozen vectors (bvector::freeze(), src/bm.h:1057) cannot change; for mutable vectors the
+/// owner calls assign() again after a change.  stale() is a cheap O(1)-per-vector check (size, root pointer, top size) that
+/// catches resizes and re-allocations of the tree but not in-place bit flips.
+template<class BV>
+class device_set
+{
+public:
+    typedef typename BV::size_type size_type;
+    explicit device_set(context& c) : ctx_(c) {}
+    ~device_set() { release(); }
+    device_set(const device_set&) = delete; device_set& operator=(const device_set&) = delete;
+
+    /// (re)build the device copy from n vectors; nb_to != 0 uploads only the block columns [nb_from, nb_to) (one rank's shard)
+    void assign(const BV* const* vecs, size_t n, uint32_t nb_from = 0, uint32_t nb_to = 0)
+    {
+        release();
+        if (!n) return;
+        uint32_t nblk = 0;
+        for (size_t k = 0; k < n; ++k) nblk = std::max(nblk, detail::blocks_of(*vecs[k]));
+        if (nb_to && nb_to < nblk) nblk = nb_to;
+        if (nb_from >= nblk) throw std::range_error("device_set: empty block range");
+        nb_from_ = nb_from; n_blocks_ = nblk - nb_from;
+        std::vector<detail::tree_view<BV>> views; std::vector<bmb200_vec_blocks> vb;
+        detail::build_views(vecs, n, nb_from, n_blocks_, views, vb);
+        check(bmb200_set_upload_vectors(ctx_.get(), (uint32_t)n, n_blocks_, vb.data(), &set_), "bmb200_set_upload_vectors");
+        index_.clear(); stamps_.resize(n); vecs_.assign(vecs, vecs + n);
+        for (size_t k = 0; k < n; ++k) { index_.emplace(vecs[k], (uint32_t)k); stamps_[k] = stamp_of(*vecs[k]); }
+    }
+    void release() { if (set_) { bmb200_set_free(set_); set_ = nullptr; } index_.clear(); vecs_.clear(); stamps_.clear(); }
+    bool resident() const { return set_ != nullptr; }
+    /// index of bv inside the set, or -1
+    long index_of(const BV* bv) const { auto it = index_.find(bv); return it == index_.end() ? -1 : (long)it->second; }
+    bool stale() const { for (size_t k = 0; k < vecs_.size(); ++k) if (!(stamps_[k] == stamp_of(*vecs_[k]))) return true; return false; }
+    bmb200_set* handle() const { return set_; }
+    uint32_t n_blocks() const { return n_blocks_; }
+    uint32_t nb_from() const { return nb_from_; }
+    size_t size() const { return vecs_.size(); }
+    context& ctx() const { return ctx_; }
+private:
+    struct stamp { size_type size; const void* root; unsigned top; bool operator==(const stamp& o) const { return size == o.size && root == o.root && top == o.top; } };
+    static stamp stamp_of(const BV& bv)
+    {
+        const typename BV::blocks_manager_type& bman = bv.get_blocks_manager();
+        return stamp{bv.size(), bman.is_init() ? (const void*)bman.top_blocks_root() : nullptr, bman.is_init() ? bman.top_block_size() : 0u};
+    }
+    context& ctx_;
+    bmb200_set* set_ = nullptr;
+    uint32_t n_blocks_ = 0, nb_from_ = 0;
+    std::unordered_map<const BV*, uint32_t> index_;
+    std::vector<const BV*> vecs_;
+    std::vector<stamp> stamps_;
+};
 
 /// Drop-in for bm::aggregator<BV>: combine_or / combine_and / combine_and_sub on the GPU.
 template<class BV>
@@ -128,6 +206,12 @@ public:
     typedef typename BV::size_type size_type;
 
     explicit aggregator(context& ctx) : ctx_(ctx) {}
+    ~aggregator() { if (res_) bmb200_result_free(res_); }
+    aggregator(const aggregator&) = delete; aggregator& operator=(const aggregator&) = delete;   // like the reference (src/bmaggregator.h:820)
+
+    /// attach a resident set: calls whose sources are ALL members of it run on the device copy (no tree walk, no upload);
+    /// any other call uploads its sources as before.  nullptr detaches.
+    void set_device_set(const device_set<BV>* ds) { ds_ = ds; }
 
     // ---- setters, same meaning as src/bmaggregator.h:359-388 ----
     void set_optimization(typename BV::optmode opt = BV::opt_compress) { opt_mode_ = opt; }
@@ -196,45 +280,66 @@ public:
         return found;
     }
 
+    /// device-side result of the last combine_* call (valid until the next one); used by sharded_aggregator for the exchange
+    bmb200_result* last_result() const { return res_; }
+
     /// popcount of AND-SUB without materialising the result (pipeline counts mode, :1397-1398)
     size_type count_and_sub(const bvector_type_const_ptr* src_and, size_t n_and,
                             const bvector_type_const_ptr* src_sub, size_t n_sub)
     {
         if (!n_and) return 0;
-        bmb200_set* set = upload(src_and, n_and, src_sub, n_sub);
-        std::vector<uint32_t> g0(n_and), g1(n_sub);
-        for (size_t k = 0; k < n_and; ++k) g0[k] = (uint32_t)k;
-        for (size_t k = 0; k < n_sub; ++k) g1[k] = (uint32_t)(n_and + k);
-        bmb200_agg_args a{BMB200_OP_AND_SUB, BMB200_F_COUNT_ONLY, g0.data(), (uint32_t)n_and, g1.data(), (uint32_t)n_sub, 0, 0};
+        bool own = false;
+        bmb200_set* set = bind(src_and, n_and, src_sub, n_sub, own);
+        bmb200_agg_args a{BMB200_OP_AND_SUB, BMB200_F_COUNT_ONLY, g0_.data(), (uint32_t)n_and, g1_.data(), (uint32_t)n_sub, 0, 0};
         bmb200_result* res = nullptr;
         int rc = bmb200_aggregate(ctx_.get(), set, &a, &res);
         uint64_t total = 0; int any = 0;
         if (!rc) rc = bmb200_result_total(res, &total, &any);
         if (res) bmb200_result_free(res);
-        bmb200_set_free(set);
+        if (own) bmb200_set_free(set);
         check(rc, "bmb200_aggregate(count)");
         return (size_type)total;
     }
 
 private:
-    bmb200_set* upload(const bvector_type_const_ptr* s0, size_t n0, const bvector_type_const_ptr* s1, size_t n1)
+    /// sources -> (set, member indices): the attached resident set when every source lives in it, else a fresh upload
+    bmb200_set* bind(const bvector_type_const_ptr* s0, size_t n0, const bvector_type_const_ptr* s1, size_t n1, bool& own)
     {
-        n_blocks_ = 0; max_size_ = 0;
+        g0_.resize(n0); g1_.resize(n1);
+        max_size_ = 0;
         for (size_t k = 0; k < n0 + n1; ++k)
         {
             const BV* bv = k < n0 ? s0[k] : s1[k - n0];
-            uint32_t nb = detail::blocks_of(*bv);
-            if (nb > n_blocks_) n_blocks_ = nb;
             if (bv->size() > max_size_) max_size_ = bv->size();   // resize_target: max over sources, :2238-2248
         }
-        if (spare_blocks_ && n_blocks_ < 65536u) n_blocks_ += spare_blocks_;
-        views_.resize(n0 + n1); vb_.resize(n0 + n1);
+        if (ds_ && ds_->resident() && !spare_blocks_)
+        {
+            bool all = true;
+            for (size_t k = 0; k < n0 + n1 && all; ++k)
+            {
+                long ix = ds_->index_of(k < n0 ? s0[k] : s1[k - n0]);
+                if (ix < 0) all = false; else (k < n0 ? g0_[k] : g1_[k - n0]) = (uint32_t)ix;
+            }
+            if (all) { own = false; n_blocks_ = ds_->n_blocks(); nb_off_ = ds_->nb_from(); return ds_->handle(); }
+        }
+        for (size_t k = 0; k < n0; ++k) g0_[k] = (uint32_t)k;
+        for (size_t k = 0; k < n1; ++k) g1_[k] = (uint32_t)(n0 + k);
+        own = true; nb_off_ = 0;
+        return upload(s0, n0, s1, n1);
+    }
+
+    bmb200_set* upload(const bvector_type_const_ptr* s0, size_t n0, const bvector_type_const_ptr* s1, size_t n1)
+    {
+        n_blocks_ = 0;
+        std::vector<const BV*> all(n0 + n1);
         for (size_t k = 0; k < n0 + n1; ++k)
         {
-            const BV* bv = k < n0 ? s0[k] : s1[k - n0];
-            views_[k].build(*bv, n_blocks_);
-            vb_[k].n_blocks = n_blocks_; vb_[k].kind = views_[k].kind.data(); vb_[k].ptr = views_[k].ptr.data();
+            all[k] = k < n0 ? s0[k] : s1[k - n0];
+            uint32_t nb = detail::blocks_of(*all[k]);
+            if (nb > n_blocks_) n_blocks_ = nb;
         }
+        if (spare_blocks_ && n_blocks_ < 65536u) n_blocks_ += spare_blocks_;
+        detail::build_views(all.data(), all.size(), 0u, n_blocks_, views_, vb_);
         bmb200_set* set = nullptr;
         check(bmb200_set_upload_vectors(ctx_.get(), (uint32_t)(n0 + n1), n_blocks_, vb_.data(), &set), "bmb200_set_upload_vectors");
         return set;
@@ -243,26 +348,20 @@ private:
     bool run(bvector_type& target, int op, const bvector_type_const_ptr* s0, size_t n0,
              const bvector_type_const_ptr* s1, size_t n1, bool compress)
     {
-        bmb200_set* set = upload(s0, n0, s1, n1);
-        std::vector<uint32_t> g0(n0), g1(n1);
-        for (size_t k = 0; k < n0; ++k) g0[k] = (uint32_t)k;
-        for (size_t k = 0; k < n1; ++k) g1[k] = (uint32_t)(n0 + k);
+        bool own = false;
+        bmb200_set* set = bind(s0, n0, s1, n1, own);
         bmb200_agg_args a{op, compress ? BMB200_F_OPT_COMPRESS : BMB200_F_OPT_NONE,
-                          g0.data(), (uint32_t)n0, n1 ? g1.data() : nullptr, (uint32_t)n1, 0, 0};
-        bmb200_result* res = nullptr;
-        int rc = bmb200_aggregate(ctx_.get(), set, &a, &res);
-        uint64_t total = 0; int any = 0, rc2 = 0;
-        std::vector<uint8_t> kind(n_blocks_); std::vector<uint64_t> off(n_blocks_);
-        std::vector<uint32_t> bits; std::vector<uint16_t> gaps;
-        if (!rc) rc = bmb200_result_total(res, &total, &any);
-        if (!rc) { uint64_t nb = 0, ng = 0; rc = bmb200_result_sizes(res, &nb, &ng);
-                   if (!rc) { bits.resize(nb * BMB200_BLOCK_WORDS); gaps.resize(ng);
-                              rc = bmb200_result_fetch(res, kind.data(), off.data(), bits.data(), gaps.data()); } }
-        if (res) rc2 = bmb200_result_free(res);
-        bmb200_set_free(set);
-        check(rc, "bmb200_aggregate"); check(rc2, "bmb200_result_free");
-        detail::store_result(target, max_size_, n_blocks_, kind.data(), off.data(), bits.data(), gaps.data());
-        return any != 0;
+                          g0_.data(), (uint32_t)n0, n1 ? g1_.data() : nullptr, (uint32_t)n1, 0, 0};
+        // the result object (device buffers for every column) is recycled from call to call; the fetched blocks arrive in pinned
+        // memory owned by the context (bmb200_result_fetch_view): a warm call allocates nothing on either side
+        int rc = bmb200_aggregate(ctx_.get(), set, &a, &res_);
+        uint64_t total = 0, nb = 0, ng = 0;
+        const uint8_t* kind = nullptr; const uint64_t* off = nullptr; const uint32_t* bits = nullptr; const uint16_t* gaps = nullptr;
+        if (!rc) rc = bmb200_result_fetch_view(res_, &kind, &off, &bits, &gaps, &nb, &ng, &total);
+        if (own) { int rc2 = bmb200_set_free(set); if (!rc) rc = rc2; }
+        check(rc, "bmb200_aggregate");
+        detail::store_result(target, max_size_, n_blocks_, kind, off, bits, gaps, nb_off_);
+        return total != 0;
     }
 
     context& ctx_;
@@ -270,9 +369,77 @@ private:
     std::vector<const BV*> grp_[2];
     std::vector<detail::tree_view<BV>> views_;
     std::vector<bmb200_vec_blocks> vb_;
-    uint32_t n_blocks_ = 0;
+    std::vector<uint32_t> g0_, g1_;
+    const device_set<BV>* ds_ = nullptr;
+    bmb200_result* res_ = nullptr;
+    uint32_t n_blocks_ = 0, nb_off_ = 0;
     uint32_t spare_blocks_ = 0;
     size_type max_size_ = 0;
+};
+
+/// One rank of a block-range sharded aggregation (one process per GPU; SURVEY 8e, BASELINE config 5): this rank keeps the block
+/// columns [from, to) of EVERY vector resident on its GPU, aggregates them locally with the same kernels, and the ranks exchange
+/// per-column popcounts + cardinalities with one ncclAllGather (bmb200_exchange_popcounts).  Result blocks never move: the target
+/// of a combine_* call holds this rank's block range only.  The 128-byte communicator id comes from rank 0
+/// (sharded_aggregator::unique_id) and travels to the other ranks by whatever the application uses (MPI, sockets, files).
+template<class BV>
+class sharded_aggregator
+{
+public:
+    typedef typename BV::size_type size_type;
+    static void unique_id(void* id128) { check(bmb200_comm_unique_id(id128), "bmb200_comm_unique_id"); }
+    sharded_aggregator(context& c, int nranks, int rank, const void* id128) : ctx_(c), agg_(c), ds_(c), nranks_(nranks), rank_(rank)
+    { check(bmb200_comm_init(c.get(), nranks, rank, id128), "bmb200_comm_init"); }
+    ~sharded_aggregator() { ds_.release(); bmb200_comm_destroy(ctx_.get()); }
+    void set_optimization(typename BV::optmode opt = BV::opt_compress) { agg_.set_optimization(opt); }
+
+    /// upload this rank's shard of the vectors (they stay resident until the next assign)
+    void assign(const BV* const* vecs, size_t n)
+    {
+        uint32_t nblk = 0;
+        for (size_t k = 0; k < n; ++k) nblk = std::max(nblk, detail::blocks_of(*vecs[k]));
+        n_blocks_ = nblk; widest_ = 0;
+        for (int r = 0; r < nranks_; ++r) { uint32_t a, b; check(bmb200_shard_range(nblk, nranks_, r, &a, &b), "bmb200_shard_range"); widest_ = std::max(widest_, b - a); }
+        check(bmb200_shard_range(nblk, nranks_, rank_, &from_, &to_), "bmb200_shard_range");
+        if (to_ > from_) ds_.assign(vecs, n, from_, to_); else ds_.release();
+        agg_.set_device_set(&ds_);
+    }
+    uint32_t shard_from() const { return from_; }
+    uint32_t shard_to() const { return to_; }
+
+    /// same contracts as aggregator<BV>; sources must be members of the assigned set
+    void combine_or(BV& target, const BV* const* src, size_t n) { agg_.combine_or(target, src, n); exchange(); }
+    void combine_and(BV& target, const BV* const* src, size_t n) { agg_.combine_and(target, src, n); exchange(); }
+    bool combine_and_sub(BV& target, const BV* const* src_and, size_t n_and, const BV* const* src_sub, size_t n_sub)
+    { agg_.combine_and_sub(target, src_and, n_and, src_sub, n_sub, false); exchange(); return count() != 0; }
+
+    /// global cardinality of the last result (sum over all ranks)
+    uint64_t count() { fetch(); return total_; }
+    /// per-column popcounts of the whole result, all shards concatenated in block order: [n_blocks]
+    const std::vector<uint32_t>& block_popcounts() { fetch(); return pop_; }
+private:
+    void exchange()
+    {
+        fetched_ = false;
+        if (!agg_.last_result()) throw std::logic_error("sharded_aggregator: no device result (empty source list?)");
+        check(bmb200_exchange_popcounts(agg_.last_result(), widest_), "bmb200_exchange_popcounts");
+    }
+    void fetch()
+    {
+        if (fetched_) return;
+        std::vector<uint32_t> all((size_t)nranks_ * widest_);
+        check(bmb200_exchange_fetch(ctx_.get(), &total_, nullptr, all.data(), nullptr, nullptr), "bmb200_exchange_fetch");
+        pop_.assign(n_blocks_, 0u);
+        for (int r = 0; r < nranks_; ++r) { uint32_t a, b; bmb200_shard_range(n_blocks_, nranks_, r, &a, &b);
+                                            std::copy(all.begin() + (size_t)r * widest_, all.begin() + (size_t)r * widest_ + (b - a), pop_.begin() + a); }
+        fetched_ = true;
+    }
+    context& ctx_;
+    aggregator<BV> agg_;
+    device_set<BV> ds_;
+    int nranks_, rank_;
+    uint32_t n_blocks_ = 0, from_ = 0, to_ = 0, widest_ = 0;
+    uint64_t total_ = 0; std::vector<uint32_t> pop_; bool fetched_ = true;
 };
 
 /// Drop-in for aggregator::pipeline<agg_opt_bvect_and_counts> + aggregator::combine_and_sub(TPipe&)

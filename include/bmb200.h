@@ -177,12 +177,20 @@ int bmb200_device_info(const bmb200_ctx* ctx, int* sm_count, int* cc_major, int*
  * through the shared-memory ring, 1 always gather), key 1 = resident CTAs per SM of the aggregation kernel */
 #define BMB200_TUNE_GAP_MODE     0
 #define BMB200_TUNE_CTAS_PER_SM  1
+#define BMB200_TUNE_HOST_THREADS 2   /* host threads that pack blocks in bmb200_set_upload_vectors: 0 = all cores (at most 64) */
 int bmb200_ctx_set_tuning(bmb200_ctx* ctx, int key, int value);
+/* pin the CALLING thread (and the threads it starts later, e.g. the packers of bmb200_set_upload_vectors) to the CPUs of the NUMA
+ * node this context's GPU hangs off, so that pinned staging memory is allocated next to the GPU's PCIe root.  *node = the node, or
+ * -1 when the box has no NUMA information (then nothing is changed).  Call it before the first upload. */
+int bmb200_ctx_bind_host_numa(bmb200_ctx* ctx, int* node);
 
 /* ---------------- sets ---------------- */
 /* copy a packed set from HOST memory (pinned or pageable) into HBM */
 int bmb200_set_upload(bmb200_ctx* ctx, const bmb200_packed_set* host, bmb200_set** out);
-/* gather per-vector block pointers (the host block tree) into a packed device set */
+/* gather per-vector block pointers (the host block tree) into a packed device set.  The blocks are packed by a team of host
+ * threads (BMB200_TUNE_HOST_THREADS) into a ring of pinned staging slots owned by the context and copied chunk by chunk, packing
+ * and DMA overlapped; the set then stays resident until bmb200_set_free (bm::b200::device_set in the C++ binding).
+ * To upload only a shard, pass kind + nb_from / ptr + nb_from with n_blocks = the shard's width. */
 int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks,
                               const bmb200_vec_blocks* vecs, bmb200_set** out);
 /* deserialize-to-device: vector v of the set arrives as a BitMagic serialization BLOB (bm::serializer<>, src/bmserial.h) and
@@ -247,6 +255,12 @@ int bmb200_result_sizes(bmb200_result* res, uint64_t* n_bit_blocks, uint64_t* n_
  * offset into gaps (u16 words) for GAP columns */
 int bmb200_result_fetch(bmb200_result* res, uint8_t* kind, uint64_t* off,
                         uint32_t* bits, uint16_t* gaps);
+/* same result, delivered into pinned host memory OWNED BY THE CONTEXT (no allocation once warm, two stream synchronisations):
+ * kind[n_cols], off[n_cols], bits, gaps as in bmb200_result_fetch; *total = cardinality over all groups.  The pointers stay
+ * valid until the next bmb200_result_fetch_view on the same context.  This is the call a resident-set ("warm") aggregation
+ * ends with: bm::b200::aggregator materialises its target bvector from these views. */
+int bmb200_result_fetch_view(bmb200_result* res, const uint8_t** kind, const uint64_t** off, const uint32_t** bits,
+                             const uint16_t** gaps, uint64_t* n_bit_blocks, uint64_t* n_gap_words, uint64_t* total);
 /* device addresses: blocks [n_cols][2048] u32, popcnt [n_cols] u32, digest [n_cols] u64, flag [n_cols] u8 */
 int bmb200_result_device_ptrs(const bmb200_result* res, void** blocks, void** popcnt,
                               void** digest, void** flag, uint32_t* n_cols);
@@ -278,11 +292,37 @@ typedef struct bmb200_scan_args {
 } bmb200_scan_args;
 int bmb200_scan(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_scan_args* args, bmb200_result** inout);
 
-/* end-to-end convenience: HOST packed set in, HOST metadata out, in one call
- * (H2D of the set, kernel, D2H of kind/popcnt/digest [+ result blocks when bits != NULL]) */
+/* end-to-end convenience: HOST packed set in, HOST metadata out, in one call: H2D of the whole set (every call), kernel,
+ * D2H of the per-column metadata requested in meta_out (kind / popcnt / digest / nruns) and of the cardinality.  The result
+ * blocks stay on the device (fetch them with bmb200_result_fetch on a result of bmb200_aggregate when they are needed). */
 int bmb200_aggregate_host(bmb200_ctx* ctx, const bmb200_packed_set* host,
                           const bmb200_agg_args* args, const bmb200_result_meta* meta_out,
                           uint64_t* total_out);
+
+/* ---------------- multi-GPU: block-range shards + ONE exchange (one process per GPU) ----------------
+ * Every block column is independent (the reference loops (i,j) without carried state, src/bmaggregator.h:1113-1121,1184-1218),
+ * so rank g of G owns a contiguous, superblock-aligned range of block columns of EVERY vector, uploads and aggregates only that
+ * range, and the ranks exchange the per-column popcounts (4 B / column) and their cardinalities with one ncclAllGather over
+ * NVLink / NVSwitch.  NCCL is bound at run time (dlopen libnccl.so.2); BMB200_ERR_UNSUPPORTED when it cannot be found. */
+#define BMB200_COMM_ID_BYTES 128                       /* = sizeof(ncclUniqueId) */
+int bmb200_shard_range(uint32_t n_blocks, int nranks, int rank, uint32_t* nb_from, uint32_t* nb_to);
+/* rank 0: create the id and hand the 128 bytes to the other ranks (MPI / sockets / torch.distributed ...) */
+int bmb200_comm_unique_id(void* id);
+/* collective over all ranks: one communicator + one side stream per context */
+int bmb200_comm_init(bmb200_ctx* ctx, int nranks, int rank, const void* id);
+int bmb200_comm_info(const bmb200_ctx* ctx, int* nranks, int* rank);
+int bmb200_comm_destroy(bmb200_ctx* ctx);
+/* exchange of the local result `res` (single group) with all ranks: asynchronous, on the context's SIDE stream, ordered after the
+ * work already queued on the context stream; double-buffered, so the exchange of step i overlaps the aggregation of step i+1.
+ * cols_per_rank = the width of the widest shard (the same value on every rank; narrower shards are zero-padded), 0 = the
+ * result's own column count when all shards are equal. */
+int bmb200_exchange_popcounts(bmb200_result* res, uint32_t cols_per_rank);
+/* make the context stream wait for every exchange issued so far (asynchronous) */
+int bmb200_exchange_fence(bmb200_ctx* ctx);
+/* wait for the LAST exchange and read it: global cardinality, per-rank cardinalities [nranks], per-column popcounts of every
+ * shard [nranks * n_cols] (host; any may be NULL); *d_gathered = the same data in HBM, rank r's columns at r * *stride u32 */
+int bmb200_exchange_fetch(bmb200_ctx* ctx, uint64_t* global_total, uint64_t* rank_totals, uint32_t* popcnt,
+                          const uint32_t** d_gathered, uint32_t* stride);
 
 /* ---------------- rank / select ---------------- */
 /* build the rs_index of vector `vec` of `set`; the set must outlive the index */

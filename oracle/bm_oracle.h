@@ -53,6 +53,14 @@ void orc_set_token_hist(uint32_t* hist);
 int orc_scan(const bmb200_packed_set* set, const bmb200_scan_args* args,
              uint8_t* kind, uint32_t* popcnt, uint64_t* digest, uint32_t* nruns, uint32_t* blocks, uint16_t* gaps);
 
+/* ---- synthetic benchmark inputs on the host (bm_synth.c): the same counter-based generator as bmb200_synth_set ---- */
+typedef struct orc_synth orc_synth;
+int  orc_synth_create(uint32_t n_vec, uint32_t n_blocks, const double* density, const uint64_t* seed, int optimize, int threads,
+                      orc_synth** out);
+void orc_synth_packed(const orc_synth* s, bmb200_packed_set* out);      /* view into s; valid until orc_synth_free */
+void orc_synth_free(orc_synth* s);
+void orc_synth_force_scalar(int on);                                    /* 1 = never take the AVX-512 form of the generator */
+
 /* ---- rank / select over vector `vec` of a packed set ---- */
 int orc_rs_build(const bmb200_packed_set* set, uint32_t vec,
                  uint32_t* bcount, uint64_t* sub_count, uint64_t* sb_count);

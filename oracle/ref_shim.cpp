@@ -598,4 +598,116 @@ int ref_time_aggregate(const bmb200_packed_set* s, const bmb200_agg_args* a,
     } catch (...) { return 1; }
 }
 
+/*
+ * Persistent timing / parity job: the bvectors are built ONCE (per worker: its contiguous range of block columns of every
+ * source vector), every ref_job_run pass runs the reference aggregator on all workers, and ref_job_export walks the
+ * result of the last pass into per-column kind / popcount / digest (calc_block_digest0, src/bmfunc.h:1239) / GAP length.
+ * Workers = T = `threads` (one bm::aggregator per thread over a contiguous range of block indices).
+ */
+struct RefJob {
+    bmb200_agg_args a;
+    std::vector<uint32_t> g0, g1;
+    std::vector<Built> built;
+    std::vector<uint32_t> lo, hi;
+    std::vector<std::unique_ptr<bvect>> target;
+    uint32_t nb_from = 0, ncols = 0;
+};
+
+void* ref_job_create(const bmb200_packed_set* s, const bmb200_agg_args* a, int threads)
+{
+    try {
+        std::unique_ptr<RefJob> j(new RefJob());
+        j->a = *a;
+        j->g0.assign(a->group0, a->group0 + a->n0); j->a.group0 = j->g0.data();
+        if (a->op == BMB200_OP_AND_SUB && a->n1) { j->g1.assign(a->group1, a->group1 + a->n1); j->a.group1 = j->g1.data(); }
+        else { j->a.group1 = 0; j->a.n1 = 0; }
+        uint32_t nb_to = a->nb_to ? a->nb_to : s->n_blocks;
+        j->nb_from = a->nb_from; j->ncols = nb_to - a->nb_from;
+        if (threads < 1) threads = 1;
+        if ((uint32_t)threads > j->ncols) threads = (int)j->ncols;
+        j->built.resize(threads); j->lo.resize(threads); j->hi.resize(threads); j->target.resize(threads);
+        for (int t = 0; t < threads; ++t) {
+            j->lo[t] = a->nb_from + (uint32_t)((uint64_t)j->ncols * t / threads);
+            j->hi[t] = a->nb_from + (uint32_t)((uint64_t)j->ncols * (t + 1) / threads);
+            j->target[t].reset(new bvect());
+        }
+        std::vector<std::thread> th;
+        RefJob* jp = j.get();
+        for (int t = 0; t < threads; ++t)
+            th.emplace_back([jp, s, t]() { build_groups(s, &jp->a, jp->lo[t], jp->hi[t], jp->built[t]); });
+        for (auto& x : th) x.join();
+        return j.release();
+    } catch (...) { return 0; }
+}
+
+int ref_job_threads(void* job) { return job ? (int)((RefJob*)job)->built.size() : 0; }
+
+/* one timed pass per repeat: all workers run the reference entry point on their range; sec[r] = wall time of pass r */
+int ref_job_run(void* job, int repeats, double* sec, uint64_t* total_bits)
+{
+    if (!job) return 2;
+    try {
+        RefJob* j = (RefJob*)job;
+        const int T = (int)j->built.size();
+        uint64_t tot = 0;
+        for (int r = 0; r < repeats; ++r) {
+            std::vector<uint64_t> cnt(T, 0);
+            auto t0 = std::chrono::steady_clock::now();
+            std::vector<std::thread> th;
+            for (int t = 0; t < T; ++t)
+                th.emplace_back([j, &cnt, t]() {
+                    bm::aggregator<bvect> agg;
+                    run_op(agg, &j->a, j->built[t], *j->target[t]);
+                    cnt[t] = j->target[t]->count();
+                });
+            for (auto& x : th) x.join();
+            auto t1 = std::chrono::steady_clock::now();
+            if (sec) sec[r] = std::chrono::duration<double>(t1 - t0).count();
+            tot = 0; for (auto c : cnt) tot += c;
+        }
+        if (total_bits) *total_bits = tot;
+        return 0;
+    } catch (...) { return 1; }
+}
+
+int ref_job_export(void* job, uint8_t* kind, uint32_t* popcnt, uint64_t* digest, uint32_t* gap_len)
+{
+    if (!job) return 2;
+    try {
+        RefJob* j = (RefJob*)job;
+        const int T = (int)j->built.size();
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t)
+            th.emplace_back([=]() {
+                const bvect& bv = *j->target[t];
+                const bvect::blocks_manager_type& bman = bv.get_blocks_manager();
+                BM_DECLARE_TEMP_BLOCK(tb)
+                for (uint32_t c = j->lo[t]; c < j->hi[t]; ++c)
+                {
+                    uint32_t lc = c - j->lo[t], oc = c - j->nb_from;
+                    unsigned i = lc >> 8, jj = lc & 255u;
+                    const bm::word_t* blk = 0;
+                    if (bman.is_init() && i < bman.top_block_size()) blk = bman.get_block_ptr(i, jj);
+                    uint8_t kd; uint32_t pc = 0, gl = 0; uint64_t dg = 0;
+                    if (!blk) kd = BMB200_BLK_NULL;
+                    else if (blk == FULL_BLOCK_FAKE_ADDR || blk == FULL_BLOCK_REAL_ADDR) { kd = BMB200_BLK_FULL; pc = 65536; dg = ~0ull; }
+                    else if (BM_IS_GAP(blk)) {
+                        const bm::gap_word_t* g = BMGAP_PTR(blk);
+                        kd = BMB200_BLK_GAP; pc = bm::gap_bit_count_unr(g); gl = bm::gap_length(g) - 1;
+                        bm::gap_convert_to_bitset(tb.begin(), g); dg = bm::calc_block_digest0(tb.begin());
+                    }
+                    else { kd = BMB200_BLK_BIT; pc = bm::bit_block_count(blk); dg = bm::calc_block_digest0(blk); }
+                    if (kind) kind[oc] = kd;
+                    if (popcnt) popcnt[oc] = pc;
+                    if (digest) digest[oc] = dg;
+                    if (gap_len) gap_len[oc] = gl;
+                }
+            });
+        for (auto& x : th) x.join();
+        return 0;
+    } catch (...) { return 1; }
+}
+
+void ref_job_free(void* job) { delete (RefJob*)job; }
+
 } // extern "C"

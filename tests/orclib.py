@@ -9,7 +9,7 @@ from pathlib import Path
 
 import numpy as np
 
-from bitmagic_b200.capi import (AggArgsC, BLOCK_WORDS, GAP_MAX_WORDS, PackedSetC, ScanArgsC, SCAN_RANGE, packed_c, ptr)
+from bitmagic_b200.capi import (AggArgsC, BLOCK_WORDS, GAP_MAX_WORDS, PackedSetC, ScanArgsC, SCAN_RANGE, packed_c, ptr)  # noqa: F401
 
 ROOT = Path(__file__).resolve().parent.parent
 ORACLE_DIR = ROOT / "oracle"
@@ -22,10 +22,12 @@ def oracle() -> C.CDLL:
     global _oracle
     if _oracle is None:
         so = ORACLE_DIR / "liboracle.so"
-        srcs = [ORACLE_DIR / "bm_oracle.c", ORACLE_DIR / "bm_oracle_entropy.c"]
+        srcs = [ORACLE_DIR / "bm_oracle.c", ORACLE_DIR / "bm_oracle_entropy.c", ORACLE_DIR / "bm_synth.c"]
         if not so.exists() or so.stat().st_mtime < max(x.stat().st_mtime for x in srcs):
             subprocess.run(["make", "-C", str(ORACLE_DIR), str(so)], check=True, capture_output=True)
         _oracle = C.CDLL(str(so))
+        _oracle.orc_synth_free.restype = None
+        _oracle.orc_synth_packed.restype = None
         _oracle.orc_bit_block_count.restype = C.c_uint32
         _oracle.orc_block_digest.restype = C.c_uint64
         _oracle.orc_bit_block_calc_change.restype = C.c_uint32
@@ -37,18 +39,109 @@ def oracle() -> C.CDLL:
     return _oracle
 
 
-def have_ref(addr64: bool = False) -> bool:
-    return (ORACLE_DIR / "_ref" / ("libbmref64.so" if addr64 else "libbmref.so")).exists()
+def _ref_name(addr64=False) -> str:
+    """addr64: False = 32-bit addressing / AVX2 (the reference's own build flags), True = -DBM64ADDR, "avx512" = -DBMAVX512OPT"""
+    return {False: "libbmref.so", True: "libbmref64.so", "avx512": "libbmref_avx512.so"}[addr64]
 
 
-def ref(addr64: bool = False) -> C.CDLL:
-    key = bool(addr64)
+def have_ref(addr64=False) -> bool:
+    return (ORACLE_DIR / "_ref" / _ref_name(addr64)).exists()
+
+
+def cpu_has_avx512() -> bool:
+    try:
+        flags = next(ln for ln in open("/proc/cpuinfo") if ln.startswith("flags")).split()
+    except Exception:
+        return False
+    return all(f in flags for f in ("avx512f", "avx512bw", "avx512vl", "avx512dq"))
+
+
+def ref(addr64=False) -> C.CDLL:
+    key = addr64
     if key not in _ref:
-        so = ORACLE_DIR / "_ref" / ("libbmref64.so" if addr64 else "libbmref.so")
-        lib = C.CDLL(str(so))
+        lib = C.CDLL(str(ORACLE_DIR / "_ref" / _ref_name(addr64)))
         lib.ref_simd.restype = C.c_char_p
+        lib.ref_job_create.restype = C.c_void_p
+        lib.ref_job_free.restype = None
         _ref[key] = lib
     return _ref[key]
+
+
+class HostSynth:
+    """orc_synth_create (oracle/bm_synth.c): the benchmark's generator restated on the host -> a PackedSet whose arrays are
+    views into the C object (kept alive by this wrapper)."""
+
+    def __init__(self, n_vec, n_blocks, density, seed, optimize, threads=0):
+        import os
+        from bitmagic_b200.hostfmt import PackedSet
+        dens = np.ascontiguousarray(density, dtype=np.float64); sd = np.ascontiguousarray(seed, dtype=np.uint64)
+        assert dens.size == n_vec and sd.size == n_vec
+        self.h = C.c_void_p(0)
+        rc = oracle().orc_synth_create(C.c_uint32(n_vec), C.c_uint32(n_blocks), ptr(dens), ptr(sd), int(bool(optimize)),
+                                       int(threads or os.cpu_count() or 1), C.byref(self.h))
+        assert rc == 0, f"orc_synth_create rc={rc}"
+        c = PackedSetC()
+        oracle().orc_synth_packed(self.h, C.byref(c))
+        self.c = c
+
+        def view(p, n, ct, dt):
+            if not n:
+                return np.zeros(0, dt)
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(ct)), shape=(n,))
+        bb = view(c.bit_base, n_blocks + 1, C.c_uint64, np.uint64); gb = view(c.gap_base, n_blocks + 1, C.c_uint64, np.uint64)
+        self.ps = PackedSet(n_vec, n_blocks, view(c.desc, n_vec * n_blocks, C.c_uint32, np.uint32), bb, gb,
+                            view(c.bit_pool, int(bb[-1]) * BLOCK_WORDS, C.c_uint32, np.uint32),
+                            view(c.gap_pool, int(gb[-1]) * 8, C.c_uint16, np.uint16))
+
+    def free(self):
+        if self.h:
+            self.ps = None
+            oracle().orc_synth_free(self.h)
+            self.h = C.c_void_p(0)
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class RefJob:
+    """Persistent reference job (oracle/ref_shim.cpp ref_job_*): bvectors built once, T worker threads, timed passes,
+    per-column kind / popcount / digest / GAP length of the result."""
+
+    def __init__(self, ps, op, g0, g1=None, flags=0, threads=1, nb_from=0, nb_to=0, variant=False):
+        self.lib = ref(variant)
+        a, self._keep = _args(op, g0, g1, flags, nb_from, nb_to)
+        c = _pc(ps)
+        self.n_cols = (nb_to if nb_to else ps.n_blocks) - nb_from
+        self.h = C.c_void_p(self.lib.ref_job_create(C.byref(c), C.byref(a), int(threads)))
+        assert self.h, "ref_job_create failed"
+        self.threads = self.lib.ref_job_threads(self.h)
+
+    def run(self, repeats=1):
+        sec = np.zeros(repeats, np.float64); tot = C.c_uint64(0)
+        rc = self.lib.ref_job_run(self.h, int(repeats), ptr(sec), C.byref(tot))
+        assert rc == 0, f"ref_job_run rc={rc}"
+        return sec, tot.value
+
+    def export(self):
+        n = self.n_cols
+        kind = np.zeros(n, np.uint8); pop = np.zeros(n, np.uint32); dig = np.zeros(n, np.uint64); gl = np.zeros(n, np.uint32)
+        rc = self.lib.ref_job_export(self.h, ptr(kind), ptr(pop), ptr(dig), ptr(gl))
+        assert rc == 0, f"ref_job_export rc={rc}"
+        return kind, pop, dig, gl
+
+    def free(self):
+        if self.h:
+            self.lib.ref_job_free(self.h)
+            self.h = C.c_void_p(0)
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def _args(op, g0, g1, flags, nb_from=0, nb_to=0):

@@ -59,3 +59,57 @@ def test_from_positions_and_positions():
     v = bm.BVector.from_positions(pos, 4)
     assert list(v.positions()) == sorted(pos)
     assert v.count() == len(pos)
+
+
+def _vec_blocks_c(vectors, n_blocks):
+    """bmb200_vec_blocks array for hostfmt.BVectors (what DeviceSet.upload_vectors builds)."""
+    import ctypes as C
+    from bitmagic_b200.capi import VecBlocksC, ptr
+    arr = (VecBlocksC * len(vectors))()
+    keep = []
+    for i, v in enumerate(vectors):
+        kind = np.ascontiguousarray(v.kind, dtype=np.uint8)
+        ptrs = np.zeros(v.n_blocks, dtype=np.uint64)
+        for nb in range(v.n_blocks):
+            if kind[nb] in (bm.BLK_BIT, bm.BLK_GAP):
+                blk = v.blocks[nb]; keep.append(blk); ptrs[nb] = blk.ctypes.data
+        keep += [kind, ptrs]
+        arr[i] = VecBlocksC(v.n_blocks, ptr(kind), ptr(ptrs))
+    return arr, keep
+
+
+def test_upload_packer_host_build_matches_packedset():
+    """The product's upload packer (csrc/host_pack.hpp: threaded layout + staging-ring pipeline), built for the host by
+    oracle/host_pack_check.cpp, against hostfmt.PackedSet.pack -- several thread counts and slot sizes (1 chunk .. 1 column per chunk)."""
+    import ctypes as C
+    import subprocess
+    so = orclib.ORACLE_DIR / "libhostpack.so"
+    if not so.exists():
+        subprocess.run(["make", "-C", str(orclib.ORACLE_DIR), str(so)], check=True, capture_output=True)
+    lib = C.CDLL(str(so))
+    rng = np.random.default_rng(11)
+    vecs = gen.mixed_vectors(rng, 9, 23) + gen.edge_vectors(23)[:3]
+    short = bm.BVector(5); short.set_full(1); short.set_bits(4, np.full(2048, 0x0F0F0F0F, np.uint32)); vecs.append(short)   # fewer blocks than the set
+    nv, nb = len(vecs), 23
+    ref = bm.PackedSet.pack(vecs, nb)
+    arr, keep = _vec_blocks_c(vecs, nb)
+    for threads, slot in ((1, 1 << 30), (3, 1 << 16), (8, 1), (5, 40000)):
+        n_bit, n_gap = C.c_uint64(0), C.c_uint64(0)
+        assert lib.host_pack_sizes(nv, nb, arr, threads, C.byref(n_bit), C.byref(n_gap)) == 0
+        assert n_bit.value == int(ref.bit_base[-1]) and n_gap.value == int(ref.gap_base[-1])
+        desc = np.zeros(nv * nb, np.uint32); bb = np.zeros(nb + 1, np.uint64); gb = np.zeros(nb + 1, np.uint64)
+        bits = np.full(n_bit.value * 2048 + 4, 0x77777777, np.uint32); gaps = np.full(n_gap.value * 8 + 8, 0x7777, np.uint16)
+        nch = C.c_uint32(0)
+        rc = lib.host_pack_check(nv, nb, arr, threads, C.c_uint64(slot), orclib.ptr(desc), orclib.ptr(bb), orclib.ptr(gb),
+                                 orclib.ptr(bits), orclib.ptr(gaps), C.byref(nch))
+        assert rc == 0
+        assert np.array_equal(desc, ref.desc) and np.array_equal(bb, ref.bit_base) and np.array_equal(gb, ref.gap_base)
+        assert np.array_equal(bits[:n_bit.value * 2048], ref.bit_pool), f"bit pool differs (threads={threads}, slot={slot})"
+        assert np.array_equal(gaps[:n_gap.value * 8], ref.gap_pool), f"gap pool differs (threads={threads}, slot={slot})"
+        if slot == 1:
+            assert nch.value > 2 * 4          # slot = the widest column: many chunks, the 4-slot ring wraps several times
+    # a GAP block whose header claims more than 1280 words is refused, like before
+    bad = bm.BVector(1); g = gen.gap_from_runs([65535], 0).copy(); g[0] = (1281 << 3); bad.set_gap(0, g)
+    arr2, keep2 = _vec_blocks_c([bad], 1)
+    n_bit, n_gap = C.c_uint64(0), C.c_uint64(0)
+    assert lib.host_pack_sizes(1, 1, arr2, 2, C.byref(n_bit), C.byref(n_gap)) == bm.capi.ERR_BADARG

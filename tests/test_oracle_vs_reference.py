@@ -428,3 +428,58 @@ def test_multi_superblock_blobs_with_bookmarks():
             for c in np.flatnonzero(dec):
                 assert np.array_equal(blk[c], rblk[c]) if kind[c] == bm.BLK_BIT else np.array_equal(gaps[c], rgap[c])
     assert n_ent > 1000
+
+
+@needs_ref
+def test_host_synth_blocks_are_what_optimize_stores():
+    """The benchmark generator, host form (oracle/bm_synth.c): its optimize()d set must hold exactly what the REAL
+    bvector::optimize(opt_compress) makes of the raw (all bit-block) set -- block kinds, GAP words, bits -- so 'stored the way
+    optimize() would store it' is pinned on the reference, not on the generator's own threshold.  Also: AVX-512 form == scalar form."""
+    nv, nb = 40, 6
+    dens = np.array([0.5 / (k + 1) for k in range(nv)]); dens[7] = 0.0; dens[9] = 1.0; dens[11] = 0.0098; dens[12] = 0.0097   # 11/12 straddle the 1276-run threshold
+    seed = np.arange(1000, 1000 + nv, dtype=np.uint64)
+    opt = orclib.HostSynth(nv, nb, dens, seed, True, threads=3)
+    raw = orclib.HostSynth(nv, nb, dens, seed, False, threads=2)
+    kinds_seen = set()
+    for v in range(nv):
+        kind, pop, blocks, gaps = orclib.ref_optimize(raw.ps, v)
+        for c in range(nb):
+            k, data = opt.ps.block(v, c)
+            assert k == kind[c], f"vector {v} block {c}: generator stores kind {k}, optimize() makes {kind[c]}"
+            kinds_seen.add(int(k))
+            if k == bm.BLK_GAP:
+                n = (int(gaps[c][0]) >> 3) + 1
+                assert np.array_equal(np.asarray(data), gaps[c][:n])
+            elif k == bm.BLK_BIT:
+                assert np.array_equal(np.asarray(data), blocks[c])
+    assert kinds_seen == {bm.BLK_NULL, bm.BLK_FULL, bm.BLK_BIT, bm.BLK_GAP}
+    k11 = {int(opt.ps.block(11, c)[0]) for c in range(nb)} | {int(opt.ps.block(12, c)[0]) for c in range(nb)}
+    assert k11 == {bm.BLK_BIT, bm.BLK_GAP}, "the threshold vectors should produce both kinds"
+    orclib.oracle().orc_synth_force_scalar(1)
+    try:
+        sc = orclib.HostSynth(nv, nb, dens, seed, True, threads=4)
+    finally:
+        orclib.oracle().orc_synth_force_scalar(0)
+    for a in ("desc", "bit_base", "gap_base", "bit_pool", "gap_pool"):
+        assert np.array_equal(getattr(sc.ps, a), getattr(opt.ps, a)), a
+
+
+@needs_ref
+def test_ref_job_matches_oracle_all_columns():
+    """The persistent reference job bench.py uses for its all-column parity (T workers, bvectors built once): kind / popcount /
+    digest / GAP length of every column equal the C oracle's, for ragged worker ranges, with and without opt_compress."""
+    nv, nb = 48, 11
+    dens = np.array([0.5 / (k + 1) for k in range(nv)])
+    seed = np.arange(77, 77 + nv, dtype=np.uint64)
+    hs = orclib.HostSynth(nv, nb, dens, seed, True, threads=2)
+    for op, g0, g1, flags in ((bm.OP_AND_SUB, [0, 1], list(range(2, nv)), bm.F_OPT_COMPRESS), (bm.OP_OR, list(range(5, nv)), None, bm.F_OPT_COMPRESS),
+                              (bm.OP_OR, list(range(20, nv)), None, bm.F_OPT_NONE), (bm.OP_AND, [3, 4, 5], None, bm.F_OPT_COMPRESS)):
+        ok, op_, od, onr, _, _ = orclib.oracle_aggregate(hs.ps, op, g0, g1, flags)
+        for threads in (1, 3, 11):
+            job = orclib.RefJob(hs.ps, op, g0, g1, flags, threads=threads)
+            sec, tot = job.run(2)
+            k, p, d, gl = job.export()
+            job.free()
+            assert tot == int(op_.sum())
+            assert np.array_equal(k, ok) and np.array_equal(p, op_) and np.array_equal(d, od)
+            assert np.array_equal(gl[k == bm.BLK_GAP], onr[k == bm.BLK_GAP])
