@@ -211,27 +211,34 @@ def run_reference(args):
     if mem_available_gb() < need_gb:
         return {"impl": "reference", "unavailable": f"host has {mem_available_gb():.0f} GB available, the workload needs {need_gb:.0f} GB"}
     t0 = time.time()
-    hs = orclib.HostSynth(w["n_vec"], n_cols, dens, seed, optimize, threads=cores)
+    hs = orclib.HostSynth(w["n_vec"], n_cols, dens, seed, optimize, threads=min(cores, 64))
     t_synth = time.time() - t0
     ps = hs.ps
     n_src_blocks = int((ps.kinds() != 0).sum())
     stored = ps.stored_bytes()
     have = orclib.have_ref()
     rows = {}
-    variants = [False] + (["avx512"] if (have and orclib.have_ref("avx512") and orclib.cpu_has_avx512()) else [])
+    # rows: (a) one worker per whole 256-block superblock range, T = min(nproc, superblocks) -- the split the reference's own
+    # top-level walk favours; (b) T = nproc workers over finer ranges (BASELINE.md section 3 "all cores"); (c) the AVX-512 build on (a).
+    t_sb = max(1, min(threads, n_cols // 256)) if n_cols >= 256 else threads
+    configs = [("avx2_sb", False, t_sb)]
+    if threads != t_sb:
+        configs.append(("avx2_nproc", False, threads))
+    if have and orclib.have_ref("avx512") and orclib.cpu_has_avx512():
+        configs.append(("avx512_sb", "avx512", t_sb))
     if not have:
         # the C port (oracle/bm_oracle.c), 1 thread -- only when oracle/_ref was not built (no /root/reference at build time)
         t0 = time.perf_counter(); orclib.oracle_aggregate(ps, op, g0, g1, flags, 0, min(n_cols, 256)); sec = time.perf_counter() - t0
         frac = min(n_cols, 256) / n_cols
         rows["port"] = {"ms": 1e3 * sec / frac, "threads": 1, "simd": "scalar", "result_bits": None, "extrapolated_from_cols": min(n_cols, 256)}
-    for var in variants if have else []:
+    for name, var, thr in configs if have else []:
         t0 = time.time()
-        job = orclib.RefJob(ps, op, g0, g1, flags, threads=threads, variant=var)
+        job = orclib.RefJob(ps, op, g0, g1, flags, threads=thr, variant=var)
         t_build = time.time() - t0
         job.run(max(1, args.warmup))
         sec, tot = job.run(args.steps)
-        rows[orclib.ref(var).ref_simd().decode()] = {"ms": 1e3 * float(np.mean(sec)), "ms_min": 1e3 * float(np.min(sec)), "threads": job.threads,
-                                                     "simd": orclib.ref(var).ref_simd().decode(), "result_bits": int(tot), "build_s": round(t_build, 2)}
+        rows[name] = {"ms": 1e3 * float(np.mean(sec)), "ms_min": 1e3 * float(np.min(sec)), "threads": job.threads,
+                      "simd": orclib.ref(var).ref_simd().decode(), "result_bits": int(tot), "build_s": round(t_build, 2)}
         job.free()
     best = min(rows, key=lambda k: rows[k]["ms"])
     ms = rows[best]["ms"]
@@ -243,7 +250,7 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": args.workload + ": " + w["desc"], "sample": sample, "reduced": bool(args.cols and args.cols != w["n_blocks"]),
-                       "inputs": f"host generator oracle/bm_synth.c, {t_synth:.1f} s on {cores} threads"},
+                       "inputs": f"host generator oracle/bm_synth.c, {t_synth:.1f} s on {min(cores, 64)} threads"},
             "cpu_baseline": {"value": value, "unit": "blocks/s", "cores": rows[best]["threads"], "kind": kind, "sample": sample,
                              "simd": rows[best]["simd"], "nproc": cores, "cpu": cpu_model(), "rows": rows,
                              "gbs": stored / (ms * 1e-3) / 1e9},
@@ -260,8 +267,10 @@ def full_parity(workload, n_cols, rank, res_meta, threads):
     op, g0, g1, flags = workload_groups(workload)
     kind_r, pop_r, dig_r, nr_r = res_meta
     t0 = time.time()
-    hs = orclib.HostSynth(w["n_vec"], n_cols, dens, seed, optimize, threads=threads)
+    hs = orclib.HostSynth(w["n_vec"], n_cols, dens, seed, optimize, threads=min(threads, 64))
     t_synth = time.time() - t0
+    if n_cols >= 256:
+        threads = max(1, min(threads, n_cols // 256))     # whole superblocks per reference worker (see run_reference)
     out = {"cols": int(n_cols), "fields": ["kind", "popcnt", "digest", "gap_len"], "inputs": "regenerated on the host (oracle/bm_synth.c)",
            "host_synth_s": round(t_synth, 2)}
     if orclib.have_ref():

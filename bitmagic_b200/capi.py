@@ -37,7 +37,7 @@ SYMBOLS = [
     "bmb200_rs_free", "bmb200_rs_rebuild", "bmb200_aggregate_batch", "bmb200_result_group_totals", "bmb200_result_or_target",
     "bmb200_scan", "bmb200_set_upload_blobs", "bmb200_result_fetch_view", "bmb200_ctx_bind_host_numa",
     "bmb200_shard_range", "bmb200_comm_unique_id", "bmb200_comm_init", "bmb200_comm_info", "bmb200_comm_destroy",
-    "bmb200_exchange_popcounts", "bmb200_exchange_fence", "bmb200_exchange_fetch",
+    "bmb200_exchange_popcounts", "bmb200_exchange_fence", "bmb200_exchange_fetch", "bmb200_ctx_trim",
 ]
 COMM_ID_BYTES = 128
 TUNE_GAP_MODE, TUNE_CTAS_PER_SM, TUNE_HOST_THREADS = 0, 1, 2
@@ -183,6 +183,10 @@ class Context:
         n = C.c_uint64(0)
         self.check(lib().bmb200_ctx_launch_count(self._h, C.byref(n)), "launch_count")
         return int(n.value)
+
+    def trim(self):
+        """Give the parked device arena (bmb200_set_free keeps the last freed set's arrays for the next upload) back to the driver."""
+        self.check(lib().bmb200_ctx_trim(self._h), "ctx_trim")
 
     def bind_host_numa(self) -> int:
         """Pin the calling thread to the CPUs of this GPU's NUMA node (bmb200_ctx_bind_host_numa); -> node or -1."""

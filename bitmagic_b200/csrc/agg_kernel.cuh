@@ -252,6 +252,19 @@ __device__ __noinline__ void flat_pair_tail(uint32_t Ls, uint32_t w)      // wor
     for (; rem >= 32u; rem -= 32u, a += 4u) reds_and(a, 0u);
     if (rem) reds_and(a, 0xffffffffu << rem);
 }
+#ifndef BMB200_FLAT_LEAN          /* 1: lean pair decode -- hi - lo by one dp2a, word address by one and-or (L is 8 KB aligned) */
+#define BMB200_FLAT_LEAN 1
+#endif
+// hi16(w) - lo16(w) in one instruction: dp2a.lo = c + lo16(a) * sbyte0(b) + hi16(a) * sbyte1(b) with b = (+1, -1)   (SASS IDP.2A)
+__device__ __forceinline__ int pair_width(uint32_t w)
+{
+    int d; asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(0x000001ffu), "r"(0)); return d;
+}
+// ((x & 0x1ffc) | base): one LOP3 (base = shared address of L, 8 KB aligned, so the OR is the add)
+__device__ __forceinline__ uint32_t and_or(uint32_t x, uint32_t msk, uint32_t base)
+{
+    uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(x), "r"(msk), "r"(base)); return r;
+}
 template <bool TEST>
 __device__ __forceinline__ void flat_quad(uint32_t Ls, const uint4& q)
 {
@@ -259,12 +272,21 @@ __device__ __forceinline__ void flat_quad(uint32_t Ls, const uint4& q)
     uint32_t a[4], m[4], nm[4], reach = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+#if BMB200_FLAT_LEAN
+        const uint32_t t = w[i] + 1u;                                         // low half = run start s = lo + 1 (s == 65536 wraps to 0: pad / terminator, mask 0)
+        const uint32_t sb = t & 31u;
+        const uint32_t wd = (uint32_t)max(pair_width(w[i]), 0);               // wd == 0: no run
+        m[i] = bmsk(sb, wd);
+        nm[i] = ~m[i];
+        a[i] = and_or(t >> 3, 0x1ffcu, Ls);
+#else
         const uint32_t lo = w[i] & 0xffffu, hi = w[i] >> 16;
         const uint32_t s = lo + 1u, sb = s & 31u;
         const uint32_t wd = (uint32_t)max((int)hi - (int)lo, 0);              // wd == 0: no run
         m[i] = bmsk(sb, wd);
         nm[i] = ~m[i];
         a[i] = Ls + ((s >> 3) & 0x1ffcu);                                     // s == 65536 (pad / terminator) wraps to word 0, mask 0
+#endif
         reach = max(reach, sb + wd);
     }
     if (TEST) {
@@ -445,7 +467,7 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     uint32_t* ring = reinterpret_cast<uint32_t*>(dyn_smem);
 
-    __shared__ __align__(16) uint32_t K[kBlockWords];   // the live mask L (see the header comment)
+    __shared__ __align__(8192) uint32_t K[kBlockWords]; // the live mask L (see the header comment); 8 KB aligned: word addresses are formed with one and-or
     __shared__ uint32_t lst_bit0[kAggChunk];
     __shared__ uint32_t lst_bit1[kAggChunk];
     __shared__ uint32_t lst_gap[kAggChunk];      // group0 GAPs from the front, group1 GAPs from the back (both in member order)

@@ -57,6 +57,10 @@ struct bmb200_ctx {
     void* h_pool[5] = {};                   // grow-only pinned scratch of the same entry points
     size_t h_pool_cap[5] = {};
     CommState comm;                         // multi-GPU exchange (bmb200_comm_*), unused on one GPU
+    // ONE recycled device arena: bmb200_set_free parks the arrays of the last freed set here and the next set_alloc that fits takes
+    // them, so that a cold upload per call (no residency) does not pay cudaMalloc + cudaFree of a multi-GB arena (25 - 230 ms) each time;
+    // released by bmb200_ctx_trim / bmb200_destroy
+    struct Arena { void *desc = nullptr, *bb = nullptr, *gb = nullptr, *bp = nullptr, *gp = nullptr; size_t cap_desc = 0, cap_base = 0, cap_bit = 0, cap_gap = 0; bool full = false; } arena;
 };
 
 struct bmb200_set {
@@ -65,6 +69,7 @@ struct bmb200_set {
     bool owns = false;
     uint64_t n_bit_blocks = 0, n_gap_units = 0;
     uint64_t gap_pool_bytes = 0;            // readable bytes of gap_pool (with the allocation slack when owned)
+    size_t cap_desc = 0, cap_base = 0, cap_bit = 0, cap_gap = 0;   // capacities when the arrays came from set_alloc (elements / blocks / units); 0 = not recyclable
 };
 
 struct bmb200_result {
@@ -256,6 +261,7 @@ int bmb200_destroy(bmb200_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->host_res) bmb200_result_free(ctx->host_res);
     if (ctx->host_set) bmb200_set_free(ctx->host_set);
+    bmb200_ctx_trim(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     cudaFree(ctx->d_work); cudaFree(ctx->d_group);
     if (ctx->h_group) cudaFreeHost(ctx->h_group);
@@ -340,6 +346,16 @@ static int set_alloc(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, uint64_
     s->gap_pool_bytes = n_gap_units * 16ull + kSlack;
     int rc;
     uint32_t* desc = nullptr; uint64_t *bb = nullptr, *gb = nullptr; uint32_t* bp = nullptr; uint16_t* gp = nullptr;
+    s->cap_desc = (size_t)n_vec * n_blocks; s->cap_base = (size_t)n_blocks + 1; s->cap_bit = n_bit; s->cap_gap = n_gap_units;
+    if (ctx->arena.full && ctx->arena.cap_desc >= s->cap_desc && ctx->arena.cap_base >= s->cap_base && ctx->arena.cap_bit >= n_bit && ctx->arena.cap_gap >= n_gap_units) {
+        auto& a = ctx->arena;                 // recycle the parked arena (the stream was synchronized when it was parked)
+        s->v.desc = (uint32_t*)a.desc; s->v.bit_base = (uint64_t*)a.bb; s->v.gap_base = (uint64_t*)a.gb; s->v.bit_pool = (uint32_t*)a.bp; s->v.gap_pool = (uint16_t*)a.gp;
+        s->cap_desc = a.cap_desc; s->cap_base = a.cap_base; s->cap_bit = a.cap_bit; s->cap_gap = a.cap_gap;
+        a = bmb200_ctx::Arena();
+        cudaMemsetAsync((char*)s->v.gap_pool + (size_t)n_gap_units * kGapUnit * 2, 0, kSlack, ctx->stream);
+        *out = s;
+        return BMB200_OK;
+    }
     if ((rc = dev_alloc(ctx, &desc, (size_t)n_vec * n_blocks)) ||
         (rc = dev_alloc(ctx, &bb, (size_t)n_blocks + 1)) ||
         (rc = dev_alloc(ctx, &gb, (size_t)n_blocks + 1)) ||
@@ -443,17 +459,24 @@ int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks
             PackPipeline pipe(n_vec, n_blocks, vecs, &L, &chunks, ctx->h_ring);
             pipe.start((unsigned)ctx->host_threads);
             const uint32_t nch = (uint32_t)chunks.size();
+            double t_pack = 0, t_dma = 0;
+            auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
             for (uint32_t c = 0; c < nch && e == cudaSuccess; ++c) {
+                const double w0 = tr.on ? now() : 0;
                 pipe.wait_chunk(c);
+                if (tr.on) t_pack += now() - w0;
                 const PackChunk& ch = chunks[c];
                 uint8_t* base = ctx->h_ring[c % kStageSlots];
                 if (ch.bit_bytes) e = cudaMemcpyAsync((uint8_t*)s->v.bit_pool + L.bb[ch.c0] * (uint64_t)BMB200_BLOCK_BYTES, base, ch.bit_bytes, cudaMemcpyHostToDevice, st);
                 if (e == cudaSuccess && ch.gap_bytes) e = cudaMemcpyAsync((uint8_t*)s->v.gap_pool + L.gb[ch.c0] * 16ull, base + ch.bit_bytes, ch.gap_bytes, cudaMemcpyHostToDevice, st);
                 if (e == cudaSuccess) e = cudaEventRecord(ctx->ring_ev[c % kStageSlots], st);
                 // the copy of chunk c is queued behind the one of chunk c-1: once c-1 has landed its slot goes back to the packers
-                if (e == cudaSuccess && c >= 1) { e = cudaEventSynchronize(ctx->ring_ev[(c - 1) % kStageSlots]); pipe.release_through(c); }
+                if (e == cudaSuccess && c >= 1) { const double w1 = tr.on ? now() : 0; e = cudaEventSynchronize(ctx->ring_ev[(c - 1) % kStageSlots]);
+                                                  if (tr.on) t_dma += now() - w1; pipe.release_through(c); }
             }
             pipe.join();
+            if (tr.on) fprintf(stderr, "[bmb200] set_upload_vectors: %u chunks of <= %.0f MB, issuing thread waited %.1f ms for the packers and %.1f ms for the DMA\n",
+                               nch, slot_bytes / 1048576.0, t_pack, t_dma);
         } catch (...) { return fail(BMB200_ERR_BADALLOC, cudaSuccess); }
         if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
     }
@@ -874,10 +897,25 @@ int bmb200_set_device_ptrs(const bmb200_set* s, bmb200_packed_set* out)
 int bmb200_set_free(bmb200_set* s)
 {
     if (!s) return BMB200_ERR_BADARG;
-    cudaSetDevice(s->ctx->device);
-    cudaStreamSynchronize(s->ctx->stream);
-    free_set_arrays(s);
+    bmb200_ctx* ctx = s->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (s->owns && s->cap_desc && !ctx->arena.full) {       // park the arrays for the next upload instead of cudaFree
+        auto& a = ctx->arena;
+        a.desc = (void*)s->v.desc; a.bb = (void*)s->v.bit_base; a.gb = (void*)s->v.gap_base; a.bp = (void*)s->v.bit_pool; a.gp = (void*)s->v.gap_pool;
+        a.cap_desc = s->cap_desc; a.cap_base = s->cap_base; a.cap_bit = s->cap_bit; a.cap_gap = s->cap_gap; a.full = true;
+    } else free_set_arrays(s);
     delete s;
+    return BMB200_OK;
+}
+
+int bmb200_ctx_trim(bmb200_ctx* ctx)
+{
+    if (!ctx) return BMB200_ERR_BADARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    auto& a = ctx->arena;
+    if (a.full) { cudaFree(a.desc); cudaFree(a.bb); cudaFree(a.gb); cudaFree(a.bp); cudaFree(a.gp); a = bmb200_ctx::Arena(); }
     return BMB200_OK;
 }
 

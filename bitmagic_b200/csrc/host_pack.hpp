@@ -8,8 +8,10 @@
 // block column on every call); here the gather happens ONCE per upload and the result stays resident (bm::b200::device_set).
 #pragma once
 #include <atomic>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -128,6 +130,7 @@ inline uint64_t pack_max_column_bytes(const PackLayout& L, uint32_t n_blocks)
 
 // The pipeline: worker threads claim columns in order and pack them into the slot of their chunk; the caller's thread (`issue`)
 // is told when a chunk is complete, starts its H2D copies and later releases the slot (`released` = chunks whose slot is free again).
+// Both waits block on condition variables: idle packers sleep instead of spinning next to the ones that copy.
 struct PackPipeline {
     uint32_t n_vec = 0, n_blocks = 0;
     const bmb200_vec_blocks* vecs = nullptr;
@@ -137,7 +140,9 @@ struct PackPipeline {
     std::vector<uint32_t> chunk_of_col;
     std::vector<std::atomic<uint32_t>> remaining;      // columns left per chunk
     std::atomic<uint32_t> next_col{0};
-    std::atomic<uint32_t> released{0};
+    std::mutex mu;
+    std::condition_variable cv_free, cv_done;
+    uint32_t released = 0;                             // guarded by mu
     std::vector<std::thread> th;
 
     PackPipeline(uint32_t nv, uint32_t nb, const bmb200_vec_blocks* v, const PackLayout* l, const std::vector<PackChunk>* ch, uint8_t* const* s)
@@ -155,22 +160,45 @@ struct PackPipeline {
     }
     void run()
     {
+        uint32_t seen_released = 0;
         for (;;) {
             const uint32_t nb = next_col.fetch_add(1, std::memory_order_relaxed);
             if (nb >= n_blocks) return;
             const uint32_t c = chunk_of_col[nb];
-            while (c >= released.load(std::memory_order_acquire) + kStageSlots) std::this_thread::yield();
+            if (c >= seen_released + kStageSlots) {                       // the slot of chunk c is still owned by chunk c - kStageSlots
+                std::unique_lock<std::mutex> lk(mu);
+                cv_free.wait(lk, [&]() { return c < released + kStageSlots; });
+                seen_released = released;
+            }
             const PackChunk& ch = (*chunks)[c];
             uint8_t* base = slot[c % kStageSlots];
             uint8_t* bit_dst = base + (L->bb[nb] - L->bb[ch.c0]) * (uint64_t)BMB200_BLOCK_BYTES;
             uint8_t* gap_dst = base + ch.bit_bytes + (L->gb[nb] - L->gb[ch.c0]) * 16ull;
             pack_column(n_vec, nb, vecs, L->desc.data() + (size_t)nb * n_vec, bit_dst, gap_dst);
-            remaining[c].fetch_sub(1, std::memory_order_acq_rel);
+            if (remaining[c].fetch_sub(1, std::memory_order_acq_rel) == 1) {   // last column of the chunk: wake the issuing thread
+                std::lock_guard<std::mutex> lk(mu);
+                cv_done.notify_all();
+            }
         }
     }
-    void wait_chunk(uint32_t c) const { while (remaining[c].load(std::memory_order_acquire) != 0) std::this_thread::yield(); }
-    void release_through(uint32_t c) { released.store(c, std::memory_order_release); }     // chunks [0, c) are free
-    void join() { next_col.store(n_blocks, std::memory_order_relaxed); released.store(0xffffffffu - kStageSlots, std::memory_order_release); for (auto& x : th) x.join(); th.clear(); }
+    void wait_chunk(uint32_t c)
+    {
+        if (remaining[c].load(std::memory_order_acquire) == 0) return;
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&]() { return remaining[c].load(std::memory_order_acquire) == 0; });
+    }
+    void release_through(uint32_t c)                                        // chunks [0, c) are free
+    {
+        { std::lock_guard<std::mutex> lk(mu); released = c; }
+        cv_free.notify_all();
+    }
+    void join()
+    {
+        next_col.store(n_blocks, std::memory_order_relaxed);
+        release_through(0xffffffffu - kStageSlots);
+        for (auto& x : th) x.join();
+        th.clear();
+    }
     ~PackPipeline() { if (!th.empty()) join(); }
 };
 

@@ -183,6 +183,9 @@ int bmb200_ctx_set_tuning(bmb200_ctx* ctx, int key, int value);
  * node this context's GPU hangs off, so that pinned staging memory is allocated next to the GPU's PCIe root.  *node = the node, or
  * -1 when the box has no NUMA information (then nothing is changed).  Call it before the first upload. */
 int bmb200_ctx_bind_host_numa(bmb200_ctx* ctx, int* node);
+/* bmb200_set_free parks the device arena of the set it frees in the context (at most one) and the next upload that fits reuses it,
+ * so per-call uploads do not pay cudaMalloc / cudaFree of a multi-GB arena every time; bmb200_ctx_trim gives that memory back */
+int bmb200_ctx_trim(bmb200_ctx* ctx);
 
 /* ---------------- sets ---------------- */
 /* copy a packed set from HOST memory (pinned or pageable) into HBM */

@@ -99,11 +99,13 @@ static void synth_block(uint64_t seed, uint32_t nb, uint32_t thr, uint32_t* w)
     }
 }
 
+/* thread-local output grows in few, large steps (x2, at least 32 MB worth of elements): every realloc of a big array is an
+ * mremap that takes the process-wide mmap lock, and 128 threads doing that often stall each other's page faults */
 static int grow(void** p, size_t* cap, size_t need, size_t elem)
 {
     if (need <= *cap) return 0;
-    size_t nc = *cap ? *cap : (1u << 16);
-    while (nc < need) nc += nc / 2 + 4096;
+    size_t nc = *cap ? *cap * 2 : (size_t)(32u << 20) / elem;
+    while (nc < need) nc *= 2;
     void* q = realloc(*p, nc * elem);
     if (!q) return 1;
     *p = q; *cap = nc;

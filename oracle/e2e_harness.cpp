@@ -13,6 +13,7 @@
  * The oracle is not involved here; the reference headers only provide the container type the product binds to.
  */
 #include <chrono>
+#include <malloc.h>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -99,6 +100,7 @@ extern "C" {
 void* e2e_create_empty(uint32_t n_vec, uint32_t n_blocks, int device, int numa, int* numa_node)
 {
     try {
+        mallopt(M_TOP_PAD, 64 << 20);      /* many threads fill the bvectors through malloc: grow the arenas in big steps (mmap lock) */
         std::unique_ptr<Harness> h(new Harness());
         h->ctx.reset(new bm::b200::context(device));
         int node = -1;

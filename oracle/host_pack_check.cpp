@@ -25,8 +25,8 @@ extern "C" int host_pack_sizes(uint32_t n_vec, uint32_t n_blocks, const bmb200_v
     return 0;
 }
 
-extern "C" int host_pack_check(uint32_t n_vec, uint32_t n_blocks, const bmb200_vec_blocks* vecs, int threads, uint64_t slot_bytes,
-                               uint32_t* desc, uint64_t* bb, uint64_t* gb, uint8_t* bit_pool, uint8_t* gap_pool, uint32_t* n_chunks)
+extern "C" int host_pack_check2(uint32_t n_vec, uint32_t n_blocks, const bmb200_vec_blocks* vecs, int threads, uint64_t slot_bytes,
+                                uint32_t* desc, uint64_t* bb, uint64_t* gb, uint8_t* bit_pool, uint8_t* gap_pool, uint32_t* n_chunks, int poison)
 {
     PackLayout L;
     pack_layout(n_vec, n_blocks, vecs, (unsigned)threads, L);
@@ -47,13 +47,20 @@ extern "C" int host_pack_check(uint32_t n_vec, uint32_t n_blocks, const bmb200_v
         for (uint32_t c = 0; c < chunks.size(); ++c) {
             pipe.wait_chunk(c);
             const PackChunk& ch = chunks[c];
+            if (poison >= 0) {
             memcpy(bit_pool + L.bb[ch.c0] * (uint64_t)BMB200_BLOCK_BYTES, slot[c % kStageSlots], ch.bit_bytes);
-            memcpy(gap_pool + L.gb[ch.c0] * 16ull, slot[c % kStageSlots] + ch.bit_bytes, ch.gap_bytes);
-            memset(slot[c % kStageSlots], 0xA5, slot_bytes);     // the slot is recycled: whatever the next chunk does not write stays garbage
+            memcpy(gap_pool + L.gb[ch.c0] * 16ull, slot[c % kStageSlots] + ch.bit_bytes, ch.gap_bytes); }
+            if (poison) memset(slot[c % kStageSlots], 0xA5, slot_bytes);     // the slot is recycled: whatever the next chunk does not write stays garbage
             if (c >= 1) pipe.release_through(c);                 // same protocol as the product: slot of chunk c-1 is free once copy c is queued
         }
         pipe.join();
     }
     for (uint32_t k = 0; k < kStageSlots; ++k) free(slot[k]);
     return 0;
+}
+
+extern "C" int host_pack_check(uint32_t n_vec, uint32_t n_blocks, const bmb200_vec_blocks* vecs, int threads, uint64_t slot_bytes,
+                               uint32_t* desc, uint64_t* bb, uint64_t* gb, uint8_t* bit_pool, uint8_t* gap_pool, uint32_t* n_chunks)
+{
+    return host_pack_check2(n_vec, n_blocks, vecs, threads, slot_bytes, desc, bb, gb, bit_pool, gap_pool, n_chunks, 1);
 }

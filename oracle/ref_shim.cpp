@@ -21,6 +21,7 @@
 #include <thread>
 #include <chrono>
 #include <algorithm>
+#include <malloc.h>
 
 #include "bm.h"
 #include "bmaggregator.h"
@@ -616,6 +617,9 @@ struct RefJob {
 void* ref_job_create(const bmb200_packed_set* s, const bmb200_agg_args* a, int threads)
 {
     try {
+        /* the workers build ~13 GB of 8 KB / sub-KB blocks through malloc at the same time: let every malloc arena grow in 64 MB
+         * steps instead of 128 KB ones (each step is an mprotect under the process-wide mmap lock, which also stalls page faults) */
+        mallopt(M_TOP_PAD, 64 << 20);
         std::unique_ptr<RefJob> j(new RefJob());
         j->a = *a;
         j->g0.assign(a->group0, a->group0 + a->n0); j->a.group0 = j->g0.data();
@@ -626,9 +630,13 @@ void* ref_job_create(const bmb200_packed_set* s, const bmb200_agg_args* a, int t
         if (threads < 1) threads = 1;
         if ((uint32_t)threads > j->ncols) threads = (int)j->ncols;
         j->built.resize(threads); j->lo.resize(threads); j->hi.resize(threads); j->target.resize(threads);
+        /* whole 256-block superblocks per worker whenever there are at least `threads` of them: the reference walks all 256
+         * sub-blocks of every top-level block it touches (src/bmaggregator.h:1565-1566), so a finer split makes it do extra work */
+        const uint32_t nsb = j->ncols / 256u;
+        const bool aligned = (j->ncols % 256u == 0) && nsb >= (uint32_t)threads;
         for (int t = 0; t < threads; ++t) {
-            j->lo[t] = a->nb_from + (uint32_t)((uint64_t)j->ncols * t / threads);
-            j->hi[t] = a->nb_from + (uint32_t)((uint64_t)j->ncols * (t + 1) / threads);
+            if (aligned) { j->lo[t] = a->nb_from + 256u * (uint32_t)((uint64_t)nsb * t / threads); j->hi[t] = a->nb_from + 256u * (uint32_t)((uint64_t)nsb * (t + 1) / threads); }
+            else { j->lo[t] = a->nb_from + (uint32_t)((uint64_t)j->ncols * t / threads); j->hi[t] = a->nb_from + (uint32_t)((uint64_t)j->ncols * (t + 1) / threads); }
             j->target[t].reset(new bvect());
         }
         std::vector<std::thread> th;

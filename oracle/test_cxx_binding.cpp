@@ -70,6 +70,46 @@ int main()
             CHECK(gpu.count_and_sub(all.data(), na, all.data() + na, all.size() - na) == t_ref.count(), "count_and_sub na=%zu", na);
         }
     }
+    {   // residency: bm::b200::device_set uploaded once, then every call whose sources are members runs on the device copy
+        bm::b200::device_set<bvect> ds(ctx);
+        ds.assign(all.data(), all.size());
+        CHECK(ds.resident() && ds.size() == all.size() && !ds.stale(), "device_set assign");
+        CHECK(ds.index_of(all[5]) == 5 && ds.index_of(nullptr) < 0, "device_set index_of");
+        bm::aggregator<bvect> ref; ref.set_optimization(bvect::opt_compress);
+        bm::b200::aggregator<bvect> gpu(ctx); gpu.set_optimization(bvect::opt_compress); gpu.set_device_set(&ds);
+        for (int rep = 0; rep < 3; ++rep) {                   // repeated calls recycle the result buffers
+            for (size_t n : {size_t(2), size_t(9), all.size()}) {
+                bvect t_ref, t_gpu;
+                ref.combine_or(t_ref, all.data() + rep, n - rep); gpu.combine_or(t_gpu, all.data() + rep, n - rep);
+                CHECK(t_ref.compare(t_gpu) == 0 && t_ref.count() == t_gpu.count(), "resident combine_or n=%zu rep=%d", n, rep);
+                bvect::statistics s1, s2; t_ref.calc_stat(&s1); t_gpu.calc_stat(&s2);
+                CHECK(s1.bit_blocks == s2.bit_blocks && s1.gap_blocks == s2.gap_blocks, "resident combine_or kinds n=%zu", n);
+            }
+            bvect t_ref, t_gpu;
+            bool f1 = ref.combine_and_sub(t_ref, all.data(), 2, all.data() + 2 + rep, all.size() - 2 - rep, false);
+            bool f2 = gpu.combine_and_sub(t_gpu, all.data(), 2, all.data() + 2 + rep, all.size() - 2 - rep, false);
+            CHECK(f1 == f2 && t_ref.compare(t_gpu) == 0, "resident combine_and_sub rep=%d", rep);
+            CHECK(gpu.count_and_sub(all.data(), 2, all.data() + 2, all.size() - 2) == [&]{ bvect t; ref.combine_and_sub(t, all.data(), 2, all.data() + 2, all.size() - 2, false); return t.count(); }(), "resident count_and_sub");
+        }
+        {   // a source that is NOT a member: the call falls back to its own upload, same answer
+            bvect extra; fill(extra, rng, n_bits, 0.01, false);
+            const bvect* mix[3] = {all[0], &extra, all[7]};
+            bvect t_ref, t_gpu; ref.combine_or(t_ref, mix, 3); gpu.combine_or(t_gpu, mix, 3);
+            CHECK(t_ref.compare(t_gpu) == 0, "non-member source falls back to upload");
+        }
+        {   // a shard of the block range: result holds those blocks only (what one rank of a sharded aggregation sees)
+            bm::b200::device_set<bvect> sh(ctx);
+            sh.assign(all.data(), all.size(), 10, 30);
+            bm::b200::aggregator<bvect> g2(ctx); g2.set_optimization(bvect::opt_compress); g2.set_device_set(&sh);
+            bvect t_ref, t_gpu; ref.combine_or(t_ref, all.data(), all.size()); g2.combine_or(t_gpu, all.data(), all.size());
+            bvect mask; mask.set_range(10u * 65536u, 30u * 65536u - 1u);
+            t_ref &= mask;
+            CHECK(t_ref.compare(t_gpu) == 0, "shard [10,30): result restricted to the shard's blocks");
+        }
+        vs[3]->resize(n_bits + 70000);                        // the O(1) stamp notices a resize
+        CHECK(ds.stale(), "device_set stale() after resize");
+        vs[3]->resize(n_bits);
+    }
     {   // member forms with add()/reset(), as samples/bvsample16/sample16.cpp uses them
         bm::aggregator<bvect> ref; bm::b200::aggregator<bvect> gpu(ctx);
         for (int k = 0; k < 3; ++k) { ref.add(all[k]); gpu.add(all[k]); }

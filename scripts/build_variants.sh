@@ -4,8 +4,8 @@ set -e
 cd "$(dirname "$0")/.."
 mkdir -p scripts/_bin
 rm -f scripts/_bin/*.so
-build() { name=$1; shift; nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared "$@" -o scripts/_bin/libbmb200_$name.so bitmagic_b200/csrc/capi.cu -lcudart & }
-build e1
-build e2 -DBMB200_FLAT_SLOTS=2
+build() { name=$1; shift; nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared "$@" -o scripts/_bin/libbmb200_$name.so bitmagic_b200/csrc/capi.cu -lcudart -ldl & }
+build old -DBMB200_FLAT_LEAN=0
+build lean1slot -DBMB200_FLAT_SLOTS=1
 wait
 ls -la scripts/_bin/

@@ -514,7 +514,7 @@ def test_adopt_device_memory_and_no_leaks(ctx):
     assert np.array_equal(kind, okind) and np.array_equal(pop, opop)
     res.free(); dset.free()
     assert bool((t_bp[: ps.bit_pool.nbytes].cpu().numpy().view(np.uint32) == ps.bit_pool).all())   # adopted memory untouched, still owned by torch
-    ctx.sync(); torch.cuda.synchronize()
+    ctx.trim(); ctx.sync(); torch.cuda.synchronize()
     free0 = torch.cuda.mem_get_info(0)[0]
     for _ in range(20):
         d = bm.DeviceSet.upload(ctx, ps)
@@ -523,7 +523,9 @@ def test_adopt_device_memory_and_no_leaks(ctx):
         r.fetch(); rs.rank(np.arange(10, dtype=np.uint64))
         rs.free(); r.free(); d.free()
     ctx.sync()
-    assert torch.cuda.mem_get_info(0)[0] >= free0 - (4 << 20), "device memory leaked across create/free cycles"
+    assert torch.cuda.mem_get_info(0)[0] >= free0 - (4 << 20), "device memory leaked across create/free cycles"   # incl. the one parked arena
+    ctx.trim()
+    assert torch.cuda.mem_get_info(0)[0] >= free0 - (2 << 20)
 
 
 def check_scan(ctx, ps, dset, pred, search, plane0, npl, uni, flags=C):
@@ -777,3 +779,159 @@ def test_c1_config_bit_and_count(ctx):
     if orclib.have_ref():
         rkind, rpop, rblk, rcnt = orclib.ref_binop(ps, 1, 0, 1)
         assert np.array_equal(rblk, want) and rcnt == t.count() == orclib.ref_count_op(ps, 1, 0, 1)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# round 2: full-size parity in the test records, generator pinned on the reference, residency / e2e paths
+# ----------------------------------------------------------------------------------------------------------------------
+def _host_mem_gb():
+    try:
+        return int(next(ln for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")).split()[1]) / 2**20
+    except Exception:
+        return 0.0
+
+
+def test_device_generator_equals_host_generator_bit_for_bit(ctx):
+    """bmb200_synth_set (CUDA) and oracle/bm_synth.c (host, pinned on bvector::optimize() by the CPU tests) are two independent
+    implementations of the benchmark generator: every array of the packed set must be identical -- so the bench's inputs are
+    exactly what the reference arm and the parity check regenerate on the host."""
+    import os
+    for nv, nbk, dens, opt in ((48, 7, np.array([0.5 / (k + 1) for k in range(48)]), True), (9, 5, np.full(9, 0.05), False),
+                               (33, 4, np.concatenate([np.full(30, 0.0025), [0.0, 1.0, 0.0098]]), True)):
+        seed = np.arange(31, 31 + nv, dtype=np.uint64) * np.uint64(7919)
+        dset = bm.DeviceSet.synth(ctx, nv, nbk, dens, seed, opt)
+        ps = dset.download()
+        hs = orclib.HostSynth(nv, nbk, dens, seed, opt, threads=min(4, os.cpu_count() or 1))
+        for a in ("desc", "bit_base", "gap_base", "bit_pool", "gap_pool"):
+            assert np.array_equal(getattr(ps, a), getattr(hs.ps, a)), f"{a} differs (n_vec={nv})"
+        hs.free(); dset.free()
+
+
+def _all_column_parity(ctx, nv, nbk, dens, seed, optimize, op, g0, g1, flags, threads):
+    dset = bm.DeviceSet.synth(ctx, nv, nbk, dens, seed, optimize)
+    res = bm.aggregate(ctx, dset, op, g0, g1, flags)
+    kind, pop, dig, nr = res.meta()
+    total, _ = res.total()
+    hs = orclib.HostSynth(nv, nbk, dens, seed, optimize, threads=threads)
+    assert hs.ps.stored_bytes() == dset.stored_bytes()
+    job = orclib.RefJob(hs.ps, op, g0, g1, flags, threads=threads)
+    sec, tot = job.run(1)
+    k, p, d, gl = job.export()
+    job.free(); hs.free()
+    assert tot == total
+    assert np.array_equal(k, kind), "block kinds"
+    assert np.array_equal(p, pop), "popcounts"
+    assert np.array_equal(d, dig), "digests"
+    assert np.array_equal(gl[k == bm.BLK_GAP], nr[k == bm.BLK_GAP]), "GAP lengths"
+    res.free(); dset.free()
+    return int(total)
+
+
+@pytest.mark.skipif(not orclib.have_ref(), reason="prebuilt reference library not present")
+def test_c2_full_size_all_columns_vs_reference(ctx):
+    """BASELINE config 2 at FULL size (combine_or over 256 x 2^28 bits, 5 %, bit-blocks = 8 GiB): kind, popcount and digest of
+    all 4096 result columns against the unmodified reference (all host cores) on host-regenerated inputs."""
+    import os
+    if _host_mem_gb() < 24:
+        pytest.skip("needs ~20 GB of host memory")
+    nv, nbk = 256, 4096
+    dens = np.full(nv, 0.05); seed = np.arange(100, 100 + nv, dtype=np.uint64)
+    tot = _all_column_parity(ctx, nv, nbk, dens, seed, False, bm.OP_OR, np.arange(nv, dtype=np.uint32), None, bm.F_OPT_NONE, os.cpu_count() or 1)
+    assert tot > 0.99 * nbk * 65536           # 0.95^256: practically all ones
+
+
+@pytest.mark.skipif(not orclib.have_ref(), reason="prebuilt reference library not present")
+def test_c3_quarter_size_all_columns_vs_reference(ctx):
+    """BASELINE config 3's recipe on 4096 of its 16384 block columns (the bench line itself carries the full-size check): AND-SUB
+    over 1024 Zipf vectors, every column's kind / popcount / digest / GAP length against the unmodified reference."""
+    import os
+    if _host_mem_gb() < 12:
+        pytest.skip("needs ~10 GB of host memory")
+    nv, nbk = 1024, 4096
+    dens = np.array([0.5 / (k + 1) for k in range(nv)]); seed = np.arange(1000, 1000 + nv, dtype=np.uint64)
+    _all_column_parity(ctx, nv, nbk, dens, seed, True, bm.OP_AND_SUB, np.array([0, 1], np.uint32), np.arange(2, nv, dtype=np.uint32), C, os.cpu_count() or 1)
+
+
+@pytest.mark.skipif(not orclib.have_ref(True), reason="prebuilt BM64ADDR reference library not present")
+@pytest.mark.parametrize("optimize", [False, True])
+def test_c4_full_size_rs_index_rank_select_vs_reference64(ctx, optimize):
+    """BASELINE config 4 at FULL size: one 2^32-bit vector (65536 blocks, 1 %), rs_index fields + 10 M count_to + 10 M select,
+    ALL answers against the unmodified reference built with -DBM64ADDR (oracle/_ref/libbmref64.so)."""
+    if _host_mem_gb() < 6:
+        pytest.skip("needs ~4 GB of host memory")
+    nbk, nq = 65536, 10_000_000
+    dset = bm.DeviceSet.synth(ctx, 1, nbk, np.array([0.01]), np.array([7], np.uint64), optimize)
+    rs = bm.DeviceRS(ctx, dset, 0)
+    total = rs.total()
+    bc, sc, sb = rs.export()
+    rng = np.random.default_rng(8)
+    pos = rng.integers(0, nbk * 65536, nq, dtype=np.uint64)
+    rank = rng.integers(1, total + 1, nq, dtype=np.uint64)
+    rank[:3] = (0, total, total + 1)                     # select fails for rank 0 and rank > count
+    g_rank = rs.rank(pos)
+    g_sel, g_found = rs.select(rank)
+    ps = dset.download()
+    rbc, rsc, rsb, rtot = orclib.ref_rs_build(ps, 0, addr64=True)
+    assert rtot == total and np.array_equal(rbc, bc) and np.array_equal(rsb, sb)
+    nz = (ps.kinds()[:, 0] == bm.BLK_BIT) | (ps.kinds()[:, 0] == bm.BLK_GAP)
+    assert np.array_equal(rsc[nz], sc[nz])
+    r_rank, r_sel, r_found, _ = orclib.ref_rank_select(ps, 0, pos, rank, addr64=True)
+    assert np.array_equal(g_rank, r_rank)
+    assert np.array_equal(g_found, r_found) and not g_found[0] and g_found[1] and not g_found[2]
+    assert np.array_equal(g_sel[g_found], r_sel[r_found])
+    rs.free(); dset.free()
+
+
+def test_upload_vectors_pipeline_many_chunks_and_threads(ctx):
+    """bmb200_set_upload_vectors: threaded packing through the pinned staging ring.  A set whose columns exceed one slot several
+    times over (forced small by 1 host thread vs many) must arrive bit-exact and aggregate like the plainly uploaded packed set."""
+    rng = np.random.default_rng(5)
+    vecs = gen.mixed_vectors(rng, 40, 48, p_null=0.05)
+    ps = bm.PackedSet.pack(vecs)
+    for threads in (1, 0, 7):
+        ctx.set_tuning(bm.capi.TUNE_HOST_THREADS, threads)
+        dset = bm.DeviceSet.upload_vectors(ctx, vecs)
+        back = dset.download()
+        for a in ("desc", "bit_base", "gap_base", "bit_pool", "gap_pool"):
+            assert np.array_equal(getattr(back, a), getattr(ps, a)), f"{a} (threads={threads})"
+        check_vs_oracle(ctx, ps, bm.OP_AND_SUB, [0, 1, 2], list(range(3, 40)), C, dset)
+        dset.free()
+    ctx.set_tuning(bm.capi.TUNE_HOST_THREADS, 0)
+
+
+def test_e2e_harness_real_bvectors_cold_warm_and_check(ctx):
+    """oracle/_ref/libbmb200_e2e.so (bench.py's e2e leg): bm::b200::aggregator on real bm::bvector<> objects -- cold call, warm call
+    on a bm::b200::device_set, and the reference aggregator on the same bvectors (compare() == 0 + calc_stat kinds)."""
+    import ctypes as Ct
+    so = orclib.ORACLE_DIR / "_ref" / "libbmb200_e2e.so"
+    if not so.exists():
+        pytest.skip("oracle/_ref/libbmb200_e2e.so not built (needs /root/reference at build time)")
+    lib = Ct.CDLL(str(so)); lib.e2e_create_empty.restype = Ct.c_void_p; lib.e2e_free.restype = None
+    nv, nbk = 96, 600                                    # spans 3 top-level blocks
+    dens = np.array([0.5 / (k + 1) for k in range(nv)]); seed = np.arange(1000, 1000 + nv, dtype=np.uint64)
+    dset = bm.DeviceSet.synth(ctx, nv, nbk, dens, seed, True)
+    node = Ct.c_int(-1)
+    h = Ct.c_void_p(lib.e2e_create_empty(nv, nbk, 0, 0, Ct.byref(node)))
+    assert h
+    from bitmagic_b200.capi import packed_c, ptr
+    for lo in range(0, nbk, 256):
+        ps = dset.download(lo, min(nbk, lo + 256))
+        c = packed_c(ps.n_vec, ps.n_blocks, ps.desc, ps.bit_base, ps.gap_base, ps.bit_pool, ps.gap_pool)
+        assert lib.e2e_append(h, Ct.byref(c), lo, 3) == 0
+    for op, g0, g1, compress in ((bm.OP_AND_SUB, np.array([0, 1], np.uint32), np.arange(2, nv, dtype=np.uint32), 1),
+                                 (bm.OP_OR, np.arange(10, nv, dtype=np.uint32), np.zeros(0, np.uint32), 1),
+                                 (bm.OP_OR, np.arange(nv, dtype=np.uint32), np.zeros(0, np.uint32), 0)):
+        want = bm.aggregate(ctx, dset, op, g0, g1 if g1.size else None, C if compress else 0).total()[0]
+        ms = np.zeros(2); cnt = Ct.c_uint64(0); h2d = Ct.c_uint64(0); d2h = Ct.c_uint64(0)
+        assert lib.e2e_cold(h, op, compress, ptr(g0), g0.size, ptr(g1), g1.size, 2, ptr(ms), Ct.byref(cnt), Ct.byref(h2d), Ct.byref(d2h)) == 0
+        assert cnt.value == want and h2d.value >= dset.stored_bytes()
+        eq = Ct.c_int(0); rc_ = Ct.c_uint64(0); rms = Ct.c_double(0)
+        assert lib.e2e_check(h, op, compress, ptr(g0), g0.size, ptr(g1), g1.size, Ct.byref(eq), Ct.byref(rc_), Ct.byref(rms)) == 0
+        assert eq.value == 1 and rc_.value == want, "cold result bvector differs from bm::aggregator"
+        wms = np.zeros(3)
+        assert lib.e2e_warm(h, op, compress, ptr(g0), g0.size, ptr(g1), g1.size, 1, 3, ptr(wms), Ct.byref(cnt), Ct.byref(d2h)) == 0
+        assert cnt.value == want
+        assert lib.e2e_check(h, op, compress, ptr(g0), g0.size, ptr(g1), g1.size, Ct.byref(eq), Ct.byref(rc_), Ct.byref(rms)) == 0
+        assert eq.value == 1, "warm (resident device_set) result bvector differs from bm::aggregator"
+    lib.e2e_free(h)
+    dset.free()
