@@ -76,7 +76,19 @@ constexpr uint32_t kRingWords     = kRingBytes / 4;
 constexpr uint32_t kGapMaxBytes   = 2560;                          // gap_max_buff_len * 2
 constexpr int      kMaxChunks     = (kAggChunk * 4096) / (int)kGapChunkBytes + 4;      // streamed only when span <= n * 4096
 constexpr uint32_t kRingTail      = kGapMaxBytes + 512;           // tail mirror (+ over-read slack of one 64-run step)
-constexpr size_t   kAggDynSmem    = kRingBytes + kRingTail;       // blocks never wrap
+constexpr size_t   kAggRingSmem   = kRingBytes + kRingTail;       // blocks never wrap
+// dynamic shared memory of agg_kernel: [pad to the next 8 KB boundary of the shared WINDOW][live mask L, 8 KB][ring + tail].
+// L must be 8 KB aligned in window addresses (flat_quad forms word addresses with one and-or); static shared memory starts at
+// window offset = the driver's reserved bytes (1 KB on sm_100), so the pad depends on the kernel's static size -- the host
+// computes it (agg_dyn_smem) and the kernel re-derives the position from the real address.
+constexpr uint32_t kLiveAlign     = 8192u;
+__host__ inline size_t agg_dyn_smem(size_t static_bytes, size_t reserved_bytes)
+{
+    const size_t start = reserved_bytes + static_bytes;                   // window offset of the dynamic region (before its own alignment)
+    const size_t start_al = (start + 127) & ~(size_t)127;
+    const size_t k_at = (start_al + kLiveAlign - 1) & ~(size_t)(kLiveAlign - 1);
+    return (k_at - start) + kLiveAlign + kAggRingSmem + 128;
+}
 // FLAT consumer: the ring is cut into one private slot per warp; warp w streams chunks w, w+16, ... of the window through
 // its own slot and its own mbarrier -- no cross-warp hand-off, the per-chunk overhead is paid once per slot, not 16 times
 #ifndef BMB200_FLAT_SLOTS         /* private slots per warp: 2 = one being consumed while the other one fills */
@@ -95,6 +107,7 @@ struct AggParams {
     uint32_t  compress;        // classify like opt_copy_bit_block(opt_compress)
     uint32_t  store_blocks;    // 0 = counts only
     uint32_t  gap_mode;        // 0 = auto (stream when sorted), 1 = always gather
+    uint32_t  dyn_bytes;       // dynamic shared memory the launch was given (checked against the aligned layout)
     uint64_t  gap_pool_bytes;  // readable bytes of gap_pool (including the allocation slack)
     uint32_t* blocks;          // [n_cols][2048]
     uint32_t* popcnt;          // [n_cols]
@@ -465,9 +478,13 @@ template <int OP>
 __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggParams p)
 {
     extern __shared__ __align__(128) uint8_t dyn_smem[];
-    uint32_t* ring = reinterpret_cast<uint32_t*>(dyn_smem);
+    // the live mask L (see the header comment) sits at the first 8 KB boundary of the shared window inside the dynamic region, the ring behind it
+    const uint32_t dyn_s = smem_u32(dyn_smem);
+    const uint32_t k_off = ((dyn_s + kLiveAlign - 1u) & ~(kLiveAlign - 1u)) - dyn_s;
+    if (k_off + kLiveAlign + (uint32_t)kAggRingSmem > p.dyn_bytes) __trap();       // host and kernel disagree about the layout
+    uint32_t* K = reinterpret_cast<uint32_t*>(dyn_smem + k_off);
+    uint32_t* ring = reinterpret_cast<uint32_t*>(dyn_smem + k_off + kLiveAlign);
 
-    __shared__ __align__(8192) uint32_t K[kBlockWords]; // the live mask L (see the header comment); 8 KB aligned: word addresses are formed with one and-or
     __shared__ uint32_t lst_bit0[kAggChunk];
     __shared__ uint32_t lst_bit1[kAggChunk];
     __shared__ uint32_t lst_gap[kAggChunk];      // group0 GAPs from the front, group1 GAPs from the back (both in member order)

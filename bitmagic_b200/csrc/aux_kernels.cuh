@@ -117,30 +117,69 @@ __device__ __forceinline__ uint32_t cnt_le(uint32_t w, uint32_t wi, uint32_t B)
     return __popc(w & (0xffffffffu >> (31u - (B & 31u))));
 }
 
+// Device-private FINE index next to the reference-format fields (which stay exactly what rs_index::register_super_block
+// receives): per block 128 entries, one per 512-bit window k:  bits 0..15 = ones in [0, 512k), bits 16..31 (GAP blocks) = index of
+// the run that holds bit 512k (gap_bfind(512k)); plus 8 pivots (the entries of k = 0, 16, .., 112) for the two-level search of
+// select.  The reference's anchors (rs3 borders, src/bmconst.h:120-124) bound a count_to scan to ~170 words = 11 sectors; with the
+// fine index a query touches one 64-byte window of the block (2 sectors) -- what a sector-granular random-access bound asks for.
+constexpr uint32_t kRsWin = 128u;           // 512-bit windows per block
+constexpr uint32_t kRsPiv = 8u;             // pivots per block (every 16th window)
+constexpr uint32_t kRsRowPiv = 16u;         // pivots per superblock row (every 16th block)
+
 __global__ void __launch_bounds__(256) rs_block_kernel(const SetView set, uint32_t vec,
                                                        uint32_t* __restrict__ bcount,
-                                                       uint64_t* __restrict__ sub_count)
+                                                       uint64_t* __restrict__ sub_count,
+                                                       uint32_t* __restrict__ fine, uint32_t* __restrict__ fine_piv)
 {
-    const int lane = threadIdx.x & 31;
+    __shared__ uint32_t s_ones[8][kRsWin], s_ends[8][kRsWin];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
     for (uint32_t nb = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); nb < set.n_blocks; nb += warps_total) {
         const uint32_t d = set.desc[(size_t)nb * set.n_vec + vec];
         const uint32_t kd = d & 3u, rel = d >> 2;
         uint32_t tot = 0, le0 = 0, le1 = 0, a0 = 0, a1 = 0;
+        uint32_t* fout = fine + (size_t)nb * kRsWin;
         if (kd == BMB200_BLK_GAP) {
             const uint16_t* g = set.gap_pool + (set.gap_base[nb] + (rel & BMB200_DESC_REL_MASK)) * (size_t)kGapUnit + (rel >> 29);
             const uint32_t hdr = g[0], len = hdr >> 3, first = hdr & 1u;
             uint32_t lt0 = 0, lt1 = 0;   // run ends < border+1  (for gap_bfind)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { s_ones[wib][4 * lane + q] = 0u; s_ends[wib][4 * lane + q] = 0u; }
+            __syncwarp();
             for (uint32_t k = 1 + lane; k <= len; k += 32) {
                 const uint32_t e = g[k];
                 const uint32_t s = (k == 1) ? 0u : (uint32_t)g[k - 1] + 1u;
                 lt0 += (e < kRs3B0 + 1u); lt1 += (e < kRs3B1 + 1u);
+                atomicAdd(&s_ends[wib][e >> 9], 1u);
                 if (first ^ ((k - 1u) & 1u)) {
                     tot += e - s + 1u;
                     if (s <= kRs3B0) le0 += min(e, kRs3B0) - s + 1u;
                     if (s <= kRs3B1) le1 += min(e, kRs3B1) - s + 1u;
+                    for (uint32_t w = s >> 9; w <= (e >> 9); ++w)       // ones of this run inside every window it touches
+                        atomicAdd(&s_ones[wib][w], min(e, (w << 9) + 511u) - max(s, w << 9) + 1u);
                 }
             }
+            __syncwarp();
+            {   // exclusive scans over the 128 windows: lane owns windows 4*lane .. 4*lane+3
+                uint32_t o[4], n[4], so = 0, sn = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { o[q] = s_ones[wib][4 * lane + q]; n[q] = s_ends[wib][4 * lane + q]; so += o[q]; sn += n[q]; }
+                uint32_t io = so, in_ = sn;
+#pragma unroll
+                for (int sft = 1; sft < 32; sft <<= 1) {
+                    const uint32_t yo = __shfl_up_sync(0xffffffffu, io, sft), yn = __shfl_up_sync(0xffffffffu, in_, sft);
+                    if (lane >= sft) { io += yo; in_ += yn; }
+                }
+                uint32_t co = io - so, cn = in_ - sn;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t ent = co | ((cn + 1u) << 16);                 // run index = (ends before the window) + 1
+                    fout[4 * lane + q] = ent;
+                    if (((4 * lane + q) & 15) == 0) fine_piv[(size_t)nb * kRsPiv + ((4 * lane + q) >> 4)] = co;
+                    co += o[q]; cn += n[q];
+                }
+            }
+            __syncwarp();
             tot = warp_sum(tot); le0 = warp_sum(le0); le1 = warp_sum(le1);
             lt0 = warp_sum(lt0); lt1 = warp_sum(lt1);
             const uint32_t i0 = lt0 + 1u, i1 = lt1 + 1u;          // gap_bfind src/bmfunc.h:1844
@@ -153,17 +192,33 @@ __global__ void __launch_bounds__(256) rs_block_kernel(const SetView set, uint32
                 uint4 v[16];
 #pragma unroll
                 for (int it = 0; it < 16; ++it) v[it] = ld_stream_v4(b4 + it * 32 + lane);
+                uint32_t carry = 0;                        // ones before the 8 windows of this iteration (warp-uniform)
 #pragma unroll
                 for (int it = 0; it < 16; ++it) {
                     const uint32_t wi = (uint32_t)(it * 32 + lane) * 4u;
                     const uint32_t w4[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+                    uint32_t p4 = 0;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const uint32_t w = w4[q];
-                        tot += __popc(w);
+                        p4 += __popc(w);
                         le0 += cnt_le(w, wi + q, kRs3B0);   le1 += cnt_le(w, wi + q, kRs3B1);
                         a0  += cnt_le(w, wi + q, kRs3B0_1); a1  += cnt_le(w, wi + q, kRs3B1_1);
                     }
+                    tot += p4;
+                    // fine index: 4 adjacent lanes = one 512-bit window (window it*8 + lane/4); exclusive scan over the 8 windows
+                    uint32_t ws = p4 + __shfl_xor_sync(0xffffffffu, p4, 1);
+                    ws += __shfl_xor_sync(0xffffffffu, ws, 2);
+                    uint32_t x = ws;
+#pragma unroll
+                    for (int sft = 4; sft < 32; sft <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, sft); if (lane >= sft) x += y; }
+                    const uint32_t before = carry + x - ws;
+                    if ((lane & 3) == 0) {
+                        const uint32_t k = (uint32_t)it * 8u + ((uint32_t)lane >> 2);
+                        fout[k] = before;
+                        if ((k & 15u) == 0u) fine_piv[(size_t)nb * kRsPiv + (k >> 4)] = before;
+                    }
+                    carry += __shfl_sync(0xffffffffu, x, 31);
                 }
             } else {   // FULL block: an all-ones block, like BLOCK_ADDR_SAN in src/bm.h:2628
                 for (uint32_t wi = lane; wi < kBlockWords; wi += 32) {
@@ -185,7 +240,8 @@ __global__ void __launch_bounds__(256) rs_block_kernel(const SetView set, uint32
 // block-scan, level 1: one CTA per 256-block superblock -> running counts inside the superblock
 // (rs_index::register_super_block src/bmrs.h:688-715) and the superblock total
 __global__ void __launch_bounds__(256) rs_scan_rows_kernel(const uint32_t* __restrict__ bcount, uint32_t n_blocks,
-                                                           uint32_t* __restrict__ row_cum, uint64_t* __restrict__ sb_tot)
+                                                           uint32_t* __restrict__ row_cum, uint64_t* __restrict__ sb_tot,
+                                                           uint32_t* __restrict__ row_piv)
 {
     __shared__ uint32_t s_w[8];
     const uint32_t sb = blockIdx.x, nb = sb * 256u + threadIdx.x;
@@ -199,7 +255,8 @@ __global__ void __launch_bounds__(256) rs_scan_rows_kernel(const uint32_t* __res
     uint32_t woff = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) { const uint32_t v = s_w[w]; if (w < warp) woff += v; total += v; }
-    if (nb < n_blocks) row_cum[nb] = woff + inc;
+    row_cum[nb] = woff + inc;                              // padded to whole superblocks: entries past n_blocks repeat the total
+    if ((threadIdx.x & 15) == 15) row_piv[sb * kRsRowPiv + (threadIdx.x >> 4)] = woff + inc;     // inclusive count at the end of each group of 16 blocks
     if (threadIdx.x == 0) sb_tot[sb] = total;
 }
 
@@ -236,19 +293,13 @@ struct RsView {
     uint32_t nsb;
     const uint32_t* bcount;     // [n_blocks]
     const uint64_t* sub_count;  // [n_blocks]
-    const uint32_t* row_cum;    // [n_blocks] inclusive running count inside the superblock
+    const uint32_t* row_cum;    // [nsb * 256] inclusive running count inside the superblock (padded with the total)
     const uint64_t* sb_cum;     // [nsb+1]
+    const uint32_t* fine;       // [n_blocks][128]   ones before window k | run index << 16
+    const uint32_t* fine_piv;   // [n_blocks][8]     ones before window 16 q
+    const uint32_t* row_piv;    // [nsb][16]         inclusive count at block 16 q + 15 of the superblock
 };
 
-// bits set in words of a bit-block at positions [from, to] (inclusive, from <= to)
-__device__ __forceinline__ uint32_t bit_count_range(const uint32_t* __restrict__ b, uint32_t from, uint32_t to)
-{
-    const uint32_t wf = from >> 5, wt = to >> 5;
-    if (wf == wt) return __popc(b[wf] & bit_range_mask(from & 31u, to & 31u));
-    uint32_t c = __popc(b[wf] & (0xffffffffu << (from & 31u)));
-    for (uint32_t w = wf + 1; w < wt; ++w) c += __popc(b[w]);
-    return c + __popc(b[wt] & (0xffffffffu >> (31u - (to & 31u))));
-}
 // 1-bits of a GAP block in [from, to], scanning from run index k (run k must contain `from`)
 __device__ __forceinline__ uint32_t gap_count_from(const uint16_t* __restrict__ g, uint32_t k, uint32_t from, uint32_t to)
 {
@@ -263,9 +314,17 @@ __device__ __forceinline__ uint32_t gap_count_from(const uint16_t* __restrict__ 
     }
     return c;
 }
+__device__ __forceinline__ uint4 ld_nc_v4(const uint4* p)
+{
+    uint4 r; asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p)); return r;
+}
+// how many of the 4 words are < x
+__device__ __forceinline__ uint32_t cnt_lt4(const uint4& v, uint32_t x) { return (v.x < x) + (v.y < x) + (v.z < x) + (v.w < x); }
+__device__ __forceinline__ uint32_t cnt_lt4_lo16(const uint4& v, uint32_t x)
+{ return ((v.x & 0xffffu) < x) + ((v.y & 0xffffu) < x) + ((v.z & 0xffffu) < x) + ((v.w & 0xffffu) < x); }
 
-// inclusive rank, bvector::count_to src/bm.h:3120-3167; block part follows block_count_to's
-// nearest-anchor idea (src/bm.h:2686-2869) with the five anchors stored in sub_count.
+// inclusive rank, bvector::count_to src/bm.h:3120-3167.  One thread per query; per query: superblock total (cached), one
+// row entry, the descriptor, ONE fine-index entry and at most one 64-byte window of the block (128-bit loads).
 __global__ void __launch_bounds__(256) rs_rank_kernel(const RsView rs, const uint64_t* __restrict__ pos, uint64_t n,
                                                       uint64_t* __restrict__ out)
 {
@@ -279,92 +338,107 @@ __global__ void __launch_bounds__(256) rs_rank_kernel(const RsView rs, const uin
         const uint32_t kd = d & 3u, rel = d >> 2;
         if (kd == BMB200_BLK_FULL) r += in + 1u;
         else if (kd != BMB200_BLK_NULL) {
-            const uint64_t sub = rs.sub_count[nb];
-            const uint32_t first = (uint32_t)(sub & 0xffffu), second = (uint32_t)((sub >> 16) & 0xffffu);
-            const uint32_t a0 = (uint32_t)((sub >> 32) & 0xffffu), a1 = (uint32_t)(sub >> 48);
+            const uint32_t k = in >> 9, f = rs.fine[(size_t)nb * kRsWin + k];
+            uint32_t c = f & 0xffffu;
             if (kd == BMB200_BLK_BIT) {
-                const uint32_t* b = rs.set.bit_pool + (rs.set.bit_base[nb] + rel) * (size_t)kBlockWords;
-                const uint32_t bc = rs.bcount[nb];
-                // anchors: (position, bits in [0,position])
-                const int32_t  ap[6] = { -1, (int32_t)kRs3B0, (int32_t)kRs3B0_1, (int32_t)kRs3B1, (int32_t)kRs3B1_1, 65535 };
-                const uint32_t ac[6] = { 0u, first, a0, first + second, a1, bc };
-                int best = 0; uint32_t bd = in + 1u;
+                const uint4* w4 = reinterpret_cast<const uint4*>(rs.set.bit_pool + (rs.set.bit_base[nb] + rel) * (size_t)kBlockWords + 16u * k);
+                const uint32_t wt = (in >> 5) & 15u;                        // word of `in` inside the window
+                const uint32_t last = 0xffffffffu >> (31u - (in & 31u));   // bits <= in of that word
 #pragma unroll
-                for (int a = 1; a < 6; ++a) {
-                    const uint32_t dist = (uint32_t)abs((int32_t)in - ap[a]);
-                    if (dist < bd) { bd = dist; best = a; }
+                for (uint32_t i = 0; i < 4; ++i) {
+                    if (4u * i > wt) break;
+                    const uint4 v = ld_nc_v4(w4 + i);
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j) {
+                        const uint32_t wi = 4u * i + j;
+                        c += __popc(w[j] & (wi < wt ? 0xffffffffu : wi == wt ? last : 0u));
+                    }
                 }
-                uint32_t c = ac[best];
-                if ((int32_t)in > ap[best])      c += bit_count_range(b, (uint32_t)(ap[best] + 1), in);
-                else if ((int32_t)in < ap[best]) c -= bit_count_range(b, in + 1u, (uint32_t)ap[best]);
-                r += c;
             } else {
                 const uint16_t* g = rs.set.gap_pool + (rs.set.gap_base[nb] + (rel & BMB200_DESC_REL_MASK)) * (size_t)kGapUnit + (rel >> 29);
-                uint32_t c;
-                if (in <= kRs3B0)      c = gap_count_from(g, 1u, 0u, in);
-                else if (in <= kRs3B1) c = first + gap_count_from(g, a0 >> 1, kRs3B0 + 1u, in);
-                else                   c = first + second + gap_count_from(g, a1 >> 1, kRs3B1 + 1u, in);
-                r += c;
+                c += gap_count_from(g, f >> 16, k << 9, in);
             }
+            r += c;
         }
         out[q] = r;
     }
 }
 
-// 1-based select, bvector::select src/bm.h:5350-5385; rs_index::find src/bmrs.h:398-460;
-// bit_find_rank src/bmfunc.h:9673-9768 (word select via __fns instead of PDEP, src/bmbmi2.h:56-71)
+// 1-based select, bvector::select src/bm.h:5350-5385 (rs_index::find src/bmrs.h:398-460, bit_find_rank src/bmfunc.h:9673-9768;
+// word select via __fns instead of PDEP, src/bmbmi2.h:56-71).  One thread per query; every level below the superblock is a
+// two-level search over 128-bit loads (16 pivots -> 16 entries), no dependent binary-search chains, then one 64-byte window.
 __global__ void __launch_bounds__(256) rs_select_kernel(const RsView rs, const uint64_t* __restrict__ rank, uint64_t n,
                                                         uint64_t* __restrict__ pos, uint8_t* __restrict__ found)
 {
     const uint64_t total = rs.sb_cum[rs.nsb];
     for (uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; q < n; q += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t r = rank[q];
+        const uint64_t r = rank[q];
         if (r == 0 || r > total) { found[q] = 0; pos[q] = 0; continue; }
-        // smallest superblock i with sb_cum[i+1] >= r
+        // smallest superblock i with sb_cum[i+1] >= r (the table is small and shared by every query: cache-resident)
         uint32_t lo = 0, hi = rs.nsb - 1u;
         while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (rs.sb_cum[mid + 1] < r) lo = mid + 1; else hi = mid; }
         const uint32_t sb = lo;
         uint32_t rr = (uint32_t)(r - rs.sb_cum[sb]);
-        // smallest block j in the superblock with row_cum >= rr
-        const uint32_t b0 = sb * 256u;
-        lo = 0; hi = min(255u, rs.set.n_blocks - 1u - b0);
-        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (rs.row_cum[b0 + mid] < rr) lo = mid + 1; else hi = mid; }
-        const uint32_t nb = b0 + lo;
-        if (lo) rr -= rs.row_cum[nb - 1];
+        // block inside the superblock: group of 16 by the pivots, then the block by the group's 16 running counts
+        const uint4* pv = reinterpret_cast<const uint4*>(rs.row_piv + (size_t)sb * kRsRowPiv);
+        const uint4 p0 = ld_nc_v4(pv), p1 = ld_nc_v4(pv + 1), p2 = ld_nc_v4(pv + 2), p3 = ld_nc_v4(pv + 3);
+        const uint32_t grp = cnt_lt4(p0, rr) + cnt_lt4(p1, rr) + cnt_lt4(p2, rr) + cnt_lt4(p3, rr);       // < 16: rr <= superblock total
+        const uint4* rc = reinterpret_cast<const uint4*>(rs.row_cum + (size_t)sb * 256u + 16u * grp);
+        const uint4 c0 = ld_nc_v4(rc), c1 = ld_nc_v4(rc + 1), c2 = ld_nc_v4(rc + 2), c3 = ld_nc_v4(rc + 3);
+        const uint32_t j = cnt_lt4(c0, rr) + cnt_lt4(c1, rr) + cnt_lt4(c2, rr) + cnt_lt4(c3, rr);
+        const uint32_t ce[16] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w};
+        const uint32_t pe[16] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w, p3.x, p3.y, p3.z, p3.w};
+        uint32_t prev = 0;
+        if (j) {
+#pragma unroll
+            for (int i = 0; i < 15; ++i) if ((uint32_t)i + 1u == j) prev = ce[i];
+        } else if (grp) {
+#pragma unroll
+            for (int i = 0; i < 15; ++i) if ((uint32_t)i + 1u == grp) prev = pe[i];
+        }
+        const uint32_t nb = sb * 256u + 16u * grp + j;
+        rr -= prev;                                                        // rank inside the block, 1-based
         const uint32_t d = rs.set.desc[(size_t)nb * rs.set.n_vec + rs.vec];
         const uint32_t kd = d & 3u, rel = d >> 2;
         uint32_t bit = 0;
         if (kd == BMB200_BLK_FULL) bit = rr - 1u;
         else {
-            const uint64_t sub = rs.sub_count[nb];
-            const uint32_t first = (uint32_t)(sub & 0xffffu), second = (uint32_t)((sub >> 16) & 0xffffu);
-            const uint32_t a0 = (uint32_t)((sub >> 32) & 0xffffu), a1 = (uint32_t)(sub >> 48);
+            // window: last k with (ones before window k) < rr -- 8 pivots, then the group's 16 entries
+            const uint4* fp = reinterpret_cast<const uint4*>(rs.fine_piv + (size_t)nb * kRsPiv);
+            const uint4 f0 = ld_nc_v4(fp), f1 = ld_nc_v4(fp + 1);
+            const uint32_t g8 = cnt_lt4(f0, rr) + cnt_lt4(f1, rr) - 1u;   // pivot 0 is 0 < rr
+            const uint4* fe = reinterpret_cast<const uint4*>(rs.fine + (size_t)nb * kRsWin + 16u * g8);
+            const uint4 e0 = ld_nc_v4(fe), e1 = ld_nc_v4(fe + 1), e2 = ld_nc_v4(fe + 2), e3 = ld_nc_v4(fe + 3);
+            const uint32_t kk = cnt_lt4_lo16(e0, rr) + cnt_lt4_lo16(e1, rr) + cnt_lt4_lo16(e2, rr) + cnt_lt4_lo16(e3, rr) - 1u;
+            const uint32_t ee[16] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
+            uint32_t ent = ee[0];
+#pragma unroll
+            for (int i = 1; i < 16; ++i) if ((uint32_t)i == kk) ent = ee[i];
+            const uint32_t k = 16u * g8 + kk;
+            uint32_t need = rr - (ent & 0xffffu);                          // >= 1, and the window holds that many ones
             if (kd == BMB200_BLK_BIT) {
-                const uint32_t* b = rs.set.bit_pool + (rs.set.bit_base[nb] + rel) * (size_t)kBlockWords;
-                // last anchor with count < rr
-                uint32_t start = 0, c = 0;
-                if (first < rr)          { start = kRs3B0 + 1u;   c = first; }
-                if (a0 < rr)             { start = kRs3B0_1 + 1u; c = a0; }
-                if (first + second < rr) { start = kRs3B1 + 1u;   c = first + second; }
-                if (a1 < rr)             { start = kRs3B1_1 + 1u; c = a1; }
-                uint32_t need = rr - c;
-                uint32_t wi = start >> 5;
-                uint32_t w = b[wi] & (0xffffffffu << (start & 31u));
-                for (;;) {
-                    const uint32_t pc = __popc(w);
-                    if (need <= pc) break;
-                    need -= pc; w = b[++wi];
+                const uint4* w4 = reinterpret_cast<const uint4*>(rs.set.bit_pool + (rs.set.bit_base[nb] + rel) * (size_t)kBlockWords + 16u * k);
+                uint32_t wsel = 0, widx = 0; bool done = false;
+#pragma unroll
+                for (uint32_t i = 0; i < 4; ++i) {
+                    if (done) break;
+                    const uint4 v = ld_nc_v4(w4 + i);
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (uint32_t jj = 0; jj < 4; ++jj) {
+                        const uint32_t pc = __popc(w[jj]);
+                        if (!done) { if (need <= pc) { wsel = w[jj]; widx = 4u * i + jj; done = true; } else need -= pc; }
+                    }
                 }
-                bit = wi * 32u + __fns(w, 0, (int)need);
+                bit = (16u * k + widx) * 32u + __fns(wsel, 0, (int)need);
             } else {
                 const uint16_t* g = rs.set.gap_pool + (rs.set.gap_base[nb] + (rel & BMB200_DESC_REL_MASK)) * (size_t)kGapUnit + (rel >> 29);
                 const uint32_t firstv = g[0] & 1u;
-                uint32_t k = 1u, s = 0u, need = rr;
-                if (first + second < rr) { k = a1 >> 1; s = kRs3B1 + 1u; need = rr - first - second; }
-                else if (first < rr)     { k = a0 >> 1; s = kRs3B0 + 1u; need = rr - first; }
-                for (;; ++k) {
-                    const uint32_t e = g[k];
-                    if (firstv ^ ((k - 1u) & 1u)) {
+                uint32_t kr = ent >> 16, s = k << 9;
+                for (;; ++kr) {
+                    const uint32_t e = g[kr];
+                    if (firstv ^ ((kr - 1u) & 1u)) {
                         const uint32_t rl = e - s + 1u;
                         if (need <= rl) { bit = s + need - 1u; break; }
                         need -= rl;

@@ -48,6 +48,7 @@ struct bmb200_ctx {
     size_t d_tmp_cap[13] = {};              //   between calls, grown on demand -- cudaMalloc / cudaFree of a few hundred MB costs tens of ms each
     int gap_mode = 0;                       // 0 = stream sorted GAP lists through the smem ring, 1 = always gather
     bool attr_set = false;
+    size_t agg_dyn[4] = {};                 // dynamic shared memory per agg_kernel<OP> (set_agg_attrs)
     int host_threads = 0;                   // host threads of bmb200_set_upload_vectors (0 = hardware concurrency, at most 64)
     uint8_t* h_ring[kStageSlots] = {};      // pinned staging ring of bmb200_set_upload_vectors (grow-only)
     size_t h_ring_cap = 0;
@@ -96,6 +97,9 @@ struct bmb200_rs {
     uint32_t* row_cum = nullptr;
     uint64_t* sb_tot = nullptr;
     uint64_t* sb_cum = nullptr;
+    uint32_t* fine = nullptr;               // device-private fine index (aux_kernels.cuh): [n_blocks][128]
+    uint32_t* fine_piv = nullptr;           // [n_blocks][8]
+    uint32_t* row_piv = nullptr;            // [nsb][16]
 };
 
 namespace {
@@ -1005,13 +1009,27 @@ static int result_alloc(bmb200_ctx* ctx, uint32_t n_cols, uint32_t n_groups, boo
     return BMB200_OK;
 }
 
+// dynamic shared memory per aggregation kernel: depends on its static size (the live mask is 8 KB aligned in the shared window)
+extern "C++" {
+template <typename KFn>
+static cudaError_t agg_attr_one(KFn fn, size_t reserved, size_t* dyn_out)
+{
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, fn);
+    if (e != cudaSuccess) return e;
+    *dyn_out = agg_dyn_smem(fa.sharedSizeBytes, reserved);
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*dyn_out);
+}
+}
 static void set_agg_attrs(bmb200_ctx* ctx, cudaError_t* e)
 {
     if (ctx->attr_set) return;
-    *e = cudaFuncSetAttribute(agg_kernel<BMB200_OP_OR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggDynSmem);
-    if (*e == cudaSuccess) *e = cudaFuncSetAttribute(agg_kernel<BMB200_OP_AND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggDynSmem);
-    if (*e == cudaSuccess) *e = cudaFuncSetAttribute(agg_kernel<BMB200_OP_AND_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggDynSmem);
-    if (*e == cudaSuccess) *e = cudaFuncSetAttribute(agg_kernel<BMB200_OP_XOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggDynSmem);
+    int reserved = 1024;
+    if (cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, ctx->device) != cudaSuccess) { cudaGetLastError(); reserved = 1024; }
+    *e = agg_attr_one(agg_kernel<BMB200_OP_OR>, (size_t)reserved, &ctx->agg_dyn[BMB200_OP_OR]);
+    if (*e == cudaSuccess) *e = agg_attr_one(agg_kernel<BMB200_OP_AND>, (size_t)reserved, &ctx->agg_dyn[BMB200_OP_AND]);
+    if (*e == cudaSuccess) *e = agg_attr_one(agg_kernel<BMB200_OP_AND_SUB>, (size_t)reserved, &ctx->agg_dyn[BMB200_OP_AND_SUB]);
+    if (*e == cudaSuccess) *e = agg_attr_one(agg_kernel<BMB200_OP_XOR>, (size_t)reserved, &ctx->agg_dyn[BMB200_OP_XOR]);
     if (*e == cudaSuccess) ctx->attr_set = true;
 }
 
@@ -1093,12 +1111,13 @@ int bmb200_aggregate_batch(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_
     if (ae != cudaSuccess) { ctx->last_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ae); if (!*inout) bmb200_result_free(r); return BMB200_ERR_CUDA; }
     uint32_t grid = (uint32_t)(ctx->sm_count * ctx->agg_ctas_per_sm);
     if (grid > n_cols) grid = n_cols;
+    if (a->op != BMB200_OP_SHIFT_R_AND) p.dyn_bytes = (uint32_t)ctx->agg_dyn[a->op];
     switch (a->op) {
-    case BMB200_OP_OR:      agg_kernel<BMB200_OP_OR><<<grid, kAggThreads, kAggDynSmem, ctx->stream>>>(p); break;
-    case BMB200_OP_AND:     agg_kernel<BMB200_OP_AND><<<grid, kAggThreads, kAggDynSmem, ctx->stream>>>(p); break;
-    case BMB200_OP_AND_SUB: agg_kernel<BMB200_OP_AND_SUB><<<grid, kAggThreads, kAggDynSmem, ctx->stream>>>(p); break;
+    case BMB200_OP_OR:      agg_kernel<BMB200_OP_OR><<<grid, kAggThreads, ctx->agg_dyn[BMB200_OP_OR], ctx->stream>>>(p); break;
+    case BMB200_OP_AND:     agg_kernel<BMB200_OP_AND><<<grid, kAggThreads, ctx->agg_dyn[BMB200_OP_AND], ctx->stream>>>(p); break;
+    case BMB200_OP_AND_SUB: agg_kernel<BMB200_OP_AND_SUB><<<grid, kAggThreads, ctx->agg_dyn[BMB200_OP_AND_SUB], ctx->stream>>>(p); break;
     case BMB200_OP_SHIFT_R_AND: shift_and_kernel<<<grid, kAggThreads, 0, ctx->stream>>>(p); break;
-    default:                agg_kernel<BMB200_OP_XOR><<<grid, kAggThreads, kAggDynSmem, ctx->stream>>>(p); break;
+    default:                agg_kernel<BMB200_OP_XOR><<<grid, kAggThreads, ctx->agg_dyn[BMB200_OP_XOR], ctx->stream>>>(p); break;
     }
     int rc = after_launch(ctx);
     if (rc) { if (!*inout) bmb200_result_free(r); return rc; }
@@ -1588,6 +1607,7 @@ static RsView rs_view(const bmb200_rs* rs)
     RsView v{};
     v.set = rs->set->v; v.vec = rs->vec; v.nsb = rs->nsb;
     v.bcount = rs->bcount; v.sub_count = rs->sub_count; v.row_cum = rs->row_cum; v.sb_cum = rs->sb_cum;
+    v.fine = rs->fine; v.fine_piv = rs->fine_piv; v.row_piv = rs->row_piv;
     return v;
 }
 
@@ -1602,8 +1622,10 @@ int bmb200_rs_build(bmb200_ctx* ctx, const bmb200_set* set, uint32_t vec, bmb200
     rs->nsb = (set->v.n_blocks + 255u) / 256u;
     int rc;
     if ((rc = dev_alloc(ctx, &rs->bcount, rs->n_blocks)) || (rc = dev_alloc(ctx, &rs->sub_count, rs->n_blocks)) ||
-        (rc = dev_alloc(ctx, &rs->row_cum, rs->n_blocks)) || (rc = dev_alloc(ctx, &rs->sb_tot, rs->nsb)) ||
-        (rc = dev_alloc(ctx, &rs->sb_cum, (size_t)rs->nsb + 1))) { bmb200_rs_free(rs); return rc; }
+        (rc = dev_alloc(ctx, &rs->row_cum, (size_t)rs->nsb * 256u)) || (rc = dev_alloc(ctx, &rs->sb_tot, rs->nsb)) ||
+        (rc = dev_alloc(ctx, &rs->sb_cum, (size_t)rs->nsb + 1)) ||
+        (rc = dev_alloc(ctx, &rs->fine, (size_t)rs->n_blocks * kRsWin)) || (rc = dev_alloc(ctx, &rs->fine_piv, (size_t)rs->n_blocks * kRsPiv)) ||
+        (rc = dev_alloc(ctx, &rs->row_piv, (size_t)rs->nsb * kRsRowPiv))) { bmb200_rs_free(rs); return rc; }
     rc = bmb200_rs_rebuild(rs);
     if (rc) { bmb200_rs_free(rs); return rc; }
     *out = rs;
@@ -1618,9 +1640,9 @@ int bmb200_rs_rebuild(bmb200_rs* rs)
     int rc;
     uint32_t grid = (rs->n_blocks + 7u) / 8u;
     const uint32_t maxg = (uint32_t)ctx->sm_count * 16u; if (grid > maxg) grid = maxg;
-    rs_block_kernel<<<grid, 256, 0, ctx->stream>>>(rs->set->v, rs->vec, rs->bcount, rs->sub_count);
+    rs_block_kernel<<<grid, 256, 0, ctx->stream>>>(rs->set->v, rs->vec, rs->bcount, rs->sub_count, rs->fine, rs->fine_piv);
     if ((rc = after_launch(ctx))) return rc;
-    rs_scan_rows_kernel<<<rs->nsb, 256, 0, ctx->stream>>>(rs->bcount, rs->n_blocks, rs->row_cum, rs->sb_tot);
+    rs_scan_rows_kernel<<<rs->nsb, 256, 0, ctx->stream>>>(rs->bcount, rs->n_blocks, rs->row_cum, rs->sb_tot, rs->row_piv);
     if ((rc = after_launch(ctx))) return rc;
     rs_scan_sb_kernel<<<1, 1024, 0, ctx->stream>>>(rs->sb_tot, rs->nsb, rs->sb_cum);
     return after_launch(ctx);
@@ -1714,6 +1736,7 @@ int bmb200_rs_free(bmb200_rs* rs)
     cudaSetDevice(rs->ctx->device);
     cudaStreamSynchronize(rs->ctx->stream);
     cudaFree(rs->bcount); cudaFree(rs->sub_count); cudaFree(rs->row_cum); cudaFree(rs->sb_tot); cudaFree(rs->sb_cum);
+    cudaFree(rs->fine); cudaFree(rs->fine_piv); cudaFree(rs->row_piv);
     delete rs;
     return BMB200_OK;
 }
