@@ -220,12 +220,19 @@ def _run_pipeline(ctx, pipe: Pipeline):
 
 
 def _binop(op, a: BVector, b: BVector, opt_mode: int, ctx=None):
+    """bvector::bit_and / bit_or / bit_xor / bit_sub (src/bm.h:6185,5973,6072,6403) through bmb200_binop: the result's block
+    kinds follow combine_operation_block_* like the reference's (GAP x GAP merged on the device, clones keep their kind)."""
     ctx = ctx or capi.default_context()
-    if op == "sub":
-        res, _, _ = _run(ctx, [a, b], OP_AND_SUB, [0], [1], opt_mode)
-    else:
-        res, _, _ = _run(ctx, [a, b], {"and": OP_AND, "or": OP_OR, "xor": OP_XOR}[op], [0, 1], None, opt_mode)
-    return res
+    dset = capi.DeviceSet.upload_vectors(ctx, [a, b], max(a.n_blocks, b.n_blocks))
+    try:
+        res = capi.binop(ctx, dset, {"and": OP_AND, "or": OP_OR, "xor": OP_XOR, "sub": capi.OP_SUB}[op], 0, 1,
+                         capi.F_OPT_COMPRESS if opt_mode == OPT_COMPRESS else capi.F_OPT_NONE)
+        try:
+            return result_to_bvector(*res.fetch())
+        finally:
+            res.free()
+    finally:
+        dset.free()
 
 
 def bit_and(a: BVector, b: BVector, opt_mode: int = OPT_NONE, ctx=None) -> BVector:

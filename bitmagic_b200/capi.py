@@ -37,8 +37,9 @@ SYMBOLS = [
     "bmb200_rs_free", "bmb200_rs_rebuild", "bmb200_aggregate_batch", "bmb200_result_group_totals", "bmb200_result_or_target",
     "bmb200_scan", "bmb200_set_upload_blobs", "bmb200_result_fetch_view", "bmb200_ctx_bind_host_numa",
     "bmb200_shard_range", "bmb200_comm_unique_id", "bmb200_comm_init", "bmb200_comm_info", "bmb200_comm_destroy",
-    "bmb200_exchange_popcounts", "bmb200_exchange_fence", "bmb200_exchange_fetch", "bmb200_ctx_trim",
+    "bmb200_exchange_popcounts", "bmb200_exchange_fence", "bmb200_exchange_fetch", "bmb200_ctx_trim", "bmb200_binop",
 ]
+OP_SUB = 5
 COMM_ID_BYTES = 128
 TUNE_GAP_MODE, TUNE_CTAS_PER_SM, TUNE_HOST_THREADS = 0, 1, 2
 
@@ -411,6 +412,16 @@ def aggregate(ctx: Context, dset: DeviceSet, op: int, group0, group1=None, flags
                     ptr(g1) if g1.size else C.c_void_p(0), g1.size, int(nb_from), int(nb_to))
     res = result if result is not None else DeviceResult(ctx)
     ctx.check(lib().bmb200_aggregate(ctx._h, dset._h, C.byref(args), C.byref(res._h)), "aggregate")
+    res.n_cols = (nb_to if nb_to else dset.n_blocks) - nb_from
+    return res
+
+
+def binop(ctx: Context, dset: DeviceSet, op: int, va: int, vb: int, flags: int = 0, nb_from: int = 0, nb_to: int = 0,
+          result: DeviceResult | None = None) -> DeviceResult:
+    """bmb200_binop: two-operand bvector op (OP_OR / OP_AND / OP_XOR / OP_SUB) with the reference's per-block result kinds
+    (GAP x GAP merged as run lists on the device)."""
+    res = result if result is not None else DeviceResult(ctx)
+    ctx.check(lib().bmb200_binop(ctx._h, dset._h, int(op), int(va), int(vb), int(flags), int(nb_from), int(nb_to), C.byref(res._h)), "binop")
     res.n_cols = (nb_to if nb_to else dset.n_blocks) - nb_from
     return res
 

@@ -108,6 +108,7 @@ struct AggParams {
     uint32_t  store_blocks;    // 0 = counts only
     uint32_t  gap_mode;        // 0 = auto (stream when sorted), 1 = always gather
     uint32_t  dyn_bytes;       // dynamic shared memory the launch was given (checked against the aligned layout)
+    uint32_t  binary;          // 0 = aggregator semantics; 1 + BINOP_* = two-operand bvector op (result kinds follow combine_operation_block_*)
     uint64_t  gap_pool_bytes;  // readable bytes of gap_pool (including the allocation slack)
     uint32_t* blocks;          // [n_cols][2048]
     uint32_t* popcnt;          // [n_cols]
@@ -389,13 +390,57 @@ __device__ __forceinline__ void gap_scatter_gather(uint32_t Ks, const uint16_t* 
     }
 }
 
+// ---- two-operand bvector ops (bvector::bit_or / bit_and / bit_xor / bit_sub, src/bm.h:5973,6185,6072,6403) ----
+// The reference decides the KIND of every result block from the kinds of the two argument blocks
+// (combine_operation_block_or/_and/_xor/_sub, src/bm.h:6945,7100,7018,7285): a NULL / FULL argument clones the other block
+// (a GAP block stays GAP, a bit-block stays a bit-block), GAP x GAP is merged into a GAP block (gap_buff_op, src/bmfunc.h:3747),
+// GAP x bit and bit x bit produce a bit-block that only opt_compress re-classifies (optimize_bit_block, src/bmblocks.h:1414),
+// with op-specific all-zero / all-one checks.  binop_rule() is that table; finish_block() applies it.
+constexpr uint32_t BINOP_OR = 0u, BINOP_AND = 1u, BINOP_SUB = 2u, BINOP_XOR = 3u;
+constexpr uint32_t kRuleComputed = 1u, kRuleCloneBit = 2u, kRuleCloneGap = 3u;   // bits 0-1
+constexpr uint32_t kRuleZchk = 4u, kRuleOchk = 8u, kRuleFull = 16u, kRuleMerge = 32u;
+__host__ __device__ __forceinline__ uint32_t binop_clone(uint32_t k)
+{   // clone_assign_block (src/bmblocks.h:893): FULL stays FULL, a GAP block is copied as GAP (all-zero -> NULL, all-one -> FULL), a bit-block verbatim
+    return k == BMB200_BLK_FULL ? kRuleFull : k == BMB200_BLK_GAP ? kRuleCloneGap : kRuleCloneBit;
+}
+__host__ __device__ __forceinline__ uint32_t binop_rule(uint32_t op, uint32_t ka, uint32_t kb)
+{
+    const uint32_t N = BMB200_BLK_NULL, F = BMB200_BLK_FULL, B = BMB200_BLK_BIT, G = BMB200_BLK_GAP;
+    if (ka == G && kb == G) return kRuleMerge;
+    switch (op) {
+    case BINOP_OR:
+        if (ka == N) return binop_clone(kb);
+        if (kb == N) return binop_clone(ka);
+        if (ka == F || kb == F) return kRuleFull;
+        return (ka == B && kb == B) ? (kRuleComputed | kRuleOchk) : kRuleComputed;        // bit_block_or_2way reports all-ones; gap_add_to_bitset does not
+    case BINOP_AND:
+        if (ka == N || kb == N) return kRuleComputed | kRuleZchk;                        // (the kernel's NULL short-circuit answers first)
+        if (ka == F) return binop_clone(kb);
+        if (kb == F) return binop_clone(ka);
+        return kRuleComputed | kRuleZchk;                                                // bit_is_all_zero / digest == 0
+    case BINOP_XOR:
+        if (ka == N) return binop_clone(kb);
+        if (kb == N) return binop_clone(ka);
+        if (ka == F && kb == F) return kRuleComputed | kRuleZchk;                        // 1 ^ 1: nothing stored
+        if (ka == F) return kb == G ? kRuleCloneGap : kRuleCloneBit;                     // inverted clone keeps the kind
+        if (kb == F) return ka == G ? kRuleCloneGap : kRuleCloneBit;
+        return (ka == B && kb == B) ? (kRuleComputed | kRuleZchk) : kRuleComputed;       // only bit_block_xor_2way checks for zero
+    default: /* BINOP_SUB: a - b */
+        if (kb == N) return binop_clone(ka);
+        if (ka == N || kb == F) return kRuleComputed | kRuleZchk;                        // (short-circuited to NULL by the kernel)
+        if (ka == F) return kb == G ? kRuleComputed : (kRuleComputed | kRuleZchk);       // FULL is treated as a real all-ones bit-block
+        if (ka == B && kb == G) return kRuleComputed;                                    // clone + gap_sub_to_bitset: no zero check
+        return kRuleComputed | kRuleZchk;
+    }
+}
+
 // Epilogue shared by agg_kernel and finalize_blocks_kernel: R = this thread's 4 words of the result block.
 // state: 0 = nothing stored, 1 = FULL, 2 = computed block.  Fuses bit_block_count, calc_block_digest0,
 // bit_block_calc_change, the opt_copy_bit_block classification and its bit_to_gap branch
 // (src/bmfunc.h:5808,1239,6040,5540; src/bmblocks.h:1355-1409).
 template <bool EMPTY_DIGEST_IS_NULL>
 __device__ __forceinline__ void finish_block(const AggParams& p, uint32_t col, uint32_t colx, uint32_t grp, uint4 R, int state,
-                                             uint32_t* K, uint32_t* s_pc, uint32_t* s_tr, uint32_t* s_dg)
+                                             uint32_t* K, uint32_t* s_pc, uint32_t* s_tr, uint32_t* s_dg, uint32_t rule = 0u)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint4* K4 = reinterpret_cast<uint4*>(K);
@@ -434,6 +479,18 @@ __device__ __forceinline__ void finish_block(const AggParams& p, uint32_t col, u
     uint32_t kd;
     if (state == 0) kd = BMB200_BLK_NULL;
     else if (state == 1) kd = BMB200_BLK_FULL;
+    else if (rule) {                     // two-operand bvector op: the kind follows the argument kinds (binop_rule)
+        const uint32_t mode = rule & 3u;
+        if (rule & kRuleFull) kd = BMB200_BLK_FULL;
+        else if (mode == kRuleCloneBit) kd = BMB200_BLK_BIT;
+        else if (mode == kRuleCloneGap) kd = tpc == 0u ? BMB200_BLK_NULL : tpc == 65536u ? BMB200_BLK_FULL : BMB200_BLK_GAP;
+        else if ((rule & kRuleZchk) && tpc == 0u) kd = BMB200_BLK_NULL;
+        else if ((rule & kRuleOchk) && tpc == 65536u) kd = BMB200_BLK_FULL;
+        else if (!p.compress) kd = BMB200_BLK_BIT;
+        else if (runs == 1u) kd = tpc ? BMB200_BLK_FULL : BMB200_BLK_NULL;      // optimize_bit_block
+        else if (runs < BMB200_GAP_THRESHOLD) kd = BMB200_BLK_GAP;
+        else kd = BMB200_BLK_BIT;
+    }
     else if (EMPTY_DIGEST_IS_NULL && dg == 0) kd = BMB200_BLK_NULL;
     else if (!p.compress) kd = BMB200_BLK_BIT;
     else if (runs == 1u) kd = tpc ? BMB200_BLK_FULL : BMB200_BLK_NULL;
@@ -544,6 +601,15 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
         const uint32_t n0 = gb1 - gb0, n1 = (OP == BMB200_OP_AND_SUB) ? gb2 - gb1 : 0u;
         const uint32_t ntot = n0 + n1;
         const uint32_t* gmem = p.group + gb0;
+        uint32_t rule = 0u;
+        if (p.binary) {                  // two-operand op: members 0 and 1 are the arguments (a, b)
+            const uint32_t* dr = p.set.desc + (size_t)nb * M;
+            rule = binop_rule(p.binary - 1u, dr[gmem[0]] & 3u, dr[gmem[1]] & 3u);
+            if (rule & kRuleMerge) {     // GAP x GAP was merged by gap_merge_kernel, unless the merged block outgrew the GAP format (kind 0xFF)
+                if (p.kind[col] != 0xffu) { __syncthreads(); continue; }    // (barrier: nobody may still be reading s_col when thread 0 rewrites it)
+                rule = kRuleComputed;    // convert_gap2bitset: a bit-block, never re-classified
+            }
+        }
 
         // live mask: everything alive (nothing covered yet / every bit still a candidate); XOR starts from zero
         K4[tid] = kIsXor ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(~0u, ~0u, ~0u, ~0u);
@@ -881,7 +947,7 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
         if (state == 0) R = make_uint4(0u, 0u, 0u, 0u);
         if (state == 1) R = make_uint4(~0u, ~0u, ~0u, ~0u);
 
-        finish_block<OP != BMB200_OP_OR>(p, col, colx, grp, R, state, K, s_pc, s_tr, s_dg);
+        finish_block<OP != BMB200_OP_OR>(p, col, colx, grp, R, state, K, s_pc, s_tr, s_dg, rule);
     }
 }
 

@@ -12,6 +12,7 @@
 #include "aux_kernels.cuh"
 #include "scan_kernel.cuh"
 #include "shift_kernel.cuh"
+#include "binop_kernel.cuh"
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -47,7 +48,7 @@ struct bmb200_ctx {
     void* d_tmp[13] = {};                   // device temporaries of bmb200_set_upload_blobs (staging, token tables, decode scratch): kept
     size_t d_tmp_cap[13] = {};              //   between calls, grown on demand -- cudaMalloc / cudaFree of a few hundred MB costs tens of ms each
     int gap_mode = 0;                       // 0 = stream sorted GAP lists through the smem ring, 1 = always gather
-    bool attr_set = false;
+    bool attr_set = false, merge_attr_set = false;
     size_t agg_dyn[4] = {};                 // dynamic shared memory per agg_kernel<OP> (set_agg_attrs)
     int host_threads = 0;                   // host threads of bmb200_set_upload_vectors (0 = hardware concurrency, at most 64)
     uint8_t* h_ring[kStageSlots] = {};      // pinned staging ring of bmb200_set_upload_vectors (grow-only)
@@ -1137,6 +1138,73 @@ int bmb200_aggregate(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_agg_ar
     const uint32_t off[3] = {0u, a->n0, a->n0 + n1};
     bmb200_batch_args b{a->op, a->flags & ~BMB200_F_OR_TARGET, 1u, mem.data(), off, a->nb_from, a->nb_to};
     return bmb200_aggregate_batch(ctx, set, &b, inout);
+}
+
+int bmb200_binop(bmb200_ctx* ctx, const bmb200_set* set, int op, uint32_t va, uint32_t vb, uint32_t flags,
+                 uint32_t nb_from, uint32_t nb_to, bmb200_result** inout)
+{
+    if (!ctx || !set || !inout || set->ctx != ctx) return BMB200_ERR_BADARG;
+    if (op != BMB200_OP_OR && op != BMB200_OP_AND && op != BMB200_OP_XOR && op != BMB200_OP_SUB) return BMB200_ERR_BADARG;
+    if (flags & (BMB200_F_COUNT_ONLY | BMB200_F_OR_TARGET)) return BMB200_ERR_BADARG;
+    if (va >= set->v.n_vec || vb >= set->v.n_vec) return BMB200_ERR_RANGE;
+    if (!nb_to) nb_to = set->v.n_blocks;
+    if (nb_from >= nb_to || nb_to > set->v.n_blocks) return BMB200_ERR_RANGE;
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t cols = nb_to - nb_from;
+    const bool compress = (flags & BMB200_F_OPT_COMPRESS) != 0;
+    bmb200_result* r = *inout;
+    if (r && (r->ctx != ctx || r->n_cols != cols || r->n_groups != 1u || !r->blocks || !r->gaps || r->or_blocks)) { bmb200_result_free(r); r = nullptr; *inout = nullptr; }
+    if (!r) { int rc = result_alloc(ctx, cols, 1u, true, true, false, &r); if (rc) return rc; }
+    r->has_blocks = true; r->compress = true; r->gaps_ready = true;      // GAP-kind results exist in every opt mode (GAP x GAP merges, cloned GAP blocks)
+    auto bail = [&](int rc) { if (!*inout) bmb200_result_free(r); return rc; };
+    // the two member ids (a, b) -> device, through the pinned group staging buffer like every aggregate
+    const uint32_t mem[2] = {va, vb};
+    const uint32_t off[3] = {0u, op == BMB200_OP_SUB ? 1u : 2u, 2u};
+    const size_t nwords = 5;
+    if (nwords > ctx->group_cap) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(ctx->d_group); if (ctx->h_group) cudaFreeHost(ctx->h_group);
+        ctx->d_group = nullptr; ctx->h_group = nullptr; ctx->group_cap = 0; ctx->last_group.clear();
+        if (cudaMalloc((void**)&ctx->d_group, 1024 * 4) != cudaSuccess || cudaMallocHost((void**)&ctx->h_group, 1024 * 4) != cudaSuccess) { ctx->last_err = "group buffer allocation"; return bail(BMB200_ERR_BADALLOC); }
+        ctx->group_cap = 1024;
+    }
+    ctx->last_group.clear();
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);              // the staging buffer may still feed a previous launch
+    memcpy(ctx->h_group, mem, 8); memcpy(ctx->h_group + 2, off, 12);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_group, ctx->h_group, nwords * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_work, 0, 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(r->total, 0, 8, ctx->stream);
+    if (e == cudaSuccess) set_agg_attrs(ctx, &e);
+    if (e == cudaSuccess && !ctx->merge_attr_set) { e = cudaFuncSetAttribute(gap_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMergeSmem); ctx->merge_attr_set = (e == cudaSuccess); }
+    if (e != cudaSuccess) { ctx->last_err = std::string("binop: ") + cudaGetErrorString(e); return bail(BMB200_ERR_CUDA); }
+    const uint32_t bop = op == BMB200_OP_OR ? BINOP_OR : op == BMB200_OP_AND ? BINOP_AND : op == BMB200_OP_XOR ? BINOP_XOR : BINOP_SUB;
+    // 1) GAP x GAP columns: merged as run lists (never expanded)
+    MergeParams mp{};
+    mp.set = set->v; mp.va = va; mp.vb = vb; mp.op = bop; mp.nb_from = nb_from; mp.n_cols = cols;
+    mp.kind = r->kind; mp.popcnt = r->popcnt; mp.digest = r->digest; mp.nruns = r->nruns; mp.gaps = r->gaps; mp.total = r->total;
+    uint32_t mgrid = (cols + kMergeWarps - 1) / kMergeWarps; const uint32_t mmax = (uint32_t)ctx->sm_count * 8u; if (mgrid > mmax) mgrid = mmax;
+    gap_merge_kernel<<<mgrid, kMergeWarps * 32, kMergeSmem, ctx->stream>>>(mp);
+    int rc = after_launch(ctx);
+    if (rc) return bail(rc);
+    // 2) every other pairing (and merged blocks that outgrew the GAP format) through the block kernel, kinds by binop_rule
+    AggParams p{};
+    p.set = set->v; p.group = ctx->d_group; p.goff = ctx->d_group + 2; p.n_groups = 1;
+    p.nb_from = nb_from; p.n_cols = cols; p.compress = compress ? 1u : 0u; p.store_blocks = 1u;
+    p.blocks = r->blocks; p.popcnt = r->popcnt; p.digest = r->digest; p.nruns = r->nruns; p.kind = r->kind; p.gaps = r->gaps;
+    p.total = r->total; p.work_counter = ctx->d_work; p.or_blocks = nullptr;
+    p.gap_mode = (uint32_t)ctx->gap_mode; p.gap_pool_bytes = set->gap_pool_bytes; p.binary = 1u + bop;
+    uint32_t grid = (uint32_t)(ctx->sm_count * ctx->agg_ctas_per_sm); if (grid > cols) grid = cols;
+    const int kop = op == BMB200_OP_SUB ? BMB200_OP_AND_SUB : op;
+    p.dyn_bytes = (uint32_t)ctx->agg_dyn[kop];
+    switch (kop) {
+    case BMB200_OP_OR:      agg_kernel<BMB200_OP_OR><<<grid, kAggThreads, ctx->agg_dyn[BMB200_OP_OR], ctx->stream>>>(p); break;
+    case BMB200_OP_AND:     agg_kernel<BMB200_OP_AND><<<grid, kAggThreads, ctx->agg_dyn[BMB200_OP_AND], ctx->stream>>>(p); break;
+    case BMB200_OP_AND_SUB: agg_kernel<BMB200_OP_AND_SUB><<<grid, kAggThreads, ctx->agg_dyn[BMB200_OP_AND_SUB], ctx->stream>>>(p); break;
+    default:                agg_kernel<BMB200_OP_XOR><<<grid, kAggThreads, ctx->agg_dyn[BMB200_OP_XOR], ctx->stream>>>(p); break;
+    }
+    if ((rc = after_launch(ctx))) return bail(rc);
+    *inout = r;
+    return BMB200_OK;
 }
 
 int bmb200_scan(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_scan_args* a, bmb200_result** inout)

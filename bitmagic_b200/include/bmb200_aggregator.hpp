@@ -537,15 +537,42 @@ private:
     bool complete_ = false;
 };
 
-/// 3-operand bvector ops (src/bm.h:1745-1850): target = a OP b
-template<class BV> void bit_or (context& c, BV& t, const BV& a, const BV& b, typename BV::optmode opt = BV::opt_none)
-{ aggregator<BV> g(c); g.set_optimization(opt); const BV* s[2] = {&a, &b}; g.combine_or(t, s, 2); }
-template<class BV> void bit_and(context& c, BV& t, const BV& a, const BV& b, typename BV::optmode opt = BV::opt_none)
-{ aggregator<BV> g(c); g.set_optimization(opt); const BV* s[2] = {&a, &b}; g.combine_and(t, s, 2); }
-template<class BV> void bit_sub(context& c, BV& t, const BV& a, const BV& b)
-{ aggregator<BV> g(c); const BV* s0[1] = {&a}; const BV* s1[1] = {&b}; g.combine_and_sub(t, s0, 1, s1, 1, false); }
-template<class BV> void bit_xor(context& c, BV& t, const BV& a, const BV& b, typename BV::optmode opt = BV::opt_none)
-{ aggregator<BV> g(c); g.set_optimization(opt); const BV* s[2] = {&a, &b}; g.combine_xor(t, s, 2); }
+/// 3-operand bvector ops (src/bm.h:1745-1850): target = a OP b through bmb200_binop.  Every result block gets the KIND the
+/// reference's combine_operation_block_* gives it (src/bm.h:6945-7380): a NULL / FULL argument clones the other block in its own
+/// kind, GAP x GAP is merged as run lists on the device (no 8 KB expansion), GAP x bit / bit x bit yield a bit-block that only
+/// opt_compress re-classifies -- so calc_stat() of the target equals the reference's, not just compare() == 0.
+/// `ds` (optional): a resident device_set holding both operands; otherwise they are uploaded for this call.
+template<class BV>
+void binop(context& c, int op, BV& t, const BV& a, const BV& b, typename BV::optmode opt = BV::opt_none, const device_set<BV>* ds = nullptr)
+{
+    if (&a == &b) { if (op == BMB200_OP_AND || op == BMB200_OP_OR) t = a; else t.clear(true); return; }   // src/bm.h:6190, 5978
+    const BV* both[2] = {&a, &b};
+    uint32_t ia = 0, ib = 1, n_blocks = 0, nb_off = 0; bmb200_set* set = nullptr; bool own = true;
+    if (ds && ds->resident() && ds->index_of(&a) >= 0 && ds->index_of(&b) >= 0)
+    { set = ds->handle(); ia = (uint32_t)ds->index_of(&a); ib = (uint32_t)ds->index_of(&b); n_blocks = ds->n_blocks(); nb_off = ds->nb_from(); own = false; }
+    else
+    {
+        n_blocks = std::max(detail::blocks_of(a), detail::blocks_of(b));
+        if (!n_blocks) { t.clear(true); return; }
+        std::vector<detail::tree_view<BV>> views; std::vector<bmb200_vec_blocks> vb;
+        detail::build_views(both, 2, 0u, n_blocks, views, vb);
+        check(bmb200_set_upload_vectors(c.get(), 2, n_blocks, vb.data(), &set), "bmb200_set_upload_vectors");
+    }
+    bmb200_result* res = nullptr;
+    int rc = bmb200_binop(c.get(), set, op, ia, ib, opt == BV::opt_compress ? BMB200_F_OPT_COMPRESS : BMB200_F_OPT_NONE, 0, 0, &res);
+    uint64_t total = 0, nb = 0, ng = 0;
+    const uint8_t* kind = nullptr; const uint64_t* off = nullptr; const uint32_t* bits = nullptr; const uint16_t* gaps = nullptr;
+    if (!rc) rc = bmb200_result_fetch_view(res, &kind, &off, &bits, &gaps, &nb, &ng, &total);
+    typename BV::size_type sz = std::max(a.size(), b.size());
+    if (!rc) detail::store_result(t, sz, n_blocks, kind, off, bits, gaps, nb_off);
+    if (res) bmb200_result_free(res);
+    if (own) bmb200_set_free(set);
+    check(rc, "bmb200_binop");
+}
+template<class BV> void bit_or (context& c, BV& t, const BV& a, const BV& b, typename BV::optmode opt = BV::opt_none) { binop(c, BMB200_OP_OR, t, a, b, opt); }
+template<class BV> void bit_and(context& c, BV& t, const BV& a, const BV& b, typename BV::optmode opt = BV::opt_none) { binop(c, BMB200_OP_AND, t, a, b, opt); }
+template<class BV> void bit_sub(context& c, BV& t, const BV& a, const BV& b, typename BV::optmode opt = BV::opt_none) { binop(c, BMB200_OP_SUB, t, a, b, opt); }
+template<class BV> void bit_xor(context& c, BV& t, const BV& a, const BV& b, typename BV::optmode opt = BV::opt_none) { binop(c, BMB200_OP_XOR, t, a, b, opt); }
 
 /// Operands that arrive as serialization BLOBs (bm::serializer<BV> output, any compression level incl. the default 6): the BLOBs
 /// are decoded ON THE GPU (bmb200_set_upload_blobs) and aggregated there -- the bvectors are never materialised on the host.

@@ -80,6 +80,8 @@ extern "C" {
                                  * n <= 65536.  Bits pushed past the last block column of the set are dropped: give the
                                  * set one spare (NULL) column if the sources can carry out of their last block. */
 
+#define BMB200_OP_SUB      5   /* bmb200_binop only: a AND NOT b (bvector::bit_sub) */
+
 /* ---- flags for bmb200_aggregate ---- */
 #define BMB200_F_COUNT_ONLY  1u  /* per-column popcount/digest only; no result blocks stored */
 #define BMB200_F_OPT_NONE    0u  /* result kinds as aggregator opt_mode_ == opt_none           */
@@ -239,6 +241,14 @@ int bmb200_synth_set(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks,
  * *reuse (may be NULL): pass a previous result of the same shape to recycle its buffers. */
 int bmb200_aggregate(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_agg_args* args,
                      bmb200_result** inout);
+/* Two-operand bvector ops with the reference's result KINDS: target = a OP b for bvector::bit_or / bit_and / bit_xor / bit_sub
+ * (src/bm.h:5973,6185,6072,6403; op = BMB200_OP_OR / _AND / _XOR / _SUB).  Per block column the kind of the result follows
+ * combine_operation_block_or/_and/_xor/_sub (src/bm.h:6945,7100,7018,7285): a NULL / FULL argument clones the other block in
+ * its own kind, GAP x GAP is MERGED as run lists on the device (gap_buff_op, src/bmfunc.h:3747: no 8 KB expansion; result GAP,
+ * all-zero -> nothing, too long -> bit-block), GAP x bit and bit x bit give a bit-block that only BMB200_F_OPT_COMPRESS
+ * re-classifies (optimize_bit_block).  calc_stat() of the stored result equals the reference's.  flags: F_OPT_NONE / F_OPT_COMPRESS. */
+int bmb200_binop(bmb200_ctx* ctx, const bmb200_set* set, int op, uint32_t va, uint32_t vb, uint32_t flags,
+                 uint32_t nb_from, uint32_t nb_to, bmb200_result** inout);
 /* aggregator::combine_and_sub(TPipe&) (src/bmaggregator.h:1291-1453): every group in ONE launch.  The result has
  * n_groups * n_cols columns, group-major (column c of group g at index g * n_cols + c); metadata / fetch calls work
  * on that flat range. */

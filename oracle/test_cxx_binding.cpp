@@ -136,7 +136,33 @@ int main()
                 CHECK(f1 == f2 && a.compare(b) == 0 && a.count() == b.count(), "combine_shift_right_and n=%zu opt=%d (%u vs %u bits)", n, opt, (unsigned)a.count(), (unsigned)b.count());
             }
     }
-    {   // 3-operand ops
+    {   // 3-operand ops: bits AND block kinds (calc_stat) for every pairing of block kinds and both opt modes.
+        // all[0..5] hold bit-blocks (not optimized), all[6..] are optimize()d (GAP / FULL / NULL / bit), k % 5 == 3 have FULL ranges
+        bvect sparse_a, sparse_b, inv;                        // GAP x GAP with disjoint, nested and identical runs; an almost-full vector
+        for (unsigned p = 100; p < n_bits; p += 997) { sparse_a.set_bit(p); sparse_a.set_bit(p + 1); }
+        for (unsigned p = 101; p < n_bits; p += 1499) sparse_b.set_range(p, p + 40);
+        inv.set_range(0, n_bits - 1); for (unsigned p = 5; p < n_bits; p += 7919) inv.clear_bit(p);
+        { BM_DECLARE_TEMP_BLOCK(tb) sparse_a.optimize(tb); sparse_b.optimize(tb); inv.optimize(tb); }
+        std::vector<const bvect*> ops = {all[0], all[3], all[7], all[8], all[13], all[20], &sparse_a, &sparse_b, &inv};
+        for (int opt = 0; opt < 2; ++opt) {
+            bvect::optmode om = opt ? bvect::opt_compress : bvect::opt_none;
+            for (size_t x = 0; x < ops.size(); ++x) for (size_t y = 0; y < ops.size(); ++y) {
+                if (x == y) continue;
+                for (int op = 0; op < 4; ++op) {
+                    bvect t1, t2;
+                    switch (op) {
+                    case 0: t1.bit_and(*ops[x], *ops[y], om); bm::b200::bit_and(ctx, t2, *ops[x], *ops[y], om); break;
+                    case 1: t1.bit_or (*ops[x], *ops[y], om); bm::b200::bit_or (ctx, t2, *ops[x], *ops[y], om); break;
+                    case 2: t1.bit_sub(*ops[x], *ops[y], om); bm::b200::bit_sub(ctx, t2, *ops[x], *ops[y], om); break;
+                    default: t1.bit_xor(*ops[x], *ops[y], om); bm::b200::bit_xor(ctx, t2, *ops[x], *ops[y], om); break;
+                    }
+                    bvect::statistics s1, s2; t1.calc_stat(&s1); t2.calc_stat(&s2);
+                    CHECK(t1.compare(t2) == 0 && t1.count() == t2.count(), "binop %d (%zu,%zu) opt=%d: bits", op, x, y, opt);
+                    CHECK(s1.bit_blocks == s2.bit_blocks && s1.gap_blocks == s2.gap_blocks, "binop %d (%zu,%zu) opt=%d: kinds ref %zu bit / %zu gap, b200 %zu bit / %zu gap",
+                          op, x, y, opt, (size_t)s1.bit_blocks, (size_t)s1.gap_blocks, (size_t)s2.bit_blocks, (size_t)s2.gap_blocks);
+                }
+            }
+        }
         bvect t1, t2;
         t1.bit_and(*all[0], *all[9], bvect::opt_none); bm::b200::bit_and(ctx, t2, *all[0], *all[9]); CHECK(t1.compare(t2) == 0, "bit_and");
         t1.bit_or(*all[2], *all[20], bvect::opt_none); bm::b200::bit_or(ctx, t2, *all[2], *all[20]); CHECK(t1.compare(t2) == 0, "bit_or");
