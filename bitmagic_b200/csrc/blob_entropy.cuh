@@ -467,7 +467,10 @@ BME_HD uint32_t ent_count_runs(const EntCtx& c)
     return runs;
 }
 // bit_block_to_gap (src/bmfunc.h:5540): out[0] = header, out[1..len] run ends; len = runs (computed by ent_count_runs)
-BME_HD void ent_write_gap(const EntCtx& c, uint16_t* out, uint32_t len)
+// sb_member: the block was built bit by bit under BM_GAP (bvector::gap_block_set_no_ret, src/bm.h:4800): its capacity level only
+// rises when the run count exceeds glen[level] - 4, so level = the smallest one with len <= glen - 4; every other GAP token goes
+// through deserialize_gap, which takes gap_calc_level(gap_length = len + 1)
+BME_HD void ent_write_gap(const EntCtx& c, uint16_t* out, uint32_t len, bool sb_member = false)
 {
     bme_sync();
     uint32_t base = 0;
@@ -490,7 +493,8 @@ BME_HD void ent_write_gap(const EntCtx& c, uint16_t* out, uint32_t len)
     }
     if (c.t.lane == 0) {
         out[len] = 65535u;
-        const uint32_t lvl = (len + 1u) <= 124u ? 0u : (len + 1u) <= 252u ? 1u : (len + 1u) <= 508u ? 2u : 3u;   // gap_calc_level(gap_length)
+        const uint32_t ll = sb_member ? len : len + 1u;
+        const uint32_t lvl = ll <= 124u ? 0u : ll <= 252u ? 1u : ll <= 508u ? 2u : 3u;   // gap_calc_level
         out[0] = (uint16_t)((c.bm[0] & 1u) | (lvl << 1) | (len << 3));
     }
     bme_sync();
@@ -863,7 +867,7 @@ BME_HDN int ent_walk_segment(const EntCtx& c, const uint8_t* stg, const EntSeg& 
                     const uint32_t runs = ent_count_runs(c);
                     if (lead) {
                         BlobTok t; t.nb = (uint32_t)(nb0 + blk); t.type = kTokSbMember; t.off = off; t.aux = (uint32_t)nb0; t.first = c.bm[0] & 1u;
-                        const bool as_gap = runs + 1u <= kGapFitWords;
+                        const bool as_gap = runs <= kGapFitWords;              // stays GAP while runs <= glen(3) - 4 (gap_block_set_no_ret, src/bm.h:4800)
                         t.kind = as_gap ? BMB200_BLK_GAP : BMB200_BLK_BIT; t.gap_words = as_gap ? runs + 1u : 0u;
                         ent_push(o, t, &err);
                     }
@@ -884,11 +888,11 @@ BME_HDN int ent_walk_segment(const EntCtx& c, const uint8_t* stg, const EntSeg& 
 // ------------------------------------------------------------------------------------------------------------------
 struct EntSetView { uint32_t n_vec, n_blocks; const uint32_t* desc; const uint64_t* bit_base; const uint64_t* gap_base; };
 
-BME_HD void ent_store_gap(const EntCtx& c, uint16_t* unit, uint32_t pad)
+BME_HD void ent_store_gap(const EntCtx& c, uint16_t* unit, uint32_t pad, bool sb_member = false)
 {
     const uint32_t runs = ent_count_runs(c);
     if (c.t.lane == 0u && pad) unit[0] = 0xffffu;
-    ent_write_gap(c, unit + pad, runs);
+    ent_write_gap(c, unit + pad, runs, sb_member);
 }
 
 BME_HDN int ent_emit(const EntCtx& c, const uint8_t* stg, uint64_t src, uint64_t end, uint32_t code, uint32_t v, uint64_t dst, uint32_t kind,
@@ -911,7 +915,7 @@ BME_HDN int ent_emit(const EntCtx& c, const uint8_t* stg, uint64_t src, uint64_t
                 if (kd == BMB200_BLK_BIT || kd == BMB200_BLK_GAP) {
                     ent_sblock_fill(c, arr, k, k2);
                     if (kd == BMB200_BLK_BIT) ent_write_bits(c, bit_pool + (set.bit_base[col] + rel) * (size_t)kEntWords);
-                    else ent_store_gap(c, gap_pool + (set.gap_base[col] + rel) * (size_t)BMB200_GAP_UNIT_WORDS, (d & BMB200_DESC_GAP_PAD) ? 1u : 0u);
+                    else ent_store_gap(c, gap_pool + (set.gap_base[col] + rel) * (size_t)BMB200_GAP_UNIT_WORDS, (d & BMB200_DESC_GAP_PAD) ? 1u : 0u, true);
                 }
             }
             k = k2;

@@ -131,12 +131,22 @@ class ShardedRS:
 def device_rs_callables(rs):
     """(local_rank, local_select) over a bitmagic_b200.DeviceRS for ShardedRS: CUDA int64 tensors in and out, the batched
     kernels read / write them in place through the *_dev entry points of the C ABI (no host round trip)."""
+    def same_stream(t: torch.Tensor):
+        # the kernels run on the CONTEXT's stream while torch produced `t` (and will consume the answers) on ITS current stream:
+        # both must be the same stream, otherwise nothing orders the two (ctx.set_stream(torch.cuda.current_stream().cuda_stream))
+        cur = torch.cuda.current_stream(t.device).cuda_stream
+        if rs.ctx.get_stream() != cur:
+            raise RuntimeError("device_rs_callables: the bmb200 context runs on another CUDA stream than torch's current stream; "
+                               "call ctx.set_stream(torch.cuda.current_stream().cuda_stream) first")
+
     def local_rank(pos_local: torch.Tensor) -> torch.Tensor:
+        same_stream(pos_local)
         out = torch.empty_like(pos_local)
         rs.rank_dev(pos_local.data_ptr(), pos_local.numel(), out.data_ptr())
         return out
 
     def local_select(r_local: torch.Tensor):
+        same_stream(r_local)
         pos = torch.empty_like(r_local)
         found = torch.empty(r_local.numel(), dtype=torch.uint8, device=r_local.device)
         rs.select_dev(r_local.data_ptr(), r_local.numel(), pos.data_ptr(), found.data_ptr())

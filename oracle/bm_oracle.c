@@ -587,7 +587,9 @@ int orc_deserialize(const uint8_t* blob, uint64_t size, uint32_t n_cols, uint8_t
                     uint64_t col = (uint64_t)sb * 256u + c;
                     if (col < n_cols) {
                         uint32_t len = orc_bit_to_gap(tg, tb);
-                        int level = gap_calc_level(len + 1);
+                        /* gap_block_set_no_ret (src/bm.h:4800): the block is extended when the run count exceeds gap_limit = glen[level] - 4,
+                         * so it stays GAP while len <= 1276 and sits on the smallest level with len <= glen - 4 */
+                        int level = gap_calc_level(len);
                         if (level < 0) { kind[col] = BMB200_BLK_BIT; }
                         else { kind[col] = BMB200_BLK_GAP; tg[0] = (uint16_t)((tg[0] & 1u) | ((uint32_t)level << 1) | (len << 3));
                                if (gaps) memcpy(gaps + col * GMAX, tg, ((size_t)len + 1) * 2); }

@@ -157,3 +157,29 @@ def c1_vectors():
             v.set_bits(nb, bits_to_words(bits[nb * BLOCK_BITS:(nb + 1) * BLOCK_BITS]))
         out.append(v)
     return out
+
+
+def block_with_exact_runs(runs):
+    """Bit-block of isolated bits with exactly `runs` runs (even counts start with a 1-run at bit 0)."""
+    bits = np.zeros(BLOCK_BITS, np.uint8)
+    n = (runs - 2) // 2 if runs % 2 == 0 else (runs - 1) // 2
+    if runs % 2 == 0:
+        bits[0] = 1
+    bits[10 + 3 * np.arange(n)] = 1
+    return bits_to_words(bits)
+
+
+SB_MEMBER_RUNS = [3, 123, 124, 125, 126, 252, 253, 254, 508, 509, 510, 1275, 1276, 1277, 1279]
+
+
+def superblock_threshold_vector(n_blocks=256):
+    """One sparse super-block whose member blocks sit right at the GAP capacity levels (124 / 252 / 508 / 1276 runs): the serializer
+    folds it into ONE set_sblock_bienc_v3 token at levels 5 / 6, and bm::deserialize rebuilds the members bit by bit under BM_GAP."""
+    v = bm.BVector(n_blocks)
+    for i, r in enumerate(SB_MEMBER_RUNS):
+        w = block_with_exact_runs(r)
+        if r < 1276:
+            v.set_gap(2 * i, bits_to_gap(w))
+        else:
+            v.set_bits(2 * i, w)
+    return v

@@ -935,3 +935,55 @@ def test_e2e_harness_real_bvectors_cold_warm_and_check(ctx):
         assert eq.value == 1, "warm (resident device_set) result bvector differs from bm::aggregator"
     lib.e2e_free(h)
     dset.free()
+
+
+@pytest.mark.skipif(not orclib.have_ref(), reason="prebuilt reference library not present")
+def test_deserialize_to_device_superblock_members_at_capacity_levels(ctx):
+    """Super-block token whose member blocks have exactly 124 / 252 / 508 / 1276 / 1277 runs (gap_block_set_no_ret thresholds,
+    src/bm.h:4800): kinds, GAP words incl. the header level bits and bits decoded on the GPU == bm::deserialize."""
+    v = gen.superblock_threshold_vector()
+    ps = bm.PackedSet.pack([v])
+    for level in (5, 6):
+        blob = orclib.ref_serialize(ps, 0, level)
+        rkind, rpop, rblk, rgap = orclib.ref_deserialize(blob, ps.n_blocks)
+        dset = bm.DeviceSet.upload_blobs(ctx, [blob], ps.n_blocks)
+        bv = dset.download().vector(0)
+        assert np.array_equal(bv.kind, rkind)
+        for c in range(ps.n_blocks):
+            if rkind[c] == bm.BLK_GAP:
+                n = (int(rgap[c][0]) >> 3) + 1
+                assert np.array_equal(bv.blocks[c], rgap[c][:n]), f"level {level} block {c}"
+            elif rkind[c] == bm.BLK_BIT:
+                assert np.array_equal(bv.blocks[c], rblk[c])
+        dset.free()
+
+
+@pytest.mark.skipif(not orclib.have_ref(), reason="prebuilt reference library not present")
+def test_binop_result_kinds_vs_reference(ctx):
+    """bmb200_binop (bvector::bit_or / bit_and / bit_xor / bit_sub): bits, popcounts AND block kinds of every column against the real
+    3-operand ops, for every pairing of NULL / FULL / bit / GAP argument blocks and both opt modes; GAP x GAP goes through the
+    device merge (gap_merge_kernel), incl. identical, disjoint and nested run lists."""
+    rng = np.random.default_rng(21)
+    vecs = gen.mixed_vectors(rng, 6, 40, p_null=0.15, p_full=0.1, p_gap=0.45) + gen.edge_vectors(40)[:4]
+    same = bm.BVector(40)
+    for nb in range(40):                                      # a GAP-only vector and an exact copy of it
+        same.set_gap(nb, bm.hostfmt.bits_to_gap(gen.block_with_runs(rng, int(rng.integers(2, 900)))))
+    vecs += [same, same.slice(0, 40)]
+    ps = bm.PackedSet.pack(vecs, 40)
+    dset = bm.DeviceSet.upload(ctx, ps)
+    n = len(vecs)
+    ops = {0: bm.OP_OR, 1: bm.OP_AND, 2: bm.capi.OP_SUB, 3: bm.OP_XOR}
+    pairs = [(a, b) for a in range(n) for b in range(n) if a != b]
+    for compress in (False, True):
+        for (a, b) in pairs[:: 3 if compress else 2]:
+            for rop, gop in ops.items():
+                rkind, rpop, rblk, rcnt = orclib.ref_binop(ps, rop, a, b, compress)
+                res = bm.capi.binop(ctx, dset, gop, a, b, C if compress else 0)
+                kind, pop, dig, nr = res.meta()
+                fk, off, bits, gaps = res.fetch()
+                bv = bm.result_to_bvector(fk, off, bits, gaps)
+                res.free()
+                assert np.array_equal(kind, rkind), f"kinds: op {rop} ({a},{b}) compress={compress}: {kind} vs {rkind}"
+                assert np.array_equal(pop, rpop) and int(pop.sum()) == rcnt
+                assert np.array_equal(np.stack([bv.block_words(c) for c in range(40)]), rblk)
+    dset.free()

@@ -483,3 +483,27 @@ def test_ref_job_matches_oracle_all_columns():
             assert tot == int(op_.sum())
             assert np.array_equal(k, ok) and np.array_equal(p, op_) and np.array_equal(d, od)
             assert np.array_equal(gl[k == bm.BLK_GAP], onr[k == bm.BLK_GAP])
+
+
+@needs_ref
+def test_superblock_members_at_the_gap_capacity_levels():
+    """Members of a super-block token (set_sblock_bienc_v3) are rebuilt with set_bit_no_check under BM_GAP (gap_block_set_no_ret,
+    src/bm.h:4800): a block stays GAP while runs <= 1276 and sits on the smallest level with runs <= glen[level] - 4 -- NOT the
+    deserialize_gap rule (gap_calc_level(runs + 1)).  Oracle and the host build of the product's decoder == bm::deserialize, headers included."""
+    v = gen.superblock_threshold_vector()
+    ps = bm.PackedSet.pack([v])
+    for level in (5, 6):
+        blob = orclib.ref_serialize(ps, 0, level)
+        h = orclib.oracle_token_hist(True)
+        rkind, rpop, rblk, rgap = orclib.ref_deserialize(blob, ps.n_blocks)
+        rc, kind, blk, gaps = orclib.oracle_deserialize(blob, ps.n_blocks)
+        orclib.oracle_token_hist(False)
+        assert h[68] == 1, "the vector should serialize as one super-block token"
+        assert rc == 0 and np.array_equal(kind, rkind) and np.array_equal(blk, rblk) and np.array_equal(gaps, rgap)
+        by_runs = {r: (int(rkind[2 * i]), (int(rgap[2 * i][0]) >> 1) & 3) for i, r in enumerate(gen.SB_MEMBER_RUNS)}
+        assert by_runs[124] == (bm.BLK_GAP, 0) and by_runs[125] == (bm.BLK_GAP, 1) and by_runs[252] == (bm.BLK_GAP, 1) and by_runs[508] == (bm.BLK_GAP, 2)
+        assert by_runs[1276] == (bm.BLK_GAP, 3) and by_runs[1277][0] == bm.BLK_BIT
+        rc, kind, dec, gw, blk, gaps, n = orclib.blob_host_check(blob, ps.n_blocks)
+        assert rc == 0 and np.array_equal(kind, rkind)
+        for c in np.flatnonzero(dec):
+            assert np.array_equal(blk[c], rblk[c]) if kind[c] == bm.BLK_BIT else np.array_equal(gaps[c], rgap[c])
