@@ -266,6 +266,9 @@ __device__ __noinline__ void flat_pair_tail(uint32_t Ls, uint32_t w)      // wor
     for (; rem >= 32u; rem -= 32u, a += 4u) reds_and(a, 0u);
     if (rem) reds_and(a, 0xffffffffu << rem);
 }
+#ifndef BMB200_FLAT_MAX_MODE      /* highest FLAT sweep form a column may reach: 1 = test-first, 2 = + grouped branch for a nearly dead live mask */
+#define BMB200_FLAT_MAX_MODE 2
+#endif
 #ifndef BMB200_FLAT_LEAN          /* 1: lean pair decode -- hi - lo by one dp2a, word address by one and-or (L is 8 KB aligned) */
 #define BMB200_FLAT_LEAN 1
 #endif
@@ -279,9 +282,13 @@ __device__ __forceinline__ uint32_t and_or(uint32_t x, uint32_t msk, uint32_t ba
 {
     uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(x), "r"(msk), "r"(base)); return r;
 }
-template <bool TEST>
+// MODE 0: L is mostly alive -- every run goes straight to its (predicated) atomic.  MODE 1: test-first.  MODE 2: test-first for a
+// nearly dead L: the four hit tests of a quad are OR-ed and ONE branch guards the four conditional atomics, so a warp without a
+// single hit (the common case once < 0.4 % of L is alive) skips them in 8 instructions instead of 16.
+template <int MODE>
 __device__ __forceinline__ void flat_quad(uint32_t Ls, const uint4& q)
 {
+    constexpr bool TEST = MODE != 0;
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
     uint32_t a[4], m[4], nm[4], reach = 0;
 #pragma unroll
@@ -306,9 +313,16 @@ __device__ __forceinline__ void flat_quad(uint32_t Ls, const uint4& q)
     if (TEST) {
         uint32_t v[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = lds32(a[i]);
+        for (int i = 0; i < 4; ++i) v[i] = lds32(a[i]) & m[i];
+        if (MODE == 2) {
+            if ((v[0] | v[1] | v[2] | v[3]) != 0u) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) reds_and_if(a[i], nm[i], v[i] & m[i]);
+                for (int i = 0; i < 4; ++i) reds_and_if(a[i], nm[i], v[i]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) reds_and_if(a[i], nm[i], v[i]);
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) reds_and_if(a[i], nm[i], m[i]);
@@ -568,7 +582,8 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
     uint32_t Ks, ring_s;
     asm volatile("mov.u32 %0, %1;" : "=r"(Ks) : "r"(smem_u32(K)));
     asm volatile("mov.u32 %0, %1;" : "=r"(ring_s) : "r"(smem_u32(ring)));
-    uint32_t done_s, wfull_s;
+    uint32_t done_s, wfull_s, flat_next_s;
+    asm volatile("mov.u32 %0, %1;" : "=r"(flat_next_s) : "r"(smem_u32(&s_flat_next)));
     asm volatile("mov.u32 %0, %1;" : "=r"(done_s) : "r"(smem_u32(s_done)));
     asm volatile("mov.u32 %0, %1;" : "=r"(wfull_s) : "r"(smem_u32(&s_wfull[warp * kFlatSlots])));
     uint32_t wphase = 0;     // bit k = phase of this warp's slot k barrier
@@ -616,7 +631,7 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
         if (tid < 4) s_stat[tid] = 0u;
         uint4 acc0 = kIsAnd ? make_uint4(~0u, ~0u, ~0u, ~0u) : make_uint4(0u, 0u, 0u, 0u);
         uint4 acc1 = make_uint4(0u, 0u, 0u, 0u);   // union of SUB-group bit-blocks
-        bool flat_test = false;                    // FLAT consumer form of this column (warp-uniform): test-first once L is sparse
+        uint32_t flat_mode = 0;                    // FLAT consumer form of this column (warp-uniform, only ever rises): 0 atomics, 1 test-first, 2 test-first + grouped branch
 
         const uint32_t* drow = p.set.desc + (size_t)nb * M;
         const uint4* bseg = reinterpret_cast<const uint4*>(p.set.bit_pool)
@@ -741,7 +756,7 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
             // private slot) and pull them through their slots
             auto flat_claim = [&]() -> uint32_t {                // whole warp; returns the first chunk of the claimed piece
                 uint32_t c = 0;
-                if (lane == 0) c = atomicAdd(&s_flat_next, 1u) * kFlatSlots;
+                if (lane == 0) c = atoms_add(flat_next_s, 1u) * kFlatSlots;      // raw atom.shared: no warp-aggregation code around a one-lane atomic
                 return __shfl_sync(0xffffffffu, c, 0);
             };
             auto flat_fill = [&](uint32_t wlo, uint32_t wbytes, uint32_t c, uint32_t k) {   // whole warp: chunk c -> slot k (caller checked c < nfc)
@@ -819,19 +834,20 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                 }
                 gseq += nc;
             };
-            auto flat_sweep = [&](uint32_t src, uint32_t bytes, bool test) {       // one slot: 32 lanes x 16 B x 2 per step
+            auto flat_sweep = [&](uint32_t src, uint32_t bytes, uint32_t mode) {   // one slot: 32 lanes x 16 B x 2 per step
                 if (bytes == kFlatChunk) {
 #pragma unroll
                     for (uint32_t h = 0; h < kFlatChunk; h += 1024u) {
                         const uint4 qa = lds128(src + h), qb = lds128(src + h + 512u);
-                        if (test) { flat_quad<true>(Ks, qa);  flat_quad<true>(Ks, qb); }
-                        else      { flat_quad<false>(Ks, qa); flat_quad<false>(Ks, qb); }
+                        if (mode == 2u)      { flat_quad<2>(Ks, qa); flat_quad<2>(Ks, qb); }
+                        else if (mode == 1u) { flat_quad<1>(Ks, qa); flat_quad<1>(Ks, qb); }
+                        else                 { flat_quad<0>(Ks, qa); flat_quad<0>(Ks, qb); }
                     }
                 } else {                                                            // last chunk of the window
 #pragma unroll 1
                     for (uint32_t h = (uint32_t)lane * 16u; h < bytes; h += 512u) {
                         const uint4 qa = lds128(src + h - (uint32_t)lane * 16u);
-                        if (test) flat_quad<true>(Ks, qa); else flat_quad<false>(Ks, qa);
+                        if (mode) flat_quad<1>(Ks, qa); else flat_quad<0>(Ks, qa);
                     }
                 }
             };
@@ -846,12 +862,13 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                         if (c < nfc) {
                             mbar_wait_a(wfull_s + 8u * k, (wphase >> k) & 1u); wphase ^= 1u << k;
                             const uint32_t bytes = min(kFlatChunk, wbytes - c * kFlatChunk);
-                            if (!flat_test) {   // 1024-bit sample of L: below 25 % alive the test-first form wins (one shared load, rarely
-                                                // an atomic); bits of L only ever get cleared, so the switch is one-way per column
+                            if (flat_mode < BMB200_FLAT_MAX_MODE && (flat_mode == 0u || (c & 7u) == 0u)) {   // (once test-first: every 8th chunk) 1024-bit sample of L: below 25 % alive the test-first form wins (one shared load, rarely
+                                                // an atomic), below 0.4 % its grouped-branch variant; bits of L only ever get cleared, so the switches are one-way
                                 const uint32_t smp = lds32(Ks + ((((uint32_t)lane * 65u + c * 7u) & (kBlockWords - 1u)) << 2));
-                                flat_test = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(smp)) < 256u;
+                                const uint32_t alive = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(smp));
+                                flat_mode = alive < 4u ? (uint32_t)BMB200_FLAT_MAX_MODE : alive < 256u ? max(flat_mode, 1u) : flat_mode;
                             }
-                            flat_sweep(ring_s + ((uint32_t)warp * kFlatSlots + k) * kFlatChunk + (uint32_t)lane * 16u, bytes, flat_test);
+                            flat_sweep(ring_s + ((uint32_t)warp * kFlatSlots + k) * kFlatChunk + (uint32_t)lane * 16u, bytes, flat_mode);
                             __syncwarp();
                         }
                         // slot k is free: the next piece is claimed when slot 0 frees up, its chunk k goes into slot k

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 oracle/_ref/test_cxx_binding 2>&1 | tail -15 | tee gpurun_out/cxx_binding.log
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -12 | tee gpurun_out/pytest_gpu.log
-for v in old lean1slot; do
+for v in old mode1 mode1_1slot mode2_1slot; do
   for w in c3 c5; do
     BMB200_LIB=$PWD/scripts/_bin/libbmb200_$v.so timeout 300 python bench.py --workload $w --steps 10 --no-e2e --no-cpu --no-parity 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$v $w', round(d['ms_per_step'],4), round(d['roofline']['frac'],4), d['result_bits'])"
   done
