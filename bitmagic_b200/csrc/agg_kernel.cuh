@@ -255,7 +255,7 @@ __device__ __forceinline__ void reds_and_if(uint32_t a, uint32_t v, uint32_t con
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.and.b32 [%0], %1;\n\t}"
                  :: "r"(a), "r"(v), "r"(cond) : "memory");
 }
-__device__ __noinline__ void flat_pair_tail(uint32_t Ls, uint32_t w)      // words after the first of a long run
+__device__ __forceinline__ void flat_pair_tail(uint32_t Ls, uint32_t w)   // words after the first of a long run
 {
     const uint32_t lo = w & 0xffffu, hi = w >> 16;
     if (lo >= hi) return;
@@ -266,9 +266,10 @@ __device__ __noinline__ void flat_pair_tail(uint32_t Ls, uint32_t w)      // wor
     for (; rem >= 32u; rem -= 32u, a += 4u) reds_and(a, 0u);
     if (rem) reds_and(a, 0xffffffffu << rem);
 }
-#ifndef BMB200_FLAT_MAX_MODE      /* highest FLAT sweep form a column may reach: 1 = test-first, 2 = + grouped branch for a nearly dead live mask */
-#define BMB200_FLAT_MAX_MODE 2
-#endif
+__device__ __noinline__ void flat_quad_tail(uint32_t Ls, const uint4 q)   // rare: some run of the quad continues past its first word
+{
+    flat_pair_tail(Ls, q.x); flat_pair_tail(Ls, q.y); flat_pair_tail(Ls, q.z); flat_pair_tail(Ls, q.w);
+}
 #ifndef BMB200_FLAT_LEAN          /* 1: lean pair decode -- hi - lo by one dp2a, word address by one and-or (L is 8 KB aligned) */
 #define BMB200_FLAT_LEAN 1
 #endif
@@ -282,9 +283,9 @@ __device__ __forceinline__ uint32_t and_or(uint32_t x, uint32_t msk, uint32_t ba
 {
     uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(x), "r"(msk), "r"(base)); return r;
 }
-// MODE 0: L is mostly alive -- every run goes straight to its (predicated) atomic.  MODE 1: test-first.  MODE 2: test-first for a
-// nearly dead L: the four hit tests of a quad are OR-ed and ONE branch guards the four conditional atomics, so a warp without a
-// single hit (the common case once < 0.4 % of L is alive) skips them in 8 instructions instead of 16.
+// MODE 0: L is mostly alive -- every run goes straight to its (predicated) atomic.  MODE 1: test-first.
+// (A third form that OR-ed the four hit tests of a quad behind ONE branch was measured and dropped: C5 5.27 ms vs 4.97 ms, the
+// extra divergence costs more than the skipped instructions.)
 template <int MODE>
 __device__ __forceinline__ void flat_quad(uint32_t Ls, const uint4& q)
 {
@@ -314,20 +315,34 @@ __device__ __forceinline__ void flat_quad(uint32_t Ls, const uint4& q)
         uint32_t v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) v[i] = lds32(a[i]) & m[i];
-        if (MODE == 2) {
-            if ((v[0] | v[1] | v[2] | v[3]) != 0u) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) reds_and_if(a[i], nm[i], v[i]);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) reds_and_if(a[i], nm[i], v[i]);
-        }
+        for (int i = 0; i < 4; ++i) reds_and_if(a[i], nm[i], v[i]);
     } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) reds_and_if(a[i], nm[i], m[i]);
     }
-    if (reach > 32u) { flat_pair_tail(Ls, q.x); flat_pair_tail(Ls, q.y); flat_pair_tail(Ls, q.z); flat_pair_tail(Ls, q.w); }
+    if (reach > 32u) flat_quad_tail(Ls, q);
+}
+
+// One slot of the FLAT window (bytes = what the bulk copy delivered, a multiple of 16; src = slot address + lane * 16): every lane eats
+// 4 runs per 128-bit load, 1 KB of the slot per step.  Deliberately ONE out-of-line copy per kernel: inlined into both slot
+// branches of the consumer (and unrolled) the sweep alone was ~50 KB of SASS, more than the instruction cache of an SM
+// sub-partition holds -- ncu showed `no_instruction` as the top stall of the GAP phase.
+template <int MODE>
+__device__ __forceinline__ void flat_sweep_mode(uint32_t Ls, uint32_t src, uint32_t bytes, uint32_t lane_off)
+{
+    uint32_t h = 0;
+#pragma unroll 1
+    for (; h + 1024u <= bytes; h += 1024u) {
+        const uint4 qa = lds128(src + h), qb = lds128(src + h + 512u);
+        flat_quad<MODE>(Ls, qa); flat_quad<MODE>(Ls, qb);
+    }
+    if (h + lane_off < bytes)        { const uint4 qa = lds128(src + h);        flat_quad<MODE>(Ls, qa); }     // last, partial KB of the window
+    if (h + 512u + lane_off < bytes) { const uint4 qb = lds128(src + h + 512u); flat_quad<MODE>(Ls, qb); }
+}
+__device__ __noinline__ void flat_sweep_fn(uint32_t Ls, uint32_t src, uint32_t bytes, uint32_t lane_off, uint32_t mode)
+{
+    if (mode) flat_sweep_mode<1>(Ls, src, bytes, lane_off); else flat_sweep_mode<0>(Ls, src, bytes, lane_off);
 }
 
 // GAP format (src/bmfunc.h:1696-1725): buf[0] = header (bit0 first-run value, len = hdr>>3),
@@ -631,7 +646,7 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
         if (tid < 4) s_stat[tid] = 0u;
         uint4 acc0 = kIsAnd ? make_uint4(~0u, ~0u, ~0u, ~0u) : make_uint4(0u, 0u, 0u, 0u);
         uint4 acc1 = make_uint4(0u, 0u, 0u, 0u);   // union of SUB-group bit-blocks
-        uint32_t flat_mode = 0;                    // FLAT consumer form of this column (warp-uniform, only ever rises): 0 atomics, 1 test-first, 2 test-first + grouped branch
+        uint32_t flat_mode = 0;                    // FLAT consumer form of this column (warp-uniform, one-way): 0 = atomics, 1 = test-first
 
         const uint32_t* drow = p.set.desc + (size_t)nb * M;
         const uint4* bseg = reinterpret_cast<const uint4*>(p.set.bit_pool)
@@ -834,23 +849,6 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                 }
                 gseq += nc;
             };
-            auto flat_sweep = [&](uint32_t src, uint32_t bytes, uint32_t mode) {   // one slot: 32 lanes x 16 B x 2 per step
-                if (bytes == kFlatChunk) {
-#pragma unroll
-                    for (uint32_t h = 0; h < kFlatChunk; h += 1024u) {
-                        const uint4 qa = lds128(src + h), qb = lds128(src + h + 512u);
-                        if (mode == 2u)      { flat_quad<2>(Ks, qa); flat_quad<2>(Ks, qb); }
-                        else if (mode == 1u) { flat_quad<1>(Ks, qa); flat_quad<1>(Ks, qb); }
-                        else                 { flat_quad<0>(Ks, qa); flat_quad<0>(Ks, qb); }
-                    }
-                } else {                                                            // last chunk of the window
-#pragma unroll 1
-                    for (uint32_t h = (uint32_t)lane * 16u; h < bytes; h += 512u) {
-                        const uint4 qa = lds128(src + h - (uint32_t)lane * 16u);
-                        if (mode) flat_quad<1>(Ks, qa); else flat_quad<0>(Ks, qa);
-                    }
-                }
-            };
             auto flat_consume = [&](int q) {                     // per warp, no cross-warp synchronisation at all
                 const uint32_t wlo = q ? lo1 : lo0, wbytes = q ? wb1 : wb0;
                 const uint32_t nfc = (wbytes + kFlatChunk - 1u) / kFlatChunk;
@@ -862,13 +860,12 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                         if (c < nfc) {
                             mbar_wait_a(wfull_s + 8u * k, (wphase >> k) & 1u); wphase ^= 1u << k;
                             const uint32_t bytes = min(kFlatChunk, wbytes - c * kFlatChunk);
-                            if (flat_mode < BMB200_FLAT_MAX_MODE && (flat_mode == 0u || (c & 7u) == 0u)) {   // (once test-first: every 8th chunk) 1024-bit sample of L: below 25 % alive the test-first form wins (one shared load, rarely
-                                                // an atomic), below 0.4 % its grouped-branch variant; bits of L only ever get cleared, so the switches are one-way
+                            if (flat_mode == 0u) {   // 1024-bit sample of L: below 25 % alive the test-first form wins (one shared load, rarely
+                                                // an atomic); bits of L only ever get cleared, so the switch is one-way per column
                                 const uint32_t smp = lds32(Ks + ((((uint32_t)lane * 65u + c * 7u) & (kBlockWords - 1u)) << 2));
-                                const uint32_t alive = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(smp));
-                                flat_mode = alive < 4u ? (uint32_t)BMB200_FLAT_MAX_MODE : alive < 256u ? max(flat_mode, 1u) : flat_mode;
+                                flat_mode = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(smp)) < 256u ? 1u : 0u;
                             }
-                            flat_sweep(ring_s + ((uint32_t)warp * kFlatSlots + k) * kFlatChunk + (uint32_t)lane * 16u, bytes, flat_mode);
+                            flat_sweep_fn(Ks, ring_s + ((uint32_t)warp * kFlatSlots + k) * kFlatChunk + (uint32_t)lane * 16u, bytes, (uint32_t)lane * 16u, flat_mode);
                             __syncwarp();
                         }
                         // slot k is free: the next piece is claimed when slot 0 frees up, its chunk k goes into slot k

@@ -67,7 +67,27 @@ for label, optimize in (("bit_blocks", False), ("optimized", True)):
         nz = rbc > 0
         res["parity"]["index_fields_equal"] = bool(np.array_equal(bc, rbc) and np.array_equal(sc[nz], rsc[nz]) and np.array_equal(sb, rsb) and rtot == total)
         res["speedup_vs_1thread"] = {"build": tb * 1e3 / build_ms, "rank": (NQ / rank_ms / 1e3) / (NQ / tr / 1e6), "select": (NQ / sel_ms / 1e3) / (NQ / ts / 1e6)}
+    # sector accounting: 32-byte sectors a query touches by construction of the index (sb_cum is a 2 KB table shared by all
+    # queries = cache-resident, not counted): rank = row_cum + descriptor + fine entry + <= 2 sectors of the block's 64-byte window;
+    # select = 2 (row pivots) + 2 (row entries) + descriptor + 1 (fine pivots) + 2 (fine entries) + 2 (window)
+    res["sectors_per_query_by_construction"] = {"rank": 5, "select": 10, "round1_anchor_scheme": {"rank": "~15 (3 index + ~11 of a <= 170-word scan)", "select": "~29"}}
     out[label] = res
     rs.free(); dset.free()
     print(label, json.dumps(res), flush=True)
-print(json.dumps({"workload": "c4: rs_index build + rank/select on one 2^32-bit vector, 1% density", "n_queries": NQ, "results": out}))
+# the random-access bound of this GPU: independent random 32-byte sector reads over a 512 MiB footprint (scripts/microbench_sector.cu)
+bound = None
+try:
+    import subprocess
+    exe = ROOT / "scripts" / "_bin" / "microbench_sector"
+    if exe.exists():
+        lines = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120).stdout.strip().splitlines()
+        bound = [json.loads(x) for x in lines]
+        gs = bound[0]["Gsectors_per_s"]
+        for label in out:
+            g = out[label]["gpu"]
+            out[label]["fraction_of_sector_bound"] = {"rank": g["rank_Mq_per_s"] / 1e3 * 5 / gs, "select": g["select_Mq_per_s"] / 1e3 * 10 / gs,
+                                                      "bound_Gsectors_per_s": gs}
+except Exception as e:       # the microbenchmark is optional evidence
+    bound = str(e)
+print(json.dumps({"workload": "c4: rs_index build + rank/select on one 2^32-bit vector, 1% density", "n_queries": NQ, "results": out,
+                  "random_sector_bound": bound}))

@@ -5,9 +5,7 @@ cd "$(dirname "$0")/.."
 mkdir -p scripts/_bin
 rm -f scripts/_bin/*.so
 build() { name=$1; shift; nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared "$@" -o scripts/_bin/libbmb200_$name.so bitmagic_b200/csrc/capi.cu -lcudart -ldl & }
-build old -DBMB200_FLAT_LEAN=0 -DBMB200_FLAT_MAX_MODE=1
-build mode1 -DBMB200_FLAT_MAX_MODE=1
-build mode1_1slot -DBMB200_FLAT_MAX_MODE=1 -DBMB200_FLAT_SLOTS=1
-build mode2_1slot -DBMB200_FLAT_SLOTS=1
+build oneslot -DBMB200_FLAT_SLOTS=1
+build unroll2 -DBMB200_BIT_UNROLL=2
 wait
 ls -la scripts/_bin/
