@@ -36,6 +36,7 @@
 //   * epilogue fuses popcount, 64-wave digest, run count and the result-kind decision.
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 namespace bmb200 {
 
@@ -91,12 +92,19 @@ __host__ inline size_t agg_dyn_smem(size_t static_bytes, size_t reserved_bytes)
 }
 // FLAT consumer: the ring is cut into one private slot per warp; warp w streams chunks w, w+16, ... of the window through
 // its own slot and its own mbarrier -- no cross-warp hand-off, the per-chunk overhead is paid once per slot, not 16 times
-#ifndef BMB200_FLAT_SLOTS         /* private slots per warp: 2 = one being consumed while the other one fills */
-#define BMB200_FLAT_SLOTS 2
+#ifndef BMB200_FLAT_SLOTS         /* private slots per warp: 2 = one being consumed while the other one fills, 1 = one 4 KB slot, 0 = by window size */
+#define BMB200_FLAT_SLOTS 0
 #endif
-constexpr uint32_t kFlatSlots     = BMB200_FLAT_SLOTS;
-constexpr uint32_t kFlatChunk     = kRingBytes / (kAggWarps * kFlatSlots);   // 2 KB with the 64 KB ring
-static_assert(kFlatChunk % 1024u == 0 && kFlatChunk >= 1024u, "a flat slot is a whole number of 32-lane x 16 B x 2 sweeps");
+constexpr uint32_t kFlatSlots     = 2u;                                      // barriers per warp (the most slots a warp's region is cut into)
+constexpr uint32_t kFlatWarpBytes = kRingBytes / kAggWarps;                  // 4 KB of the 64 KB ring per warp
+static_assert(kFlatWarpBytes % 2048u == 0, "a warp's ring region is cut into 1 or 2 slots of whole KB");
+// The region is used as TWO 2 KB slots (one fills while the other is consumed) or as ONE 4 KB slot, chosen per window: the per-slot
+// control code (claim, mbarrier wait, refill) is ~18 % of the GAP-phase instructions with 2 KB slots, so long windows (config 5: 2.7 MB
+// per column) take 4 KB pieces; short ones (config 3: ~0.4 MB per column = 6 pieces per warp) keep 2 KB pieces, whose finer claim
+// granularity balances the 16 warps better.  BMB200_FLAT_SLOTS = 1 / 2 forces one form, 0 = choose by window size.
+#ifndef BMB200_FLAT_BIG_WINDOW
+#define BMB200_FLAT_BIG_WINDOW (1u << 20)
+#endif
 
 struct AggParams {
     SetView   set;
@@ -340,7 +348,15 @@ __device__ __forceinline__ void flat_sweep_mode(uint32_t Ls, uint32_t src, uint3
     if (h + lane_off < bytes)        { const uint4 qa = lds128(src + h);        flat_quad<MODE>(Ls, qa); }     // last, partial KB of the window
     if (h + 512u + lane_off < bytes) { const uint4 qb = lds128(src + h + 512u); flat_quad<MODE>(Ls, qb); }
 }
-__device__ __noinline__ void flat_sweep_fn(uint32_t Ls, uint32_t src, uint32_t bytes, uint32_t lane_off, uint32_t mode)
+#ifndef BMB200_FLAT_OOL           /* 1: one out-of-line copy of the sweep per kernel; 0: inlined at every call site */
+#define BMB200_FLAT_OOL 1
+#endif
+#if BMB200_FLAT_OOL
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+void flat_sweep_fn(uint32_t Ls, uint32_t src, uint32_t bytes, uint32_t lane_off, uint32_t mode)
 {
     if (mode) flat_sweep_mode<1>(Ls, src, bytes, lane_off); else flat_sweep_mode<0>(Ls, src, bytes, lane_off);
 }
@@ -769,30 +785,39 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
             };
             // FLAT: warps claim pieces of the window from a shared counter (one claim = kFlatSlots consecutive chunks, one per
             // private slot) and pull them through their slots
-            auto flat_claim = [&]() -> uint32_t {                // whole warp; returns the first chunk of the claimed piece
+            auto flat_big = [&](uint32_t wbytes) -> bool {       // uniform: one 4 KB slot per warp instead of two 2 KB slots
+                return BMB200_FLAT_SLOTS == 1 ? true : BMB200_FLAT_SLOTS == 2 ? false : wbytes >= (uint32_t)BMB200_FLAT_BIG_WINDOW;
+            };
+            auto flat_claim = [&](auto S) -> uint32_t {          // whole warp; returns the first chunk of the claimed piece (S chunks)
                 uint32_t c = 0;
-                if (lane == 0) c = atoms_add(flat_next_s, 1u) * kFlatSlots;      // raw atom.shared: no warp-aggregation code around a one-lane atomic
+                if (lane == 0) c = atoms_add(flat_next_s, 1u) * decltype(S)::value;   // raw atom.shared: no warp-aggregation code around a one-lane atomic
                 return __shfl_sync(0xffffffffu, c, 0);
             };
-            auto flat_fill = [&](uint32_t wlo, uint32_t wbytes, uint32_t c, uint32_t k) {   // whole warp: chunk c -> slot k (caller checked c < nfc)
+            auto flat_fill = [&](auto S, uint32_t wlo, uint32_t wbytes, uint32_t c, uint32_t k) {   // whole warp: chunk c -> slot k (caller checked c < nfc)
+                constexpr uint32_t kChunk = kFlatWarpBytes / decltype(S)::value;
                 if (lane == 0) {
-                    const uint32_t off = c * kFlatChunk;
-                    const uint32_t bytes = min(kFlatChunk, wbytes - off);
+                    const uint32_t off = c * kChunk;
+                    const uint32_t bytes = min(kChunk, wbytes - off);
                     const uint32_t bar = wfull_s + 8u * k;
                     fence_proxy_async();
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 :: "r"(ring_s + ((uint32_t)warp * kFlatSlots + k) * kFlatChunk),
+                                 :: "r"(ring_s + (uint32_t)warp * kFlatWarpBytes + k * kChunk),
                                     "l"(reinterpret_cast<const uint8_t*>(gseg) + (size_t)wlo * 16u + off), "r"(bytes), "r"(bar) : "memory");
                 }
+            };
+            auto flat_setup = [&](auto S, uint32_t wlo, uint32_t wbytes) {
+                constexpr uint32_t kS = decltype(S)::value, kChunk = kFlatWarpBytes / kS;
+                const uint32_t nfc = (wbytes + kChunk - 1u) / kChunk;
+                const uint32_t c0 = flat_claim(S);
+#pragma unroll
+                for (uint32_t k = 0; k < kS; ++k) { wchunk[k] = c0 + k; if (c0 + k < nfc) flat_fill(S, wlo, wbytes, c0 + k, k); }
             };
             auto stream_setup = [&](int q, bool isflat) {               // all threads; ends with a block barrier
                 const uint32_t n = q ? ngap1 : ngap0, wlo = q ? lo1 : lo0, nc = q ? nc1 : nc0, wbytes = q ? wb1 : wb0;
                 if (isflat) {      // the ring is idle here (block barrier at the end of the previous pass / column)
-                    const uint32_t nfc = (wbytes + kFlatChunk - 1u) / kFlatChunk;
-                    const uint32_t c0 = flat_claim();
-#pragma unroll
-                    for (uint32_t k = 0; k < kFlatSlots; ++k) { wchunk[k] = c0 + k; if (c0 + k < nfc) flat_fill(wlo, wbytes, c0 + k, k); }
+                    if (flat_big(wbytes)) flat_setup(std::integral_constant<uint32_t, 1u>{}, wlo, wbytes);
+                    else                  flat_setup(std::integral_constant<uint32_t, 2u>{}, wlo, wbytes);
                     return;
                 }
                 {
@@ -849,31 +874,36 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                 }
                 gseq += nc;
             };
-            auto flat_consume = [&](int q) {                     // per warp, no cross-warp synchronisation at all
-                const uint32_t wlo = q ? lo1 : lo0, wbytes = q ? wb1 : wb0;
-                const uint32_t nfc = (wbytes + kFlatChunk - 1u) / kFlatChunk;
+            auto flat_consume_s = [&](auto S, uint32_t wlo, uint32_t wbytes) {   // per warp, no cross-warp synchronisation at all
+                constexpr uint32_t kS = decltype(S)::value, kChunk = kFlatWarpBytes / kS;
+                const uint32_t nfc = (wbytes + kChunk - 1u) / kChunk;
                 for (;;) {
                     if (wchunk[0] >= nfc) break;                 // chunks of a piece are consecutive: slot 0 empty = nothing left
 #pragma unroll
-                    for (uint32_t k = 0; k < kFlatSlots; ++k) {
+                    for (uint32_t k = 0; k < kS; ++k) {
                         const uint32_t c = wchunk[k];
                         if (c < nfc) {
                             mbar_wait_a(wfull_s + 8u * k, (wphase >> k) & 1u); wphase ^= 1u << k;
-                            const uint32_t bytes = min(kFlatChunk, wbytes - c * kFlatChunk);
+                            const uint32_t bytes = min(kChunk, wbytes - c * kChunk);
                             if (flat_mode == 0u) {   // 1024-bit sample of L: below 25 % alive the test-first form wins (one shared load, rarely
                                                 // an atomic); bits of L only ever get cleared, so the switch is one-way per column
                                 const uint32_t smp = lds32(Ks + ((((uint32_t)lane * 65u + c * 7u) & (kBlockWords - 1u)) << 2));
                                 flat_mode = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(smp)) < 256u ? 1u : 0u;
                             }
-                            flat_sweep_fn(Ks, ring_s + ((uint32_t)warp * kFlatSlots + k) * kFlatChunk + (uint32_t)lane * 16u, bytes, (uint32_t)lane * 16u, flat_mode);
+                            flat_sweep_fn(Ks, ring_s + (uint32_t)warp * kFlatWarpBytes + k * kChunk + (uint32_t)lane * 16u, bytes, (uint32_t)lane * 16u, flat_mode);
                             __syncwarp();
                         }
                         // slot k is free: the next piece is claimed when slot 0 frees up, its chunk k goes into slot k
-                        const uint32_t cn = (k == 0) ? flat_claim() : wchunk[0] + k;
+                        const uint32_t cn = (k == 0) ? flat_claim(S) : wchunk[0] + k;
                         wchunk[k] = cn;
-                        if (cn < nfc) flat_fill(wlo, wbytes, cn, k);
+                        if (cn < nfc) flat_fill(S, wlo, wbytes, cn, k);
                     }
                 }
+            };
+            auto flat_consume = [&](int q) {
+                const uint32_t wlo = q ? lo1 : lo0, wbytes = q ? wb1 : wb0;
+                if (flat_big(wbytes)) flat_consume_s(std::integral_constant<uint32_t, 1u>{}, wlo, wbytes);
+                else                  flat_consume_s(std::integral_constant<uint32_t, 2u>{}, wlo, wbytes);
             };
             auto gather_pass = [&](int q, uint32_t want) {       // per warp; dynamic block distribution
                 const uint32_t n = q ? ngap1 : ngap0;

@@ -131,7 +131,11 @@ __global__ void __launch_bounds__(256) rs_block_kernel(const SetView set, uint32
                                                        uint64_t* __restrict__ sub_count,
                                                        uint32_t* __restrict__ fine, uint32_t* __restrict__ fine_piv)
 {
-    __shared__ uint32_t s_ones[8][kRsWin], s_ends[8][kRsWin];
+    // GAP blocks: the whole block is staged in shared memory with 128-bit loads (it is at most 2.5 KB), a prefix of the ones per run is
+    // built next to it, and everything the index needs -- the two rs3 borders and the 128 fine windows -- is then ONE binary search
+    // each over the staged run ends (130 searches per block, 4-5 per lane) instead of per-run work with shared atomics
+    __shared__ __align__(16) uint16_t s_raw[8][1296];
+    __shared__ uint16_t s_pfx[8][1288];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
     for (uint32_t nb = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); nb < set.n_blocks; nb += warps_total) {
@@ -140,51 +144,56 @@ __global__ void __launch_bounds__(256) rs_block_kernel(const SetView set, uint32
         uint32_t tot = 0, le0 = 0, le1 = 0, a0 = 0, a1 = 0;
         uint32_t* fout = fine + (size_t)nb * kRsWin;
         if (kd == BMB200_BLK_GAP) {
-            const uint16_t* g = set.gap_pool + (set.gap_base[nb] + (rel & BMB200_DESC_REL_MASK)) * (size_t)kGapUnit + (rel >> 29);
-            const uint32_t hdr = g[0], len = hdr >> 3, first = hdr & 1u;
-            uint32_t lt0 = 0, lt1 = 0;   // run ends < border+1  (for gap_bfind)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { s_ones[wib][4 * lane + q] = 0u; s_ends[wib][4 * lane + q] = 0u; }
+            const uint16_t* unit = set.gap_pool + (set.gap_base[nb] + (rel & BMB200_DESC_REL_MASK)) * (size_t)kGapUnit;
+            const uint32_t pad = rel >> 29;
+            const uint32_t hdr = unit[pad], len = hdr >> 3, first = hdr & 1u;
             __syncwarp();
-            for (uint32_t k = 1 + lane; k <= len; k += 32) {
-                const uint32_t e = g[k];
-                const uint32_t s = (k == 1) ? 0u : (uint32_t)g[k - 1] + 1u;
-                lt0 += (e < kRs3B0 + 1u); lt1 += (e < kRs3B1 + 1u);
-                atomicAdd(&s_ends[wib][e >> 9], 1u);
-                if (first ^ ((k - 1u) & 1u)) {
-                    tot += e - s + 1u;
-                    if (s <= kRs3B0) le0 += min(e, kRs3B0) - s + 1u;
-                    if (s <= kRs3B1) le1 += min(e, kRs3B1) - s + 1u;
-                    for (uint32_t w = s >> 9; w <= (e >> 9); ++w)       // ones of this run inside every window it touches
-                        atomicAdd(&s_ones[wib][w], min(e, (w << 9) + 511u) - max(s, w << 9) + 1u);
-                }
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(unit);
+                const uint32_t nvec = (len + 1u + pad + 7u) >> 3;
+                for (uint32_t v = lane; v < nvec; v += 32u) reinterpret_cast<uint4*>(s_raw[wib])[v] = ld_stream_v4(src + v);
             }
             __syncwarp();
-            {   // exclusive scans over the 128 windows: lane owns windows 4*lane .. 4*lane+3
-                uint32_t o[4], n[4], so = 0, sn = 0;
+            const uint16_t* E = s_raw[wib] + pad;            // E[0] = header, E[1 .. len] = run ends
+            uint16_t* P = s_pfx[wib];                        // P[k] = ones in runs 1 .. k (fits 16 bits for every k < len)
+            uint32_t carry = 0;
+            for (uint32_t base = 1u; base <= len; base += 256u) {        // 8 consecutive runs per lane and trip
+                const uint32_t k0 = base + 8u * (uint32_t)lane;
+                uint32_t prev = (k0 == 1u || k0 > len) ? 0xffffffffu : (uint32_t)E[k0 - 1u];      // run 1 starts at bit 0
+                uint32_t loc[8], sum = 0;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { o[q] = s_ones[wib][4 * lane + q]; n[q] = s_ends[wib][4 * lane + q]; so += o[q]; sn += n[q]; }
-                uint32_t io = so, in_ = sn;
-#pragma unroll
-                for (int sft = 1; sft < 32; sft <<= 1) {
-                    const uint32_t yo = __shfl_up_sync(0xffffffffu, io, sft), yn = __shfl_up_sync(0xffffffffu, in_, sft);
-                    if (lane >= sft) { io += yo; in_ += yn; }
+                for (uint32_t q = 0; q < 8u; ++q) {
+                    const uint32_t k = k0 + q;
+                    if (k <= len) { const uint32_t e = E[k]; if (first ^ ((k - 1u) & 1u)) sum += e - prev; prev = e; }
+                    loc[q] = sum;
                 }
-                uint32_t co = io - so, cn = in_ - sn;
+                uint32_t x = sum;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t ent = co | ((cn + 1u) << 16);                 // run index = (ends before the window) + 1
-                    fout[4 * lane + q] = ent;
-                    if (((4 * lane + q) & 15) == 0) fine_piv[(size_t)nb * kRsPiv + ((4 * lane + q) >> 4)] = co;
-                    co += o[q]; cn += n[q];
-                }
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+                const uint32_t before = carry + x - sum;
+#pragma unroll
+                for (uint32_t q = 0; q < 8u; ++q) if (k0 + q <= len) P[k0 + q] = (uint16_t)(before + loc[q]);
+                carry += __shfl_sync(0xffffffffu, x, 31);
             }
+            if (lane == 0) P[0] = 0;
+            tot = carry;
             __syncwarp();
-            tot = warp_sum(tot); le0 = warp_sum(le0); le1 = warp_sum(le1);
-            lt0 = warp_sum(lt0); lt1 = warp_sum(lt1);
-            const uint32_t i0 = lt0 + 1u, i1 = lt1 + 1u;          // gap_bfind src/bmfunc.h:1844
-            a0 = (i0 << 1) | (first ^ ((i0 - 1u) & 1u));
-            a1 = (i1 << 1) | (first ^ ((i1 - 1u) & 1u));
+            // 130 searches: the 128 window starts 512 t, then the two rs3 borders (positions B0 + 1 and B1 + 1)
+            for (uint32_t t = lane; t < kRsWin + 2u; t += 32u) {
+                const uint32_t b = t < kRsWin ? (t << 9) : (t == kRsWin ? kRs3B0 + 1u : kRs3B1 + 1u);
+                uint32_t lo = 1u, hi = len;                              // first run j with E[j] >= b: the run that holds bit b (gap_bfind, src/bmfunc.h:1844)
+                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((uint32_t)E[mid] < b) lo = mid + 1u; else hi = mid; }
+                const uint32_t j = lo, sj = (j == 1u) ? 0u : (uint32_t)E[j - 1u] + 1u, val = first ^ ((j - 1u) & 1u);
+                const uint32_t ob = (uint32_t)P[j - 1u] + ((val && b > sj) ? b - sj : 0u);      // ones in [0, b)
+                if (t < kRsWin) {
+                    fout[t] = ob | (j << 16);
+                    if ((t & 15u) == 0u) fine_piv[(size_t)nb * kRsPiv + (t >> 4)] = ob;
+                } else if (t == kRsWin) { le0 = ob; a0 = (j << 1) | val; }
+                else { le1 = ob; a1 = (j << 1) | val; }
+            }
+            // t = 128 ran on lane 0, t = 129 on lane 1
+            le1 = __shfl_sync(0xffffffffu, le1, 1); a1 = __shfl_sync(0xffffffffu, a1, 1);
+            __syncwarp();
         } else if (kd != BMB200_BLK_NULL) {
             if (kd == BMB200_BLK_BIT) {
                 // 16 coalesced 512-byte warp loads per block, all issued before the popcounts (8 KB in flight per warp)

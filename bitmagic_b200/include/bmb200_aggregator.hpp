@@ -81,7 +81,9 @@ uint32_t blocks_of(const BV& bv)
     return (uint32_t)((uint64_t(sz) + 65535ull) >> 16);
 }
 
-/// store a fetched result (per-column flat form) into a cleared target through the public block manager
+/// store a fetched result (per-column flat form) into a cleared target through the public block manager.  Large results are stored by
+/// a few host threads, each owning whole top-level sub-trees (disjoint i): the block manager's per-(i,j) calls touch nothing shared
+/// once the top array is reserved and no allocator pool is attached (every block comes straight from the block allocator).
 template<class BV>
 void store_result(BV& target, typename BV::size_type new_size, uint32_t n_cols,
                   const uint8_t* kind, const uint64_t* off, const uint32_t* bits, const uint16_t* gaps, uint32_t nb_off = 0)
@@ -90,32 +92,49 @@ void store_result(BV& target, typename BV::size_type new_size, uint32_t n_cols,
     target.resize(new_size);
     target.init();
     typename BV::blocks_manager_type& bman = target.get_blocks_manager();
-    BM_DECLARE_TEMP_BLOCK(tb)
-    for (uint32_t c = 0; c < n_cols; ++c)
+    if (!n_cols) return;
+    const unsigned i_lo = nb_off >> bm::set_array_shift, i_hi = (nb_off + n_cols - 1u) >> bm::set_array_shift;
+    bman.reserve_top_blocks(i_hi + 1);
+    auto store_top = [&](unsigned i, bm::word_t* tb)
     {
-        if (kind[c] == BMB200_BLK_NULL) continue;
-        unsigned i = (c + nb_off) >> bm::set_array_shift, j = (c + nb_off) & bm::set_array_mask;
-        bman.reserve_top_blocks(i + 1);
+        const uint32_t nb0 = std::max<uint32_t>(i << bm::set_array_shift, nb_off), nb1 = std::min<uint32_t>((i + 1u) << bm::set_array_shift, nb_off + n_cols);
+        bool any = false;
+        for (uint32_t nb = nb0; nb < nb1; ++nb) if (kind[nb - nb_off] != BMB200_BLK_NULL) { any = true; break; }
+        if (!any) return;
         bman.check_alloc_top_subblock(i);
-        if (kind[c] == BMB200_BLK_FULL)
+        for (uint32_t nb = nb0; nb < nb1; ++nb)
         {
-            bman.set_block_ptr(i, j, FULL_BLOCK_FAKE_ADDR);
-            if (j == bm::set_sub_array_size - 1) bman.validate_top_full(i);
+            const uint32_t c = nb - nb_off; const unsigned j = nb & bm::set_array_mask;
+            if (kind[c] == BMB200_BLK_NULL) continue;
+            if (kind[c] == BMB200_BLK_FULL)
+            {
+                bman.set_block_ptr(i, j, FULL_BLOCK_FAKE_ADDR);
+                if (j == bm::set_sub_array_size - 1) bman.validate_top_full(i);
+            }
+            else if (kind[c] == BMB200_BLK_BIT)
+            {
+                std::memcpy(tb, bits + off[c] * (size_t)BMB200_BLOCK_WORDS, BMB200_BLOCK_BYTES);   // SIMD-aligned staging for bit_block_stream
+                bman.copy_bit_block(i, j, tb);
+            }
+            else
+            {
+                const bm::gap_word_t* g = gaps + off[c];
+                unsigned len = bm::gap_length(g) - 1;
+                int level = bm::gap_calc_level(len, bman.glen());
+                bm::gap_word_t* gb = bman.allocate_gap_block(unsigned(level), g);
+                bman.set_block_ptr(i, j, (bm::word_t*)BMPTR_SETBIT0(gb));
+            }
         }
-        else if (kind[c] == BMB200_BLK_BIT)
-        {
-            std::memcpy(tb.begin(), bits + off[c] * (size_t)BMB200_BLOCK_WORDS, BMB200_BLOCK_BYTES);
-            bman.copy_bit_block(i, j, tb.begin());
-        }
-        else
-        {
-            const bm::gap_word_t* g = gaps + off[c];
-            unsigned len = bm::gap_length(g) - 1;
-            int level = bm::gap_calc_level(len, bman.glen());
-            bm::gap_word_t* gb = bman.allocate_gap_block(unsigned(level), g);
-            bman.set_block_ptr(i, j, (bm::word_t*)BMPTR_SETBIT0(gb));
-        }
-    }
+    };
+    unsigned T = 1;
+    if (n_cols >= 2048u && !bman.get_allocator().get_pool())
+    { T = std::thread::hardware_concurrency(); if (!T) T = 1; if (T > 8) T = 8; if (T > i_hi - i_lo + 1u) T = i_hi - i_lo + 1u; }
+    auto work = [&](unsigned t) { BM_DECLARE_TEMP_BLOCK(tb) for (unsigned i = i_lo + t; i <= i_hi; i += T) store_top(i, tb.begin()); };
+    if (T <= 1) { work(0); return; }
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
 }
 
 /// walk the block trees of n vectors with a team of host threads (one vector at a time per thread); blocks [nb_from, nb_from + n_blocks)

@@ -163,10 +163,13 @@ int e2e_cold_split(void* hv, int op, int compress, const uint32_t* g0, uint32_t 
         std::vector<const bvect*> all(g.g0); all.insert(all.end(), g.g1.begin(), g.g1.end());
         bm::b200::device_set<bvect> ds(*h->ctx);
         bm::b200::aggregator<bvect> agg(*h->ctx);
+        ds.assign(all.data(), all.size());                 // warm-up: pinned ring, parked arena and the aggregator's result buffers exist afterwards,
+        agg.set_device_set(&ds);                           //   exactly the state the timed cold steps of e2e_cold run in
+        call(agg, op, compress != 0, h->last, g);
+        ds.release();
         double t0 = now_ms();
         ds.assign(all.data(), all.size());
         double t1 = now_ms();
-        agg.set_device_set(&ds);
         call(agg, op, compress != 0, h->last, g);
         double t2 = now_ms();
         *assign_ms = t1 - t0; *agg_ms = t2 - t1;

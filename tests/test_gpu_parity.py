@@ -907,7 +907,7 @@ def test_e2e_harness_real_bvectors_cold_warm_and_check(ctx):
     if not so.exists():
         pytest.skip("oracle/_ref/libbmb200_e2e.so not built (needs /root/reference at build time)")
     lib = Ct.CDLL(str(so)); lib.e2e_create_empty.restype = Ct.c_void_p; lib.e2e_free.restype = None
-    nv, nbk = 96, 600                                    # spans 3 top-level blocks
+    nv, nbk = 96, 2304                                   # 9 top-level blocks: the result store runs on several host threads (>= 2048 columns)
     dens = np.array([0.5 / (k + 1) for k in range(nv)]); seed = np.arange(1000, 1000 + nv, dtype=np.uint64)
     dset = bm.DeviceSet.synth(ctx, nv, nbk, dens, seed, True)
     node = Ct.c_int(-1)
