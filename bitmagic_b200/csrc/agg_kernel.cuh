@@ -42,7 +42,11 @@ namespace bmb200 {
 
 constexpr int kAggThreads = 512;
 constexpr int kAggWarps   = kAggThreads / 32;
-constexpr int kAggChunk   = 1024;   // group members classified per pass
+constexpr int kAggChunk   = 1024;   // group members classified per pass (AND-SUB)
+#ifndef BMB200_AGG_CHUNK_WIDE
+#define BMB200_AGG_CHUNK_WIDE 1408
+#endif
+constexpr int kAggChunkWide = BMB200_AGG_CHUNK_WIDE;  // ... in the one-group kernels (OR / AND / XOR)
 
 // build-time variants (scripts/build_variants.sh explores them; defaults = best measured)
 #ifndef BMB200_CTAS_PER_SM       /* resident CTAs per SM the kernel is shaped for: 2 (64 regs, 4-stage ring) or 3 (40 regs, 3-stage ring) */
@@ -103,7 +107,7 @@ static_assert(kFlatWarpBytes % 2048u == 0, "a warp's ring region is cut into 1 o
 // per column) take 4 KB pieces; short ones (config 3: ~0.4 MB per column = 6 pieces per warp) keep 2 KB pieces, whose finer claim
 // granularity balances the 16 warps better.  BMB200_FLAT_SLOTS = 1 / 2 forces one form, 0 = choose by window size.
 #ifndef BMB200_FLAT_BIG_WINDOW
-#define BMB200_FLAT_BIG_WINDOW (1u << 20)
+#define BMB200_FLAT_BIG_WINDOW (640u << 10)   /* >= 10 pieces of 4 KB for each of the 16 warps */
 #endif
 
 struct AggParams {
@@ -579,6 +583,11 @@ __device__ __forceinline__ void finish_block(const AggParams& p, uint32_t col, u
 template <int OP>
 __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggParams p)
 {
+    // members classified per pass: the AND-SUB kernel keeps three lists (static smem must stay below the 16 KB boundary the live mask
+    // sits on), the one-group kernels use the room for longer lists -- a 4096-member OR (config 5) takes 3 passes instead of 4, and
+    // every pass costs a classification, a window check over the descriptor row and two block barriers
+    constexpr int kChunkN = (OP == BMB200_OP_AND_SUB) ? kAggChunk : kAggChunkWide;
+    constexpr int kMaxChunksN = (kChunkN * 4096) / (int)kGapChunkBytes + 4;      // streamed only when span <= n * 4096
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     // the live mask L (see the header comment) sits at the first 8 KB boundary of the shared window inside the dynamic region, the ring behind it
     const uint32_t dyn_s = smem_u32(dyn_smem);
@@ -587,10 +596,10 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
     uint32_t* K = reinterpret_cast<uint32_t*>(dyn_smem + k_off);
     uint32_t* ring = reinterpret_cast<uint32_t*>(dyn_smem + k_off + kLiveAlign);
 
-    __shared__ uint32_t lst_bit0[kAggChunk];
-    __shared__ uint32_t lst_bit1[kAggChunk];
-    __shared__ uint32_t lst_gap[kAggChunk];      // group0 GAPs from the front, group1 GAPs from the back (both in member order)
-    __shared__ uint32_t s_cfirst[kMaxChunks];    // first list entry starting in each ring chunk
+    __shared__ uint32_t lst_bit0[kChunkN];
+    __shared__ uint32_t lst_bit1[kChunkN];
+    __shared__ uint32_t lst_gap[kChunkN];      // group0 GAPs from the front, group1 GAPs from the back (both in member order)
+    __shared__ uint32_t s_cfirst[kMaxChunksN];    // first list entry starting in each ring chunk
     __shared__ __align__(8) uint64_t s_full[kGapStages];
     __shared__ uint32_t s_done[kGapStages];
     __shared__ __align__(8) uint64_t s_wfull[kAggWarps * kFlatSlots];   // FLAT consumer: one "slot filled" barrier per private slot
@@ -672,16 +681,16 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
         const uint64_t gseg_avail = p.gap_pool_bytes - gseg_unit * 16ull;   // readable bytes from gseg on
         if (ntot == 0) __syncthreads();
 
-        for (uint32_t cs = 0; cs < ntot; cs += kAggChunk) {
+        for (uint32_t cs = 0; cs < ntot; cs += kChunkN) {
             if (tid == 0) { s_gap_next = 0u; s_flat_next = 0u; s_flat[0] = 0u; s_flat[1] = 0xffffffffu; s_flat[2] = 0u; }
             // ---- classification (sort_input_blocks_*): order-preserving compaction into 4 lists ----
             // per trip: 4 ballots, one packed count pair per warp, ONE block barrier, then every warp scans the 16 warp
             // counts with shuffles; the running list lengths stay in (uniform) registers
-            const uint32_t ce = min(cs + (uint32_t)kAggChunk, ntot);
+            const uint32_t ce = min(cs + (uint32_t)kChunkN, ntot);
             uint32_t fl = 0, nfull0 = 0, nonflat = 0;
             uint32_t run01 = 0, run23 = 0;                       // nbit0 | nbit1 << 16, ngap0 | ngap1 << 16 so far
             int trip = 0;
-            for (uint32_t kb = cs; kb < ce; kb += kAggThreads, trip ^= 1) {   // uniform trip count (<= 2)
+            for (uint32_t kb = cs; kb < ce; kb += kAggThreads, trip ^= 1) {   // uniform trip count (<= 3)
                 const uint32_t k = kb + tid;
                 uint32_t kind = 0xffu, rel = 0; bool g1 = false;
                 if (k < ce) {
@@ -711,7 +720,7 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                 if (c0) lst_bit0[(e01 & 0xffffu) + __popc(m0 & lt)] = rel;
                 if (c1) lst_bit1[(e01 >> 16) + __popc(m1 & lt)] = rel;
                 if (c2) lst_gap[(e23 & 0xffffu) + __popc(m2 & lt)] = rel;
-                if (c3) lst_gap[kAggChunk - 1 - ((e23 >> 16) + __popc(m3 & lt))] = rel;
+                if (c3) lst_gap[kChunkN - 1 - ((e23 >> 16) + __popc(m3 & lt))] = rel;
                 run01 += t01; run23 += t23;
             }
             fl = __reduce_or_sync(0xffffffffu, fl);
@@ -732,7 +741,7 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                 int bad0 = 0, bad1 = 0;
                 for (uint32_t i = tid; i + 1 < ngap0; i += kAggThreads) bad0 |= !((lst_gap[i] & kRelMask) < (lst_gap[i + 1] & kRelMask));
                 for (uint32_t i = tid; i + 1 < ngap1; i += kAggThreads)
-                    bad1 |= !((lst_gap[kAggChunk - 1 - i] & kRelMask) < (lst_gap[kAggChunk - 2 - i] & kRelMask));
+                    bad1 |= !((lst_gap[kChunkN - 1 - i] & kRelMask) < (lst_gap[kChunkN - 2 - i] & kRelMask));
                 // NB: __syncthreads_or returns a predicate, not a bitwise OR -> one vote per list
                 const bool sorted0 = !__syncthreads_or(bad0), sorted1 = !__syncthreads_or(bad1);
                 // FLAT window: the units [lo, end) hold exactly the list's GAP blocks, all in FLAT form
@@ -740,8 +749,8 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                     const uint32_t nq = kFlatList ? ngap1 : ngap0;
                     const bool sortedq = kFlatList ? sorted1 : sorted0;
                     if (nq >= kFlatMinBlocks && sortedq && !s_flat[2] && M <= 8u * nq + 1024u) {   // uniform
-                        const uint32_t lo = (kFlatList ? lst_gap[kAggChunk - 1] : lst_gap[0]) & kRelMask;
-                        const uint32_t hi = (kFlatList ? lst_gap[kAggChunk - nq] : lst_gap[nq - 1]) & kRelMask;
+                        const uint32_t lo = (kFlatList ? lst_gap[kChunkN - 1] : lst_gap[0]) & kRelMask;
+                        const uint32_t hi = (kFlatList ? lst_gap[kChunkN - nq] : lst_gap[nq - 1]) & kRelMask;
                         uint32_t c = 0, e = (uint32_t)(p.set.gap_base[nb + 1] - gseg_unit);
                         for (uint32_t v = tid; v < M; v += kAggThreads) {
                             const uint32_t d = drow[v];
@@ -771,7 +780,7 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                     ok = true; wlo = lo; wb = (uint32_t)w; nc = (uint32_t)((w + kGapChunkBytes - 1) / kGapChunkBytes);
                 };
                 if (ngap0 && !(flat && kFlatList == 0)) plan(ngap0, sorted0, lst_gap[0] & kRelMask, lst_gap[ngap0 - 1] & kRelMask, ok0, lo0, wb0, nc0);
-                if (ngap1 && !(flat && kFlatList == 1)) plan(ngap1, sorted1, lst_gap[kAggChunk - 1] & kRelMask, lst_gap[kAggChunk - ngap1] & kRelMask, ok1, lo1, wb1, nc1);
+                if (ngap1 && !(flat && kFlatList == 1)) plan(ngap1, sorted1, lst_gap[kChunkN - 1] & kRelMask, lst_gap[kChunkN - ngap1] & kRelMask, ok1, lo1, wb1, nc1);
             }
             auto issue_fill = [&](uint32_t wlo, uint32_t wbytes, uint32_t c, bool mirror) {   // one thread: arm the stage of chunk c, start the copy
                 const uint32_t s = (gseq + c) % kGapStages;
@@ -822,10 +831,10 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                 }
                 {
                     for (uint32_t i = tid; i < n; i += kAggThreads) {
-                        const uint32_t ei = (q ? lst_gap[kAggChunk - 1 - i] : lst_gap[i]) & kRelMask;
+                        const uint32_t ei = (q ? lst_gap[kChunkN - 1 - i] : lst_gap[i]) & kRelMask;
                         const uint32_t ci = ((ei - wlo) * 16u) / kGapChunkBytes;
                         int cp = -1;
-                        if (i) { const uint32_t ep = (q ? lst_gap[kAggChunk - i] : lst_gap[i - 1]) & kRelMask; cp = (int)(((ep - wlo) * 16u) / kGapChunkBytes); }
+                        if (i) { const uint32_t ep = (q ? lst_gap[kChunkN - i] : lst_gap[i - 1]) & kRelMask; cp = (int)(((ep - wlo) * 16u) / kGapChunkBytes); }
                         for (int c = cp + 1; c <= (int)ci; ++c) s_cfirst[c] = i;
                         if (i == n - 1) for (uint32_t c = ci + 1; c <= nc; ++c) s_cfirst[c] = n;
                     }
@@ -865,7 +874,7 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                         const int sub = lane & (int)(kLanesPerBlock - 1u);
                         const uint32_t ibeg = s_cfirst[r], iend = s_cfirst[r + 1];
                         for (uint32_t i = ibeg + ((slot - ibeg) & (kSlots - 1u)); i < iend; i += kSlots) {
-                            const uint32_t ent = q ? lst_gap[kAggChunk - 1 - i] : lst_gap[i];
+                            const uint32_t ent = q ? lst_gap[kChunkN - 1 - i] : lst_gap[i];
                             const uint32_t ba = ring_s + (rot + ((ent & kRelMask) - wlo) * 16u) % kRingBytes;
                             gap_scatter_ring<kIsXor>(Ks, ba, ent >> 29, want, sub);
                         }
@@ -912,7 +921,7 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                     if (lane == 0) g = atomicAdd(&s_gap_next, 1u);
                     g = __shfl_sync(0xffffffffu, g, 0);
                     if (g >= n) break;
-                    const uint32_t ent = q ? lst_gap[kAggChunk - 1 - g] : lst_gap[g];
+                    const uint32_t ent = q ? lst_gap[kChunkN - 1 - g] : lst_gap[g];
                     gap_scatter_gather<kIsXor>(Ks, gseg + (size_t)(ent & kRelMask) * kGapUnit + (ent >> 29), want, lane);
                 }
             };
@@ -941,7 +950,7 @@ __global__ void __launch_bounds__(kAggThreads, kCtasPerSm) agg_kernel(const AggP
                 // clears at most a suffix of (0 .. buf[1]); clear the whole run here
                 const uint32_t n = kFlatList ? ngap1 : ngap0;
                 for (uint32_t i = tid; i < n; i += kAggThreads) {
-                    const uint32_t ent = kFlatList ? lst_gap[kAggChunk - 1 - i] : lst_gap[i];
+                    const uint32_t ent = kFlatList ? lst_gap[kChunkN - 1 - i] : lst_gap[i];
                     if (!(ent >> 29)) apply_run<false>(Ks, 0u, gseg[(size_t)(ent & kRelMask) * kGapUnit + 1u]);
                 }
                 flat_consume(kFlatList);

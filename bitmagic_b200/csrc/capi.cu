@@ -464,7 +464,7 @@ int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks
             PackPipeline pipe(n_vec, n_blocks, vecs, &L, &chunks, ctx->h_ring);
             pipe.start((unsigned)ctx->host_threads);
             const uint32_t nch = (uint32_t)chunks.size();
-            double t_pack = 0, t_dma = 0;
+            double t_pack = 0, t_dma = 0, t_issue = 0;
             auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
             for (uint32_t c = 0; c < nch && e == cudaSuccess; ++c) {
                 const double w0 = tr.on ? now() : 0;
@@ -472,16 +472,18 @@ int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks
                 if (tr.on) t_pack += now() - w0;
                 const PackChunk& ch = chunks[c];
                 uint8_t* base = ctx->h_ring[c % kStageSlots];
+                const double w2 = tr.on ? now() : 0;
                 if (ch.bit_bytes) e = cudaMemcpyAsync((uint8_t*)s->v.bit_pool + L.bb[ch.c0] * (uint64_t)BMB200_BLOCK_BYTES, base, ch.bit_bytes, cudaMemcpyHostToDevice, st);
                 if (e == cudaSuccess && ch.gap_bytes) e = cudaMemcpyAsync((uint8_t*)s->v.gap_pool + L.gb[ch.c0] * 16ull, base + ch.bit_bytes, ch.gap_bytes, cudaMemcpyHostToDevice, st);
                 if (e == cudaSuccess) e = cudaEventRecord(ctx->ring_ev[c % kStageSlots], st);
+                if (tr.on) t_issue += now() - w2;
                 // the copy of chunk c is queued behind the one of chunk c-1: once c-1 has landed its slot goes back to the packers
                 if (e == cudaSuccess && c >= 1) { const double w1 = tr.on ? now() : 0; e = cudaEventSynchronize(ctx->ring_ev[(c - 1) % kStageSlots]);
                                                   if (tr.on) t_dma += now() - w1; pipe.release_through(c); }
             }
             pipe.join();
-            if (tr.on) fprintf(stderr, "[bmb200] set_upload_vectors: %u chunks of <= %.0f MB, issuing thread waited %.1f ms for the packers and %.1f ms for the DMA\n",
-                               nch, slot_bytes / 1048576.0, t_pack, t_dma);
+            if (tr.on) fprintf(stderr, "[bmb200] set_upload_vectors: %u chunks of <= %.0f MB, issuing thread waited %.1f ms for the packers and %.1f ms for the DMA, spent %.1f ms inside cudaMemcpyAsync / cudaEventRecord\n",
+                               nch, slot_bytes / 1048576.0, t_pack, t_dma, t_issue);
         } catch (...) { return fail(BMB200_ERR_BADALLOC, cudaSuccess); }
         if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
     }

@@ -5,10 +5,7 @@ cd "$(dirname "$0")/.."
 mkdir -p scripts/_bin
 rm -f scripts/_bin/*.so
 build() { name=$1; shift; nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared "$@" -o scripts/_bin/libbmb200_$name.so bitmagic_b200/csrc/capi.cu -lcudart -ldl & }
-build inl_adapt -DBMB200_FLAT_OOL=0
-build inl_2slot -DBMB200_FLAT_OOL=0 -DBMB200_FLAT_SLOTS=2
-build inl_1slot -DBMB200_FLAT_OOL=0 -DBMB200_FLAT_SLOTS=1
-build ool_1slot -DBMB200_FLAT_SLOTS=1
-build ool_2slot -DBMB200_FLAT_SLOTS=2
+build narrow -DBMB200_AGG_CHUNK_WIDE=1024
+build narrow_2slot -DBMB200_AGG_CHUNK_WIDE=1024 -DBMB200_FLAT_SLOTS=2
 wait
 ls -la scripts/_bin/

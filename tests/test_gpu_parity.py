@@ -987,3 +987,20 @@ def test_binop_result_kinds_vs_reference(ctx):
                 assert np.array_equal(pop, rpop) and int(pop.sum()) == rcnt
                 assert np.array_equal(np.stack([bv.block_words(c) for c in range(40)]), rblk)
     dset.free()
+
+
+def test_sharded_aggregator_cxx_two_ranks_nccl(tmp_path):
+    """bm::b200::sharded_aggregator (C++ binding) on 2 GPUs, one process per GPU: block-range shards, the library's own NCCL exchange
+    (bmb200_comm_init / bmb200_exchange_popcounts, id passed through a file) vs bm::aggregator on the full vectors.  Needs >= 2 GPUs."""
+    import subprocess
+    import torch
+    exe = orclib.ORACLE_DIR / "_ref" / "test_sharded"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/test_sharded not built (needs /root/reference at build time)")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (NCCL refuses two ranks on one device)")
+    idf = tmp_path / "nccl_id.bin"
+    procs = [subprocess.Popen([str(exe), str(r), "2", str(idf)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and "OK:" in o, f"rank {r}:\n{o[-2000:]}"

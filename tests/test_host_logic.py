@@ -113,3 +113,15 @@ def test_upload_packer_host_build_matches_packedset():
     arr2, keep2 = _vec_blocks_c([bad], 1)
     n_bit, n_gap = C.c_uint64(0), C.c_uint64(0)
     assert lib.host_pack_sizes(1, 1, arr2, 2, C.byref(n_bit), C.byref(n_gap)) == bm.capi.ERR_BADARG
+
+
+def test_binding_result_store_recycles_blocks_in_place():
+    """bm::b200::detail::store_result (C++ binding): results of changing shapes stored into ONE target bvector (blocks recycled in
+    place, threaded over top-level sub-trees) == the same results stored into fresh bvectors (compare() == 0, calc_stat kinds, size)."""
+    import subprocess
+    exe = orclib.ORACLE_DIR / "_ref" / "store_result_check"
+    if not exe.exists():
+        import pytest
+        pytest.skip("oracle/_ref/store_result_check not built (needs /root/reference at build time)")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK:" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
