@@ -303,8 +303,8 @@ def full_parity(workload, n_cols, rank, res_meta, threads):
 class E2E:
     """ctypes face of oracle/_ref/libbmb200_e2e.so (oracle/e2e_harness.cpp): bm::b200::aggregator on real bm::bvector<> objects."""
 
-    def __init__(self):
-        so = ROOT / "oracle" / "_ref" / "libbmb200_e2e.so"
+    def __init__(self, name="libbmb200_e2e.so"):
+        so = ROOT / "oracle" / "_ref" / name
         self.lib = C.CDLL(str(so)) if so.exists() else None
         if self.lib:
             self.lib.e2e_create_empty.restype = C.c_void_p
@@ -336,16 +336,20 @@ def run_e2e(args, ctx, dset, device, world, dist, torch, op, g0, g1, flags, tota
     lib = e.lib
     g1a = g1 if g1 is not None else np.zeros(0, np.uint32)
     node = C.c_int(-1)
-    # real bm::bvector<> objects, filled chunk by chunk from the device copy of this rank's inputs (the download is setup, not timed)
-    h = C.c_void_p(lib.e2e_create_empty(C.c_uint32(dset.n_vec), C.c_uint32(dset.n_blocks), int(device), 1, C.byref(node)))
-    assert h, "e2e_create_empty failed"
-    step_cols = 1024
-    for lo in range(0, dset.n_blocks, step_cols):
-        ps = dset.download(lo, min(dset.n_blocks, lo + step_cols))
-        c = packed_c(ps.n_vec, ps.n_blocks, ps.desc, ps.bit_base, ps.gap_base, ps.bit_pool, ps.gap_pool)
-        rc = lib.e2e_append(h, C.byref(c), C.c_uint32(lo), int(thr))
-        assert rc == 0, "e2e_append failed"
-        del ps
+
+    def build_bvectors(lib_):
+        # real bm::bvector<> objects, filled chunk by chunk from the device copy of this rank's inputs (the download is setup, not timed)
+        h_ = C.c_void_p(lib_.e2e_create_empty(C.c_uint32(dset.n_vec), C.c_uint32(dset.n_blocks), int(device), 1, C.byref(node)))
+        assert h_, "e2e_create_empty failed"
+        step_cols = 1024
+        for lo in range(0, dset.n_blocks, step_cols):
+            ps = dset.download(lo, min(dset.n_blocks, lo + step_cols))
+            c = packed_c(ps.n_vec, ps.n_blocks, ps.desc, ps.bit_base, ps.gap_base, ps.bit_pool, ps.gap_pool)
+            rc_ = lib_.e2e_append(h_, C.byref(c), C.c_uint32(lo), int(min(thr, 64)))
+            assert rc_ == 0, "e2e_append failed"
+            del ps
+        return h_
+    h = build_bvectors(lib)
     n0, n1 = int(g0.size), int(g1a.size)
     compress = 1 if flags & F_OPT_COMPRESS else 0
 
@@ -378,6 +382,38 @@ def run_e2e(args, ctx, dset, device, world, dist, torch, op, g0, g1, flags, tota
         chk = {"compare_eq_0_and_calc_stat_equal": bool(eq.value), "reference_count": int(rcnt.value), "reference_1thread_ms": rms.value}
         assert eq.value, "bm::b200::aggregator result differs from bm::aggregator on the same bvectors"
     lib.e2e_free(h)
+    # ---- cold again, for applications that keep their bvectors on the page-locked slab allocator (bm::b200::slab_bvector,
+    #      bitmagic_b200/include/bmb200_alloc.hpp): the slabs go up by DMA as they lie, the gather happens on the device ----
+    slab = None
+    es = E2E("libbmb200_e2e_slab.so")
+    if world == 1 and es.ok() and not args.no_e2e_slab and mem_available_gb() >= need_gb:
+        ctx.trim()
+        t0 = time.perf_counter()
+        hs = build_bvectors(es.lib)
+        build_s = time.perf_counter() - t0
+        nsl, sbytes = C.c_uint64(0), C.c_uint64(0)
+        es.lib.e2e_slab_info(C.byref(nsl), C.byref(sbytes))
+        sms = np.zeros(args.e2e_steps + 1); scnt = C.c_uint64(0); sh2d = C.c_uint64(0); sd2h = C.c_uint64(0)
+        rc = es.lib.e2e_cold(hs, int(op), compress, ptr(g0), n0, ptr(g1a), n1, int(args.e2e_steps + 1), ptr(sms), C.byref(scnt), C.byref(sh2d), C.byref(sd2h))
+        assert rc == 0, "e2e_cold (slab allocator) failed"
+        assert scnt.value == total_bits, f"e2e (cold, slab allocator) result count {scnt.value} != device-resident run {total_bits}"
+        sa_ms, sg_ms = C.c_double(0), C.c_double(0)
+        rc = es.lib.e2e_cold_split(hs, int(op), compress, ptr(g0), n0, ptr(g1a), n1, C.byref(sa_ms), C.byref(sg_ms))
+        assert rc == 0
+        seq = None
+        if not args.no_e2e_check:
+            eq = C.c_int(0); rcnt = C.c_uint64(0); rms = C.c_double(0)
+            rc = es.lib.e2e_check(hs, int(op), compress, ptr(g0), n0, ptr(g1a), n1, C.byref(eq), C.byref(rcnt), C.byref(rms))
+            assert rc == 0 and eq.value, "slab_bvector result differs from bm::aggregator on the same bvectors"
+            seq = bool(eq.value)
+        es.lib.e2e_free(hs)
+        scold = float(np.mean(sms[1:]))
+        slab = {"value": src_blocks_all / (scold * 1e-3), "unit": "blocks/s", "ms_per_step": scold, "host_slabs": int(nsl.value),
+                "h2d_bytes_per_step": int(sbytes.value) + 8 * dset.n_vec * dset.n_blocks, "h2d_gbs": sbytes.value / scold / 1e6,
+                "split_ms": {"device_set_assign(slab DMA | walk+layout, gather kernel)": sa_ms.value, "aggregate_on_resident(kernel+D2H+bvector)": sg_ms.value},
+                "pcie_floor_ms": sbytes.value / 55e9 * 1e3, "compare_eq_0_and_calc_stat_equal": seq, "bvector_build_s": build_s,
+                "path": "cold on bm::b200::slab_bvector: bmb200_host_slabs_prefetch + bmb200_set_upload_slabs (no host packing) + kernel + D2H + result bvector"}
+        ctx.trim()
     t = torch.tensor([cold_ms, warm_ms], dtype=torch.float64, device=f"cuda:{device}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -395,7 +431,7 @@ def run_e2e(args, ctx, dset, device, world, dist, torch, op, g0, g1, flags, tota
                      "h2d_bytes_per_step": int(h2d.value), "d2h_bytes_per_step": int(d2h.value), "h2d_gbs": h2d.value / cold_ms / 1e6,
                      "path": "cold: the same call with nothing resident (tree walk + layout + threaded pack + H2D + kernel + D2H + result bvector, every step)",
                      "split_ms": {"device_set_assign(walk+layout+pack+H2D)": a_ms.value, "aggregate_on_resident(kernel+D2H+bvector)": g_ms.value},
-                     "pcie_floor_ms": h2d.value / 55e9 * 1e3},
+                     "pcie_floor_ms": h2d.value / 55e9 * 1e3, "slab_allocator": slab},
             "host_threads": thr, "numa_node": node.value, "check": chk}
 
 
@@ -483,6 +519,7 @@ def _main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-check", action="store_true")
+    ap.add_argument("--no-e2e-slab", action="store_true", help="skip the cold e2e leg on slab-allocator bvectors (N=1 only; page-locks ~ the set size)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-c5", action="store_true", help="skip the extra config-5 shard line that 8-GPU runs carry")

@@ -38,6 +38,7 @@ SYMBOLS = [
     "bmb200_scan", "bmb200_set_upload_blobs", "bmb200_result_fetch_view", "bmb200_ctx_bind_host_numa",
     "bmb200_shard_range", "bmb200_comm_unique_id", "bmb200_comm_init", "bmb200_comm_info", "bmb200_comm_destroy",
     "bmb200_exchange_popcounts", "bmb200_exchange_fence", "bmb200_exchange_fetch", "bmb200_ctx_trim", "bmb200_binop",
+    "bmb200_set_upload_slabs", "bmb200_host_slabs_prefetch", "bmb200_host_slab_alloc", "bmb200_host_slab_free",
 ]
 OP_SUB = 5
 COMM_ID_BYTES = 128
@@ -54,6 +55,10 @@ class PackedSetC(C.Structure):
 
 class VecBlocksC(C.Structure):
     _fields_ = [("n_blocks", C.c_uint32), ("kind", C.c_void_p), ("ptr", C.c_void_p)]
+
+
+class HostSlabC(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("bytes", C.c_uint64)]
 
 
 class AggArgsC(C.Structure):
@@ -278,6 +283,72 @@ class DeviceSet:
             arr[i] = VecBlocksC(v.n_blocks, ptr(kind), ptr(ptrs))
         h = C.c_void_p(0)
         ctx.check(lib().bmb200_set_upload_vectors(ctx._h, len(vectors), int(n_blocks), arr, C.byref(h)), "set_upload_vectors")
+        return cls(ctx, h)
+
+    @classmethod
+    def upload_slabs(cls, ctx: Context, vectors, n_blocks: int | None = None, slab_bytes: int = 1 << 20, pinned: bool = True,
+                     prefetch: bool = False, stray: bool = False) -> "DeviceSet":
+        """bmb200_set_upload_slabs: the blocks of `vectors` (hostfmt.BVector) are first laid into a few host slabs the way a
+        slab-backed block allocator would hold them (64-byte aligned, in allocation order = vector by vector), then uploaded by
+        DMA of the slabs + the device gather.  pinned: slabs from bmb200_host_slab_alloc (else numpy memory); prefetch: queue the
+        DMA with bmb200_host_slabs_prefetch first; stray: leave one block outside every slab (the call must fall back)."""
+        if n_blocks is None:
+            n_blocks = max(v.n_blocks for v in vectors)
+        slabs, views, keep = [], [], []
+        cur = {"buf": None, "used": 0}
+
+        def new_slab(need):
+            size = max(slab_bytes, need)
+            if pinned:
+                p = C.c_void_p(0)
+                ctx.check(lib().bmb200_host_slab_alloc(C.c_uint64(size), C.byref(p)), "host_slab_alloc")
+                buf = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(size,))
+                slabs.append([p.value, buf, 0, True])
+            else:
+                raw = np.zeros(size + 64, dtype=np.uint8)
+                off = (-raw.ctypes.data) % 64
+                buf = raw[off:off + size]
+                keep.append(raw)
+                slabs.append([buf.ctypes.data, buf, 0, False])
+            cur["buf"], cur["used"] = slabs[-1], 0
+
+        def place(blk):
+            b = np.ascontiguousarray(blk).view(np.uint8)
+            need = (b.size + 63) & ~63
+            if cur["buf"] is None or cur["buf"][1].size - cur["buf"][2] < need:
+                new_slab(need)
+            sl = cur["buf"]
+            sl[1][sl[2]:sl[2] + b.size] = b
+            addr = sl[0] + sl[2]
+            sl[2] += need
+            return addr
+
+        arr = (VecBlocksC * len(vectors))()
+        strayed = not stray
+        for i, v in enumerate(vectors):
+            kind = np.ascontiguousarray(v.kind, dtype=np.uint8)
+            ptrs = np.zeros(v.n_blocks, dtype=np.uint64)
+            for nb in range(v.n_blocks):
+                if kind[nb] == BLK_BIT or kind[nb] == BLK_GAP:
+                    if not strayed:
+                        blk = np.ascontiguousarray(v.blocks[nb]); keep.append(blk); ptrs[nb] = blk.ctypes.data; strayed = True
+                    else:
+                        ptrs[nb] = place(v.blocks[nb])
+            keep += [kind, ptrs]
+            arr[i] = VecBlocksC(v.n_blocks, ptr(kind), ptr(ptrs))
+        carr = (HostSlabC * max(1, len(slabs)))()
+        for k, sl in enumerate(slabs):
+            carr[k].base = sl[0]; carr[k].bytes = sl[2]
+        try:
+            if prefetch:
+                ctx.check(lib().bmb200_host_slabs_prefetch(ctx._h, carr, len(slabs)), "host_slabs_prefetch")
+            h = C.c_void_p(0)
+            ctx.check(lib().bmb200_set_upload_slabs(ctx._h, len(vectors), int(n_blocks), arr, carr, len(slabs), C.byref(h)), "set_upload_slabs")
+        finally:
+            ctx.sync()
+            for sl in slabs:
+                if sl[3]:
+                    lib().bmb200_host_slab_free(C.c_void_p(sl[0]))
         return cls(ctx, h)
 
     @classmethod

@@ -103,6 +103,69 @@ __global__ void __launch_bounds__(256) result_compact_kernel(const uint32_t* __r
     }
 }
 
+// bmb200_set_upload_slabs: the host slabs were copied to the device as they lie (mirror); this kernel moves every real block from
+// its place in the mirror (src[nb][v], 32-byte units) to its place in the column-major arena -- the device-side twin of
+// host_pack.hpp's pack_column, same FLAT form (lead pad 0xFFFF iff the first run is 0, zeros up to the next 16-byte unit).
+// One warp per block: 8 KB = 16 x 128-bit per lane; a GAP block without lead pad is a straight 128-bit copy (the mirror keeps
+// the allocator's 32-byte alignment), one with lead pad shifts by one u16 through 16-bit loads.
+// HBM bytes: every stored byte is read once and written once (+ 8 B of descriptor / source per block).
+__global__ void __launch_bounds__(256) slab_gather_kernel(SetView set, const uint8_t* __restrict__ mirror,
+                                                          const uint32_t* __restrict__ src)
+{
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    for (uint32_t nb = blockIdx.x; nb < set.n_blocks; nb += gridDim.x) {
+        const uint32_t* drow = set.desc + (size_t)nb * set.n_vec;
+        const uint32_t* srow = src + (size_t)nb * set.n_vec;
+        uint4* bit_dst = reinterpret_cast<uint4*>(const_cast<uint32_t*>(set.bit_pool) + set.bit_base[nb] * (size_t)kBlockWords);
+        uint16_t* gap_dst = const_cast<uint16_t*>(set.gap_pool) + set.gap_base[nb] * (size_t)kGapUnit;
+        for (uint32_t v = warp; v < set.n_vec; v += 8u) {
+            const uint32_t d = drow[v], kd = d & 3u;
+            if (kd == BMB200_BLK_BIT) {
+                const uint4* in = reinterpret_cast<const uint4*>(mirror + (size_t)srow[v] * 32u);
+                uint4* out = bit_dst + (size_t)((d >> 2) & BMB200_DESC_REL_MASK) * (kBlockWords / 4u);
+                uint4 r[16];
+#pragma unroll
+                for (uint32_t k = 0; k < 16; ++k) r[k] = ld_stream_v4(in + lane + 32u * k);
+#pragma unroll
+                for (uint32_t k = 0; k < 16; ++k) out[lane + 32u * k] = r[k];
+            } else if (kd == BMB200_BLK_GAP) {
+                const uint16_t* in = reinterpret_cast<const uint16_t*>(mirror + (size_t)srow[v] * 32u);
+                uint16_t* out = gap_dst + (size_t)((d >> 2) & BMB200_DESC_REL_MASK) * kGapUnit;
+                const uint32_t words = (uint32_t)(in[0] >> 3) + 1u, pad = d >> 31;
+                const uint32_t units = (words + pad + kGapUnit - 1u) / kGapUnit;
+                if (!pad) {
+                    for (uint32_t u = lane; u < units; u += 32u) {
+                        uint4 q = reinterpret_cast<const uint4*>(in)[u];          // the last unit may read past the block: still inside the mirror (slack)
+                        const uint32_t keep = words - u * kGapUnit;               // valid u16 in this unit (>= 1)
+                        if (keep < kGapUnit) {
+                            uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                            for (uint32_t k = 0; k < 4; ++k) {
+                                const uint32_t lo = 2u * k < keep ? 0xffffu : 0u, hi = 2u * k + 1u < keep ? 0xffff0000u : 0u;
+                                w[k] &= lo | hi;
+                            }
+                            q = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                        reinterpret_cast<uint4*>(out)[u] = q;
+                    }
+                } else {
+                    for (uint32_t u = lane; u < units; u += 32u) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; ++k) {
+                            const uint32_t i0 = u * kGapUnit + 2u * k, i1 = i0 + 1u;      // output positions; input = position - 1
+                            const uint32_t a = i0 == 0 ? 0xffffu : (i0 - 1u < words ? (uint32_t)in[i0 - 1u] : 0u);
+                            const uint32_t b = i1 - 1u < words ? (uint32_t)in[i1 - 1u] : 0u;
+                            w[k] = a | (b << 16);
+                        }
+                        reinterpret_cast<uint4*>(out)[u] = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // rs_index build (bvector::build_rs_index src/bm.h:2531-2660): one warp per block computes
 //   bcount, first = bits in [0,21824], second = bits in (21824,43648], aux0, aux1

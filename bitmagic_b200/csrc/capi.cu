@@ -54,10 +54,12 @@ struct bmb200_ctx {
     uint8_t* h_ring[kStageSlots] = {};      // pinned staging ring of bmb200_set_upload_vectors (grow-only)
     size_t h_ring_cap = 0;
     cudaEvent_t ring_ev[kStageSlots] = {};
-    void* d_pool[6] = {};                   // grow-only device scratch of the fetch / rank / select entry points (no cudaMalloc per call)
-    size_t d_pool_cap[6] = {};
-    void* h_pool[5] = {};                   // grow-only pinned scratch of the same entry points
-    size_t h_pool_cap[5] = {};
+    void* d_pool[8] = {};                   // grow-only device scratch of the fetch / rank / select entry points (no cudaMalloc per call)
+    size_t d_pool_cap[8] = {};
+    std::vector<std::pair<uint64_t, uint64_t>> mirror_sig;   // slab list (base, bytes) whose copies into d_pool[6] were queued last
+    bool mirror_live = false;               // ... by bmb200_host_slabs_prefetch, not yet consumed by an upload
+    void* h_pool[6] = {};                   // grow-only pinned scratch of the same entry points
+    size_t h_pool_cap[6] = {};
     CommState comm;                         // multi-GPU exchange (bmb200_comm_*), unused on one GPU
     // ONE recycled device arena: bmb200_set_free parks the arrays of the last freed set here and the next set_alloc that fits takes
     // them, so that a cold upload per call (no residency) does not pay cudaMalloc + cudaFree of a multi-GB arena (25 - 230 ms) each time;
@@ -172,7 +174,7 @@ int pool_dev(bmb200_ctx* ctx, int slot, size_t bytes, void** out)
 {
     if (bytes > ctx->d_pool_cap[slot]) {
         if (ctx->d_pool[slot]) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->d_pool[slot]); ctx->d_pool[slot] = nullptr; ctx->d_pool_cap[slot] = 0; }
-        const size_t cap = bytes + bytes / 4 + 256;
+        const size_t cap = bytes + (bytes > (1ull << 30) ? 0 : bytes / 4) + 256;     // multi-GB buffers (the slab mirror) are sized exactly
         cudaError_t e = cudaMalloc(&ctx->d_pool[slot], cap);
         if (e != cudaSuccess) { ctx->last_err = std::string("cudaMalloc(pool): ") + cudaGetErrorString(e); return e == cudaErrorMemoryAllocation ? BMB200_ERR_BADALLOC : BMB200_ERR_CUDA; }
         ctx->d_pool_cap[slot] = cap;
@@ -490,6 +492,125 @@ int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks
     e = cudaStreamSynchronize(st);                  // L.desc / the ring are host memory of this call
     if (e != cudaSuccess) return fail(BMB200_ERR_CUDA, e);
     tr.mark("pack + H2D (pipelined)");
+    *out = s;
+    return BMB200_OK;
+}
+
+int bmb200_host_slab_alloc(uint64_t bytes, void** out)
+{
+    if (!out || !bytes) return BMB200_ERR_BADARG;
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorMemoryAllocation ? BMB200_ERR_BADALLOC : BMB200_ERR_CUDA; }
+    *out = p;
+    return BMB200_OK;
+}
+int bmb200_host_slab_free(void* slab)
+{
+    if (!slab) return BMB200_ERR_BADARG;
+    return cudaFreeHost(slab) == cudaSuccess ? BMB200_OK : BMB200_ERR_CUDA;
+}
+
+// the device mirror of a slab list: slabs back to back (256-byte aligned), sorted by host address for the pointer -> slab search;
+// issue = queue the H2D copies now.  ctx->mirror_sig remembers what is in flight so that a prefetch is not repeated.
+static int mirror_begin(bmb200_ctx* ctx, const bmb200_host_slab* slabs, uint32_t n_slabs, SlabMap& M, uint8_t** mirror_out, uint64_t* bytes_out)
+{
+    uint64_t mirror_bytes = 0;
+    std::vector<std::pair<uint64_t, uint64_t>> sig;
+    try {
+        std::vector<uint32_t> order;
+        for (uint32_t k = 0; k < n_slabs; ++k) if (slabs[k].base && slabs[k].bytes) order.push_back(k);
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return (uintptr_t)slabs[a].base < (uintptr_t)slabs[b].base; });
+        for (uint32_t k : order) {
+            M.base.push_back((uint64_t)(uintptr_t)slabs[k].base); M.end.push_back(M.base.back() + slabs[k].bytes);
+            M.dev_off.push_back(mirror_bytes);
+            mirror_bytes += (slabs[k].bytes + 255ull) & ~255ull;
+            sig.emplace_back(M.base.back(), slabs[k].bytes);
+        }
+    } catch (...) { return BMB200_ERR_BADALLOC; }
+    *bytes_out = mirror_bytes; *mirror_out = nullptr;
+    if (M.base.empty() || mirror_bytes > (128ull << 30)) return BMB200_OK;         // caller falls back to host packing
+    CU(cudaSetDevice(ctx->device));
+    uint8_t* mirror = nullptr;
+    int rc = pool_dev(ctx, 6, mirror_bytes + 64, (void**)&mirror);
+    if (rc) return rc;
+    *mirror_out = mirror;
+    if (ctx->mirror_live && ctx->mirror_sig == sig) { ctx->mirror_live = false; return BMB200_OK; }      // prefetched by bmb200_host_slabs_prefetch
+    cudaError_t e = cudaSuccess;
+    for (size_t k = 0; k < M.base.size() && e == cudaSuccess; ++k)
+        e = cudaMemcpyAsync(mirror + M.dev_off[k], (const void*)(uintptr_t)M.base[k], M.end[k] - M.base[k], cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { cudaStreamSynchronize(ctx->stream); ctx->last_err = std::string("slab mirror: ") + cudaGetErrorString(e); return BMB200_ERR_CUDA; }
+    ctx->mirror_sig.swap(sig);
+    return BMB200_OK;
+}
+
+int bmb200_host_slabs_prefetch(bmb200_ctx* ctx, const bmb200_host_slab* slabs, uint32_t n_slabs)
+{
+    if (!ctx || (n_slabs && !slabs)) return BMB200_ERR_BADARG;
+    SlabMap M; uint8_t* mirror = nullptr; uint64_t bytes = 0;
+    ctx->mirror_live = false;
+    int rc = mirror_begin(ctx, slabs, n_slabs, M, &mirror, &bytes);
+    if (!rc && mirror) ctx->mirror_live = true;
+    return rc;
+}
+
+int bmb200_set_upload_slabs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, const bmb200_vec_blocks* vecs,
+                            const bmb200_host_slab* slabs, uint32_t n_slabs, bmb200_set** out)
+{
+    if (!ctx || !vecs || !out || !n_vec || !n_blocks || (n_slabs && !slabs)) return BMB200_ERR_BADARG;
+    for (uint32_t v = 0; v < n_vec; ++v)
+        if (vecs[v].n_blocks > n_blocks || (vecs[v].n_blocks && (!vecs[v].kind || !vecs[v].ptr))) return BMB200_ERR_BADARG;
+    PhaseTrace tr("set_upload_slabs", ctx->stream);
+    // 1. the slabs start crossing PCIe now (unless a prefetch already started them); everything the host has to do happens underneath
+    SlabMap M;
+    uint64_t mirror_bytes = 0;
+    uint8_t* mirror = nullptr;
+    int rc = mirror_begin(ctx, slabs, n_slabs, M, &mirror, &mirror_bytes);
+    ctx->mirror_live = false;
+    if (rc) return rc;
+    if (!mirror) return bmb200_set_upload_vectors(ctx, n_vec, n_blocks, vecs, out);
+    cudaStream_t st = ctx->stream;
+    cudaError_t e = cudaSuccess;
+    if (tr.on) fprintf(stderr, "[bmb200] set_upload_slabs: %zu slabs, %.1f MB queued for DMA\n", M.base.size(), mirror_bytes / 1048576.0);
+    // 2. layout (descriptors, prefix sums) + where every block sits in the mirror
+    PackLayout L;
+    uint32_t* h_src = nullptr;
+    bool inside = false;
+    try {
+        pack_layout(n_vec, n_blocks, vecs, (unsigned)ctx->host_threads, L);
+        if (!L.rc && !(rc = pool_host(ctx, 5, (size_t)n_vec * n_blocks * 4, (void**)&h_src)))
+            inside = pack_sources(n_vec, n_blocks, vecs, L, M, (unsigned)ctx->host_threads, h_src);
+    } catch (...) { rc = BMB200_ERR_BADALLOC; }
+    if (L.rc || rc || !inside) {
+        cudaStreamSynchronize(st);                                  // the DMAs read caller memory: let them finish, then take the other road
+        if (L.rc) return L.rc;
+        if (rc) return rc;
+        return bmb200_set_upload_vectors(ctx, n_vec, n_blocks, vecs, out);
+    }
+    const uint64_t n_bit = L.bb[n_blocks], n_gap = L.gb[n_blocks];
+    bmb200_set* s = nullptr;
+    if ((rc = set_alloc(ctx, n_vec, n_blocks, n_bit, n_gap, &s))) { cudaStreamSynchronize(st); return rc; }
+    uint32_t* d_src = nullptr;
+    if ((rc = pool_dev(ctx, 7, (size_t)n_vec * n_blocks * 4, (void**)&d_src))) { cudaStreamSynchronize(st); free_set_arrays(s); delete s; return rc; }
+    e = cudaMemcpyAsync(d_src, h_src, (size_t)n_vec * n_blocks * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync((void*)s->v.desc, L.desc.data(), L.desc.size() * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync((void*)s->v.bit_base, L.bb.data(), L.bb.size() * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync((void*)s->v.gap_base, L.gb.data(), L.gb.size() * 8, cudaMemcpyHostToDevice, st);
+    tr.mark("tree layout + source table under the DMA, then their H2D");
+    // 3. mirror -> column-major arena
+    if (e == cudaSuccess) {
+        uint32_t grid = (uint32_t)ctx->sm_count * 8u; if (grid > n_blocks) grid = n_blocks;
+        slab_gather_kernel<<<grid, 256, 0, st>>>(s->v, mirror, d_src);
+        rc = after_launch(ctx);
+        e = cudaStreamSynchronize(st);                              // L / h_src are host memory of this call
+    }
+    if (e != cudaSuccess || rc) {
+        cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { ctx->last_err = std::string("set_upload_slabs: ") + cudaGetErrorString(e); rc = BMB200_ERR_CUDA; }
+        free_set_arrays(s); delete s;
+        return rc;
+    }
+    tr.mark("gather kernel (mirror -> arena)");
     *out = s;
     return BMB200_OK;
 }
@@ -923,6 +1044,8 @@ int bmb200_ctx_trim(bmb200_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     auto& a = ctx->arena;
     if (a.full) { cudaFree(a.desc); cudaFree(a.bb); cudaFree(a.gb); cudaFree(a.bp); cudaFree(a.gp); a = bmb200_ctx::Arena(); }
+    for (int slot = 6; slot <= 7; ++slot)           // the slab mirror and its source table (bmb200_set_upload_slabs)
+        if (ctx->d_pool[slot]) { cudaFree(ctx->d_pool[slot]); ctx->d_pool[slot] = nullptr; ctx->d_pool_cap[slot] = 0; }
     return BMB200_OK;
 }
 

@@ -91,6 +91,50 @@ inline void pack_layout(uint32_t n_vec, uint32_t n_blocks, const bmb200_vec_bloc
     for (uint32_t nb = 0; nb < n_blocks; ++nb) { L.bb[nb + 1] += L.bb[nb]; L.gb[nb + 1] += L.gb[nb]; }
 }
 
+// Slab-backed sources (bmb200_set_upload_slabs): where every real block sits inside the device mirror of the host slabs, in 32-byte
+// units (u32: mirrors up to 128 GB).  Threads own column ranges.  false = a block lies outside the slabs or is not 32-byte aligned.
+struct SlabMap { std::vector<uint64_t> base, end, dev_off; };          // sorted by base; dev_off = byte offset of the slab inside the mirror
+
+inline bool pack_sources(uint32_t n_vec, uint32_t n_blocks, const bmb200_vec_blocks* vecs, const PackLayout& L, const SlabMap& M,
+                         unsigned threads, uint32_t* src)
+{
+    const unsigned T = pack_threads(threads, n_blocks);
+    const size_t ns = M.base.size();
+    std::vector<uint8_t> ok(T, 1);
+    auto work = [&](unsigned t) {
+        const uint32_t lo = (uint32_t)((uint64_t)n_blocks * t / T), hi = (uint32_t)((uint64_t)n_blocks * (t + 1) / T);
+        size_t last = 0;
+        for (uint32_t nb = lo; nb < hi; ++nb) {
+            const uint32_t* drow = L.desc.data() + (size_t)nb * n_vec;
+            uint32_t* srow = src + (size_t)nb * n_vec;
+            for (uint32_t v = 0; v < n_vec; ++v) {
+                const uint32_t kd = drow[v] & 3u;
+                if (kd != BMB200_BLK_BIT && kd != BMB200_BLK_GAP) { srow[v] = 0; continue; }
+                const uint64_t p = (uint64_t)(uintptr_t)vecs[v].ptr[nb];
+                const uint64_t len = kd == BMB200_BLK_BIT ? (uint64_t)BMB200_BLOCK_BYTES
+                                                          : ((uint64_t)(*(const uint16_t*)vecs[v].ptr[nb] >> 3) + 1u) * 2u;
+                if (!(p >= M.base[last] && p + len <= M.end[last])) {
+                    size_t a = 0, b = ns;                                   // last slab with base <= p
+                    while (b - a > 1) { const size_t m = (a + b) / 2; if (M.base[m] <= p) a = m; else b = m; }
+                    if (!(p >= M.base[a] && p + len <= M.end[a])) { ok[t] = 0; return; }
+                    last = a;
+                }
+                const uint64_t off = M.dev_off[last] + (p - M.base[last]);
+                if (off & 31u) { ok[t] = 0; return; }
+                srow[v] = (uint32_t)(off >> 5);
+            }
+        }
+    };
+    if (T == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; ++t) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    for (uint8_t o : ok) if (!o) return false;
+    return true;
+}
+
 // one column into its place inside a staging slot: bit-blocks at bit_dst (in descriptor order), GAP units at gap_dst
 inline void pack_column(uint32_t n_vec, uint32_t nb, const bmb200_vec_blocks* vecs, const uint32_t* drow, uint8_t* bit_dst, uint8_t* gap_dst)
 {

@@ -13,7 +13,10 @@
 #ifndef BMB200_AGGREGATOR_HPP_INCLUDED
 #define BMB200_AGGREGATOR_HPP_INCLUDED
 
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <memory>
@@ -27,6 +30,7 @@
 #include "bmaggregator.h"
 
 #include "bmb200.h"
+#include "bmb200_alloc.hpp"
 
 namespace bm { namespace b200 {
 
@@ -199,6 +203,30 @@ void build_views(const BV* const* vecs, size_t n, uint32_t nb_from, uint32_t n_b
 
 } // namespace detail
 
+namespace detail {
+/// Slab-backed vectors (bmb200_alloc.hpp) reach the device by DMA of their slabs + a device gather, any other bm::bvector<>
+/// through the host packing pipeline.  The DMA moves the WHOLE heap, so it is the road for sets of many vectors (the aggregator's
+/// case: >= 64 here); begin() queues the copies before the block trees are walked, finish() lays the set out under them.
+template<class BV>
+struct set_uploader
+{
+    std::vector<bmb200_host_slab> slabs;
+    bool use_slabs = false;
+    void begin(bmb200_ctx* ctx, size_t n_vec)
+    {
+        use_slabs = false;
+        if (!slab_backed<BV>::value || n_vec < 64) return;
+        slab_heap::instance().snapshot(slabs);
+        use_slabs = !slabs.empty() && bmb200_host_slabs_prefetch(ctx, slabs.data(), (uint32_t)slabs.size()) == BMB200_OK;
+    }
+    int finish(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, const bmb200_vec_blocks* vb, bmb200_set** set)
+    {
+        if (use_slabs) return bmb200_set_upload_slabs(ctx, n_vec, n_blocks, vb, slabs.data(), (uint32_t)slabs.size(), set);
+        return bmb200_set_upload_vectors(ctx, n_vec, n_blocks, vb, set);
+    }
+};
+}  // namespace detail
+
 /// Residency: a set of bvectors uploaded ONCE (block trees walked and blocks packed by host threads, H2D pipelined -- all inside
 /// bmb200_set_upload_vectors) and then addressed by bvector ADDRESS in every aggregator call that is given this set
 /// (aggregator::set_device_set).  This is the upload / cache API SURVEY section 7 asks for: at 6+ TB/s the aggregation of a
@@ -226,13 +254,17 @@ public:
         if (nb_from >= nblk) throw std::range_error("device_set: empty block range");
         nb_from_ = nb_from; n_blocks_ = nblk - nb_from;
         std::vector<detail::tree_view<BV>> views; std::vector<bmb200_vec_blocks> vb;
+        detail::set_uploader<BV> up;
+        up.begin(ctx_.get(), n);
         detail::build_views(vecs, n, nb_from, n_blocks_, views, vb);
-        check(bmb200_set_upload_vectors(ctx_.get(), (uint32_t)n, n_blocks_, vb.data(), &set_), "bmb200_set_upload_vectors");
+        check(up.finish(ctx_.get(), (uint32_t)n, n_blocks_, vb.data(), &set_), "bmb200_set_upload_vectors");
         index_.clear(); stamps_.resize(n); vecs_.assign(vecs, vecs + n);
         for (size_t k = 0; k < n; ++k) { index_.emplace(vecs[k], (uint32_t)k); stamps_[k] = stamp_of(*vecs[k]); }
     }
-    void release() { if (set_) { bmb200_set_free(set_); set_ = nullptr; } index_.clear(); vecs_.clear(); stamps_.clear(); }
+    void release() { if (set_) { bmb200_set_free(set_); set_ = nullptr; } index_.clear(); vecs_.clear(); stamps_.clear(); ++epoch_; }
     bool resident() const { return set_ != nullptr; }
+    /// changes whenever the device copy is rebuilt or dropped (the aggregator caches its source -> member lookups against it)
+    uint64_t epoch() const { return epoch_; }
     /// index of bv inside the set, or -1
     long index_of(const BV* bv) const { auto it = index_.find(bv); return it == index_.end() ? -1 : (long)it->second; }
     bool stale() const { for (size_t k = 0; k < vecs_.size(); ++k) if (!(stamps_[k] == stamp_of(*vecs_[k]))) return true; return false; }
@@ -251,6 +283,7 @@ private:
     context& ctx_;
     bmb200_set* set_ = nullptr;
     uint32_t n_blocks_ = 0, nb_from_ = 0;
+    uint64_t epoch_ = 0;
     std::unordered_map<const BV*, uint32_t> index_;
     std::vector<const BV*> vecs_;
     std::vector<stamp> stamps_;
@@ -271,7 +304,7 @@ public:
 
     /// attach a resident set: calls whose sources are ALL members of it run on the device copy (no tree walk, no upload);
     /// any other call uploads its sources as before.  nullptr detaches.
-    void set_device_set(const device_set<BV>* ds) { ds_ = ds; }
+    void set_device_set(const device_set<BV>* ds) { ds_ = ds; bound_ds_ = nullptr; }
 
     // ---- setters, same meaning as src/bmaggregator.h:359-388 ----
     void set_optimization(typename BV::optmode opt = BV::opt_compress) { opt_mode_ = opt; }
@@ -342,6 +375,8 @@ public:
 
     /// device-side result of the last combine_* call (valid until the next one); used by sharded_aggregator for the exchange
     bmb200_result* last_result() const { return res_; }
+    /// bytes the last combine_* call read back from the device (column kinds + lengths + the result blocks themselves)
+    uint64_t last_d2h_bytes() const { return last_d2h_; }
 
     /// popcount of AND-SUB without materialising the result (pipeline counts mode, :1397-1398)
     size_type count_and_sub(const bvector_type_const_ptr* src_and, size_t n_and,
@@ -365,6 +400,13 @@ private:
     /// sources -> (set, member indices): the attached resident set when every source lives in it, else a fresh upload
     bmb200_set* bind(const bvector_type_const_ptr* s0, size_t n0, const bvector_type_const_ptr* s1, size_t n1, bool& own)
     {
+        // the same source lists against the same resident copy as the previous call (a query loop over long-lived vectors): the
+        // member ids, block count and target size of that call still hold -- 16384 hash lookups and size() reads are ~1 ms
+        if (ds_ && ds_->resident() && !spare_blocks_ && bound_ds_ == ds_ && bound_epoch_ == ds_->epoch() && bound_n0_ == n0 &&
+            bound_.size() == n0 + n1 && (!n0 || !memcmp(bound_.data(), s0, n0 * sizeof(*s0))) &&
+            (!n1 || !memcmp(bound_.data() + n0, s1, n1 * sizeof(*s1))))
+        { own = false; return ds_->handle(); }
+        bound_ds_ = nullptr;
         g0_.resize(n0); g1_.resize(n1);
         max_size_ = 0;
         for (size_t k = 0; k < n0 + n1; ++k)
@@ -380,7 +422,13 @@ private:
                 long ix = ds_->index_of(k < n0 ? s0[k] : s1[k - n0]);
                 if (ix < 0) all = false; else (k < n0 ? g0_[k] : g1_[k - n0]) = (uint32_t)ix;
             }
-            if (all) { own = false; n_blocks_ = ds_->n_blocks(); nb_off_ = ds_->nb_from(); return ds_->handle(); }
+            if (all)
+            {
+                own = false; n_blocks_ = ds_->n_blocks(); nb_off_ = ds_->nb_from();
+                bound_.assign(s0, s0 + n0); bound_.insert(bound_.end(), s1, s1 + n1);
+                bound_ds_ = ds_; bound_epoch_ = ds_->epoch(); bound_n0_ = n0;
+                return ds_->handle();
+            }
         }
         for (size_t k = 0; k < n0; ++k) g0_[k] = (uint32_t)k;
         for (size_t k = 0; k < n1; ++k) g1_[k] = (uint32_t)(n0 + k);
@@ -399,17 +447,23 @@ private:
             if (nb > n_blocks_) n_blocks_ = nb;
         }
         if (spare_blocks_ && n_blocks_ < 65536u) n_blocks_ += spare_blocks_;
+        detail::set_uploader<BV> up;
+        up.begin(ctx_.get(), n0 + n1);
         detail::build_views(all.data(), all.size(), 0u, n_blocks_, views_, vb_);
         bmb200_set* set = nullptr;
-        check(bmb200_set_upload_vectors(ctx_.get(), (uint32_t)(n0 + n1), n_blocks_, vb_.data(), &set), "bmb200_set_upload_vectors");
+        check(up.finish(ctx_.get(), (uint32_t)(n0 + n1), n_blocks_, vb_.data(), &set), "bmb200_set_upload_vectors");
         return set;
     }
 
     bool run(bvector_type& target, int op, const bvector_type_const_ptr* s0, size_t n0,
              const bvector_type_const_ptr* s1, size_t n1, bool compress)
     {
+        static const bool trace = getenv("BMB200_TRACE") != nullptr;
+        auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t0 = trace ? now() : 0;
         bool own = false;
         bmb200_set* set = bind(s0, n0, s1, n1, own);
+        const double t1 = trace ? now() : 0;
         bmb200_agg_args a{op, compress ? BMB200_F_OPT_COMPRESS : BMB200_F_OPT_NONE,
                           g0_.data(), (uint32_t)n0, n1 ? g1_.data() : nullptr, (uint32_t)n1, 0, 0};
         // the result object (device buffers for every column) is recycled from call to call; the fetched blocks arrive in pinned
@@ -420,7 +474,11 @@ private:
         if (!rc) rc = bmb200_result_fetch_view(res_, &kind, &off, &bits, &gaps, &nb, &ng, &total);
         if (own) { int rc2 = bmb200_set_free(set); if (!rc) rc = rc2; }
         check(rc, "bmb200_aggregate");
+        last_d2h_ = (uint64_t)n_blocks_ * 5u + 8u + nb * (uint64_t)BMB200_BLOCK_BYTES + ng * 2u;
+        const double t2 = trace ? now() : 0;
         detail::store_result(target, max_size_, n_blocks_, kind, off, bits, gaps, nb_off_);
+        if (trace) fprintf(stderr, "[bmb200] aggregator::run: bind %.3f ms, aggregate + fetch (%llu bit-blocks, %llu GAP words) %.3f ms, store into the target %.3f ms\n",
+                           t1 - t0, (unsigned long long)nb, (unsigned long long)ng, t2 - t1, now() - t2);
         return total != 0;
     }
 
@@ -431,6 +489,11 @@ private:
     std::vector<bmb200_vec_blocks> vb_;
     std::vector<uint32_t> g0_, g1_;
     const device_set<BV>* ds_ = nullptr;
+    const device_set<BV>* bound_ds_ = nullptr;       // bind() cache: source list of the last call that ran on ds_
+    std::vector<const BV*> bound_;
+    uint64_t bound_epoch_ = 0;
+    size_t bound_n0_ = 0;
+    uint64_t last_d2h_ = 0;
     bmb200_result* res_ = nullptr;
     uint32_t n_blocks_ = 0, nb_off_ = 0;
     uint32_t spare_blocks_ = 0;

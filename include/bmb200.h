@@ -186,7 +186,8 @@ int bmb200_ctx_set_tuning(bmb200_ctx* ctx, int key, int value);
  * -1 when the box has no NUMA information (then nothing is changed).  Call it before the first upload. */
 int bmb200_ctx_bind_host_numa(bmb200_ctx* ctx, int* node);
 /* bmb200_set_free parks the device arena of the set it frees in the context (at most one) and the next upload that fits reuses it,
- * so per-call uploads do not pay cudaMalloc / cudaFree of a multi-GB arena every time; bmb200_ctx_trim gives that memory back */
+ * so per-call uploads do not pay cudaMalloc / cudaFree of a multi-GB arena every time; bmb200_set_upload_slabs likewise keeps its
+ * device mirror of the host slabs for the next call.  bmb200_ctx_trim gives all of that memory back */
 int bmb200_ctx_trim(bmb200_ctx* ctx);
 
 /* ---------------- sets ---------------- */
@@ -198,6 +199,25 @@ int bmb200_set_upload(bmb200_ctx* ctx, const bmb200_packed_set* host, bmb200_set
  * To upload only a shard, pass kind + nb_from / ptr + nb_from with n_blocks = the shard's width. */
 int bmb200_set_upload_vectors(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks,
                               const bmb200_vec_blocks* vecs, bmb200_set** out);
+/* The same upload for vectors whose blocks live inside a few large HOST SLABS (a slab-backed block allocator in the place of
+ * bm::block_allocator, src/bmalloc.h:57-98 -- the seam sample6.cpp:47-110 shows -- or the arenas of frozen vectors,
+ * src/bmblocks.h:2607-2771): no host thread touches a block.  The slabs cross PCIe as they lie (one DMA each, at link speed when
+ * they are pinned: bmb200_host_slab_alloc), the block tree is walked and laid out WHILE they are in flight, and one kernel then
+ * gathers the blocks from the device mirror into the column-major arena (same arena, descriptors and results as
+ * bmb200_set_upload_vectors).  Every BIT / GAP block pointer must lie inside one of the slabs and be 32-byte aligned, and
+ * the slabs may hold up to 128 GB together; when that does not hold the call falls back to bmb200_set_upload_vectors. */
+typedef struct bmb200_host_slab {
+    const void* base;    /* start of the slab                                                            */
+    uint64_t    bytes;   /* bytes in use from base (the extent that is copied)                           */
+} bmb200_host_slab;
+int bmb200_set_upload_slabs(bmb200_ctx* ctx, uint32_t n_vec, uint32_t n_blocks, const bmb200_vec_blocks* vecs,
+                            const bmb200_host_slab* slabs, uint32_t n_slabs, bmb200_set** out);
+/* optional: queue the DMA of the slabs BEFORE the caller walks its block trees (the walk then runs under the copies too); the next
+ * bmb200_set_upload_slabs on this context with the same slab list picks the copies up instead of issuing them again */
+int bmb200_host_slabs_prefetch(bmb200_ctx* ctx, const bmb200_host_slab* slabs, uint32_t n_slabs);
+/* page-locked host memory for such slabs (cudaHostAlloc, portable across the GPUs of the process).  No context needed. */
+int bmb200_host_slab_alloc(uint64_t bytes, void** out);
+int bmb200_host_slab_free(void* slab);
 /* deserialize-to-device: vector v of the set arrives as a BitMagic serialization BLOB (bm::serializer<>, src/bmserial.h) and
  * is decoded on the GPU straight into the arena -- what bm::deserialize(bv, buf) (src/bmserial.h:4152) + an upload of the
  * materialised blocks would produce (same bits, same block kinds), with only the compressed bytes crossing PCIe.

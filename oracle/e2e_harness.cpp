@@ -26,7 +26,11 @@
 #include "bmb200.h"
 #include "bmb200_aggregator.hpp"
 
+#ifdef E2E_SLAB       /* the same harness on bvectors whose blocks live in page-locked slabs (bmb200_alloc.hpp): libbmb200_e2e_slab.so */
+typedef bm::b200::slab_bvector bvect;
+#else
 typedef bm::bvector<> bvect;
+#endif
 
 namespace {
 
@@ -148,8 +152,7 @@ int e2e_cold(void* hv, int op, int compress, const uint32_t* g0, uint32_t n0, co
         }
         if (count) *count = h->last.count();
         if (h2d_bytes) *h2d_bytes = h->set_bytes + 4ull * (n0 + n1);
-        if (d2h_bytes) { bvect::statistics st; h->last.calc_stat(&st);
-                         *d2h_bytes = (uint64_t)h->n_blocks * 5 + 8 + (uint64_t)st.bit_blocks * BMB200_BLOCK_BYTES + (uint64_t)st.gap_blocks * 2 * 8; }
+        if (d2h_bytes) *d2h_bytes = agg.last_d2h_bytes();    /* counted by the binding from what bmb200_result_fetch_view handed back */
         return 0;
     } catch (...) { return 1; }
 }
@@ -197,8 +200,7 @@ int e2e_warm(void* hv, int op, int compress, const uint32_t* g0, uint32_t n0, co
         }
         if (ds.stale()) return 3;
         if (count) *count = h->last.count();
-        if (d2h_bytes) { bvect::statistics st; h->last.calc_stat(&st);
-                         *d2h_bytes = (uint64_t)h->n_blocks * 5 + 8 + (uint64_t)st.bit_blocks * BMB200_BLOCK_BYTES + (uint64_t)st.gap_blocks * 2 * 8; }
+        if (d2h_bytes) *d2h_bytes = agg.last_d2h_bytes();    /* counted by the binding from what bmb200_result_fetch_view handed back */
         return 0;
     } catch (...) { return 1; }
 }
@@ -223,5 +225,17 @@ int e2e_check(void* hv, int op, int compress, const uint32_t* g0, uint32_t n0, c
 }
 
 void e2e_free(void* hv) { delete (Harness*)hv; }
+
+/* slab build only: how many host slabs the vectors occupy and how many bytes of them are in use (= what a cold upload DMAs) */
+int e2e_slab_info(uint64_t* n_slabs, uint64_t* bytes)
+{
+#ifdef E2E_SLAB
+    *n_slabs = bm::b200::slab_heap::instance().slab_count(); *bytes = bm::b200::slab_heap::instance().bytes_handed_out();
+    return 0;
+#else
+    *n_slabs = 0; *bytes = 0;
+    return 1;
+#endif
+}
 
 } // extern "C"

@@ -64,3 +64,27 @@ extern "C" int host_pack_check(uint32_t n_vec, uint32_t n_blocks, const bmb200_v
 {
     return host_pack_check2(n_vec, n_blocks, vecs, threads, slot_bytes, desc, bb, gb, bit_pool, gap_pool, n_chunks, 1);
 }
+
+/* bmb200_set_upload_slabs, host half: the mirror layout (slabs sorted by address, back to back at 256-byte steps) and the
+ * per-block source table pack_sources builds.  dev_off[k] = mirror offset of INPUT slab k.  Returns 0, or 1 when a block lies
+ * outside the slabs / is misaligned (the product then falls back to the packing path). */
+extern "C" int host_pack_sources(uint32_t n_vec, uint32_t n_blocks, const bmb200_vec_blocks* vecs, int threads,
+                                 const bmb200_host_slab* slabs, uint32_t n_slabs, uint32_t* src, uint64_t* dev_off, uint64_t* mirror_bytes)
+{
+    PackLayout L;
+    pack_layout(n_vec, n_blocks, vecs, (unsigned)threads, L);
+    if (L.rc) return L.rc;
+    SlabMap M;
+    std::vector<uint32_t> order;
+    for (uint32_t k = 0; k < n_slabs; ++k) order.push_back(k);
+    for (size_t a = 0; a < order.size(); ++a) for (size_t b = a + 1; b < order.size(); ++b)
+        if ((uintptr_t)slabs[order[b]].base < (uintptr_t)slabs[order[a]].base) { uint32_t t = order[a]; order[a] = order[b]; order[b] = t; }
+    uint64_t total = 0;
+    for (uint32_t k : order) {
+        M.base.push_back((uint64_t)(uintptr_t)slabs[k].base); M.end.push_back(M.base.back() + slabs[k].bytes);
+        M.dev_off.push_back(total); dev_off[k] = total;
+        total += (slabs[k].bytes + 255ull) & ~255ull;
+    }
+    *mirror_bytes = total;
+    return pack_sources(n_vec, n_blocks, vecs, L, M, (unsigned)threads, src) ? 0 : 1;
+}

@@ -110,6 +110,47 @@ int main()
         CHECK(ds.stale(), "device_set stale() after resize");
         vs[3]->resize(n_bits);
     }
+    {   // bvectors on the page-locked slab allocator (bmb200_alloc.hpp): >= 64 sources go up by slab DMA + device gather
+        typedef bm::b200::slab_bvector sbv;
+        std::vector<std::unique_ptr<sbv>> ss; std::vector<const sbv*> sp;
+        std::mt19937_64 r2(777);
+        for (int k = 0; k < 80; ++k) {
+            ss.emplace_back(new sbv());
+            std::geometric_distribution<unsigned> skip(0.3 / (k + 1));
+            for (uint64_t p = skip(r2); p < n_bits; p += 1 + skip(r2)) ss.back()->set_bit_no_check((sbv::size_type)p);
+            if (k % 5 == 3) ss.back()->set_range(70000, 270000);
+            if (k >= 10) { BM_DECLARE_TEMP_BLOCK(tb) ss.back()->optimize(tb, sbv::opt_compress); }
+            sp.push_back(ss.back().get());
+        }
+        CHECK(bm::b200::slab_heap::instance().slab_count() >= 1, "slab heap in use");
+        bm::aggregator<sbv> ref; ref.set_optimization(sbv::opt_compress);
+        bm::b200::aggregator<sbv> gpu(ctx); gpu.set_optimization(sbv::opt_compress);
+        {   // cold calls: every call uploads (80 sources: slab road; 9 sources: packing road)
+            for (size_t n : {size_t(9), sp.size()}) {
+                sbv t_ref, t_gpu; ref.combine_or(t_ref, sp.data(), n); gpu.combine_or(t_gpu, sp.data(), n);
+                CHECK(t_ref.compare(t_gpu) == 0 && t_ref.count() == t_gpu.count(), "slab_bvector cold combine_or n=%zu", n);
+            }
+            sbv t_ref, t_gpu;
+            bool f1 = ref.combine_and_sub(t_ref, sp.data(), 2, sp.data() + 2, sp.size() - 2, false);
+            bool f2 = gpu.combine_and_sub(t_gpu, sp.data(), 2, sp.data() + 2, sp.size() - 2, false);
+            CHECK(f1 == f2 && t_ref.compare(t_gpu) == 0, "slab_bvector cold combine_and_sub");
+        }
+        bm::b200::device_set<sbv> ds(ctx);
+        ds.assign(sp.data(), sp.size());
+        gpu.set_device_set(&ds);
+        for (int rep = 0; rep < 2; ++rep) {
+            sbv t_ref, t_gpu;
+            ref.combine_or(t_ref, sp.data() + rep, sp.size() - rep); gpu.combine_or(t_gpu, sp.data() + rep, sp.size() - rep);
+            CHECK(t_ref.compare(t_gpu) == 0, "slab_bvector resident combine_or rep=%d", rep);
+            sbv::statistics s1, s2; t_ref.calc_stat(&s1); t_gpu.calc_stat(&s2);
+            CHECK(s1.bit_blocks == s2.bit_blocks && s1.gap_blocks == s2.gap_blocks, "slab_bvector resident kinds rep=%d", rep);
+            bool f1 = ref.combine_and_sub(t_ref, sp.data(), 3, sp.data() + 3 + rep, sp.size() - 3 - rep, false);
+            bool f2 = gpu.combine_and_sub(t_gpu, sp.data(), 3, sp.data() + 3 + rep, sp.size() - 3 - rep, false);
+            CHECK(f1 == f2 && t_ref.compare(t_gpu) == 0, "slab_bvector resident combine_and_sub rep=%d", rep);
+        }
+        ds.release();
+        bmb200_ctx_trim(ctx.get());
+    }
     {   // member forms with add()/reset(), as samples/bvsample16/sample16.cpp uses them
         bm::aggregator<bvect> ref; bm::b200::aggregator<bvect> gpu(ctx);
         for (int k = 0; k < 3; ++k) { ref.add(all[k]); gpu.add(all[k]); }

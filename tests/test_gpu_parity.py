@@ -899,13 +899,37 @@ def test_upload_vectors_pipeline_many_chunks_and_threads(ctx):
     ctx.set_tuning(bm.capi.TUNE_HOST_THREADS, 0)
 
 
-def test_e2e_harness_real_bvectors_cold_warm_and_check(ctx):
+def test_upload_slabs_dma_plus_device_gather_equals_host_packing(ctx):
+    """bmb200_set_upload_slabs: blocks that live inside a few host slabs (what a slab-backed bm::bvector<> allocator holds) cross
+    PCIe as they lie and are gathered into the arena on the device -- the arena must equal the host-packed one byte for byte
+    (descriptors, prefix sums, bit pool, FLAT GAP pool incl. lead pads and zero fill), pinned or pageable slabs, with and without
+    the prefetch; a block outside every slab makes the call fall back to the packing path (same result)."""
+    rng = np.random.default_rng(11)
+    vecs = gen.mixed_vectors(rng, 70, 40, p_null=0.05)
+    ps = bm.PackedSet.pack(vecs)
+    launches0 = ctx.launch_count()
+    for kw in (dict(pinned=True), dict(pinned=False, slab_bytes=300_000), dict(pinned=True, prefetch=True, slab_bytes=4 << 20), dict(pinned=False, stray=True)):
+        dset = bm.DeviceSet.upload_slabs(ctx, vecs, **kw)
+        back = dset.download()
+        for a in ("desc", "bit_base", "gap_base", "bit_pool", "gap_pool"):
+            assert np.array_equal(getattr(back, a), getattr(ps, a)), f"{a} ({kw})"
+        check_vs_oracle(ctx, ps, bm.OP_AND_SUB, [0, 1, 2], list(range(3, 70)), C, dset)
+        check_vs_oracle(ctx, ps, bm.OP_OR, list(range(70)), None, C, dset)
+        dset.free()
+    assert ctx.launch_count() > launches0
+    ctx.trim()
+
+
+@pytest.mark.parametrize("flavour", ["e2e", "e2e_slab"])
+def test_e2e_harness_real_bvectors_cold_warm_and_check(ctx, flavour):
     """oracle/_ref/libbmb200_e2e.so (bench.py's e2e leg): bm::b200::aggregator on real bm::bvector<> objects -- cold call, warm call
-    on a bm::b200::device_set, and the reference aggregator on the same bvectors (compare() == 0 + calc_stat kinds)."""
+    on a bm::b200::device_set, and the reference aggregator on the same bvectors (compare() == 0 + calc_stat kinds).
+    libbmb200_e2e_slab.so is the same harness on bm::b200::slab_bvector (page-locked slab allocator; cold upload = slab DMA +
+    device gather)."""
     import ctypes as Ct
-    so = orclib.ORACLE_DIR / "_ref" / "libbmb200_e2e.so"
+    so = orclib.ORACLE_DIR / "_ref" / f"libbmb200_{flavour}.so"
     if not so.exists():
-        pytest.skip("oracle/_ref/libbmb200_e2e.so not built (needs /root/reference at build time)")
+        pytest.skip(f"oracle/_ref/{so.name} not built (needs /root/reference at build time)")
     lib = Ct.CDLL(str(so)); lib.e2e_create_empty.restype = Ct.c_void_p; lib.e2e_free.restype = None
     nv, nbk = 96, 2304                                   # 9 top-level blocks: the result store runs on several host threads (>= 2048 columns)
     dens = np.array([0.5 / (k + 1) for k in range(nv)]); seed = np.arange(1000, 1000 + nv, dtype=np.uint64)

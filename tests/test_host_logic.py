@@ -1,5 +1,6 @@
 """Host-side containers (numpy only): packing, GAP encode/decode, compare; checked against the oracle."""
 import numpy as np
+import pytest
 
 import bitmagic_b200 as bm
 from bitmagic_b200 import hostfmt as hf
@@ -76,6 +77,76 @@ def _vec_blocks_c(vectors, n_blocks):
         keep += [kind, ptrs]
         arr[i] = VecBlocksC(v.n_blocks, ptr(kind), ptr(ptrs))
     return arr, keep
+
+
+def test_slab_upload_source_table_host_build():
+    """bmb200_set_upload_slabs, host half (csrc/host_pack.hpp pack_sources via oracle/host_pack_check.cpp): blocks laid into a few
+    64-byte aligned host slabs; the source table must point at every block's bytes inside the mirror (slabs sorted by address,
+    256-byte steps), and a block outside the slabs / a misaligned one must be reported (the product then packs on the host)."""
+    import ctypes as C
+    import subprocess
+    from bitmagic_b200.capi import HostSlabC, VecBlocksC, ptr
+    so = orclib.ORACLE_DIR / "libhostpack.so"
+    subprocess.run(["make", "-C", str(orclib.ORACLE_DIR), str(so)], check=True, capture_output=True)
+    lib = C.CDLL(str(so))
+    rng = np.random.default_rng(3)
+    vecs = gen.mixed_vectors(rng, 11, 17, p_null=0.1)
+    nv, nb = len(vecs), 17
+    raw = [np.zeros(200_000 + 64, np.uint8) for _ in range(40)]
+    slabs = []
+    for r in raw:
+        off = (-r.ctypes.data) % 64
+        slabs.append([r.ctypes.data + off, r[off:off + 200_000], 0])
+    cur = 0
+    arr = (VecBlocksC * nv)(); keep = []; where = {}
+    for i, v in enumerate(vecs):
+        kind = np.ascontiguousarray(v.kind, dtype=np.uint8); ptrs = np.zeros(nb, np.uint64)
+        for c in range(v.n_blocks):
+            if kind[c] in (bm.BLK_BIT, bm.BLK_GAP):
+                b = np.ascontiguousarray(v.blocks[c]).view(np.uint8); need = (b.size + 63) & ~63
+                if slabs[cur][1].size - slabs[cur][2] < need:
+                    cur += 1
+                sl = slabs[cur]; sl[1][sl[2]:sl[2] + b.size] = b; ptrs[c] = sl[0] + sl[2]; where[(c, i)] = b.copy(); sl[2] += need
+        keep += [kind, ptrs]; arr[i] = VecBlocksC(nb, ptr(kind), ptr(ptrs))
+    used = [sl for sl in slabs if sl[2]]
+    rng.shuffle(used)                                       # the caller's slab order is arbitrary
+    carr = (HostSlabC * len(used))()
+    for k, sl in enumerate(used):
+        carr[k].base = sl[0]; carr[k].bytes = sl[2]
+    for threads in (1, 4):
+        src = np.zeros(nv * nb, np.uint32); dev_off = np.zeros(len(used), np.uint64); total = C.c_uint64(0)
+        assert lib.host_pack_sources(nv, nb, arr, threads, carr, len(used), ptr(src), ptr(dev_off), C.byref(total)) == 0
+        mirror = np.zeros(total.value, np.uint8)
+        for k, sl in enumerate(used):
+            assert int(dev_off[k]) % 256 == 0
+            mirror[int(dev_off[k]):int(dev_off[k]) + sl[2]] = sl[1][:sl[2]]
+        order = np.argsort([sl[0] for sl in used])
+        assert all(dev_off[order[k]] < dev_off[order[k + 1]] for k in range(len(used) - 1)), "mirror follows address order"
+        for (c, i), b in where.items():
+            o = int(src[c * nv + i]) * 32
+            assert np.array_equal(mirror[o:o + b.size], b), f"block ({c},{i})"
+    # one block outside every slab / one misaligned pointer: reported, not mis-copied
+    kind0 = keep[0]; ptrs0 = keep[1]
+    c0 = int(np.flatnonzero((kind0 == bm.BLK_BIT) | (kind0 == bm.BLK_GAP))[0])
+    saved = int(ptrs0[c0])
+    stray = np.ascontiguousarray(vecs[0].blocks[c0]); ptrs0[c0] = stray.ctypes.data
+    src = np.zeros(nv * nb, np.uint32); dev_off = np.zeros(len(used), np.uint64); total = C.c_uint64(0)
+    assert lib.host_pack_sources(nv, nb, arr, 2, carr, len(used), ptr(src), ptr(dev_off), C.byref(total)) == 1
+    if kind0[c0] == bm.BLK_GAP:
+        ptrs0[c0] = saved + 2
+        assert lib.host_pack_sources(nv, nb, arr, 2, carr, len(used), ptr(src), ptr(dev_off), C.byref(total)) == 1
+    ptrs0[c0] = saved
+
+
+def test_slab_allocator_under_bvector_traffic():
+    """bm::b200::slab_bvector (bmb200_alloc.hpp) next to bm::bvector<> on the same operations, 8 threads: equal contents and
+    block kinds, every block inside the heap's slabs and 64-byte aligned, freed blocks reused (oracle/slab_heap_check.cpp)."""
+    import subprocess
+    exe = orclib.ORACLE_DIR / "_ref" / "slab_heap_check"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/slab_heap_check not built (needs /root/reference at build time)")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
 
 
 def test_upload_packer_host_build_matches_packedset():
