@@ -393,8 +393,8 @@ def run_e2e(args, ctx, dset, device, world, dist, torch, op, g0, g1, flags, tota
         build_s = time.perf_counter() - t0
         nsl, sbytes = C.c_uint64(0), C.c_uint64(0)
         es.lib.e2e_slab_info(C.byref(nsl), C.byref(sbytes))
-        sms = np.zeros(args.e2e_steps + 1); scnt = C.c_uint64(0); sh2d = C.c_uint64(0); sd2h = C.c_uint64(0)
-        rc = es.lib.e2e_cold(hs, int(op), compress, ptr(g0), n0, ptr(g1a), n1, int(args.e2e_steps + 1), ptr(sms), C.byref(scnt), C.byref(sh2d), C.byref(sd2h))
+        sms = np.zeros(args.e2e_steps + 2); scnt = C.c_uint64(0); sh2d = C.c_uint64(0); sd2h = C.c_uint64(0)
+        rc = es.lib.e2e_cold(hs, int(op), compress, ptr(g0), n0, ptr(g1a), n1, int(args.e2e_steps + 2), ptr(sms), C.byref(scnt), C.byref(sh2d), C.byref(sd2h))
         assert rc == 0, "e2e_cold (slab allocator) failed"
         assert scnt.value == total_bits, f"e2e (cold, slab allocator) result count {scnt.value} != device-resident run {total_bits}"
         sa_ms, sg_ms = C.c_double(0), C.c_double(0)
@@ -407,7 +407,7 @@ def run_e2e(args, ctx, dset, device, world, dist, torch, op, g0, g1, flags, tota
             assert rc == 0 and eq.value, "slab_bvector result differs from bm::aggregator on the same bvectors"
             seq = bool(eq.value)
         es.lib.e2e_free(hs)
-        scold = float(np.mean(sms[1:]))
+        scold = float(np.mean(sms[2:]))        # step 0 allocates (result blocks come from the slab heap too: it grows once), step 1 re-sizes the device mirror for that
         slab = {"value": src_blocks_all / (scold * 1e-3), "unit": "blocks/s", "ms_per_step": scold, "host_slabs": int(nsl.value),
                 "h2d_bytes_per_step": int(sbytes.value) + 8 * dset.n_vec * dset.n_blocks, "h2d_gbs": sbytes.value / scold / 1e6,
                 "split_ms": {"device_set_assign(slab DMA | walk+layout, gather kernel)": sa_ms.value, "aggregate_on_resident(kernel+D2H+bvector)": sg_ms.value},

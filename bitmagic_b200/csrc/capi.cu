@@ -58,8 +58,10 @@ struct bmb200_ctx {
     size_t d_pool_cap[8] = {};
     std::vector<std::pair<uint64_t, uint64_t>> mirror_sig;   // slab list (base, bytes) whose copies into d_pool[6] were queued last
     bool mirror_live = false;               // ... by bmb200_host_slabs_prefetch, not yet consumed by an upload
-    void* h_pool[6] = {};                   // grow-only pinned scratch of the same entry points
-    size_t h_pool_cap[6] = {};
+    void* h_pool[8] = {};                   // grow-only pinned scratch of the same entry points
+    size_t h_pool_cap[8] = {};
+    cudaEvent_t fetch_ev[8] = {};           // one per D2H chunk of bmb200_result_fetch_view_async
+    unsigned fetch_flip = 0;                // bmb200_result_fetch_view alternates between two pinned block buffers (see there)
     CommState comm;                         // multi-GPU exchange (bmb200_comm_*), unused on one GPU
     // ONE recycled device arena: bmb200_set_free parks the arrays of the last freed set here and the next set_alloc that fits takes
     // them, so that a cold upload per call (no residency) does not pay cudaMalloc + cudaFree of a multi-GB arena (25 - 230 ms) each time;
@@ -89,6 +91,7 @@ struct bmb200_result {
     uint8_t*  kind = nullptr;
     uint16_t* gaps = nullptr;
     unsigned long long* total = nullptr;
+    uint32_t fetch_chunk_cols = 0, fetch_chunks = 0;   // bmb200_result_fetch_view_async: columns per D2H chunk, chunks in flight
 };
 
 struct bmb200_rs {
@@ -277,6 +280,7 @@ int bmb200_destroy(bmb200_ctx* ctx)
     for (void* q : ctx->d_pool) if (q) cudaFree(q);
     for (void* q : ctx->h_pool) if (q) cudaFreeHost(q);
     for (uint32_t k = 0; k < kStageSlots; ++k) { if (ctx->h_ring[k]) cudaFreeHost(ctx->h_ring[k]); if (ctx->ring_ev[k]) cudaEventDestroy(ctx->ring_ev[k]); }
+    for (cudaEvent_t ev : ctx->fetch_ev) if (ev) cudaEventDestroy(ev);
     comm_release(ctx);
     delete ctx;
     return BMB200_OK;
@@ -532,7 +536,7 @@ static int mirror_begin(bmb200_ctx* ctx, const bmb200_host_slab* slabs, uint32_t
     if (M.base.empty() || mirror_bytes > (128ull << 30)) return BMB200_OK;         // caller falls back to host packing
     CU(cudaSetDevice(ctx->device));
     uint8_t* mirror = nullptr;
-    int rc = pool_dev(ctx, 6, mirror_bytes + 64, (void**)&mirror);
+    int rc = pool_dev(ctx, 6, mirror_bytes + mirror_bytes / 16 + 64, (void**)&mirror);      // headroom: a heap that grew by a slab does not force a re-allocation
     if (rc) return rc;
     *mirror_out = mirror;
     if (ctx->mirror_live && ctx->mirror_sig == sig) { ctx->mirror_live = false; return BMB200_OK; }      // prefetched by bmb200_host_slabs_prefetch
@@ -1535,8 +1539,8 @@ int bmb200_result_fetch(bmb200_result* r, uint8_t* kind_out, uint64_t* off_out, 
     return BMB200_OK;
 }
 
-int bmb200_result_fetch_view(bmb200_result* r, const uint8_t** kind_out, const uint64_t** off_out, const uint32_t** bits_out,
-                             const uint16_t** gaps_out, uint64_t* n_bit_blocks, uint64_t* n_gap_words, uint64_t* total_out)
+static int fetch_view_impl(bmb200_result* r, const uint8_t** kind_out, const uint64_t** off_out, const uint32_t** bits_out,
+                           const uint16_t** gaps_out, uint64_t* n_bit_blocks, uint64_t* n_gap_words, uint64_t* total_out, bool async)
 {
     if (!r || !r->has_blocks || !kind_out || !off_out || !bits_out || !gaps_out) return BMB200_ERR_BADARG;
     bmb200_ctx* ctx = r->ctx;
@@ -1551,7 +1555,11 @@ int bmb200_result_fetch_view(bmb200_result* r, const uint8_t** kind_out, const u
     CU(cudaMemcpyAsync(kind, r->kind, n, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(nruns, r->nruns, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(tot, r->total, 8 * (size_t)r->n_groups, cudaMemcpyDeviceToHost, ctx->stream));
+    static const bool trace = getenv("BMB200_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double w0 = trace ? now() : 0;
     CU(cudaStreamSynchronize(ctx->stream));
+    const double w1 = trace ? now() : 0;
     uint64_t nb = 0, ng = 0;
     for (size_t c = 0; c < n; ++c) {
         off[c] = 0;
@@ -1563,20 +1571,70 @@ int bmb200_result_fetch_view(bmb200_result* r, const uint8_t** kind_out, const u
         uint64_t* d_off = nullptr; uint32_t* d_bits = nullptr; uint16_t* d_gaps = nullptr;
         if ((rc = pool_dev(ctx, 0, n * 8, (void**)&d_off)) || (rc = pool_dev(ctx, 1, (size_t)nb * BMB200_BLOCK_BYTES + 16, (void**)&d_bits)) ||
             (rc = pool_dev(ctx, 2, (size_t)ng * 2 + 16, (void**)&d_gaps)) ||
-            (rc = pool_host(ctx, 3, (size_t)nb * BMB200_BLOCK_BYTES + 16, (void**)&hb)) || (rc = pool_host(ctx, 4, (size_t)ng * 2 + 16, (void**)&hg))) return rc;
+            false) return rc;
+        // two pinned buffers, used in turn: the caller's threads have just READ the previous call's blocks, which parks those lines in
+        // their private L2 caches, and a DMA write into lines cached by many cores has to snoop every one of them (measured on the
+        // 2-socket Xeon of the B200 box: 24 MB D2H in 0.55 ms into cold lines, 1.6 ms into lines last read by 8 cores)
+        const int fb = (ctx->fetch_flip ^= 1u) ? 6 : 3, fg = fb + 1;
+        if ((rc = pool_host(ctx, fb, (size_t)nb * BMB200_BLOCK_BYTES + 16, (void**)&hb)) || (rc = pool_host(ctx, fg, (size_t)ng * 2 + 16, (void**)&hg))) return rc;
         CU(cudaMemcpyAsync(d_off, off, n * 8, cudaMemcpyHostToDevice, ctx->stream));
         uint32_t grid = (uint32_t)ctx->sm_count * 8u; if (grid > r->n_cols) grid = r->n_cols;
         result_compact_kernel<<<grid, 256, 0, ctx->stream>>>(r->blocks, r->gaps, r->kind, d_off, d_bits, d_gaps, r->n_cols);
         if ((rc = after_launch(ctx))) return rc;
-        if (nb) CU(cudaMemcpyAsync(hb, d_bits, (size_t)nb * BMB200_BLOCK_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
-        if (ng) CU(cudaMemcpyAsync(hg, d_gaps, (size_t)ng * 2, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-    }
+        r->fetch_chunks = 0;
+        if (!async) {
+            if (nb) CU(cudaMemcpyAsync(hb, d_bits, (size_t)nb * BMB200_BLOCK_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+            if (ng) CU(cudaMemcpyAsync(hg, d_gaps, (size_t)ng * 2, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        } else {
+            // the blocks come back in up to 8 column chunks, each followed by an event: the caller starts on the first columns
+            // while the later ones are still crossing PCIe (bmb200_result_fetch_wait)
+            const uint32_t nch = n >= 2048 ? 8u : 1u, cc = (uint32_t)((n + nch - 1) / nch);
+            uint64_t b0 = 0, g0 = 0;
+            for (uint32_t c = 0; c < nch; ++c) {
+                const size_t c1 = std::min<size_t>(n, (size_t)(c + 1) * cc);
+                uint64_t b1 = b0, g1 = g0;                                        // first block / GAP word past this chunk
+                for (size_t k = (size_t)c * cc; k < c1; ++k) {
+                    if (kind[k] == BMB200_BLK_BIT) b1 = off[k] + 1;
+                    else if (kind[k] == BMB200_BLK_GAP) g1 = off[k] + ((uint64_t)nruns[k] + 1 + kGapUnit - 1) / kGapUnit * kGapUnit;
+                }
+                if (b1 > b0) CU(cudaMemcpyAsync(hb + b0 * kBlockWords, d_bits + b0 * kBlockWords, (size_t)(b1 - b0) * BMB200_BLOCK_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+                if (g1 > g0) CU(cudaMemcpyAsync(hg + g0, d_gaps + g0, (size_t)(g1 - g0) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+                if (!ctx->fetch_ev[c]) CU(cudaEventCreateWithFlags(&ctx->fetch_ev[c], cudaEventDisableTiming));
+                CU(cudaEventRecord(ctx->fetch_ev[c], ctx->stream));
+                b0 = b1; g0 = g1;
+            }
+            r->fetch_chunk_cols = cc; r->fetch_chunks = nch;
+        }
+    } else r->fetch_chunks = 0;
+    if (trace) fprintf(stderr, "[bmb200] result_fetch_view: waited %.3f ms for the kernel + column kinds, %.3f ms for compaction + D2H of %.1f MB\n",
+                       w1 - w0, now() - w1, (nb * (double)BMB200_BLOCK_BYTES + ng * 2.0) / 1048576.0);
     *kind_out = kind; *off_out = off; *bits_out = hb; *gaps_out = hg;
     if (n_bit_blocks) *n_bit_blocks = nb;
     if (n_gap_words) *n_gap_words = ng;
     if (total_out) { uint64_t t = 0; for (uint32_t g = 0; g < r->n_groups; ++g) t += tot[g]; *total_out = t; }
     return BMB200_OK;
+}
+
+int bmb200_result_fetch_view(bmb200_result* r, const uint8_t** kind_out, const uint64_t** off_out, const uint32_t** bits_out,
+                             const uint16_t** gaps_out, uint64_t* n_bit_blocks, uint64_t* n_gap_words, uint64_t* total_out)
+{
+    return fetch_view_impl(r, kind_out, off_out, bits_out, gaps_out, n_bit_blocks, n_gap_words, total_out, false);
+}
+
+int bmb200_result_fetch_view_async(bmb200_result* r, const uint8_t** kind_out, const uint64_t** off_out, const uint32_t** bits_out,
+                                   const uint16_t** gaps_out, uint64_t* n_bit_blocks, uint64_t* n_gap_words, uint64_t* total_out)
+{
+    return fetch_view_impl(r, kind_out, off_out, bits_out, gaps_out, n_bit_blocks, n_gap_words, total_out, true);
+}
+
+int bmb200_result_fetch_wait(bmb200_result* r, uint32_t col)
+{
+    if (!r) return BMB200_ERR_BADARG;
+    if (!r->fetch_chunks) return BMB200_OK;                       // nothing in flight (empty result or the synchronous call)
+    uint32_t c = r->fetch_chunk_cols ? col / r->fetch_chunk_cols : 0u;
+    if (c >= r->fetch_chunks) c = r->fetch_chunks - 1;
+    return cudaEventSynchronize(r->ctx->fetch_ev[c]) == cudaSuccess ? BMB200_OK : BMB200_ERR_CUDA;
 }
 
 int bmb200_result_device_ptrs(const bmb200_result* r, void** blocks, void** popcnt, void** digest, void** flag, uint32_t* n_cols)

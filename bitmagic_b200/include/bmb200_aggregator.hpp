@@ -91,9 +91,12 @@ uint32_t blocks_of(const BV& bv)
 /// the same target then costs one memcpy per block instead of a free + malloc pair (16 384 GAP blocks: 7 ms -> ~1 ms on one core).
 /// Large results are stored by a few host threads, each owning whole top-level sub-trees (disjoint i): the block manager's
 /// per-(i,j) calls touch nothing shared once the top array is reserved and no allocator pool is attached.
+/// `landed` != 0: the blocks are still arriving (bmb200_result_fetch_view_async); every thread waits for the last column of a
+/// top-level sub-tree before it reads that sub-tree's blocks, so the store of the first columns overlaps the D2H of the rest.
 template<class BV>
 void store_result(BV& target, typename BV::size_type new_size, uint32_t n_cols,
-                  const uint8_t* kind, const uint64_t* off, const uint32_t* bits, const uint16_t* gaps, uint32_t nb_off = 0)
+                  const uint8_t* kind, const uint64_t* off, const uint32_t* bits, const uint16_t* gaps, uint32_t nb_off = 0,
+                  bmb200_result* landed = nullptr)
 {
     typedef typename BV::blocks_manager_type bman_type;
     if (target.is_ro() || !target.get_blocks_manager().is_init() || target.size() != new_size)
@@ -125,6 +128,7 @@ void store_result(BV& target, typename BV::size_type new_size, uint32_t n_cols,
         bool any = false;
         for (uint32_t nb = nb0; nb < nb1; ++nb) if (kind[nb - nb_off] != BMB200_BLK_NULL) { any = true; break; }
         if (!any) { drop_top(i); return; }
+        if (landed && bmb200_result_fetch_wait(landed, nb1 - 1u - nb_off) != BMB200_OK) throw std::runtime_error("bmb200_result_fetch_wait");
         bm::word_t** sub = bman.check_alloc_top_subblock(i);        // (expands a FULL top-level entry into 256 FULL pointers)
         for (unsigned j = 0; j < bm::set_sub_array_size; ++j)
         {
@@ -168,7 +172,10 @@ void store_result(BV& target, typename BV::size_type new_size, uint32_t n_cols,
     };
     unsigned T = 1;
     if (n_cols >= 2048u && !bman.get_allocator().get_pool())
-    { T = std::thread::hardware_concurrency(); if (!T) T = 1; if (T > 8) T = 8; if (T > i_hi - i_lo + 1u) T = i_hi - i_lo + 1u; }
+    {
+        static const unsigned want = []() { const char* e = getenv("BMB200_STORE_THREADS"); return e ? (unsigned)atoi(e) : 0u; }();
+        T = want ? want : std::thread::hardware_concurrency(); if (!T) T = 1; if (T > 8 && !want) T = 8; if (T > i_hi - i_lo + 1u) T = i_hi - i_lo + 1u;
+    }
     auto work = [&](unsigned t)
     {
         BM_DECLARE_TEMP_BLOCK(tb)
@@ -468,15 +475,19 @@ private:
                           g0_.data(), (uint32_t)n0, n1 ? g1_.data() : nullptr, (uint32_t)n1, 0, 0};
         // the result object (device buffers for every column) is recycled from call to call; the fetched blocks arrive in pinned
         // memory owned by the context (bmb200_result_fetch_view): a warm call allocates nothing on either side
+        // The blocks come back in column chunks (bmb200_result_fetch_view_async): the store of the first columns runs under the
+        // D2H of the rest.  Whatever happens, nothing stays in flight and a per-call set is freed when this scope ends.
+        struct drain { bmb200_result*& r; uint32_t last; bmb200_set* set;
+                       ~drain() { if (r) bmb200_result_fetch_wait(r, last); if (set) bmb200_set_free(set); } }
+            guard{res_, n_blocks_ ? n_blocks_ - 1u : 0u, own ? set : nullptr};
         int rc = bmb200_aggregate(ctx_.get(), set, &a, &res_);
         uint64_t total = 0, nb = 0, ng = 0;
         const uint8_t* kind = nullptr; const uint64_t* off = nullptr; const uint32_t* bits = nullptr; const uint16_t* gaps = nullptr;
-        if (!rc) rc = bmb200_result_fetch_view(res_, &kind, &off, &bits, &gaps, &nb, &ng, &total);
-        if (own) { int rc2 = bmb200_set_free(set); if (!rc) rc = rc2; }
+        if (!rc) rc = bmb200_result_fetch_view_async(res_, &kind, &off, &bits, &gaps, &nb, &ng, &total);
         check(rc, "bmb200_aggregate");
         last_d2h_ = (uint64_t)n_blocks_ * 5u + 8u + nb * (uint64_t)BMB200_BLOCK_BYTES + ng * 2u;
         const double t2 = trace ? now() : 0;
-        detail::store_result(target, max_size_, n_blocks_, kind, off, bits, gaps, nb_off_);
+        detail::store_result(target, max_size_, n_blocks_, kind, off, bits, gaps, nb_off_, res_);
         if (trace) fprintf(stderr, "[bmb200] aggregator::run: bind %.3f ms, aggregate + fetch (%llu bit-blocks, %llu GAP words) %.3f ms, store into the target %.3f ms\n",
                            t1 - t0, (unsigned long long)nb, (unsigned long long)ng, t2 - t1, now() - t2);
         return total != 0;

@@ -294,6 +294,13 @@ int bmb200_result_fetch(bmb200_result* res, uint8_t* kind, uint64_t* off,
  * ends with: bm::b200::aggregator materialises its target bvector from these views. */
 int bmb200_result_fetch_view(bmb200_result* res, const uint8_t** kind, const uint64_t** off, const uint32_t** bits,
                              const uint16_t** gaps, uint64_t* n_bit_blocks, uint64_t* n_gap_words, uint64_t* total);
+/* the same views, handed out as soon as kind[] / off[] are known: the blocks are still arriving, in column order, in up to 8
+ * chunks.  bmb200_result_fetch_wait(res, col) returns once every block of the columns [0, col] has landed (callable from several
+ * threads); the caller then reads bits / gaps of those columns.  bm::b200::aggregator stores the first columns into the target
+ * bvector while the last ones are still crossing PCIe.  Wait for the last column before the next fetch on this context. */
+int bmb200_result_fetch_view_async(bmb200_result* res, const uint8_t** kind, const uint64_t** off, const uint32_t** bits,
+                                   const uint16_t** gaps, uint64_t* n_bit_blocks, uint64_t* n_gap_words, uint64_t* total);
+int bmb200_result_fetch_wait(bmb200_result* res, uint32_t col);
 /* device addresses: blocks [n_cols][2048] u32, popcnt [n_cols] u32, digest [n_cols] u64, flag [n_cols] u8 */
 int bmb200_result_device_ptrs(const bmb200_result* res, void** blocks, void** popcnt,
                               void** digest, void** flag, uint32_t* n_cols);

@@ -15,6 +15,7 @@
 #include <chrono>
 #include <malloc.h>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <thread>
@@ -193,7 +194,9 @@ int e2e_warm(void* hv, int op, int compress, const uint32_t* g0, uint32_t n0, co
         bm::b200::aggregator<bvect> agg(*h->ctx);
         agg.set_device_set(&ds);
         for (int k = 0; k < warmup; ++k) call(agg, op, compress != 0, h->last, g);
+        std::vector<char> thrash(getenv("E2E_THRASH") ? (size_t)atoi(getenv("E2E_THRASH")) << 20 : 0);   /* diagnostic: evict the CPU caches between calls (untimed) */
         for (int k = 0; k < steps; ++k) {
+            if (!thrash.empty()) memset(thrash.data(), k, thrash.size());
             const double t0 = now_ms();
             call(agg, op, compress != 0, h->last, g);
             ms[k] = now_ms() - t0;
