@@ -464,15 +464,17 @@ def timed_resident(args, bm, torch, ctx, dset, op, g0, g1, flags, world, dist, d
     res = bm.aggregate(ctx, dset, op, g0, g1, flags)     # allocates the result buffers once
     ctx.sync()
 
+    exchange = world > 1 and not os.environ.get("BENCH_NO_EXCHANGE")     # (diagnostic switch: the N>1 line always runs the exchange)
+
     def step():
         bm.aggregate(ctx, dset, op, g0, g1, flags, result=res)
-        if world > 1:
+        if exchange:
             ctx.exchange_popcounts(res)                  # side stream: overlaps the next step's kernel
 
     l0 = ctx.launch_count()
     for _ in range(args.warmup):
         step()
-    if world > 1:
+    if exchange:
         ctx.exchange_fence()
     torch.cuda.synchronize(dev)
     launches_per_step = (ctx.launch_count() - l0) // args.warmup
@@ -491,9 +493,9 @@ def timed_resident(args, bm, torch, ctx, dset, op, g0, g1, flags, world, dist, d
         kev[i][0].record(stream)
         bm.aggregate(ctx, dset, op, g0, g1, flags, result=res)
         kev[i][1].record(stream)
-        if world > 1:
+        if exchange:
             ctx.exchange_popcounts(res)
-    if world > 1:
+    if exchange:
         ctx.exchange_fence()                             # the launching stream waits for every exchange: they are inside the timed region
     ev1.record(stream)
     torch.cuda.synchronize(dev)
@@ -582,9 +584,19 @@ def _main():
     alg_bytes = counts["bit"] * 8192 + gap_words * 2 + res_bytes + n_cols * 12
     xchg = None
     if world > 1:
-        gtot, rtot, _ = ctx.exchange_fetch(world, n_cols, want_popcounts=False)
+        gtot, rtot, gpop = ctx.exchange_fetch(world, n_cols, want_popcounts=True)
         assert int(rtot[rank]) == int(total_bits), "exchange: this rank's cardinality did not come back"
-        xchg = {"global_result_bits": int(gtot), "collective": exchange}
+        assert np.array_equal(gpop[rank], pop_r), "exchange: this rank's per-column popcounts did not come back"
+        tb = torch.tensor([int(total_bits)], dtype=torch.int64, device=dev)
+        dist.all_reduce(tb)                                  # the same sum over torch.distributed's own NCCL communicator
+        assert int(tb.item()) == int(gtot) == int(gpop.astype(np.int64).sum()), "exchange: global cardinality differs from an all_reduce of the rank totals"
+        mode = ctx.exchange_mode()
+        exchange = {2: "bmb200_exchange_popcounts over peer memory: every rank's exchange buffer is mapped by all ranks (CUDA IPC); a small kernel behind the "
+                       "aggregation kernel stores this rank's (columns + 2) u32 row into every peer over NVLink and publishes a sequence number; "
+                       "the last exchange is awaited inside the timed region",
+                    1: "bmb200_exchange_popcounts: one ncclAllGather of (columns + 2) u32 per rank on a side stream, step i's exchange overlaps step "
+                       "i+1's kernel; the last one is fenced inside the timed region"}.get(mode, exchange)
+        xchg = {"global_result_bits": int(gtot), "collective": exchange, "mode": mode, "checked": "own row + all_reduce of the rank totals"}
 
     src_blocks_all = torch.tensor([n_src_blocks], dtype=torch.int64, device=dev)
     if world > 1:

@@ -39,7 +39,7 @@ SYMBOLS = [
     "bmb200_shard_range", "bmb200_comm_unique_id", "bmb200_comm_init", "bmb200_comm_info", "bmb200_comm_destroy",
     "bmb200_exchange_popcounts", "bmb200_exchange_fence", "bmb200_exchange_fetch", "bmb200_ctx_trim", "bmb200_binop",
     "bmb200_set_upload_slabs", "bmb200_host_slabs_prefetch", "bmb200_host_slab_alloc", "bmb200_host_slab_free",
-    "bmb200_result_fetch_view_async", "bmb200_result_fetch_wait",
+    "bmb200_result_fetch_view_async", "bmb200_result_fetch_wait", "bmb200_exchange_mode",
 ]
 OP_SUB = 5
 COMM_ID_BYTES = 128
@@ -219,6 +219,12 @@ class Context:
 
     def exchange_popcounts(self, res: "DeviceResult", cols_per_rank: int = 0):
         self.check(lib().bmb200_exchange_popcounts(res._h, int(cols_per_rank)), "exchange_popcounts")
+
+    def exchange_mode(self) -> int:
+        """0 = no exchange yet, 1 = ncclAllGather on the side stream, 2 = peer-memory pushes (CUDA IPC over NVLink)"""
+        m = C.c_int(0)
+        self.check(lib().bmb200_exchange_mode(self._h, C.byref(m)), "exchange_mode")
+        return m.value
 
     def exchange_fence(self):
         self.check(lib().bmb200_exchange_fence(self._h), "exchange_fence")

@@ -21,6 +21,7 @@
 #include "blob_entropy.cuh"
 #include "host_pack.hpp"
 #include "comm.hpp"
+#include "xchg_kernel.cuh"
 #include <sched.h>
 #include <fstream>
 
@@ -91,6 +92,12 @@ struct bmb200_result {
     uint8_t*  kind = nullptr;
     uint16_t* gaps = nullptr;
     unsigned long long* total = nullptr;
+    // single-group results keep TWO (popcnt[n_cols] | total) buffers back to back and alternate between them while a communicator
+    // is attached: bmb200_exchange_popcounts then sends straight out of the buffer the kernel wrote (no staging copy) while the
+    // next aggregation already fills the other one
+    uint32_t* popcnt_base = nullptr;
+    uint32_t xstride = 0, xflip = 0;
+    bool total_inline = false;
     uint32_t fetch_chunk_cols = 0, fetch_chunks = 0;   // bmb200_result_fetch_view_async: columns per D2H chunk, chunks in flight
 };
 
@@ -167,8 +174,8 @@ void free_set_arrays(bmb200_set* s)
 void free_result_arrays(bmb200_result* r)
 {
     if (!r) return;
-    cudaFree(r->blocks); cudaFree(r->popcnt); cudaFree(r->digest); cudaFree(r->nruns);
-    cudaFree(r->kind); cudaFree(r->gaps); cudaFree(r->total); cudaFree(r->or_blocks);
+    cudaFree(r->blocks); cudaFree(r->popcnt_base ? r->popcnt_base : r->popcnt); cudaFree(r->digest); cudaFree(r->nruns);
+    cudaFree(r->kind); cudaFree(r->gaps); if (!r->total_inline) cudaFree(r->total); cudaFree(r->or_blocks);
 }
 
 // grow-only scratch owned by the context: the hot entry points never call cudaMalloc / cudaMallocHost once warm.
@@ -198,6 +205,81 @@ int pool_host(bmb200_ctx* ctx, int slot, size_t bytes, void** out)
     return BMB200_OK;
 }
 
+// the peer-memory exchange buffer of this rank and its mappings of the other ranks' buffers.  Collective: every rank gets here at
+// the same exchange (or at comm_destroy); its own pushes are complete once its stream is synchronized, and the all-gather below is
+// the barrier after which nobody writes into a buffer that is about to be unmapped / freed.
+void xchg_release(bmb200_ctx* ctx)
+{
+    CommState& c = ctx->comm;
+    if (!c.xbuf) return;
+    cudaStreamSynchronize(ctx->stream);
+    if (c.comm && c.stage[0] && c.gathered[0]) {
+        nccl_api().AllGather(c.stage[0], c.gathered[0], 1, kNcclUint32, c.comm, c.side);
+        const auto t0 = std::chrono::steady_clock::now();               // a peer that is gone must not hang the teardown
+        while (cudaStreamQuery(c.side) == cudaErrorNotReady && std::chrono::steady_clock::now() - t0 < std::chrono::seconds(10))
+            std::this_thread::sleep_for(std::chrono::milliseconds(1));
+    }
+    for (int q = 0; q < c.nranks && q < 64; ++q) if (c.peer_map[q]) { cudaIpcCloseMemHandle(c.peer_map[q]); c.peer_map[q] = nullptr; }
+    cudaFree(c.xbuf); cudaFree(c.d_peers); cudaFree(c.d_err);
+    c.xbuf = nullptr; c.d_peers = nullptr; c.d_err = nullptr; c.direct = false; c.xwords = 0; c.xseq = 0;
+}
+
+// (re)build the peer-memory exchange for rows of `words` u32.  Collective.  On any failure on any rank every rank falls back to the
+// ncclAllGather path (c.direct stays false).
+void xchg_setup(bmb200_ctx* ctx, size_t words)
+{
+    CommState& c = ctx->comm;
+    xchg_release(ctx);
+    // Measured on 2 B200s (profiles/r02/exchange_modes_n2.txt): the all-gather costs ~37 us per 2.33 ms step, the peer-memory push
+    // ~75 us, so ncclAllGather is the default and BMB200_EXCHANGE_DIRECT=1 selects the pushes.
+    if (!getenv("BMB200_EXCHANGE_DIRECT") || c.nranks > 64) return;
+    struct Msg { cudaIpcMemHandle_t h; uint32_t ok; uint32_t pad[3]; };
+    static_assert(sizeof(Msg) % 4 == 0, "message in u32 words");
+    const size_t msg_words = sizeof(Msg) / 4;
+    if (msg_words > words) return;                                   // (the staging buffers carry the handles)
+    Msg mine; memset(&mine, 0, sizeof mine);
+    const size_t bytes = ((size_t)2 * c.nranks * words + (size_t)2 * c.nranks) * 4;
+    bool ok = cudaMalloc((void**)&c.xbuf, bytes) == cudaSuccess && cudaMemset(c.xbuf, 0, bytes) == cudaSuccess &&
+              cudaMalloc((void**)&c.d_peers, sizeof(uint32_t*) * (size_t)c.nranks) == cudaSuccess &&
+              cudaMalloc((void**)&c.d_err, 64) == cudaSuccess && cudaMemset(c.d_err, 0, 64) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.h, c.xbuf) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    mine.ok = ok ? 1u : 0u;
+    std::vector<Msg> all((size_t)c.nranks);
+    auto gather = [&](const Msg& m) -> bool {                        // host-visible all-gather of one Msg per rank through the NCCL buffers
+        if (cudaMemcpy(c.stage[0], &m, sizeof m, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+        if (nccl_api().AllGather(c.stage[0], c.gathered[0], msg_words, kNcclUint32, c.comm, c.side) != 0) return false;
+        if (cudaStreamSynchronize(c.side) != cudaSuccess) return false;
+        return cudaMemcpy(all.data(), c.gathered[0], sizeof(Msg) * (size_t)c.nranks, cudaMemcpyDeviceToHost) == cudaSuccess;
+    };
+    bool gathered = gather(mine);
+    std::vector<uint32_t*> peers((size_t)c.nranks, nullptr);
+    if (gathered) for (int q = 0; q < c.nranks; ++q) ok = ok && all[(size_t)q].ok;
+    if (gathered && ok) {
+        for (int q = 0; q < c.nranks && ok; ++q) {
+            if (q == c.rank) { peers[(size_t)q] = c.xbuf; continue; }
+            void* pmap = nullptr;
+            if (cudaIpcOpenMemHandle(&pmap, all[(size_t)q].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+            c.peer_map[q] = pmap; peers[(size_t)q] = (uint32_t*)pmap;
+        }
+        if (ok) ok = cudaMemcpy(c.d_peers, peers.data(), sizeof(uint32_t*) * (size_t)c.nranks, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    // second round: direct only if EVERY rank mapped every buffer
+    mine.ok = (gathered && ok) ? 1u : 0u;
+    bool all_ok = gather(mine);
+    if (all_ok) for (int q = 0; q < c.nranks; ++q) all_ok = all_ok && all[(size_t)q].ok;
+    if (!all_ok) { xchg_release(ctx); return; }
+    // both kernels run between two launches of the aggregation kernel, which needs the SMs' largest shared-memory carve-out: ask for
+    // the same split, or every step pays two re-partitions of the L1 / shared memory (an SM can only be re-partitioned when idle)
+    static const bool keep = getenv("BMB200_XCHG_DEFAULT_CARVEOUT") == nullptr;
+    if (keep) {
+        cudaFuncSetAttribute(xchg_push_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(xchg_wait_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        cudaGetLastError();
+    }
+    c.direct = true; c.xwords = words; c.xseq = 0;
+}
+
 void comm_release(bmb200_ctx* ctx)
 {
     CommState& c = ctx->comm;
@@ -207,6 +289,7 @@ void comm_release(bmb200_ctx* ctx)
         if (c.done[k]) cudaEventDestroy(c.done[k]);
         cudaFree(c.stage[k]); cudaFree(c.gathered[k]);
     }
+    xchg_release(ctx);
     if (c.comm && nccl_api().CommDestroy) nccl_api().CommDestroy(c.comm);
     if (c.side) cudaStreamDestroy(c.side);
     c = CommState();
@@ -1126,9 +1209,16 @@ static int result_alloc(bmb200_ctx* ctx, uint32_t n_cols, uint32_t n_groups, boo
     if (!r) return BMB200_ERR_BADALLOC;
     r->ctx = ctx; r->n_cols = n_cols; r->n_groups = n_groups; r->cols_per_group = n_cols / n_groups;
     int rc;
-    if ((rc = dev_alloc(ctx, &r->popcnt, n_cols)) || (rc = dev_alloc(ctx, &r->digest, n_cols)) ||
+    if (n_groups == 1) {
+        const uint32_t n_even = (n_cols + 1u) & ~1u;                     // the 64-bit total sits 8-byte aligned behind the popcounts
+        r->xstride = n_even + 2u;
+        if ((rc = dev_alloc(ctx, &r->popcnt_base, (size_t)r->xstride * 2))) { delete r; return rc; }
+        cudaMemsetAsync(r->popcnt_base, 0, (size_t)r->xstride * 2 * 4, ctx->stream);
+        r->popcnt = r->popcnt_base; r->total = reinterpret_cast<unsigned long long*>(r->popcnt_base + n_even); r->total_inline = true;
+    }
+    if ((!r->total_inline && ((rc = dev_alloc(ctx, &r->popcnt, n_cols)) || (rc = dev_alloc(ctx, &r->total, n_groups)))) ||
+        (rc = dev_alloc(ctx, &r->digest, n_cols)) ||
         (rc = dev_alloc(ctx, &r->nruns, n_cols)) || (rc = dev_alloc(ctx, &r->kind, n_cols)) ||
-        (rc = dev_alloc(ctx, &r->total, n_groups)) ||
         (or_target && (rc = dev_alloc(ctx, &r->or_blocks, (size_t)(n_cols / n_groups) * kBlockWords))) ||
         (blocks && (rc = dev_alloc(ctx, &r->blocks, (size_t)n_cols * kBlockWords))) ||
         (gaps && (rc = dev_alloc(ctx, &r->gaps, (size_t)n_cols * kGapMax)))) {
@@ -1194,6 +1284,13 @@ int bmb200_aggregate_batch(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_
         if (rc) return rc;
     }
     r->has_blocks = store; r->compress = compress; r->gaps_ready = false;
+    if (r->total_inline && ctx->comm.comm) {
+        r->xflip ^= 1u;
+        r->popcnt = r->popcnt_base + (size_t)r->xflip * r->xstride;
+        r->total = reinterpret_cast<unsigned long long*>(r->popcnt + (r->xstride - 2u));
+        for (int k = 0; k < 2; ++k)          // an all-gather that still sends out of this buffer (two steps back) goes first
+            if (ctx->comm.pending[k] && ctx->comm.sendbuf[k] == r->popcnt) cudaStreamWaitEvent(ctx->stream, ctx->comm.done[k], 0);
+    }
 
     // member ids + offsets -> device (pinned staging keeps the copy asynchronous; skipped when unchanged)
     const size_t nwords = nmem + 2 * (size_t)ng + 1;
@@ -1773,19 +1870,47 @@ int bmb200_exchange_popcounts(bmb200_result* r, uint32_t cols_per_rank)
             CU(cudaMalloc((void**)&c.gathered[k], words * 4 * (size_t)c.nranks));
         }
         c.cap_cols = n;
+        xchg_setup(ctx, words);
+    }
+    if (c.direct) {
+        // the library's own exchange: this rank's row goes into every peer's buffer by peer stores, right behind the aggregation kernel
+        XchgParams xp{};
+        xp.peers = c.d_peers; xp.nranks = (uint32_t)c.nranks; xp.rank = (uint32_t)c.rank; xp.xwords = (uint32_t)c.xwords;
+        xp.seq = (uint32_t)(++c.xseq); xp.slot = xp.seq & 1u;
+        xp.n_cols = r->n_cols; xp.n = (uint32_t)n; xp.popcnt = r->popcnt; xp.total = r->total; xp.err = c.d_err;
+        xp.timeout_ns = 30ull * 1000000000ull;
+        xchg_push_kernel<<<(unsigned)c.nranks, 256, 0, ctx->stream>>>(xp);
+        int rcl = after_launch(ctx);
+        if (rcl) return rcl;
+        c.cols[xp.slot] = (uint32_t)n; c.seq++;
+        return BMB200_OK;
     }
     const int k = (int)(c.seq & 1u);
-    // slot k was last used by the exchange two steps back: the copy below must not overtake that all-gather
+    // slot k was last used by the exchange two steps back: nothing below may overtake that all-gather
     if (c.pending[k]) CU(cudaStreamWaitEvent(ctx->stream, c.done[k], 0));
-    if (n > r->n_cols) CU(cudaMemsetAsync(c.stage[k] + r->n_cols, 0, (n - r->n_cols) * 4, ctx->stream));     // ragged shards: zero padding
-    CU(cudaMemcpyAsync(c.stage[k], r->popcnt, (size_t)r->n_cols * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(c.stage[k] + n, r->total, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    static const bool no_direct = getenv("BMB200_EXCHANGE_STAGED") != nullptr;
+    const uint32_t* send = c.stage[k];
+    if (r->total_inline && n == r->n_cols && !(n & 1u) && !no_direct)
+        send = r->popcnt;                                       // (popcnt | total) as the kernel wrote them: no staging copy
+    else {
+        if (n > r->n_cols) CU(cudaMemsetAsync(c.stage[k] + r->n_cols, 0, (n - r->n_cols) * 4, ctx->stream));     // ragged shards: zero padding
+        CU(cudaMemcpyAsync(c.stage[k], r->popcnt, (size_t)r->n_cols * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(c.stage[k] + n, r->total, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    c.sendbuf[k] = send;
     CU(cudaEventRecord(c.ready[k], ctx->stream));
     CU(cudaStreamWaitEvent(c.side, c.ready[k], 0));
-    const int nrc = nccl_api().AllGather(c.stage[k], c.gathered[k], words, kNcclUint32, c.comm, c.side);
+    const int nrc = nccl_api().AllGather(send, c.gathered[k], words, kNcclUint32, c.comm, c.side);
     if (nrc != 0) { ctx->last_err = std::string("ncclAllGather: ") + nccl_api().GetErrorString(nrc); return BMB200_ERR_CUDA; }
     CU(cudaEventRecord(c.done[k], c.side));
     c.pending[k] = true; c.cols[k] = (uint32_t)n; c.seq++;
+    return BMB200_OK;
+}
+
+int bmb200_exchange_mode(const bmb200_ctx* ctx, int* mode)
+{
+    if (!ctx || !mode) return BMB200_ERR_BADARG;
+    *mode = (!ctx->comm.comm || !ctx->comm.seq) ? 0 : (ctx->comm.direct ? 2 : 1);
     return BMB200_OK;
 }
 
@@ -1793,7 +1918,13 @@ int bmb200_exchange_fence(bmb200_ctx* ctx)
 {
     if (!ctx || !ctx->comm.comm) return BMB200_ERR_BADARG;
     CU(cudaSetDevice(ctx->device));
-    for (int k = 0; k < 2; ++k) if (ctx->comm.pending[k]) CU(cudaStreamWaitEvent(ctx->stream, ctx->comm.done[k], 0));
+    CommState& c = ctx->comm;
+    if (c.direct) {
+        if (!c.xseq) return BMB200_OK;
+        xchg_wait_kernel<<<1, 64, 0, ctx->stream>>>(c.xbuf, (uint32_t)c.nranks, (uint32_t)c.xwords, (uint32_t)(c.xseq & 1u), (uint32_t)c.xseq, c.d_err, 30ull * 1000000000ull);
+        return after_launch(ctx);
+    }
+    for (int k = 0; k < 2; ++k) if (c.pending[k]) CU(cudaStreamWaitEvent(ctx->stream, c.done[k], 0));
     return BMB200_OK;
 }
 
@@ -1802,16 +1933,38 @@ int bmb200_exchange_fetch(bmb200_ctx* ctx, uint64_t* global_total, uint64_t* ran
     if (!ctx || !ctx->comm.comm || !ctx->comm.seq) return BMB200_ERR_BADARG;
     CommState& c = ctx->comm;
     CU(cudaSetDevice(ctx->device));
-    const int k = (int)((c.seq - 1) & 1u);
-    const size_t n = c.cols[k], words = n + 2;
-    CU(cudaEventSynchronize(c.done[k]));
-    if (d_gathered) *d_gathered = c.gathered[k];
+    int k = (int)((c.seq - 1) & 1u);
+    const uint32_t* rows = nullptr;
+    size_t words = 0, n = 0;
+    if (c.direct) {
+        if (!c.xseq) return BMB200_ERR_BADARG;
+        k = (int)(c.xseq & 1u);
+        n = c.cols[k]; words = c.xwords;
+        int rcw = bmb200_exchange_fence(ctx);
+        if (rcw) return rcw;
+        uint32_t err = 0;
+        CU(cudaMemcpyAsync(&err, c.d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (err) { ctx->last_err = "exchange: a peer did not publish its row within 30 s"; return BMB200_ERR_CUDA; }
+        if (getenv("BMB200_TRACE")) {
+            unsigned long long st[4] = {0, 0, 0, 0};
+            cudaMemcpy(st, c.d_err + 2, sizeof st, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[bmb200] exchange (peer memory), last push: flow-control wait %.1f us, row stores + fence %.1f us, flag %.1f us\n",
+                    (st[1] - st[0]) / 1e3, (st[2] - st[1]) / 1e3, (st[3] - st[2]) / 1e3);
+        }
+        rows = c.xbuf + (size_t)k * c.nranks * c.xwords;
+    } else {
+        n = c.cols[k]; words = n + 2;
+        CU(cudaEventSynchronize(c.done[k]));
+        rows = c.gathered[k];
+    }
+    if (d_gathered) *d_gathered = rows;
     if (stride) *stride = (uint32_t)words;
     if (global_total || rank_totals || popcnt) {
         uint32_t* h = nullptr;
         int rc = pool_host(ctx, 1, words * 4 * (size_t)c.nranks, (void**)&h);
         if (rc) return rc;
-        CU(cudaMemcpyAsync(h, c.gathered[k], words * 4 * (size_t)c.nranks, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(h, rows, words * 4 * (size_t)c.nranks, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         uint64_t tot = 0;
         for (int q = 0; q < c.nranks; ++q) {

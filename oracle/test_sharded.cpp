@@ -46,6 +46,7 @@ int main(int argc, char** argv)
     std::vector<std::unique_ptr<bvect>> vs;
     for (int k = 0; k < 12; ++k) {
         vs.emplace_back(new bvect());
+        vs.back()->resize(n_bits);                          // (a default bvector spans 2^32 - 1 bits = 65536 blocks)
         std::geometric_distribution<unsigned> skip(0.002 / (k + 1));
         for (uint64_t p = skip(rng); p < n_bits; p += 1 + skip(rng)) vs.back()->set_bit_no_check((bvect::size_type)p);
         if (k % 4 == 1) vs.back()->set_range(65536u * 300u, 65536u * 302u + 99u);
@@ -77,6 +78,7 @@ int main(int argc, char** argv)
         bvect shard_ref(t_ref); shard_ref &= mask;
         CHECK(shard_ref.compare(t_gpu) == 0, "pass %d: rank %d target != reference restricted to blocks [%u, %u)", pass, rank, from, to);
     }
-    std::printf("%s: rank %d/%d blocks [%u, %u): %d checks, %d failed\n", g_fail ? "FAILED" : "OK", rank, nranks, from, to, g_checks, g_fail);
+    std::printf("%s: rank %d/%d blocks [%u, %u): %d checks, %d failed; exchange mode %d (2 = peer memory, 1 = ncclAllGather)\n",
+                g_fail ? "FAILED" : "OK", rank, nranks, from, to, g_checks, g_fail, sh.exchange_mode());
     return g_fail ? 1 : 0;
 }
