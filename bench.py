@@ -464,7 +464,9 @@ def timed_resident(args, bm, torch, ctx, dset, op, g0, g1, flags, world, dist, d
     res = bm.aggregate(ctx, dset, op, g0, g1, flags)     # allocates the result buffers once
     ctx.sync()
 
-    exchange = world > 1 and not os.environ.get("BENCH_NO_EXCHANGE")     # (diagnostic switch: the N>1 line always runs the exchange)
+    # diagnostic switches (the N>1 line always runs the exchange): BENCH_SELF_EXCHANGE=1 runs the exchange machinery on ONE GPU with a
+    # 1-rank communicator, to separate its stream-level cost from what the peers add
+    exchange = (world > 1 and not os.environ.get("BENCH_NO_EXCHANGE")) or bool(os.environ.get("BENCH_SELF_EXCHANGE"))
 
     def step():
         bm.aggregate(ctx, dset, op, g0, g1, flags, result=res)
@@ -488,6 +490,12 @@ def timed_resident(args, bm, torch, ctx, dset, op, g0, g1, flags, world, dist, d
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # a dedicated event pair around the dominant kernel of every step (aggregate launch only)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        # the host-side barrier above releases the ranks' CPU threads up to a millisecond apart, and with a per-step exchange a rank
+        # that starts late is waited for by all others (measured: 0.7 ms of start skew = 37 us on each of 20 steps).  A device-side
+        # rendezvous right in front of the first event makes every rank's timed region start together on the GPUs.
+        sync_t = torch.zeros(1, device=dev)
+        dist.all_reduce(sync_t)
     ev0.record(stream)
     for i in range(args.steps):
         kev[i][0].record(stream)
@@ -557,6 +565,8 @@ def _main():
     stream = torch.cuda.current_stream(dev)
     ctx.set_stream(stream.cuda_stream)
     exchange = None
+    if world == 1 and os.environ.get("BENCH_SELF_EXCHANGE"):
+        ctx.comm_init(1, 0, bytes(ctx.comm_unique_id()))
     if world > 1:
         # the library's own communicator: rank 0 makes the id, torch.distributed only ships its 128 bytes
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)

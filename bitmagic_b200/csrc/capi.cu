@@ -232,7 +232,7 @@ void xchg_setup(bmb200_ctx* ctx, size_t words)
     xchg_release(ctx);
     // Measured on 2 B200s (profiles/r02/exchange_modes_n2.txt): the all-gather costs ~37 us per 2.33 ms step, the peer-memory push
     // ~75 us, so ncclAllGather is the default and BMB200_EXCHANGE_DIRECT=1 selects the pushes.
-    if (!getenv("BMB200_EXCHANGE_DIRECT") || c.nranks > 64) return;
+    if (!getenv("BMB200_EXCHANGE_DIRECT") || c.nranks > 64 || c.nranks < 2) return;
     struct Msg { cudaIpcMemHandle_t h; uint32_t ok; uint32_t pad[3]; };
     static_assert(sizeof(Msg) % 4 == 0, "message in u32 words");
     const size_t msg_words = sizeof(Msg) / 4;
@@ -284,7 +284,7 @@ void comm_release(bmb200_ctx* ctx)
 {
     CommState& c = ctx->comm;
     if (c.side) cudaStreamSynchronize(c.side);
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < CommState::kSlots; ++k) {
         if (c.ready[k]) cudaEventDestroy(c.ready[k]);
         if (c.done[k]) cudaEventDestroy(c.done[k]);
         cudaFree(c.stage[k]); cudaFree(c.gathered[k]);
@@ -1212,8 +1212,8 @@ static int result_alloc(bmb200_ctx* ctx, uint32_t n_cols, uint32_t n_groups, boo
     if (n_groups == 1) {
         const uint32_t n_even = (n_cols + 1u) & ~1u;                     // the 64-bit total sits 8-byte aligned behind the popcounts
         r->xstride = n_even + 2u;
-        if ((rc = dev_alloc(ctx, &r->popcnt_base, (size_t)r->xstride * 2))) { delete r; return rc; }
-        cudaMemsetAsync(r->popcnt_base, 0, (size_t)r->xstride * 2 * 4, ctx->stream);
+        if ((rc = dev_alloc(ctx, &r->popcnt_base, (size_t)r->xstride * CommState::kSlots))) { delete r; return rc; }
+        cudaMemsetAsync(r->popcnt_base, 0, (size_t)r->xstride * CommState::kSlots * 4, ctx->stream);
         r->popcnt = r->popcnt_base; r->total = reinterpret_cast<unsigned long long*>(r->popcnt_base + n_even); r->total_inline = true;
     }
     if ((!r->total_inline && ((rc = dev_alloc(ctx, &r->popcnt, n_cols)) || (rc = dev_alloc(ctx, &r->total, n_groups)))) ||
@@ -1285,10 +1285,10 @@ int bmb200_aggregate_batch(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_
     }
     r->has_blocks = store; r->compress = compress; r->gaps_ready = false;
     if (r->total_inline && ctx->comm.comm) {
-        r->xflip ^= 1u;
+        r->xflip = (r->xflip + 1u) % (uint32_t)CommState::kSlots;
         r->popcnt = r->popcnt_base + (size_t)r->xflip * r->xstride;
         r->total = reinterpret_cast<unsigned long long*>(r->popcnt + (r->xstride - 2u));
-        for (int k = 0; k < 2; ++k)          // an all-gather that still sends out of this buffer (two steps back) goes first
+        for (int k = 0; k < CommState::kSlots; ++k)          // an all-gather that still sends out of this buffer (kSlots steps back) goes first
             if (ctx->comm.pending[k] && ctx->comm.sendbuf[k] == r->popcnt) cudaStreamWaitEvent(ctx->stream, ctx->comm.done[k], 0);
     }
 
@@ -1337,6 +1337,12 @@ int bmb200_aggregate_batch(bmb200_ctx* ctx, const bmb200_set* set, const bmb200_
     cudaError_t ae = cudaSuccess; set_agg_attrs(ctx, &ae);
     if (ae != cudaSuccess) { ctx->last_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ae); if (!*inout) bmb200_result_free(r); return BMB200_ERR_CUDA; }
     uint32_t grid = (uint32_t)(ctx->sm_count * ctx->agg_ctas_per_sm);
+    if (ctx->comm.comm && ctx->comm.nranks > 1 && ctx->sm_count > 8) {
+        // sharded runs: the all-gather of the previous step has to find SMs while this (persistent, SM-filling) kernel runs, or it
+        // waits for the gap between two aggregation kernels and stretches it; BMB200_AGG_RESERVE_SMS leaves that many SMs free
+        static const int reserve = []() { const char* e = getenv("BMB200_AGG_RESERVE_SMS"); return e ? atoi(e) : 0; }();
+        if (reserve > 0 && reserve < ctx->sm_count) grid = (uint32_t)((ctx->sm_count - reserve) * ctx->agg_ctas_per_sm);
+    }
     if (grid > n_cols) grid = n_cols;
     if (a->op != BMB200_OP_SHIFT_R_AND) p.dyn_bytes = (uint32_t)ctx->agg_dyn[a->op];
     switch (a->op) {
@@ -1829,7 +1835,7 @@ int bmb200_comm_init(bmb200_ctx* ctx, int nranks, int rank, const void* id)
     if (nrc != 0) { ctx->last_err = std::string("ncclCommInitRank: ") + api.GetErrorString(nrc); c.comm = nullptr; return BMB200_ERR_CUDA; }
     c.nranks = nranks; c.rank = rank;
     cudaError_t e = cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking);
-    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+    for (int k = 0; k < CommState::kSlots && e == cudaSuccess; ++k) {
         e = cudaEventCreateWithFlags(&c.ready[k], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c.done[k], cudaEventDisableTiming);
     }
@@ -1863,9 +1869,9 @@ int bmb200_exchange_popcounts(bmb200_result* r, uint32_t cols_per_rank)
     const size_t n = cols_per_rank ? cols_per_rank : r->n_cols, words = n + 2;
     if (n > c.cap_cols) {
         CU(cudaStreamSynchronize(c.side));
-        for (int k = 0; k < 2; ++k) { cudaFree(c.stage[k]); cudaFree(c.gathered[k]); c.stage[k] = c.gathered[k] = nullptr; c.pending[k] = false; }
+        for (int k = 0; k < CommState::kSlots; ++k) { cudaFree(c.stage[k]); cudaFree(c.gathered[k]); c.stage[k] = c.gathered[k] = nullptr; c.pending[k] = false; }
         c.cap_cols = 0;
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < CommState::kSlots; ++k) {
             CU(cudaMalloc((void**)&c.stage[k], words * 4));
             CU(cudaMalloc((void**)&c.gathered[k], words * 4 * (size_t)c.nranks));
         }
@@ -1885,8 +1891,8 @@ int bmb200_exchange_popcounts(bmb200_result* r, uint32_t cols_per_rank)
         c.cols[xp.slot] = (uint32_t)n; c.seq++;
         return BMB200_OK;
     }
-    const int k = (int)(c.seq & 1u);
-    // slot k was last used by the exchange two steps back: nothing below may overtake that all-gather
+    const int k = (int)(c.seq % (uint64_t)CommState::kSlots);
+    // slot k was last used by the exchange kSlots steps back: nothing below may overtake that all-gather
     if (c.pending[k]) CU(cudaStreamWaitEvent(ctx->stream, c.done[k], 0));
     static const bool no_direct = getenv("BMB200_EXCHANGE_STAGED") != nullptr;
     const uint32_t* send = c.stage[k];
@@ -1924,7 +1930,7 @@ int bmb200_exchange_fence(bmb200_ctx* ctx)
         xchg_wait_kernel<<<1, 64, 0, ctx->stream>>>(c.xbuf, (uint32_t)c.nranks, (uint32_t)c.xwords, (uint32_t)(c.xseq & 1u), (uint32_t)c.xseq, c.d_err, 30ull * 1000000000ull);
         return after_launch(ctx);
     }
-    for (int k = 0; k < 2; ++k) if (c.pending[k]) CU(cudaStreamWaitEvent(ctx->stream, c.done[k], 0));
+    for (int k = 0; k < CommState::kSlots; ++k) if (c.pending[k]) CU(cudaStreamWaitEvent(ctx->stream, c.done[k], 0));
     return BMB200_OK;
 }
 
@@ -1933,7 +1939,7 @@ int bmb200_exchange_fetch(bmb200_ctx* ctx, uint64_t* global_total, uint64_t* ran
     if (!ctx || !ctx->comm.comm || !ctx->comm.seq) return BMB200_ERR_BADARG;
     CommState& c = ctx->comm;
     CU(cudaSetDevice(ctx->device));
-    int k = (int)((c.seq - 1) & 1u);
+    int k = (int)((c.seq - 1) % (uint64_t)CommState::kSlots);
     const uint32_t* rows = nullptr;
     size_t words = 0, n = 0;
     if (c.direct) {

@@ -51,18 +51,21 @@ constexpr int kNcclUint8 = 1, kNcclUint32 = 3, kNcclUint64 = 5, kNcclSum = 0;
 
 inline NcclApi& nccl_api() { static NcclApi api; return api; }
 
-// per-context communicator + the double-buffered exchange state
+// per-context communicator + the exchange ring
 struct CommState {
     NcclApi::Comm comm = nullptr;
     int nranks = 0, rank = -1;
     cudaStream_t side = nullptr;             // the exchange runs here, so that step i's all-gather overlaps step i+1's kernel
-    cudaEvent_t ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
-    uint32_t* stage[2] = {nullptr, nullptr}; // [cap_cols + 2] u32: this rank's per-column popcounts, then its cardinality (u64)
-    uint32_t* gathered[2] = {nullptr, nullptr};   // [nranks][cap_cols + 2]
+    static constexpr int kSlots = 3;         // all-gathers in flight: an all-gather only finds SMs in the gap between two aggregation
+                                             // kernels, so the kernel of step i must not wait for the all-gather of step i-2 (it runs in
+                                             // the gap right before it) -- with three slots it waits for step i-3's, done one gap earlier
+    cudaEvent_t ready[kSlots] = {}, done[kSlots] = {};
+    uint32_t* stage[kSlots] = {}; // [cap_cols + 2] u32: this rank's per-column popcounts, then its cardinality (u64)
+    uint32_t* gathered[kSlots] = {};   // [nranks][cap_cols + 2]
     size_t cap_cols = 0;                     // columns the buffers were sized for
-    uint32_t cols[2] = {0, 0};               // columns of the exchange in flight in each slot
+    uint32_t cols[kSlots] = {};               // columns of the exchange in flight in each slot
     uint64_t seq = 0;                        // exchanges issued
-    bool pending[2] = {false, false};
+    bool pending[kSlots] = {};
     // direct exchange over peer memory (xchg_kernel.cuh): the default when every rank could map every other rank's buffer
     bool direct = false;
     uint32_t* xbuf = nullptr;                // [2][nranks][xwords] rows + [2][nranks] flags; cudaMalloc, exported through CUDA IPC
@@ -71,7 +74,7 @@ struct CommState {
     size_t xwords = 0;
     uint32_t* d_err = nullptr;               // set by a wait that timed out (a peer died): the next fetch reports BMB200_ERR_CUDA
     uint64_t xseq = 0;                       // exchanges pushed into the current xbuf
-    const uint32_t* sendbuf[2] = {nullptr, nullptr};   // what the all-gather of each slot reads (a staging buffer or the result's own popcount buffer)
+    const uint32_t* sendbuf[kSlots] = {};   // what the all-gather of each slot reads (a staging buffer or the result's own popcount buffer)
 };
 
 }  // namespace bmb200

@@ -353,7 +353,7 @@ int bmb200_comm_init(bmb200_ctx* ctx, int nranks, int rank, const void* id);
 int bmb200_comm_info(const bmb200_ctx* ctx, int* nranks, int* rank);
 int bmb200_comm_destroy(bmb200_ctx* ctx);
 /* exchange of the local result `res` (single group) with all ranks; asynchronous, ordered after the work already queued on the
- * context stream; double-buffered, so a rank may be one exchange ahead of its peers.  Collective: every rank issues the same
+ * context stream; buffered three deep (the aggregation of step i never waits for the exchange of step i-1 or i-2).  Collective: every rank issues the same
  * sequence of exchanges.  Two transports (bmb200_exchange_mode):
  *   1 = one ncclAllGather of the rows on the context's SIDE stream (the default: the faster of the two where it was measured);
  *   2 = peer memory (BMB200_EXCHANGE_DIRECT=1): every rank's exchange buffer is mapped by every other rank through CUDA IPC and
