@@ -1,4 +1,5 @@
 #!/bin/bash
+# two ranks of oracle/_ref/test_sharded (bm::b200::sharded_aggregator vs bm::aggregator), one per GPU, communicator id through a file
 mkdir -p gpurun_out
 rm -f /tmp/ncclid.bin
 NCCL_DEBUG=WARN oracle/_ref/test_sharded 0 2 /tmp/ncclid.bin > gpurun_out/sharded_r0.log 2>&1 &
