@@ -40,6 +40,7 @@ SYMBOLS = [
     "bmb200_exchange_popcounts", "bmb200_exchange_fence", "bmb200_exchange_fetch", "bmb200_ctx_trim", "bmb200_binop",
     "bmb200_set_upload_slabs", "bmb200_host_slabs_prefetch", "bmb200_host_slab_alloc", "bmb200_host_slab_free",
     "bmb200_result_fetch_view_async", "bmb200_result_fetch_wait", "bmb200_exchange_mode",
+    "bmb200_result_fetch_column",
 ]
 OP_SUB = 5
 COMM_ID_BYTES = 128

@@ -323,6 +323,113 @@ public:
     }
     void reset() { grp_[0].clear(); grp_[1].clear(); }
 
+    /// aggregator::set_range_hint / reset_range_hint, src/bmaggregator.h:961-994: narrows find_first_and_sub to the blocks of
+    /// [from, to]; a range inside ONE block additionally masks that block (the reference ANDs a range GAP block into it).
+    /// Returns true for such a one-block range, like the reference.  (The combine_* calls of this binding ignore the hint.)
+    bool set_range_hint(size_type from, size_type to)
+    {
+        range_set_ = true; range_from_ = from; range_to_ = to;
+        return (from >> bm::set_block_shift) == (to >> bm::set_block_shift);
+    }
+    void reset_range_hint() { range_set_ = false; }
+
+    /// aggregator::find_first_and_sub, src/bmaggregator.h:1078-1084, 1457-1549: index of the first bit of AND(group 0) - OR(group 1).
+    /// The block columns the reference would visit (its per-top-block limits, :1513-1531, hint included) are aggregated in one
+    /// launch, the first non-empty one is located from the per-column popcounts and only that column's block comes back.
+    /// One deliberate difference: for a block where every AND source is FULL and there is no SUB group the reference returns the
+    /// digest ~0 without writing its temp block (:1752-1759) and then reports the first bit of whatever that block held before;
+    /// this binding reports the block's true first bit.
+    bool find_first_and_sub(size_type& idx) { return find_first_and_sub(idx, grp_[0].data(), grp_[0].size(), grp_[1].data(), grp_[1].size()); }
+    bool find_first_and_sub(size_type& idx, const bvector_type_const_ptr* src_and, size_t n_and,
+                            const bvector_type_const_ptr* src_sub, size_t n_sub)
+    {
+        // -- which block columns does the reference look at? --
+        unsigned top_blocks = std::max(max_top_blocks(src_and, n_and), max_top_blocks(src_sub, n_sub));
+        const uint64_t nb_f = range_set_ ? (uint64_t)(range_from_ >> bm::set_block_shift) : 0u,
+                       nb_t = range_set_ ? (uint64_t)(range_to_ >> bm::set_block_shift) : 0u;
+        const bool one_block = range_set_ && nb_f == nb_t;
+        std::vector<std::pair<uint32_t, uint32_t>> spans;          // [first, last) block columns, ascending
+        if (one_block) spans.emplace_back((uint32_t)nb_f, (uint32_t)nb_f + 1u);
+        else
+        {
+            unsigned top_from = 0;
+            const unsigned top_to = (unsigned)(nb_t >> bm::set_array_shift);
+            if (range_set_) { top_from = (unsigned)(nb_f >> bm::set_array_shift); if (top_to < top_blocks) top_blocks = top_to + 1u; }
+            for (unsigned i = top_from; i < top_blocks; ++i)
+            {
+                unsigned j = 0, jmax = bm::set_sub_array_size;
+                if (range_set_)
+                {
+                    if (i == top_from) j = (unsigned)(nb_f & bm::set_array_mask);
+                    if (i == top_to) jmax = 1u + (unsigned)(nb_t & bm::set_array_mask);
+                }
+                else
+                {
+                    jmax = effective_sub_size(i, src_and, n_and, true);
+                    if (!jmax) continue;
+                    if (n_sub)
+                    {   // (the reference narrows the scan to the SUB group's extent here and questions it itself, :1524-1530)
+                        unsigned j2 = effective_sub_size(i, src_sub, n_sub, false);
+                        if (j2 < jmax) jmax = j2;
+                    }
+                }
+                if (j < jmax) spans.emplace_back((i << bm::set_array_shift) + j, (i << bm::set_array_shift) + jmax);
+            }
+        }
+        if (!n_and || spans.empty()) return false;
+        // -- one aggregation over the hull of those columns, bit-blocks kept (no re-compression: only one block is read) --
+        bool own = false;
+        bmb200_set* set = bind(src_and, n_and, src_sub, n_sub, own);
+        struct release { bmb200_set* s; ~release() { if (s) bmb200_set_free(s); } } guard{own ? set : nullptr};
+        uint32_t lo = spans.front().first, hi = spans.back().second;
+        const uint32_t have_lo = nb_off_, have_hi = nb_off_ + n_blocks_;
+        if (hi > have_hi) hi = have_hi;
+        if (lo < have_lo) lo = have_lo;
+        if (lo >= hi) return false;
+        bmb200_agg_args a{BMB200_OP_AND_SUB, BMB200_F_OPT_NONE, g0_.data(), (uint32_t)n_and, n_sub ? g1_.data() : nullptr, (uint32_t)n_sub,
+                          lo - nb_off_, hi - nb_off_};
+        bmb200_result* res = nullptr;
+        check(bmb200_aggregate(ctx_.get(), set, &a, &res), "bmb200_aggregate(find_first)");
+        struct drop { bmb200_result* r; ~drop() { if (r) bmb200_result_free(r); } } rguard{res};
+        std::vector<uint32_t> pop(hi - lo);
+        bmb200_result_meta m{}; m.popcnt = pop.data();
+        check(bmb200_result_fetch_meta(res, &m), "bmb200_result_fetch_meta");
+        for (const auto& sp : spans)
+            for (uint32_t nb = std::max(sp.first, lo); nb < std::min(sp.second, hi); ++nb)
+            {
+                if (!pop[nb - lo]) continue;
+                uint8_t kd = 0; std::vector<uint32_t> bits(BMB200_BLOCK_WORDS); std::vector<uint16_t> gaps(BMB200_GAP_MAX_WORDS);
+                check(bmb200_result_fetch_column(res, nb - lo, &kd, bits.data(), gaps.data()), "bmb200_result_fetch_column");
+                unsigned b0 = one_block ? (unsigned)(range_from_ & bm::set_block_mask) : 0u,
+                         b1 = one_block ? (unsigned)(range_to_ & bm::set_block_mask) : 65535u;
+                unsigned first = 65536u;
+                if (kd == BMB200_BLK_FULL) first = b0;
+                else if (kd == BMB200_BLK_BIT)
+                {
+                    for (unsigned w = b0 >> 5; w <= (b1 >> 5) && first == 65536u; ++w)
+                    {
+                        uint32_t x = bits[w];
+                        if (w == (b0 >> 5)) x &= ~0u << (b0 & 31u);
+                        if (w == (b1 >> 5) && (b1 & 31u) != 31u) x &= (1u << ((b1 & 31u) + 1u)) - 1u;
+                        if (x) first = (w << 5) + (unsigned)__builtin_ctz(x);
+                    }
+                }
+                else if (kd == BMB200_BLK_GAP)
+                {
+                    const unsigned len = gaps[0] >> 3; unsigned val = gaps[0] & 1u, start = 0;
+                    for (unsigned k = 1; k <= len && first == 65536u; ++k, val ^= 1u)
+                    {
+                        const unsigned end = gaps[k];
+                        if (val && end >= b0 && start <= b1) first = std::max(start, b0);
+                        start = end + 1u;
+                    }
+                }
+                if (first != 65536u) { idx = (size_type)((uint64_t)nb * 65536u + first); return true; }
+                if (one_block) return false;
+            }
+        return false;
+    }
+
     // ---- member forms ----
     void combine_or(bvector_type& target)  { combine_or(target, grp_[0].data(), grp_[0].size()); }
     void combine_and(bvector_type& target)
@@ -404,6 +511,30 @@ public:
     }
 
 private:
+    /// aggregator::max_top_blocks, src/bmaggregator.h:2256-2273
+    static unsigned max_top_blocks(const bvector_type_const_ptr* src, size_t n)
+    {
+        unsigned top = 1;
+        for (size_t k = 0; k < n; ++k) if (src[k]) top = std::max(top, (unsigned)src[k]->get_blocks_manager().top_block_size());
+        return top;
+    }
+    /// aggregator::find_effective_sub_block_size, src/bmaggregator.h:1556-1599 (approximate there too: 256 for more than 32 sources)
+    static unsigned effective_sub_size(unsigned i, const bvector_type_const_ptr* src, size_t n, bool top_null_as_zero)
+    {
+        if (n > 32) return bm::set_sub_array_size;
+        unsigned max_size = 1;
+        for (size_t k = 0; k < n; ++k)
+        {
+            const typename BV::blocks_manager_type& bman = src[k]->get_blocks_manager();
+            const bm::word_t* const* sub = bman.get_topblock(i);
+            if (!sub) { if (top_null_as_zero) return 0; continue; }
+            if ((bm::word_t*)sub == FULL_BLOCK_FAKE_ADDR) return bm::set_sub_array_size;
+            for (unsigned j = bm::set_sub_array_size - 1; j > max_size; --j) if (sub[j]) { max_size = j; break; }
+            if (max_size == bm::set_sub_array_size - 1) break;
+        }
+        return max_size + 1;
+    }
+
     /// sources -> (set, member indices): the attached resident set when every source lives in it, else a fresh upload
     bmb200_set* bind(const bvector_type_const_ptr* s0, size_t n0, const bvector_type_const_ptr* s1, size_t n1, bool& own)
     {
@@ -505,6 +636,8 @@ private:
     uint64_t bound_epoch_ = 0;
     size_t bound_n0_ = 0;
     uint64_t last_d2h_ = 0;
+    bool range_set_ = false;
+    size_type range_from_ = 0, range_to_ = 0;
     bmb200_result* res_ = nullptr;
     uint32_t n_blocks_ = 0, nb_off_ = 0;
     uint32_t spare_blocks_ = 0;

@@ -282,6 +282,10 @@ int bmb200_result_optimize(bmb200_result* res);
 /* total popcount over all columns and "any bit found" (combine_and_sub's return value) */
 int bmb200_result_total(bmb200_result* res, uint64_t* total, int* any);
 int bmb200_result_fetch_meta(bmb200_result* res, const bmb200_result_meta* out);
+/* ONE column of a result: *kind = BMB200_BLK_*; a BIT column fills bits[2048], a GAP column fills gaps[BMB200_GAP_MAX_WORDS]
+ * (header + run ends), NULL / FULL columns write nothing.  What aggregator::find_first_and_sub reads after it has located the
+ * first non-empty column from the popcounts (bm::bit_find_first on the temp block, src/bmaggregator.h:1538-1546). */
+int bmb200_result_fetch_column(bmb200_result* res, uint32_t col, uint8_t* kind, uint32_t* bits, uint16_t* gaps);
 /* sizes of the compacted result: BIT blocks and GAP u16 words (each GAP block padded to 8 words) */
 int bmb200_result_sizes(bmb200_result* res, uint64_t* n_bit_blocks, uint64_t* n_gap_words);
 /* compacted result in per-vector flat form: off[c] = index into bits (blocks) for BIT columns,

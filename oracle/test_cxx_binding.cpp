@@ -151,6 +151,39 @@ int main()
         ds.release();
         bmb200_ctx_trim(ctx.get());
     }
+    {   // find_first_and_sub + set_range_hint (src/bmaggregator.h:961-994, 1457-1549): same index / same "found" as the reference,
+        // without a hint, with a multi-block hint (block range only) and with a one-block hint (block masked by the range)
+        bm::aggregator<bvect> ref; bm::b200::aggregator<bvect> gpu(ctx);
+        bm::b200::device_set<bvect> ds(ctx); ds.assign(all.data(), all.size());
+        bvect lone_a, lone_b, lone_s;                        // sparse trees: hits far from bit 0, SUB group with a short extent
+        // (no block where EVERY AND source is FULL and the SUB group is empty: there the reference returns ~0 as digest without writing
+        //  its temp block, src/bmaggregator.h:1752-1759, and find_first_and_sub then reads the first bit of a stale block)
+        lone_a.set_range(5u * 65536u + 100u, 5u * 65536u + 4000u); lone_a.set_range(30u * 65536u + 10u, 30u * 65536u + 70000u);
+        lone_b.set_range(5u * 65536u + 300u, 31u * 65536u); lone_s.set_range(5u * 65536u, 5u * 65536u + 999u); lone_s.set_bit(2u * 65536u + 7u);
+        std::vector<std::vector<const bvect*>> ands = {{all[0], all[1]}, {all[0], all[1], all[2], all[3]}, {all[7]}, {all[20], all[21]}, {&lone_a, &lone_b}};
+        std::vector<std::vector<const bvect*>> subs = {{}, {all[4]}, {all[5], all[9], all[13]}, {&lone_s}, {all[0]}};
+        struct Hint { bool on; unsigned from, to; };
+        const Hint hints[] = {{false, 0, 0}, {true, 3u * 65536u + 17u, 9u * 65536u + 5u}, {true, 65536u * 5u + 500u, 65536u * 5u + 3500u},
+                              {true, 65536u * 30u + 60000u, 65536u * 33u}, {true, 70010u, 70020u}, {true, 65536u * 39u, n_bits - 1u}};
+        for (int resident = 0; resident < 2; ++resident) {
+            gpu.set_device_set(resident ? &ds : nullptr);
+            for (const Hint& h : hints)
+                for (size_t x = 0; x < ands.size(); ++x) for (size_t y = 0; y < subs.size(); ++y) {
+                    if (resident && (x == 4 || y == 3)) continue;          // the lone vectors are not members of ds: that is the upload road, covered above
+                    ref.reset_range_hint(); gpu.reset_range_hint();
+                    if (h.on) { bool r1 = ref.set_range_hint(h.from, h.to), r2 = gpu.set_range_hint(h.from, h.to); CHECK(r1 == r2, "set_range_hint return"); }
+                    bvect::size_type i1 = 0, i2 = 0;
+                    bool f1 = ref.find_first_and_sub(i1, ands[x].data(), ands[x].size(), subs[y].empty() ? 0 : subs[y].data(), subs[y].size());
+                    bool f2 = gpu.find_first_and_sub(i2, ands[x].data(), ands[x].size(), subs[y].empty() ? 0 : subs[y].data(), subs[y].size());
+                    CHECK(f1 == f2 && (!f1 || i1 == i2), "find_first_and_sub and=%zu sub=%zu hint=%d[%u,%u] resident=%d: ref %d@%u vs %d@%u",
+                          x, y, (int)h.on, h.from, h.to, resident, (int)f1, (unsigned)i1, (int)f2, (unsigned)i2);
+                }
+        }
+        ref.reset_range_hint(); gpu.reset_range_hint(); gpu.set_device_set(nullptr);
+        for (int k = 0; k < 2; ++k) { ref.add(all[k]); gpu.add(all[k]); } ref.add(all[4], 1); gpu.add(all[4], 1);
+        bvect::size_type i1 = 0, i2 = 0; bool f1 = ref.find_first_and_sub(i1), f2 = gpu.find_first_and_sub(i2);
+        CHECK(f1 == f2 && i1 == i2, "member find_first_and_sub");
+    }
     {   // member forms with add()/reset(), as samples/bvsample16/sample16.cpp uses them
         bm::aggregator<bvect> ref; bm::b200::aggregator<bvect> gpu(ctx);
         for (int k = 0; k < 3; ++k) { ref.add(all[k]); gpu.add(all[k]); }
