@@ -65,6 +65,52 @@ class Aggregator:
     def reset(self):
         self._groups = [[], []]
 
+    def set_range_hint(self, frm: int, to: int) -> bool:
+        """aggregator::set_range_hint (src/bmaggregator.h:974-994): narrows find_first_and_sub to the blocks of [frm, to]; a range
+        inside one block also masks that block.  Returns True for such a one-block range."""
+        self._range = (int(frm), int(to))
+        return (frm >> 16) == (to >> 16)
+
+    def reset_range_hint(self):
+        self._range = None
+
+    def find_first_and_sub(self, bv_src_and: list[BVector] | None = None, bv_src_sub: list[BVector] | None = None):
+        """aggregator::find_first_and_sub (src/bmaggregator.h:1457-1549) -> (found, index of the first bit of AND(group 0) - OR(group 1)).
+        One launch over the hinted block range, the first non-empty column is located from the popcounts, one block comes back."""
+        a = self._groups[0] if bv_src_and is None else bv_src_and
+        s = self._groups[1] if bv_src_sub is None else bv_src_sub
+        if not a:
+            return False, 0
+        vecs = list(a) + list(s)
+        n_blocks = max(v.n_blocks for v in vecs)
+        rng = getattr(self, "_range", None)
+        lo, hi = (0, n_blocks) if rng is None else (rng[0] >> 16, min(n_blocks, (rng[1] >> 16) + 1))
+        if lo >= hi:
+            return False, 0
+        one_block = rng is not None and (rng[0] >> 16) == (rng[1] >> 16)
+        b0, b1 = ((rng[0] & 65535, rng[1] & 65535) if one_block else (0, 65535))
+        dset = capi.DeviceSet.upload_vectors(self.ctx, vecs, n_blocks)
+        try:
+            res = capi.aggregate(self.ctx, dset, OP_AND_SUB, np.arange(len(a)), np.arange(len(a), len(vecs)), F_OPT_NONE, lo, hi)
+            try:
+                _, pop, _, _ = res.meta()
+                for c in np.flatnonzero(pop):
+                    kind, bits, gaps = res.fetch_column(int(c))
+                    if kind == capi.BLK_FULL:
+                        return True, (lo + int(c)) * 65536 + b0
+                    if kind == capi.BLK_BIT:
+                        pos = np.flatnonzero(np.unpackbits(bits.view(np.uint8), bitorder="little"))
+                        pos = pos[(pos >= b0) & (pos <= b1)]
+                        if pos.size:
+                            return True, (lo + int(c)) * 65536 + int(pos[0])
+                    if one_block:
+                        break
+                return False, 0
+            finally:
+                res.free()
+        finally:
+            dset.free()
+
     # --- C-style entry points (src/bmaggregator.h:503-540) ---
     def combine_or(self, bv_src: list[BVector] | None = None) -> BVector:
         src = self._groups[0] if bv_src is None else bv_src

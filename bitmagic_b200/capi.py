@@ -454,6 +454,14 @@ class DeviceResult:
                                                  ptr(gaps) if ng.value else C.c_void_p(0)), "result_fetch")
         return kind, off, bits, gaps
 
+    def fetch_column(self, col: int):
+        """bmb200_result_fetch_column -> (kind, bits[2048] | None, gap words | None) of ONE result column."""
+        kind = C.c_uint8(0)
+        bits = np.empty(BLOCK_WORDS, np.uint32); gaps = np.empty(1280, np.uint16)
+        self.ctx.check(lib().bmb200_result_fetch_column(self._h, int(col), C.byref(kind), ptr(bits), ptr(gaps)), "result_fetch_column")
+        k = kind.value
+        return k, (bits if k == BLK_BIT else None), (gaps[:(int(gaps[0]) >> 3) + 1] if k == BLK_GAP else None)
+
     def group_totals(self, n_groups: int) -> np.ndarray:
         t = np.zeros(n_groups, np.uint64)
         self.ctx.check(lib().bmb200_result_group_totals(self._h, ptr(t), int(n_groups)), "result_group_totals")

@@ -765,6 +765,36 @@ def test_sharded_rs_device_callables_two_shards_one_gpu():
         ctx.close()
 
 
+def test_find_first_and_sub_with_range_hints(ctx):
+    """Aggregator.find_first_and_sub + set_range_hint (aggregator::find_first_and_sub, src/bmaggregator.h:1457-1549) against the first
+    position of the oracle's AND-SUB result restricted the way the reference restricts it: block range for a multi-block hint,
+    block range + in-block mask for a one-block hint."""
+    rng = np.random.default_rng(77)
+    vecs = gen.mixed_vectors(rng, 9, 12, p_null=0.2)
+    ps = bm.PackedSet.pack(vecs)
+    agg = bm.Aggregator(ctx)
+    for g0, g1 in (([0, 1], [2, 3]), ([4], []), ([5, 6, 7], [8]), ([0, 1, 2, 3, 4], [5])):
+        okind, _, _, _, want_blocks, _ = orclib.oracle_aggregate(ps, bm.OP_AND_SUB, g0, g1, 0)
+        want_blocks = want_blocks.copy(); want_blocks[okind == bm.BLK_FULL] = 0xFFFFFFFF; want_blocks[okind == bm.BLK_NULL] = 0
+        allpos = np.flatnonzero(np.unpackbits(np.ascontiguousarray(want_blocks).view(np.uint8), bitorder="little"))
+        for hint in (None, (3 * 65536 + 5, 8 * 65536 + 100), (2 * 65536 + 1000, 2 * 65536 + 40000), (11 * 65536, 12 * 65536 - 1), (65536 * 5 + 7, 65536 * 5 + 7)):
+            agg.reset_range_hint()
+            pos = allpos
+            if hint is not None:
+                one = agg.set_range_hint(*hint)
+                assert one == ((hint[0] >> 16) == (hint[1] >> 16))
+                if one:
+                    pos = allpos[(allpos >= hint[0]) & (allpos <= hint[1])]
+                else:
+                    pos = allpos[(allpos >= (hint[0] >> 16) * 65536) & (allpos < ((hint[1] >> 16) + 1) * 65536)]
+            found, idx = agg.find_first_and_sub([vecs[k] for k in g0], [vecs[k] for k in g1])
+            assert found == bool(pos.size), (g0, g1, hint)
+            if found:
+                assert idx == int(pos[0]), (g0, g1, hint, idx, int(pos[0]))
+    agg.reset_range_hint()
+    assert agg.find_first_and_sub([], [vecs[0]]) == (False, 0)
+
+
 def test_c1_config_bit_and_count(ctx):
     """BASELINE configs[0]: two bvectors of 2^20 bits, 10 % random fill: bit_and + count() and count_and through the C ABI == the oracle
     (and the reference when its library travelled); bytes touched = 3 * 16 * 8192."""
