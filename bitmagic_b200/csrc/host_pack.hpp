@@ -195,7 +195,7 @@ struct PackPipeline {
     std::vector<std::atomic<uint32_t>> remaining;      // columns left per chunk
     std::atomic<uint32_t> next_col{0};
     std::mutex mu;
-    std::condition_variable cv_free, cv_done;
+    std::condition_variable cv_free[kStageSlots], cv_done;   // packers wait per SLOT: a freed slot wakes the packers of its next chunk, not the whole team
     uint32_t released = 0;                             // guarded by mu
     std::vector<std::thread> th;
 
@@ -221,7 +221,7 @@ struct PackPipeline {
             const uint32_t c = chunk_of_col[nb];
             if (c >= seen_released + kStageSlots) {                       // the slot of chunk c is still owned by chunk c - kStageSlots
                 std::unique_lock<std::mutex> lk(mu);
-                cv_free.wait(lk, [&]() { return c < released + kStageSlots; });
+                cv_free[c % kStageSlots].wait(lk, [&]() { return c < released + kStageSlots; });
                 seen_released = released;
             }
             const PackChunk& ch = (*chunks)[c];
@@ -243,8 +243,11 @@ struct PackPipeline {
     }
     void release_through(uint32_t c)                                        // chunks [0, c) are free
     {
-        { std::lock_guard<std::mutex> lk(mu); released = c; }
-        cv_free.notify_all();
+        uint32_t before;
+        { std::lock_guard<std::mutex> lk(mu); before = released; released = c; }
+        // chunks [before + kStageSlots, c + kStageSlots) became admissible: wake the slots they live in (at most all of them)
+        const uint32_t span = c - before >= kStageSlots ? kStageSlots : c - before;
+        for (uint32_t k = 0; k < span; ++k) cv_free[(before + k) % kStageSlots].notify_all();
     }
     void join()
     {
