@@ -274,7 +274,8 @@ struct PackPipeline {
         uint32_t before;
         { std::lock_guard<std::mutex> lk(mu); before = released; released = c; }
         // chunks [before + kStageSlots, c + kStageSlots) became admissible: wake the slots they live in (at most all of them)
-        const uint32_t span = c - before >= kStageSlots ? kStageSlots : c - before;
+        static const bool herd = getenv("BMB200_PACK_WAKE_ALL") != nullptr;          // A/B switch: wake every slot's waiters on every release
+        const uint32_t span = (herd || c - before >= kStageSlots) ? kStageSlots : c - before;
         for (uint32_t k = 0; k < span; ++k) cv_free[(before + k) % kStageSlots].notify_all();
     }
     void join()
