@@ -467,9 +467,9 @@ def timed_resident(args, bm, torch, ctx, dset, op, g0, g1, flags, world, dist, d
     res = bm.aggregate(ctx, dset, op, g0, g1, flags)     # allocates the result buffers once
     ctx.sync()
 
-    # diagnostic switches (the N>1 line always runs the exchange): BENCH_SELF_EXCHANGE=1 runs the exchange machinery on ONE GPU with a
+    # diagnostic switch (the N>1 line always runs the exchange): BENCH_SELF_EXCHANGE=1 runs the exchange machinery on ONE GPU with a
     # 1-rank communicator, to separate its stream-level cost from what the peers add
-    exchange = (world > 1 and not os.environ.get("BENCH_NO_EXCHANGE")) or bool(os.environ.get("BENCH_SELF_EXCHANGE"))
+    exchange = world > 1 or bool(os.environ.get("BENCH_SELF_EXCHANGE"))
 
     def step():
         bm.aggregate(ctx, dset, op, g0, g1, flags, result=res)
